@@ -1,0 +1,207 @@
+/*
+ * tskit_b200.h -- C ABI of the B200 general-statistics engine.
+ *
+ * Drop-in boundary for tskit's general-statistics hot path.  Every entry point
+ * keeps the argument order, types and error codes of the reference function it
+ * replaces (cited per function; paths are relative to the tskit repository),
+ * except that the `const tsk_treeseq_t *self` argument becomes an opaque
+ * handle owning the device copy of the tables ("plan").  Plain pointers and
+ * sizes only; all pointers are HOST pointers borrowed for the duration of the
+ * call; `result` is caller-allocated and zeroed/overwritten by the callee
+ * exactly as the reference does (c/tskit/trees.c:1417, 1703, 8979).
+ *
+ * Types mirror c/tskit/core.h:99-123: tsk_id_t=int32_t, tsk_size_t=uint64_t,
+ * tsk_flags_t=uint32_t, TSK_NULL=-1.
+ */
+#ifndef TSKIT_B200_H
+#define TSKIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- option bits: identical values to c/tskit/trees.h:47-56 ---- */
+#define TSKB_STAT_SITE (1u << 0)
+#define TSKB_STAT_BRANCH (1u << 1)
+#define TSKB_STAT_NODE (1u << 2)
+#define TSKB_STAT_POLARISED (1u << 10)
+#define TSKB_STAT_SPAN_NORMALISE (1u << 11)
+#define TSKB_STAT_ALLOW_TIME_UNCALIBRATED (1u << 12)
+#define TSKB_STAT_PAIR_NORMALISE (1u << 13)
+#define TSKB_STAT_NONCENTRED (1u << 14)
+/* c/tskit/genotypes.h:35 */
+#define TSKB_ISOLATED_NOT_MISSING (1u << 1)
+
+/* ---- error codes: identical values to c/tskit/core.h:259-698 ---- */
+#define TSKB_ERR_NO_MEMORY (-2)
+#define TSKB_ERR_BAD_PARAM_VALUE (-4)
+#define TSKB_ERR_NODE_OUT_OF_BOUNDS (-202)
+#define TSKB_ERR_DUPLICATE_SAMPLE (-600)
+#define TSKB_ERR_BAD_SAMPLES (-601)
+#define TSKB_ERR_BAD_NUM_WINDOWS (-900)
+#define TSKB_ERR_BAD_WINDOWS (-901)
+#define TSKB_ERR_MULTIPLE_STAT_MODES (-902)
+#define TSKB_ERR_BAD_STATE_DIMS (-903)
+#define TSKB_ERR_BAD_RESULT_DIMS (-904)
+#define TSKB_ERR_INSUFFICIENT_SAMPLE_SETS (-905)
+#define TSKB_ERR_INSUFFICIENT_INDEX_TUPLES (-906)
+#define TSKB_ERR_BAD_SAMPLE_SET_INDEX (-907)
+#define TSKB_ERR_EMPTY_SAMPLE_SET (-908)
+#define TSKB_ERR_UNSUPPORTED_STAT_MODE (-909)
+#define TSKB_ERR_TIME_UNCALIBRATED (-910)
+#define TSKB_ERR_STAT_POLARISED_UNSUPPORTED (-911)
+/* engine-specific codes, outside tskit's range */
+#define TSKB_ERR_CUDA (-20001)           /* a CUDA runtime call failed */
+#define TSKB_ERR_BAD_INDEX_ORDER (-20002) /* edge indexes not in canonical order */
+#define TSKB_ERR_UNSUPPORTED (-20003)     /* valid tskit call the engine does not accelerate */
+#define TSKB_ERR_NO_DEVICE (-20004)       /* no CUDA device: there is NO CPU fallback */
+
+typedef struct tskb_treeseq tskb_treeseq_t;
+
+/* The columns the path reads; same SoA columns as tsk_table_collection_t
+ * (c/tskit/tables.h:309-601) and the derived arrays tsk_treeseq_init builds
+ * (c/tskit/trees.c:455-545).  edge_*_order are the reference's edge indexes
+ * (c/tskit/tables.c:11392-11459), consumed as given. */
+typedef struct {
+    double sequence_length;
+    int32_t time_uncalibrated; /* tsk_treeseq_t.time_uncalibrated, trees.c:538 */
+    uint64_t num_nodes;
+    const uint32_t *node_flags;
+    const double *node_time;
+    uint64_t num_edges;
+    const double *edge_left;
+    const double *edge_right;
+    const int32_t *edge_parent;
+    const int32_t *edge_child;
+    const int32_t *edge_insertion_order;
+    const int32_t *edge_removal_order;
+    uint64_t num_sites;
+    const double *site_position;
+    const char *site_ancestral_state;
+    const uint64_t *site_ancestral_state_offset;
+    uint64_t num_mutations;
+    const int32_t *mutation_site;
+    const int32_t *mutation_node;
+    const int32_t *mutation_parent;
+    const char *mutation_derived_state;
+    const uint64_t *mutation_derived_state_offset;
+} tskb_tables_t;
+
+/* Replaces tsk_treeseq_init (c/tskit/trees.c:455) for this path: stages the
+ * tables in HBM and builds the replay plan.  [range_left, range_right) clips
+ * the genome (multi-GPU window sharding); pass 0, sequence_length for all of it.
+ * device is the CUDA ordinal. */
+int tskb_treeseq_init(tskb_treeseq_t **self, const tskb_tables_t *tables, int device,
+    double range_left, double range_right, uint32_t options);
+int tskb_treeseq_free(tskb_treeseq_t *self);
+
+/* tsk_strerror (c/tskit/core.c) for the codes above */
+const char *tskb_strerror(int err);
+/* detail of the last TSKB_ERR_CUDA on this thread */
+const char *tskb_last_cuda_error(void);
+
+/* one_way_sample_stat_method, c/tskit/trees.h:1098-1112 */
+int tskb_treeseq_diversity(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result);
+int tskb_treeseq_segregating_sites(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result);
+int tskb_treeseq_Y1(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result);
+
+/* general_sample_stat_method, c/tskit/trees.h:1118-1121, 1189-1239 */
+int tskb_treeseq_divergence(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets,
+    uint64_t num_index_tuples, const int32_t *index_tuples, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result);
+int tskb_treeseq_Y2(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets,
+    uint64_t num_index_tuples, const int32_t *index_tuples, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result);
+int tskb_treeseq_f2(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets,
+    uint64_t num_index_tuples, const int32_t *index_tuples, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result);
+int tskb_treeseq_genetic_relatedness(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets,
+    uint64_t num_index_tuples, const int32_t *index_tuples, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result);
+int tskb_treeseq_Y3(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets,
+    uint64_t num_index_tuples, const int32_t *index_tuples, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result);
+int tskb_treeseq_f3(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets,
+    uint64_t num_index_tuples, const int32_t *index_tuples, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result);
+int tskb_treeseq_f4(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets,
+    uint64_t num_index_tuples, const int32_t *index_tuples, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result);
+
+/* tsk_treeseq_general_stat (c/tskit/trees.h:1035-1037) for the summary
+ * functions a device can evaluate: the callback `f` is replaced by a table.
+ * For state_dim == 1, `f_table` is [(max_count + 1) x result_dim] with row c =
+ * f(c) for the integer sample count c (weights must be 0/1, as
+ * tsk_treeseq_sample_count_stat builds them, trees.c:2174-2220). */
+int tskb_treeseq_sample_count_stat_tabulated(const tskb_treeseq_t *self,
+    uint64_t num_sample_sets, const uint64_t *sample_set_sizes,
+    const int32_t *sample_sets, uint64_t result_dim, uint64_t table_rows,
+    const double *f_table, uint64_t num_windows, const double *windows,
+    uint32_t options, double *result);
+
+/* tsk_treeseq_divergence_matrix, c/tskit/trees.h:1241 (trees.c:8901-9001) */
+int tskb_treeseq_divergence_matrix(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result);
+
+/* tsk_variant_decode over all sites (c/tskit/genotypes.c:473-594): int8
+ * genotype matrix [num_sites x num_samples] for the given sample nodes
+ * (samples == NULL: all samples, in tsk_treeseq_get_samples order). */
+int tskb_treeseq_genotype_matrix(const tskb_treeseq_t *self, const int32_t *samples,
+    uint64_t num_samples, uint32_t options, int8_t *genotypes);
+
+/* Integer parity outputs: parent array and per-node tracked-sample counts of
+ * the tree covering each position (tsk_tree_seek + tsk_tree_t.parent /
+ * tsk_tree_get_num_tracked_samples, trees.c:7092, 6679-6760).  out_* are
+ * [num_positions x num_nodes] int32; tracked == NULL counts all samples. */
+int tskb_treeseq_trees_at(const tskb_treeseq_t *self, uint64_t num_positions,
+    const double *positions, const int32_t *tracked, uint64_t num_tracked,
+    int32_t *out_parent, int32_t *out_count);
+
+/* ---- measurement / introspection (no reference counterpart) ---- */
+typedef struct {
+    uint64_t num_events;       /* edge diffs replayed per sweep */
+    uint64_t num_visits;       /* sum over edge diffs of ancestors visited (d-bar * events) */
+    uint64_t num_levels;       /* dependency levels of the count propagation */
+    double stage_ms;           /* wall time of tskb_treeseq_init */
+    double last_call_ms;       /* device time of the last statistic call (CUDA events) */
+    double last_kernel_ms[8];  /* per phase: 0 weights, 1 propagate, 2 summary, 3 scan, 4 windows, 5 d2h */
+    uint64_t last_launches;    /* kernels launched by the last statistic call */
+    uint64_t device_bytes;     /* HBM held by the plan */
+} tskb_stats_t;
+int tskb_treeseq_get_stats(const tskb_treeseq_t *self, tskb_stats_t *out);
+
+/* Same statistic entry points with inputs/outputs already resident in HBM
+ * (device pointers), used by bench.py to time the kernels without PCIe. */
+int tskb_treeseq_stat_device(const tskb_treeseq_t *self, int stat_id,
+    uint64_t num_sample_sets, const uint64_t *sample_set_sizes,
+    const int32_t *d_sample_sets, uint64_t num_index_tuples, const int32_t *index_tuples,
+    uint64_t num_windows, const double *windows, uint32_t options, double *d_result);
+
+/* Debug/test access to plan arrays (copied to host). name in: "ev_pos",
+ * "ev_child", "ev_sign", "ev_src", "voff", "em_node", "em_perm", "em_bl",
+ * "nm_src", "nm_flag", "nm_key", "level", "rank_node", "level_begin",
+ * "mut_src".  Returns the element count, or <0 on error; copies at most
+ * max_bytes. */
+int64_t tskb_treeseq_debug_array(const tskb_treeseq_t *self, const char *name, void *out,
+    uint64_t max_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

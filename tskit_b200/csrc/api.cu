@@ -1,0 +1,343 @@
+// api.cu -- the extern "C" boundary (include/tskit_b200.h): argument validation with the
+// reference's error codes and precedence, then dispatch to the device engine.
+// There is deliberately no host implementation of any statistic in this library.
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "plan.cuh"
+
+using namespace tskb;
+
+struct tskb_treeseq {
+    Plan *plan;
+};
+
+namespace {
+
+template <typename Fn>
+int guarded(Fn &&fn) {
+    try {
+        return fn();
+    } catch (const CudaFail &f) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s: %s (%s:%d)", cudaGetErrorName(f.err), f.what, f.file, f.line);
+        last_error_string() = buf;
+        cudaGetLastError();
+        return f.err == cudaErrorMemoryAllocation ? TSKB_ERR_NO_MEMORY : TSKB_ERR_CUDA;
+    } catch (int code) {
+        return code;
+    } catch (const std::bad_alloc &) {
+        return TSKB_ERR_NO_MEMORY;
+    }
+}
+
+// tsk_treeseq_check_windows with TSK_REQUIRE_FULL_SPAN (trees.c:1244-1286)
+int check_windows(const Plan &P, uint64_t num_windows, const double *windows, bool full_span) {
+    if (num_windows < 1) return TSKB_ERR_BAD_NUM_WINDOWS;
+    if (full_span) {
+        if (windows[0] != 0) return TSKB_ERR_BAD_WINDOWS;
+        if (windows[num_windows] != P.L) return TSKB_ERR_BAD_WINDOWS;
+    } else {
+        if (windows[0] < 0) return TSKB_ERR_BAD_WINDOWS;
+        if (windows[num_windows] > P.L) return TSKB_ERR_BAD_WINDOWS;
+    }
+    for (uint64_t j = 0; j < num_windows; j++) {
+        if (windows[j] >= windows[j + 1]) return TSKB_ERR_BAD_WINDOWS;
+    }
+    return 0;
+}
+
+// tsk_treeseq_check_sample_sets (trees.c:2114-2149) followed by the duplicate
+// check of tsk_treeseq_sample_count_stat (trees.c:2195-2213)
+int check_sample_sets(const Plan &P, uint64_t K, const uint64_t *sizes, const int32_t *sets) {
+    if (K == 0) return TSKB_ERR_INSUFFICIENT_SAMPLE_SETS;
+    uint64_t j = 0;
+    for (uint64_t k = 0; k < K; k++) {
+        if (sizes[k] == 0) return TSKB_ERR_EMPTY_SAMPLE_SET;
+        for (uint64_t l = 0; l < sizes[k]; l++, j++) {
+            int32_t u = sets[j];
+            if (u < 0 || u >= (int32_t) P.N) return TSKB_ERR_NODE_OUT_OF_BOUNDS;
+            if (P.sample_index_map[u] == -1) return TSKB_ERR_BAD_SAMPLES;
+        }
+    }
+    std::vector<uint32_t> seen(P.num_samples, 0);
+    j = 0;
+    for (uint64_t k = 0; k < K; k++) {
+        for (uint64_t l = 0; l < sizes[k]; l++, j++) {
+            uint32_t &slot = seen[P.sample_index_map[sets[j]]];
+            if (slot == k + 1) return TSKB_ERR_DUPLICATE_SAMPLE;
+            slot = (uint32_t) k + 1;
+        }
+    }
+    return 0;
+}
+
+int tuple_width(int stat_id) {
+    switch (stat_id) {
+        case STAT_DIVERGENCE: case STAT_Y2: case STAT_F2: case STAT_RELATEDNESS:
+        case STAT_RELATEDNESS_NC:
+            return 2;
+        case STAT_Y3: case STAT_F3:
+            return 3;
+        case STAT_F4:
+            return 4;
+    }
+    return 0;
+}
+
+// Common path of every sample-count statistic; check precedence follows the
+// reference call chain: index tuples (check_sample_stat_inputs, trees.c:4667)
+// -> sample sets (trees.c:2191) -> duplicates (2207) -> mode (2053) -> dims
+// (2058-2065) -> windows (2070) -> time units (1383).
+int sample_count_stat(const tskb_treeseq_t *self, int stat_id, uint64_t K, const uint64_t *sizes,
+    const int32_t *sets, bool sets_on_device, const int32_t *host_sets_for_checks,
+    uint64_t num_tuples, const int32_t *tuples, uint64_t result_dim, uint64_t table_rows,
+    const double *f_table, uint64_t num_windows, const double *windows, uint32_t options,
+    double *result, bool result_on_device) {
+    if (self == nullptr || self->plan == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    const Plan &P = *self->plan;
+    return guarded([&]() -> int {
+        int tw = tuple_width(stat_id);
+        if (stat_id == STAT_RELATEDNESS && (options & TSKB_STAT_NONCENTRED)) {
+            stat_id = STAT_RELATEDNESS_NC;
+        }
+        uint64_t M = result_dim;
+        if (tw > 0) {
+            if (K < 1) return TSKB_ERR_INSUFFICIENT_SAMPLE_SETS;
+            if (num_tuples < 1) return TSKB_ERR_INSUFFICIENT_INDEX_TUPLES;
+            for (uint64_t j = 0; j < num_tuples * tw; j++) {
+                if (tuples[j] < 0 || tuples[j] >= (int32_t) K) return TSKB_ERR_BAD_SAMPLE_SET_INDEX;
+            }
+            M = num_tuples;
+        } else if (stat_id != STAT_TABULATED) {
+            M = K;
+        }
+        if (host_sets_for_checks != nullptr || K == 0) {
+            int ret = check_sample_sets(P, K, sizes, host_sets_for_checks);
+            if (ret != 0) return ret;
+        }
+        bool site = options & TSKB_STAT_SITE, branch = options & TSKB_STAT_BRANCH,
+             node = options & TSKB_STAT_NODE;
+        if (!(site || branch || node)) {
+            site = true;
+            options |= TSKB_STAT_SITE;
+        }
+        if (site + branch + node > 1) return TSKB_ERR_MULTIPLE_STAT_MODES;
+        if (K < 1) return TSKB_ERR_BAD_STATE_DIMS;
+        if (M < 1) return TSKB_ERR_BAD_RESULT_DIMS;
+        double default_windows[2] = { 0, P.L };
+        if (windows == nullptr) {
+            num_windows = 1;
+            windows = default_windows;
+        } else {
+            int ret = check_windows(P, num_windows, windows, true);
+            if (ret != 0) return ret;
+        }
+        if (node) return TSKB_ERR_UNSUPPORTED;  // W x N x M output: not on this path
+        if (branch && P.time_uncalibrated && !(options & TSKB_STAT_ALLOW_TIME_UNCALIBRATED)) {
+            return TSKB_ERR_TIME_UNCALIBRATED;
+        }
+        if (stat_id == STAT_TABULATED && K != 1) return TSKB_ERR_UNSUPPORTED;
+        StatSpec sp = {};
+        sp.stat_id = stat_id;
+        sp.K = (uint32_t) K;
+        sp.M = (uint32_t) M;
+        sp.tuple = (uint32_t) tw;
+        sp.sizes = sizes;
+        sp.sets = sets;
+        sp.sets_on_device = sets_on_device;
+        sp.indexes = tuples;
+        sp.W = (uint32_t) num_windows;
+        sp.windows = windows;
+        sp.options = options;
+        sp.result = result;
+        sp.result_on_device = result_on_device;
+        sp.f_table = f_table;
+        sp.table_rows = table_rows;
+        return run_sample_count_stat(&P, sp);
+    });
+}
+
+}  // namespace
+
+extern "C" {
+
+int tskb_treeseq_init(tskb_treeseq_t **self, const tskb_tables_t *tables, int device,
+    double range_left, double range_right, uint32_t options) {
+    if (self == nullptr || tables == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    *self = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        last_error_string() = "no CUDA device visible; this engine has no CPU fallback";
+        return TSKB_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) return TSKB_ERR_BAD_PARAM_VALUE;
+    if (!(range_left >= 0 && range_right <= tables->sequence_length && range_left < range_right)) {
+        return TSKB_ERR_BAD_PARAM_VALUE;
+    }
+    if (tables->num_edges > 0
+        && (tables->edge_insertion_order == nullptr || tables->edge_removal_order == nullptr)) {
+        return TSKB_ERR_BAD_PARAM_VALUE;
+    }
+    return guarded([&]() -> int {
+        Plan *p = build_plan(tables, device, range_left, range_right, options);
+        *self = new tskb_treeseq{ p };
+        return 0;
+    });
+}
+
+int tskb_treeseq_free(tskb_treeseq_t *self) {
+    if (self != nullptr) {
+        if (self->plan != nullptr) {
+            cudaSetDevice(self->plan->device);
+            delete self->plan;
+        }
+        delete self;
+    }
+    return 0;
+}
+
+const char *tskb_last_cuda_error(void) { return last_error_string().c_str(); }
+
+const char *tskb_strerror(int err) {
+    // messages of tsk_strerror (c/tskit/core.c) for the codes this path can return
+    switch (err) {
+        case 0: return "Normal exit condition. This is not an error!";
+        case TSKB_ERR_NO_MEMORY: return "Out of memory. (TSK_ERR_NO_MEMORY)";
+        case TSKB_ERR_BAD_PARAM_VALUE: return "Bad parameter value provided. (TSK_ERR_BAD_PARAM_VALUE)";
+        case TSKB_ERR_NODE_OUT_OF_BOUNDS: return "Node out of bounds. (TSK_ERR_NODE_OUT_OF_BOUNDS)";
+        case TSKB_ERR_DUPLICATE_SAMPLE: return "Duplicate sample value. (TSK_ERR_DUPLICATE_SAMPLE)";
+        case TSKB_ERR_BAD_SAMPLES: return "The nodes provided are not samples. (TSK_ERR_BAD_SAMPLES)";
+        case TSKB_ERR_BAD_NUM_WINDOWS: return "Must have at least one window, [0, L]. (TSK_ERR_BAD_NUM_WINDOWS)";
+        case TSKB_ERR_BAD_WINDOWS: return "Windows must be increasing list [0, ..., L]. (TSK_ERR_BAD_WINDOWS)";
+        case TSKB_ERR_MULTIPLE_STAT_MODES: return "Cannot specify more than one stats mode. (TSK_ERR_MULTIPLE_STAT_MODES)";
+        case TSKB_ERR_BAD_STATE_DIMS: return "Must have state dimension >= 1. (TSK_ERR_BAD_STATE_DIMS)";
+        case TSKB_ERR_BAD_RESULT_DIMS: return "Must have result dimension >= 1. (TSK_ERR_BAD_RESULT_DIMS)";
+        case TSKB_ERR_INSUFFICIENT_SAMPLE_SETS: return "Insufficient sample sets provided. (TSK_ERR_INSUFFICIENT_SAMPLE_SETS)";
+        case TSKB_ERR_INSUFFICIENT_INDEX_TUPLES: return "Insufficient sample set index tuples provided. (TSK_ERR_INSUFFICIENT_INDEX_TUPLES)";
+        case TSKB_ERR_BAD_SAMPLE_SET_INDEX: return "Sample set index out of bounds. (TSK_ERR_BAD_SAMPLE_SET_INDEX)";
+        case TSKB_ERR_EMPTY_SAMPLE_SET: return "Samples cannot be empty. (TSK_ERR_EMPTY_SAMPLE_SET)";
+        case TSKB_ERR_UNSUPPORTED_STAT_MODE: return "Requested statistics mode not supported for this method. (TSK_ERR_UNSUPPORTED_STAT_MODE)";
+        case TSKB_ERR_TIME_UNCALIBRATED: return "Statistics using branch lengths cannot be calculated when time_units is 'uncalibrated'. (TSK_ERR_TIME_UNCALIBRATED)";
+        case TSKB_ERR_STAT_POLARISED_UNSUPPORTED: return "The TSK_STAT_POLARISED option is not supported by this statistic. (TSK_ERR_STAT_POLARISED_UNSUPPORTED)";
+        case TSKB_ERR_CUDA: return "CUDA runtime error (see tskb_last_cuda_error)";
+        case TSKB_ERR_BAD_INDEX_ORDER: return "Edge indexes are not in the order tsk_table_collection_build_index produces";
+        case TSKB_ERR_UNSUPPORTED: return "Valid tskit call that the B200 engine does not accelerate";
+        case TSKB_ERR_NO_DEVICE: return "No CUDA device: the B200 engine has no CPU fallback";
+    }
+    return "Unknown error";
+}
+
+#define ONE_WAY(NAME, ID)                                                                       \
+    int tskb_treeseq_##NAME(const tskb_treeseq_t *self, uint64_t num_sample_sets,                \
+        const uint64_t *sample_set_sizes, const int32_t *sample_sets, uint64_t num_windows,     \
+        const double *windows, uint32_t options, double *result) {                              \
+        return sample_count_stat(self, ID, num_sample_sets, sample_set_sizes, sample_sets,      \
+            false, sample_sets, 0, nullptr, num_sample_sets, 0, nullptr, num_windows, windows,  \
+            options, result, false);                                                            \
+    }
+ONE_WAY(diversity, STAT_DIVERSITY)
+ONE_WAY(segregating_sites, STAT_SEGSITES)
+ONE_WAY(Y1, STAT_Y1)
+
+#define K_WAY(NAME, ID)                                                                         \
+    int tskb_treeseq_##NAME(const tskb_treeseq_t *self, uint64_t num_sample_sets,                \
+        const uint64_t *sample_set_sizes, const int32_t *sample_sets,                           \
+        uint64_t num_index_tuples, const int32_t *index_tuples, uint64_t num_windows,           \
+        const double *windows, uint32_t options, double *result) {                              \
+        return sample_count_stat(self, ID, num_sample_sets, sample_set_sizes, sample_sets,      \
+            false, sample_sets, num_index_tuples, index_tuples, num_index_tuples, 0, nullptr,   \
+            num_windows, windows, options, result, false);                                      \
+    }
+K_WAY(divergence, STAT_DIVERGENCE)
+K_WAY(Y2, STAT_Y2)
+K_WAY(f2, STAT_F2)
+K_WAY(genetic_relatedness, STAT_RELATEDNESS)
+K_WAY(Y3, STAT_Y3)
+K_WAY(f3, STAT_F3)
+K_WAY(f4, STAT_F4)
+
+int tskb_treeseq_sample_count_stat_tabulated(const tskb_treeseq_t *self,
+    uint64_t num_sample_sets, const uint64_t *sample_set_sizes, const int32_t *sample_sets,
+    uint64_t result_dim, uint64_t table_rows, const double *f_table, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result) {
+    if (f_table == nullptr || (num_sample_sets == 1 && table_rows < sample_set_sizes[0] + 1)) {
+        return TSKB_ERR_BAD_PARAM_VALUE;
+    }
+    return sample_count_stat(self, STAT_TABULATED, num_sample_sets, sample_set_sizes,
+        sample_sets, false, sample_sets, 0, nullptr, result_dim, table_rows, f_table,
+        num_windows, windows, options, result, false);
+}
+
+int tskb_treeseq_stat_device(const tskb_treeseq_t *self, int stat_id, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *d_sample_sets, uint64_t num_index_tuples,
+    const int32_t *index_tuples, uint64_t num_windows, const double *windows, uint32_t options,
+    double *d_result) {
+    if (stat_id < 0 || stat_id > STAT_F4) return TSKB_ERR_BAD_PARAM_VALUE;
+    return sample_count_stat(self, stat_id, num_sample_sets, sample_set_sizes, d_sample_sets,
+        true, nullptr, num_index_tuples, index_tuples, num_sample_sets, 0, nullptr, num_windows,
+        windows, options, d_result, true);
+}
+
+int tskb_treeseq_trees_at(const tskb_treeseq_t *self, uint64_t num_positions,
+    const double *positions, const int32_t *tracked, uint64_t num_tracked, int32_t *out_parent,
+    int32_t *out_count) {
+    if (self == nullptr || self->plan == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    const Plan &P = *self->plan;
+    for (uint64_t q = 0; q < num_positions; q++) {
+        if (!(positions[q] >= 0 && positions[q] < P.L)) return TSKB_ERR_BAD_PARAM_VALUE;
+    }
+    for (uint64_t j = 0; tracked != nullptr && j < num_tracked; j++) {
+        if (tracked[j] < 0 || tracked[j] >= (int32_t) P.N) return TSKB_ERR_NODE_OUT_OF_BOUNDS;
+    }
+    return guarded([&]() -> int {
+        return run_trees_at(&P, num_positions, positions, tracked, num_tracked, out_parent,
+            out_count);
+    });
+}
+
+int tskb_treeseq_get_stats(const tskb_treeseq_t *self, tskb_stats_t *out) {
+    if (self == nullptr || self->plan == nullptr || out == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    std::lock_guard<std::mutex> lock(self->plan->mu);
+    *out = self->plan->stats;
+    return 0;
+}
+
+int64_t tskb_treeseq_debug_array(const tskb_treeseq_t *self, const char *name, void *out,
+    uint64_t max_bytes) {
+    if (self == nullptr || self->plan == nullptr || name == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    const Plan &P = *self->plan;
+    std::lock_guard<std::mutex> lock(P.mu);
+    const void *src = nullptr;
+    size_t n = 0, esize = 0;
+    bool host = false;
+    std::string s(name);
+#define ARR(NAME, A) if (s == NAME) { src = P.A.p; n = P.A.n; esize = sizeof(*P.A.p); }
+    ARR("ev_pos", ev_pos) ARR("ev_child", ev_child) ARR("ev_sign", ev_sign) ARR("ev_sbl", ev_sbl)
+    ARR("ev_src", ev_src) ARR("voff", voff) ARR("em_node", em_node) ARR("em_perm", em_perm)
+    ARR("em_bl", em_bl) ARR("nm_src", nm_src) ARR("nm_flag", nm_flag) ARR("nm_key", nm_key)
+    ARR("level", level) ARR("rank_node", rank_node) ARR("mut_src", mut_src)
+    ARR("mut_allele", mut_allele) ARR("mut_alt", mut_alt)
+#undef ARR
+    if (s == "level_begin") {
+        src = P.level_begin.data(); n = P.level_begin.size(); esize = sizeof(uint32_t); host = true;
+    }
+    if (esize == 0) return TSKB_ERR_BAD_PARAM_VALUE;
+    size_t bytes = std::min<size_t>(n * esize, max_bytes);
+    if (out != nullptr && bytes > 0) {
+        if (host) {
+            memcpy(out, src, bytes);
+        } else {
+            cudaSetDevice(P.device);
+            if (cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                cudaGetLastError();
+                return TSKB_ERR_CUDA;
+            }
+        }
+    }
+    return (int64_t) n;
+}
+
+}  // extern "C"

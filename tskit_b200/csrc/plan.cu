@@ -1,0 +1,663 @@
+// plan.cu -- staging: tables -> HBM, and construction of the replay plan (see plan.cuh).
+//
+// Everything here runs once per tree sequence (the counterpart of
+// tsk_treeseq_init, c/tskit/trees.c:455-545).  Sorting / compaction / scans use
+// CUB device primitives; the plan-specific kernels are below.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+
+#include "plan.cuh"
+
+namespace tskb {
+
+std::string &last_error_string() {
+    static thread_local std::string s;
+    return s;
+}
+
+Plan::~Plan() {
+    arena.destroy();
+    for (auto &e : ev) {
+        if (e) cudaEventDestroy(e);
+    }
+    if (stream) cudaStreamDestroy(stream);
+}
+
+uint64_t Plan::device_bytes() const {
+    return time.bytes() + d_samples.bytes() + coff.bytes() + csr_left.bytes() + csr_right.bytes()
+           + csr_parent.bytes() + ev_pos.bytes() + ev_child.bytes() + ev_sign.bytes()
+           + ev_sbl.bytes() + ev_src.bytes() + voff.bytes() + em_node.bytes() + em_perm.bytes()
+           + em_bl.bytes() + nm_src.bytes() + nm_flag.bytes() + nm_key.bytes()
+           + rank_node.bytes() + level.bytes() + site_pos.bytes() + site_moff.bytes()
+           + site_aoff.bytes() + mut_node.bytes() + mut_src.bytes() + mut_allele.bytes()
+           + mut_alt.bytes();
+}
+
+namespace {
+
+constexpr int TB = 256;
+
+// ------------------------------------------------------------------ kernels
+
+__global__ void k_iota(uint32_t *out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+
+// order-preserving map of an IEEE double onto uint64 (node times may be negative)
+__device__ inline uint64_t ordered_bits(double x) {
+    uint64_t b = (uint64_t) __double_as_longlong(x);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// seed candidates: prefix of the insertion index with left <= range_left;
+// keep those still alive at range_left (right > range_left)
+__global__ void k_seed_flags(const int32_t *I, uint32_t n, const double *er, double a,
+    uint8_t *flag, uint64_t *key, const int32_t *ep, const double *time) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) {
+        int32_t e = I[j];
+        flag[j] = er[e] > a;
+        key[j] = ordered_bits(time[ep[e]]);
+    }
+}
+
+__global__ void k_build_ins(const int32_t *seed_edges, uint32_t n_seed, const int32_t *I_rest,
+    uint32_t n_ins, const double *el, double a, int32_t *ins_edge, double *ins_pos) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_ins) {
+        int32_t e = j < n_seed ? seed_edges[j] : I_rest[j - n_seed];
+        ins_edge[j] = e;
+        double l = el[e];
+        ins_pos[j] = l > a ? l : a;
+    }
+}
+
+__global__ void k_build_rem(const int32_t *O_slice, uint32_t n_rem, const double *er,
+    int32_t *rem_edge, double *rem_pos) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_rem) {
+        int32_t e = O_slice[k];
+        rem_edge[k] = e;
+        rem_pos[k] = er[e];
+    }
+}
+
+// Event index = position in the reference's processing order: at one
+// breakpoint all removals precede all insertions (trees.c:1425-1474).
+__global__ void k_merge_events(const int32_t *ins_edge, const double *ins_pos, uint32_t n_ins,
+    const int32_t *rem_edge, const double *rem_pos, uint32_t n_rem, const int32_t *ep,
+    const int32_t *ec, const double *time, double *ev_pos, int32_t *ev_child, int32_t *ev_parent,
+    int8_t *ev_sign, double *ev_sbl) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ins + n_rem) return;
+    uint32_t idx;
+    int32_t e;
+    double pos;
+    int8_t sign;
+    if (t < n_ins) {
+        pos = ins_pos[t];
+        e = ins_edge[t];
+        idx = t + upper_bound_dev(rem_pos, n_rem, pos);
+        sign = 1;
+    } else {
+        uint32_t k = t - n_ins;
+        pos = rem_pos[k];
+        e = rem_edge[k];
+        idx = k + lower_bound_dev(ins_pos, n_ins, pos);
+        sign = -1;
+    }
+    int32_t p = ep[e], c = ec[e];
+    ev_pos[idx] = pos;
+    ev_child[idx] = c;
+    ev_parent[idx] = p;
+    ev_sign[idx] = sign;
+    double bl = time[p] - time[c];  // trees.c:1456
+    ev_sbl[idx] = sign > 0 ? bl : -bl;
+}
+
+// canonical index order check: removals old parent first, insertions young parent first
+__global__ void k_check_order(const double *ev_pos, const int8_t *ev_sign,
+    const int32_t *ev_parent, const double *time, uint32_t nev, int *bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= nev) return;
+    if (ev_pos[i] == ev_pos[i + 1] && ev_sign[i] == ev_sign[i + 1]) {
+        double t0 = time[ev_parent[i]], t1 = time[ev_parent[i + 1]];
+        if ((ev_sign[i] < 0 && t0 < t1) || (ev_sign[i] > 0 && t0 > t1)) *bad = 1;
+    }
+}
+
+__global__ void k_csr_keys(const int32_t *I, const int32_t *ec, uint32_t E, uint32_t *key,
+    uint32_t *val) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < E) {
+        int32_t e = I[j];
+        key[j] = (uint32_t) ec[e];
+        val[j] = (uint32_t) e;
+    }
+}
+
+__global__ void k_csr_gather(const uint32_t *edge, uint32_t E, const double *el, const double *er,
+    const int32_t *ep, double *csr_left, double *csr_right, int32_t *csr_parent) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < E) {
+        uint32_t e = edge[j];
+        csr_left[j] = el[e];
+        csr_right[j] = er[e];
+        csr_parent[j] = ep[e];
+    }
+}
+
+// out[q] = lower_bound(sorted_keys, q) for q in [0, nq)
+__global__ void k_offsets(const uint32_t *sorted_keys, uint32_t n, uint32_t nq, uint32_t *out) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) out[q] = lower_bound_dev(sorted_keys, n, q);
+}
+
+// parent of u through an edge spanning ACROSS x: left < x < right (and x inside the range)
+__device__ inline int32_t span_parent(int32_t u, double x, double a, const uint32_t *coff,
+    const double *csr_left, const double *csr_right, const int32_t *csr_parent) {
+    if (!(x > a)) return -1;
+    uint32_t lo = coff[u], hi = coff[u + 1];
+    uint32_t k = lower_bound_dev(csr_left + lo, hi - lo, x);  // edges with left < x
+    if (k == 0) return -1;
+    uint32_t e = lo + k - 1;
+    return csr_right[e] > x ? csr_parent[e] : -1;
+}
+
+constexpr uint32_t MAX_CHAIN = 1u << 22;
+
+__global__ void k_chain_count(const int32_t *ev_parent, const double *ev_pos, uint32_t nev,
+    double a, const uint32_t *coff, const double *csr_left, const double *csr_right,
+    const int32_t *csr_parent, uint32_t *count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nev) return;
+    double x = ev_pos[i];
+    int32_t u = ev_parent[i];
+    uint32_t c = 0;
+    while (u != -1 && c < MAX_CHAIN) {
+        c++;
+        u = span_parent(u, x, a, coff, csr_left, csr_right, csr_parent);
+    }
+    count[i] = c;
+}
+
+__global__ void k_chain_fill(const int32_t *ev_parent, const double *ev_pos, uint32_t nev,
+    double a, const uint32_t *coff, const double *csr_left, const double *csr_right,
+    const int32_t *csr_parent, const double *time, const uint32_t *voff, int32_t *em_node,
+    double *em_bl, uint32_t *em_ev) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nev) return;
+    double x = ev_pos[i];
+    int32_t u = ev_parent[i];
+    uint32_t j = voff[i], end = voff[i + 1];
+    while (u != -1 && j < end) {
+        int32_t v = span_parent(u, x, a, coff, csr_left, csr_right, csr_parent);
+        em_node[j] = u;
+        em_ev[j] = i;
+        em_bl[j] = v == -1 ? 0.0 : time[v] - time[u];
+        j++;
+        u = v;
+    }
+}
+
+__global__ void k_relax_levels(const int32_t *ep, const int32_t *ec, uint32_t E, uint32_t *level,
+    int *changed) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    uint32_t lc = level[ec[e]] + 1;
+    int32_t p = ep[e];
+    if (level[p] < lc) {
+        atomicMax(&level[p], lc);
+        *changed = 1;
+    }
+}
+
+__global__ void k_scatter_rank(const uint32_t *rank_node, uint32_t N, uint32_t *rank) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < N) rank[rank_node[r]] = r;
+}
+
+__global__ void k_visit_keys(const int32_t *em_node, const uint32_t *rank, uint32_t V,
+    uint32_t *key) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < V) key[j] = rank[em_node[j]];
+}
+
+__global__ void k_nm_finish(const uint32_t *nm_em, const uint32_t *em_ev, uint32_t V,
+    uint32_t *em_perm, uint32_t *nm_ev) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < V) {
+        uint32_t j = nm_em[k];
+        em_perm[j] = k;
+        nm_ev[k] = em_ev[j];
+    }
+}
+
+// src of event i: the child's last visit strictly before event i (its state
+// at the moment the reference reads state[child], trees.c:1436/1462)
+__global__ void k_event_src(const int32_t *ev_child, uint32_t nev, const uint32_t *rank,
+    const uint32_t *noff, const uint32_t *nm_ev, int32_t *ev_src) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nev) return;
+    int32_t c = ev_child[i];
+    uint32_t r = rank[c];
+    uint32_t lo = noff[r], hi = noff[r + 1];
+    uint32_t k = lower_bound_dev(nm_ev + lo, hi - lo, i);
+    ev_src[i] = k > 0 ? (int32_t) (lo + k - 1) : ~c;
+}
+
+__global__ void k_nm_src(const uint32_t *nm_ev, const uint32_t *nm_key, uint32_t V,
+    const int32_t *ev_src, const int8_t *ev_sign, int32_t *nm_src, uint8_t *nm_flag) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= V) return;
+    uint32_t i = nm_ev[k];
+    nm_src[k] = ev_src[i];
+    uint8_t f = ev_sign[i] < 0 ? 1 : 0;
+    if (k == 0 || nm_key[k] != nm_key[k - 1]) f |= 2;
+    nm_flag[k] = f;
+}
+
+// state[mutation.node] at the site's tree = value after the node's last visit
+// among events at positions <= site position (trees.c:1744-1763)
+__global__ void k_mut_src(const int32_t *mut_site, const int32_t *mut_node, uint32_t Mu,
+    const double *site_pos, const double *ev_pos, uint32_t nev, const uint32_t *rank,
+    const uint32_t *noff, const uint32_t *nm_ev, int32_t *mut_src) {
+    uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= Mu) return;
+    double x = site_pos[mut_site[m]];
+    uint32_t e_hi = upper_bound_dev(ev_pos, nev, x);
+    int32_t u = mut_node[m];
+    uint32_t r = rank[u];
+    uint32_t lo = noff[r], hi = noff[r + 1];
+    uint32_t k = lower_bound_dev(nm_ev + lo, hi - lo, e_hi);
+    mut_src[m] = k > 0 ? (int32_t) (lo + k - 1) : ~u;
+}
+
+// ------------------------------------------------------------ CUB wrappers
+
+struct Temp {
+    void *p = nullptr;
+    size_t cap = 0;
+    ~Temp() { if (p) cudaFree(p); }
+    void *need(size_t bytes) {
+        if (bytes > cap) {
+            if (p) cudaFree(p);
+            cap = bytes + (bytes >> 2) + 1024;
+            TSKB_CK(cudaMalloc(&p, cap));
+        }
+        return p;
+    }
+};
+
+template <typename K, typename Vt>
+void sort_pairs(Temp &tmp, const K *kin, K *kout, const Vt *vin, Vt *vout, uint32_t n, int end_bit,
+    cudaStream_t s) {
+    if (n == 0) return;
+    size_t bytes = 0;
+    TSKB_CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, n, 0, end_bit, s));
+    void *t = tmp.need(bytes);
+    TSKB_CK(cub::DeviceRadixSort::SortPairs(t, bytes, kin, kout, vin, vout, n, 0, end_bit, s));
+}
+
+uint32_t host_upper_bound_indexed(const double *col, const int32_t *order, uint64_t n, double x) {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint64_t mid = lo + ((hi - lo) >> 1);
+        if (col[order[mid]] <= x) lo = mid + 1; else hi = mid;
+    }
+    return (uint32_t) lo;
+}
+uint32_t host_lower_bound_indexed(const double *col, const int32_t *order, uint64_t n, double x) {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint64_t mid = lo + ((hi - lo) >> 1);
+        if (col[order[mid]] < x) lo = mid + 1; else hi = mid;
+    }
+    return (uint32_t) lo;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ build
+
+Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double range_right,
+    uint32_t /*options*/) {
+    auto t_start = std::chrono::steady_clock::now();
+    TSKB_CK(cudaSetDevice(device));
+    std::unique_ptr<Plan> plan(new Plan());
+    Plan &P = *plan;
+    P.device = device;
+    TSKB_CK(cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking));
+    for (auto &e : P.ev) TSKB_CK(cudaEventCreate(&e));
+    cudaStream_t s = P.stream;
+    P.N = t->num_nodes;
+    P.E = t->num_edges;
+    P.S = t->num_sites;
+    P.Mu = t->num_mutations;
+    P.L = t->sequence_length;
+    P.range_left = range_left;
+    P.range_right = range_right;
+    P.time_uncalibrated = t->time_uncalibrated;
+    const uint32_t N = (uint32_t) P.N, E = (uint32_t) P.E;
+    const double a = range_left, b = range_right;
+
+    // samples / sample_index_map exactly as init_nodes (trees.c:404-453)
+    P.sample_index_map.assign(N, -1);
+    for (uint32_t u = 0; u < N; u++) {
+        if (t->node_flags[u] & 1u) {
+            P.sample_index_map[u] = (int32_t) P.samples.size();
+            P.samples.push_back((int32_t) u);
+        }
+    }
+    P.num_samples = (uint32_t) P.samples.size();
+    P.d_samples.upload(P.samples.data(), P.samples.size(), s);
+    P.time.upload(t->node_time, N, s);
+
+    Temp tmp;
+    DevArray<double> el, er;
+    DevArray<int32_t> ep, ec, dI, dO;
+    el.upload(t->edge_left, E, s);
+    er.upload(t->edge_right, E, s);
+    ep.upload(t->edge_parent, E, s);
+    ec.upload(t->edge_child, E, s);
+    dI.upload(t->edge_insertion_order, E, s);
+    dO.upload(t->edge_removal_order, E, s);
+
+    // ---- event lists (host binary searches over the borrowed host columns)
+    const uint32_t i0 = host_upper_bound_indexed(t->edge_left, t->edge_insertion_order, E, a);
+    const uint32_t i1 = host_lower_bound_indexed(t->edge_left, t->edge_insertion_order, E, b);
+    const uint32_t r0 = host_upper_bound_indexed(t->edge_right, t->edge_removal_order, E, a);
+    const uint32_t r1 = host_lower_bound_indexed(t->edge_right, t->edge_removal_order, E, b);
+    DevArray<int32_t> seed_sorted;
+    const int32_t *seed_edges = dI.p;
+    uint32_t n_seed = i0;
+    if (a > 0 && i0 > 0) {
+        // tree at range_left: alive edges, inserted bottom-up (time[parent] ascending)
+        DevArray<uint8_t> flag;
+        DevArray<uint64_t> key, key_sel, key_out;
+        DevArray<int32_t> sel;
+        DevArray<uint32_t> nsel;
+        flag.alloc(i0); key.alloc(i0); key_sel.alloc(i0); key_out.alloc(i0); sel.alloc(i0);
+        seed_sorted.alloc(i0); nsel.alloc(1);
+        k_seed_flags<<<grid_for(i0, TB), TB, 0, s>>>(dI.p, i0, er.p, a, flag.p, key.p, ep.p,
+            P.time.p);
+        TSKB_CK_LAUNCH();
+        size_t bytes = 0;
+        TSKB_CK(cub::DeviceSelect::Flagged(nullptr, bytes, dI.p, flag.p, sel.p, nsel.p, i0, s));
+        TSKB_CK(cub::DeviceSelect::Flagged(tmp.need(bytes), bytes, dI.p, flag.p, sel.p, nsel.p, i0, s));
+        TSKB_CK(cub::DeviceSelect::Flagged(nullptr, bytes, key.p, flag.p, key_sel.p, nsel.p, i0, s));
+        TSKB_CK(cub::DeviceSelect::Flagged(tmp.need(bytes), bytes, key.p, flag.p, key_sel.p, nsel.p, i0, s));
+        TSKB_CK(cudaMemcpyAsync(&n_seed, nsel.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        TSKB_CK(cudaStreamSynchronize(s));
+        sort_pairs(tmp, key_sel.p, key_out.p, sel.p, seed_sorted.p, n_seed, 64, s);
+        TSKB_CK(cudaStreamSynchronize(s));
+        seed_edges = seed_sorted.p;
+    }
+    const uint32_t n_ins = n_seed + (i1 > i0 ? i1 - i0 : 0);
+    const uint32_t n_rem = r1 > r0 ? r1 - r0 : 0;
+    const uint32_t nev = n_ins + n_rem;
+    P.nev = nev;
+
+    DevArray<int32_t> ev_parent;
+    {
+        DevArray<int32_t> ins_edge, rem_edge;
+        DevArray<double> ins_pos, rem_pos;
+        ins_edge.alloc(n_ins); ins_pos.alloc(n_ins); rem_edge.alloc(n_rem); rem_pos.alloc(n_rem);
+        if (n_ins) {
+            k_build_ins<<<grid_for(n_ins, TB), TB, 0, s>>>(seed_edges, n_seed, dI.p + i0, n_ins,
+                el.p, a, ins_edge.p, ins_pos.p);
+            TSKB_CK_LAUNCH();
+        }
+        if (n_rem) {
+            k_build_rem<<<grid_for(n_rem, TB), TB, 0, s>>>(dO.p + r0, n_rem, er.p, rem_edge.p,
+                rem_pos.p);
+            TSKB_CK_LAUNCH();
+        }
+        P.ev_pos.alloc(nev); P.ev_child.alloc(nev); P.ev_sign.alloc(nev); P.ev_sbl.alloc(nev);
+        ev_parent.alloc(nev);
+        if (nev) {
+            k_merge_events<<<grid_for(nev, TB), TB, 0, s>>>(ins_edge.p, ins_pos.p, n_ins,
+                rem_edge.p, rem_pos.p, n_rem, ep.p, ec.p, P.time.p, P.ev_pos.p, P.ev_child.p,
+                ev_parent.p, P.ev_sign.p, P.ev_sbl.p);
+            TSKB_CK_LAUNCH();
+        }
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
+    {
+        DevArray<int> bad;
+        bad.alloc(1);
+        TSKB_CK(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+        if (nev > 1) {
+            k_check_order<<<grid_for(nev, TB), TB, 0, s>>>(P.ev_pos.p, P.ev_sign.p, ev_parent.p,
+                P.time.p, nev, bad.p);
+            TSKB_CK_LAUNCH();
+        }
+        int h_bad = 0;
+        TSKB_CK(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        TSKB_CK(cudaStreamSynchronize(s));
+        if (h_bad) {
+            throw (int) TSKB_ERR_BAD_INDEX_ORDER;
+        }
+    }
+
+    // ---- child-major CSR over all edges, sorted by (child, left)
+    P.coff.alloc(N + 1);
+    P.csr_left.alloc(E); P.csr_right.alloc(E); P.csr_parent.alloc(E);
+    {
+        DevArray<uint32_t> kin, kout, vin, vout;
+        kin.alloc(E); kout.alloc(E); vin.alloc(E); vout.alloc(E);
+        if (E) {
+            k_csr_keys<<<grid_for(E, TB), TB, 0, s>>>(dI.p, ec.p, E, kin.p, vin.p);
+            TSKB_CK_LAUNCH();
+            sort_pairs(tmp, kin.p, kout.p, vin.p, vout.p, E, (int) std::max(1u, ceil_log2(N)), s);
+            k_csr_gather<<<grid_for(E, TB), TB, 0, s>>>(vout.p, E, el.p, er.p, ep.p, P.csr_left.p,
+                P.csr_right.p, P.csr_parent.p);
+            TSKB_CK_LAUNCH();
+        }
+        k_offsets<<<grid_for(N + 1, TB), TB, 0, s>>>(kout.p, E, N + 1, P.coff.p);
+        TSKB_CK_LAUNCH();
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
+
+    // ---- chains: count, scan, fill
+    P.voff.alloc(nev + 1);
+    uint32_t V = 0;
+    {
+        DevArray<uint32_t> cnt;
+        cnt.alloc(nev + 1);
+        TSKB_CK(cudaMemsetAsync(cnt.p, 0, (nev + 1) * sizeof(uint32_t), s));
+        if (nev) {
+            k_chain_count<<<grid_for(nev, TB), TB, 0, s>>>(ev_parent.p, P.ev_pos.p, nev, a,
+                P.coff.p, P.csr_left.p, P.csr_right.p, P.csr_parent.p, cnt.p);
+            TSKB_CK_LAUNCH();
+        }
+        size_t bytes = 0;
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt.p, P.voff.p, nev + 1, s));
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(tmp.need(bytes), bytes, cnt.p, P.voff.p, nev + 1, s));
+        TSKB_CK(cudaMemcpyAsync(&V, P.voff.p + nev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
+    P.V = V;
+    P.em_node.alloc(V); P.em_bl.alloc(V); P.em_perm.alloc(V);
+    DevArray<uint32_t> em_ev;
+    em_ev.alloc(V);
+    if (nev && V) {
+        k_chain_fill<<<grid_for(nev, TB), TB, 0, s>>>(ev_parent.p, P.ev_pos.p, nev, a, P.coff.p,
+            P.csr_left.p, P.csr_right.p, P.csr_parent.p, P.time.p, P.voff.p, P.em_node.p,
+            P.em_bl.p, em_ev.p);
+        TSKB_CK_LAUNCH();
+    }
+    ev_parent.release();
+
+    // ---- dependency levels: level[parent] > level[child] over every edge
+    P.level.alloc(N);
+    TSKB_CK(cudaMemsetAsync(P.level.p, 0, N * sizeof(uint32_t), s));
+    {
+        DevArray<int> changed;
+        changed.alloc(1);
+        int h_changed = E > 0;
+        int rounds = 0;
+        while (h_changed) {
+            TSKB_CK(cudaMemsetAsync(changed.p, 0, sizeof(int), s));
+            for (int r = 0; r < 8; r++) {
+                k_relax_levels<<<grid_for(E, TB), TB, 0, s>>>(ep.p, ec.p, E, P.level.p, changed.p);
+            }
+            TSKB_CK_LAUNCH();
+            TSKB_CK(cudaMemcpyAsync(&h_changed, changed.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+            TSKB_CK(cudaStreamSynchronize(s));
+            if (++rounds > (1 << 20)) break;  // cyclic (invalid) input
+        }
+    }
+    uint32_t max_level = 0;
+    {
+        DevArray<uint32_t> mx;
+        mx.alloc(1);
+        size_t bytes = 0;
+        if (N) {
+            TSKB_CK(cub::DeviceReduce::Max(nullptr, bytes, P.level.p, mx.p, N, s));
+            TSKB_CK(cub::DeviceReduce::Max(tmp.need(bytes), bytes, P.level.p, mx.p, N, s));
+            TSKB_CK(cudaMemcpyAsync(&max_level, mx.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            TSKB_CK(cudaStreamSynchronize(s));
+        }
+    }
+    P.nlevels = max_level + 1;
+
+    // ---- node rank: nodes sorted by (level, id)
+    DevArray<uint32_t> rank, lvl_rank_off;
+    rank.alloc(N);
+    P.rank_node.alloc(N);
+    lvl_rank_off.alloc(P.nlevels + 1);
+    {
+        DevArray<uint32_t> ids, lvl_sorted;
+        ids.alloc(N); lvl_sorted.alloc(N);
+        if (N) {
+            k_iota<<<grid_for(N, TB), TB, 0, s>>>(ids.p, N);
+            TSKB_CK_LAUNCH();
+            sort_pairs(tmp, P.level.p, lvl_sorted.p, ids.p, (uint32_t *) P.rank_node.p, N,
+                (int) std::max(1u, ceil_log2(P.nlevels + 1)), s);
+            k_scatter_rank<<<grid_for(N, TB), TB, 0, s>>>((uint32_t *) P.rank_node.p, N, rank.p);
+            TSKB_CK_LAUNCH();
+        }
+        k_offsets<<<grid_for(P.nlevels + 1, TB), TB, 0, s>>>(lvl_sorted.p, N, P.nlevels + 1,
+            lvl_rank_off.p);
+        TSKB_CK_LAUNCH();
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
+
+    // ---- node-major order of the visits
+    P.nm_key.alloc(V); P.nm_src.alloc(V); P.nm_flag.alloc(V);
+    DevArray<uint32_t> nm_ev, noff;
+    nm_ev.alloc(V);
+    noff.alloc(N + 1);
+    {
+        DevArray<uint32_t> kin, vin, nm_em;
+        kin.alloc(V); vin.alloc(V); nm_em.alloc(V);
+        if (V) {
+            k_visit_keys<<<grid_for(V, TB), TB, 0, s>>>(P.em_node.p, rank.p, V, kin.p);
+            k_iota<<<grid_for(V, TB), TB, 0, s>>>(vin.p, V);
+            TSKB_CK_LAUNCH();
+            sort_pairs(tmp, kin.p, P.nm_key.p, vin.p, nm_em.p, V, (int) std::max(1u, ceil_log2(N)), s);
+            k_nm_finish<<<grid_for(V, TB), TB, 0, s>>>(nm_em.p, em_ev.p, V, P.em_perm.p, nm_ev.p);
+            TSKB_CK_LAUNCH();
+        }
+        k_offsets<<<grid_for(N + 1, TB), TB, 0, s>>>(P.nm_key.p, V, N + 1, noff.p);
+        TSKB_CK_LAUNCH();
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
+    em_ev.release();
+    {
+        // level_begin[l] = noff[lvl_rank_off[l]]
+        std::vector<uint32_t> h_lro = lvl_rank_off.download(s);
+        std::vector<uint32_t> h_noff = noff.download(s);
+        P.level_begin.resize(P.nlevels + 1);
+        for (uint32_t l = 0; l <= P.nlevels; l++) {
+            P.level_begin[l] = h_noff[h_lro[l]];
+        }
+    }
+    P.ev_src.alloc(nev);
+    if (nev) {
+        k_event_src<<<grid_for(nev, TB), TB, 0, s>>>(P.ev_child.p, nev, rank.p, noff.p, nm_ev.p,
+            P.ev_src.p);
+        TSKB_CK_LAUNCH();
+    }
+    if (V) {
+        k_nm_src<<<grid_for(V, TB), TB, 0, s>>>(nm_ev.p, P.nm_key.p, V, P.ev_src.p, P.ev_sign.p,
+            P.nm_src.p, P.nm_flag.p);
+        TSKB_CK_LAUNCH();
+    }
+
+    // ---- sites and mutations: allele strings -> small integer codes on the host
+    // (replaces the memcmp loops of get_allele_weights, trees.c:1557-1596)
+    {
+        const uint32_t S = (uint32_t) P.S, Mu = (uint32_t) P.Mu;
+        std::vector<uint32_t> moff(S + 1, 0), aoff(S + 1, 0);
+        std::vector<uint16_t> m_allele(Mu), m_alt(Mu);
+        for (uint32_t m = 0; m < Mu; m++) moff[t->mutation_site[m] + 1]++;
+        for (uint32_t j = 0; j < S; j++) moff[j + 1] += moff[j];
+        struct Str { const char *p; uint64_t n; };
+        std::vector<Str> alleles;
+        auto find = [&](const Str &q) -> int {
+            for (size_t k = 0; k < alleles.size(); k++) {
+                if (alleles[k].n == q.n && memcmp(alleles[k].p, q.p, q.n) == 0) return (int) k;
+            }
+            return -1;
+        };
+        for (uint32_t j = 0; j < S; j++) {
+            alleles.clear();
+            uint64_t o0 = t->site_ancestral_state_offset[j], o1 = t->site_ancestral_state_offset[j + 1];
+            alleles.push_back({ t->site_ancestral_state + o0, o1 - o0 });
+            for (uint32_t m = moff[j]; m < moff[j + 1]; m++) {
+                uint64_t d0 = t->mutation_derived_state_offset[m], d1 = t->mutation_derived_state_offset[m + 1];
+                Str der{ t->mutation_derived_state + d0, d1 - d0 };
+                int k = find(der);
+                if (k < 0) { k = (int) alleles.size(); alleles.push_back(der); }
+                m_allele[m] = (uint16_t) k;
+                Str alt = alleles[0];
+                int32_t pm = t->mutation_parent ? t->mutation_parent[m] : -1;
+                if (pm >= 0) {
+                    uint64_t p0 = t->mutation_derived_state_offset[pm], p1 = t->mutation_derived_state_offset[pm + 1];
+                    alt = Str{ t->mutation_derived_state + p0, p1 - p0 };
+                }
+                int ka = find(alt);
+                m_alt[m] = (uint16_t) (ka < 0 ? 0 : ka);
+                if (alleles.size() > 65000) throw (int) TSKB_ERR_UNSUPPORTED;
+            }
+            aoff[j + 1] = aoff[j] + (uint32_t) alleles.size();
+        }
+        P.total_alleles = aoff[S];
+        P.h_site_pos.assign(t->site_position, t->site_position + S);
+        P.site_lo = (uint32_t) (std::lower_bound(P.h_site_pos.begin(), P.h_site_pos.end(), a) - P.h_site_pos.begin());
+        P.site_hi = (uint32_t) (std::lower_bound(P.h_site_pos.begin(), P.h_site_pos.end(), b) - P.h_site_pos.begin());
+        P.site_pos.upload(t->site_position, S, s);
+        P.site_moff.upload(moff.data(), S + 1, s);
+        P.site_aoff.upload(aoff.data(), S + 1, s);
+        P.mut_node.upload(t->mutation_node, Mu, s);
+        P.mut_allele.upload(m_allele.data(), Mu, s);
+        P.mut_alt.upload(m_alt.data(), Mu, s);
+        P.mut_src.alloc(Mu);
+        if (Mu) {
+            DevArray<int32_t> d_msite;
+            d_msite.upload(t->mutation_site, Mu, s);
+            k_mut_src<<<grid_for(Mu, TB), TB, 0, s>>>(d_msite.p, P.mut_node.p, Mu, P.site_pos.p,
+                P.ev_pos.p, nev, rank.p, noff.p, nm_ev.p, P.mut_src.p);
+            TSKB_CK_LAUNCH();
+            TSKB_CK(cudaStreamSynchronize(s));
+        }
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
+    TSKB_CK(cudaStreamSynchronize(s));
+
+    P.stats.num_events = nev;
+    P.stats.num_visits = V;
+    P.stats.num_levels = P.nlevels;
+    P.stats.device_bytes = P.device_bytes();
+    P.stats.stage_ms = std::chrono::duration<double, std::milli>(
+        std::chrono::steady_clock::now() - t_start).count();
+    return plan.release();
+}
+
+}  // namespace tskb

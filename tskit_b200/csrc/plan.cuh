@@ -1,0 +1,136 @@
+// plan.cuh -- the device-resident "replay plan" of one tree sequence.
+//
+// The reference sweeps the genome left to right applying edge diffs and, for
+// every diff, walks from the edge's parent to the root updating per-node state
+// (c/tskit/trees.c:1424-1507, 1712-1734).  That sweep is sequential.  The plan
+// turns it into data-parallel work once per tree sequence:
+//
+//   * event i      = one edge diff in the reference's exact processing order
+//                    (all removals at x in removal-index order, then all
+//                    insertions at x in insertion-index order);
+//   * visit (i, u) = one iteration of the reference's `while (u != TSK_NULL)`
+//                    walk for event i.  The chain of an event is found without
+//                    any sweep state: because removals are ordered old-parent
+//                    first and insertions young-parent first
+//                    (c/tskit/tables.c:11392-11459), the walk follows exactly
+//                    the edges that span ACROSS x (left < x < right), which an
+//                    interval query in a child-major edge CSR answers;
+//   * per node, the visits in event order form a list whose running sum is the
+//                    node's state after each visit; the addend of visit (i, u)
+//                    is +-state[child_i] at that moment, i.e. the value after
+//                    the child's last earlier visit ("src");
+//   * nodes are grouped into dependency levels (level[parent] > level[child]
+//                    over every edge) so that all lists of one level can be
+//                    prefix-summed in parallel once lower levels are done.
+//
+// "em" arrays are in event-major order (visits of event 0, of event 1, ...),
+// "nm" arrays are in node-major order (sorted by (level, node, event)).
+#pragma once
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/tskit_b200.h"
+#include "common.cuh"
+
+namespace tskb {
+
+struct Plan {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    // sizes
+    uint64_t N = 0, E = 0, S = 0, Mu = 0;
+    double L = 0, range_left = 0, range_right = 0;
+    int time_uncalibrated = 0;
+    uint32_t nev = 0;      // events (edge diffs) inside the range
+    uint32_t V = 0;        // visits
+    uint32_t nlevels = 0;  // max level + 1
+    uint32_t num_samples = 0;
+    uint32_t site_lo = 0, site_hi = 0;  // sites inside the range
+    uint64_t total_alleles = 0;
+
+    // host copies needed for argument validation
+    std::vector<int32_t> sample_index_map;  // node -> sample index or -1 (trees.c:404-453)
+    std::vector<int32_t> samples;
+    std::vector<uint32_t> level_begin;  // nm offset of each level, size nlevels + 1
+
+    // --- tables in HBM ---
+    DevArray<double> time;            // [N]
+    DevArray<int32_t> d_samples;      // [n]
+    // child-major CSR of all edges, sorted by (child, left)
+    DevArray<uint32_t> coff;          // [N + 1]
+    DevArray<double> csr_left, csr_right;
+    DevArray<int32_t> csr_parent;
+    // --- events ---
+    DevArray<double> ev_pos;          // [nev] breakpoint of the diff (clipped to the range)
+    DevArray<int32_t> ev_child;       // [nev]
+    DevArray<int8_t> ev_sign;         // [nev] -1 removal, +1 insertion
+    DevArray<double> ev_sbl;          // [nev] sign * (time[parent] - time[child])
+    DevArray<int32_t> ev_src;         // [nev] nm index of the child's last earlier visit, or ~child
+    DevArray<uint32_t> voff;          // [nev + 1] visit offsets (em order)
+    // --- visits, event-major ---
+    DevArray<int32_t> em_node;        // [V]
+    DevArray<uint32_t> em_perm;       // [V] em index -> nm index
+    DevArray<double> em_bl;           // [V] branch length above the visited node at that moment (0 at chain top)
+    // --- visits, node-major ---
+    DevArray<int32_t> nm_src;         // [V] ev_src of the visit's event
+    DevArray<uint8_t> nm_flag;        // [V] bit0: removal (negative addend), bit1: first visit of its node
+    DevArray<uint32_t> nm_key;        // [V] rank of the visited node
+    DevArray<int32_t> rank_node;      // [N] rank -> node id (nodes sorted by (level, id))
+    DevArray<uint32_t> level;         // [N]
+    // --- sites ---
+    DevArray<double> site_pos;        // [S]
+    DevArray<uint32_t> site_moff;     // [S + 1] mutation CSR
+    DevArray<uint32_t> site_aoff;     // [S + 1] allele-slot CSR
+    DevArray<int32_t> mut_node;       // [Mu]
+    DevArray<int32_t> mut_src;        // [Mu] nm index holding state[mutation.node] at the site, or ~node
+    DevArray<uint16_t> mut_allele;    // [Mu] allele index of the derived state
+    DevArray<uint16_t> mut_alt;       // [Mu] allele index the mutation's state is subtracted from
+    std::vector<double> h_site_pos;
+
+    // per-call scratch + statistics
+    mutable std::mutex mu;
+    mutable Arena arena;
+    mutable tskb_stats_t stats = {};
+    size_t scan_temp_bytes = 0;
+
+    ~Plan();
+    uint64_t device_bytes() const;
+};
+
+// plan.cu
+Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double range_right,
+    uint32_t options);
+
+// stats.cu
+struct StatSpec {
+    int stat_id;          // see StatId
+    uint32_t K;           // number of sample sets (state_dim)
+    uint32_t M;           // result_dim
+    uint32_t tuple;       // index tuple width (0 for one-way)
+    const uint64_t *sizes;       // host [K]
+    const int32_t *sets;         // flattened sample ids (host or device, see sets_on_device)
+    bool sets_on_device;
+    const int32_t *indexes;      // host [M * tuple]
+    uint32_t W;
+    const double *windows;       // host [W + 1]
+    uint32_t options;
+    double *result;              // host or device [W * M]
+    bool result_on_device;
+    // tabulated summary (stat_id == STAT_TABULATED)
+    const double *f_table = nullptr;
+    uint64_t table_rows = 0;
+};
+
+enum StatId {
+    STAT_DIVERSITY = 0, STAT_SEGSITES = 1, STAT_Y1 = 2, STAT_DIVERGENCE = 3, STAT_Y2 = 4,
+    STAT_F2 = 5, STAT_RELATEDNESS = 6, STAT_Y3 = 7, STAT_F3 = 8, STAT_F4 = 9,
+    STAT_RELATEDNESS_NC = 10, STAT_TABULATED = 11
+};
+
+int run_sample_count_stat(const Plan *plan, const StatSpec &spec);
+int run_trees_at(const Plan *plan, uint64_t nq, const double *positions, const int32_t *tracked,
+    uint64_t num_tracked, int32_t *out_parent, int32_t *out_count);
+
+}  // namespace tskb

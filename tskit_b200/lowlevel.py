@@ -1,0 +1,344 @@
+"""Host-side mirror of the reference's low-level statistics interface.
+
+``LLTreeSequence`` exposes the statistics methods of ``_tskit.TreeSequence``
+(``python/_tskitmodule.c:6525-7510``; method table 8657-9022) with the same
+names, positional/keyword arguments, dtypes, return shapes and exceptions, but
+computes on the B200 through the C ABI in ``include/tskit_b200.h``.  It is what
+the drop-in proxy (``tskit_b200.dropin``) puts in place of
+``ts._ll_tree_sequence`` while a statistic runs.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .tables import Tables
+
+STAT_SITE, STAT_BRANCH, STAT_NODE = 1, 2, 4
+STAT_POLARISED, STAT_SPAN_NORMALISE = 1 << 10, 1 << 11
+STAT_NONCENTRED = 1 << 14
+ISOLATED_NOT_MISSING = 1 << 1
+
+STAT_IDS = {"diversity": 0, "segregating_sites": 1, "Y1": 2, "divergence": 3, "Y2": 4,
+            "f2": 5, "genetic_relatedness": 6, "Y3": 7, "f3": 8, "f4": 9}
+TUPLE = {"divergence": 2, "Y2": 2, "f2": 2, "genetic_relatedness": 2, "Y3": 3, "f3": 3,
+         "f4": 4}
+
+
+class LibraryError(Exception):
+    """Mirror of ``_tskit.LibraryError`` (``_tskitmodule.c:231-300``)."""
+
+    def __init__(self, code, msg=None):
+        self.code = code
+        super().__init__(msg if msg is not None else _lib.lib().tskb_strerror(code).decode())
+
+
+def _handle(ret):
+    if ret != 0:
+        msg = _lib.lib().tskb_strerror(ret).decode()
+        if ret == -20001:
+            msg += ": " + _lib.lib().tskb_last_cuda_error().decode()
+        raise LibraryError(ret, msg)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def parse_stats_mode(mode):
+    """``parse_stats_mode`` (``_tskitmodule.c:6588-6607``)."""
+    if mode is None or mode == "site":
+        return STAT_SITE
+    if mode == "branch":
+        return STAT_BRANCH
+    if mode == "node":
+        return STAT_NODE
+    if not isinstance(mode, str):
+        raise TypeError("mode must be a string")
+    raise ValueError("Unrecognised stats mode")
+
+
+def parse_windows(windows):
+    """``parse_windows`` (``_tskitmodule.c:6609-6636``)."""
+    w = np.array(windows, dtype=np.float64, copy=True, order="C", ndmin=1)
+    if w.ndim != 1:
+        raise ValueError("object too deep for desired array")
+    if w.shape[0] < 2:
+        raise ValueError("Windows array must have at least 2 elements")
+    return w
+
+
+def parse_sample_sets(sample_set_sizes, sample_sets):
+    """``parse_sample_sets`` (``_tskitmodule.c:799-851``)."""
+    sizes = np.array(sample_set_sizes, dtype=np.uint64, copy=True, order="C", ndmin=1)
+    sets = np.array(sample_sets, dtype=np.int32, copy=True, order="C", ndmin=1)
+    if sizes.ndim != 1 or sets.ndim != 1:
+        raise ValueError("object too deep for desired array")
+    if int(sizes.sum()) != sets.shape[0]:
+        raise ValueError("Sum of sample_set_sizes must equal length of sample_sets array")
+    return sizes, sets
+
+
+class LLTreeSequence:
+    """Device-resident tree sequence exposing ``_tskit.TreeSequence``'s statistics methods."""
+
+    def __init__(self, tables: Tables, device=0, genome_range=None):
+        tables.ensure_derived()
+        self.tables = tables
+        self.device = device
+        lo, hi = (0.0, tables.sequence_length) if genome_range is None else genome_range
+        self.genome_range = (float(lo), float(hi))
+        t = _lib.Tables()
+        t.sequence_length = tables.sequence_length
+        t.time_uncalibrated = int(tables.time_uncalibrated)
+        t.num_nodes = tables.num_nodes
+        t.node_flags = _p(tables.nodes_flags)
+        t.node_time = _p(tables.nodes_time)
+        t.num_edges = tables.num_edges
+        t.edge_left = _p(tables.edges_left)
+        t.edge_right = _p(tables.edges_right)
+        t.edge_parent = _p(tables.edges_parent)
+        t.edge_child = _p(tables.edges_child)
+        t.edge_insertion_order = _p(tables.edge_insertion_order)
+        t.edge_removal_order = _p(tables.edge_removal_order)
+        t.num_sites = tables.num_sites
+        t.site_position = _p(tables.sites_position)
+        t.site_ancestral_state = _p(tables.sites_ancestral_state)
+        t.site_ancestral_state_offset = _p(tables.sites_ancestral_state_offset)
+        t.num_mutations = tables.num_mutations
+        t.mutation_site = _p(tables.mutations_site)
+        t.mutation_node = _p(tables.mutations_node)
+        t.mutation_parent = _p(tables.mutations_parent)
+        t.mutation_derived_state = _p(tables.mutations_derived_state)
+        t.mutation_derived_state_offset = _p(tables.mutations_derived_state_offset)
+        h = C.c_void_p()
+        self._h = None
+        _handle(_lib.lib().tskb_treeseq_init(C.byref(h), C.byref(t), int(device),
+                                             self.genome_range[0], self.genome_range[1], 0))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            _lib.lib().tskb_treeseq_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the accessors trees.py uses next to the stats methods
+    def get_num_samples(self):
+        return self.tables.num_samples
+
+    def get_num_nodes(self):
+        return self.tables.num_nodes
+
+    def get_sequence_length(self):
+        return self.tables.sequence_length
+
+    def get_samples(self):
+        return self.tables.samples
+
+    def engine_stats(self):
+        s = _lib.Stats()
+        _handle(_lib.lib().tskb_treeseq_get_stats(self._h, C.byref(s)))
+        return {
+            "num_events": s.num_events, "num_visits": s.num_visits,
+            "num_levels": s.num_levels, "stage_ms": s.stage_ms,
+            "last_call_ms": s.last_call_ms, "last_kernel_ms": list(s.last_kernel_ms),
+            "last_launches": s.last_launches, "device_bytes": s.device_bytes}
+
+    def debug_array(self, name, dtype):
+        n = _lib.lib().tskb_treeseq_debug_array(self._h, name.encode(), None, 0)
+        if n < 0:
+            raise LibraryError(int(n))
+        out = np.empty(n, dtype=dtype)
+        _lib.lib().tskb_treeseq_debug_array(self._h, name.encode(), _p(out), out.nbytes)
+        return out
+
+    # ---- TreeSequence_one_way_stat_method (_tskitmodule.c:6909-6975)
+    def _one_way(self, name, sample_set_sizes, sample_sets, windows, mode, span_normalise,
+                 polarised):
+        options = parse_stats_mode(mode)
+        sizes, sets = parse_sample_sets(sample_set_sizes, sample_sets)
+        w = parse_windows(windows)
+        if span_normalise:
+            options |= STAT_SPAN_NORMALISE
+        if polarised:
+            options |= STAT_POLARISED
+        if options & STAT_NODE:
+            result = np.zeros((len(w) - 1, self.tables.num_nodes, len(sizes)))
+        else:
+            result = np.zeros((len(w) - 1, len(sizes)))
+        fn = getattr(_lib.lib(), "tskb_treeseq_" + name)
+        _handle(fn(self._h, len(sizes), _p(sizes), _p(sets), len(w) - 1, _p(w), options,
+                   _p(result)))
+        return result
+
+    def diversity(self, sample_set_sizes, sample_sets, windows=None, mode=None,
+                  span_normalise=True, polarised=False):
+        return self._one_way("diversity", sample_set_sizes, sample_sets, windows, mode,
+                             span_normalise, polarised)
+
+    def segregating_sites(self, sample_set_sizes, sample_sets, windows=None, mode=None,
+                          span_normalise=True, polarised=False):
+        return self._one_way("segregating_sites", sample_set_sizes, sample_sets, windows, mode,
+                             span_normalise, polarised)
+
+    def Y1(self, sample_set_sizes, sample_sets, windows=None, mode=None, span_normalise=True,
+           polarised=False):
+        return self._one_way("Y1", sample_set_sizes, sample_sets, windows, mode,
+                             span_normalise, polarised)
+
+    # ---- TreeSequence_k_way_stat_method (_tskitmodule.c:7104-7194)
+    def _k_way(self, name, sample_set_sizes, sample_sets, indexes, windows, mode,
+               span_normalise, polarised, centre):
+        options = parse_stats_mode(mode)
+        sizes, sets = parse_sample_sets(sample_set_sizes, sample_sets)
+        w = parse_windows(windows)
+        if span_normalise:
+            options |= STAT_SPAN_NORMALISE
+        if polarised:
+            options |= STAT_POLARISED
+        if not centre:
+            options |= STAT_NONCENTRED
+        idx = np.array(indexes, dtype=np.int32, copy=True, order="C")
+        if idx.ndim != 2:
+            raise ValueError("object of too small depth for desired array"
+                             if idx.ndim < 2 else "object too deep for desired array")
+        if idx.shape[0] < 1 or idx.shape[1] != TUPLE[name]:
+            raise ValueError(f"indexes must be a k x {TUPLE[name]} array.")
+        if options & STAT_NODE:
+            result = np.zeros((len(w) - 1, self.tables.num_nodes, idx.shape[0]))
+        else:
+            result = np.zeros((len(w) - 1, idx.shape[0]))
+        fn = getattr(_lib.lib(), "tskb_treeseq_" + name)
+        _handle(fn(self._h, len(sizes), _p(sizes), _p(sets), idx.shape[0], _p(idx),
+                   len(w) - 1, _p(w), options, _p(result)))
+        return result
+
+    def divergence(self, sample_set_sizes, sample_sets, indexes, windows=None, mode=None,
+                   span_normalise=True, polarised=False, centre=True):
+        return self._k_way("divergence", sample_set_sizes, sample_sets, indexes, windows, mode,
+                           span_normalise, polarised, centre)
+
+    def genetic_relatedness(self, sample_set_sizes, sample_sets, indexes, windows=None,
+                            mode=None, span_normalise=True, polarised=False, centre=True):
+        return self._k_way("genetic_relatedness", sample_set_sizes, sample_sets, indexes,
+                           windows, mode, span_normalise, polarised, centre)
+
+    def Y2(self, sample_set_sizes, sample_sets, indexes, windows=None, mode=None,
+           span_normalise=True, polarised=False, centre=True):
+        return self._k_way("Y2", sample_set_sizes, sample_sets, indexes, windows, mode,
+                           span_normalise, polarised, centre)
+
+    def f2(self, sample_set_sizes, sample_sets, indexes, windows=None, mode=None,
+           span_normalise=True, polarised=False, centre=True):
+        return self._k_way("f2", sample_set_sizes, sample_sets, indexes, windows, mode,
+                           span_normalise, polarised, centre)
+
+    def Y3(self, sample_set_sizes, sample_sets, indexes, windows=None, mode=None,
+           span_normalise=True, polarised=False, centre=True):
+        return self._k_way("Y3", sample_set_sizes, sample_sets, indexes, windows, mode,
+                           span_normalise, polarised, centre)
+
+    def f3(self, sample_set_sizes, sample_sets, indexes, windows=None, mode=None,
+           span_normalise=True, polarised=False, centre=True):
+        return self._k_way("f3", sample_set_sizes, sample_sets, indexes, windows, mode,
+                           span_normalise, polarised, centre)
+
+    def f4(self, sample_set_sizes, sample_sets, indexes, windows=None, mode=None,
+           span_normalise=True, polarised=False, centre=True):
+        return self._k_way("f4", sample_set_sizes, sample_sets, indexes, windows, mode,
+                           span_normalise, polarised, centre)
+
+    # ---- TreeSequence_general_stat (_tskitmodule.c:6665-6745)
+    def general_stat(self, weights, summary_func, output_dim, windows=None, mode=None,
+                     polarised=False, span_normalise=True):
+        """0/1 weight columns only (what ``sample_count_stat`` builds,
+        ``trees.py:8096``): one column is evaluated through a device lookup
+        table of ``summary_func`` over every possible count.  Anything else
+        raises; it is never computed on the host."""
+        options = parse_stats_mode(mode)
+        w = parse_windows(windows)
+        if not callable(summary_func):
+            raise TypeError("summary_func must be callable")
+        W = np.array(weights, dtype=np.float64, copy=True, order="C")
+        if W.ndim != 2:
+            raise ValueError("object of too small depth for desired array")
+        if W.shape[0] != self.tables.num_samples:
+            raise ValueError("First dimension must be num_samples")
+        if span_normalise:
+            options |= STAT_SPAN_NORMALISE
+        if polarised:
+            options |= STAT_POLARISED
+        if not np.all((W == 0) | (W == 1)):
+            raise LibraryError(-20003, "general_stat on the B200 engine needs 0/1 sample "
+                               "weights (sample_count_stat); weighted statistics are not "
+                               "accelerated")
+        if W.shape[1] != 1:
+            raise LibraryError(-20003, "general_stat with a Python summary function is "
+                               "accelerated for one sample set (state_dim == 1) only")
+        samples = self.tables.samples
+        members = samples[W[:, 0] == 1].astype(np.int32)
+        sizes = np.array([len(members)], dtype=np.uint64)
+        n = len(members)
+        table = np.empty((n + 1, output_dim), dtype=np.float64)
+        for c in range(n + 1):
+            y = np.asarray(summary_func(np.array([float(c)])), dtype=np.float64)
+            if y.shape != (output_dim,):
+                raise ValueError("summary_func returned array of wrong dimension")
+            table[c] = y
+        if options & STAT_NODE:
+            result = np.zeros((len(w) - 1, self.tables.num_nodes, output_dim))
+        else:
+            result = np.zeros((len(w) - 1, output_dim))
+        _handle(_lib.lib().tskb_treeseq_sample_count_stat_tabulated(
+            self._h, 1, _p(sizes), _p(members), output_dim, n + 1, _p(table), len(w) - 1,
+            _p(w), options, _p(result)))
+        return result
+
+    # ---- TreeSequence_divergence_matrix (_tskitmodule.c:7435-7509)
+    def divergence_matrix(self, windows, sample_sets=None, sample_set_sizes=None, mode=None,
+                          span_normalise=True):
+        options = parse_stats_mode(mode)
+        w = parse_windows(windows)
+        if span_normalise:
+            options |= STAT_SPAN_NORMALISE
+        if sample_sets is None:
+            if sample_set_sizes is not None:
+                raise TypeError("Must specify both sample_sets and sample_set_sizes")
+            sizes = sets = None
+            n = self.tables.num_samples
+        else:
+            if sample_set_sizes is None:
+                raise TypeError("Must specify both sample_sets and sample_set_sizes")
+            sizes, sets = parse_sample_sets(sample_set_sizes, sample_sets)
+            n = len(sizes)
+        result = np.zeros((len(w) - 1, n, n))
+        _handle(_lib.lib().tskb_treeseq_divergence_matrix(
+            self._h, n, _p(sizes), _p(sets), len(w) - 1, _p(w), options, _p(result)))
+        return result
+
+    # ---- integer parity outputs
+    def trees_at(self, positions, tracked=None):
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        N = self.tables.num_nodes
+        par = np.empty((len(pos), N), dtype=np.int32)
+        cnt = np.empty((len(pos), N), dtype=np.int32)
+        tr = None if tracked is None else np.ascontiguousarray(tracked, dtype=np.int32)
+        _handle(_lib.lib().tskb_treeseq_trees_at(
+            self._h, len(pos), _p(pos), _p(tr), 0 if tr is None else len(tr), _p(par),
+            _p(cnt)))
+        return par, cnt
+
+    def genotype_matrix(self, samples=None, isolated_as_missing=True):
+        n = self.tables.num_samples if samples is None else len(samples)
+        s = None if samples is None else np.ascontiguousarray(samples, dtype=np.int32)
+        out = np.empty((self.tables.num_sites, n), dtype=np.int8)
+        _handle(_lib.lib().tskb_treeseq_genotype_matrix(
+            self._h, _p(s), 0 if s is None else n,
+            0 if isolated_as_missing else ISOLATED_NOT_MISSING, _p(out)))
+        return out
