@@ -304,14 +304,15 @@ __global__ void k_tile_reduce(const double *D, uint32_t n, uint32_t ntiles, doub
 }
 
 // one block per row: exclusive scan of the tile sums (in place)
-__global__ void k_agg_scan(double *agg, uint32_t ntiles) {
-    typedef cub::BlockScan<double, 1024> BS;
+constexpr int AGG_TB = 512;
+__global__ void __launch_bounds__(AGG_TB) k_agg_scan(double *agg, uint32_t ntiles) {
+    typedef cub::BlockScan<double, AGG_TB> BS;
     __shared__ typename BS::TempStorage tmp;
     __shared__ double carry;
     double *row = agg + (size_t) blockIdx.x * ntiles;
     if (threadIdx.x == 0) carry = 0.0;
     __syncthreads();
-    for (uint32_t base = 0; base < ntiles; base += 1024) {
+    for (uint32_t base = 0; base < ntiles; base += AGG_TB) {
         uint32_t i = base + threadIdx.x;
         double v = i < ntiles ? row[i] : 0.0;
         double ex, total;
@@ -556,7 +557,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
             uint32_t ntiles = (nev + SCAN_TILE - 1) / SCAN_TILE;
             double *agg = A.get<double>((size_t) M * ntiles);
             k_tile_reduce<<<dim3(ntiles, M), TB, 0, s>>>(D, nev, ntiles, agg);
-            k_agg_scan<<<M, 1024, 0, s>>>(agg, ntiles);
+            k_agg_scan<<<M, AGG_TB, 0, s>>>(agg, ntiles);
             k_tile_scan<<<dim3(ntiles, M), TB, 0, s>>>(D, nev, ntiles, agg);
             TSKB_CK_LAUNCH();
             L.n += 3;

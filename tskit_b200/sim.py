@@ -32,3 +32,40 @@ def add_mutations(t: Tables, target, seed=1):
     t.mutations_derived_state = np.full(S, ord("1"), dtype=np.int8)
     t.mutations_derived_state_offset = np.arange(S + 1, dtype=np.uint64)
     return t
+
+
+def wright_fisher(n, generations, L, ncross=1, seed=42):
+    """Seeded haploid Wright-Fisher ARG of `n` samples (population size n,
+    `generations` generations, `ncross` crossovers per meiosis at integer
+    positions in [1, L-1]), already simplified; see csrc/wfsim.cpp."""
+    import ctypes as C
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtskb_sim.so")
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: run `make -C tskit_b200/csrc`")
+    lib = C.CDLL(path)
+    lib.tskb_wfsim_run.restype = C.c_void_p
+    lib.tskb_wfsim_run.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_uint32, C.c_uint64]
+    lib.tskb_wfsim_sizes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.tskb_wfsim_copy.argtypes = [C.c_void_p] * 9
+    lib.tskb_wfsim_free.argtypes = [C.c_void_p]
+    h = lib.tskb_wfsim_run(n, generations, float(L), ncross, seed)
+    try:
+        N, E = C.c_uint64(), C.c_uint64()
+        lib.tskb_wfsim_sizes(h, C.byref(N), C.byref(E))
+        N, E = N.value, E.value
+        flags = np.empty(N, dtype=np.uint32)
+        time = np.empty(N, dtype=np.float64)
+        left = np.empty(E, dtype=np.float64)
+        right = np.empty(E, dtype=np.float64)
+        parent = np.empty(E, dtype=np.int32)
+        child = np.empty(E, dtype=np.int32)
+        ins = np.empty(E, dtype=np.int32)
+        rem = np.empty(E, dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        lib.tskb_wfsim_copy(h, p(flags), p(time), p(left), p(right), p(parent), p(child),
+                            p(ins), p(rem))
+    finally:
+        lib.tskb_wfsim_free(h)
+    return Tables(float(L), flags, time, left, right, parent, child,
+                  edge_insertion_order=ins, edge_removal_order=rem)
