@@ -1,0 +1,180 @@
+"""ctypes binding of oracle/stats_oracle.c (the plain-C restatement).  TEST
+INFRASTRUCTURE ONLY -- see the header of stats_oracle.c."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "stats_oracle.c")
+_OUT = os.path.join(_HERE, "_build", "liboracle.so")
+
+STAT_IDS = {"diversity": 0, "segregating_sites": 1, "Y1": 2, "divergence": 3, "Y2": 4,
+            "f2": 5, "genetic_relatedness": 6, "Y3": 7, "f3": 8, "f4": 9}
+TUPLE = {"divergence": 2, "Y2": 2, "f2": 2, "genetic_relatedness": 2, "Y3": 3, "f3": 3,
+         "f4": 4}
+SUMMARY_FUNC = C.CFUNCTYPE(C.c_int, C.c_uint64, C.POINTER(C.c_double), C.c_uint64,
+                           C.POINTER(C.c_double), C.c_void_p)
+
+
+def build(force=False):
+    if force or not os.path.exists(_OUT) or os.path.getmtime(_OUT) < os.path.getmtime(_SRC):
+        os.makedirs(os.path.dirname(_OUT), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-std=c99", "-Wall", "-shared", "-fPIC", _SRC,
+                               "-lm", "-o", _OUT])
+    return _OUT
+
+
+class OrcTables(C.Structure):
+    _fields_ = [
+        ("sequence_length", C.c_double), ("time_uncalibrated", C.c_int32),
+        ("num_nodes", C.c_uint64), ("node_flags", C.c_void_p), ("node_time", C.c_void_p),
+        ("num_edges", C.c_uint64), ("edge_left", C.c_void_p), ("edge_right", C.c_void_p),
+        ("edge_parent", C.c_void_p), ("edge_child", C.c_void_p),
+        ("edge_insertion_order", C.c_void_p), ("edge_removal_order", C.c_void_p),
+        ("num_sites", C.c_uint64), ("site_position", C.c_void_p),
+        ("site_ancestral_state", C.c_void_p), ("site_ancestral_state_offset", C.c_void_p),
+        ("num_mutations", C.c_uint64), ("mutation_site", C.c_void_p),
+        ("mutation_node", C.c_void_p), ("mutation_parent", C.c_void_p),
+        ("mutation_derived_state", C.c_void_p), ("mutation_derived_state_offset", C.c_void_p)]
+
+
+class OracleError(Exception):
+    def __init__(self, code):
+        self.code = code
+        super().__init__(f"oracle error {code}")
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _flags(mode, span_normalise=True, polarised=False, centre=True):
+    f = {"site": 1, "branch": 2, "node": 4, None: 1}[mode]
+    if span_normalise:
+        f |= 1 << 11
+    if polarised:
+        f |= 1 << 10
+    if not centre:
+        f |= 1 << 14
+    return f
+
+
+class Oracle:
+    def __init__(self, tables):
+        self.lib = C.CDLL(build())
+        tables.ensure_derived()
+        self.t = tables
+        o = OrcTables()
+        o.sequence_length = tables.sequence_length
+        o.time_uncalibrated = int(tables.time_uncalibrated)
+        o.num_nodes, o.node_flags, o.node_time = tables.num_nodes, _p(tables.nodes_flags), _p(tables.nodes_time)
+        o.num_edges = tables.num_edges
+        o.edge_left, o.edge_right = _p(tables.edges_left), _p(tables.edges_right)
+        o.edge_parent, o.edge_child = _p(tables.edges_parent), _p(tables.edges_child)
+        o.edge_insertion_order = _p(tables.edge_insertion_order)
+        o.edge_removal_order = _p(tables.edge_removal_order)
+        o.num_sites, o.site_position = tables.num_sites, _p(tables.sites_position)
+        o.site_ancestral_state = _p(tables.sites_ancestral_state)
+        o.site_ancestral_state_offset = _p(tables.sites_ancestral_state_offset)
+        o.num_mutations = tables.num_mutations
+        o.mutation_site, o.mutation_node = _p(tables.mutations_site), _p(tables.mutations_node)
+        o.mutation_parent = _p(tables.mutations_parent)
+        o.mutation_derived_state = _p(tables.mutations_derived_state)
+        o.mutation_derived_state_offset = _p(tables.mutations_derived_state_offset)
+        self.o = o
+
+    def _windows(self, windows):
+        if windows is None:
+            windows = [0.0, self.t.sequence_length]
+        return np.ascontiguousarray(windows, dtype=np.float64)
+
+    @staticmethod
+    def _sets(sample_sets):
+        sizes = np.array([len(s) for s in sample_sets], dtype=np.uint64)
+        flat = (np.concatenate([np.asarray(s, dtype=np.int32) for s in sample_sets])
+                if len(sample_sets) else np.zeros(0, dtype=np.int32))
+        return sizes, np.ascontiguousarray(flat, dtype=np.int32)
+
+    def stat(self, name, sample_sets, indexes=None, windows=None, mode="site",
+             span_normalise=True, polarised=False, centre=True):
+        sizes, flat = self._sets(sample_sets)
+        w = self._windows(windows)
+        if name in TUPLE:
+            idx = np.ascontiguousarray(indexes, dtype=np.int32).reshape(-1, TUPLE[name])
+            M = len(idx)
+        else:
+            idx, M = None, len(sizes)
+        res = np.empty((len(w) - 1, max(M, 1)), dtype=np.float64)
+        ret = self.lib.orc_sample_count_stat(
+            C.byref(self.o), C.c_int(STAT_IDS[name]), C.c_uint64(len(sizes)), _p(sizes),
+            _p(flat), C.c_uint64(0 if idx is None else len(idx)), _p(idx),
+            C.c_uint64(len(w) - 1), _p(w),
+            C.c_uint32(_flags(mode, span_normalise, polarised, centre)), _p(res))
+        if ret != 0:
+            raise OracleError(ret)
+        return res[:, :M]
+
+    def general_stat(self, weights, f, output_dim, windows=None, mode="site",
+                     span_normalise=True, polarised=False):
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        w = self._windows(windows)
+        res = np.empty((len(w) - 1, output_dim), dtype=np.float64)
+
+        def tramp(k, state, m, result, params):
+            y = np.asarray(f(np.ctypeslib.as_array(state, shape=(k,)).copy()), dtype=np.float64)
+            for j in range(m):
+                result[j] = y[j]
+            return 0
+
+        cb = SUMMARY_FUNC(tramp)
+        ret = self.lib.orc_general_stat(
+            C.byref(self.o), C.c_uint64(weights.shape[1]), _p(weights), C.c_uint64(output_dim),
+            cb, None, C.c_uint64(len(w) - 1), _p(w),
+            C.c_uint32(_flags(mode, span_normalise, polarised)), _p(res))
+        if ret != 0:
+            raise OracleError(ret)
+        return res
+
+    def trees_at(self, positions, tracked=None):
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        order = np.argsort(pos, kind="stable")
+        N = self.t.num_nodes
+        par = np.empty((len(pos), N), dtype=np.int32)
+        cnt = np.empty((len(pos), N), dtype=np.int32)
+        tr = None if tracked is None else np.ascontiguousarray(tracked, dtype=np.int32)
+        sp = np.ascontiguousarray(pos[order])
+        ret = self.lib.orc_trees_at(C.byref(self.o), C.c_uint64(len(pos)), _p(sp), _p(tr),
+                                    C.c_uint64(0 if tr is None else len(tr)), _p(par), _p(cnt))
+        if ret != 0:
+            raise OracleError(ret)
+        inv = np.empty_like(order)
+        inv[order] = np.arange(len(order))
+        return par[inv], cnt[inv]
+
+    def genotype_matrix(self, samples=None, isolated_as_missing=True):
+        s = self.t.samples if samples is None else np.ascontiguousarray(samples, dtype=np.int32)
+        out = np.empty((self.t.num_sites, len(s)), dtype=np.int32)
+        ret = self.lib.orc_genotype_matrix(C.byref(self.o), _p(s), C.c_uint64(len(s)),
+                                           C.c_uint32(0 if isolated_as_missing else 2), _p(out))
+        if ret != 0:
+            raise OracleError(ret)
+        return out
+
+    def divergence_matrix(self, sample_sets=None, windows=None, mode="site",
+                          span_normalise=True):
+        w = self._windows(windows)
+        if sample_sets is None:
+            sizes = flat = None
+            n = self.t.num_samples
+        else:
+            sizes, flat = self._sets(sample_sets)
+            n = len(sizes)
+        res = np.empty((len(w) - 1, n, n), dtype=np.float64)
+        ret = self.lib.orc_divergence_matrix(
+            C.byref(self.o), C.c_uint64(n), _p(sizes), _p(flat), C.c_uint64(len(w) - 1), _p(w),
+            C.c_uint32(_flags(mode, span_normalise)), _p(res))
+        if ret != 0:
+            raise OracleError(ret)
+        return res
