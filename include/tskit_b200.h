@@ -194,9 +194,9 @@ int tskb_treeseq_stat_device(const tskb_treeseq_t *self, int stat_id,
     uint64_t num_windows, const double *windows, uint32_t options, double *d_result);
 
 /* Debug/test access to plan arrays (copied to host). name in: "ev_pos",
- * "ev_child", "ev_sign", "ev_src", "voff", "em_node", "em_perm", "em_bl",
+ * "ev_child", "ev_sign", "voff", "bp_pos", "bp_end", "em_idx", "em_bl",
  * "nm_src", "nm_flag", "nm_key", "level", "rank_node", "level_begin",
- * "mut_src".  Returns the element count, or <0 on error; copies at most
+ * "mut_src", "mut_allele", "mut_alt".  Returns the element count, or <0 on error; copies at most
  * max_bytes. */
 int64_t tskb_treeseq_debug_array(const tskb_treeseq_t *self, const char *name, void *out,
     uint64_t max_bytes);

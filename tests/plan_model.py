@@ -69,59 +69,82 @@ def build(t, a=None, b=None):
             u = v
         voff.append(len(em_node))
     voff = np.array(voff, dtype=np.uint32)
-    em_node = np.array(em_node, dtype=np.int32)
-    em_bl = np.array(em_bl, dtype=np.float64)
-    em_ev = np.array(em_ev, dtype=np.int64)
-    V = len(em_node)
+    vis_node = np.array(em_node, dtype=np.int64)
+    vis_bl = np.array(em_bl, dtype=np.float64)
+    vis_ev = np.array(em_ev, dtype=np.int64)
+    V = len(vis_node)
     level = np.zeros(N, dtype=np.uint32)
-    o = np.lexsort((ec, ep, tm[ep]))
-    for p, c in zip(ep[o].tolist(), ec[o].tolist()):
-        if level[c] + 1 > level[p]:
-            level[p] = level[c] + 1
-    # longest-path levels need children final first: iterate to a fixed point
     changed = True
     while changed:
         nl = level.copy()
-        np.maximum.at(nl, ep, level[ec] + 1)
+        if E:
+            np.maximum.at(nl, ep, level[ec] + 1)
         changed = not np.array_equal(nl, level)
         level = nl
     rank_node = np.lexsort((np.arange(N), level)).astype(np.int32)
     rank = np.empty(N, dtype=np.int64)
     rank[rank_node] = np.arange(N)
-    key = rank[em_node] if V else np.zeros(0, dtype=np.int64)
-    nm_em = np.argsort(key, kind="stable")
-    em_perm = np.empty(V, dtype=np.uint32)
-    em_perm[nm_em] = np.arange(V)
-    nm_key = key[nm_em].astype(np.uint32)
-    nm_ev = em_ev[nm_em]
-    noff = np.searchsorted(nm_key, np.arange(N + 1))
-    ev_src = np.empty(nev, dtype=np.int32)
-    for i in range(nev):
-        c = int(ev_child[i])
-        lo, hi = noff[rank[c]], noff[rank[c] + 1]
-        k = np.searchsorted(nm_ev[lo:hi], i, side="left")
-        ev_src[i] = lo + k - 1 if k > 0 else ~c
-    nm_src = ev_src[nm_ev] if V else np.zeros(0, dtype=np.int32)
-    head = np.ones(V, dtype=bool)
-    head[1:] = nm_key[1:] != nm_key[:-1]
-    nm_flag = ((ev_sign[nm_ev] < 0).astype(np.uint8) | (head.astype(np.uint8) << 1)) if V \
-        else np.zeros(0, dtype=np.uint8)
+    key = rank[vis_node] if V else np.zeros(0, dtype=np.int64)
+    sorted_vis = np.argsort(key, kind="stable")
+    sorted_key = key[sorted_vis]
+    sorted_ev = vis_ev[sorted_vis]
+    noff = np.searchsorted(sorted_key, np.arange(N + 1))
+    vis_nm = np.empty(V, dtype=np.int64)
+    vis_nm[sorted_vis] = np.arange(V) + sorted_key + 1
+
+    def state_entry(u, i):
+        r = rank[u]
+        lo, hi = noff[r], noff[r + 1]
+        k = np.searchsorted(sorted_ev[lo:hi], i, side="left")
+        return lo + k + r
+
+    ev_src = np.array([state_entry(int(ev_child[i]), i) for i in range(nev)], dtype=np.int64)
+    Vn, Ve = V + N, V + nev
+    nm_src = np.zeros(Vn, dtype=np.int32)
+    nm_flag = np.zeros(Vn, dtype=np.uint8)
+    nm_key = np.zeros(Vn, dtype=np.uint32)
+    idx = np.arange(V) + sorted_key + 1
+    nm_src[idx] = ev_src[sorted_ev]
+    nm_flag[idx] = (ev_sign[sorted_ev] < 0).astype(np.uint8)
+    nm_key[idx] = sorted_key
+    init = noff[:N] + np.arange(N)
+    nm_src[init] = rank_node
+    nm_flag[init] = 2
+    nm_key[init] = np.arange(N)
+    em_idx = np.zeros(Ve, dtype=np.uint32)
+    em_bl2 = np.zeros(Ve, dtype=np.float64)
+    eoff = voff[:-1].astype(np.int64) + np.arange(nev)
+    em_idx[eoff] = ev_src.astype(np.uint32) | np.uint32(0x80000000)
+    em_bl2[eoff] = ev_sbl
+    epos = np.arange(V) + vis_ev + 1
+    em_idx[epos] = vis_nm
+    em_bl2[epos] = vis_bl
+    flag = np.ones(nev, dtype=bool)
+    flag[:-1] = ev_pos[:-1] != ev_pos[1:]
+    bp_pos = ev_pos[flag]
+    bp_end = (voff[1:].astype(np.int64) + np.arange(nev) + 1)[flag].astype(np.uint32)
     nlevels = int(level.max()) + 1 if N else 1
     lvl_sorted = level[rank_node]
     lro = np.searchsorted(lvl_sorted, np.arange(nlevels + 1))
-    level_begin = noff[lro].astype(np.uint32)
-    return dict(ev_pos=ev_pos, ev_child=ev_child.astype(np.int32), ev_sign=ev_sign,
-                ev_sbl=ev_sbl, ev_src=ev_src, voff=voff, em_node=em_node, em_perm=em_perm,
-                em_bl=em_bl, nm_src=nm_src.astype(np.int32), nm_flag=nm_flag, nm_key=nm_key,
-                level=level, rank_node=rank_node, level_begin=level_begin)
+    level_begin = (noff[lro] + lro).astype(np.uint32)
+    # sites
+    mut_src = np.zeros(t.num_mutations, dtype=np.int32)
+    for m in range(t.num_mutations):
+        x = t.sites_position[t.mutations_site[m]]
+        e_hi = np.searchsorted(ev_pos, x, side="right")
+        mut_src[m] = state_entry(int(t.mutations_node[m]), e_hi)
+    return dict(ev_pos=ev_pos, ev_child=ev_child.astype(np.int32), ev_sign=ev_sign, voff=voff,
+                bp_pos=bp_pos, bp_end=bp_end, em_idx=em_idx, em_bl=em_bl2, nm_src=nm_src,
+                nm_flag=nm_flag, nm_key=nm_key, level=level, rank_node=rank_node,
+                level_begin=level_begin, mut_src=mut_src)
 
 
-DTYPES = dict(ev_pos=np.float64, ev_child=np.int32, ev_sign=np.int8, ev_sbl=np.float64,
-              ev_src=np.int32, voff=np.uint32, em_node=np.int32, em_perm=np.uint32,
-              em_bl=np.float64, nm_src=np.int32, nm_flag=np.uint8, nm_key=np.uint32,
-              level=np.uint32, rank_node=np.int32, level_begin=np.uint32)
-ORDER = ["ev_pos", "ev_child", "ev_sign", "ev_sbl", "voff", "em_node", "em_bl", "level",
-         "rank_node", "nm_key", "em_perm", "level_begin", "ev_src", "nm_src", "nm_flag"]
+DTYPES = dict(ev_pos=np.float64, ev_child=np.int32, ev_sign=np.int8, voff=np.uint32,
+              bp_pos=np.float64, bp_end=np.uint32, em_idx=np.uint32, em_bl=np.float64,
+              nm_src=np.int32, nm_flag=np.uint8, nm_key=np.uint32, level=np.uint32,
+              rank_node=np.int32, level_begin=np.uint32, mut_src=np.int32)
+ORDER = ["ev_pos", "ev_child", "ev_sign", "voff", "bp_pos", "bp_end", "level", "rank_node",
+         "level_begin", "nm_key", "nm_flag", "nm_src", "em_idx", "em_bl", "mut_src"]
 
 
 def compare(ll, t, a=None, b=None):

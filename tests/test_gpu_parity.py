@@ -1,0 +1,290 @@
+"""GPU suite (run on the B200 box): the CUDA path, called through the C ABI, against the
+oracle on identical inputs.  Integer outputs bit-exact; fp64 statistics within rtol 1e-9
+(north_star), with an absolute floor of 1e-9 x the largest magnitude in the result for
+statistics that are differences of large terms (f2/f3/f4, relatedness)."""
+import numpy as np
+import pytest
+
+from oracle import port, ref
+from tests import fixtures as fx
+from tests import plan_model
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+ONE_WAY = ["diversity", "segregating_sites", "Y1"]
+K_WAY = {"divergence": [[0, 1], [1, 2], [0, 0]], "Y2": [[0, 1], [2, 1]], "f2": [[0, 1], [0, 2]],
+         "genetic_relatedness": [[0, 1], [2, 2]], "Y3": [[0, 1, 2]], "f3": [[0, 1, 2], [2, 1, 0]],
+         "f4": [[0, 1, 2, 0]]}
+
+
+def close(got, want, cancelling=False):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    atol = RTOL * np.nanmax(np.abs(want), initial=0.0) if cancelling else 0.0
+    return np.allclose(got, want, rtol=RTOL, atol=atol, equal_nan=True)
+
+
+def sets_args(sets):
+    sizes = np.array([len(x) for x in sets], dtype=np.uint64)
+    flat = np.concatenate([np.asarray(x, dtype=np.int32) for x in sets])
+    return sizes, flat
+
+
+@pytest.fixture(scope="module")
+def engines(wf_small):
+    from tskit_b200.lowlevel import LLTreeSequence
+    return LLTreeSequence(wf_small), port.Oracle(wf_small)
+
+
+def test_plan_matches_model(wf_small, engines):
+    assert plan_model.compare(engines[0], wf_small) == []
+
+
+def test_plan_matches_model_clipped(wf_small):
+    from tskit_b200.lowlevel import LLTreeSequence
+    ll = LLTreeSequence(wf_small, genome_range=(30000.0, 70000.0))
+    assert plan_model.compare(ll, wf_small, 30000.0, 70000.0) == []
+
+
+@pytest.mark.parametrize("mode", ["branch", "site"])
+@pytest.mark.parametrize("polarised", [False, True])
+def test_all_statistics_wright_fisher(wf_small, engines, mode, polarised):
+    ll, o = engines
+    s = wf_small.samples
+    sets = [s[:50], s[50:120], s[120:]]
+    sizes, flat = sets_args(sets)
+    for windows in (np.array([0.0, wf_small.sequence_length]),
+                    np.linspace(0, wf_small.sequence_length, 8),
+                    np.array([0.0, 10.5, 11.0, 50000.25, wf_small.sequence_length])):
+        for name in ONE_WAY:
+            got = getattr(ll, name)(sizes, flat, windows=windows, mode=mode, polarised=polarised)
+            want = o.stat(name, sets, windows=windows, mode=mode, polarised=polarised)
+            assert close(got, want), (name, mode)
+        for name, idx in K_WAY.items():
+            got = getattr(ll, name)(sizes, flat, np.array(idx, dtype=np.int32), windows=windows,
+                                    mode=mode, polarised=polarised)
+            want = o.stat(name, sets, idx, windows=windows, mode=mode, polarised=polarised)
+            assert close(got, want, cancelling=True), (name, mode)
+        got = ll.genetic_relatedness(sizes, flat, np.array([[0, 1]], dtype=np.int32),
+                                     windows=windows, mode=mode, polarised=polarised, centre=False)
+        want = o.stat("genetic_relatedness", sets, [[0, 1]], windows=windows, mode=mode,
+                      polarised=polarised, centre=False)
+        assert close(got, want, cancelling=True)
+
+
+@pytest.mark.parametrize("mode", ["branch", "site"])
+def test_span_normalise_off_and_many_windows(wf_small, engines, mode):
+    ll, o = engines
+    s = wf_small.samples
+    sizes, flat = sets_args([s])
+    windows = np.linspace(0, wf_small.sequence_length, 20001)  # windows far smaller than trees
+    got = ll.diversity(sizes, flat, windows=windows, mode=mode, span_normalise=False)
+    want = o.stat("diversity", [s], windows=windows, mode=mode, span_normalise=False)
+    assert close(got, want)
+
+
+def test_overlapping_sample_sets_and_eight_sets(wf_small, engines):
+    ll, o = engines
+    s = wf_small.samples
+    sets = [s[i * 20:(i + 2) * 20] for i in range(8)]  # a sample may be in several sets
+    sizes, flat = sets_args(sets)
+    idx = np.array([(i, j) for i in range(8) for j in range(i, 8)], dtype=np.int32)
+    for mode in ("branch", "site"):
+        assert close(ll.divergence(sizes, flat, idx, mode=mode, windows=[0, 1e5]),
+                     o.stat("divergence", sets, idx, mode=mode))
+        assert close(ll.f2(sizes, flat, idx, mode=mode, windows=[0, 1e5]),
+                     o.stat("f2", sets, idx, mode=mode), cancelling=True)
+
+
+@pytest.mark.parametrize("name", list(fx.ALL))
+def test_reference_fixtures(name):
+    from tskit_b200.lowlevel import LLTreeSequence
+    t = fx.load(name)
+    ll, o = LLTreeSequence(t), port.Oracle(t)
+    assert plan_model.compare(ll, t) == []
+    s = t.samples
+    sets = [s[:1], s[1:2], s[2:]]
+    sizes, flat = sets_args(sets)
+    L = t.sequence_length
+    for windows in (np.array([0.0, L]), np.array([0.0, L / 3, L])):
+        for mode in ("branch", "site"):
+            for pol in (False, True):
+                for nm in ONE_WAY:
+                    got = getattr(ll, nm)(sizes, flat, windows=windows, mode=mode, polarised=pol)
+                    want = o.stat(nm, sets, windows=windows, mode=mode, polarised=pol)
+                    assert close(got, want, cancelling=True), (nm, mode, pol)
+                for nm, idx in K_WAY.items():
+                    got = getattr(ll, nm)(sizes, flat, np.array(idx, dtype=np.int32),
+                                          windows=windows, mode=mode, polarised=pol)
+                    want = o.stat(nm, sets, idx, windows=windows, mode=mode, polarised=pol)
+                    assert close(got, want, cancelling=True), (nm, mode, pol)
+    if t.num_edges:
+        q = np.array([0.0, L / 2, L * 0.99])
+        gp, gc = ll.trees_at(q)
+        op, oc = o.trees_at(q)
+        assert np.array_equal(gp, op) and np.array_equal(gc, oc)
+
+
+def test_golden_values():
+    from tskit_b200.lowlevel import LLTreeSequence
+    ll = LLTreeSequence(fx.load("paper"))
+    sizes, flat = sets_args([[0, 1, 2, 3]])
+    pi = ll.diversity(sizes, flat, windows=[0, 10], mode="site", span_normalise=False)
+    assert abs(pi[0, 0] - fx.PAPER_SITE_DIVERSITY) < 1e-9
+    sizes, flat = sets_args([[0]])
+    assert np.isnan(ll.diversity(sizes, flat, windows=[0, 10], mode="site")[0, 0])
+    assert np.isnan(ll.diversity(sizes, flat, windows=[0, 10], mode="branch")[0, 0])
+    ll = LLTreeSequence(fx.load("four_taxa"))
+    sizes, flat = sets_args([[0], [1], [2], [3]])
+    idx = np.array([[0, 1, 2, 3]], dtype=np.int32)
+    got = ll.f4(sizes, flat, idx, windows=fx.FOUR_TAXA_WINDOWS, mode="branch")[:, 0]
+    assert np.allclose(got, fx.FOUR_TAXA_F4_0123_WINDOWED, atol=1e-12)
+    sizes, flat = sets_args([[0, 1, 2, 3]])
+    got = ll.diversity(sizes, flat, windows=fx.FOUR_TAXA_WINDOWS, mode="branch")[:, 0]
+    assert np.allclose(got, fx.FOUR_TAXA_DIVERSITY_WINDOWED, atol=1e-12)
+    ll = LLTreeSequence(fx.load("case_1"))
+    for (i, j), v in fx.CASE_1_BRANCH_DIVERGENCE.items():
+        sizes, flat = sets_args([[i], [j]])
+        got = ll.divergence(sizes, flat, np.array([[0, 1]], dtype=np.int32), windows=[0, 1.0],
+                            mode="branch")
+        assert abs(got[0, 0] - v) < 1e-12
+
+
+def test_error_codes_and_precedence(wf_small, engines):
+    from tskit_b200.lowlevel import LibraryError
+    ll, _ = engines
+    L = wf_small.sequence_length
+    s = wf_small.samples
+    internal = int(np.nonzero((wf_small.nodes_flags & 1) == 0)[0][0])
+
+    def code(fn):
+        with pytest.raises(LibraryError) as e:
+            fn()
+        return e.value.code
+
+    u64 = lambda *a: np.array(a, dtype=np.uint64)  # noqa: E731
+    i32 = lambda *a: np.array(a, dtype=np.int32)  # noqa: E731
+    w = [0, L]
+    assert code(lambda: ll.diversity(u64(), i32(), windows=w)) == -905
+    assert code(lambda: ll.diversity(u64(1, 0), i32(0), windows=w)) == -908
+    assert code(lambda: ll.diversity(u64(2), i32(0, 0), windows=w)) == -600
+    assert code(lambda: ll.diversity(u64(1), i32(10 ** 6), windows=w)) == -202
+    assert code(lambda: ll.diversity(u64(1), i32(internal), windows=w)) == -601
+    assert code(lambda: ll.diversity(u64(1), i32(0), windows=[0, L / 2])) == -901
+    assert code(lambda: ll.diversity(u64(1), i32(0), windows=[0, L, L / 2])) == -901
+    assert code(lambda: ll.diversity(u64(1), i32(0), windows=[1, L])) == -901
+    assert code(lambda: ll.divergence(u64(1, 1), i32(0, 1), [[0, 2]], windows=w)) == -907
+    # index tuples are checked before sample sets, sample sets before windows
+    assert code(lambda: ll.divergence(u64(1, 0), i32(0), [[0, 5]], windows=[0, 1])) == -907
+    assert code(lambda: ll.diversity(u64(2), i32(0, 0), windows=[0, 1])) == -600
+    assert code(lambda: ll.diversity(u64(1), i32(0), windows=w, mode="node")) == -20003
+    with pytest.raises(ValueError):
+        ll.diversity(u64(1), i32(0), windows=w, mode="bogus")
+    with pytest.raises(ValueError):
+        ll.diversity(u64(2), i32(0), windows=w)
+    with pytest.raises(ValueError):
+        ll.diversity(u64(1), i32(0), windows=[0.0])
+    # a same-sample-in-two-sets call is legal (trees.c:2201-2214)
+    assert ll.diversity(u64(2, 2), i32(s[0], s[1], s[0], s[2]), windows=w).shape == (1, 2)
+
+
+def test_time_uncalibrated():
+    from tskit_b200.lowlevel import LibraryError, LLTreeSequence
+    t = fx.load("paper")
+    t.time_uncalibrated = True
+    ll = LLTreeSequence(t)
+    sizes, flat = sets_args([[0, 1]])
+    with pytest.raises(LibraryError) as e:
+        ll.diversity(sizes, flat, windows=[0, 10], mode="branch")
+    assert e.value.code == -910
+    assert ll.diversity(sizes, flat, windows=[0, 10], mode="site").shape == (1, 1)
+
+
+def test_trees_at_every_breakpoint(wf_small, engines):
+    ll, o = engines
+    bp = np.unique(np.concatenate([wf_small.edges_left, wf_small.edges_right]))
+    q = bp[bp < wf_small.sequence_length][::7]
+    gp, gc = ll.trees_at(q)
+    op, oc = o.trees_at(q)
+    assert np.array_equal(gp, op)
+    assert np.array_equal(gc, oc)
+    tracked = wf_small.samples[::3]
+    gp, gc = ll.trees_at(q[:50], tracked=tracked)
+    op, oc = o.trees_at(q[:50], tracked=tracked)
+    assert np.array_equal(gp, op) and np.array_equal(gc, oc)
+
+
+def test_custom_summary_function_tabulated(wf_small, engines):
+    """sample_count_stat with a Python f (trees.py:8006-8106) through the device LUT."""
+    ll, o = engines
+    s = wf_small.samples
+    n = len(s)
+    W = np.ones((n, 1))
+
+    def f(x):
+        return np.array([x[0] * (n - x[0]) / (n * (n - 1)), float(x[0] > 0)])
+
+    windows = np.linspace(0, wf_small.sequence_length, 6)
+    for mode in ("branch", "site"):
+        for pol in (False, True):
+            got = ll.general_stat(W, f, 2, windows=windows, mode=mode, polarised=pol)
+            want = o.general_stat(W, f, 2, windows=windows, mode=mode, polarised=pol)
+            assert close(got, want), (mode, pol)
+    # equals the built-in diversity (up to the unpolarised double count)
+    sizes, flat = sets_args([s])
+    d = ll.diversity(sizes, flat, windows=windows, mode="branch")
+    g = ll.general_stat(W, f, 2, windows=windows, mode="branch")
+    assert np.allclose(g[:, 0], d[:, 0], rtol=1e-12)
+
+
+def test_library_scan_path_agrees(wf_small, monkeypatch):
+    """hand-written look-back propagation == cub::DeviceScan::InclusiveSumByKey path"""
+    from tskit_b200.lowlevel import LLTreeSequence
+    ll = LLTreeSequence(wf_small)
+    s = wf_small.samples
+    sizes, flat = sets_args([s[:90], s[90:]])
+    idx = np.array([[0, 1]], dtype=np.int32)
+    w = np.linspace(0, wf_small.sequence_length, 12)
+    a = ll.divergence(sizes, flat, idx, windows=w, mode="branch")
+    monkeypatch.setenv("TSKB_PROPAGATE", "cub")
+    b = ll.divergence(sizes, flat, idx, windows=w, mode="branch")
+    assert np.array_equal(a, b)
+
+
+def test_genome_range_shards_sum_to_whole(wf_small, engines):
+    """multi-GPU decomposition: shards over [a, b) computed independently add up per window"""
+    from tskit_b200.lowlevel import LLTreeSequence
+    ll, o = engines
+    s = wf_small.samples
+    sizes, flat = sets_args([s[:100], s[100:]])
+    idx = np.array([[0, 1]], dtype=np.int32)
+    L = wf_small.sequence_length
+    w = np.linspace(0, L, 10)
+    cuts = [0.0, 21000.5, w[4], 77777.0, L]  # inside windows and on a window edge
+    for mode in ("branch", "site"):
+        whole = ll.divergence(sizes, flat, idx, windows=w, mode=mode, span_normalise=False)
+        acc = np.zeros_like(whole)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            part = LLTreeSequence(wf_small, genome_range=(a, b))
+            acc += part.divergence(sizes, flat, idx, windows=w, mode=mode, span_normalise=False)
+        assert np.allclose(acc, whole, rtol=1e-11)
+        assert close(whole, o.stat("divergence", [s[:100], s[100:]], idx, windows=w, mode=mode,
+                                   span_normalise=False))
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+def test_against_compiled_reference_1k(wf_1k):
+    from tskit_b200.lowlevel import LLTreeSequence
+    ll, r = LLTreeSequence(wf_1k), ref.RefTreeSequence(wf_1k)
+    s = wf_1k.samples
+    sets = [s[:300], s[300:]]
+    sizes, flat = sets_args(sets)
+    w = np.linspace(0, wf_1k.sequence_length, 101)
+    for mode in ("branch", "site"):
+        assert close(ll.diversity(sizes, flat, windows=w, mode=mode),
+                     r.one_way("diversity", sets, windows=w, mode=mode))
+        assert close(ll.divergence(sizes, flat, np.array([[0, 1]], dtype=np.int32), windows=w,
+                                   mode=mode),
+                     r.k_way("divergence", sets, [[0, 1]], windows=w, mode=mode))

@@ -29,11 +29,10 @@ Plan::~Plan() {
 uint64_t Plan::device_bytes() const {
     return time.bytes() + d_samples.bytes() + coff.bytes() + csr_left.bytes() + csr_right.bytes()
            + csr_parent.bytes() + ev_pos.bytes() + ev_child.bytes() + ev_sign.bytes()
-           + ev_sbl.bytes() + ev_src.bytes() + voff.bytes() + em_node.bytes() + em_perm.bytes()
-           + em_bl.bytes() + nm_src.bytes() + nm_flag.bytes() + nm_key.bytes()
-           + rank_node.bytes() + level.bytes() + site_pos.bytes() + site_moff.bytes()
-           + site_aoff.bytes() + mut_node.bytes() + mut_src.bytes() + mut_allele.bytes()
-           + mut_alt.bytes();
+           + voff.bytes() + bp_pos.bytes() + bp_end.bytes() + em_idx.bytes() + em_bl.bytes()
+           + nm_src.bytes() + nm_flag.bytes() + nm_key.bytes() + rank_node.bytes()
+           + level.bytes() + site_pos.bytes() + site_moff.bytes() + site_aoff.bytes()
+           + mut_node.bytes() + mut_src.bytes() + mut_allele.bytes() + mut_alt.bytes();
 }
 
 namespace {
@@ -187,8 +186,8 @@ __global__ void k_chain_count(const int32_t *ev_parent, const double *ev_pos, ui
 
 __global__ void k_chain_fill(const int32_t *ev_parent, const double *ev_pos, uint32_t nev,
     double a, const uint32_t *coff, const double *csr_left, const double *csr_right,
-    const int32_t *csr_parent, const double *time, const uint32_t *voff, int32_t *em_node,
-    double *em_bl, uint32_t *em_ev) {
+    const int32_t *csr_parent, const double *time, const uint32_t *voff, int32_t *vis_node,
+    double *vis_bl, uint32_t *vis_ev) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nev) return;
     double x = ev_pos[i];
@@ -196,9 +195,9 @@ __global__ void k_chain_fill(const int32_t *ev_parent, const double *ev_pos, uin
     uint32_t j = voff[i], end = voff[i + 1];
     while (u != -1 && j < end) {
         int32_t v = span_parent(u, x, a, coff, csr_left, csr_right, csr_parent);
-        em_node[j] = u;
-        em_ev[j] = i;
-        em_bl[j] = v == -1 ? 0.0 : time[v] - time[u];
+        vis_node[j] = u;
+        vis_ev[j] = i;
+        vis_bl[j] = v == -1 ? 0.0 : time[v] - time[u];
         j++;
         u = v;
     }
@@ -221,60 +220,108 @@ __global__ void k_scatter_rank(const uint32_t *rank_node, uint32_t N, uint32_t *
     if (r < N) rank[rank_node[r]] = r;
 }
 
-__global__ void k_visit_keys(const int32_t *em_node, const uint32_t *rank, uint32_t V,
+__global__ void k_visit_keys(const int32_t *vis_node, const uint32_t *rank, uint32_t V,
     uint32_t *key) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < V) key[j] = rank[em_node[j]];
+    if (j < V) key[j] = rank[vis_node[j]];
 }
 
-__global__ void k_nm_finish(const uint32_t *nm_em, const uint32_t *em_ev, uint32_t V,
-    uint32_t *em_perm, uint32_t *nm_ev) {
+// Sorted position k (visits sorted by node rank, stable in event order) lives at nm index
+// k + rank + 1: every node's list is preceded by its INIT entry.
+__global__ void k_nm_finish(const uint32_t *sorted_vis, const uint32_t *sorted_key,
+    const uint32_t *vis_ev, uint32_t V, uint32_t *vis_nm, uint32_t *sorted_ev) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < V) {
-        uint32_t j = nm_em[k];
-        em_perm[j] = k;
-        nm_ev[k] = em_ev[j];
+        uint32_t j = sorted_vis[k];
+        vis_nm[j] = k + sorted_key[k] + 1;
+        sorted_ev[k] = vis_ev[j];
     }
 }
 
-// src of event i: the child's last visit strictly before event i (its state
-// at the moment the reference reads state[child], trees.c:1436/1462)
-__global__ void k_event_src(const int32_t *ev_child, uint32_t nev, const uint32_t *rank,
-    const uint32_t *noff, const uint32_t *nm_ev, int32_t *ev_src) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nev) return;
-    int32_t c = ev_child[i];
-    uint32_t r = rank[c];
+// nm entry holding state[u] just before event i (i = nev: after every event <= e_hi):
+// u's last visit among events < i, else u's INIT entry
+__device__ inline uint32_t state_entry(int32_t u, uint32_t i, const uint32_t *rank,
+    const uint32_t *noff, const uint32_t *sorted_ev) {
+    uint32_t r = rank[u];
     uint32_t lo = noff[r], hi = noff[r + 1];
-    uint32_t k = lower_bound_dev(nm_ev + lo, hi - lo, i);
-    ev_src[i] = k > 0 ? (int32_t) (lo + k - 1) : ~c;
+    uint32_t k = lower_bound_dev(sorted_ev + lo, hi - lo, i);
+    return lo + k + r;  // k == 0: the INIT entry at lo + r; else visit (lo + k - 1) + r + 1
 }
 
-__global__ void k_nm_src(const uint32_t *nm_ev, const uint32_t *nm_key, uint32_t V,
-    const int32_t *ev_src, const int8_t *ev_sign, int32_t *nm_src, uint8_t *nm_flag) {
+// src of event i: the state of its child at the moment the reference reads
+// state[child] (trees.c:1436/1462)
+__global__ void k_event_src(const int32_t *ev_child, uint32_t nev, const uint32_t *rank,
+    const uint32_t *noff, const uint32_t *sorted_ev, uint32_t *ev_src) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nev) ev_src[i] = state_entry(ev_child[i], i, rank, noff, sorted_ev);
+}
+
+__global__ void k_nm_fill_visits(const uint32_t *sorted_ev, const uint32_t *sorted_key,
+    uint32_t V, const uint32_t *ev_src, const int8_t *ev_sign, int32_t *nm_src,
+    uint8_t *nm_flag, uint32_t *nm_key) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= V) return;
-    uint32_t i = nm_ev[k];
-    nm_src[k] = ev_src[i];
-    uint8_t f = ev_sign[i] < 0 ? 1 : 0;
-    if (k == 0 || nm_key[k] != nm_key[k - 1]) f |= 2;
-    nm_flag[k] = f;
+    uint32_t i = sorted_ev[k], r = sorted_key[k];
+    uint32_t idx = k + r + 1;
+    nm_src[idx] = (int32_t) ev_src[i];
+    nm_flag[idx] = ev_sign[i] < 0 ? 1 : 0;
+    nm_key[idx] = r;
+}
+
+__global__ void k_nm_fill_init(const uint32_t *noff, const int32_t *rank_node, uint32_t N,
+    int32_t *nm_src, uint8_t *nm_flag, uint32_t *nm_key) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    uint32_t idx = noff[r] + r;
+    nm_src[idx] = rank_node[r];
+    nm_flag[idx] = 2;
+    nm_key[idx] = r;
+}
+
+constexpr uint32_t CHILD_BIT = 0x80000000u;
+
+__global__ void k_em_fill_child(const uint32_t *voff, const uint32_t *ev_src,
+    const double *ev_sbl, uint32_t nev, uint32_t *em_idx, double *em_bl) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nev) return;
+    uint32_t e = voff[i] + i;
+    em_idx[e] = ev_src[i] | CHILD_BIT;
+    em_bl[e] = ev_sbl[i];
+}
+
+__global__ void k_em_fill_visits(const uint32_t *vis_ev, const uint32_t *vis_nm,
+    const double *vis_bl, uint32_t V, uint32_t *em_idx, double *em_bl) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= V) return;
+    uint32_t e = j + vis_ev[j] + 1;
+    em_idx[e] = vis_nm[j];
+    em_bl[e] = vis_bl[j];
+}
+
+__global__ void k_bp_flags(const double *ev_pos, uint32_t nev, uint32_t *flag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nev) flag[i] = (i + 1 == nev || ev_pos[i] != ev_pos[i + 1]) ? 1u : 0u;
+}
+
+__global__ void k_bp_fill(const double *ev_pos, const uint32_t *flag, const uint32_t *slot,
+    const uint32_t *voff, uint32_t nev, double *bp_pos, uint32_t *bp_end) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nev && flag[i]) {
+        bp_pos[slot[i]] = ev_pos[i];
+        bp_end[slot[i]] = voff[i + 1] + i + 1;
+    }
 }
 
 // state[mutation.node] at the site's tree = value after the node's last visit
 // among events at positions <= site position (trees.c:1744-1763)
 __global__ void k_mut_src(const int32_t *mut_site, const int32_t *mut_node, uint32_t Mu,
     const double *site_pos, const double *ev_pos, uint32_t nev, const uint32_t *rank,
-    const uint32_t *noff, const uint32_t *nm_ev, int32_t *mut_src) {
+    const uint32_t *noff, const uint32_t *sorted_ev, int32_t *mut_src) {
     uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= Mu) return;
     double x = site_pos[mut_site[m]];
     uint32_t e_hi = upper_bound_dev(ev_pos, nev, x);
-    int32_t u = mut_node[m];
-    uint32_t r = rank[u];
-    uint32_t lo = noff[r], hi = noff[r + 1];
-    uint32_t k = lower_bound_dev(nm_ev + lo, hi - lo, e_hi);
-    mut_src[m] = k > 0 ? (int32_t) (lo + k - 1) : ~u;
+    mut_src[m] = (int32_t) state_entry(mut_node[m], e_hi, rank, noff, sorted_ev);
 }
 
 // ------------------------------------------------------------ CUB wrappers
@@ -403,6 +450,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     P.nev = nev;
 
     DevArray<int32_t> ev_parent;
+    DevArray<double> ev_sbl;
     {
         DevArray<int32_t> ins_edge, rem_edge;
         DevArray<double> ins_pos, rem_pos;
@@ -417,12 +465,12 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
                 rem_pos.p);
             TSKB_CK_LAUNCH();
         }
-        P.ev_pos.alloc(nev); P.ev_child.alloc(nev); P.ev_sign.alloc(nev); P.ev_sbl.alloc(nev);
+        P.ev_pos.alloc(nev); P.ev_child.alloc(nev); P.ev_sign.alloc(nev); ev_sbl.alloc(nev);
         ev_parent.alloc(nev);
         if (nev) {
             k_merge_events<<<grid_for(nev, TB), TB, 0, s>>>(ins_edge.p, ins_pos.p, n_ins,
                 rem_edge.p, rem_pos.p, n_rem, ep.p, ec.p, P.time.p, P.ev_pos.p, P.ev_child.p,
-                ev_parent.p, P.ev_sign.p, P.ev_sbl.p);
+                ev_parent.p, P.ev_sign.p, ev_sbl.p);
             TSKB_CK_LAUNCH();
         }
         TSKB_CK(cudaStreamSynchronize(s));
@@ -482,16 +530,47 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK(cudaStreamSynchronize(s));
     }
     P.V = V;
-    P.em_node.alloc(V); P.em_bl.alloc(V); P.em_perm.alloc(V);
-    DevArray<uint32_t> em_ev;
-    em_ev.alloc(V);
+    P.Vn = V + N;
+    P.Ve = V + nev;
+    if ((uint64_t) V + N >= 0x7fffffffull || (uint64_t) V + nev >= 0x7fffffffull) {
+        throw (int) TSKB_ERR_UNSUPPORTED;  // 31-bit entry indexes; shard the genome instead
+    }
+    DevArray<int32_t> vis_node;
+    DevArray<double> vis_bl;
+    DevArray<uint32_t> vis_ev;
+    vis_node.alloc(V); vis_bl.alloc(V); vis_ev.alloc(V);
     if (nev && V) {
         k_chain_fill<<<grid_for(nev, TB), TB, 0, s>>>(ev_parent.p, P.ev_pos.p, nev, a, P.coff.p,
-            P.csr_left.p, P.csr_right.p, P.csr_parent.p, P.time.p, P.voff.p, P.em_node.p,
-            P.em_bl.p, em_ev.p);
+            P.csr_left.p, P.csr_right.p, P.csr_parent.p, P.time.p, P.voff.p, vis_node.p,
+            vis_bl.p, vis_ev.p);
         TSKB_CK_LAUNCH();
     }
     ev_parent.release();
+
+    // ---- breakpoints: distinct event positions
+    {
+        DevArray<uint32_t> flag, slot;
+        flag.alloc(nev + 1); slot.alloc(nev + 1);
+        TSKB_CK(cudaMemsetAsync(flag.p, 0, (nev + 1) * sizeof(uint32_t), s));
+        if (nev) {
+            k_bp_flags<<<grid_for(nev, TB), TB, 0, s>>>(P.ev_pos.p, nev, flag.p);
+            TSKB_CK_LAUNCH();
+        }
+        size_t bytes = 0;
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.p, slot.p, nev + 1, s));
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(tmp.need(bytes), bytes, flag.p, slot.p, nev + 1, s));
+        uint32_t T = 0;
+        TSKB_CK(cudaMemcpyAsync(&T, slot.p + nev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        TSKB_CK(cudaStreamSynchronize(s));
+        P.T = T;
+        P.bp_pos.alloc(T); P.bp_end.alloc(T);
+        if (nev) {
+            k_bp_fill<<<grid_for(nev, TB), TB, 0, s>>>(P.ev_pos.p, flag.p, slot.p, P.voff.p, nev,
+                P.bp_pos.p, P.bp_end.p);
+            TSKB_CK_LAUNCH();
+        }
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
 
     // ---- dependency levels: level[parent] > level[child] over every edge
     P.level.alloc(N);
@@ -549,46 +628,70 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     }
 
     // ---- node-major order of the visits
-    P.nm_key.alloc(V); P.nm_src.alloc(V); P.nm_flag.alloc(V);
-    DevArray<uint32_t> nm_ev, noff;
-    nm_ev.alloc(V);
+    const uint32_t Vn = P.Vn, Ve = P.Ve;
+    P.nm_key.alloc(Vn); P.nm_src.alloc(Vn); P.nm_flag.alloc(Vn);
+    P.em_idx.alloc(Ve); P.em_bl.alloc(Ve);
+    DevArray<uint32_t> sorted_ev, noff, sorted_key, vis_nm;
+    sorted_ev.alloc(V); sorted_key.alloc(V); vis_nm.alloc(V);
     noff.alloc(N + 1);
     {
-        DevArray<uint32_t> kin, vin, nm_em;
-        kin.alloc(V); vin.alloc(V); nm_em.alloc(V);
+        DevArray<uint32_t> kin, vin, sorted_vis;
+        kin.alloc(V); vin.alloc(V); sorted_vis.alloc(V);
         if (V) {
-            k_visit_keys<<<grid_for(V, TB), TB, 0, s>>>(P.em_node.p, rank.p, V, kin.p);
+            k_visit_keys<<<grid_for(V, TB), TB, 0, s>>>(vis_node.p, rank.p, V, kin.p);
             k_iota<<<grid_for(V, TB), TB, 0, s>>>(vin.p, V);
             TSKB_CK_LAUNCH();
-            sort_pairs(tmp, kin.p, P.nm_key.p, vin.p, nm_em.p, V, (int) std::max(1u, ceil_log2(N)), s);
-            k_nm_finish<<<grid_for(V, TB), TB, 0, s>>>(nm_em.p, em_ev.p, V, P.em_perm.p, nm_ev.p);
+            sort_pairs(tmp, kin.p, sorted_key.p, vin.p, sorted_vis.p, V,
+                (int) std::max(1u, ceil_log2(N)), s);
+            k_nm_finish<<<grid_for(V, TB), TB, 0, s>>>(sorted_vis.p, sorted_key.p, vis_ev.p, V,
+                vis_nm.p, sorted_ev.p);
             TSKB_CK_LAUNCH();
         }
-        k_offsets<<<grid_for(N + 1, TB), TB, 0, s>>>(P.nm_key.p, V, N + 1, noff.p);
+        k_offsets<<<grid_for(N + 1, TB), TB, 0, s>>>(sorted_key.p, V, N + 1, noff.p);
         TSKB_CK_LAUNCH();
         TSKB_CK(cudaStreamSynchronize(s));
     }
-    em_ev.release();
+    vis_node.release();
     {
-        // level_begin[l] = noff[lvl_rank_off[l]]
+        // level_begin[l] = nm index of the first entry of level l
         std::vector<uint32_t> h_lro = lvl_rank_off.download(s);
         std::vector<uint32_t> h_noff = noff.download(s);
         P.level_begin.resize(P.nlevels + 1);
+        P.level_tile0.resize(P.nlevels + 1);
+        uint32_t tiles = 0;
         for (uint32_t l = 0; l <= P.nlevels; l++) {
-            P.level_begin[l] = h_noff[h_lro[l]];
+            P.level_begin[l] = h_noff[h_lro[l]] + h_lro[l];
         }
+        for (uint32_t l = 0; l < P.nlevels; l++) {
+            P.level_tile0[l] = tiles;
+            tiles += (P.level_begin[l + 1] - P.level_begin[l] + PROP_TILE - 1) / PROP_TILE;
+        }
+        P.level_tile0[P.nlevels] = tiles;
     }
-    P.ev_src.alloc(nev);
+    DevArray<uint32_t> ev_src;
+    ev_src.alloc(nev);
     if (nev) {
-        k_event_src<<<grid_for(nev, TB), TB, 0, s>>>(P.ev_child.p, nev, rank.p, noff.p, nm_ev.p,
-            P.ev_src.p);
+        k_event_src<<<grid_for(nev, TB), TB, 0, s>>>(P.ev_child.p, nev, rank.p, noff.p,
+            sorted_ev.p, ev_src.p);
+        TSKB_CK_LAUNCH();
+        k_em_fill_child<<<grid_for(nev, TB), TB, 0, s>>>(P.voff.p, ev_src.p, ev_sbl.p, nev,
+            P.em_idx.p, P.em_bl.p);
         TSKB_CK_LAUNCH();
     }
     if (V) {
-        k_nm_src<<<grid_for(V, TB), TB, 0, s>>>(nm_ev.p, P.nm_key.p, V, P.ev_src.p, P.ev_sign.p,
-            P.nm_src.p, P.nm_flag.p);
+        k_nm_fill_visits<<<grid_for(V, TB), TB, 0, s>>>(sorted_ev.p, sorted_key.p, V, ev_src.p,
+            P.ev_sign.p, P.nm_src.p, P.nm_flag.p, P.nm_key.p);
+        k_em_fill_visits<<<grid_for(V, TB), TB, 0, s>>>(vis_ev.p, vis_nm.p, vis_bl.p, V,
+            P.em_idx.p, P.em_bl.p);
         TSKB_CK_LAUNCH();
     }
+    if (N) {
+        k_nm_fill_init<<<grid_for(N, TB), TB, 0, s>>>(noff.p, P.rank_node.p, N, P.nm_src.p,
+            P.nm_flag.p, P.nm_key.p);
+        TSKB_CK_LAUNCH();
+    }
+    TSKB_CK(cudaStreamSynchronize(s));
+    ev_sbl.release(); vis_bl.release(); vis_ev.release(); vis_nm.release(); sorted_key.release();
 
     // ---- sites and mutations: allele strings -> small integer codes on the host
     // (replaces the memcmp loops of get_allele_weights, trees.c:1557-1596)
@@ -643,7 +746,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
             DevArray<int32_t> d_msite;
             d_msite.upload(t->mutation_site, Mu, s);
             k_mut_src<<<grid_for(Mu, TB), TB, 0, s>>>(d_msite.p, P.mut_node.p, Mu, P.site_pos.p,
-                P.ev_pos.p, nev, rank.p, noff.p, nm_ev.p, P.mut_src.p);
+                P.ev_pos.p, nev, rank.p, noff.p, sorted_ev.p, P.mut_src.p);
             TSKB_CK_LAUNCH();
             TSKB_CK(cudaStreamSynchronize(s));
         }

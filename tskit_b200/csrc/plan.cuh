@@ -23,8 +23,12 @@
 //                    over every edge) so that all lists of one level can be
 //                    prefix-summed in parallel once lower levels are done.
 //
-// "em" arrays are in event-major order (visits of event 0, of event 1, ...),
-// "nm" arrays are in node-major order (sorted by (level, node, event)).
+// "em" arrays are in event-major order: for event 0, 1, ... one CHILD entry (the
+// edge's own branch appearing/disappearing) followed by its visits bottom-up.
+// "nm" arrays are in node-major order, sorted by (level, node, event); every
+// node's list starts with an INIT entry holding its initial state (its sample
+// weight), so "state before a visit" is always the previous nm entry and a
+// child that was never visited still has an entry to point at.
 #pragma once
 
 #include <mutex>
@@ -34,6 +38,8 @@
 #include "common.cuh"
 
 namespace tskb {
+
+constexpr uint32_t PROP_TILE = 1024;  // nm entries per propagation tile
 
 struct Plan {
     int device = 0;
@@ -62,29 +68,34 @@ struct Plan {
     DevArray<uint32_t> coff;          // [N + 1]
     DevArray<double> csr_left, csr_right;
     DevArray<int32_t> csr_parent;
-    // --- events ---
+    // --- events (edge diffs) ---
     DevArray<double> ev_pos;          // [nev] breakpoint of the diff (clipped to the range)
     DevArray<int32_t> ev_child;       // [nev]
     DevArray<int8_t> ev_sign;         // [nev] -1 removal, +1 insertion
-    DevArray<double> ev_sbl;          // [nev] sign * (time[parent] - time[child])
-    DevArray<int32_t> ev_src;         // [nev] nm index of the child's last earlier visit, or ~child
-    DevArray<uint32_t> voff;          // [nev + 1] visit offsets (em order)
-    // --- visits, event-major ---
-    DevArray<int32_t> em_node;        // [V]
-    DevArray<uint32_t> em_perm;       // [V] em index -> nm index
-    DevArray<double> em_bl;           // [V] branch length above the visited node at that moment (0 at chain top)
-    // --- visits, node-major ---
-    DevArray<int32_t> nm_src;         // [V] ev_src of the visit's event
-    DevArray<uint8_t> nm_flag;        // [V] bit0: removal (negative addend), bit1: first visit of its node
-    DevArray<uint32_t> nm_key;        // [V] rank of the visited node
+    DevArray<uint32_t> voff;          // [nev + 1] visit offsets
+    // --- breakpoints (distinct event positions) ---
+    uint32_t T = 0;
+    DevArray<double> bp_pos;          // [T]
+    DevArray<uint32_t> bp_end;        // [T] one past the last em entry of the diffs at bp_pos[t]
+    // --- entries, event-major: Ve = nev + V ---
+    uint32_t Ve = 0;
+    DevArray<uint32_t> em_idx;        // [Ve] nm index of the entry's state; bit 31 set on CHILD entries
+    DevArray<double> em_bl;           // [Ve] CHILD: sign * (time[parent] - time[child]);
+                                      //      visit: branch length above the visited node then (0 at chain top)
+    // --- entries, node-major: Vn = V + N ---
+    uint32_t Vn = 0;
+    DevArray<int32_t> nm_src;         // [Vn] visit: nm index holding state[child of the diff]; INIT: node id
+    DevArray<uint8_t> nm_flag;        // [Vn] bit0: removal (negative addend), bit1: INIT entry (list head)
+    DevArray<uint32_t> nm_key;        // [Vn] rank of the node (kept for the library scan-by-key check path)
     DevArray<int32_t> rank_node;      // [N] rank -> node id (nodes sorted by (level, id))
     DevArray<uint32_t> level;         // [N]
+    std::vector<uint32_t> level_tile0;  // first look-back descriptor of each level, size nlevels + 1
     // --- sites ---
     DevArray<double> site_pos;        // [S]
     DevArray<uint32_t> site_moff;     // [S + 1] mutation CSR
     DevArray<uint32_t> site_aoff;     // [S + 1] allele-slot CSR
     DevArray<int32_t> mut_node;       // [Mu]
-    DevArray<int32_t> mut_src;        // [Mu] nm index holding state[mutation.node] at the site, or ~node
+    DevArray<int32_t> mut_src;        // [Mu] nm index holding state[mutation.node] at the site
     DevArray<uint16_t> mut_allele;    // [Mu] allele index of the derived state
     DevArray<uint16_t> mut_alt;       // [Mu] allele index the mutation's state is subtracted from
     std::vector<double> h_site_pos;

@@ -14,6 +14,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "plan.cuh"
 
@@ -46,56 +48,42 @@ struct SumP {
     uint32_t table_rows;
 };
 
-template <int KP>
-__device__ inline double pick(const double (&x)[KP], int i) {
-    double r = x[0];
-#pragma unroll
-    for (int k = 1; k < KP; k++) r = (i == k) ? x[k] : r;
-    return r;
-}
-__device__ inline double pickn(const SumP &P, int i) {
-    double r = P.n[0];
-#pragma unroll
-    for (int k = 1; k < 8; k++) r = (i == k) ? P.n[k] : r;
-    return r;
-}
-
 // The summary functions, in the reference's exact operation order
 // (c/tskit/trees.c:3934-3948, 4221-4264, 4690-4773, 4899-4959, 5177-5291).
-template <int KP>
-__device__ inline double f_eval(const SumP &P, const double (&x)[KP], int m) {
+// x: the K state values as doubles; P.n: sample set sizes.
+__device__ __forceinline__ double f_eval(const SumP &P, const double *x, int m) {
     switch (P.stat) {
         case STAT_DIVERSITY: {
-            double n = pickn(P, m), xm = pick<KP>(x, m);
+            double n = P.n[m], xm = x[m];
             return xm * (n - xm) / (n * (n - 1));
         }
         case STAT_SEGSITES: {
-            double n = pickn(P, m), xm = pick<KP>(x, m);
+            double n = P.n[m], xm = x[m];
             return (xm > 0) * (1 - xm / n);
         }
         case STAT_Y1: {
-            double ni = pickn(P, m), xi = pick<KP>(x, m);
+            double ni = P.n[m], xi = x[m];
             double denom = ni * (ni - 1) * (ni - 2);
             double numer = xi * (ni - xi) * (ni - xi - 1);
             return numer / denom;
         }
         case STAT_DIVERGENCE: {
             int i = P.idx[2 * m], j = P.idx[2 * m + 1];
-            double ni = pickn(P, i), nj = pickn(P, j);
+            double ni = P.n[i], nj = P.n[j];
             double denom = ni * (nj - (i == j));
-            return pick<KP>(x, i) * (nj - pick<KP>(x, j)) / denom;
+            return x[i] * (nj - x[j]) / denom;
         }
         case STAT_Y2: {
             int i = P.idx[2 * m], j = P.idx[2 * m + 1];
-            double ni = pickn(P, i), nj = pickn(P, j);
-            double xi = pick<KP>(x, i), xj = pick<KP>(x, j);
+            double ni = P.n[i], nj = P.n[j];
+            double xi = x[i], xj = x[j];
             double denom = ni * nj * (nj - 1);
             return xi * (nj - xj) * (nj - xj - 1) / denom;
         }
         case STAT_F2: {
             int i = P.idx[2 * m], j = P.idx[2 * m + 1];
-            double ni = pickn(P, i), nj = pickn(P, j);
-            double xi = pick<KP>(x, i), xj = pick<KP>(x, j);
+            double ni = P.n[i], nj = P.n[j];
+            double xi = x[i], xj = x[j];
             double denom = ni * (ni - 1) * nj * (nj - 1);
             double numer = xi * (xi - 1) * (nj - xj) * (nj - xj - 1)
                            - xi * (ni - xi) * (nj - xj) * xj;
@@ -103,39 +91,36 @@ __device__ inline double f_eval(const SumP &P, const double (&x)[KP], int m) {
         }
         case STAT_RELATEDNESS: {
             double sumx = 0;
-#pragma unroll
-            for (int k = 0; k < KP; k++) {
-                if (k < P.K) sumx += x[k] / P.n[k];
-            }
+            for (int k = 0; k < P.K; k++) sumx += x[k] / P.n[k];
             double meanx = sumx / (double) P.K;
             int i = P.idx[2 * m], j = P.idx[2 * m + 1];
-            double ni = pickn(P, i), nj = pickn(P, j);
-            return (pick<KP>(x, i) / ni - meanx) * (pick<KP>(x, j) / nj - meanx);
+            double ni = P.n[i], nj = P.n[j];
+            return (x[i] / ni - meanx) * (x[j] / nj - meanx);
         }
         case STAT_RELATEDNESS_NC: {
             int i = P.idx[2 * m], j = P.idx[2 * m + 1];
-            double ni = pickn(P, i), nj = pickn(P, j);
-            return pick<KP>(x, i) * pick<KP>(x, j) / (ni * nj);
+            double ni = P.n[i], nj = P.n[j];
+            return x[i] * x[j] / (ni * nj);
         }
         case STAT_Y3: {
             int i = P.idx[3 * m], j = P.idx[3 * m + 1], k = P.idx[3 * m + 2];
-            double ni = pickn(P, i), nj = pickn(P, j), nk = pickn(P, k);
+            double ni = P.n[i], nj = P.n[j], nk = P.n[k];
             double denom = ni * nj * nk;
-            double numer = pick<KP>(x, i) * (nj - pick<KP>(x, j)) * (nk - pick<KP>(x, k));
+            double numer = x[i] * (nj - x[j]) * (nk - x[k]);
             return numer / denom;
         }
         case STAT_F3: {
             int i = P.idx[3 * m], j = P.idx[3 * m + 1], k = P.idx[3 * m + 2];
-            double ni = pickn(P, i), nj = pickn(P, j), nk = pickn(P, k);
-            double xi = pick<KP>(x, i), xj = pick<KP>(x, j), xk = pick<KP>(x, k);
+            double ni = P.n[i], nj = P.n[j], nk = P.n[k];
+            double xi = x[i], xj = x[j], xk = x[k];
             double denom = ni * (ni - 1) * nj * nk;
             double numer = xi * (xi - 1) * (nj - xj) * (nk - xk) - xi * (ni - xi) * (nj - xj) * xk;
             return numer / denom;
         }
         case STAT_F4: {
             int i = P.idx[4 * m], j = P.idx[4 * m + 1], k = P.idx[4 * m + 2], l = P.idx[4 * m + 3];
-            double ni = pickn(P, i), nj = pickn(P, j), nk = pickn(P, k), nl = pickn(P, l);
-            double xi = pick<KP>(x, i), xj = pick<KP>(x, j), xk = pick<KP>(x, k), xl = pick<KP>(x, l);
+            double ni = P.n[i], nj = P.n[j], nk = P.n[k], nl = P.n[l];
+            double xi = x[i], xj = x[j], xk = x[k], xl = x[l];
             double denom = ni * nj * nk * nl;
             double numer = xi * xk * (nj - xj) * (nl - xl) - xi * xl * (nj - xj) * (nk - xk);
             return numer / denom;
@@ -151,15 +136,15 @@ __device__ inline double f_eval(const SumP &P, const double (&x)[KP], int m) {
 
 // branch mode: f(x) + f(total - x) unless polarised (trees.c:1944-1972)
 template <int KP>
-__device__ inline double F_branch(const SumP &P, const IVec<KP> &c, int m) {
+__device__ __forceinline__ double F_branch(const SumP &P, const IVec<KP> &c, int m) {
     double x[KP];
 #pragma unroll
     for (int k = 0; k < KP; k++) x[k] = (double) c.v[k];
-    double r = f_eval<KP>(P, x, m);
+    double r = f_eval(P, x, m);
     if (!P.polarised) {
 #pragma unroll
         for (int k = 0; k < KP; k++) x[k] = (k < P.K ? P.n[k] : 0.0) - x[k];
-        r += f_eval<KP>(P, x, m);
+        r += f_eval(P, x, m);
     }
     return r;
 }
@@ -177,60 +162,228 @@ __global__ void k_set_weights(const int32_t *sets, const uint32_t *set_off, uint
 }
 
 // ---------------------------------------------------------------- phase 1
+// state[u] after every visit = running sum over u's node-major list, whose first
+// (INIT) entry is u's own sample weight (trees.c:1406-1415) and whose other
+// addends are +-state[child of the diff] (update_state, trees.c:1317-1327).
 
-// addend of visit k: +-state[child] at that moment; the node's initial state
-// (its own sample weight, trees.c:1406-1415) is folded into its first addend
+// library check path: addends materialised, then cub::DeviceScan::InclusiveSumByKey
 template <int KP>
 __global__ void k_gather_delta(uint32_t begin, uint32_t end, const int32_t *nm_src,
-    const uint8_t *nm_flag, const uint32_t *nm_key, const int32_t *rank_node,
-    const IVec<KP> *val, const IVec<KP> *w, IVec<KP> *delta) {
+    const uint8_t *nm_flag, const IVec<KP> *val, const IVec<KP> *w, IVec<KP> *delta) {
     uint32_t k = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= end) return;
     int32_t s = nm_src[k];
     uint8_t f = nm_flag[k];
-    IVec<KP> x = s >= 0 ? val[s] : w[~s];
+    IVec<KP> x = (f & 2) ? w[s] : val[s];
     if (f & 1) {
 #pragma unroll
         for (int q = 0; q < KP; q++) x.v[q] = -x.v[q];
     }
-    if (f & 2) x = x + w[rank_node[nm_key[k]]];
     delta[k - begin] = x;
+}
+
+// level 0: nodes that are never a parent; their lists are the INIT entry alone
+template <int KP>
+__global__ void k_level0(uint32_t end, const int32_t *nm_src, const IVec<KP> *w, IVec<KP> *val) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < end) val[k] = w[nm_src[k]];
+}
+
+// Fused addend gather + segmented inclusive scan of one level, single pass with
+// decoupled look-back between tiles.  A segment = one node's list; list heads are
+// the INIT entries.  (value, head) pairs combine as
+//   a (+) b = b.head ? b : (a.value + b.value, a.head).
+template <int KP>
+struct SegVal {
+    IVec<KP> v;
+    int head;
+};
+template <int KP>
+struct SegOp {
+    __device__ __forceinline__ SegVal<KP> operator()(const SegVal<KP> &a, const SegVal<KP> &b) const {
+        if (b.head) return b;
+        SegVal<KP> r;
+        r.v = a.v + b.v;
+        r.head = a.head;
+        return r;
+    }
+};
+
+// descriptors are written by one CTA and read by others in the same launch: bypass L1
+template <int KP>
+__device__ __forceinline__ SegVal<KP> load_cg(const SegVal<KP> *p) {
+    SegVal<KP> r;
+    const int *q = reinterpret_cast<const int *>(p);
+#pragma unroll
+    for (int c = 0; c < KP; c++) r.v.v[c] = __ldcg(q + c);
+    r.head = __ldcg(reinterpret_cast<const int *>(&p->head));
+    return r;
+}
+template <int KP>
+__device__ __forceinline__ void store_cg(SegVal<KP> *p, const SegVal<KP> &x) {
+    int *q = reinterpret_cast<int *>(p);
+#pragma unroll
+    for (int c = 0; c < KP; c++) __stcg(q + c, x.v.v[c]);
+    __stcg(reinterpret_cast<int *>(&p->head), x.head);
+}
+
+// look-back descriptor of one tile: status 0 = empty, 1 = aggregate ready, 2 = prefix ready
+template <int KP>
+struct TileDesc {
+    SegVal<KP> agg;
+    SegVal<KP> prefix;
+    volatile int status;
+    int pad[3];
+};
+
+constexpr int PROP_TB = 256;
+constexpr int PROP_IPT = PROP_TILE / PROP_TB;
+
+template <int KP>
+__global__ void __launch_bounds__(PROP_TB) k_propagate_level(uint32_t begin, uint32_t end,
+    const int32_t *__restrict__ nm_src, const uint8_t *__restrict__ nm_flag,
+    const IVec<KP> *__restrict__ w, IVec<KP> *val, TileDesc<KP> *desc, uint32_t *ticket,
+    int *error_flag) {
+    typedef cub::BlockScan<SegVal<KP>, PROP_TB> BS;
+    __shared__ typename BS::TempStorage tmp;
+    __shared__ uint32_t s_tile;
+    __shared__ SegVal<KP> s_carry;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = begin + tile * PROP_TILE + threadIdx.x * PROP_IPT;
+    SegOp<KP> op;
+
+    // gather addends; thread-local segmented scan
+    SegVal<KP> item[PROP_IPT];
+#pragma unroll
+    for (int q = 0; q < PROP_IPT; q++) {
+        uint32_t k = base + q;
+        SegVal<KP> x;
+#pragma unroll
+        for (int c = 0; c < KP; c++) x.v.v[c] = 0;
+        x.head = 0;
+        if (k < end) {
+            int32_t s = nm_src[k];
+            uint8_t f = nm_flag[k];
+            x.v = (f & 2) ? w[s] : val[s];
+            if (f & 1) {
+#pragma unroll
+                for (int c = 0; c < KP; c++) x.v.v[c] = -x.v.v[c];
+            }
+            x.head = (f & 2) ? 1 : 0;
+        }
+        item[q] = q == 0 ? x : op(item[q - 1], x);
+    }
+    SegVal<KP> thread_agg = item[PROP_IPT - 1];
+    SegVal<KP> identity;
+#pragma unroll
+    for (int c = 0; c < KP; c++) identity.v.v[c] = 0;
+    identity.head = 0;
+    SegVal<KP> thread_excl, tile_agg;
+    BS(tmp).ExclusiveScan(thread_agg, thread_excl, identity, op, tile_agg);
+
+    // decoupled look-back: carry entering this tile
+    if (threadIdx.x == 0) {
+        SegVal<KP> carry = identity;
+        TileDesc<KP> *me = desc + tile;
+        if (tile == 0) {
+            store_cg(&me->prefix, tile_agg);
+            __threadfence();
+            me->status = 2;
+        } else {
+            store_cg(&me->agg, tile_agg);
+            __threadfence();
+            me->status = 1;
+            {
+                int32_t p = (int32_t) tile - 1;
+                uint32_t spins = 0;
+                while (true) {
+                    TileDesc<KP> *d = desc + p;
+                    int st = d->status;
+                    if (st == 0) {
+                        if (++spins > (1u << 28)) {
+                            *error_flag = 1;
+                            break;
+                        }
+                        continue;
+                    }
+                    __threadfence();
+                    if (st == 2) {
+                        carry = op(load_cg(&d->prefix), carry);
+                        break;
+                    }
+                    carry = op(load_cg(&d->agg), carry);
+                    if (carry.head || p == 0) break;
+                    p--;
+                }
+            }
+            store_cg(&me->prefix, op(carry, tile_agg));
+            __threadfence();
+            me->status = 2;
+        }
+        s_carry = carry;
+    }
+    __syncthreads();
+    // values entering this thread: carry (+) thread_excl
+    SegVal<KP> in = op(s_carry, thread_excl);
+#pragma unroll
+    for (int q = 0; q < PROP_IPT; q++) {
+        uint32_t k = base + q;
+        if (k < end) {
+            SegVal<KP> r = op(in, item[q]);
+            val[k] = r.v;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- phase 2
 
+constexpr uint32_t CHILD_BIT = 0x80000000u;
+
+// branch mode.  One warp per breakpoint: sum over the diffs at that position of the change of
+// the running sum  sum_u branch_length[u] * summary[u]  (update_running_sum,
+// trees.c:1339-1350; loops :1425-1474):
+//   CHILD entry: +-(time[p] - time[c]) * F(state[c])          (trees.c:1428-1432, 1455-1457)
+//   visit entry: bl[u] * (F(state[u] after) - F(state[u] before))  (trees.c:1434-1447, 1460-1473)
 template <int KP>
-__global__ void k_event_summary(uint32_t nev, const uint32_t *voff, const uint32_t *em_perm,
-    const double *em_bl, const int32_t *em_node, const uint8_t *nm_flag, const IVec<KP> *val,
-    const IVec<KP> *w, const int32_t *ev_src, const double *ev_sbl, SumP P, double *D) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nev) return;
-    int32_t s = ev_src[i];
-    IVec<KP> xc = s >= 0 ? val[s] : w[~s];
-    double sbl = ev_sbl[i];
-    uint32_t j0 = voff[i], j1 = voff[i + 1];
+__global__ void k_bp_summary(uint32_t T, const uint32_t *__restrict__ bp_end,
+    const uint32_t *__restrict__ em_idx, const double *__restrict__ em_bl,
+    const IVec<KP> *__restrict__ val, SumP P, double *B) {
+    uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (t >= T) return;
+    uint32_t j0 = t > 0 ? bp_end[t - 1] : 0, j1 = bp_end[t];
     for (int m0 = 0; m0 < P.M; m0 += MC) {
         double acc[MC];
 #pragma unroll
-        for (int q = 0; q < MC; q++) {
-            acc[q] = (m0 + q < P.M) ? sbl * F_branch<KP>(P, xc, m0 + q) : 0.0;
-        }
-        for (uint32_t j = j0; j < j1; j++) {
+        for (int q = 0; q < MC; q++) acc[q] = 0.0;
+        for (uint32_t j = j0 + lane; j < j1; j += 32) {
+            uint32_t idx = em_idx[j];
             double bl = em_bl[j];
-            if (bl == 0.0 && P.skip_zero_bl) continue;
-            uint32_t k = em_perm[j];
-            IVec<KP> xn = val[k];
-            IVec<KP> xo = (nm_flag[k] & 2) ? w[em_node[j]] : val[k - 1];
+            uint32_t k = idx & ~CHILD_BIT;
+            if (idx & CHILD_BIT) {
+                IVec<KP> xc = val[k];
 #pragma unroll
-            for (int q = 0; q < MC; q++) {
-                if (m0 + q < P.M) {
-                    acc[q] += bl * (F_branch<KP>(P, xn, m0 + q) - F_branch<KP>(P, xo, m0 + q));
+                for (int q = 0; q < MC; q++) {
+                    if (m0 + q < P.M) acc[q] += bl * F_branch<KP>(P, xc, m0 + q);
+                }
+            } else if (bl != 0.0 || !P.skip_zero_bl) {
+                IVec<KP> xn = val[k], xo = val[k - 1];
+#pragma unroll
+                for (int q = 0; q < MC; q++) {
+                    if (m0 + q < P.M) {
+                        acc[q] += bl * (F_branch<KP>(P, xn, m0 + q) - F_branch<KP>(P, xo, m0 + q));
+                    }
                 }
             }
         }
 #pragma unroll
         for (int q = 0; q < MC; q++) {
-            if (m0 + q < P.M) D[(size_t) (m0 + q) * nev + i] = acc[q];
+            double v = acc[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0 && m0 + q < P.M) B[(size_t) (m0 + q) * T + t] = v;
         }
     }
 }
@@ -238,8 +391,8 @@ __global__ void k_event_summary(uint32_t nev, const uint32_t *voff, const uint32
 template <int KP>
 __global__ void k_site_summary(uint32_t site_lo, uint32_t nsites, const uint32_t *site_moff,
     const uint32_t *site_aoff, const int32_t *mut_src, const uint16_t *mut_allele,
-    const uint16_t *mut_alt, const IVec<KP> *val, const IVec<KP> *w, IVec<KP> totals,
-    IVec<KP> *scratch, SumP P, double *R) {
+    const uint16_t *mut_alt, const IVec<KP> *val, IVec<KP> totals, IVec<KP> *scratch, SumP P,
+    double *R) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsites) return;
     uint32_t site = site_lo + t;
@@ -250,8 +403,7 @@ __global__ void k_site_summary(uint32_t site_lo, uint32_t nsites, const uint32_t
     scratch[a0] = totals;  // allele 0 starts at total_weight (trees.c:1548)
     for (uint32_t al = 1; al < na; al++) scratch[a0 + al] = zero;
     for (uint32_t m = site_moff[site]; m < site_moff[site + 1]; m++) {
-        int32_t s = mut_src[m];
-        IVec<KP> x = s >= 0 ? val[s] : w[~s];
+        IVec<KP> x = val[mut_src[m]];
         IVec<KP> d = scratch[a0 + mut_allele[m]];
         scratch[a0 + mut_allele[m]] = d + x;
         IVec<KP> e = scratch[a0 + mut_alt[m]];
@@ -270,7 +422,7 @@ __global__ void k_site_summary(uint32_t site_lo, uint32_t nsites, const uint32_t
             for (int k = 0; k < KP; k++) x[k] = (double) c.v[k];
 #pragma unroll
             for (int q = 0; q < MC; q++) {
-                if (m0 + q < P.M) acc[q] += f_eval<KP>(P, x, m0 + q);
+                if (m0 + q < P.M) acc[q] += f_eval(P, x, m0 + q);
             }
         }
 #pragma unroll
@@ -344,27 +496,28 @@ __global__ void k_tile_scan(double *D, uint32_t n, uint32_t ntiles, const double
 
 // ---------------------------------------------------------------- phase 4
 
-// branch: result[w] = sum_i S_i * |[pos_i, pos_{i+1}) ^ window w|  (trees.c:1484-1504)
-__global__ void k_window_branch(const double *windows, uint32_t nsplit, const double *ev_pos,
-    uint32_t nev, double range_right, const double *S, uint32_t M, double *partial) {
+// branch: result[w] = sum_t S_t * |[pos_t, pos_{t+1}) ^ window w| over breakpoints t, S_t the
+// running sum once every diff at pos_t is applied (trees.c:1484-1504)
+__global__ void k_window_branch(const double *windows, uint32_t nsplit, const double *bp_pos,
+    uint32_t T, double range_right, const double *S, uint32_t M, double *partial) {
     typedef cub::BlockReduce<double, TB> BR;
     __shared__ typename BR::TempStorage tmp;
     uint32_t w = blockIdx.x, c = blockIdx.y;
     double wl = windows[w], wr = windows[w + 1];
-    uint32_t lo = upper_bound_dev(ev_pos, nev, wl);
+    uint32_t lo = upper_bound_dev(bp_pos, T, wl);
     lo = lo > 0 ? lo - 1 : 0;
-    uint32_t hi = lower_bound_dev(ev_pos, nev, wr);
+    uint32_t hi = lower_bound_dev(bp_pos, T, wr);
     if (hi < lo) hi = lo;
     uint32_t len = hi - lo, per = (len + nsplit - 1) / nsplit;
     uint32_t s0 = lo + c * per, s1 = s0 + per;
     if (s0 > hi) s0 = hi;
     if (s1 > hi) s1 = hi;
     for (uint32_t m = 0; m < M; m++) {
-        const double *row = S + (size_t) m * nev;
+        const double *row = S + (size_t) m * T;
         double sum = 0.0;
         for (uint32_t i = s0 + threadIdx.x; i < s1; i += TB) {
-            double p = ev_pos[i];
-            double nx = i + 1 < nev ? ev_pos[i + 1] : range_right;
+            double p = bp_pos[i];
+            double nx = i + 1 < T ? bp_pos[i + 1] : range_right;
             double l = p > wl ? p : wl;
             double r = nx < wr ? nx : wr;
             if (r > l) sum += row[i] * (r - l);
@@ -447,6 +600,11 @@ struct Launches {
     uint64_t n = 0;
 };
 
+static bool use_cub_propagate() {
+    const char *e = getenv("TSKB_PROPAGATE");
+    return e != nullptr && strcmp(e, "cub") == 0;
+}
+
 template <int KP>
 int run_impl(const Plan &P, const StatSpec &sp) {
     cudaStream_t s = P.stream;
@@ -513,27 +671,49 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     TSKB_CK(cudaEventRecord(P.ev[1], s));
 
     // ---- phase 1: propagate
-    IVec<KP> *val = A.get<IVec<KP>>(P.V);
-    uint32_t max_range = 0;
-    for (uint32_t l = 0; l < P.nlevels; l++) {
-        max_range = std::max(max_range, P.level_begin[l + 1] - P.level_begin[l]);
-    }
-    IVec<KP> *delta = A.get<IVec<KP>>(max_range);
-    size_t scan_bytes = 0;
-    if (max_range) {
-        TSKB_CK(cub::DeviceScan::InclusiveSumByKey(nullptr, scan_bytes, P.nm_key.p, delta, val,
-            max_range, ::cuda::std::equal_to<>(), s));
-    }
-    char *scan_tmp = A.get<char>(scan_bytes);
-    for (uint32_t l = 1; l < P.nlevels; l++) {
-        uint32_t b0 = P.level_begin[l], b1 = P.level_begin[l + 1];
-        if (b1 == b0) continue;
-        k_gather_delta<KP><<<grid_for(b1 - b0, TB), TB, 0, s>>>(b0, b1, P.nm_src.p, P.nm_flag.p,
-            P.nm_key.p, P.rank_node.p, val, w, delta);
+    IVec<KP> *val = A.get<IVec<KP>>(P.Vn);
+    const std::vector<uint32_t> &lb = P.level_begin;
+    if (lb[1] > 0) {
+        k_level0<KP><<<grid_for(lb[1], TB), TB, 0, s>>>(lb[1], P.nm_src.p, w, val);
+        TSKB_CK_LAUNCH();
         L.n++;
-        size_t bytes = scan_bytes;
-        TSKB_CK(cub::DeviceScan::InclusiveSumByKey(scan_tmp, bytes, P.nm_key.p + b0, delta,
-            val + b0, b1 - b0, ::cuda::std::equal_to<>(), s));
+    }
+    int *d_err = A.get<int>(1);
+    TSKB_CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
+    if (use_cub_propagate()) {
+        uint32_t max_range = 0;
+        for (uint32_t l = 1; l < P.nlevels; l++) max_range = std::max(max_range, lb[l + 1] - lb[l]);
+        IVec<KP> *delta = A.get<IVec<KP>>(max_range);
+        size_t scan_bytes = 0;
+        if (max_range) {
+            TSKB_CK(cub::DeviceScan::InclusiveSumByKey(nullptr, scan_bytes, P.nm_key.p, delta, val,
+                max_range, ::cuda::std::equal_to<>(), s));
+        }
+        char *scan_tmp = A.get<char>(scan_bytes);
+        for (uint32_t l = 1; l < P.nlevels; l++) {
+            uint32_t b0 = lb[l], b1 = lb[l + 1];
+            if (b1 == b0) continue;
+            k_gather_delta<KP><<<grid_for(b1 - b0, TB), TB, 0, s>>>(b0, b1, P.nm_src.p,
+                P.nm_flag.p, val, w, delta);
+            L.n++;
+            size_t bytes = scan_bytes;
+            TSKB_CK(cub::DeviceScan::InclusiveSumByKey(scan_tmp, bytes, P.nm_key.p + b0, delta,
+                val + b0, b1 - b0, ::cuda::std::equal_to<>(), s));
+        }
+    } else {
+        const uint32_t ntiles = P.level_tile0[P.nlevels];
+        TileDesc<KP> *desc = A.get<TileDesc<KP>>(ntiles + 1);
+        uint32_t *ticket = A.get<uint32_t>(P.nlevels + 1);
+        TSKB_CK(cudaMemsetAsync(desc, 0, (size_t) (ntiles + 1) * sizeof(TileDesc<KP>), s));
+        TSKB_CK(cudaMemsetAsync(ticket, 0, (P.nlevels + 1) * sizeof(uint32_t), s));
+        for (uint32_t l = 1; l < P.nlevels; l++) {
+            uint32_t b0 = lb[l], b1 = lb[l + 1];
+            if (b1 == b0) continue;
+            uint32_t tiles = P.level_tile0[l + 1] - P.level_tile0[l];
+            k_propagate_level<KP><<<tiles, PROP_TB, 0, s>>>(b0, b1, P.nm_src.p, P.nm_flag.p, w,
+                val, desc + P.level_tile0[l], ticket + l, d_err);
+            L.n++;
+        }
     }
     TSKB_CK_LAUNCH();
     TSKB_CK(cudaEventRecord(P.ev[2], s));
@@ -544,27 +724,27 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     double *d_result = sp.result_on_device ? sp.result : A.get<double>((size_t) W * M);
     const int span_norm = (sp.options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0;
     if (branch) {
-        const uint32_t nev = P.nev;
-        double *D = A.get<double>((size_t) M * std::max<uint32_t>(nev, 1));
-        if (nev) {
-            k_event_summary<KP><<<grid_for(nev, 128), 128, 0, s>>>(nev, P.voff.p, P.em_perm.p,
-                P.em_bl.p, P.em_node.p, P.nm_flag.p, val, w, P.ev_src.p, P.ev_sbl.p, sumP, D);
+        const uint32_t T = P.T;
+        double *B = A.get<double>((size_t) M * std::max<uint32_t>(T, 1));
+        if (T) {
+            k_bp_summary<KP><<<grid_for((size_t) T * 32, 128), 128, 0, s>>>(T, P.bp_end.p,
+                P.em_idx.p, P.em_bl.p, val, sumP, B);
             TSKB_CK_LAUNCH();
             L.n++;
         }
         TSKB_CK(cudaEventRecord(P.ev[3], s));
-        if (nev) {
-            uint32_t ntiles = (nev + SCAN_TILE - 1) / SCAN_TILE;
+        if (T) {
+            uint32_t ntiles = (T + SCAN_TILE - 1) / SCAN_TILE;
             double *agg = A.get<double>((size_t) M * ntiles);
-            k_tile_reduce<<<dim3(ntiles, M), TB, 0, s>>>(D, nev, ntiles, agg);
+            k_tile_reduce<<<dim3(ntiles, M), TB, 0, s>>>(B, T, ntiles, agg);
             k_agg_scan<<<M, AGG_TB, 0, s>>>(agg, ntiles);
-            k_tile_scan<<<dim3(ntiles, M), TB, 0, s>>>(D, nev, ntiles, agg);
+            k_tile_scan<<<dim3(ntiles, M), TB, 0, s>>>(B, T, ntiles, agg);
             TSKB_CK_LAUNCH();
             L.n += 3;
         }
         TSKB_CK(cudaEventRecord(P.ev[4], s));
-        k_window_branch<<<dim3(W, nsplit), TB, 0, s>>>(d_windows, nsplit, P.ev_pos.p, nev,
-            P.range_right, D, M, partial);
+        k_window_branch<<<dim3(W, nsplit), TB, 0, s>>>(d_windows, nsplit, P.bp_pos.p, T,
+            P.range_right, B, M, partial);
         TSKB_CK_LAUNCH();
         L.n++;
     } else {
@@ -573,7 +753,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         IVec<KP> *scratch = A.get<IVec<KP>>(P.total_alleles + 1);
         if (nsites) {
             k_site_summary<KP><<<grid_for(nsites, 128), 128, 0, s>>>(P.site_lo, nsites,
-                P.site_moff.p, P.site_aoff.p, P.mut_src.p, P.mut_allele.p, P.mut_alt.p, val, w,
+                P.site_moff.p, P.site_aoff.p, P.mut_src.p, P.mut_allele.p, P.mut_alt.p, val,
                 totals, scratch, sumP, R);
             TSKB_CK_LAUNCH();
             L.n++;
@@ -590,6 +770,8 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     TSKB_CK_LAUNCH();
     L.n++;
     TSKB_CK(cudaEventRecord(P.ev[5], s));
+    int h_err = 0;
+    TSKB_CK(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
     if (!sp.result_on_device) {
         TSKB_CK(cudaMemcpyAsync(sp.result, d_result, (size_t) W * M * sizeof(double),
             cudaMemcpyDeviceToHost, s));
@@ -604,6 +786,10 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     TSKB_CK(cudaEventElapsedTime(&ms, P.ev[0], P.ev[6]));
     P.stats.last_call_ms = ms;
     P.stats.last_launches = L.n;
+    if (h_err) {
+        last_error_string() = "propagation look-back timed out";
+        return TSKB_ERR_CUDA;
+    }
     return 0;
 }
 

@@ -12,15 +12,21 @@
 // directly by running the same pedigree process backwards in time and carrying
 // only ancestral segments (the per-individual segment merge below is the
 // overlap-merging step of simplify, Kelleher et al. 2018 algorithm S), which is
-// what makes 10^5 samples x 10^7 edges feasible in seconds.  Output tables are in
+// what makes 10^5 samples x 10^7 edges feasible.  Output tables are in
 // tskit's canonical order (edges by (time[parent], parent, child, left), abutting
 // edges squashed) together with the edge insertion/removal indexes
 // (sort keys of c/tskit/tables.c:11392-11459).
+//
+// Every random draw is a pure function of (seed, generation, individual), and node
+// ids are assigned in individual order, so the output is bit-identical for any
+// thread count.
 #include <stdint.h>
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -28,6 +34,11 @@ namespace {
 struct Seg {
     double left, right;
     int32_t node;
+};
+
+struct Piece {
+    uint32_t parent;
+    Seg seg;
 };
 
 struct Edge {
@@ -45,7 +56,8 @@ inline uint64_t splitmix(uint64_t x) {
 // counter-based stream: draw k of (seed, generation, individual)
 struct Rng {
     uint64_t key, ctr;
-    Rng(uint64_t seed, uint64_t g, uint64_t i) : key(splitmix(seed ^ splitmix(g * 0x100000001B3ull + i))), ctr(0) {}
+    Rng(uint64_t seed, uint64_t g, uint64_t i)
+        : key(splitmix(seed ^ splitmix(g * 0x100000001B3ull + i))), ctr(0) {}
     uint64_t next() { return splitmix(key + (ctr++) * 0xD1342543DE82EF95ull); }
     uint64_t below(uint64_t n) { return (uint64_t) (((__uint128_t) next() * n) >> 64); }
 };
@@ -57,16 +69,22 @@ struct Result {
     std::vector<int32_t> ins, rem;
 };
 
-void merge_into_parent(std::vector<Seg> &pieces, int32_t &parent_node, double time,
-    Result &R, std::vector<Seg> &out, std::vector<Seg> &X) {
+constexpr int32_t PENDING = INT32_MIN;  // node id of a coalescence not yet numbered
+
+// Merge the pieces inherited by one parent individual.  Overlaps of >= 2 pieces
+// coalesce into the parent's node (id assigned later: PENDING); everything else
+// passes through with its own node id.  Returns true if the parent coalesced.
+bool merge_into_parent(Seg *pieces, size_t count, std::vector<Edge> &edges,
+    std::vector<Seg> &out, std::vector<Seg> &heap, std::vector<Seg> &X) {
     out.clear();
-    if (pieces.size() == 1) {
+    if (count == 1) {
         out.push_back(pieces[0]);
-        return;
+        return false;
     }
-    // min-heap on left
+    heap.assign(pieces, pieces + count);
     auto cmp = [](const Seg &a, const Seg &b) { return a.left > b.left; };
-    std::make_heap(pieces.begin(), pieces.end(), cmp);
+    std::make_heap(heap.begin(), heap.end(), cmp);
+    bool coalesced = false;
     auto push_out = [&](const Seg &a) {
         if (!out.empty() && out.back().node == a.node && out.back().right == a.left) {
             out.back().right = a.right;
@@ -74,106 +92,213 @@ void merge_into_parent(std::vector<Seg> &pieces, int32_t &parent_node, double ti
             out.push_back(a);
         }
     };
-    while (!pieces.empty()) {
-        double l = pieces.front().left;
+    while (!heap.empty()) {
+        double l = heap.front().left;
         double r = 1e300;
         X.clear();
-        while (!pieces.empty() && pieces.front().left == l) {
-            std::pop_heap(pieces.begin(), pieces.end(), cmp);
-            Seg x = pieces.back();
-            pieces.pop_back();
+        while (!heap.empty() && heap.front().left == l) {
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            Seg x = heap.back();
+            heap.pop_back();
             if (x.right < r) r = x.right;
             X.push_back(x);
         }
-        if (!pieces.empty() && pieces.front().left < r) r = pieces.front().left;
+        if (!heap.empty() && heap.front().left < r) r = heap.front().left;
         if (X.size() == 1) {
             Seg x = X[0];
             Seg alpha = x;
-            if (!pieces.empty() && pieces.front().left < x.right) {
-                alpha.right = pieces.front().left;
-                x.left = pieces.front().left;
-                pieces.push_back(x);
-                std::push_heap(pieces.begin(), pieces.end(), cmp);
+            if (!heap.empty() && heap.front().left < x.right) {
+                alpha.right = heap.front().left;
+                x.left = heap.front().left;
+                heap.push_back(x);
+                std::push_heap(heap.begin(), heap.end(), cmp);
             }
             push_out(alpha);
         } else {
-            if (parent_node < 0) {
-                parent_node = (int32_t) R.node_time.size();
-                R.node_time.push_back(time);
-                R.node_flags.push_back(0);
-            }
+            coalesced = true;
             for (Seg &x : X) {
-                R.edges.push_back(Edge{ l, r, parent_node, x.node });
+                edges.push_back(Edge{ l, r, PENDING, x.node });
                 if (x.right > r) {
                     x.left = r;
-                    pieces.push_back(x);
-                    std::push_heap(pieces.begin(), pieces.end(), cmp);
+                    heap.push_back(x);
+                    std::push_heap(heap.begin(), heap.end(), cmp);
                 }
             }
-            push_out(Seg{ l, r, parent_node });
+            push_out(Seg{ l, r, PENDING });
         }
     }
+    return coalesced;
 }
+
+// sense-reversing spin barrier for the SPMD generation loop
+struct Barrier {
+    std::atomic<unsigned> count{0};
+    std::atomic<unsigned> sense{0};
+    unsigned n;
+    explicit Barrier(unsigned n_) : n(n_) {}
+    void wait() {
+        unsigned s = sense.load(std::memory_order_acquire);
+        if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+            count.store(0, std::memory_order_relaxed);
+            sense.store(s + 1, std::memory_order_release);
+        } else {
+            unsigned spins = 0;
+            while (sense.load(std::memory_order_acquire) == s) {
+                if (++spins > 2000) std::this_thread::yield();
+            }
+        }
+    }
+};
 
 }  // namespace
 
 extern "C" {
 
-void *tskb_wfsim_run(uint64_t n, uint64_t generations, double L, uint32_t ncross, uint64_t seed) {
+void *tskb_wfsim_run(uint64_t n, uint64_t generations, double L, uint32_t ncross, uint64_t seed,
+    uint32_t num_threads) {
+    unsigned nt = num_threads ? num_threads : std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 64) nt = 64;
     Result *Rp = new Result();
     Result &R = *Rp;
     R.node_time.assign(n, 0.0);
     R.node_flags.assign(n, 1);
-    std::vector<std::vector<Seg>> cur(n), nxt(n);
+    std::vector<std::vector<Seg>> cur(n);
     std::vector<uint32_t> active(n), next_active;
     for (uint64_t i = 0; i < n; i++) {
         cur[i].push_back(Seg{ 0.0, L, (int32_t) i });
         active[i] = (uint32_t) i;
     }
-    std::vector<double> bps;
-    std::vector<Seg> out, X;
     const uint64_t Lint = (uint64_t) L;
-    for (uint64_t g = 1; g <= generations; g++) {
-        next_active.clear();
-        for (uint32_t idx : active) {
-            std::vector<Seg> &segs = cur[idx];
-            Rng rng(seed, g, idx);
-            uint32_t par[2] = { (uint32_t) rng.below(n), (uint32_t) rng.below(n) };
-            bps.clear();
-            for (uint32_t k = 0; k < ncross && Lint > 1; k++) {
-                bps.push_back((double) (1 + rng.below(Lint - 1)));
+    std::vector<std::vector<Piece>> tpieces(nt);
+    std::vector<std::vector<Edge>> tedges(nt);
+    std::vector<std::atomic<uint32_t>> count(n);
+    std::vector<uint32_t> start(n + 1), cursor_init(n);
+    std::vector<std::atomic<uint32_t>> cursor(n);
+    std::vector<Seg> flat;
+    std::vector<uint8_t> coalesced(n);
+    std::vector<int32_t> newid(n);
+    for (uint64_t i = 0; i < n; i++) count[i].store(0, std::memory_order_relaxed);
+
+    if (nt > 1 && n / nt < 2000) nt = (unsigned) std::max<uint64_t>(1, n / 2000);
+    tpieces.resize(nt);
+    tedges.resize(nt);
+    Barrier bar(nt);
+    size_t np = 0;
+    auto worker = [&](unsigned t) {
+        std::vector<double> bps;
+        std::vector<Seg> out, heap, X;
+        for (uint64_t g = 1; g <= generations; g++) {
+            const size_t na = active.size();
+            // phase 1: meiosis -- split every lineage's segments between its two parents
+            {
+                std::vector<Piece> &P = tpieces[t];
+                P.clear();
+                size_t a0 = na * t / nt, a1 = na * (t + 1) / nt;
+                for (size_t a = a0; a < a1; a++) {
+                    uint32_t idx = active[a];
+                    std::vector<Seg> &segs = cur[idx];
+                    Rng rng(seed, g, idx);
+                    uint32_t par[2] = { (uint32_t) rng.below(n), (uint32_t) rng.below(n) };
+                    bps.clear();
+                    for (uint32_t k = 0; k < ncross && Lint > 1; k++) {
+                        bps.push_back((double) (1 + rng.below(Lint - 1)));
+                    }
+                    std::sort(bps.begin(), bps.end());
+                    bps.erase(std::unique(bps.begin(), bps.end()), bps.end());
+                    size_t b = 0;  // number of crossovers <= current position
+                    for (const Seg &s0 : segs) {
+                        Seg s = s0;
+                        while (b < bps.size() && bps[b] <= s.left) b++;
+                        while (true) {
+                            uint32_t p = par[b & 1];
+                            if (b < bps.size() && bps[b] < s.right) {
+                                P.push_back(Piece{ p, Seg{ s.left, bps[b], s.node } });
+                                s.left = bps[b];
+                                b++;
+                            } else {
+                                P.push_back(Piece{ p, s });
+                                break;
+                            }
+                        }
+                    }
+                    segs.clear();
+                }
+                for (const Piece &pc : P) count[pc.parent].fetch_add(1, std::memory_order_relaxed);
             }
-            std::sort(bps.begin(), bps.end());
-            bps.erase(std::unique(bps.begin(), bps.end()), bps.end());
-            size_t b = 0;  // number of crossovers <= current position
-            for (const Seg &s0 : segs) {
-                Seg s = s0;
-                while (b < bps.size() && bps[b] <= s.left) b++;
-                while (true) {
-                    uint32_t p = par[b & 1];
-                    if (b < bps.size() && bps[b] < s.right) {
-                        if (nxt[p].empty()) next_active.push_back(p);
-                        nxt[p].push_back(Seg{ s.left, bps[b], s.node });
-                        s.left = bps[b];
-                        b++;
-                    } else {
-                        if (nxt[p].empty()) next_active.push_back(p);
-                        nxt[p].push_back(s);
-                        break;
+            bar.wait();
+            // phase 2: group the pieces by parent (counting sort)
+            if (t == 0) {
+                next_active.clear();
+                uint32_t total = 0;
+                for (uint64_t p = 0; p < n; p++) {
+                    uint32_t c = count[p].load(std::memory_order_relaxed);
+                    start[p] = total;
+                    if (c) next_active.push_back((uint32_t) p);
+                    total += c;
+                    cursor[p].store(start[p], std::memory_order_relaxed);
+                    count[p].store(0, std::memory_order_relaxed);
+                }
+                start[n] = total;
+                flat.resize(total);
+                np = next_active.size();
+            }
+            bar.wait();
+            for (const Piece &pc : tpieces[t]) {
+                flat[cursor[pc.parent].fetch_add(1, std::memory_order_relaxed)] = pc.seg;
+            }
+            bar.wait();
+            // phase 3: merge per parent; coalescences get PENDING node ids
+            size_t a0 = np * t / nt, a1 = np * (t + 1) / nt;
+            for (size_t a = a0; a < a1; a++) {
+                uint32_t p = next_active[a];
+                size_t e0 = tedges[t].size();
+                bool c = merge_into_parent(flat.data() + start[p], start[p + 1] - start[p],
+                    tedges[t], out, heap, X);
+                coalesced[p] = c;
+                // remember which individual the PENDING ids of these edges belong to
+                for (size_t e = e0; e < tedges[t].size(); e++) {
+                    tedges[t][e].parent = -(int32_t) p - 2;
+                }
+                cur[p].assign(out.begin(), out.end());
+            }
+            bar.wait();
+            // phase 4: number the new nodes in individual order (thread-count independent)
+            if (t == 0) {
+                for (uint32_t p : next_active) {
+                    if (coalesced[p]) {
+                        newid[p] = (int32_t) R.node_time.size();
+                        R.node_time.push_back((double) g);
+                        R.node_flags.push_back(0);
                     }
                 }
             }
-            segs.clear();
+            bar.wait();
+            for (size_t a = a0; a < a1; a++) {
+                uint32_t p = next_active[a];
+                if (coalesced[p]) {
+                    for (Seg &s : cur[p]) {
+                        if (s.node == PENDING) s.node = newid[p];
+                    }
+                }
+            }
+            for (Edge &e : tedges[t]) {
+                if (e.parent < -1) e.parent = newid[(uint32_t) (-(e.parent + 2))];
+            }
+            bar.wait();
+            if (t == 0) active.swap(next_active);
+            bar.wait();
         }
-        // ids must not depend on hash-bucket order: visit parents in id order
-        std::sort(next_active.begin(), next_active.end());
-        for (uint32_t p : next_active) {
-            int32_t parent_node = -1;
-            merge_into_parent(nxt[p], parent_node, (double) g, R, out, X);
-            cur[p].assign(out.begin(), out.end());
-            nxt[p].clear();
-        }
-        active.swap(next_active);
+    };
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; t++) th.emplace_back(worker, t);
+        worker(0);
+        for (auto &x : th) x.join();
+    }
+    for (unsigned t = 0; t < nt; t++) {
+        R.edges.insert(R.edges.end(), tedges[t].begin(), tedges[t].end());
+        std::vector<Edge>().swap(tedges[t]);
     }
     // squash abutting edges and put them in canonical order
     std::vector<Edge> &E = R.edges;
@@ -197,16 +322,19 @@ void *tskb_wfsim_run(uint64_t n, uint64_t generations, double L, uint32_t ncross
     R.rem.resize(m);
     std::iota(R.ins.begin(), R.ins.end(), 0);
     std::iota(R.rem.begin(), R.rem.end(), 0);
-    std::sort(R.ins.begin(), R.ins.end(), [&](int32_t a, int32_t b) {
-        if (E[a].left != E[b].left) return E[a].left < E[b].left;
-        if (E[a].parent != E[b].parent) return E[a].parent < E[b].parent;
-        return E[a].child < E[b].child;
+    std::thread ti([&]() {
+        std::sort(R.ins.begin(), R.ins.end(), [&](int32_t a, int32_t b) {
+            if (E[a].left != E[b].left) return E[a].left < E[b].left;
+            if (E[a].parent != E[b].parent) return E[a].parent < E[b].parent;
+            return E[a].child < E[b].child;
+        });
     });
     std::sort(R.rem.begin(), R.rem.end(), [&](int32_t a, int32_t b) {
         if (E[a].right != E[b].right) return E[a].right < E[b].right;
         if (E[a].parent != E[b].parent) return E[a].parent > E[b].parent;
         return E[a].child > E[b].child;
     });
+    ti.join();
     return Rp;
 }
 

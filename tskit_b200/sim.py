@@ -34,7 +34,7 @@ def add_mutations(t: Tables, target, seed=1):
     return t
 
 
-def wright_fisher(n, generations, L, ncross=1, seed=42):
+def wright_fisher(n, generations, L, ncross=1, seed=42, num_threads=0):
     """Seeded haploid Wright-Fisher ARG of `n` samples (population size n,
     `generations` generations, `ncross` crossovers per meiosis at integer
     positions in [1, L-1]), already simplified; see csrc/wfsim.cpp."""
@@ -45,11 +45,12 @@ def wright_fisher(n, generations, L, ncross=1, seed=42):
         raise RuntimeError(f"{path} not found: run `make -C tskit_b200/csrc`")
     lib = C.CDLL(path)
     lib.tskb_wfsim_run.restype = C.c_void_p
-    lib.tskb_wfsim_run.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_uint32, C.c_uint64]
+    lib.tskb_wfsim_run.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_uint32, C.c_uint64,
+                                   C.c_uint32]
     lib.tskb_wfsim_sizes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tskb_wfsim_copy.argtypes = [C.c_void_p] * 9
     lib.tskb_wfsim_free.argtypes = [C.c_void_p]
-    h = lib.tskb_wfsim_run(n, generations, float(L), ncross, seed)
+    h = lib.tskb_wfsim_run(n, generations, float(L), ncross, seed, num_threads)
     try:
         N, E = C.c_uint64(), C.c_uint64()
         lib.tskb_wfsim_sizes(h, C.byref(N), C.byref(E))
