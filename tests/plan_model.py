@@ -84,45 +84,54 @@ def build(t, a=None, b=None):
     rank_node = np.lexsort((np.arange(N), level)).astype(np.int32)
     rank = np.empty(N, dtype=np.int64)
     rank[rank_node] = np.arange(N)
-    key = rank[vis_node] if V else np.zeros(0, dtype=np.int64)
-    sorted_vis = np.argsort(key, kind="stable")
-    sorted_key = key[sorted_vis]
-    sorted_ev = vis_ev[sorted_vis]
-    noff = np.searchsorted(sorted_key, np.arange(N + 1))
-    vis_nm = np.empty(V, dtype=np.int64)
-    vis_nm[sorted_vis] = np.arange(V) + sorted_key + 1
-
-    def state_entry(u, i):
-        r = rank[u]
-        lo, hi = noff[r], noff[r + 1]
-        k = np.searchsorted(sorted_ev[lo:hi], i, side="left")
-        return lo + k + r
-
-    ev_src = np.array([state_entry(int(ev_child[i]), i) for i in range(nev)], dtype=np.int64)
-    Vn, Ve = V + N, V + nev
-    nm_src = np.zeros(Vn, dtype=np.int32)
-    nm_flag = np.zeros(Vn, dtype=np.uint8)
-    nm_key = np.zeros(Vn, dtype=np.uint32)
-    idx = np.arange(V) + sorted_key + 1
-    nm_src[idx] = ev_src[sorted_ev]
-    nm_flag[idx] = (ev_sign[sorted_ev] < 0).astype(np.uint8)
-    nm_key[idx] = sorted_key
-    init = noff[:N] + np.arange(N)
-    nm_src[init] = rank_node
-    nm_flag[init] = 2
-    nm_key[init] = np.arange(N)
-    em_idx = np.zeros(Ve, dtype=np.uint32)
-    em_bl2 = np.zeros(Ve, dtype=np.float64)
+    # entries, event-major: CHILD entry of event i at voff[i] + i, then its visits
+    Ve = V + nev
+    em_node = np.zeros(Ve, dtype=np.int64)
+    em_ev = np.zeros(Ve, dtype=np.int64)
+    em_child = np.zeros(Ve, dtype=bool)
+    em_blv = np.zeros(Ve, dtype=np.float64)
     eoff = voff[:-1].astype(np.int64) + np.arange(nev)
-    em_idx[eoff] = ev_src.astype(np.uint32) | np.uint32(0x80000000)
-    em_bl2[eoff] = ev_sbl
+    em_node[eoff] = ev_child
+    em_ev[eoff] = np.arange(nev)
+    em_child[eoff] = True
+    em_blv[eoff] = np.where(ev_sign > 0, ev_sbl, 0.0)
     epos = np.arange(V) + vis_ev + 1
-    em_idx[epos] = vis_nm
-    em_bl2[epos] = vis_bl
+    em_node[epos] = vis_node
+    em_ev[epos] = vis_ev
+    em_blv[epos] = vis_bl
     flag = np.ones(nev, dtype=bool)
     flag[:-1] = ev_pos[:-1] != ev_pos[1:]
-    bp_pos = ev_pos[flag]
-    bp_end = (voff[1:].astype(np.int64) + np.arange(nev) + 1)[flag].astype(np.uint32)
+    ev_bp = np.concatenate([[0], np.cumsum(flag)[:-1]]).astype(np.int64) if nev else np.zeros(0, dtype=np.int64)
+    key = rank[em_node]
+    sorted_e = np.argsort(key, kind="stable")
+    sorted_key = key[sorted_e]
+    noff = np.searchsorted(sorted_key, np.arange(N + 1))
+    bp_k = ev_bp[em_ev[sorted_e]]
+    end = np.ones(Ve, dtype=bool)
+    if Ve > 1:
+        end[:-1] = (sorted_key[1:] != sorted_key[:-1]) | (bp_k[1:] != bp_k[:-1])
+    endscan = np.concatenate([[0], np.cumsum(end)]).astype(np.int64)
+    ends_total = int(endscan[-1])
+    inv = np.empty(Ve, dtype=np.int64)
+    inv[sorted_e] = np.arange(Ve)
+    pidx = endscan[:-1] + sorted_key + 1
+    kc = inv[eoff]
+    ev_src = pidx[kc] - (ev_sign < 0)
+    Na, P = Ve + N, ends_total + N
+    ad = np.zeros(Na, dtype=np.uint32)
+    pc_x = np.zeros(P)
+    pc_bl = np.zeros(P)
+    i_k = em_ev[sorted_e]
+    word = np.where(em_child[sorted_e], np.uint32(3 << 30),
+                    (np.where(ev_sign[i_k] < 0, 1, 0).astype(np.uint32) << np.uint32(30))
+                    | ev_src[i_k].astype(np.uint32))
+    word = word | np.where(end, np.uint32(1 << 29), np.uint32(0))
+    ad[np.arange(Ve) + sorted_key + 1] = word
+    pc_x[pidx[end]] = ev_pos[i_k[end]]
+    pc_bl[pidx[end]] = em_blv[sorted_e[end]]
+    poff = np.concatenate([endscan[noff[:N]] if N else [], [ends_total]]).astype(np.int64) + np.arange(N + 1)
+    ad[noff[:N] + np.arange(N)] = np.uint32((2 << 30) | (1 << 29)) | rank_node.astype(np.uint32)
+    pc_x[poff[:N]] = -1.0
     nlevels = int(level.max()) + 1 if N else 1
     lvl_sorted = level[rank_node]
     lro = np.searchsorted(lvl_sorted, np.arange(nlevels + 1))
@@ -131,20 +140,19 @@ def build(t, a=None, b=None):
     mut_src = np.zeros(t.num_mutations, dtype=np.int32)
     for m in range(t.num_mutations):
         x = t.sites_position[t.mutations_site[m]]
-        e_hi = np.searchsorted(ev_pos, x, side="right")
-        mut_src[m] = state_entry(int(t.mutations_node[m]), e_hi)
+        r = rank[t.mutations_node[m]]
+        lo, hi = poff[r], poff[r + 1]
+        mut_src[m] = lo + np.searchsorted(pc_x[lo:hi], x, side="right") - 1
     return dict(ev_pos=ev_pos, ev_child=ev_child.astype(np.int32), ev_sign=ev_sign, voff=voff,
-                bp_pos=bp_pos, bp_end=bp_end, em_idx=em_idx, em_bl=em_bl2, nm_src=nm_src,
-                nm_flag=nm_flag, nm_key=nm_key, level=level, rank_node=rank_node,
+                ad=ad, pc_x=pc_x, pc_bl=pc_bl, level=level, rank_node=rank_node,
                 level_begin=level_begin, mut_src=mut_src)
 
 
 DTYPES = dict(ev_pos=np.float64, ev_child=np.int32, ev_sign=np.int8, voff=np.uint32,
-              bp_pos=np.float64, bp_end=np.uint32, em_idx=np.uint32, em_bl=np.float64,
-              nm_src=np.int32, nm_flag=np.uint8, nm_key=np.uint32, level=np.uint32,
+              ad=np.uint32, pc_x=np.float64, pc_bl=np.float64, level=np.uint32,
               rank_node=np.int32, level_begin=np.uint32, mut_src=np.int32)
-ORDER = ["ev_pos", "ev_child", "ev_sign", "voff", "bp_pos", "bp_end", "level", "rank_node",
-         "level_begin", "nm_key", "nm_flag", "nm_src", "em_idx", "em_bl", "mut_src"]
+ORDER = ["ev_pos", "ev_child", "ev_sign", "voff", "level", "rank_node", "level_begin", "ad",
+         "pc_x", "pc_bl", "mut_src"]
 
 
 def compare(ll, t, a=None, b=None):

@@ -239,20 +239,6 @@ def test_custom_summary_function_tabulated(wf_small, engines):
     assert np.allclose(g[:, 0], d[:, 0], rtol=1e-12)
 
 
-def test_library_scan_path_agrees(wf_small, monkeypatch):
-    """hand-written look-back propagation == cub::DeviceScan::InclusiveSumByKey path"""
-    from tskit_b200.lowlevel import LLTreeSequence
-    ll = LLTreeSequence(wf_small)
-    s = wf_small.samples
-    sizes, flat = sets_args([s[:90], s[90:]])
-    idx = np.array([[0, 1]], dtype=np.int32)
-    w = np.linspace(0, wf_small.sequence_length, 12)
-    a = ll.divergence(sizes, flat, idx, windows=w, mode="branch")
-    monkeypatch.setenv("TSKB_PROPAGATE", "cub")
-    b = ll.divergence(sizes, flat, idx, windows=w, mode="branch")
-    assert np.array_equal(a, b)
-
-
 def test_genome_range_shards_sum_to_whole(wf_small, engines):
     """multi-GPU decomposition: shards over [a, b) computed independently add up per window"""
     from tskit_b200.lowlevel import LLTreeSequence

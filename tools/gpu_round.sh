@@ -10,16 +10,18 @@ python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exi
 tail -3 $OUT/pytest_gpu.log
 python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
 cat $OUT/bench.json
+if [ -z "$SKIP_REF" ]; then
 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref exit $?"
 cat $OUT/bench_ref.json
-KREGEX='regex:k_(set_weights|level0|propagate|bp_summary|tile_reduce|agg_scan|tile_scan|window|site_summary|entry)'
+fi
+KREGEX='regex:k_(set_weights|propagate|branch_summary|branch_finalize|window|site_summary)'
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 600 \
     --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_launch.log 2>&1
 echo "ncu launches exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_propagate -s 40 -c 2 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_propagate -s 2 -c 2 \
     -o $OUT/prof_propagate -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_prop.log 2>&1
 echo "ncu propagate exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bp_summary -s 1 -c 1 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_branch_summary -s 2 -c 2 \
     -o $OUT/prof_summary -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_sum.log 2>&1
 echo "ncu summary exit $?"
 ls -la $OUT

@@ -29,10 +29,10 @@ Plan::~Plan() {
 uint64_t Plan::device_bytes() const {
     return time.bytes() + d_samples.bytes() + coff.bytes() + csr_left.bytes() + csr_right.bytes()
            + csr_parent.bytes() + ev_pos.bytes() + ev_child.bytes() + ev_sign.bytes()
-           + voff.bytes() + bp_pos.bytes() + bp_end.bytes() + em_idx.bytes() + em_bl.bytes()
-           + nm_src.bytes() + nm_flag.bytes() + nm_key.bytes() + rank_node.bytes()
-           + level.bytes() + site_pos.bytes() + site_moff.bytes() + site_aoff.bytes()
-           + mut_node.bytes() + mut_src.bytes() + mut_allele.bytes() + mut_alt.bytes();
+           + voff.bytes() + ad.bytes() + pc_x.bytes() + pc_bl.bytes() + tiles.bytes()
+           + rank_node.bytes() + level.bytes() + site_pos.bytes() + site_moff.bytes()
+           + site_aoff.bytes() + mut_node.bytes() + mut_src.bytes() + mut_allele.bytes()
+           + mut_alt.bytes();
 }
 
 namespace {
@@ -220,108 +220,135 @@ __global__ void k_scatter_rank(const uint32_t *rank_node, uint32_t N, uint32_t *
     if (r < N) rank[rank_node[r]] = r;
 }
 
-__global__ void k_visit_keys(const int32_t *vis_node, const uint32_t *rank, uint32_t V,
-    uint32_t *key) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < V) key[j] = rank[vis_node[j]];
-}
-
-// Sorted position k (visits sorted by node rank, stable in event order) lives at nm index
-// k + rank + 1: every node's list is preceded by its INIT entry.
-__global__ void k_nm_finish(const uint32_t *sorted_vis, const uint32_t *sorted_key,
-    const uint32_t *vis_ev, uint32_t V, uint32_t *vis_nm, uint32_t *sorted_ev) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < V) {
-        uint32_t j = sorted_vis[k];
-        vis_nm[j] = k + sorted_key[k] + 1;
-        sorted_ev[k] = vis_ev[j];
-    }
-}
-
-// nm entry holding state[u] just before event i (i = nev: after every event <= e_hi):
-// u's last visit among events < i, else u's INIT entry
-__device__ inline uint32_t state_entry(int32_t u, uint32_t i, const uint32_t *rank,
-    const uint32_t *noff, const uint32_t *sorted_ev) {
-    uint32_t r = rank[u];
-    uint32_t lo = noff[r], hi = noff[r + 1];
-    uint32_t k = lower_bound_dev(sorted_ev + lo, hi - lo, i);
-    return lo + k + r;  // k == 0: the INIT entry at lo + r; else visit (lo + k - 1) + r + 1
-}
-
-// src of event i: the state of its child at the moment the reference reads
-// state[child] (trees.c:1436/1462)
-__global__ void k_event_src(const int32_t *ev_child, uint32_t nev, const uint32_t *rank,
-    const uint32_t *noff, const uint32_t *sorted_ev, uint32_t *ev_src) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nev) ev_src[i] = state_entry(ev_child[i], i, rank, noff, sorted_ev);
-}
-
-__global__ void k_nm_fill_visits(const uint32_t *sorted_ev, const uint32_t *sorted_key,
-    uint32_t V, const uint32_t *ev_src, const int8_t *ev_sign, int32_t *nm_src,
-    uint8_t *nm_flag, uint32_t *nm_key) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= V) return;
-    uint32_t i = sorted_ev[k], r = sorted_key[k];
-    uint32_t idx = k + r + 1;
-    nm_src[idx] = (int32_t) ev_src[i];
-    nm_flag[idx] = ev_sign[i] < 0 ? 1 : 0;
-    nm_key[idx] = r;
-}
-
-__global__ void k_nm_fill_init(const uint32_t *noff, const int32_t *rank_node, uint32_t N,
-    int32_t *nm_src, uint8_t *nm_flag, uint32_t *nm_key) {
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= N) return;
-    uint32_t idx = noff[r] + r;
-    nm_src[idx] = rank_node[r];
-    nm_flag[idx] = 2;
-    nm_key[idx] = r;
-}
-
-constexpr uint32_t CHILD_BIT = 0x80000000u;
-
-__global__ void k_em_fill_child(const uint32_t *voff, const uint32_t *ev_src,
-    const double *ev_sbl, uint32_t nev, uint32_t *em_idx, double *em_bl) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nev) return;
-    uint32_t e = voff[i] + i;
-    em_idx[e] = ev_src[i] | CHILD_BIT;
-    em_bl[e] = ev_sbl[i];
-}
-
-__global__ void k_em_fill_visits(const uint32_t *vis_ev, const uint32_t *vis_nm,
-    const double *vis_bl, uint32_t V, uint32_t *em_idx, double *em_bl) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= V) return;
-    uint32_t e = j + vis_ev[j] + 1;
-    em_idx[e] = vis_nm[j];
-    em_bl[e] = vis_bl[j];
-}
-
 __global__ void k_bp_flags(const double *ev_pos, uint32_t nev, uint32_t *flag) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nev) flag[i] = (i + 1 == nev || ev_pos[i] != ev_pos[i + 1]) ? 1u : 0u;
 }
 
-__global__ void k_bp_fill(const double *ev_pos, const uint32_t *flag, const uint32_t *slot,
-    const uint32_t *voff, uint32_t nev, double *bp_pos, uint32_t *bp_end) {
+// Entries in event-major order: for event i, its CHILD entry (the edge's own child gets a new
+// piece: its branch appears / disappears) at e = voff[i] + i, then its visits bottom-up.
+__global__ void k_entry_keys_child(const int32_t *ev_child, const uint32_t *voff,
+    const uint32_t *rank, uint32_t nev, uint32_t *key, uint32_t *em_ev) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nev && flag[i]) {
-        bp_pos[slot[i]] = ev_pos[i];
-        bp_end[slot[i]] = voff[i + 1] + i + 1;
+    if (i >= nev) return;
+    uint32_t e = voff[i] + i;
+    key[e] = rank[ev_child[i]];
+    em_ev[e] = i;
+}
+__global__ void k_entry_keys_visit(const int32_t *vis_node, const uint32_t *vis_ev,
+    const uint32_t *rank, uint32_t V, uint32_t *key, uint32_t *em_ev) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= V) return;
+    uint32_t i = vis_ev[j];
+    uint32_t e = j + i + 1;
+    key[e] = rank[vis_node[j]];
+    em_ev[e] = i;
+}
+
+// node-major position k of every entry; an entry ends its piece when the next entry of the
+// order belongs to another node or another breakpoint
+__global__ void k_entry_ends(const uint32_t *sorted_e, const uint32_t *sorted_key,
+    const uint32_t *em_ev, const uint32_t *ev_bp, uint32_t Ve, uint32_t *inv, uint32_t *endflag) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Ve) return;
+    uint32_t e = sorted_e[k];
+    inv[e] = k;
+    uint32_t end = 1;
+    if (k + 1 < Ve && sorted_key[k + 1] == sorted_key[k]) {
+        end = ev_bp[em_ev[sorted_e[k + 1]]] != ev_bp[em_ev[e]];
+    }
+    endflag[k] = end;
+}
+
+// src of event i: the piece holding state[child] when the reference reads it
+// (trees.c:1436/1462): the child's piece at this breakpoint for an insertion (state right of
+// x), the one before it for a removal (state left of x).  The child's own CHILD entry of
+// event i lies in its piece at this breakpoint.
+__global__ void k_event_src(const uint32_t *voff, const int8_t *ev_sign, const uint32_t *inv,
+    const uint32_t *sorted_key, const uint32_t *endscan, uint32_t nev, uint32_t *ev_src) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nev) return;
+    uint32_t k = inv[voff[i] + i];
+    uint32_t piece = endscan[k] + sorted_key[k] + 1;
+    ev_src[i] = ev_sign[i] < 0 ? piece - 1 : piece;
+}
+
+__global__ void k_fill_entries(const uint32_t *sorted_e, const uint32_t *sorted_key,
+    const uint32_t *em_ev, const uint32_t *endflag, const uint32_t *endscan, const uint32_t *voff,
+    const int8_t *ev_sign, const double *ev_sbl, const double *ev_pos, const uint32_t *ev_src,
+    const double *vis_bl, uint32_t Ve, uint32_t *ad, double *pc_x, double *pc_bl) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Ve) return;
+    uint32_t e = sorted_e[k], r = sorted_key[k], i = em_ev[e];
+    bool child = e == voff[i] + i;
+    uint32_t end = endflag[k];
+    uint32_t word;
+    if (child) {
+        word = AD_ZERO << AD_KIND_SHIFT;
+    } else {
+        word = ((ev_sign[i] < 0 ? AD_NEG : AD_POS) << AD_KIND_SHIFT) | ev_src[i];
+    }
+    ad[k + r + 1] = word | (end ? AD_END : 0u);
+    if (end) {
+        // the piece's branch length is the one in force after the LAST diff of the breakpoint
+        // that touches the node: its own insertion if there is one (trees.c:1455-1457), 0
+        // after its removal (trees.c:1432), else the branch across x
+        double bl = child ? (ev_sign[i] > 0 ? ev_sbl[i] : 0.0) : vis_bl[e - i - 1];
+        uint32_t p = endscan[k] + r + 1;
+        pc_x[p] = ev_pos[i];
+        pc_bl[p] = bl;
     }
 }
 
-// state[mutation.node] at the site's tree = value after the node's last visit
-// among events at positions <= site position (trees.c:1744-1763)
+__global__ void k_fill_init(const uint32_t *noff, const uint32_t *endscan, uint32_t Ve,
+    uint32_t ends_total, const int32_t *rank_node, uint32_t N, uint32_t *ad, double *pc_x,
+    double *pc_bl, uint32_t *poff) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > N) return;
+    uint32_t k = r < N ? noff[r] : Ve;
+    uint32_t p = (k < Ve ? endscan[k] : ends_total) + r;
+    poff[r] = p;
+    if (r < N) {
+        ad[k + r] = (AD_INIT << AD_KIND_SHIFT) | AD_END | (uint32_t) rank_node[r];
+        pc_x[p] = -1.0;
+        pc_bl[p] = 0.0;
+    }
+}
+
+// piece the first addend of each tile belongs to
+__global__ void k_tile_piece(uint4 *tiles, uint32_t ntiles, const uint32_t *noff,
+    const uint32_t *endscan, const uint32_t *poff, uint32_t N, uint32_t Ve, uint32_t ends_total) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ntiles) return;
+    uint32_t s = tiles[g].x;
+    // rank r of the node whose list contains addend s: last r with noff[r] + r <= s
+    uint32_t lo = 0, hi = N;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (noff[mid] + mid <= s) lo = mid + 1; else hi = mid;
+    }
+    uint32_t r = lo - 1;
+    uint32_t piece;
+    if (s == noff[r] + r) {
+        piece = poff[r];
+    } else {
+        uint32_t k = s - r - 1;
+        piece = (k < Ve ? endscan[k] : ends_total) + r + 1;
+    }
+    tiles[g].z = piece;
+}
+
+// state[mutation.node] at the site's tree = the node's last piece starting at or before the
+// site position (trees.c:1744-1763); INIT pieces start at -1
 __global__ void k_mut_src(const int32_t *mut_site, const int32_t *mut_node, uint32_t Mu,
-    const double *site_pos, const double *ev_pos, uint32_t nev, const uint32_t *rank,
-    const uint32_t *noff, const uint32_t *sorted_ev, int32_t *mut_src) {
+    const double *site_pos, const uint32_t *rank, const uint32_t *poff, const double *pc_x,
+    int32_t *mut_src) {
     uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= Mu) return;
     double x = site_pos[mut_site[m]];
-    uint32_t e_hi = upper_bound_dev(ev_pos, nev, x);
-    mut_src[m] = (int32_t) state_entry(mut_node[m], e_hi, rank, noff, sorted_ev);
+    uint32_t r = rank[mut_node[m]];
+    uint32_t lo = poff[r], n = poff[r + 1] - lo;
+    mut_src[m] = (int32_t) (lo + upper_bound_dev(pc_x + lo, n, x) - 1);
 }
 
 // ------------------------------------------------------------ CUB wrappers
@@ -530,10 +557,8 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK(cudaStreamSynchronize(s));
     }
     P.V = V;
-    P.Vn = V + N;
-    P.Ve = V + nev;
-    if ((uint64_t) V + N >= 0x7fffffffull || (uint64_t) V + nev >= 0x7fffffffull) {
-        throw (int) TSKB_ERR_UNSUPPORTED;  // 31-bit entry indexes; shard the genome instead
+    if ((uint64_t) V + nev + N >= 0xffffffffull) {
+        throw (int) TSKB_ERR_UNSUPPORTED;  // 32-bit addend indexes; shard the genome instead
     }
     DevArray<int32_t> vis_node;
     DevArray<double> vis_bl;
@@ -547,29 +572,24 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     }
     ev_parent.release();
 
-    // ---- breakpoints: distinct event positions
+    // ---- breakpoint index of every event (distinct event positions)
+    DevArray<uint32_t> ev_bp;
+    ev_bp.alloc(nev + 1);
     {
-        DevArray<uint32_t> flag, slot;
-        flag.alloc(nev + 1); slot.alloc(nev + 1);
+        DevArray<uint32_t> flag;
+        flag.alloc(nev + 1);
         TSKB_CK(cudaMemsetAsync(flag.p, 0, (nev + 1) * sizeof(uint32_t), s));
         if (nev) {
             k_bp_flags<<<grid_for(nev, TB), TB, 0, s>>>(P.ev_pos.p, nev, flag.p);
             TSKB_CK_LAUNCH();
         }
         size_t bytes = 0;
-        TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.p, slot.p, nev + 1, s));
-        TSKB_CK(cub::DeviceScan::ExclusiveSum(tmp.need(bytes), bytes, flag.p, slot.p, nev + 1, s));
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.p, ev_bp.p, nev + 1, s));
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(tmp.need(bytes), bytes, flag.p, ev_bp.p, nev + 1, s));
         uint32_t T = 0;
-        TSKB_CK(cudaMemcpyAsync(&T, slot.p + nev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        TSKB_CK(cudaMemcpyAsync(&T, ev_bp.p + nev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         TSKB_CK(cudaStreamSynchronize(s));
         P.T = T;
-        P.bp_pos.alloc(T); P.bp_end.alloc(T);
-        if (nev) {
-            k_bp_fill<<<grid_for(nev, TB), TB, 0, s>>>(P.ev_pos.p, flag.p, slot.p, P.voff.p, nev,
-                P.bp_pos.p, P.bp_end.p);
-            TSKB_CK_LAUNCH();
-        }
-        TSKB_CK(cudaStreamSynchronize(s));
     }
 
     // ---- dependency levels: level[parent] > level[child] over every edge
@@ -627,71 +647,103 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK(cudaStreamSynchronize(s));
     }
 
-    // ---- node-major order of the visits
-    const uint32_t Vn = P.Vn, Ve = P.Ve;
-    P.nm_key.alloc(Vn); P.nm_src.alloc(Vn); P.nm_flag.alloc(Vn);
-    P.em_idx.alloc(Ve); P.em_bl.alloc(Ve);
-    DevArray<uint32_t> sorted_ev, noff, sorted_key, vis_nm;
-    sorted_ev.alloc(V); sorted_key.alloc(V); vis_nm.alloc(V);
-    noff.alloc(N + 1);
+    // ---- node-major order of the entries (CHILD entries + visits), pieces, addends
+    const uint32_t Ve = V + nev;
+    P.Na = Ve + N;
+    DevArray<uint32_t> sorted_e, sorted_key, em_ev, noff, endflag, endscan, inv, poff;
+    sorted_e.alloc(Ve); sorted_key.alloc(Ve); em_ev.alloc(Ve); noff.alloc(N + 1);
+    endflag.alloc(Ve + 1); endscan.alloc(Ve + 1); inv.alloc(Ve); poff.alloc(N + 1);
     {
-        DevArray<uint32_t> kin, vin, sorted_vis;
-        kin.alloc(V); vin.alloc(V); sorted_vis.alloc(V);
-        if (V) {
-            k_visit_keys<<<grid_for(V, TB), TB, 0, s>>>(vis_node.p, rank.p, V, kin.p);
-            k_iota<<<grid_for(V, TB), TB, 0, s>>>(vin.p, V);
-            TSKB_CK_LAUNCH();
-            sort_pairs(tmp, kin.p, sorted_key.p, vin.p, sorted_vis.p, V,
-                (int) std::max(1u, ceil_log2(N)), s);
-            k_nm_finish<<<grid_for(V, TB), TB, 0, s>>>(sorted_vis.p, sorted_key.p, vis_ev.p, V,
-                vis_nm.p, sorted_ev.p);
+        DevArray<uint32_t> kin, vin;
+        kin.alloc(Ve); vin.alloc(Ve);
+        if (nev) {
+            k_entry_keys_child<<<grid_for(nev, TB), TB, 0, s>>>(P.ev_child.p, P.voff.p, rank.p,
+                nev, kin.p, em_ev.p);
             TSKB_CK_LAUNCH();
         }
-        k_offsets<<<grid_for(N + 1, TB), TB, 0, s>>>(sorted_key.p, V, N + 1, noff.p);
+        if (V) {
+            k_entry_keys_visit<<<grid_for(V, TB), TB, 0, s>>>(vis_node.p, vis_ev.p, rank.p, V,
+                kin.p, em_ev.p);
+            TSKB_CK_LAUNCH();
+        }
+        if (Ve) {
+            k_iota<<<grid_for(Ve, TB), TB, 0, s>>>(vin.p, Ve);
+            TSKB_CK_LAUNCH();
+            // stable: entries of one node stay in event order
+            sort_pairs(tmp, kin.p, sorted_key.p, vin.p, sorted_e.p, Ve,
+                (int) std::max(1u, ceil_log2(N)), s);
+        }
+        k_offsets<<<grid_for(N + 1, TB), TB, 0, s>>>(sorted_key.p, Ve, N + 1, noff.p);
         TSKB_CK_LAUNCH();
         TSKB_CK(cudaStreamSynchronize(s));
     }
-    vis_node.release();
+    vis_node.release(); vis_ev.release();
+    uint32_t ends_total = 0;
     {
-        // level_begin[l] = nm index of the first entry of level l
+        TSKB_CK(cudaMemsetAsync(endflag.p, 0, (Ve + 1) * sizeof(uint32_t), s));
+        if (Ve) {
+            k_entry_ends<<<grid_for(Ve, TB), TB, 0, s>>>(sorted_e.p, sorted_key.p, em_ev.p,
+                ev_bp.p, Ve, inv.p, endflag.p);
+            TSKB_CK_LAUNCH();
+        }
+        size_t bytes = 0;
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, endflag.p, endscan.p, Ve + 1, s));
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(tmp.need(bytes), bytes, endflag.p, endscan.p, Ve + 1, s));
+        TSKB_CK(cudaMemcpyAsync(&ends_total, endscan.p + Ve, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
+    P.P = ends_total + N;
+    if ((uint64_t) P.P >= AD_PAYLOAD || (uint64_t) N >= AD_PAYLOAD) {
+        throw (int) TSKB_ERR_UNSUPPORTED;  // 29-bit piece indexes; shard the genome instead
+    }
+    P.ad.alloc(P.Na); P.pc_x.alloc(P.P); P.pc_bl.alloc(P.P);
+    {
+        DevArray<uint32_t> ev_src;
+        ev_src.alloc(nev);
+        if (nev) {
+            k_event_src<<<grid_for(nev, TB), TB, 0, s>>>(P.voff.p, P.ev_sign.p, inv.p,
+                sorted_key.p, endscan.p, nev, ev_src.p);
+            TSKB_CK_LAUNCH();
+        }
+        if (Ve) {
+            k_fill_entries<<<grid_for(Ve, TB), TB, 0, s>>>(sorted_e.p, sorted_key.p, em_ev.p,
+                endflag.p, endscan.p, P.voff.p, P.ev_sign.p, ev_sbl.p, P.ev_pos.p, ev_src.p,
+                vis_bl.p, Ve, P.ad.p, P.pc_x.p, P.pc_bl.p);
+            TSKB_CK_LAUNCH();
+        }
+        k_fill_init<<<grid_for(N + 1, TB), TB, 0, s>>>(noff.p, endscan.p, Ve, ends_total,
+            P.rank_node.p, N, P.ad.p, P.pc_x.p, P.pc_bl.p, poff.p);
+        TSKB_CK_LAUNCH();
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
+    ev_sbl.release(); vis_bl.release(); inv.release(); em_ev.release(); sorted_e.release();
+    ev_bp.release(); endflag.release();
+    {
+        // level_begin[l] = ad index of the first entry of level l; tiles never straddle levels
         std::vector<uint32_t> h_lro = lvl_rank_off.download(s);
         std::vector<uint32_t> h_noff = noff.download(s);
         P.level_begin.resize(P.nlevels + 1);
-        P.level_tile0.resize(P.nlevels + 1);
-        uint32_t tiles = 0;
         for (uint32_t l = 0; l <= P.nlevels; l++) {
             P.level_begin[l] = h_noff[h_lro[l]] + h_lro[l];
         }
+        std::vector<uint4> h_tiles;
         for (uint32_t l = 0; l < P.nlevels; l++) {
-            P.level_tile0[l] = tiles;
-            tiles += (P.level_begin[l + 1] - P.level_begin[l] + PROP_TILE - 1) / PROP_TILE;
+            const uint32_t dep = (uint32_t) h_tiles.size();
+            for (uint32_t b0 = P.level_begin[l]; b0 < P.level_begin[l + 1]; b0 += PROP_TILE) {
+                uint32_t cnt = std::min(PROP_TILE, P.level_begin[l + 1] - b0);
+                h_tiles.push_back(make_uint4(b0, cnt, 0u, dep));
+            }
         }
-        P.level_tile0[P.nlevels] = tiles;
+        P.ntiles = (uint32_t) h_tiles.size();
+        P.tiles.upload(h_tiles.data(), h_tiles.size(), s);
+        if (P.ntiles) {
+            k_tile_piece<<<grid_for(P.ntiles, TB), TB, 0, s>>>(P.tiles.p, P.ntiles, noff.p,
+                endscan.p, poff.p, N, Ve, ends_total);
+            TSKB_CK_LAUNCH();
+        }
+        TSKB_CK(cudaStreamSynchronize(s));
     }
-    DevArray<uint32_t> ev_src;
-    ev_src.alloc(nev);
-    if (nev) {
-        k_event_src<<<grid_for(nev, TB), TB, 0, s>>>(P.ev_child.p, nev, rank.p, noff.p,
-            sorted_ev.p, ev_src.p);
-        TSKB_CK_LAUNCH();
-        k_em_fill_child<<<grid_for(nev, TB), TB, 0, s>>>(P.voff.p, ev_src.p, ev_sbl.p, nev,
-            P.em_idx.p, P.em_bl.p);
-        TSKB_CK_LAUNCH();
-    }
-    if (V) {
-        k_nm_fill_visits<<<grid_for(V, TB), TB, 0, s>>>(sorted_ev.p, sorted_key.p, V, ev_src.p,
-            P.ev_sign.p, P.nm_src.p, P.nm_flag.p, P.nm_key.p);
-        k_em_fill_visits<<<grid_for(V, TB), TB, 0, s>>>(vis_ev.p, vis_nm.p, vis_bl.p, V,
-            P.em_idx.p, P.em_bl.p);
-        TSKB_CK_LAUNCH();
-    }
-    if (N) {
-        k_nm_fill_init<<<grid_for(N, TB), TB, 0, s>>>(noff.p, P.rank_node.p, N, P.nm_src.p,
-            P.nm_flag.p, P.nm_key.p);
-        TSKB_CK_LAUNCH();
-    }
-    TSKB_CK(cudaStreamSynchronize(s));
-    ev_sbl.release(); vis_bl.release(); vis_ev.release(); vis_nm.release(); sorted_key.release();
+    sorted_key.release(); endscan.release();
 
     // ---- sites and mutations: allele strings -> small integer codes on the host
     // (replaces the memcmp loops of get_allele_weights, trees.c:1557-1596)
@@ -746,7 +798,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
             DevArray<int32_t> d_msite;
             d_msite.upload(t->mutation_site, Mu, s);
             k_mut_src<<<grid_for(Mu, TB), TB, 0, s>>>(d_msite.p, P.mut_node.p, Mu, P.site_pos.p,
-                P.ev_pos.p, nev, rank.p, noff.p, sorted_ev.p, P.mut_src.p);
+                rank.p, poff.p, P.pc_x.p, P.mut_src.p);
             TSKB_CK_LAUNCH();
             TSKB_CK(cudaStreamSynchronize(s));
         }

@@ -14,21 +14,28 @@
 //                    first and insertions young-parent first
 //                    (c/tskit/tables.c:11392-11459), the walk follows exactly
 //                    the edges that span ACROSS x (left < x < right), which an
-//                    interval query in a child-major edge CSR answers;
-//   * per node, the visits in event order form a list whose running sum is the
-//                    node's state after each visit; the addend of visit (i, u)
-//                    is +-state[child_i] at that moment, i.e. the value after
-//                    the child's last earlier visit ("src");
+//                    interval query in a child-major edge CSR answers.  The same
+//                    ordering means state[child] read by a removal is the child's
+//                    state in the tree LEFT of x and by an insertion its state in
+//                    the tree RIGHT of x -- never an intermediate one;
+//   * piece (u, t) = node u between two consecutive breakpoints that touch it
+//                    (u visited by, or the child of, a diff at breakpoint t):
+//                    state[u] and branch_length[u] are constant over a piece.
+//                    Branch statistics are sums over pieces of
+//                    branch_length * f(state) * |piece ^ window|; the reference's
+//                    running sum (trees.c:1339-1350) telescopes to exactly this;
+//   * addend       = one term of  state(u, t) = state(u, t-) +- state(child_i):
+//                    one per visit, listed node-major so that a node's pieces are
+//                    the running sum of its addend list ("ad"), which starts
+//                    with an INIT entry holding the node's own sample weight;
 //   * nodes are grouped into dependency levels (level[parent] > level[child]
-//                    over every edge) so that all lists of one level can be
+//                    over every edge): all lists of one level can be
 //                    prefix-summed in parallel once lower levels are done.
 //
-// "em" arrays are in event-major order: for event 0, 1, ... one CHILD entry (the
-// edge's own branch appearing/disappearing) followed by its visits bottom-up.
-// "nm" arrays are in node-major order, sorted by (level, node, event); every
-// node's list starts with an INIT entry holding its initial state (its sample
-// weight), so "state before a visit" is always the previous nm entry and a
-// child that was never visited still has an entry to point at.
+// Node-major order is (level, node id, event).  Entry encoding of ad[]:
+//   bits 31-30 kind: 0 +state[src piece], 1 -state[src piece], 2 INIT (payload =
+//   node id), 3 ZERO (node is only the child of the diff: new piece, same state)
+//   bit 29: last addend of its piece;  bits 28-0: payload.
 #pragma once
 
 #include <mutex>
@@ -39,7 +46,9 @@
 
 namespace tskb {
 
-constexpr uint32_t PROP_TILE = 1024;  // nm entries per propagation tile
+constexpr uint32_t PROP_TILE = 1024;  // addends per propagation tile
+constexpr uint32_t AD_KIND_SHIFT = 30, AD_END = 1u << 29, AD_PAYLOAD = AD_END - 1;
+enum AdKind : uint32_t { AD_POS = 0, AD_NEG = 1, AD_INIT = 2, AD_ZERO = 3 };
 
 struct Plan {
     int device = 0;
@@ -52,6 +61,7 @@ struct Plan {
     uint32_t nev = 0;      // events (edge diffs) inside the range
     uint32_t V = 0;        // visits
     uint32_t nlevels = 0;  // max level + 1
+    uint32_t T = 0;        // breakpoints (distinct diff positions) inside the range
     uint32_t num_samples = 0;
     uint32_t site_lo = 0, site_hi = 0;  // sites inside the range
     uint64_t total_alleles = 0;
@@ -59,7 +69,7 @@ struct Plan {
     // host copies needed for argument validation
     std::vector<int32_t> sample_index_map;  // node -> sample index or -1 (trees.c:404-453)
     std::vector<int32_t> samples;
-    std::vector<uint32_t> level_begin;  // nm offset of each level, size nlevels + 1
+    std::vector<uint32_t> level_begin;  // ad offset of each level, size nlevels + 1
 
     // --- tables in HBM ---
     DevArray<double> time;            // [N]
@@ -73,29 +83,25 @@ struct Plan {
     DevArray<int32_t> ev_child;       // [nev]
     DevArray<int8_t> ev_sign;         // [nev] -1 removal, +1 insertion
     DevArray<uint32_t> voff;          // [nev + 1] visit offsets
-    // --- breakpoints (distinct event positions) ---
-    uint32_t T = 0;
-    DevArray<double> bp_pos;          // [T]
-    DevArray<uint32_t> bp_end;        // [T] one past the last em entry of the diffs at bp_pos[t]
-    // --- entries, event-major: Ve = nev + V ---
-    uint32_t Ve = 0;
-    DevArray<uint32_t> em_idx;        // [Ve] nm index of the entry's state; bit 31 set on CHILD entries
-    DevArray<double> em_bl;           // [Ve] CHILD: sign * (time[parent] - time[child]);
-                                      //      visit: branch length above the visited node then (0 at chain top)
-    // --- entries, node-major: Vn = V + N ---
-    uint32_t Vn = 0;
-    DevArray<int32_t> nm_src;         // [Vn] visit: nm index holding state[child of the diff]; INIT: node id
-    DevArray<uint8_t> nm_flag;        // [Vn] bit0: removal (negative addend), bit1: INIT entry (list head)
-    DevArray<uint32_t> nm_key;        // [Vn] rank of the node (kept for the library scan-by-key check path)
+    // --- addend stream, node-major: Na = V + nev + N entries ---
+    uint32_t Na = 0;
+    DevArray<uint32_t> ad;            // [Na] see encoding above
+    // --- pieces, node-major: every node's INIT piece followed by one piece per touching breakpoint
+    uint32_t P = 0;
+    DevArray<double> pc_x;            // [P] left end of the piece (its breakpoint); -1 for INIT
+    DevArray<double> pc_bl;           // [P] branch length above the node over the piece
+    // --- propagation tiles: PROP_TILE consecutive addends of one level
+    uint32_t ntiles = 0;
+    DevArray<uint4> tiles;            // [ntiles] {first addend, count, index of the piece the first
+                                      //  addend belongs to, tiles that must be complete before}
     DevArray<int32_t> rank_node;      // [N] rank -> node id (nodes sorted by (level, id))
     DevArray<uint32_t> level;         // [N]
-    std::vector<uint32_t> level_tile0;  // first look-back descriptor of each level, size nlevels + 1
     // --- sites ---
     DevArray<double> site_pos;        // [S]
     DevArray<uint32_t> site_moff;     // [S + 1] mutation CSR
     DevArray<uint32_t> site_aoff;     // [S + 1] allele-slot CSR
     DevArray<int32_t> mut_node;       // [Mu]
-    DevArray<int32_t> mut_src;        // [Mu] nm index holding state[mutation.node] at the site
+    DevArray<int32_t> mut_src;        // [Mu] piece holding state[mutation.node] at the site
     DevArray<uint16_t> mut_allele;    // [Mu] allele index of the derived state
     DevArray<uint16_t> mut_alt;       // [Mu] allele index the mutation's state is subtracted from
     std::vector<double> h_site_pos;

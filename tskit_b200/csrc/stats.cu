@@ -2,13 +2,15 @@
 // (tsk_treeseq_sample_count_stat -> tsk_treeseq_general_stat, c/tskit/trees.c:2035-2220).
 //
 // Phases of one call (all on the plan's stream):
-//   0 weights    sample sets -> 0/1 int32 weight rows per node         (trees.c:2195-2213)
-//   1 propagate  per dependency level: addend gather + segmented prefix sum over the
-//                node-major visit lists = state[u] after every visit   (trees.c:1317-1327)
-//   2 summary    branch: per edge diff, change of the running sum      (trees.c:1339-1350, 1425-1474)
-//                site:   per site, allele states and sum of f          (trees.c:1525-1652)
-//   3 scan       branch: running sum after every diff (prefix sum over diffs)
-//   4 windows    integrate / bin into windows, span-normalise          (trees.c:1484-1504, 1753-1762, 1920-1934)
+//   0 weights    sample sets -> 0/1 int32 weight rows per node          (trees.c:2195-2213)
+//   1 propagate  ONE launch: addend gather + segmented prefix sum over the node-major addend
+//                lists = state[u] over every piece; tiles of a level wait on a completion
+//                counter for the levels below                           (trees.c:1317-1327)
+//   2 summary    branch: stream the pieces, G = branch_length * f(state), bin G - G_prev into
+//                the window holding the piece's left end                (trees.c:1339-1350, 1484-1504)
+//                site:   per site, allele states and sum of f           (trees.c:1525-1652)
+//   3 finalize   branch: prefix over windows + span-normalise; site: window sums
+//                                                                       (trees.c:1753-1762, 1920-1934)
 //   5 d2h        result -> host
 #include <cub/cub.cuh>
 
@@ -23,129 +25,127 @@ namespace tskb {
 namespace {
 
 constexpr int TB = 256;
-constexpr int MC = 4;  // result columns evaluated per pass over an event's visits
 
 template <int KP>
 struct alignas(KP >= 4 ? 16 : 4 * KP) IVec {
     int32_t v[KP];
-    __host__ __device__ IVec operator+(const IVec &o) const {
+    __host__ __device__ __forceinline__ IVec operator+(const IVec &o) const {
         IVec r;
 #pragma unroll
         for (int k = 0; k < KP; k++) r.v[k] = v[k] + o.v[k];
         return r;
     }
+    __host__ __device__ __forceinline__ IVec operator-(const IVec &o) const {
+        IVec r;
+#pragma unroll
+        for (int k = 0; k < KP; k++) r.v[k] = v[k] - o.v[k];
+        return r;
+    }
+};
+
+template <int KP>
+__device__ __forceinline__ IVec<KP> ivec_zero() {
+    IVec<KP> r;
+#pragma unroll
+    for (int k = 0; k < KP; k++) r.v[k] = 0;
+    return r;
+}
+
+// one result column: the sample-set indexes of its tuple and their sizes
+struct ColP {
+    int32_t i, j, k, l;
+    double ni, nj, nk, nl;
 };
 
 struct SumP {
-    int stat;
     int K;
     int M;
     int polarised;
-    int skip_zero_bl;  // summaries are finite: a zero branch length contributes exactly 0
-    double n[8];
-    const int32_t *idx;    // device [M * tuple]
-    const double *table;   // device [rows * M] (STAT_TABULATED)
+    double n[8];            // sample set sizes
+    const ColP *cols;       // device [M]
+    const double *table;    // device [rows * M] (STAT_TABULATED)
     uint32_t table_rows;
 };
 
+// x[i] without dynamic register indexing
+template <int KP>
+__device__ __forceinline__ double pick(const IVec<KP> &s, int i) {
+    int32_t r = s.v[0];
+#pragma unroll
+    for (int k = 1; k < KP; k++) r = (i == k) ? s.v[k] : r;
+    return (double) r;
+}
+
 // The summary functions, in the reference's exact operation order
 // (c/tskit/trees.c:3934-3948, 4221-4264, 4690-4773, 4899-4959, 5177-5291).
-// x: the K state values as doubles; P.n: sample set sizes.
-__device__ __forceinline__ double f_eval(const SumP &P, const double *x, int m) {
-    switch (P.stat) {
-        case STAT_DIVERSITY: {
-            double n = P.n[m], xm = x[m];
-            return xm * (n - xm) / (n * (n - 1));
+template <int STAT, int KP>
+__device__ __forceinline__ double f_eval(const SumP &P, const ColP &c, int m, const IVec<KP> &s) {
+    if constexpr (STAT == STAT_DIVERSITY) {
+        double n = c.ni, x = pick<KP>(s, c.i);
+        return x * (n - x) / (n * (n - 1));
+    } else if constexpr (STAT == STAT_SEGSITES) {
+        double n = c.ni, x = pick<KP>(s, c.i);
+        return (x > 0) * (1 - x / n);
+    } else if constexpr (STAT == STAT_Y1) {
+        double ni = c.ni, xi = pick<KP>(s, c.i);
+        double denom = ni * (ni - 1) * (ni - 2);
+        double numer = xi * (ni - xi) * (ni - xi - 1);
+        return numer / denom;
+    } else if constexpr (STAT == STAT_DIVERGENCE) {
+        double ni = c.ni, nj = c.nj;
+        double denom = ni * (nj - (c.i == c.j));
+        return pick<KP>(s, c.i) * (nj - pick<KP>(s, c.j)) / denom;
+    } else if constexpr (STAT == STAT_Y2) {
+        double ni = c.ni, nj = c.nj;
+        double xi = pick<KP>(s, c.i), xj = pick<KP>(s, c.j);
+        double denom = ni * nj * (nj - 1);
+        return xi * (nj - xj) * (nj - xj - 1) / denom;
+    } else if constexpr (STAT == STAT_F2) {
+        double ni = c.ni, nj = c.nj;
+        double xi = pick<KP>(s, c.i), xj = pick<KP>(s, c.j);
+        double denom = ni * (ni - 1) * nj * (nj - 1);
+        double numer = xi * (xi - 1) * (nj - xj) * (nj - xj - 1) - xi * (ni - xi) * (nj - xj) * xj;
+        return numer / denom;
+    } else if constexpr (STAT == STAT_RELATEDNESS) {
+        double sumx = 0;
+#pragma unroll
+        for (int k = 0; k < KP; k++) {
+            if (k < P.K) sumx += (double) s.v[k] / P.n[k];
         }
-        case STAT_SEGSITES: {
-            double n = P.n[m], xm = x[m];
-            return (xm > 0) * (1 - xm / n);
-        }
-        case STAT_Y1: {
-            double ni = P.n[m], xi = x[m];
-            double denom = ni * (ni - 1) * (ni - 2);
-            double numer = xi * (ni - xi) * (ni - xi - 1);
-            return numer / denom;
-        }
-        case STAT_DIVERGENCE: {
-            int i = P.idx[2 * m], j = P.idx[2 * m + 1];
-            double ni = P.n[i], nj = P.n[j];
-            double denom = ni * (nj - (i == j));
-            return x[i] * (nj - x[j]) / denom;
-        }
-        case STAT_Y2: {
-            int i = P.idx[2 * m], j = P.idx[2 * m + 1];
-            double ni = P.n[i], nj = P.n[j];
-            double xi = x[i], xj = x[j];
-            double denom = ni * nj * (nj - 1);
-            return xi * (nj - xj) * (nj - xj - 1) / denom;
-        }
-        case STAT_F2: {
-            int i = P.idx[2 * m], j = P.idx[2 * m + 1];
-            double ni = P.n[i], nj = P.n[j];
-            double xi = x[i], xj = x[j];
-            double denom = ni * (ni - 1) * nj * (nj - 1);
-            double numer = xi * (xi - 1) * (nj - xj) * (nj - xj - 1)
-                           - xi * (ni - xi) * (nj - xj) * xj;
-            return numer / denom;
-        }
-        case STAT_RELATEDNESS: {
-            double sumx = 0;
-            for (int k = 0; k < P.K; k++) sumx += x[k] / P.n[k];
-            double meanx = sumx / (double) P.K;
-            int i = P.idx[2 * m], j = P.idx[2 * m + 1];
-            double ni = P.n[i], nj = P.n[j];
-            return (x[i] / ni - meanx) * (x[j] / nj - meanx);
-        }
-        case STAT_RELATEDNESS_NC: {
-            int i = P.idx[2 * m], j = P.idx[2 * m + 1];
-            double ni = P.n[i], nj = P.n[j];
-            return x[i] * x[j] / (ni * nj);
-        }
-        case STAT_Y3: {
-            int i = P.idx[3 * m], j = P.idx[3 * m + 1], k = P.idx[3 * m + 2];
-            double ni = P.n[i], nj = P.n[j], nk = P.n[k];
-            double denom = ni * nj * nk;
-            double numer = x[i] * (nj - x[j]) * (nk - x[k]);
-            return numer / denom;
-        }
-        case STAT_F3: {
-            int i = P.idx[3 * m], j = P.idx[3 * m + 1], k = P.idx[3 * m + 2];
-            double ni = P.n[i], nj = P.n[j], nk = P.n[k];
-            double xi = x[i], xj = x[j], xk = x[k];
-            double denom = ni * (ni - 1) * nj * nk;
-            double numer = xi * (xi - 1) * (nj - xj) * (nk - xk) - xi * (ni - xi) * (nj - xj) * xk;
-            return numer / denom;
-        }
-        case STAT_F4: {
-            int i = P.idx[4 * m], j = P.idx[4 * m + 1], k = P.idx[4 * m + 2], l = P.idx[4 * m + 3];
-            double ni = P.n[i], nj = P.n[j], nk = P.n[k], nl = P.n[l];
-            double xi = x[i], xj = x[j], xk = x[k], xl = x[l];
-            double denom = ni * nj * nk * nl;
-            double numer = xi * xk * (nj - xj) * (nl - xl) - xi * xl * (nj - xj) * (nk - xk);
-            return numer / denom;
-        }
-        case STAT_TABULATED: {
-            uint32_t c = (uint32_t) x[0];
-            if (c >= P.table_rows) c = P.table_rows - 1;
-            return P.table[(size_t) c * P.M + m];
-        }
+        double meanx = sumx / (double) P.K;
+        return (pick<KP>(s, c.i) / c.ni - meanx) * (pick<KP>(s, c.j) / c.nj - meanx);
+    } else if constexpr (STAT == STAT_RELATEDNESS_NC) {
+        return pick<KP>(s, c.i) * pick<KP>(s, c.j) / (c.ni * c.nj);
+    } else if constexpr (STAT == STAT_Y3) {
+        double denom = c.ni * c.nj * c.nk;
+        double numer = pick<KP>(s, c.i) * (c.nj - pick<KP>(s, c.j)) * (c.nk - pick<KP>(s, c.k));
+        return numer / denom;
+    } else if constexpr (STAT == STAT_F3) {
+        double ni = c.ni, nj = c.nj, nk = c.nk;
+        double xi = pick<KP>(s, c.i), xj = pick<KP>(s, c.j), xk = pick<KP>(s, c.k);
+        double denom = ni * (ni - 1) * nj * nk;
+        double numer = xi * (xi - 1) * (nj - xj) * (nk - xk) - xi * (ni - xi) * (nj - xj) * xk;
+        return numer / denom;
+    } else if constexpr (STAT == STAT_F4) {
+        double ni = c.ni, nj = c.nj, nk = c.nk, nl = c.nl;
+        double xi = pick<KP>(s, c.i), xj = pick<KP>(s, c.j), xk = pick<KP>(s, c.k),
+               xl = pick<KP>(s, c.l);
+        double denom = ni * nj * nk * nl;
+        double numer = xi * xk * (nj - xj) * (nl - xl) - xi * xl * (nj - xj) * (nk - xk);
+        return numer / denom;
+    } else {  // STAT_TABULATED
+        uint32_t cnt = (uint32_t) s.v[0];
+        if (cnt >= P.table_rows) cnt = P.table_rows - 1;
+        return __ldg(P.table + (size_t) cnt * P.M + m);
     }
-    return 0.0;
 }
 
 // branch mode: f(x) + f(total - x) unless polarised (trees.c:1944-1972)
-template <int KP>
-__device__ __forceinline__ double F_branch(const SumP &P, const IVec<KP> &c, int m) {
-    double x[KP];
-#pragma unroll
-    for (int k = 0; k < KP; k++) x[k] = (double) c.v[k];
-    double r = f_eval(P, x, m);
-    if (!P.polarised) {
-#pragma unroll
-        for (int k = 0; k < KP; k++) x[k] = (k < P.K ? P.n[k] : 0.0) - x[k];
-        r += f_eval(P, x, m);
-    }
+template <int STAT, int KP>
+__device__ __forceinline__ double F_branch(const SumP &P, const ColP &c, int m, const IVec<KP> &s,
+    const IVec<KP> &totals) {
+    double r = f_eval<STAT, KP>(P, c, m, s);
+    if (!P.polarised) r += f_eval<STAT, KP>(P, c, m, totals - s);
     return r;
 }
 
@@ -162,147 +162,170 @@ __global__ void k_set_weights(const int32_t *sets, const uint32_t *set_off, uint
 }
 
 // ---------------------------------------------------------------- phase 1
-// state[u] after every visit = running sum over u's node-major list, whose first
-// (INIT) entry is u's own sample weight (trees.c:1406-1415) and whose other
-// addends are +-state[child of the diff] (update_state, trees.c:1317-1327).
+// state[u] over every piece = running sum over u's node-major addend list, whose first
+// (INIT) entry is u's own sample weight (trees.c:1406-1415) and whose other addends are
+// +-state[child of the diff] (update_state, trees.c:1317-1327).
+//
+// One launch covers every level.  Tiles are claimed in order through a ticket, so a tile only
+// ever waits on tiles claimed earlier, which are resident: (a) on the completion counter, until
+// every tile of the lower levels has published its states, then (b) within the level, by
+// decoupled look-back, on the carry of a node list that began in an earlier tile.
+// (value, head, ends) triples combine as
+//   a (+) b = b.head ? (b.value, 1, a.ends + b.ends) : (a.value + b.value, a.head, a.ends + b.ends).
 
-// library check path: addends materialised, then cub::DeviceScan::InclusiveSumByKey
-template <int KP>
-__global__ void k_gather_delta(uint32_t begin, uint32_t end, const int32_t *nm_src,
-    const uint8_t *nm_flag, const IVec<KP> *val, const IVec<KP> *w, IVec<KP> *delta) {
-    uint32_t k = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= end) return;
-    int32_t s = nm_src[k];
-    uint8_t f = nm_flag[k];
-    IVec<KP> x = (f & 2) ? w[s] : val[s];
-    if (f & 1) {
-#pragma unroll
-        for (int q = 0; q < KP; q++) x.v[q] = -x.v[q];
-    }
-    delta[k - begin] = x;
-}
-
-// level 0: nodes that are never a parent; their lists are the INIT entry alone
-template <int KP>
-__global__ void k_level0(uint32_t end, const int32_t *nm_src, const IVec<KP> *w, IVec<KP> *val) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < end) val[k] = w[nm_src[k]];
-}
-
-// Fused addend gather + segmented inclusive scan of one level, single pass with
-// decoupled look-back between tiles.  A segment = one node's list; list heads are
-// the INIT entries.  (value, head) pairs combine as
-//   a (+) b = b.head ? b : (a.value + b.value, a.head).
 template <int KP>
 struct SegVal {
     IVec<KP> v;
     int head;
+    int ends;
 };
 template <int KP>
 struct SegOp {
     __device__ __forceinline__ SegVal<KP> operator()(const SegVal<KP> &a, const SegVal<KP> &b) const {
-        if (b.head) return b;
         SegVal<KP> r;
-        r.v = a.v + b.v;
-        r.head = a.head;
+        if (b.head) {
+            r.v = b.v;
+            r.head = 1;
+        } else {
+            r.v = a.v + b.v;
+            r.head = a.head;
+        }
+        r.ends = a.ends + b.ends;
         return r;
     }
 };
 
-// descriptors are written by one CTA and read by others in the same launch: bypass L1
-template <int KP>
-__device__ __forceinline__ SegVal<KP> load_cg(const SegVal<KP> *p) {
-    SegVal<KP> r;
-    const int *q = reinterpret_cast<const int *>(p);
-#pragma unroll
-    for (int c = 0; c < KP; c++) r.v.v[c] = __ldcg(q + c);
-    r.head = __ldcg(reinterpret_cast<const int *>(&p->head));
-    return r;
-}
-template <int KP>
-__device__ __forceinline__ void store_cg(SegVal<KP> *p, const SegVal<KP> &x) {
-    int *q = reinterpret_cast<int *>(p);
-#pragma unroll
-    for (int c = 0; c < KP; c++) __stcg(q + c, x.v.v[c]);
-    __stcg(reinterpret_cast<int *>(&p->head), x.head);
-}
-
 // look-back descriptor of one tile: status 0 = empty, 1 = aggregate ready, 2 = prefix ready
 template <int KP>
 struct TileDesc {
-    SegVal<KP> agg;
-    SegVal<KP> prefix;
-    volatile int status;
-    int pad[3];
+    int agg[KP + 1];     // value, head
+    int prefix[KP + 1];
+    int status;
+    int pad[(KP + 1) % 2 == 0 ? 1 : 2];
 };
+
+// descriptors and states are written by one CTA and read by others in the same launch: L2 only
+template <int KP>
+__device__ __forceinline__ SegVal<KP> desc_load(const int *q) {
+    SegVal<KP> r;
+#pragma unroll
+    for (int c = 0; c < KP; c++) r.v.v[c] = __ldcg(q + c);
+    r.head = __ldcg(q + KP);
+    r.ends = 0;
+    return r;
+}
+template <int KP>
+__device__ __forceinline__ void desc_store(int *q, const SegVal<KP> &x) {
+#pragma unroll
+    for (int c = 0; c < KP; c++) __stcg(q + c, x.v.v[c]);
+    __stcg(q + KP, x.head);
+}
+template <int KP>
+__device__ __forceinline__ IVec<KP> state_load(const IVec<KP> *p) {
+    IVec<KP> r;
+    if constexpr (KP >= 4) {
+        const int4 *q = reinterpret_cast<const int4 *>(p);
+#pragma unroll
+        for (int c = 0; c < KP / 4; c++) {
+            int4 t = __ldcg(q + c);
+            r.v[4 * c] = t.x; r.v[4 * c + 1] = t.y; r.v[4 * c + 2] = t.z; r.v[4 * c + 3] = t.w;
+        }
+    } else if constexpr (KP == 2) {
+        int2 t = __ldcg(reinterpret_cast<const int2 *>(p));
+        r.v[0] = t.x; r.v[1] = t.y;
+    } else {
+        r.v[0] = __ldcg(reinterpret_cast<const int *>(p));
+    }
+    return r;
+}
 
 constexpr int PROP_TB = 256;
 constexpr int PROP_IPT = PROP_TILE / PROP_TB;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;  // ~seconds; a legitimate wait is < the kernel's own run time
 
 template <int KP>
-__global__ void __launch_bounds__(PROP_TB) k_propagate_level(uint32_t begin, uint32_t end,
-    const int32_t *__restrict__ nm_src, const uint8_t *__restrict__ nm_flag,
-    const IVec<KP> *__restrict__ w, IVec<KP> *val, TileDesc<KP> *desc, uint32_t *ticket,
-    int *error_flag) {
+__global__ void __launch_bounds__(PROP_TB) k_propagate(const uint4 *__restrict__ tiles,
+    const uint32_t *__restrict__ ad, const IVec<KP> *__restrict__ w, IVec<KP> *pval,
+    TileDesc<KP> *desc, uint32_t *counters, int *error_flag) {
     typedef cub::BlockScan<SegVal<KP>, PROP_TB> BS;
     __shared__ typename BS::TempStorage tmp;
     __shared__ uint32_t s_tile;
     __shared__ SegVal<KP> s_carry;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    if (threadIdx.x == 0) s_tile = atomicAdd(&counters[0], 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint32_t base = begin + tile * PROP_TILE + threadIdx.x * PROP_IPT;
+    const uint4 meta = __ldg(tiles + tile);
+    const uint32_t local0 = threadIdx.x * PROP_IPT;
     SegOp<KP> op;
+
+    // the addend words do not depend on other tiles: fetch them before waiting
+    uint32_t word[PROP_IPT];
+#pragma unroll
+    for (int q = 0; q < PROP_IPT; q++) {
+        word[q] = local0 + q < meta.y ? __ldg(ad + meta.x + local0 + q) : (AD_ZERO << AD_KIND_SHIFT);
+    }
+    // (a) every lower level complete
+    if (meta.w > 0) {
+        if (threadIdx.x == 0) {
+            volatile uint32_t *done = counters + 1;
+            uint32_t spins = 0;
+            while (*done < meta.w) {
+                if (++spins > SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int *) error_flag)) {
+                    *error_flag = 1;
+                    break;
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
 
     // gather addends; thread-local segmented scan
     SegVal<KP> item[PROP_IPT];
 #pragma unroll
     for (int q = 0; q < PROP_IPT; q++) {
-        uint32_t k = base + q;
+        const uint32_t kind = word[q] >> AD_KIND_SHIFT, pay = word[q] & AD_PAYLOAD;
         SegVal<KP> x;
-#pragma unroll
-        for (int c = 0; c < KP; c++) x.v.v[c] = 0;
+        x.v = ivec_zero<KP>();
         x.head = 0;
-        if (k < end) {
-            int32_t s = nm_src[k];
-            uint8_t f = nm_flag[k];
-            x.v = (f & 2) ? w[s] : val[s];
-            if (f & 1) {
-#pragma unroll
-                for (int c = 0; c < KP; c++) x.v.v[c] = -x.v.v[c];
-            }
-            x.head = (f & 2) ? 1 : 0;
+        x.ends = (word[q] & AD_END) ? 1 : 0;
+        if (kind == AD_INIT) {
+            x.v = w[pay];
+            x.head = 1;
+        } else if (kind != AD_ZERO) {
+            IVec<KP> g = state_load<KP>(pval + pay);
+            x.v = kind == AD_NEG ? ivec_zero<KP>() - g : g;
         }
         item[q] = q == 0 ? x : op(item[q - 1], x);
     }
-    SegVal<KP> thread_agg = item[PROP_IPT - 1];
     SegVal<KP> identity;
-#pragma unroll
-    for (int c = 0; c < KP; c++) identity.v.v[c] = 0;
+    identity.v = ivec_zero<KP>();
     identity.head = 0;
+    identity.ends = 0;
     SegVal<KP> thread_excl, tile_agg;
-    BS(tmp).ExclusiveScan(thread_agg, thread_excl, identity, op, tile_agg);
+    BS(tmp).ExclusiveScan(item[PROP_IPT - 1], thread_excl, identity, op, tile_agg);
 
-    // decoupled look-back: carry entering this tile
+    // (b) carry entering this tile
     if (threadIdx.x == 0) {
         SegVal<KP> carry = identity;
         TileDesc<KP> *me = desc + tile;
-        if (tile == 0) {
-            store_cg(&me->prefix, tile_agg);
+        if (tile == meta.w) {  // first tile of its level
+            desc_store<KP>(me->prefix, tile_agg);
             __threadfence();
-            me->status = 2;
+            *(volatile int *) &me->status = 2;
         } else {
-            store_cg(&me->agg, tile_agg);
+            desc_store<KP>(me->agg, tile_agg);
             __threadfence();
-            me->status = 1;
+            *(volatile int *) &me->status = 1;
             {
                 int32_t p = (int32_t) tile - 1;
                 uint32_t spins = 0;
                 while (true) {
                     TileDesc<KP> *d = desc + p;
-                    int st = d->status;
+                    int st = *(volatile int *) &d->status;
                     if (st == 0) {
-                        if (++spins > (1u << 28)) {
+                        if (++spins > SPIN_LIMIT
+                            || ((spins & 1023u) == 0 && *(volatile int *) error_flag)) {
                             *error_flag = 1;
                             break;
                         }
@@ -310,221 +333,217 @@ __global__ void __launch_bounds__(PROP_TB) k_propagate_level(uint32_t begin, uin
                     }
                     __threadfence();
                     if (st == 2) {
-                        carry = op(load_cg(&d->prefix), carry);
+                        carry = op(desc_load<KP>(d->prefix), carry);
                         break;
                     }
-                    carry = op(load_cg(&d->agg), carry);
-                    if (carry.head || p == 0) break;
+                    carry = op(desc_load<KP>(d->agg), carry);
+                    if (carry.head || p == (int32_t) meta.w) break;
                     p--;
                 }
             }
-            store_cg(&me->prefix, op(carry, tile_agg));
+            desc_store<KP>(me->prefix, op(carry, tile_agg));
             __threadfence();
-            me->status = 2;
+            *(volatile int *) &me->status = 2;
         }
         s_carry = carry;
     }
     __syncthreads();
-    // values entering this thread: carry (+) thread_excl
+    // values entering this thread: carry (+) thread_excl; publish the state at every piece end
     SegVal<KP> in = op(s_carry, thread_excl);
+    const uint32_t piece0 = meta.z + (uint32_t) thread_excl.ends;
 #pragma unroll
     for (int q = 0; q < PROP_IPT; q++) {
-        uint32_t k = base + q;
-        if (k < end) {
+        if (word[q] & AD_END) {
             SegVal<KP> r = op(in, item[q]);
-            val[k] = r.v;
+            pval[piece0 + (uint32_t) item[q].ends - 1] = r.v;
         }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&counters[1], 1u);
     }
 }
 
-// ---------------------------------------------------------------- phase 2
+// ---------------------------------------------------------------- phase 2, branch mode
+// Node u contributes  sum over its pieces of  G = branch_length * F(state)  times the overlap
+// of the piece with each window.  A piece ends where the next one starts, so this is the sum
+// over pieces of (G - G_prev) * |[x, range_right) ^ window|: every piece adds
+//   c = G - G_prev   to A[w(x)]  (all windows right of w(x) gain c * their span) and
+//   c * (right(w(x)) - x)  to B[w(x)].
+// This is the reference's running sum (trees.c:1339-1350, 1484-1504) with the updates of one
+// node at one breakpoint telescoped.
 
-constexpr uint32_t CHILD_BIT = 0x80000000u;
+constexpr int SUM_IPT = 4;
+constexpr int SUM_TILE = TB * SUM_IPT;
 
-// branch mode.  One warp per breakpoint: sum over the diffs at that position of the change of
-// the running sum  sum_u branch_length[u] * summary[u]  (update_running_sum,
-// trees.c:1339-1350; loops :1425-1474):
-//   CHILD entry: +-(time[p] - time[c]) * F(state[c])          (trees.c:1428-1432, 1455-1457)
-//   visit entry: bl[u] * (F(state[u] after) - F(state[u] before))  (trees.c:1434-1447, 1460-1473)
-template <int KP>
-__global__ void k_bp_summary(uint32_t T, const uint32_t *__restrict__ bp_end,
-    const uint32_t *__restrict__ em_idx, const double *__restrict__ em_bl,
-    const IVec<KP> *__restrict__ val, SumP P, double *B) {
-    uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
-    if (t >= T) return;
-    uint32_t j0 = t > 0 ? bp_end[t - 1] : 0, j1 = bp_end[t];
-    for (int m0 = 0; m0 < P.M; m0 += MC) {
-        double acc[MC];
+template <int STAT, int KP, bool SMEM>
+__global__ void __launch_bounds__(TB) k_branch_summary(uint32_t P, const double *__restrict__ pc_x,
+    const double *__restrict__ pc_bl, const IVec<KP> *__restrict__ pval, SumP sp, IVec<KP> totals,
+    const double *__restrict__ windows, uint32_t W, double range_right, uint32_t mc, double *gA,
+    double *gB) {
+    extern __shared__ double smem[];
+    double *s_win = smem;                      // [W + 1]
+    double *s_A = smem + (W + 1);              // [mc][W]
+    double *s_B = s_A + (size_t) mc * W;       // [mc][W]
+    const uint32_t m0 = blockIdx.y * mc;
+    const uint32_t m1 = min(m0 + mc, (uint32_t) sp.M);
+    if (SMEM) {
+        for (uint32_t i = threadIdx.x; i <= W; i += TB) s_win[i] = windows[i];
+        for (uint32_t i = threadIdx.x; i < 2 * mc * W; i += TB) s_A[i] = 0.0;
+        __syncthreads();
+    }
+    const double *win = SMEM ? s_win : windows;
+    const uint32_t ntiles = (P + SUM_TILE - 1) / SUM_TILE;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t first = tile * SUM_TILE + threadIdx.x * SUM_IPT;
+        double x[SUM_IPT], bl[SUM_IPT + 1];
+        IVec<KP> s[SUM_IPT + 1];
+        bool prev_real = false;
+        // predecessor of the first item (same node unless that item is an INIT piece)
+        s[0] = ivec_zero<KP>();
+        bl[0] = 0.0;
+        if (first > 0 && first < P) {
+            prev_real = pc_x[first - 1] >= 0.0;
+            bl[0] = pc_bl[first - 1];
+            s[0] = pval[first - 1];
+        }
 #pragma unroll
-        for (int q = 0; q < MC; q++) acc[q] = 0.0;
-        for (uint32_t j = j0 + lane; j < j1; j += 32) {
-            uint32_t idx = em_idx[j];
-            double bl = em_bl[j];
-            uint32_t k = idx & ~CHILD_BIT;
-            if (idx & CHILD_BIT) {
-                IVec<KP> xc = val[k];
+        for (int q = 0; q < SUM_IPT; q++) {
+            uint32_t p = first + q;
+            x[q] = -1.0;
+            bl[q + 1] = 0.0;
+            s[q + 1] = ivec_zero<KP>();
+            if (p < P) {
+                x[q] = pc_x[p];
+                bl[q + 1] = pc_bl[p];
+                s[q + 1] = pval[p];
+            }
+        }
+        uint32_t wi[SUM_IPT];
+        double rem[SUM_IPT];
 #pragma unroll
-                for (int q = 0; q < MC; q++) {
-                    if (m0 + q < P.M) acc[q] += bl * F_branch<KP>(P, xc, m0 + q);
+        for (int q = 0; q < SUM_IPT; q++) {
+            wi[q] = 0;
+            rem[q] = 0.0;
+            if (x[q] >= 0.0) {
+                uint32_t u = upper_bound_dev(win, W + 1, x[q]);
+                u = u > 0 ? u - 1 : 0;
+                if (u >= W) u = W - 1;
+                wi[q] = u;
+                double wr = win[u + 1];
+                rem[q] = (wr < range_right ? wr : range_right) - x[q];
+            }
+        }
+        for (uint32_t m = m0; m < m1; m++) {
+            const ColP col = sp.cols[m];
+            double prevG = prev_real ? bl[0] * F_branch<STAT, KP>(sp, col, m, s[0], totals) : 0.0;
+#pragma unroll
+            for (int q = 0; q < SUM_IPT; q++) {
+                if (x[q] < 0.0) {  // INIT piece (or padding): the node is not in any tree yet
+                    prevG = 0.0;
+                    continue;
                 }
-            } else if (bl != 0.0 || !P.skip_zero_bl) {
-                IVec<KP> xn = val[k], xo = val[k - 1];
-#pragma unroll
-                for (int q = 0; q < MC; q++) {
-                    if (m0 + q < P.M) {
-                        acc[q] += bl * (F_branch<KP>(P, xn, m0 + q) - F_branch<KP>(P, xo, m0 + q));
+                double G = bl[q + 1] * F_branch<STAT, KP>(sp, col, m, s[q + 1], totals);
+                double c = G - prevG;
+                prevG = G;
+                if (c != 0.0) {
+                    if (SMEM) {
+                        atomicAdd(&s_A[(size_t) (m - m0) * W + wi[q]], c);
+                        atomicAdd(&s_B[(size_t) (m - m0) * W + wi[q]], c * rem[q]);
+                    } else {
+                        atomicAdd(&gA[(size_t) m * W + wi[q]], c);
+                        atomicAdd(&gB[(size_t) m * W + wi[q]], c * rem[q]);
                     }
                 }
             }
         }
-#pragma unroll
-        for (int q = 0; q < MC; q++) {
-            double v = acc[q];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-            if (lane == 0 && m0 + q < P.M) B[(size_t) (m0 + q) * T + t] = v;
+    }
+    if (SMEM) {
+        __syncthreads();
+        const uint32_t cols = m1 - m0;
+        for (uint32_t i = threadIdx.x; i < cols * W; i += TB) {
+            uint32_t m = m0 + i / W, wdx = i % W;
+            double a = s_A[i], b = s_B[i];
+            if (a != 0.0) atomicAdd(&gA[(size_t) m * W + wdx], a);
+            if (b != 0.0) atomicAdd(&gB[(size_t) m * W + wdx], b);
         }
     }
 }
 
-template <int KP>
+// result[w][m] = (sum of A[m][w'] over w' < w) * |window ^ range| + B[m][w], span-normalised
+// (trees.c:1920-1934).  One block per column, windows in chunks with a running carry.
+__global__ void __launch_bounds__(TB) k_branch_finalize(const double *gA, const double *gB,
+    const double *windows, uint32_t W, uint32_t M, double range_left, double range_right,
+    int span_normalise, double *result) {
+    typedef cub::BlockScan<double, TB> BS;
+    __shared__ typename BS::TempStorage tmp;
+    __shared__ double s_carry;
+    const uint32_t m = blockIdx.x;
+    if (threadIdx.x == 0) s_carry = 0.0;
+    __syncthreads();
+    for (uint32_t base = 0; base < W; base += TB) {
+        uint32_t wdx = base + threadIdx.x;
+        double a = wdx < W ? gA[(size_t) m * W + wdx] : 0.0;
+        double ex, total;
+        BS(tmp).ExclusiveSum(a, ex, total);
+        double carry = s_carry;
+        if (wdx < W) {
+            double wl = windows[wdx], wr = windows[wdx + 1];
+            double l = wl > range_left ? wl : range_left;
+            double r = wr < range_right ? wr : range_right;
+            double v = 0.0;
+            if (r > l) v = (carry + ex) * (r - l) + gB[(size_t) m * W + wdx];
+            if (span_normalise) v /= wr - wl;
+            result[(size_t) wdx * M + m] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- phase 2, site mode
+
+constexpr int MC = 4;  // result columns evaluated per pass over a site's alleles
+
+template <int STAT, int KP>
 __global__ void k_site_summary(uint32_t site_lo, uint32_t nsites, const uint32_t *site_moff,
     const uint32_t *site_aoff, const int32_t *mut_src, const uint16_t *mut_allele,
-    const uint16_t *mut_alt, const IVec<KP> *val, IVec<KP> totals, IVec<KP> *scratch, SumP P,
+    const uint16_t *mut_alt, const IVec<KP> *pval, IVec<KP> totals, IVec<KP> *scratch, SumP P,
     double *R) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsites) return;
     uint32_t site = site_lo + t;
     uint32_t a0 = site_aoff[site], na = site_aoff[site + 1] - a0;
-    IVec<KP> zero;
-#pragma unroll
-    for (int k = 0; k < KP; k++) zero.v[k] = 0;
+    const uint32_t mb = site_moff[site], me = site_moff[site + 1];
+    if (na == 2 && me - mb == 1) {
+        // one mutation, two alleles: no scratch traffic
+        IVec<KP> x = pval[mut_src[mb]];
+        IVec<KP> anc = totals - x;
+        for (int m = 0; m < P.M; m++) {
+            const ColP col = P.cols[m];
+            double acc = 0.0;
+            if (!P.polarised) acc += f_eval<STAT, KP>(P, col, m, anc);
+            acc += f_eval<STAT, KP>(P, col, m, x);
+            R[(size_t) m * nsites + t] = acc;
+        }
+        return;
+    }
     scratch[a0] = totals;  // allele 0 starts at total_weight (trees.c:1548)
-    for (uint32_t al = 1; al < na; al++) scratch[a0 + al] = zero;
-    for (uint32_t m = site_moff[site]; m < site_moff[site + 1]; m++) {
-        IVec<KP> x = val[mut_src[m]];
-        IVec<KP> d = scratch[a0 + mut_allele[m]];
-        scratch[a0 + mut_allele[m]] = d + x;
-        IVec<KP> e = scratch[a0 + mut_alt[m]];
-#pragma unroll
-        for (int k = 0; k < KP; k++) e.v[k] -= x.v[k];
-        scratch[a0 + mut_alt[m]] = e;
+    for (uint32_t al = 1; al < na; al++) scratch[a0 + al] = ivec_zero<KP>();
+    for (uint32_t m = mb; m < me; m++) {
+        IVec<KP> x = pval[mut_src[m]];
+        scratch[a0 + mut_allele[m]] = scratch[a0 + mut_allele[m]] + x;
+        scratch[a0 + mut_alt[m]] = scratch[a0 + mut_alt[m]] - x;
     }
-    for (int m0 = 0; m0 < P.M; m0 += MC) {
-        double acc[MC];
-#pragma unroll
-        for (int q = 0; q < MC; q++) acc[q] = 0.0;
+    for (int m = 0; m < P.M; m++) {
+        const ColP col = P.cols[m];
+        double acc = 0.0;
         for (uint32_t al = P.polarised ? 1 : 0; al < na; al++) {
-            IVec<KP> c = scratch[a0 + al];
-            double x[KP];
-#pragma unroll
-            for (int k = 0; k < KP; k++) x[k] = (double) c.v[k];
-#pragma unroll
-            for (int q = 0; q < MC; q++) {
-                if (m0 + q < P.M) acc[q] += f_eval(P, x, m0 + q);
-            }
+            acc += f_eval<STAT, KP>(P, col, m, scratch[a0 + al]);
         }
-#pragma unroll
-        for (int q = 0; q < MC; q++) {
-            if (m0 + q < P.M) R[(size_t) (m0 + q) * nsites + t] = acc[q];
-        }
-    }
-}
-
-// ---------------------------------------------------------------- phase 3
-// Deterministic three-step prefix sum over each row of D[M][n]:
-// tile sums -> scan of tile sums -> tile-local scan with carry-in.
-
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = TB * SCAN_ITEMS;
-
-__global__ void k_tile_reduce(const double *D, uint32_t n, uint32_t ntiles, double *agg) {
-    typedef cub::BlockReduce<double, TB> BR;
-    __shared__ typename BR::TempStorage tmp;
-    uint32_t tile = blockIdx.x, m = blockIdx.y;
-    const double *row = D + (size_t) m * n;
-    double v[SCAN_ITEMS];
-    uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-#pragma unroll
-    for (int q = 0; q < SCAN_ITEMS; q++) v[q] = base + q < n ? row[base + q] : 0.0;
-    double s = 0;
-#pragma unroll
-    for (int q = 0; q < SCAN_ITEMS; q++) s += v[q];
-    double tot = BR(tmp).Sum(s);
-    if (threadIdx.x == 0) agg[(size_t) m * ntiles + tile] = tot;
-}
-
-// one block per row: exclusive scan of the tile sums (in place)
-constexpr int AGG_TB = 512;
-__global__ void __launch_bounds__(AGG_TB) k_agg_scan(double *agg, uint32_t ntiles) {
-    typedef cub::BlockScan<double, AGG_TB> BS;
-    __shared__ typename BS::TempStorage tmp;
-    __shared__ double carry;
-    double *row = agg + (size_t) blockIdx.x * ntiles;
-    if (threadIdx.x == 0) carry = 0.0;
-    __syncthreads();
-    for (uint32_t base = 0; base < ntiles; base += AGG_TB) {
-        uint32_t i = base + threadIdx.x;
-        double v = i < ntiles ? row[i] : 0.0;
-        double ex, total;
-        BS(tmp).ExclusiveSum(v, ex, total);
-        double c = carry;
-        if (i < ntiles) row[i] = c + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry = c + total;
-        __syncthreads();
-    }
-}
-
-__global__ void k_tile_scan(double *D, uint32_t n, uint32_t ntiles, const double *agg) {
-    typedef cub::BlockScan<double, TB> BS;
-    __shared__ typename BS::TempStorage tmp;
-    uint32_t tile = blockIdx.x, m = blockIdx.y;
-    double *row = D + (size_t) m * n;
-    double v[SCAN_ITEMS];
-    uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-#pragma unroll
-    for (int q = 0; q < SCAN_ITEMS; q++) v[q] = base + q < n ? row[base + q] : 0.0;
-    BS(tmp).InclusiveSum(v, v);
-    double c = agg[(size_t) m * ntiles + tile];
-#pragma unroll
-    for (int q = 0; q < SCAN_ITEMS; q++) {
-        if (base + q < n) row[base + q] = c + v[q];
-    }
-}
-
-// ---------------------------------------------------------------- phase 4
-
-// branch: result[w] = sum_t S_t * |[pos_t, pos_{t+1}) ^ window w| over breakpoints t, S_t the
-// running sum once every diff at pos_t is applied (trees.c:1484-1504)
-__global__ void k_window_branch(const double *windows, uint32_t nsplit, const double *bp_pos,
-    uint32_t T, double range_right, const double *S, uint32_t M, double *partial) {
-    typedef cub::BlockReduce<double, TB> BR;
-    __shared__ typename BR::TempStorage tmp;
-    uint32_t w = blockIdx.x, c = blockIdx.y;
-    double wl = windows[w], wr = windows[w + 1];
-    uint32_t lo = upper_bound_dev(bp_pos, T, wl);
-    lo = lo > 0 ? lo - 1 : 0;
-    uint32_t hi = lower_bound_dev(bp_pos, T, wr);
-    if (hi < lo) hi = lo;
-    uint32_t len = hi - lo, per = (len + nsplit - 1) / nsplit;
-    uint32_t s0 = lo + c * per, s1 = s0 + per;
-    if (s0 > hi) s0 = hi;
-    if (s1 > hi) s1 = hi;
-    for (uint32_t m = 0; m < M; m++) {
-        const double *row = S + (size_t) m * T;
-        double sum = 0.0;
-        for (uint32_t i = s0 + threadIdx.x; i < s1; i += TB) {
-            double p = bp_pos[i];
-            double nx = i + 1 < T ? bp_pos[i + 1] : range_right;
-            double l = p > wl ? p : wl;
-            double r = nx < wr ? nx : wr;
-            if (r > l) sum += row[i] * (r - l);
-        }
-        double tot = BR(tmp).Sum(sum);
-        if (threadIdx.x == 0) partial[((size_t) w * nsplit + c) * M + m] = tot;
-        __syncthreads();
+        R[(size_t) m * nsites + t] = acc;
     }
 }
 
@@ -596,23 +615,107 @@ __global__ void k_count_at(const int32_t *tracked, uint32_t nt, uint32_t nq, uin
 
 // ---------------------------------------------------------------- driver
 
-struct Launches {
-    uint64_t n = 0;
+constexpr size_t SMEM_BIN_BUDGET = 96 * 1024;
+
+struct CallCtx {
+    const Plan *P;
+    const StatSpec *sp;
+    cudaStream_t s;
+    SumP sumP;
+    double *d_windows;
+    double *d_result;
+    uint64_t launches;
 };
 
-static bool use_cub_propagate() {
-    const char *e = getenv("TSKB_PROPAGATE");
-    return e != nullptr && strcmp(e, "cub") == 0;
+template <int STAT, int KP>
+void launch_branch(CallCtx &c, const IVec<KP> *pval, IVec<KP> totals) {
+    const Plan &P = *c.P;
+    const uint32_t W = c.sp->W, M = c.sp->M;
+    Arena &A = P.arena;
+    double *gA = A.get<double>((size_t) 2 * M * W);
+    double *gB = gA + (size_t) M * W;
+    TSKB_CK(cudaMemsetAsync(gA, 0, (size_t) 2 * M * W * sizeof(double), c.s));
+    const uint32_t ntiles = (P.P + SUM_TILE - 1) / SUM_TILE;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
+    const size_t win_bytes = (size_t) (W + 1) * sizeof(double);
+    const size_t col_bytes = (size_t) 2 * W * sizeof(double);
+    if (P.P > 0) {
+        if (win_bytes + col_bytes <= SMEM_BIN_BUDGET) {
+            uint32_t mc = (uint32_t) std::min<size_t>(M, (SMEM_BIN_BUDGET - win_bytes) / col_bytes);
+            uint32_t chunks = (M + mc - 1) / mc;
+            size_t smem = win_bytes + mc * col_bytes;
+            auto kern = k_branch_summary<STAT, KP, true>;
+            TSKB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            int per_sm = 1;
+            TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, smem));
+            uint32_t gx = std::min<uint32_t>(ntiles, (uint32_t) (sms * std::min(std::max(per_sm, 1), 4)));
+            kern<<<dim3(gx, chunks), TB, smem, c.s>>>(P.P, P.pc_x.p, P.pc_bl.p, pval, c.sumP, totals,
+                c.d_windows, W, P.range_right, mc, gA, gB);
+        } else {
+            auto kern = k_branch_summary<STAT, KP, false>;
+            uint32_t gx = std::min<uint32_t>(ntiles, (uint32_t) sms * 8);
+            kern<<<dim3(gx, 1), TB, 0, c.s>>>(P.P, P.pc_x.p, P.pc_bl.p, pval, c.sumP, totals,
+                c.d_windows, W, P.range_right, M, gA, gB);
+        }
+        TSKB_CK_LAUNCH();
+        c.launches++;
+    }
+    TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+    k_branch_finalize<<<M, TB, 0, c.s>>>(gA, gB, c.d_windows, W, M, P.range_left, P.range_right,
+        (c.sp->options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0, c.d_result);
+    TSKB_CK_LAUNCH();
+    c.launches++;
+    TSKB_CK(cudaEventRecord(P.ev[4], c.s));
+}
+
+template <int STAT, int KP>
+void launch_site(CallCtx &c, const IVec<KP> *pval, IVec<KP> totals) {
+    const Plan &P = *c.P;
+    const uint32_t W = c.sp->W, M = c.sp->M;
+    Arena &A = P.arena;
+    const uint32_t nsites = P.site_hi - P.site_lo;
+    const uint32_t nsplit = std::max<uint32_t>(1, (592 + W - 1) / W);
+    double *partial = A.get<double>((size_t) W * nsplit * M);
+    double *R = A.get<double>((size_t) M * std::max<uint32_t>(nsites, 1));
+    IVec<KP> *scratch = A.get<IVec<KP>>(P.total_alleles + 1);
+    if (nsites) {
+        k_site_summary<STAT, KP><<<grid_for(nsites, 128), 128, 0, c.s>>>(P.site_lo, nsites,
+            P.site_moff.p, P.site_aoff.p, P.mut_src.p, P.mut_allele.p, P.mut_alt.p, pval, totals,
+            scratch, c.sumP, R);
+        TSKB_CK_LAUNCH();
+        c.launches++;
+    }
+    TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+    k_window_site<<<dim3(W, nsplit), TB, 0, c.s>>>(c.d_windows, nsplit, P.site_pos.p, P.site_lo,
+        nsites, R, M, partial);
+    TSKB_CK_LAUNCH();
+    k_window_final<<<grid_for((size_t) W * M, TB), TB, 0, c.s>>>(partial, c.d_windows, W, nsplit, M,
+        (c.sp->options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0, c.d_result);
+    TSKB_CK_LAUNCH();
+    c.launches += 2;
+    TSKB_CK(cudaEventRecord(P.ev[4], c.s));
+}
+
+template <int STAT, int KP>
+void launch_summary(CallCtx &c, const IVec<KP> *pval, IVec<KP> totals) {
+    if (c.sp->options & TSKB_STAT_BRANCH) {
+        launch_branch<STAT, KP>(c, pval, totals);
+    } else {
+        launch_site<STAT, KP>(c, pval, totals);
+    }
 }
 
 template <int KP>
 int run_impl(const Plan &P, const StatSpec &sp) {
     cudaStream_t s = P.stream;
-    Launches L;
     const uint32_t K = sp.K, M = sp.M, W = sp.W, N = (uint32_t) P.N;
-    const bool branch = (sp.options & TSKB_STAT_BRANCH) != 0;
     Arena &A = P.arena;
     A.reset();
+    CallCtx c = {};
+    c.P = &P;
+    c.sp = &sp;
+    c.s = s;
     TSKB_CK(cudaEventRecord(P.ev[0], s));
 
     // ---- phase 0: weights
@@ -631,32 +734,37 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         d_sets = tmp_sets;
     }
     TSKB_CK(cudaMemcpyAsync(d_off, h_off.data(), (K + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    double *d_windows = A.get<double>(W + 1);
-    TSKB_CK(cudaMemcpyAsync(d_windows, sp.windows, (W + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
+    c.d_windows = A.get<double>(W + 1);
+    TSKB_CK(cudaMemcpyAsync(c.d_windows, sp.windows, (W + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
     TSKB_CK(cudaMemsetAsync(w, 0, (size_t) N * sizeof(IVec<KP>), s));
     k_set_weights<KP><<<grid_for(total, TB), TB, 0, s>>>(d_sets, d_off, K, (uint32_t) total, w);
     TSKB_CK_LAUNCH();
-    L.n++;
+    c.launches++;
 
-    SumP sumP = {};
-    sumP.stat = sp.stat_id;
+    SumP &sumP = c.sumP;
     sumP.K = (int) K;
     sumP.M = (int) M;
     sumP.polarised = (sp.options & TSKB_STAT_POLARISED) ? 1 : 0;
-    uint64_t min_size = ~uint64_t(0);
     IVec<KP> totals;
     for (int k = 0; k < KP; k++) totals.v[k] = 0;
     for (uint32_t k = 0; k < K; k++) {
         sumP.n[k] = (double) sp.sizes[k];
         totals.v[k] = (int32_t) sp.sizes[k];
-        min_size = std::min<uint64_t>(min_size, sp.sizes[k]);
     }
-    sumP.skip_zero_bl = min_size > 3 ? 1 : 0;
-    if (sp.tuple > 0) {
-        int32_t *d_idx = A.get<int32_t>((size_t) M * sp.tuple);
-        TSKB_CK(cudaMemcpyAsync(d_idx, sp.indexes, (size_t) M * sp.tuple * sizeof(int32_t),
-            cudaMemcpyHostToDevice, s));
-        sumP.idx = d_idx;
+    std::vector<ColP> cols(M);
+    {
+        for (uint32_t m = 0; m < M; m++) {
+            ColP &q = cols[m];
+            int32_t t[4] = { (int32_t) (m < K ? m : 0), 0, 0, 0 };
+            for (uint32_t a = 0; a < sp.tuple; a++) t[a] = sp.indexes[(size_t) m * sp.tuple + a];
+            if (sp.stat_id == STAT_TABULATED) t[0] = 0;
+            q.i = t[0]; q.j = t[1]; q.k = t[2]; q.l = t[3];
+            q.ni = (double) sp.sizes[t[0]]; q.nj = (double) sp.sizes[t[1]];
+            q.nk = (double) sp.sizes[t[2]]; q.nl = (double) sp.sizes[t[3]];
+        }
+        ColP *d_cols = A.get<ColP>(M);
+        TSKB_CK(cudaMemcpyAsync(d_cols, cols.data(), M * sizeof(ColP), cudaMemcpyHostToDevice, s));
+        sumP.cols = d_cols;
     }
     if (sp.stat_id == STAT_TABULATED) {
         double *d_tab = A.get<double>(sp.table_rows * M);
@@ -664,116 +772,51 @@ int run_impl(const Plan &P, const StatSpec &sp) {
             cudaMemcpyHostToDevice, s));
         sumP.table = d_tab;
         sumP.table_rows = (uint32_t) sp.table_rows;
-        bool finite = true;
-        for (uint64_t q = 0; q < sp.table_rows * M; q++) finite = finite && std::isfinite(sp.f_table[q]);
-        sumP.skip_zero_bl = finite ? 1 : 0;
     }
     TSKB_CK(cudaEventRecord(P.ev[1], s));
 
     // ---- phase 1: propagate
-    IVec<KP> *val = A.get<IVec<KP>>(P.Vn);
-    const std::vector<uint32_t> &lb = P.level_begin;
-    if (lb[1] > 0) {
-        k_level0<KP><<<grid_for(lb[1], TB), TB, 0, s>>>(lb[1], P.nm_src.p, w, val);
-        TSKB_CK_LAUNCH();
-        L.n++;
-    }
+    IVec<KP> *pval = A.get<IVec<KP>>(P.P);
     int *d_err = A.get<int>(1);
     TSKB_CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
-    if (use_cub_propagate()) {
-        uint32_t max_range = 0;
-        for (uint32_t l = 1; l < P.nlevels; l++) max_range = std::max(max_range, lb[l + 1] - lb[l]);
-        IVec<KP> *delta = A.get<IVec<KP>>(max_range);
-        size_t scan_bytes = 0;
-        if (max_range) {
-            TSKB_CK(cub::DeviceScan::InclusiveSumByKey(nullptr, scan_bytes, P.nm_key.p, delta, val,
-                max_range, ::cuda::std::equal_to<>(), s));
-        }
-        char *scan_tmp = A.get<char>(scan_bytes);
-        for (uint32_t l = 1; l < P.nlevels; l++) {
-            uint32_t b0 = lb[l], b1 = lb[l + 1];
-            if (b1 == b0) continue;
-            k_gather_delta<KP><<<grid_for(b1 - b0, TB), TB, 0, s>>>(b0, b1, P.nm_src.p,
-                P.nm_flag.p, val, w, delta);
-            L.n++;
-            size_t bytes = scan_bytes;
-            TSKB_CK(cub::DeviceScan::InclusiveSumByKey(scan_tmp, bytes, P.nm_key.p + b0, delta,
-                val + b0, b1 - b0, ::cuda::std::equal_to<>(), s));
-        }
-    } else {
-        const uint32_t ntiles = P.level_tile0[P.nlevels];
-        TileDesc<KP> *desc = A.get<TileDesc<KP>>(ntiles + 1);
-        uint32_t *ticket = A.get<uint32_t>(P.nlevels + 1);
-        TSKB_CK(cudaMemsetAsync(desc, 0, (size_t) (ntiles + 1) * sizeof(TileDesc<KP>), s));
-        TSKB_CK(cudaMemsetAsync(ticket, 0, (P.nlevels + 1) * sizeof(uint32_t), s));
-        for (uint32_t l = 1; l < P.nlevels; l++) {
-            uint32_t b0 = lb[l], b1 = lb[l + 1];
-            if (b1 == b0) continue;
-            uint32_t tiles = P.level_tile0[l + 1] - P.level_tile0[l];
-            k_propagate_level<KP><<<tiles, PROP_TB, 0, s>>>(b0, b1, P.nm_src.p, P.nm_flag.p, w,
-                val, desc + P.level_tile0[l], ticket + l, d_err);
-            L.n++;
-        }
+    if (P.ntiles) {
+        TileDesc<KP> *desc = A.get<TileDesc<KP>>(P.ntiles);
+        uint32_t *counters = A.get<uint32_t>(2);
+        TSKB_CK(cudaMemsetAsync(desc, 0, (size_t) P.ntiles * sizeof(TileDesc<KP>), s));
+        TSKB_CK(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
+        k_propagate<KP><<<P.ntiles, PROP_TB, 0, s>>>(P.tiles.p, P.ad.p, w, pval, desc, counters, d_err);
+        TSKB_CK_LAUNCH();
+        c.launches++;
     }
-    TSKB_CK_LAUNCH();
     TSKB_CK(cudaEventRecord(P.ev[2], s));
 
-    // ---- phases 2-4
-    const uint32_t nsplit = std::max<uint32_t>(1, (592 + W - 1) / W);
-    double *partial = A.get<double>((size_t) W * nsplit * M);
-    double *d_result = sp.result_on_device ? sp.result : A.get<double>((size_t) W * M);
-    const int span_norm = (sp.options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0;
-    if (branch) {
-        const uint32_t T = P.T;
-        double *B = A.get<double>((size_t) M * std::max<uint32_t>(T, 1));
-        if (T) {
-            k_bp_summary<KP><<<grid_for((size_t) T * 32, 128), 128, 0, s>>>(T, P.bp_end.p,
-                P.em_idx.p, P.em_bl.p, val, sumP, B);
-            TSKB_CK_LAUNCH();
-            L.n++;
-        }
-        TSKB_CK(cudaEventRecord(P.ev[3], s));
-        if (T) {
-            uint32_t ntiles = (T + SCAN_TILE - 1) / SCAN_TILE;
-            double *agg = A.get<double>((size_t) M * ntiles);
-            k_tile_reduce<<<dim3(ntiles, M), TB, 0, s>>>(B, T, ntiles, agg);
-            k_agg_scan<<<M, AGG_TB, 0, s>>>(agg, ntiles);
-            k_tile_scan<<<dim3(ntiles, M), TB, 0, s>>>(B, T, ntiles, agg);
-            TSKB_CK_LAUNCH();
-            L.n += 3;
-        }
-        TSKB_CK(cudaEventRecord(P.ev[4], s));
-        k_window_branch<<<dim3(W, nsplit), TB, 0, s>>>(d_windows, nsplit, P.bp_pos.p, T,
-            P.range_right, B, M, partial);
-        TSKB_CK_LAUNCH();
-        L.n++;
-    } else {
-        const uint32_t nsites = P.site_hi - P.site_lo;
-        double *R = A.get<double>((size_t) M * std::max<uint32_t>(nsites, 1));
-        IVec<KP> *scratch = A.get<IVec<KP>>(P.total_alleles + 1);
-        if (nsites) {
-            k_site_summary<KP><<<grid_for(nsites, 128), 128, 0, s>>>(P.site_lo, nsites,
-                P.site_moff.p, P.site_aoff.p, P.mut_src.p, P.mut_allele.p, P.mut_alt.p, val,
-                totals, scratch, sumP, R);
-            TSKB_CK_LAUNCH();
-            L.n++;
-        }
-        TSKB_CK(cudaEventRecord(P.ev[3], s));
-        TSKB_CK(cudaEventRecord(P.ev[4], s));
-        k_window_site<<<dim3(W, nsplit), TB, 0, s>>>(d_windows, nsplit, P.site_pos.p, P.site_lo,
-            nsites, R, M, partial);
-        TSKB_CK_LAUNCH();
-        L.n++;
+    // ---- phases 2-3
+    c.d_result = sp.result_on_device ? sp.result : A.get<double>((size_t) W * M);
+    switch (sp.stat_id) {
+        case STAT_DIVERSITY: launch_summary<STAT_DIVERSITY, KP>(c, pval, totals); break;
+        case STAT_SEGSITES: launch_summary<STAT_SEGSITES, KP>(c, pval, totals); break;
+        case STAT_Y1: launch_summary<STAT_Y1, KP>(c, pval, totals); break;
+        case STAT_DIVERGENCE: launch_summary<STAT_DIVERGENCE, KP>(c, pval, totals); break;
+        case STAT_Y2: launch_summary<STAT_Y2, KP>(c, pval, totals); break;
+        case STAT_F2: launch_summary<STAT_F2, KP>(c, pval, totals); break;
+        case STAT_RELATEDNESS: launch_summary<STAT_RELATEDNESS, KP>(c, pval, totals); break;
+        case STAT_RELATEDNESS_NC: launch_summary<STAT_RELATEDNESS_NC, KP>(c, pval, totals); break;
+        case STAT_Y3: launch_summary<STAT_Y3, KP>(c, pval, totals); break;
+        case STAT_F3: launch_summary<STAT_F3, KP>(c, pval, totals); break;
+        case STAT_F4: launch_summary<STAT_F4, KP>(c, pval, totals); break;
+        case STAT_TABULATED:
+            if constexpr (KP == 1) {
+                launch_summary<STAT_TABULATED, KP>(c, pval, totals);
+                break;
+            }
+            return TSKB_ERR_UNSUPPORTED;
+        default: return TSKB_ERR_BAD_PARAM_VALUE;
     }
-    k_window_final<<<grid_for((size_t) W * M, TB), TB, 0, s>>>(partial, d_windows, W, nsplit, M,
-        span_norm, d_result);
-    TSKB_CK_LAUNCH();
-    L.n++;
     TSKB_CK(cudaEventRecord(P.ev[5], s));
     int h_err = 0;
     TSKB_CK(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
     if (!sp.result_on_device) {
-        TSKB_CK(cudaMemcpyAsync(sp.result, d_result, (size_t) W * M * sizeof(double),
+        TSKB_CK(cudaMemcpyAsync(sp.result, c.d_result, (size_t) W * M * sizeof(double),
             cudaMemcpyDeviceToHost, s));
     }
     TSKB_CK(cudaEventRecord(P.ev[6], s));
@@ -785,9 +828,9 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     }
     TSKB_CK(cudaEventElapsedTime(&ms, P.ev[0], P.ev[6]));
     P.stats.last_call_ms = ms;
-    P.stats.last_launches = L.n;
+    P.stats.last_launches = c.launches;
     if (h_err) {
-        last_error_string() = "propagation look-back timed out";
+        last_error_string() = "propagation wait timed out";
         return TSKB_ERR_CUDA;
     }
     return 0;
