@@ -29,7 +29,7 @@ Plan::~Plan() {
 uint64_t Plan::device_bytes() const {
     return time.bytes() + d_samples.bytes() + coff.bytes() + csr_left.bytes() + csr_right.bytes()
            + csr_parent.bytes() + ev_pos.bytes() + ev_child.bytes() + ev_sign.bytes()
-           + voff.bytes() + ad.bytes() + pc_x.bytes() + pc_bl.bytes() + tiles.bytes()
+           + voff.bytes() + ad.bytes() + pc_x.bytes() + pc_bl.bytes() + tile_dep.bytes() + wt_piece.bytes()
            + rank_node.bytes() + level.bytes() + site_pos.bytes() + site_moff.bytes()
            + site_aoff.bytes() + mut_node.bytes() + mut_src.bytes() + mut_allele.bytes()
            + mut_alt.bytes();
@@ -273,22 +273,43 @@ __global__ void k_event_src(const uint32_t *voff, const int8_t *ev_sign, const u
     ev_src[i] = ev_sign[i] < 0 ? piece - 1 : piece;
 }
 
+__global__ void k_fill_f64(double *out, size_t n, double v) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
+__global__ void k_fill_u32(uint32_t *out, size_t n, uint32_t v) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
 __global__ void k_fill_entries(const uint32_t *sorted_e, const uint32_t *sorted_key,
     const uint32_t *em_ev, const uint32_t *endflag, const uint32_t *endscan, const uint32_t *voff,
     const int8_t *ev_sign, const double *ev_sbl, const double *ev_pos, const uint32_t *ev_src,
-    const double *vis_bl, uint32_t Ve, uint32_t *ad, double *pc_x, double *pc_bl) {
+    const double *vis_bl, const uint32_t *inv, uint32_t Ve, const int32_t *rank_node,
+    const uint32_t *level, const uint32_t *padoff, uint32_t *ad, double *pc_x, double *pc_bl) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Ve) return;
     uint32_t e = sorted_e[k], r = sorted_key[k], i = em_ev[e];
-    bool child = e == voff[i] + i;
+    const uint32_t e0 = voff[i] + i;  // CHILD entry of the event; its visits follow bottom-up
+    bool child = e == e0;
     uint32_t end = endflag[k];
-    uint32_t word;
-    if (child) {
-        word = AD_ZERO << AD_KIND_SHIFT;
-    } else {
+    uint32_t word = AD_ZERO_WORD;
+    if (e == e0 + 1) {
+        // first iteration of the walk: the edge's parent gains / loses state[child]
         word = ((ev_sign[i] < 0 ? AD_NEG : AD_POS) << AD_KIND_SHIFT) | ev_src[i];
+    } else if (!child) {
+        // later iteration: the walk came up through v = the node visited just before.  All
+        // walks of this breakpoint through v add up to state(v, t) - state(v, t-); the one
+        // owning v's first entry at this breakpoint carries that term, the others nothing.
+        uint32_t kv = inv[e - 1];
+        bool first = kv == 0 || endflag[kv - 1] != 0;
+        if (first) {
+            uint32_t rv = sorted_key[kv];
+            word = (AD_DIFF << AD_KIND_SHIFT) | (endscan[kv] + rv + 1);
+        }
     }
-    ad[k + r + 1] = word | (end ? AD_END : 0u);
+    ad[k + r + 1 + padoff[level[rank_node[r]]]] = word | (end ? AD_END : 0u);
     if (end) {
         // the piece's branch length is the one in force after the LAST diff of the breakpoint
         // that touches the node: its own insertion if there is one (trees.c:1455-1457), 0
@@ -301,26 +322,35 @@ __global__ void k_fill_entries(const uint32_t *sorted_e, const uint32_t *sorted_
 }
 
 __global__ void k_fill_init(const uint32_t *noff, const uint32_t *endscan, uint32_t Ve,
-    uint32_t ends_total, const int32_t *rank_node, uint32_t N, uint32_t *ad, double *pc_x,
-    double *pc_bl, uint32_t *poff) {
+    uint32_t ends_total, const int32_t *rank_node, const uint32_t *level, const uint32_t *padoff,
+    uint32_t N, uint32_t *ad, double *pc_x, double *pc_bl, uint32_t *poff) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r > N) return;
     uint32_t k = r < N ? noff[r] : Ve;
     uint32_t p = (k < Ve ? endscan[k] : ends_total) + r;
     poff[r] = p;
     if (r < N) {
-        ad[k + r] = (AD_INIT << AD_KIND_SHIFT) | AD_END | (uint32_t) rank_node[r];
+        int32_t u = rank_node[r];
+        ad[k + r + padoff[level[u]]] = AD_INIT_WORD | (uint32_t) u;
         pc_x[p] = -1.0;
         pc_bl[p] = 0.0;
     }
 }
 
-// piece the first addend of each tile belongs to
-__global__ void k_tile_piece(uint4 *tiles, uint32_t ntiles, const uint32_t *noff,
-    const uint32_t *endscan, const uint32_t *poff, uint32_t N, uint32_t Ve, uint32_t ends_total) {
+// piece the first addend of each warp tile belongs to (= pieces that end before it).
+// tile_u0 / tile_uend: unpadded addend index of the CTA tile's start / of its level's end.
+__global__ void k_tile_piece(const uint32_t *tile_u0, const uint32_t *tile_uend, uint32_t nwt,
+    const uint32_t *noff, const uint32_t *endscan, const uint32_t *poff, uint32_t N, uint32_t Ve,
+    uint32_t ends_total, uint32_t *wt_piece) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ntiles) return;
-    uint32_t s = tiles[g].x;
+    if (g >= nwt) return;
+    uint32_t tile = g / PROP_WARPS, wq = g % PROP_WARPS;
+    uint32_t s = tile_u0[tile] + wq * WTILE;
+    if (s > tile_uend[tile]) s = tile_uend[tile];
+    if (s >= Ve + N) {
+        wt_piece[g] = ends_total + N;
+        return;
+    }
     // rank r of the node whose list contains addend s: last r with noff[r] + r <= s
     uint32_t lo = 0, hi = N;
     while (lo < hi) {
@@ -335,7 +365,7 @@ __global__ void k_tile_piece(uint4 *tiles, uint32_t ntiles, const uint32_t *noff
         uint32_t k = s - r - 1;
         piece = (k < Ve ? endscan[k] : ends_total) + r + 1;
     }
-    tiles[g].z = piece;
+    wt_piece[g] = piece;
 }
 
 // state[mutation.node] at the site's tree = the node's last piece starting at or before the
@@ -649,7 +679,6 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
 
     // ---- node-major order of the entries (CHILD entries + visits), pieces, addends
     const uint32_t Ve = V + nev;
-    P.Na = Ve + N;
     DevArray<uint32_t> sorted_e, sorted_key, em_ev, noff, endflag, endscan, inv, poff;
     sorted_e.alloc(Ve); sorted_key.alloc(Ve); em_ev.alloc(Ve); noff.alloc(N + 1);
     endflag.alloc(Ve + 1); endscan.alloc(Ve + 1); inv.alloc(Ve); poff.alloc(N + 1);
@@ -696,10 +725,53 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     if ((uint64_t) P.P >= AD_PAYLOAD || (uint64_t) N >= AD_PAYLOAD) {
         throw (int) TSKB_ERR_UNSUPPORTED;  // 29-bit piece indexes; shard the genome instead
     }
-    P.ad.alloc(P.Na); P.pc_x.alloc(P.P); P.pc_bl.alloc(P.P);
+    // ---- level layout of the addend stream: every level padded to whole CTA tiles
+    DevArray<uint32_t> padoff, tile_u0, tile_uend;
+    {
+        std::vector<uint32_t> h_lro = lvl_rank_off.download(s);
+        std::vector<uint32_t> h_noff = noff.download(s);
+        std::vector<uint32_t> ub(P.nlevels + 1), h_pad(P.nlevels + 1), h_dep, h_u0, h_uend;
+        P.level_begin.resize(P.nlevels + 1);
+        uint64_t padded = 0;
+        for (uint32_t l = 0; l <= P.nlevels; l++) {
+            ub[l] = h_noff[h_lro[l]] + h_lro[l];
+        }
+        for (uint32_t l = 0; l < P.nlevels; l++) {
+            P.level_begin[l] = (uint32_t) padded;
+            h_pad[l] = (uint32_t) (padded - ub[l]);
+            const uint32_t dep = (uint32_t) h_dep.size();
+            for (uint32_t u = ub[l]; u < ub[l + 1]; u += PROP_TILE) {
+                h_dep.push_back(dep);
+                h_u0.push_back(u);
+                h_uend.push_back(ub[l + 1]);
+            }
+            padded = (uint64_t) h_dep.size() * PROP_TILE;
+            if (padded >= 0xffffffffull) throw (int) TSKB_ERR_UNSUPPORTED;
+        }
+        P.level_begin[P.nlevels] = (uint32_t) padded;
+        h_pad[P.nlevels] = 0;
+        P.Na = (uint32_t) padded;
+        P.ntiles = (uint32_t) h_dep.size();
+        padoff.upload(h_pad.data(), h_pad.size(), s);
+        P.tile_dep.upload(h_dep.data(), h_dep.size(), s);
+        tile_u0.upload(h_u0.data(), h_u0.size(), s);
+        tile_uend.upload(h_uend.data(), h_uend.size(), s);
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
+    // pieces are streamed in whole tiles of 1024 by the summary kernel: pad with INIT markers
+    const size_t P_pad = ((size_t) P.P + 1023) / 1024 * 1024;
+    P.ad.alloc(P.Na); P.pc_x.alloc(P_pad); P.pc_bl.alloc(P_pad);
+    TSKB_CK(cudaMemsetAsync(P.pc_bl.p, 0, P_pad * sizeof(double), s));
+    k_fill_f64<<<grid_for(P_pad - P.P + 1, TB), TB, 0, s>>>(P.pc_x.p + P.P, P_pad - P.P, -1.0);
+    TSKB_CK_LAUNCH();
+    P.wt_piece.alloc((size_t) P.ntiles * PROP_WARPS);
     {
         DevArray<uint32_t> ev_src;
         ev_src.alloc(nev);
+        if (P.Na) {
+            k_fill_u32<<<grid_for(P.Na, TB), TB, 0, s>>>(P.ad.p, P.Na, AD_ZERO_WORD);
+            TSKB_CK_LAUNCH();
+        }
         if (nev) {
             k_event_src<<<grid_for(nev, TB), TB, 0, s>>>(P.voff.p, P.ev_sign.p, inv.p,
                 sorted_key.p, endscan.p, nev, ev_src.p);
@@ -708,41 +780,22 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         if (Ve) {
             k_fill_entries<<<grid_for(Ve, TB), TB, 0, s>>>(sorted_e.p, sorted_key.p, em_ev.p,
                 endflag.p, endscan.p, P.voff.p, P.ev_sign.p, ev_sbl.p, P.ev_pos.p, ev_src.p,
-                vis_bl.p, Ve, P.ad.p, P.pc_x.p, P.pc_bl.p);
+                vis_bl.p, inv.p, Ve, P.rank_node.p, P.level.p, padoff.p, P.ad.p, P.pc_x.p, P.pc_bl.p);
             TSKB_CK_LAUNCH();
         }
         k_fill_init<<<grid_for(N + 1, TB), TB, 0, s>>>(noff.p, endscan.p, Ve, ends_total,
-            P.rank_node.p, N, P.ad.p, P.pc_x.p, P.pc_bl.p, poff.p);
+            P.rank_node.p, P.level.p, padoff.p, N, P.ad.p, P.pc_x.p, P.pc_bl.p, poff.p);
         TSKB_CK_LAUNCH();
+        if (P.ntiles) {
+            const uint32_t nwt = P.ntiles * PROP_WARPS;
+            k_tile_piece<<<grid_for(nwt, TB), TB, 0, s>>>(tile_u0.p, tile_uend.p, nwt, noff.p,
+                endscan.p, poff.p, N, Ve, ends_total, P.wt_piece.p);
+            TSKB_CK_LAUNCH();
+        }
         TSKB_CK(cudaStreamSynchronize(s));
     }
     ev_sbl.release(); vis_bl.release(); inv.release(); em_ev.release(); sorted_e.release();
     ev_bp.release(); endflag.release();
-    {
-        // level_begin[l] = ad index of the first entry of level l; tiles never straddle levels
-        std::vector<uint32_t> h_lro = lvl_rank_off.download(s);
-        std::vector<uint32_t> h_noff = noff.download(s);
-        P.level_begin.resize(P.nlevels + 1);
-        for (uint32_t l = 0; l <= P.nlevels; l++) {
-            P.level_begin[l] = h_noff[h_lro[l]] + h_lro[l];
-        }
-        std::vector<uint4> h_tiles;
-        for (uint32_t l = 0; l < P.nlevels; l++) {
-            const uint32_t dep = (uint32_t) h_tiles.size();
-            for (uint32_t b0 = P.level_begin[l]; b0 < P.level_begin[l + 1]; b0 += PROP_TILE) {
-                uint32_t cnt = std::min(PROP_TILE, P.level_begin[l + 1] - b0);
-                h_tiles.push_back(make_uint4(b0, cnt, 0u, dep));
-            }
-        }
-        P.ntiles = (uint32_t) h_tiles.size();
-        P.tiles.upload(h_tiles.data(), h_tiles.size(), s);
-        if (P.ntiles) {
-            k_tile_piece<<<grid_for(P.ntiles, TB), TB, 0, s>>>(P.tiles.p, P.ntiles, noff.p,
-                endscan.p, poff.p, N, Ve, ends_total);
-            TSKB_CK_LAUNCH();
-        }
-        TSKB_CK(cudaStreamSynchronize(s));
-    }
     sorted_key.release(); endscan.release();
 
     // ---- sites and mutations: allele strings -> small integer codes on the host

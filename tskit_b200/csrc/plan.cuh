@@ -24,18 +24,24 @@
 //                    Branch statistics are sums over pieces of
 //                    branch_length * f(state) * |piece ^ window|; the reference's
 //                    running sum (trees.c:1339-1350) telescopes to exactly this;
-//   * addend       = one term of  state(u, t) = state(u, t-) +- state(child_i):
-//                    one per visit, listed node-major so that a node's pieces are
-//                    the running sum of its addend list ("ad"), which starts
-//                    with an INIT entry holding the node's own sample weight;
+//   * addend       = one term of  state(u, t) = state(u, t-) + ...: for a diff at t whose
+//                    edge has parent u, +-state[child] (update_state, trees.c:1317-1327, first
+//                    iteration of the walk); for every child v of u across x that was itself
+//                    visited at t, state(v, t) - state(v, t-): the later iterations of all the
+//                    walks that reach u through v, summed.  Addends are listed node-major so
+//                    that a node's pieces are the running sum of its addend list ("ad"),
+//                    which starts with an INIT entry holding the node's own sample weight.
+//                    A parent reads its children's pieces in their own order, so the gathers
+//                    of the propagation walk sequentially through the piece array;
 //   * nodes are grouped into dependency levels (level[parent] > level[child]
 //                    over every edge): all lists of one level can be
 //                    prefix-summed in parallel once lower levels are done.
 //
 // Node-major order is (level, node id, event).  Entry encoding of ad[]:
-//   bits 31-30 kind: 0 +state[src piece], 1 -state[src piece], 2 INIT (payload =
-//   node id), 3 ZERO (node is only the child of the diff: new piece, same state)
-//   bit 29: last addend of its piece;  bits 28-0: payload.
+//   bits 31-30 kind: 0 +state[piece], 1 -state[piece], 2 state[piece] - state[piece - 1],
+//   3 no addend (with bit 28: INIT, payload = node id; without: the node is only the child of
+//   the diff, or the walk's contribution is already counted: new piece, no new term)
+//   bit 29: last addend of its piece;  bits 27-0: payload.
 #pragma once
 
 #include <mutex>
@@ -46,9 +52,13 @@
 
 namespace tskb {
 
-constexpr uint32_t PROP_TILE = 1024;  // addends per propagation tile
-constexpr uint32_t AD_KIND_SHIFT = 30, AD_END = 1u << 29, AD_PAYLOAD = AD_END - 1;
-enum AdKind : uint32_t { AD_POS = 0, AD_NEG = 1, AD_INIT = 2, AD_ZERO = 3 };
+constexpr uint32_t WTILE = 256;                      // addends per warp tile of the propagation
+constexpr uint32_t PROP_WARPS = 8;                   // warp tiles per CTA tile
+constexpr uint32_t PROP_TILE = WTILE * PROP_WARPS;   // addends per CTA tile
+constexpr uint32_t AD_KIND_SHIFT = 30, AD_END = 1u << 29, AD_HEAD = 1u << 28, AD_PAYLOAD = AD_HEAD - 1;
+enum AdKind : uint32_t { AD_POS = 0, AD_NEG = 1, AD_DIFF = 2, AD_NONE = 3 };
+constexpr uint32_t AD_INIT_WORD = (AD_NONE << AD_KIND_SHIFT) | AD_HEAD | AD_END;  // | node id
+constexpr uint32_t AD_ZERO_WORD = AD_NONE << AD_KIND_SHIFT;
 
 struct Plan {
     int device = 0;
@@ -69,7 +79,7 @@ struct Plan {
     // host copies needed for argument validation
     std::vector<int32_t> sample_index_map;  // node -> sample index or -1 (trees.c:404-453)
     std::vector<int32_t> samples;
-    std::vector<uint32_t> level_begin;  // ad offset of each level, size nlevels + 1
+    std::vector<uint32_t> level_begin;  // (padded) ad offset of each level, size nlevels + 1
 
     // --- tables in HBM ---
     DevArray<double> time;            // [N]
@@ -83,17 +93,20 @@ struct Plan {
     DevArray<int32_t> ev_child;       // [nev]
     DevArray<int8_t> ev_sign;         // [nev] -1 removal, +1 insertion
     DevArray<uint32_t> voff;          // [nev + 1] visit offsets
-    // --- addend stream, node-major: Na = V + nev + N entries ---
+    // --- addend stream, node-major: V + nev + N entries, every level padded with ZERO
+    //     entries to a multiple of PROP_TILE so that tile t covers ad[t * PROP_TILE ...)
     uint32_t Na = 0;
     DevArray<uint32_t> ad;            // [Na] see encoding above
     // --- pieces, node-major: every node's INIT piece followed by one piece per touching breakpoint
     uint32_t P = 0;
     DevArray<double> pc_x;            // [P] left end of the piece (its breakpoint); -1 for INIT
     DevArray<double> pc_bl;           // [P] branch length above the node over the piece
-    // --- propagation tiles: PROP_TILE consecutive addends of one level
-    uint32_t ntiles = 0;
-    DevArray<uint4> tiles;            // [ntiles] {first addend, count, index of the piece the first
-                                      //  addend belongs to, tiles that must be complete before}
+    // --- propagation tiles
+    uint32_t ntiles = 0;              // CTA tiles
+    DevArray<uint32_t> tile_dep;      // [ntiles] first tile of the tile's level = number of tiles
+                                      //  that must be complete before its gathers
+    DevArray<uint32_t> wt_piece;      // [ntiles * PROP_WARPS] piece the first addend of each warp
+                                      //  tile belongs to
     DevArray<int32_t> rank_node;      // [N] rank -> node id (nodes sorted by (level, id))
     DevArray<uint32_t> level;         // [N]
     // --- sites ---

@@ -55,6 +55,7 @@ __device__ __forceinline__ IVec<KP> ivec_zero() {
 struct ColP {
     int32_t i, j, k, l;
     double ni, nj, nk, nl;
+    double inv;  // 1 / denominator of the column (a constant of the sample set sizes)
 };
 
 struct SumP {
@@ -76,36 +77,49 @@ __device__ __forceinline__ double pick(const IVec<KP> &s, int i) {
     return (double) r;
 }
 
-// The summary functions, in the reference's exact operation order
+// Denominator of a column, in the reference's operation order.  The device multiplies by its
+// reciprocal: 0 * inf is NaN and x * inf is +-inf exactly where the reference's 0/0 and x/0 are
+// (sample sets of size 1 or 2, test_stats.c:1737-1741), and a zero numerator stays an exact 0.
+inline double column_denominator(int stat, const ColP &c) {
+    switch (stat) {
+        case STAT_DIVERSITY: return c.ni * (c.ni - 1);
+        case STAT_Y1: return c.ni * (c.ni - 1) * (c.ni - 2);
+        case STAT_DIVERGENCE: return c.ni * (c.nj - (c.i == c.j));
+        case STAT_Y2: return c.ni * c.nj * (c.nj - 1);
+        case STAT_F2: return c.ni * (c.ni - 1) * c.nj * (c.nj - 1);
+        case STAT_RELATEDNESS_NC: return c.ni * c.nj;
+        case STAT_Y3: return c.ni * c.nj * c.nk;
+        case STAT_F3: return c.ni * (c.ni - 1) * c.nj * c.nk;
+        case STAT_F4: return c.ni * c.nj * c.nk * c.nl;
+    }
+    return 1.0;
+}
+
+// The summary functions, numerators in the reference's exact operation order
 // (c/tskit/trees.c:3934-3948, 4221-4264, 4690-4773, 4899-4959, 5177-5291).
 template <int STAT, int KP>
 __device__ __forceinline__ double f_eval(const SumP &P, const ColP &c, int m, const IVec<KP> &s) {
     if constexpr (STAT == STAT_DIVERSITY) {
         double n = c.ni, x = pick<KP>(s, c.i);
-        return x * (n - x) / (n * (n - 1));
+        return x * (n - x) * c.inv;
     } else if constexpr (STAT == STAT_SEGSITES) {
         double n = c.ni, x = pick<KP>(s, c.i);
         return (x > 0) * (1 - x / n);
     } else if constexpr (STAT == STAT_Y1) {
         double ni = c.ni, xi = pick<KP>(s, c.i);
-        double denom = ni * (ni - 1) * (ni - 2);
         double numer = xi * (ni - xi) * (ni - xi - 1);
-        return numer / denom;
+        return numer * c.inv;
     } else if constexpr (STAT == STAT_DIVERGENCE) {
-        double ni = c.ni, nj = c.nj;
-        double denom = ni * (nj - (c.i == c.j));
-        return pick<KP>(s, c.i) * (nj - pick<KP>(s, c.j)) / denom;
+        return pick<KP>(s, c.i) * (c.nj - pick<KP>(s, c.j)) * c.inv;
     } else if constexpr (STAT == STAT_Y2) {
-        double ni = c.ni, nj = c.nj;
+        double nj = c.nj;
         double xi = pick<KP>(s, c.i), xj = pick<KP>(s, c.j);
-        double denom = ni * nj * (nj - 1);
-        return xi * (nj - xj) * (nj - xj - 1) / denom;
+        return xi * (nj - xj) * (nj - xj - 1) * c.inv;
     } else if constexpr (STAT == STAT_F2) {
         double ni = c.ni, nj = c.nj;
         double xi = pick<KP>(s, c.i), xj = pick<KP>(s, c.j);
-        double denom = ni * (ni - 1) * nj * (nj - 1);
         double numer = xi * (xi - 1) * (nj - xj) * (nj - xj - 1) - xi * (ni - xi) * (nj - xj) * xj;
-        return numer / denom;
+        return numer * c.inv;
     } else if constexpr (STAT == STAT_RELATEDNESS) {
         double sumx = 0;
 #pragma unroll
@@ -115,24 +129,21 @@ __device__ __forceinline__ double f_eval(const SumP &P, const ColP &c, int m, co
         double meanx = sumx / (double) P.K;
         return (pick<KP>(s, c.i) / c.ni - meanx) * (pick<KP>(s, c.j) / c.nj - meanx);
     } else if constexpr (STAT == STAT_RELATEDNESS_NC) {
-        return pick<KP>(s, c.i) * pick<KP>(s, c.j) / (c.ni * c.nj);
+        return pick<KP>(s, c.i) * pick<KP>(s, c.j) * c.inv;
     } else if constexpr (STAT == STAT_Y3) {
-        double denom = c.ni * c.nj * c.nk;
         double numer = pick<KP>(s, c.i) * (c.nj - pick<KP>(s, c.j)) * (c.nk - pick<KP>(s, c.k));
-        return numer / denom;
+        return numer * c.inv;
     } else if constexpr (STAT == STAT_F3) {
         double ni = c.ni, nj = c.nj, nk = c.nk;
         double xi = pick<KP>(s, c.i), xj = pick<KP>(s, c.j), xk = pick<KP>(s, c.k);
-        double denom = ni * (ni - 1) * nj * nk;
         double numer = xi * (xi - 1) * (nj - xj) * (nk - xk) - xi * (ni - xi) * (nj - xj) * xk;
-        return numer / denom;
+        return numer * c.inv;
     } else if constexpr (STAT == STAT_F4) {
-        double ni = c.ni, nj = c.nj, nk = c.nk, nl = c.nl;
+        double nj = c.nj, nk = c.nk, nl = c.nl;
         double xi = pick<KP>(s, c.i), xj = pick<KP>(s, c.j), xk = pick<KP>(s, c.k),
                xl = pick<KP>(s, c.l);
-        double denom = ni * nj * nk * nl;
         double numer = xi * xk * (nj - xj) * (nl - xl) - xi * xl * (nj - xj) * (nk - xk);
-        return numer / denom;
+        return numer * c.inv;
     } else {  // STAT_TABULATED
         uint32_t cnt = (uint32_t) s.v[0];
         if (cnt >= P.table_rows) cnt = P.table_rows - 1;
@@ -195,33 +206,24 @@ struct SegOp {
     }
 };
 
-// look-back descriptor of one tile: status 0 = empty, 1 = aggregate ready, 2 = prefix ready
+// look-back descriptor of one warp tile: status 0 = empty, 1 = aggregate ready, 2 = prefix ready.
+// One state column packs (value, head, status) into a single 64-bit word so that publishing is
+// one store; wider states publish value, fence, then status.
 template <int KP>
-struct TileDesc {
+struct WDesc {
     int agg[KP + 1];     // value, head
     int prefix[KP + 1];
     int status;
     int pad[(KP + 1) % 2 == 0 ? 1 : 2];
 };
+template <>
+struct WDesc<1> {
+    unsigned long long word;  // bits 0-31 value, bit 32 head, bits 33-34 status
+};
 
-// descriptors and states are written by one CTA and read by others in the same launch: L2 only
-template <int KP>
-__device__ __forceinline__ SegVal<KP> desc_load(const int *q) {
-    SegVal<KP> r;
-#pragma unroll
-    for (int c = 0; c < KP; c++) r.v.v[c] = __ldcg(q + c);
-    r.head = __ldcg(q + KP);
-    r.ends = 0;
-    return r;
-}
-template <int KP>
-__device__ __forceinline__ void desc_store(int *q, const SegVal<KP> &x) {
-#pragma unroll
-    for (int c = 0; c < KP; c++) __stcg(q + c, x.v.v[c]);
-    __stcg(q + KP, x.head);
-}
 template <int KP>
 __device__ __forceinline__ IVec<KP> state_load(const IVec<KP> *p) {
+    // states are written by other CTAs of the same launch: read through L2, never L1
     IVec<KP> r;
     if constexpr (KP >= 4) {
         const int4 *q = reinterpret_cast<const int4 *>(p);
@@ -239,120 +241,176 @@ __device__ __forceinline__ IVec<KP> state_load(const IVec<KP> *p) {
     return r;
 }
 
-constexpr int PROP_TB = 256;
-constexpr int PROP_IPT = PROP_TILE / PROP_TB;
+constexpr int PROP_TB = 32 * PROP_WARPS;
+constexpr int PW_IPT = WTILE / 32;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;  // ~seconds; a legitimate wait is < the kernel's own run time
 
 template <int KP>
-__global__ void __launch_bounds__(PROP_TB) k_propagate(const uint4 *__restrict__ tiles,
-    const uint32_t *__restrict__ ad, const IVec<KP> *__restrict__ w, IVec<KP> *pval,
-    TileDesc<KP> *desc, uint32_t *counters, int *error_flag) {
-    typedef cub::BlockScan<SegVal<KP>, PROP_TB> BS;
-    __shared__ typename BS::TempStorage tmp;
+__device__ __forceinline__ SegVal<KP> seg_shfl_up(const SegVal<KP> &x, int delta) {
+    SegVal<KP> r;
+#pragma unroll
+    for (int c = 0; c < KP; c++) r.v.v[c] = __shfl_up_sync(0xffffffffu, x.v.v[c], delta);
+    r.head = __shfl_up_sync(0xffffffffu, x.head, delta);
+    r.ends = __shfl_up_sync(0xffffffffu, x.ends, delta);
+    return r;
+}
+
+template <int KP>
+__device__ __forceinline__ void desc_publish(WDesc<KP> *d, const SegVal<KP> &x, int status) {
+    if constexpr (KP == 1) {
+        unsigned long long wd = (unsigned long long) (uint32_t) x.v.v[0]
+                                | ((unsigned long long) (x.head ? 1 : 0) << 32)
+                                | ((unsigned long long) status << 33);
+        *(volatile unsigned long long *) &d->word = wd;
+    } else {
+        int *q = status == 1 ? d->agg : d->prefix;
+#pragma unroll
+        for (int c = 0; c < KP; c++) __stcg(q + c, x.v.v[c]);
+        __stcg(q + KP, x.head);
+        __threadfence();
+        *(volatile int *) &d->status = status;
+    }
+}
+
+// returns the status seen (0: nothing published yet); fills x from the matching slot
+template <int KP>
+__device__ __forceinline__ int desc_peek(WDesc<KP> *d, SegVal<KP> &x) {
+    x.ends = 0;
+    if constexpr (KP == 1) {
+        unsigned long long wd = *(volatile unsigned long long *) &d->word;
+        x.v.v[0] = (int32_t) (uint32_t) wd;
+        x.head = (int) ((wd >> 32) & 1);
+        return (int) ((wd >> 33) & 3);
+    } else {
+        int st = *(volatile int *) &d->status;
+        if (st == 0) return 0;
+        __threadfence();
+        const int *q = st == 2 ? d->prefix : d->agg;
+#pragma unroll
+        for (int c = 0; c < KP; c++) x.v.v[c] = __ldcg(q + c);
+        x.head = __ldcg(q + KP);
+        return st;
+    }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(PROP_TB) k_propagate(const uint32_t *__restrict__ tile_dep,
+    const uint32_t *__restrict__ wt_piece, const uint32_t *__restrict__ ad,
+    const IVec<KP> *__restrict__ w, IVec<KP> *pval, WDesc<KP> *desc, uint32_t *counters,
+    int *error_flag) {
     __shared__ uint32_t s_tile;
-    __shared__ SegVal<KP> s_carry;
     if (threadIdx.x == 0) s_tile = atomicAdd(&counters[0], 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint4 meta = __ldg(tiles + tile);
-    const uint32_t local0 = threadIdx.x * PROP_IPT;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t wt = tile * PROP_WARPS + warp;
+    const uint32_t dep = __ldg(tile_dep + tile);
+    const uint32_t piece_base = __ldg(wt_piece + wt);
     SegOp<KP> op;
 
     // the addend words do not depend on other tiles: fetch them before waiting
-    uint32_t word[PROP_IPT];
+    uint32_t word[PW_IPT];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(ad + (size_t) wt * WTILE + lane * PW_IPT);
 #pragma unroll
-    for (int q = 0; q < PROP_IPT; q++) {
-        word[q] = local0 + q < meta.y ? __ldg(ad + meta.x + local0 + q) : (AD_ZERO << AD_KIND_SHIFT);
+        for (int q = 0; q < PW_IPT / 4; q++) {
+            uint4 t = __ldg(src + q);
+            word[4 * q] = t.x; word[4 * q + 1] = t.y; word[4 * q + 2] = t.z; word[4 * q + 3] = t.w;
+        }
     }
-    // (a) every lower level complete
-    if (meta.w > 0) {
+    // (a) every lower level complete: one thread watches the global counter
+    if (dep > 0) {
         if (threadIdx.x == 0) {
             volatile uint32_t *done = counters + 1;
             uint32_t spins = 0;
-            while (*done < meta.w) {
+            while (*done < dep) {
                 if (++spins > SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int *) error_flag)) {
                     *error_flag = 1;
                     break;
                 }
+                __nanosleep(32);
             }
             __threadfence();
         }
         __syncthreads();
     }
 
-    // gather addends; thread-local segmented scan
-    SegVal<KP> item[PROP_IPT];
+    // gather addends; lane-local segmented scan
+    SegVal<KP> item[PW_IPT];
 #pragma unroll
-    for (int q = 0; q < PROP_IPT; q++) {
+    for (int q = 0; q < PW_IPT; q++) {
         const uint32_t kind = word[q] >> AD_KIND_SHIFT, pay = word[q] & AD_PAYLOAD;
         SegVal<KP> x;
         x.v = ivec_zero<KP>();
         x.head = 0;
         x.ends = (word[q] & AD_END) ? 1 : 0;
-        if (kind == AD_INIT) {
-            x.v = w[pay];
-            x.head = 1;
-        } else if (kind != AD_ZERO) {
+        if (kind == AD_NONE) {
+            if (word[q] & AD_HEAD) {
+                x.v = w[pay];
+                x.head = 1;
+            }
+        } else {
             IVec<KP> g = state_load<KP>(pval + pay);
-            x.v = kind == AD_NEG ? ivec_zero<KP>() - g : g;
+            if (kind == AD_DIFF) {
+                x.v = g - state_load<KP>(pval + pay - 1);
+            } else {
+                x.v = kind == AD_NEG ? ivec_zero<KP>() - g : g;
+            }
         }
-        item[q] = q == 0 ? x : op(item[q - 1], x);
+        item[q] = x;
+    }
+#pragma unroll
+    for (int q = 1; q < PW_IPT; q++) item[q] = op(item[q - 1], item[q]);
+    // warp scan of the lane aggregates
+    SegVal<KP> incl = item[PW_IPT - 1];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        SegVal<KP> up = seg_shfl_up<KP>(incl, d);
+        if (lane >= (uint32_t) d) incl = op(up, incl);
     }
     SegVal<KP> identity;
     identity.v = ivec_zero<KP>();
     identity.head = 0;
     identity.ends = 0;
-    SegVal<KP> thread_excl, tile_agg;
-    BS(tmp).ExclusiveScan(item[PROP_IPT - 1], thread_excl, identity, op, tile_agg);
+    SegVal<KP> excl = seg_shfl_up<KP>(incl, 1);
+    if (lane == 0) excl = identity;
 
-    // (b) carry entering this tile
-    if (threadIdx.x == 0) {
-        SegVal<KP> carry = identity;
-        TileDesc<KP> *me = desc + tile;
-        if (tile == meta.w) {  // first tile of its level
-            desc_store<KP>(me->prefix, tile_agg);
-            __threadfence();
-            *(volatile int *) &me->status = 2;
+    // (b) carry entering this warp tile: decoupled look-back within the level
+    SegVal<KP> carry = identity;
+    if (lane == 31) {
+        WDesc<KP> *me = desc + wt;
+        const uint32_t first = dep * PROP_WARPS;
+        if (wt == first) {
+            desc_publish<KP>(me, incl, 2);
         } else {
-            desc_store<KP>(me->agg, tile_agg);
-            __threadfence();
-            *(volatile int *) &me->status = 1;
-            {
-                int32_t p = (int32_t) tile - 1;
-                uint32_t spins = 0;
-                while (true) {
-                    TileDesc<KP> *d = desc + p;
-                    int st = *(volatile int *) &d->status;
-                    if (st == 0) {
-                        if (++spins > SPIN_LIMIT
-                            || ((spins & 1023u) == 0 && *(volatile int *) error_flag)) {
-                            *error_flag = 1;
-                            break;
-                        }
-                        continue;
-                    }
-                    __threadfence();
-                    if (st == 2) {
-                        carry = op(desc_load<KP>(d->prefix), carry);
+            desc_publish<KP>(me, incl, 1);
+            uint32_t p = wt - 1, spins = 0;
+            while (true) {
+                SegVal<KP> got;
+                int st = desc_peek<KP>(desc + p, got);
+                if (st == 0) {
+                    if (++spins > SPIN_LIMIT
+                        || ((spins & 1023u) == 0 && *(volatile int *) error_flag)) {
+                        *error_flag = 1;
                         break;
                     }
-                    carry = op(desc_load<KP>(d->agg), carry);
-                    if (carry.head || p == (int32_t) meta.w) break;
-                    p--;
+                    continue;
                 }
+                carry = op(got, carry);
+                if (st == 2 || carry.head || p == first) break;
+                p--;
             }
-            desc_store<KP>(me->prefix, op(carry, tile_agg));
-            __threadfence();
-            *(volatile int *) &me->status = 2;
+            desc_publish<KP>(me, op(carry, incl), 2);
         }
-        s_carry = carry;
     }
-    __syncthreads();
-    // values entering this thread: carry (+) thread_excl; publish the state at every piece end
-    SegVal<KP> in = op(s_carry, thread_excl);
-    const uint32_t piece0 = meta.z + (uint32_t) thread_excl.ends;
 #pragma unroll
-    for (int q = 0; q < PROP_IPT; q++) {
+    for (int c = 0; c < KP; c++) carry.v.v[c] = __shfl_sync(0xffffffffu, carry.v.v[c], 31);
+    carry.head = __shfl_sync(0xffffffffu, carry.head, 31);
+    // values entering this lane: carry (+) excl; publish the state at every piece end
+    SegVal<KP> in = op(carry, excl);
+    const uint32_t piece0 = piece_base + (uint32_t) excl.ends;
+#pragma unroll
+    for (int q = 0; q < PW_IPT; q++) {
         if (word[q] & AD_END) {
             SegVal<KP> r = op(in, item[q]);
             pval[piece0 + (uint32_t) item[q].ends - 1] = r.v;
@@ -375,50 +433,82 @@ __global__ void __launch_bounds__(PROP_TB) k_propagate(const uint4 *__restrict__
 // node at one breakpoint telescoped.
 
 constexpr int SUM_IPT = 4;
-constexpr int SUM_TILE = TB * SUM_IPT;
+constexpr int SUM_TILE = TB * SUM_IPT;   // pc_x / pc_bl / pval are padded to whole tiles
+constexpr uint32_t LUT_CELLS = 2048;     // uniform cells over the genome -> window index
+
+// window holding x: start from the lookup cell, then walk (windows are sorted; exact for any
+// window layout, one step for evenly spaced windows)
+__device__ __forceinline__ uint32_t window_of(const double *win, const uint16_t *lut, uint32_t W,
+    double x, double inv_cell) {
+    uint32_t g = (uint32_t) (x * inv_cell);
+    if (g >= LUT_CELLS) g = LUT_CELLS - 1;
+    uint32_t u = lut[g];
+    while (u > 0 && x < win[u]) u--;
+    while (u + 1 < W && x >= win[u + 1]) u++;
+    return u;
+}
 
 template <int STAT, int KP, bool SMEM>
-__global__ void __launch_bounds__(TB) k_branch_summary(uint32_t P, const double *__restrict__ pc_x,
-    const double *__restrict__ pc_bl, const IVec<KP> *__restrict__ pval, SumP sp, IVec<KP> totals,
+__global__ void __launch_bounds__(TB, SMEM ? 4 : 2) k_branch_summary(uint32_t ntiles,
+    const double *__restrict__ pc_x, const double *__restrict__ pc_bl,
+    const IVec<KP> *__restrict__ pval, SumP sp, IVec<KP> totals,
     const double *__restrict__ windows, uint32_t W, double range_right, uint32_t mc, double *gA,
     double *gB) {
     extern __shared__ double smem[];
-    double *s_win = smem;                      // [W + 1]
-    double *s_A = smem + (W + 1);              // [mc][W]
-    double *s_B = s_A + (size_t) mc * W;       // [mc][W]
+    double *s_win = smem;                              // [W + 1]
+    double *s_bins = smem + (W + 1);                   // [mc][W][2]: A, B interleaved
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(s_bins + (SMEM ? 2 * mc * W : 0));
     const uint32_t m0 = blockIdx.y * mc;
     const uint32_t m1 = min(m0 + mc, (uint32_t) sp.M);
+    double inv_cell = 0.0;
     if (SMEM) {
         for (uint32_t i = threadIdx.x; i <= W; i += TB) s_win[i] = windows[i];
-        for (uint32_t i = threadIdx.x; i < 2 * mc * W; i += TB) s_A[i] = 0.0;
+        for (uint32_t i = threadIdx.x; i < 2 * mc * W; i += TB) s_bins[i] = 0.0;
+        __syncthreads();
+        const double cell = (s_win[W] - s_win[0]) / (double) LUT_CELLS;
+        inv_cell = 1.0 / cell;
+        for (uint32_t g = threadIdx.x; g < LUT_CELLS; g += TB) {
+            uint32_t u = upper_bound_dev(s_win, W + 1, s_win[0] + g * cell);
+            u = u > 0 ? u - 1 : 0;
+            s_lut[g] = (uint16_t) (u < W ? u : W - 1);
+        }
         __syncthreads();
     }
-    const double *win = SMEM ? s_win : windows;
-    const uint32_t ntiles = (P + SUM_TILE - 1) / SUM_TILE;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t first = tile * SUM_TILE + threadIdx.x * SUM_IPT;
         double x[SUM_IPT], bl[SUM_IPT + 1];
         IVec<KP> s[SUM_IPT + 1];
-        bool prev_real = false;
+        {
+            const double2 *qx = reinterpret_cast<const double2 *>(pc_x + first);
+            const double2 *qb = reinterpret_cast<const double2 *>(pc_bl + first);
+#pragma unroll
+            for (int q = 0; q < SUM_IPT / 2; q++) {
+                double2 t = qx[q];
+                x[2 * q] = t.x; x[2 * q + 1] = t.y;
+                t = qb[q];
+                bl[2 * q + 1] = t.x; bl[2 * q + 2] = t.y;
+            }
+            const int4 *qs = reinterpret_cast<const int4 *>(pval + first);
+            int flat[SUM_IPT * KP];
+#pragma unroll
+            for (int q = 0; q < KP; q++) {
+                int4 t = qs[q];
+                flat[4 * q] = t.x; flat[4 * q + 1] = t.y; flat[4 * q + 2] = t.z; flat[4 * q + 3] = t.w;
+            }
+#pragma unroll
+            for (int q = 0; q < SUM_IPT; q++) {
+#pragma unroll
+                for (int k = 0; k < KP; k++) s[q + 1].v[k] = flat[q * KP + k];
+            }
+        }
         // predecessor of the first item (same node unless that item is an INIT piece)
+        bool prev_real = false;
         s[0] = ivec_zero<KP>();
         bl[0] = 0.0;
-        if (first > 0 && first < P) {
+        if (first > 0 && x[0] >= 0.0) {
             prev_real = pc_x[first - 1] >= 0.0;
             bl[0] = pc_bl[first - 1];
             s[0] = pval[first - 1];
-        }
-#pragma unroll
-        for (int q = 0; q < SUM_IPT; q++) {
-            uint32_t p = first + q;
-            x[q] = -1.0;
-            bl[q + 1] = 0.0;
-            s[q + 1] = ivec_zero<KP>();
-            if (p < P) {
-                x[q] = pc_x[p];
-                bl[q + 1] = pc_bl[p];
-                s[q + 1] = pval[p];
-            }
         }
         uint32_t wi[SUM_IPT];
         double rem[SUM_IPT];
@@ -427,17 +517,25 @@ __global__ void __launch_bounds__(TB) k_branch_summary(uint32_t P, const double 
             wi[q] = 0;
             rem[q] = 0.0;
             if (x[q] >= 0.0) {
-                uint32_t u = upper_bound_dev(win, W + 1, x[q]);
-                u = u > 0 ? u - 1 : 0;
-                if (u >= W) u = W - 1;
+                uint32_t u;
+                double wr;
+                if (SMEM) {
+                    u = window_of(s_win, s_lut, W, x[q], inv_cell);
+                    wr = s_win[u + 1];
+                } else {
+                    u = upper_bound_dev(windows, W + 1, x[q]);
+                    u = u > 0 ? u - 1 : 0;
+                    if (u >= W) u = W - 1;
+                    wr = windows[u + 1];
+                }
                 wi[q] = u;
-                double wr = win[u + 1];
                 rem[q] = (wr < range_right ? wr : range_right) - x[q];
             }
         }
         for (uint32_t m = m0; m < m1; m++) {
             const ColP col = sp.cols[m];
             double prevG = prev_real ? bl[0] * F_branch<STAT, KP>(sp, col, m, s[0], totals) : 0.0;
+            double *binm = SMEM ? s_bins + 2 * (m - m0) * W : nullptr;
 #pragma unroll
             for (int q = 0; q < SUM_IPT; q++) {
                 if (x[q] < 0.0) {  // INIT piece (or padding): the node is not in any tree yet
@@ -449,8 +547,8 @@ __global__ void __launch_bounds__(TB) k_branch_summary(uint32_t P, const double 
                 prevG = G;
                 if (c != 0.0) {
                     if (SMEM) {
-                        atomicAdd(&s_A[(size_t) (m - m0) * W + wi[q]], c);
-                        atomicAdd(&s_B[(size_t) (m - m0) * W + wi[q]], c * rem[q]);
+                        atomicAdd(binm + 2 * wi[q], c);
+                        atomicAdd(binm + 2 * wi[q] + 1, c * rem[q]);
                     } else {
                         atomicAdd(&gA[(size_t) m * W + wi[q]], c);
                         atomicAdd(&gB[(size_t) m * W + wi[q]], c * rem[q]);
@@ -464,7 +562,7 @@ __global__ void __launch_bounds__(TB) k_branch_summary(uint32_t P, const double 
         const uint32_t cols = m1 - m0;
         for (uint32_t i = threadIdx.x; i < cols * W; i += TB) {
             uint32_t m = m0 + i / W, wdx = i % W;
-            double a = s_A[i], b = s_B[i];
+            double a = s_bins[2 * i], b = s_bins[2 * i + 1];
             if (a != 0.0) atomicAdd(&gA[(size_t) m * W + wdx], a);
             if (b != 0.0) atomicAdd(&gB[(size_t) m * W + wdx], b);
         }
@@ -635,13 +733,13 @@ void launch_branch(CallCtx &c, const IVec<KP> *pval, IVec<KP> totals) {
     double *gA = A.get<double>((size_t) 2 * M * W);
     double *gB = gA + (size_t) M * W;
     TSKB_CK(cudaMemsetAsync(gA, 0, (size_t) 2 * M * W * sizeof(double), c.s));
-    const uint32_t ntiles = (P.P + SUM_TILE - 1) / SUM_TILE;
+    const uint32_t ntiles = (P.P + SUM_TILE - 1) / SUM_TILE;  // plan arrays are padded to this
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
-    const size_t win_bytes = (size_t) (W + 1) * sizeof(double);
+    const size_t win_bytes = (size_t) (W + 1) * sizeof(double) + LUT_CELLS * sizeof(uint16_t);
     const size_t col_bytes = (size_t) 2 * W * sizeof(double);
     if (P.P > 0) {
-        if (win_bytes + col_bytes <= SMEM_BIN_BUDGET) {
+        if (win_bytes + col_bytes <= SMEM_BIN_BUDGET && W < 65536) {
             uint32_t mc = (uint32_t) std::min<size_t>(M, (SMEM_BIN_BUDGET - win_bytes) / col_bytes);
             uint32_t chunks = (M + mc - 1) / mc;
             size_t smem = win_bytes + mc * col_bytes;
@@ -649,13 +747,13 @@ void launch_branch(CallCtx &c, const IVec<KP> *pval, IVec<KP> totals) {
             TSKB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             int per_sm = 1;
             TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, smem));
-            uint32_t gx = std::min<uint32_t>(ntiles, (uint32_t) (sms * std::min(std::max(per_sm, 1), 4)));
-            kern<<<dim3(gx, chunks), TB, smem, c.s>>>(P.P, P.pc_x.p, P.pc_bl.p, pval, c.sumP, totals,
+            uint32_t gx = std::min<uint32_t>(ntiles, (uint32_t) (sms * std::max(per_sm, 1)));
+            kern<<<dim3(gx, chunks), TB, smem, c.s>>>(ntiles, P.pc_x.p, P.pc_bl.p, pval, c.sumP, totals,
                 c.d_windows, W, P.range_right, mc, gA, gB);
         } else {
             auto kern = k_branch_summary<STAT, KP, false>;
             uint32_t gx = std::min<uint32_t>(ntiles, (uint32_t) sms * 8);
-            kern<<<dim3(gx, 1), TB, 0, c.s>>>(P.P, P.pc_x.p, P.pc_bl.p, pval, c.sumP, totals,
+            kern<<<dim3(gx, 1), TB, 0, c.s>>>(ntiles, P.pc_x.p, P.pc_bl.p, pval, c.sumP, totals,
                 c.d_windows, W, P.range_right, M, gA, gB);
         }
         TSKB_CK_LAUNCH();
@@ -761,6 +859,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
             q.i = t[0]; q.j = t[1]; q.k = t[2]; q.l = t[3];
             q.ni = (double) sp.sizes[t[0]]; q.nj = (double) sp.sizes[t[1]];
             q.nk = (double) sp.sizes[t[2]]; q.nl = (double) sp.sizes[t[3]];
+            q.inv = 1.0 / column_denominator(sp.stat_id, q);
         }
         ColP *d_cols = A.get<ColP>(M);
         TSKB_CK(cudaMemcpyAsync(d_cols, cols.data(), M * sizeof(ColP), cudaMemcpyHostToDevice, s));
@@ -776,15 +875,17 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     TSKB_CK(cudaEventRecord(P.ev[1], s));
 
     // ---- phase 1: propagate
-    IVec<KP> *pval = A.get<IVec<KP>>(P.P);
+    IVec<KP> *pval = A.get<IVec<KP>>((size_t) P.P + 2048);  // summary tiles read whole tiles
     int *d_err = A.get<int>(1);
     TSKB_CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
     if (P.ntiles) {
-        TileDesc<KP> *desc = A.get<TileDesc<KP>>(P.ntiles);
+        const size_t nwt = (size_t) P.ntiles * PROP_WARPS;
+        WDesc<KP> *desc = A.get<WDesc<KP>>(nwt);
         uint32_t *counters = A.get<uint32_t>(2);
-        TSKB_CK(cudaMemsetAsync(desc, 0, (size_t) P.ntiles * sizeof(TileDesc<KP>), s));
+        TSKB_CK(cudaMemsetAsync(desc, 0, nwt * sizeof(WDesc<KP>), s));
         TSKB_CK(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
-        k_propagate<KP><<<P.ntiles, PROP_TB, 0, s>>>(P.tiles.p, P.ad.p, w, pval, desc, counters, d_err);
+        k_propagate<KP><<<P.ntiles, PROP_TB, 0, s>>>(P.tile_dep.p, P.wt_piece.p, P.ad.p, w, pval, desc,
+            counters, d_err);
         TSKB_CK_LAUNCH();
         c.launches++;
     }
