@@ -8,6 +8,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+REF_PY = os.path.join(ROOT, "baseline", "_ref")
+if os.path.isdir(os.path.join(REF_PY, "tskit")) and REF_PY not in sys.path:
+    sys.path.insert(0, REF_PY)  # the unmodified reference Python package (drop-in tests)
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

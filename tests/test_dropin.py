@@ -1,0 +1,113 @@
+"""The drop-in seam (tskit_b200/dropin.py) under the unchanged tskit.TreeSequence API.
+CPU part: seam mechanics with an engine stand-in that answers from the reference's own low-level
+object (no CUDA).  GPU part: every public statistic through the real engine == the reference."""
+import numpy as np
+import pytest
+
+tskit = pytest.importorskip("tskit", reason="baseline/_ref (reference tskit) not installed")
+
+from tskit_b200 import dropin  # noqa: E402
+
+
+class EchoEngine:
+    """Engine stand-in: forwards to the reference low-level object and records the calls."""
+
+    def __init__(self, ll):
+        self.ll = ll
+        self.calls = []
+
+    def __getattr__(self, name):
+        def f(*a, **k):
+            self.calls.append(name)
+            return getattr(self.ll, name)(*a, **k)
+        f.__name__ = name
+        return f
+
+
+@pytest.fixture(scope="module")
+def ts(wf_small):
+    return dropin.from_tables(wf_small)
+
+
+def test_seam_routes_statistics_only(ts):
+    eng = EchoEngine(ts.ll_tree_sequence)
+    acc = dropin.accelerate(ts, engine=eng)
+    s = ts.samples()
+    sets = [s[:60], s[60:130], s[130:]]
+    w = np.linspace(0, ts.sequence_length, 6)
+    assert np.array_equal(acc.diversity(sets, windows=w, mode="branch"),
+                          ts.diversity(sets, windows=w, mode="branch"))
+    assert np.array_equal(acc.Fst(sets, indexes=[(0, 1), (1, 2)], windows=w),
+                          ts.Fst(sets, indexes=[(0, 1), (1, 2)], windows=w))
+    assert np.array_equal(acc.Tajimas_D(sets, windows=w), ts.Tajimas_D(sets, windows=w))
+    assert np.array_equal(acc.f4(sets + [s[:10]], indexes=[(0, 1, 2, 3)], mode="branch"),
+                          ts.f4(sets + [s[:10]], indexes=[(0, 1, 2, 3)], mode="branch"))
+    assert np.array_equal(acc.genetic_relatedness(sets, indexes=[(0, 1)], mode="site"),
+                          ts.genetic_relatedness(sets, indexes=[(0, 1)], mode="site"))
+    assert "diversity" in eng.calls and "divergence" in eng.calls and "f4" in eng.calls
+    assert "segregating_sites" in eng.calls  # Tajima's D and relatedness(proportion=True)
+    assert acc.accel_stats["accelerated"] == len(eng.calls)
+    # outside a statistics call the real low-level object is visible: C constructors work
+    assert acc._ll_tree_sequence is ts.ll_tree_sequence
+    assert acc.first().num_samples() == ts.num_samples
+    assert sum(1 for _ in acc.variants()) == ts.num_sites
+    n_before = len(eng.calls)
+    acc.genotype_matrix()
+    acc.simplify(s[:20])
+    assert len(eng.calls) == n_before
+
+
+def test_node_mode_is_forwarded_visibly(ts):
+    eng = EchoEngine(ts.ll_tree_sequence)
+    acc = dropin.accelerate(ts, engine=eng)
+    got = acc.diversity([ts.samples()[:50]], mode="node")
+    assert got.shape == (ts.num_nodes, 1)
+    assert acc.accel_stats == {"accelerated": 0, "forwarded": 1}
+    assert eng.calls == []
+
+
+def test_errors_keep_reference_type(ts):
+    import _tskit
+    acc = dropin.accelerate(ts, engine=EchoEngine(ts.ll_tree_sequence))
+    with pytest.raises(_tskit.LibraryError):
+        acc.diversity([ts.samples()[:5]], windows=[0, ts.sequence_length / 2], mode="branch")
+
+
+@pytest.mark.gpu
+def test_public_api_matches_reference_on_gpu(ts):
+    acc = dropin.accelerate(ts)
+    s = ts.samples()
+    sets = [s[:60], s[60:130], s[130:]]
+    w = np.linspace(0, ts.sequence_length, 11)
+
+    def same(a, b, tol=1e-9):
+        a, b = np.asarray(a), np.asarray(b)
+        assert a.shape == b.shape
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.allclose(a, b, rtol=tol, atol=tol * np.nanmax(np.abs(b), initial=0.0), equal_nan=True)
+
+    for mode in ("site", "branch"):
+        for windows in (None, w, "trees"):
+            same(acc.diversity(sets, windows=windows, mode=mode), ts.diversity(sets, windows=windows, mode=mode))
+            same(acc.divergence(sets, indexes=[(0, 1), (0, 2)], windows=windows, mode=mode),
+                 ts.divergence(sets, indexes=[(0, 1), (0, 2)], windows=windows, mode=mode))
+        same(acc.segregating_sites(sets, windows=w, mode=mode), ts.segregating_sites(sets, windows=w, mode=mode))
+        same(acc.Fst(sets, indexes=[(0, 1), (1, 2)], windows=w, mode=mode),
+             ts.Fst(sets, indexes=[(0, 1), (1, 2)], windows=w, mode=mode))
+        same(acc.Tajimas_D(sets, windows=w, mode=mode), ts.Tajimas_D(sets, windows=w, mode=mode))
+        for name, k in (("Y1", 1), ("Y2", 2), ("f2", 2), ("Y3", 3), ("f3", 3), ("f4", 4)):
+            kw = {} if k == 1 else {"indexes": [tuple(range(k)) if k <= 3 else (0, 1, 2, 0)]}
+            same(getattr(acc, name)(sets, windows=w, mode=mode, **kw),
+                 getattr(ts, name)(sets, windows=w, mode=mode, **kw))
+        same(acc.genetic_relatedness(sets, indexes=[(0, 1), (2, 2)], windows=w, mode=mode),
+             ts.genetic_relatedness(sets, indexes=[(0, 1), (2, 2)], windows=w, mode=mode))
+        same(acc.genetic_relatedness(sets, indexes=[(0, 1)], windows=w, mode=mode, proportion=False, centre=False),
+             ts.genetic_relatedness(sets, indexes=[(0, 1)], windows=w, mode=mode, proportion=False, centre=False))
+        n = len(sets[0])
+        f = lambda x: x * (n - x) / (n * (n - 1))  # noqa: E731
+        same(acc.sample_count_stat([sets[0]], f, 1, windows=w, mode=mode),
+             ts.sample_count_stat([sets[0]], f, 1, windows=w, mode=mode))
+    assert acc.accel_stats["forwarded"] == 0 and acc.accel_stats["accelerated"] > 30
+    same(acc.diversity([s[:50]], mode="node"), ts.diversity([s[:50]], mode="node"))
+    assert acc.accel_stats["forwarded"] == 1
+    assert acc.first().num_samples() == ts.num_samples

@@ -1,0 +1,103 @@
+"""Multi-GPU host logic on CPU: world_size-2 gloo processes, each computing its genome range with
+an engine stand-in built on the oracle (test infrastructure), combined by the product's
+sharding module; the result must equal the whole-genome oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tskit_b200 import sharding
+from tskit_b200.tables import Tables
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA = os.path.join(ROOT, "tests", "data", "wf_200_500_100000.npz")
+
+
+class OracleRangeEngine:
+    """Statistic of the trees/sites inside [lo, hi) only, from the whole-genome oracle: refine
+    the windows with the cuts, evaluate un-normalised, add the sub-windows inside the range."""
+
+    def __init__(self, tables, rng):
+        from oracle import port
+        self.o = port.Oracle(tables)
+        self.lo, self.hi = rng
+
+    def _run(self, name, sets, indexes, windows, mode, **kw):
+        w = np.asarray(windows, dtype=np.float64)
+        fine = np.unique(np.concatenate([w, [self.lo, self.hi]]))
+        r = self.o.stat(name, sets, indexes, windows=fine, mode=mode, span_normalise=False, **kw)
+        out = np.zeros((len(w) - 1, r.shape[1]))
+        mid = 0.5 * (fine[:-1] + fine[1:])
+        inside = (mid >= self.lo) & (mid < self.hi)
+        owner = np.searchsorted(w, mid, side="right") - 1
+        np.add.at(out, owner[inside], r[inside])
+        return out
+
+    def diversity(self, sets, windows, mode, span_normalise):
+        assert span_normalise is False
+        return self._run("diversity", sets, None, windows, mode)
+
+    def divergence(self, sets, indexes, windows, mode, span_normalise):
+        assert span_normalise is False
+        return self._run("divergence", sets, indexes, windows, mode)
+
+
+def _worker(rank, world, port_no, W, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t = Tables.load(DATA).ensure_derived()
+    windows = np.linspace(0, t.sequence_length, W + 1)
+    sh = sharding.ShardedTreeSequence(t, windows, rank, world, engine_factory=OracleRangeEngine)
+    s = t.samples
+    sets = [s[:90], s[90:]]
+    out = {}
+    for mode in ("branch", "site"):
+        out[("diversity", mode)] = sh.stat("diversity", sets, windows=windows, mode=mode)
+        out[("divergence", mode)] = sh.stat("divergence", sets, [[0, 1]], windows=windows, mode=mode)
+    q.put((rank, sh.ranges, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("W", [1, 7])
+def test_two_rank_gloo_matches_whole_genome(W):
+    from oracle import port
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = 29500 + (os.getpid() + W) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port_no, W, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    t = Tables.load(DATA).ensure_derived()
+    o = port.Oracle(t)
+    windows = np.linspace(0, t.sequence_length, W + 1)
+    s = t.samples
+    sets = [s[:90], s[90:]]
+    for rank, ranges, out in got:
+        assert len(ranges) == 2 and ranges[0][1] == ranges[1][0]
+        if W >= 2:
+            assert ranges[0][1] in windows  # cut snapped to a window edge
+        for mode in ("branch", "site"):
+            want = o.stat("diversity", sets, windows=windows, mode=mode)
+            assert np.allclose(out[("diversity", mode)], want, rtol=1e-11)
+            want = o.stat("divergence", sets, [[0, 1]], windows=windows, mode=mode)
+            assert np.allclose(out[("divergence", mode)], want, rtol=1e-11)
+
+
+def test_plan_shards_balanced_and_covering(wf_1k):
+    pos = sharding.edge_diff_positions(wf_1k)
+    L = wf_1k.sequence_length
+    for world, W in ((8, 1000), (4, 2), (2, 1)):
+        windows = np.linspace(0, L, W + 1)
+        r = sharding.plan_shards(wf_1k, windows, world)
+        assert len(r) == world and r[0][0] == 0.0 and r[-1][1] == L
+        assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+        counts = [np.count_nonzero((pos >= lo) & (pos < hi)) for lo, hi in r]
+        assert max(counts) < 1.5 * len(pos) / world

@@ -320,6 +320,9 @@ int64_t tskb_treeseq_debug_array(const tskb_treeseq_t *self, const char *name, v
     ARR("level", level) ARR("rank_node", rank_node) ARR("mut_src", mut_src)
     ARR("mut_allele", mut_allele) ARR("mut_alt", mut_alt)
 #undef ARR
+    if (s == "trace" && P.stats_trace != nullptr) {
+        src = P.stats_trace; n = (size_t) P.ntiles * 6; esize = sizeof(unsigned long long);
+    }
     if (s == "level_begin") {
         src = P.level_begin.data(); n = P.level_begin.size(); esize = sizeof(uint32_t); host = true;
     }

@@ -123,6 +123,7 @@ struct Plan {
     mutable std::mutex mu;
     mutable Arena arena;
     mutable tskb_stats_t stats = {};
+    mutable unsigned long long *stats_trace = nullptr;  // TSKB_TRACE: per-tile timeline of the last call (arena)
     size_t scan_temp_bytes = 0;
 
     ~Plan();

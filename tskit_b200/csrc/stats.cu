@@ -293,133 +293,204 @@ __device__ __forceinline__ int desc_peek(WDesc<KP> *d, SegVal<KP> &x) {
     }
 }
 
+// transpose buffers: index i of a 256-entry warp tile lives at i + i / 32, which makes both the
+// striped (q * 32 + lane) and the blocked (lane * 8 + q) access pattern bank-conflict free
+constexpr int WBUF = WTILE + WTILE / 32;
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// optional per-tile timeline (TSKB_TRACE=1): 6 timestamps per CTA tile
+#define TRACE(slot) do { if (trace != nullptr && threadIdx.x == 0) trace[(size_t) tile * 6 + (slot)] = gtime(); } while (0)
+__device__ __forceinline__ int padi(int i) { return i + (i >> 5); }
+
 template <int KP>
-__global__ void __launch_bounds__(PROP_TB) k_propagate(const uint32_t *__restrict__ tile_dep,
-    const uint32_t *__restrict__ wt_piece, const uint32_t *__restrict__ ad,
-    const IVec<KP> *__restrict__ w, IVec<KP> *pval, WDesc<KP> *desc, uint32_t *counters,
-    int *error_flag) {
-    __shared__ uint32_t s_tile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(&counters[0], 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+constexpr size_t propagate_smem() {
+    // per warp: transpose buffers for values and words + two stages of prefetched addend words
+    return (size_t) PROP_WARPS * (WBUF * (sizeof(IVec<KP>) + sizeof(uint32_t)) + 2 * WTILE * sizeof(uint32_t));
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    unsigned sa = (unsigned) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// Persistent, co-resident CTAs (cooperative launch): CTA b processes tiles b, b + G, b + 2G, ...
+// and prefetches the next one's addend words into shared memory while it works on (or waits
+// for) the current one, so that a tile's gathers start the moment its level is released.  With
+// G larger than the tiles of a level, a level's tiles all sit in different CTAs.  Every CTA
+// processes its tiles in increasing order and a tile only waits on lower-numbered tiles, so the
+// lowest unfinished tile can always run: no deadlock.
+template <int KP>
+__global__ void __launch_bounds__(PROP_TB) k_propagate(uint32_t ntiles,
+    const uint32_t *__restrict__ tile_dep, const uint32_t *__restrict__ wt_piece,
+    const uint32_t *__restrict__ ad, uint32_t piece0, IVec<KP> *state, WDesc<KP> *desc,
+    uint32_t *counters, int *error_flag, unsigned long long *trace) {
+    // state[0 .. piece0) are the nodes' own sample weights (written by k_set_weights before this
+    // launch), state[piece0 + p] is piece p: one base address for both kinds of gather
+    IVec<KP> *pval = state + piece0;
+    extern __shared__ __align__(16) unsigned char prop_smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t wt = tile * PROP_WARPS + warp;
-    const uint32_t dep = __ldg(tile_dep + tile);
-    const uint32_t piece_base = __ldg(wt_piece + wt);
+    IVec<KP> *vbuf = reinterpret_cast<IVec<KP> *>(prop_smem) + (size_t) warp * WBUF;
+    uint32_t *wbuf = reinterpret_cast<uint32_t *>(prop_smem + (size_t) PROP_WARPS * WBUF * sizeof(IVec<KP>))
+                     + (size_t) warp * WBUF;
+    uint32_t *stage = reinterpret_cast<uint32_t *>(
+        prop_smem + (size_t) PROP_WARPS * WBUF * (sizeof(IVec<KP>) + sizeof(uint32_t)))
+                      + (size_t) warp * 2 * WTILE;
     SegOp<KP> op;
-
-    // the addend words do not depend on other tiles: fetch them before waiting
-    uint32_t word[PW_IPT];
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(ad + (size_t) wt * WTILE + lane * PW_IPT);
-#pragma unroll
-        for (int q = 0; q < PW_IPT / 4; q++) {
-            uint4 t = __ldg(src + q);
-            word[4 * q] = t.x; word[4 * q + 1] = t.y; word[4 * q + 2] = t.z; word[4 * q + 3] = t.w;
-        }
-    }
-    // (a) every lower level complete: one thread watches the global counter
-    if (dep > 0) {
-        if (threadIdx.x == 0) {
-            volatile uint32_t *done = counters + 1;
-            uint32_t spins = 0;
-            while (*done < dep) {
-                if (++spins > SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int *) error_flag)) {
-                    *error_flag = 1;
-                    break;
-                }
-                __nanosleep(32);
-            }
-            __threadfence();
-        }
-        __syncthreads();
-    }
-
-    // gather addends; lane-local segmented scan
-    SegVal<KP> item[PW_IPT];
-#pragma unroll
-    for (int q = 0; q < PW_IPT; q++) {
-        const uint32_t kind = word[q] >> AD_KIND_SHIFT, pay = word[q] & AD_PAYLOAD;
-        SegVal<KP> x;
-        x.v = ivec_zero<KP>();
-        x.head = 0;
-        x.ends = (word[q] & AD_END) ? 1 : 0;
-        if (kind == AD_NONE) {
-            if (word[q] & AD_HEAD) {
-                x.v = w[pay];
-                x.head = 1;
-            }
-        } else {
-            IVec<KP> g = state_load<KP>(pval + pay);
-            if (kind == AD_DIFF) {
-                x.v = g - state_load<KP>(pval + pay - 1);
-            } else {
-                x.v = kind == AD_NEG ? ivec_zero<KP>() - g : g;
-            }
-        }
-        item[q] = x;
-    }
-#pragma unroll
-    for (int q = 1; q < PW_IPT; q++) item[q] = op(item[q - 1], item[q]);
-    // warp scan of the lane aggregates
-    SegVal<KP> incl = item[PW_IPT - 1];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        SegVal<KP> up = seg_shfl_up<KP>(incl, d);
-        if (lane >= (uint32_t) d) incl = op(up, incl);
-    }
     SegVal<KP> identity;
     identity.v = ivec_zero<KP>();
     identity.head = 0;
     identity.ends = 0;
-    SegVal<KP> excl = seg_shfl_up<KP>(incl, 1);
-    if (lane == 0) excl = identity;
 
-    // (b) carry entering this warp tile: decoupled look-back within the level
-    SegVal<KP> carry = identity;
-    if (lane == 31) {
-        WDesc<KP> *me = desc + wt;
-        const uint32_t first = dep * PROP_WARPS;
-        if (wt == first) {
-            desc_publish<KP>(me, incl, 2);
-        } else {
-            desc_publish<KP>(me, incl, 1);
-            uint32_t p = wt - 1, spins = 0;
-            while (true) {
-                SegVal<KP> got;
-                int st = desc_peek<KP>(desc + p, got);
-                if (st == 0) {
-                    if (++spins > SPIN_LIMIT
-                        || ((spins & 1023u) == 0 && *(volatile int *) error_flag)) {
+    if (blockIdx.x < ntiles) {
+        const uint32_t *src = ad + ((size_t) blockIdx.x * PROP_WARPS + warp) * WTILE;
+        for (uint32_t j = lane * 4; j < WTILE; j += 128) cp_async16(stage + j, src + j);
+    }
+    uint32_t buf = 0;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        TRACE(0);
+        cp_async_wait_all();  // this tile's words (issued one iteration ago)
+        __syncwarp();
+        // prefetch the next tile
+        const uint32_t next = tile + gridDim.x;
+        if (next < ntiles) {
+            const uint32_t *src = ad + ((size_t) next * PROP_WARPS + warp) * WTILE;
+            uint32_t *dst = stage + (buf ^ 1) * WTILE;
+            for (uint32_t j = lane * 4; j < WTILE; j += 128) cp_async16(dst + j, src + j);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        const uint32_t wt = tile * PROP_WARPS + warp;
+        const uint32_t dep = __ldg(tile_dep + tile);
+        const uint32_t piece_base = __ldg(wt_piece + wt);
+        // striped: lane l holds addends q * 32 + l, so that one load instruction covers 32
+        // consecutive addends and its gathers (consecutive pieces of a child, mostly) share sectors
+        uint32_t ws[PW_IPT];
+#pragma unroll
+        for (int q = 0; q < PW_IPT; q++) ws[q] = stage[buf * WTILE + q * 32 + lane];
+        // (a) every lower level complete: one thread watches the global counter
+        if (dep > 0) {
+            if (threadIdx.x == 0) {
+                volatile uint32_t *done = counters + 1;
+                uint32_t spins = 0;
+                if (trace != nullptr) trace[(size_t) tile * 6 + 1] = gtime();
+                while (*done < dep) {
+                    if (++spins > SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int *) error_flag)) {
                         *error_flag = 1;
                         break;
                     }
-                    continue;
                 }
-                carry = op(got, carry);
-                if (st == 2 || carry.head || p == first) break;
-                p--;
+                __threadfence();
             }
-            desc_publish<KP>(me, op(carry, incl), 2);
+            __syncthreads();
         }
-    }
+        TRACE(2);
+        // gather (striped): issue every load of the lane before the first use, so the 8-16 loads
+        // are one round trip; then transpose words and values to blocked (lane l owns addends
+        // l * 8 + q)
+        {
+            IVec<KP> g0[PW_IPT], g1[PW_IPT];
+            uint32_t idx[PW_IPT];
 #pragma unroll
-    for (int c = 0; c < KP; c++) carry.v.v[c] = __shfl_sync(0xffffffffu, carry.v.v[c], 31);
-    carry.head = __shfl_sync(0xffffffffu, carry.head, 31);
-    // values entering this lane: carry (+) excl; publish the state at every piece end
-    SegVal<KP> in = op(carry, excl);
-    const uint32_t piece0 = piece_base + (uint32_t) excl.ends;
+            for (int q = 0; q < PW_IPT; q++) {
+                const uint32_t kind = ws[q] >> AD_KIND_SHIFT, pay = ws[q] & AD_PAYLOAD;
+                idx[q] = pay + (kind == AD_NONE ? 0u : piece0);
+                g0[q] = ivec_zero<KP>();
+                if (kind != AD_NONE || (ws[q] & AD_HEAD)) g0[q] = state_load<KP>(state + idx[q]);
+            }
 #pragma unroll
-    for (int q = 0; q < PW_IPT; q++) {
-        if (word[q] & AD_END) {
-            SegVal<KP> r = op(in, item[q]);
-            pval[piece0 + (uint32_t) item[q].ends - 1] = r.v;
+            for (int q = 0; q < PW_IPT; q++) {
+                g1[q] = ivec_zero<KP>();
+                if ((ws[q] >> AD_KIND_SHIFT) == AD_DIFF) g1[q] = state_load<KP>(state + idx[q] - 1);
+            }
+#pragma unroll
+            for (int q = 0; q < PW_IPT; q++) {
+                const uint32_t kind = ws[q] >> AD_KIND_SHIFT;
+                IVec<KP> v = kind == AD_NEG ? g1[q] - g0[q] : g0[q] - g1[q];  // g1 is 0 unless DIFF
+                vbuf[padi(q * 32 + lane)] = v;
+                wbuf[padi(q * 32 + lane)] = ws[q];
+            }
         }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(&counters[1], 1u);
+        __syncwarp();
+        uint32_t word[PW_IPT];
+        SegVal<KP> item[PW_IPT];
+#pragma unroll
+        for (int q = 0; q < PW_IPT; q++) {
+            word[q] = wbuf[padi(lane * PW_IPT + q)];
+            item[q].v = vbuf[padi(lane * PW_IPT + q)];
+            item[q].head = (word[q] >> AD_KIND_SHIFT) == AD_NONE && (word[q] & AD_HEAD) ? 1 : 0;
+            item[q].ends = (word[q] & AD_END) ? 1 : 0;
+        }
+        __syncwarp();
+        TRACE(3);
+#pragma unroll
+        for (int q = 1; q < PW_IPT; q++) item[q] = op(item[q - 1], item[q]);
+        // warp scan of the lane aggregates
+        SegVal<KP> incl = item[PW_IPT - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            SegVal<KP> up = seg_shfl_up<KP>(incl, d);
+            if (lane >= (uint32_t) d) incl = op(up, incl);
+        }
+        SegVal<KP> excl = seg_shfl_up<KP>(incl, 1);
+        if (lane == 0) excl = identity;
+
+        // (b) carry entering this warp tile: decoupled look-back within the level
+        SegVal<KP> carry = identity;
+        if (lane == 31) {
+            WDesc<KP> *me = desc + wt;
+            const uint32_t first = dep * PROP_WARPS;
+            if (wt == first) {
+                desc_publish<KP>(me, incl, 2);
+            } else {
+                desc_publish<KP>(me, incl, 1);
+                uint32_t p = wt - 1, spins = 0;
+                while (true) {
+                    SegVal<KP> got;
+                    int st = desc_peek<KP>(desc + p, got);
+                    if (st == 0) {
+                        if (++spins > SPIN_LIMIT
+                            || ((spins & 1023u) == 0 && *(volatile int *) error_flag)) {
+                            *error_flag = 1;
+                            break;
+                        }
+                        continue;
+                    }
+                    carry = op(got, carry);
+                    if (st == 2 || carry.head || p == first) break;
+                    p--;
+                }
+                desc_publish<KP>(me, op(carry, incl), 2);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < KP; c++) carry.v.v[c] = __shfl_sync(0xffffffffu, carry.v.v[c], 31);
+        carry.head = __shfl_sync(0xffffffffu, carry.head, 31);
+        const uint32_t total_ends = (uint32_t) __shfl_sync(0xffffffffu, incl.ends, 31);
+        TRACE(4);
+        // values entering this lane: carry (+) excl; compact the state at every piece end, then
+        // publish the warp tile's pieces with coalesced stores
+        SegVal<KP> in = op(carry, excl);
+#pragma unroll
+        for (int q = 0; q < PW_IPT; q++) {
+            if (word[q] & AD_END) {
+                SegVal<KP> r = op(in, item[q]);
+                vbuf[excl.ends + item[q].ends - 1] = r.v;
+            }
+        }
+        __syncwarp();
+        for (uint32_t j = lane; j < total_ends; j += 32) pval[piece_base + j] = vbuf[j];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&counters[1], 1u);
+            if (trace != nullptr) trace[(size_t) tile * 6 + 5] = gtime();
+        }
+        buf ^= 1;
     }
 }
 
@@ -823,7 +894,9 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         total += sp.sizes[k];
         h_off[k + 1] = (uint32_t) total;
     }
-    IVec<KP> *w = A.get<IVec<KP>>(N);
+    const uint32_t Npad = (N + 3u) & ~3u;
+    IVec<KP> *state = A.get<IVec<KP>>((size_t) Npad + P.P + 2048);  // summary tiles read whole tiles
+    IVec<KP> *w = state;
     uint32_t *d_off = A.get<uint32_t>(K + 1);
     const int32_t *d_sets = sp.sets;
     if (!sp.sets_on_device) {
@@ -875,7 +948,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     TSKB_CK(cudaEventRecord(P.ev[1], s));
 
     // ---- phase 1: propagate
-    IVec<KP> *pval = A.get<IVec<KP>>((size_t) P.P + 2048);  // summary tiles read whole tiles
+    IVec<KP> *pval = state + Npad;
     int *d_err = A.get<int>(1);
     TSKB_CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
     if (P.ntiles) {
@@ -884,8 +957,28 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         uint32_t *counters = A.get<uint32_t>(2);
         TSKB_CK(cudaMemsetAsync(desc, 0, nwt * sizeof(WDesc<KP>), s));
         TSKB_CK(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
-        k_propagate<KP><<<P.ntiles, PROP_TB, 0, s>>>(P.tile_dep.p, P.wt_piece.p, P.ad.p, w, pval, desc,
-            counters, d_err);
+        unsigned long long *trace = nullptr;
+        if (getenv("TSKB_TRACE") != nullptr) {
+            trace = A.get<unsigned long long>((size_t) P.ntiles * 6);
+            TSKB_CK(cudaMemsetAsync(trace, 0, (size_t) P.ntiles * 6 * sizeof(unsigned long long), s));
+            P.stats_trace = trace;
+        }
+        TSKB_CK(cudaFuncSetAttribute(k_propagate<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) propagate_smem<KP>()));
+        int per_sm = 1, sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
+        TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<KP>, PROP_TB,
+            propagate_smem<KP>()));
+        const uint32_t grid = std::min<uint32_t>(P.ntiles, (uint32_t) (sms * std::max(per_sm, 1)));
+        {
+            uint32_t a_ntiles = P.ntiles;
+            const uint32_t *a_dep = P.tile_dep.p, *a_wtp = P.wt_piece.p, *a_ad = P.ad.p;
+            uint32_t a_piece0 = Npad;
+            void *args[] = { &a_ntiles, &a_dep, &a_wtp, &a_ad, &a_piece0, &state, &desc, &counters,
+                &d_err, &trace };
+            TSKB_CK(cudaLaunchCooperativeKernel((const void *) k_propagate<KP>, dim3(grid),
+                dim3(PROP_TB), args, propagate_smem<KP>(), s));
+        }
         TSKB_CK_LAUNCH();
         c.launches++;
     }

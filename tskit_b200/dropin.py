@@ -1,0 +1,192 @@
+"""Drop-in seam behind the unchanged ``tskit.TreeSequence`` statistics API.
+
+Every statistic of ``python/tskit/trees.py`` reaches C through the bound methods of
+``self._ll_tree_sequence`` looked up at call time (``trees.py:4157-4158``; call sites
+``:7997, 8551, 8620, 8679/8699/8799, 8948, 9837, 10010-10011, 10088/10098,
+10182/10226/10265, 10321/10375/10421``).  ``AccelTreeSequence`` is a ``tskit.TreeSequence``
+subclass sharing the same low-level object whose ``_ll_tree_sequence`` attribute is a property:
+while one of the public statistics methods runs it returns a proxy that sends the low-level
+statistics calls to the B200 engine (``lowlevel.LLTreeSequence``); at any other time it returns
+the real ``_tskit.TreeSequence`` (whose C constructors type-check their argument,
+``trees.py:713``, ``genotypes.py:124-125``), so trees(), variants(), tables, pickling ... are
+untouched.  All of ``trees.py`` (argument normalisation, dimension dropping, Fst / Tajima's D /
+GRM post-processing) runs unmodified on top.
+
+    import tskit
+    from tskit_b200.dropin import accelerate
+    ts = accelerate(tskit.load("x.trees"))       # device staging happens once, here
+    ts.diversity(sample_sets, windows=w, mode="branch")   # same call, same result, on the GPU
+
+There is no CPU fallback for the accelerated calls: an engine failure raises.  Calls the engine
+does not cover (``mode="node"``, float-weighted ``general_stat``) are forwarded to the
+reference object and counted in ``ts.accel_stats["forwarded"]`` so that tests can assert which
+path ran.
+"""
+import threading
+
+import numpy as np
+
+from . import lowlevel
+from .tables import Tables
+
+try:  # the host product; tests put baseline/_ref on sys.path
+    import tskit
+    import _tskit
+except ImportError:  # pragma: no cover
+    tskit = None
+    _tskit = None
+
+ONE_WAY = ("diversity", "segregating_sites", "Y1")
+K_WAY = ("divergence", "genetic_relatedness", "Y2", "f2", "Y3", "f3", "f4")
+PUBLIC_STATS = (
+    "diversity", "divergence", "divergence_matrix", "genetic_relatedness",
+    "genetic_relatedness_matrix", "segregating_sites", "Tajimas_D", "Fst", "Y1", "Y2", "Y3",
+    "f2", "f3", "f4", "sample_count_stat", "general_stat")
+
+
+def tables_from_tree_sequence(ts):
+    """The columns the engine reads, as zero-copy numpy views where tskit offers them
+    (``trees.py:4180-4209``)."""
+    t = ts.tables
+    return Tables(
+        sequence_length=float(ts.sequence_length),
+        nodes_flags=ts.nodes_flags, nodes_time=ts.nodes_time,
+        edges_left=ts.edges_left, edges_right=ts.edges_right,
+        edges_parent=ts.edges_parent, edges_child=ts.edges_child,
+        sites_position=ts.sites_position,
+        sites_ancestral_state=t.sites.ancestral_state,
+        sites_ancestral_state_offset=t.sites.ancestral_state_offset,
+        mutations_site=ts.mutations_site, mutations_node=ts.mutations_node,
+        mutations_parent=ts.mutations_parent,
+        mutations_derived_state=t.mutations.derived_state,
+        mutations_derived_state_offset=t.mutations.derived_state_offset,
+        time_uncalibrated=(ts.time_units == "uncalibrated"),
+        edge_insertion_order=ts.indexes_edge_insertion_order,
+        edge_removal_order=ts.indexes_edge_removal_order)
+
+
+class _Proxy:
+    """Stands in for ``ts._ll_tree_sequence`` while a statistics method runs."""
+
+    def __init__(self, real, engine, counters):
+        self._real = real
+        self._engine = engine
+        self._counters = counters
+
+    def __getattr__(self, name):  # everything that is not a statistic
+        return getattr(self._real, name)
+
+    def _run(self, name, args, kwargs):
+        mode = kwargs.get("mode")
+        if mode == "node":
+            # W x N x M output: outside the hot path; visibly forwarded
+            self._counters["forwarded"] += 1
+            return getattr(self._real, name)(*args, **kwargs)
+        try:
+            out = getattr(self._engine, name)(*args, **kwargs)
+        except lowlevel.LibraryError as e:
+            if e.code == -20003:  # valid tskit call the engine does not accelerate
+                self._counters["forwarded"] += 1
+                return getattr(self._real, name)(*args, **kwargs)
+            if -20000 < e.code < 0 and _tskit is not None:
+                raise _tskit.LibraryError(str(e)) from None  # same type and text as the reference
+            raise
+        self._counters["accelerated"] += 1
+        return out
+
+
+def _make(name):
+    def method(self, *args, **kwargs):
+        return self._run(name, args, kwargs)
+    method.__name__ = name  # trees.py:8195 inspects ll_method.__name__
+    return method
+
+
+for _n in ONE_WAY + K_WAY + ("divergence_matrix", "general_stat"):
+    setattr(_Proxy, _n, _make(_n))
+
+
+if tskit is not None:
+
+    class AccelTreeSequence(tskit.TreeSequence):
+        """``tskit.TreeSequence`` whose statistics run on the B200 engine."""
+
+        def __init__(self, ll_tree_sequence, device=0, engine=None):
+            self._accel_depth = 0
+            self._accel_lock = threading.Lock()  # divergence_matrix(num_threads>0) calls from a pool
+            self._accel_proxy = None
+            self.accel_stats = {"accelerated": 0, "forwarded": 0}
+            super().__init__(ll_tree_sequence)
+            if engine is None:
+                engine = lowlevel.LLTreeSequence(tables_from_tree_sequence(self), device=device)
+            self._accel_engine = engine
+            self._accel_proxy = _Proxy(self._ll_real, engine, self.accel_stats)
+
+        @property
+        def _ll_tree_sequence(self):
+            if self._accel_depth > 0 and self._accel_proxy is not None:
+                return self._accel_proxy
+            return self._ll_real
+
+        @_ll_tree_sequence.setter
+        def _ll_tree_sequence(self, value):  # assigned by TreeSequence.__init__ (trees.py:4157)
+            self._ll_real = value
+
+        def _accel_call(self, name, args, kwargs):
+            with self._accel_lock:
+                self._accel_depth += 1
+            try:
+                return getattr(super(), name)(*args, **kwargs)
+            finally:
+                with self._accel_lock:
+                    self._accel_depth -= 1
+
+        def __reduce__(self):
+            return (_unpickle, (super().__reduce__(),))
+
+    def _public(name):
+        def method(self, *args, **kwargs):
+            return self._accel_call(name, args, kwargs)
+        method.__name__ = name
+        method.__doc__ = getattr(tskit.TreeSequence, name).__doc__
+        return method
+
+    for _n in PUBLIC_STATS:
+        setattr(AccelTreeSequence, _n, _public(_n))
+
+    def _unpickle(base):
+        fn, args = base[0], base[1]
+        return accelerate(fn(*args))
+
+
+def accelerate(ts, device=0, engine=None):
+    """Wrap a ``tskit.TreeSequence`` (same low-level object, no copy of the tables on the host)."""
+    if tskit is None:
+        raise RuntimeError("tskit is not importable")
+    return AccelTreeSequence(ts.ll_tree_sequence, device=device, engine=engine)
+
+
+def from_tables(tables: Tables):
+    """Build a reference ``tskit.TreeSequence`` from a ``Tables`` container (tests, benchmarks)."""
+    tc = tskit.TableCollection(tables.sequence_length)
+    if tables.time_uncalibrated:
+        tc.time_units = "uncalibrated"
+    N = tables.num_nodes
+    tc.nodes.set_columns(flags=tables.nodes_flags, time=tables.nodes_time,
+                         population=np.full(N, -1, dtype=np.int32),
+                         individual=np.full(N, -1, dtype=np.int32))
+    tc.edges.set_columns(left=tables.edges_left, right=tables.edges_right,
+                         parent=tables.edges_parent, child=tables.edges_child)
+    if tables.num_sites:
+        tc.sites.set_columns(position=tables.sites_position,
+                             ancestral_state=tables.sites_ancestral_state,
+                             ancestral_state_offset=tables.sites_ancestral_state_offset)
+        tables.ensure_derived()
+        Mu = tables.num_mutations
+        tc.mutations.set_columns(site=tables.mutations_site, node=tables.mutations_node,
+                                 parent=tables.mutations_parent,
+                                 time=np.full(Mu, tskit.UNKNOWN_TIME),
+                                 derived_state=tables.mutations_derived_state,
+                                 derived_state_offset=tables.mutations_derived_state_offset)
+    tc.sort()
+    return tc.tree_sequence()
