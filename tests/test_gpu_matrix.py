@@ -1,0 +1,131 @@
+"""GPU suite, matrix path: genotype decode (bit-exact against the oracle and the reference's
+golden vectors) and the site-mode divergence matrix (exact integer counts, so fp64 results are
+compared at 1e-12), through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import port
+from tests import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engines(wf_small):
+    from tskit_b200.lowlevel import LLTreeSequence
+    return LLTreeSequence(wf_small), port.Oracle(wf_small)
+
+
+def test_genotypes_golden_single_tree():
+    from tskit_b200.lowlevel import LLTreeSequence
+    ll = LLTreeSequence(fx.load("single_tree"))
+    assert np.array_equal(ll.genotype_matrix(), fx.SINGLE_TREE_GENOTYPES)  # test_genotypes.c:447-503
+
+
+@pytest.mark.parametrize("name", [n for n in fx.ALL if n != "empty"])
+def test_genotypes_reference_fixtures(name):
+    from tskit_b200.lowlevel import LLTreeSequence
+    t = fx.load(name)
+    if t.num_sites == 0:
+        pytest.skip("no sites")
+    ll, o = LLTreeSequence(t), port.Oracle(t)
+    for missing in (True, False):
+        assert np.array_equal(ll.genotype_matrix(isolated_as_missing=missing),
+                              o.genotype_matrix(isolated_as_missing=missing)), (name, missing)
+    sub = t.samples[::2]
+    assert np.array_equal(ll.genotype_matrix(samples=sub), o.genotype_matrix(samples=sub))
+
+
+def test_genotypes_wright_fisher(wf_small, engines):
+    ll, o = engines
+    g = ll.genotype_matrix()
+    assert g.dtype == np.int8 and g.shape == (wf_small.num_sites, wf_small.num_samples)
+    assert np.array_equal(g, o.genotype_matrix())
+    sub = wf_small.samples[[5, 3, 100, 7]]  # any order, any subset
+    assert np.array_equal(ll.genotype_matrix(samples=sub, isolated_as_missing=False),
+                          o.genotype_matrix(samples=sub, isolated_as_missing=False))
+
+
+def test_genotypes_1k(wf_1k):
+    from tskit_b200.lowlevel import LLTreeSequence
+    ll, o = LLTreeSequence(wf_1k), port.Oracle(wf_1k)
+    assert np.array_equal(ll.genotype_matrix(), o.genotype_matrix())
+
+
+def test_divmat_golden_single_tree():
+    from tskit_b200.lowlevel import LLTreeSequence
+    ll = LLTreeSequence(fx.load("single_tree"))
+    d = ll.divergence_matrix([0, 1.0], mode="site", span_normalise=False)
+    assert np.array_equal(d[0], fx.SINGLE_TREE_D_SITE)  # test_stats.c:1459-1473
+
+
+def test_divmat_site_wright_fisher(wf_small, engines):
+    ll, o = engines
+    L = wf_small.sequence_length
+    s = wf_small.samples
+    for windows in ([0, L], np.linspace(0, L, 5), [L * 0.1, L * 0.35, L * 0.8]):
+        for span in (True, False):
+            got = ll.divergence_matrix(windows, mode="site", span_normalise=span)
+            want = o.divergence_matrix(None, windows=windows, mode="site", span_normalise=span)
+            assert got.shape == want.shape
+            assert np.allclose(got, want, rtol=1e-12, atol=0)
+    sets = [s[:40], s[40:41], s[50:170]]
+    sizes = np.array([len(x) for x in sets], dtype=np.uint64)
+    flat = np.concatenate(sets).astype(np.int32)
+    w = np.linspace(0, L, 4)
+    got = ll.divergence_matrix(w, sample_sets=flat, sample_set_sizes=sizes, mode="site")
+    want = o.divergence_matrix(sets, windows=w, mode="site")
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    assert np.all(got[:, 1, 1] == 0)  # singleton set: diagonal 0, not NaN (trees.c:8888-8891)
+
+
+@pytest.mark.parametrize("name", ["paper", "nonbinary", "multiroot", "missing", "case_1"])
+def test_divmat_site_fixtures(name):
+    from tskit_b200.lowlevel import LLTreeSequence
+    t = fx.load(name)
+    ll, o = LLTreeSequence(t), port.Oracle(t)
+    L = t.sequence_length
+    got = ll.divergence_matrix([0, L / 2, L], mode="site")
+    want = o.divergence_matrix(None, windows=[0, L / 2, L], mode="site")
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+
+
+def test_divmat_errors(wf_small, engines):
+    from tskit_b200.lowlevel import LibraryError
+    ll, _ = engines
+    L = wf_small.sequence_length
+    s = wf_small.samples
+
+    def code(fn):
+        with pytest.raises(LibraryError) as e:
+            fn()
+        return e.value.code
+
+    u64 = lambda *a: np.array(a, dtype=np.uint64)  # noqa: E731
+    i32 = lambda *a: np.array(a, dtype=np.int32)  # noqa: E731
+    assert code(lambda: ll.divergence_matrix([0, L], mode="node")) == -909
+    assert code(lambda: ll.divergence_matrix([0, L + 1])) == -901
+    assert code(lambda: ll.divergence_matrix([-1, L])) == -901
+    assert code(lambda: ll.divergence_matrix([0, L, L / 2])) == -901
+    assert code(lambda: ll.divergence_matrix([0, L], sample_sets=i32(s[0], s[0]), sample_set_sizes=u64(1, 1))) == -600
+    internal = int(np.nonzero((wf_small.nodes_flags & 1) == 0)[0][0])
+    assert code(lambda: ll.divergence_matrix([0, L], sample_sets=i32(internal), sample_set_sizes=u64(1))) == -601
+    assert code(lambda: ll.divergence_matrix([0, L], sample_sets=i32(10 ** 7), sample_set_sizes=u64(1))) == -202
+    assert code(lambda: ll.divergence_matrix([0, L], mode="branch")) == -20003
+
+
+def test_genetic_relatedness_matrix_through_dropin(wf_small):
+    tskit = pytest.importorskip("tskit")
+    from tskit_b200 import dropin
+    ts = dropin.from_tables(wf_small)
+    acc = dropin.accelerate(ts)
+    s = ts.samples()
+    sets = [list(s[:30]), list(s[30:90]), list(s[90:])]
+    w = np.linspace(0, ts.sequence_length, 4)
+    got = acc.genetic_relatedness_matrix(sample_sets=sets, windows=w, mode="site")
+    want = ts.genetic_relatedness_matrix(sample_sets=sets, windows=w, mode="site")
+    assert np.allclose(got, want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
+    got = acc.divergence_matrix(windows=w, mode="site")
+    want = ts.divergence_matrix(windows=w, mode="site")
+    assert np.allclose(got, want, rtol=1e-12)
+    assert acc.accel_stats["forwarded"] == 0

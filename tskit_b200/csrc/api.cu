@@ -298,6 +298,24 @@ int tskb_treeseq_trees_at(const tskb_treeseq_t *self, uint64_t num_positions,
     });
 }
 
+int tskb_treeseq_divergence_matrix(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result) {
+    if (self == nullptr || self->plan == nullptr || result == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    return guarded([&]() -> int {
+        return run_divergence_matrix(self->plan, num_sample_sets, sample_set_sizes, sample_sets,
+            num_windows, windows, options, result);
+    });
+}
+
+int tskb_treeseq_genotype_matrix(const tskb_treeseq_t *self, const int32_t *samples,
+    uint64_t num_samples, uint32_t options, int8_t *genotypes) {
+    if (self == nullptr || self->plan == nullptr || genotypes == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    return guarded([&]() -> int {
+        return run_genotype_matrix(self->plan, samples, num_samples, options, genotypes);
+    });
+}
+
 int tskb_treeseq_get_stats(const tskb_treeseq_t *self, tskb_stats_t *out) {
     if (self == nullptr || self->plan == nullptr || out == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
     std::lock_guard<std::mutex> lock(self->plan->mu);

@@ -1,20 +1,563 @@
-// matrix.cu -- genotype decode and divergence / relatedness matrices (a9-a12).
+// matrix.cu -- genotype decode and the site-mode divergence matrix (a9, a10, a12).
+//
+// Decode (tsk_variant_decode over all sites, c/tskit/genotypes.c:473-594): every genotype
+// starts at the ancestral allele 0 (genotypes.c:550-552), isolated samples are marked -1 unless
+// TSK_ISOLATED_NOT_MISSING (genotypes.c:413-455, 554-559), then the site's mutations are applied
+// in table order, each overwriting the listed samples in the subtree below its node
+// (genotypes.c:355-411).  On the device the subtree walk is a breadth-first expansion of
+// (site, node) items over a parent-major edge CSR -- output-sensitive: the work is the number
+// of non-ancestral genotypes, not sites x samples -- one round per mutation rank so that later
+// mutations of a site overwrite earlier ones exactly as the reference's loop does.
+//
+// Divergence matrix, site mode (trees.c:8684-8826, 8876-8899): for every site of the window and
+// every pair of samples carrying different alleles the pair's entry grows by one.  With the
+// genotypes sample-major, "same allele" counts are  sum over alleles a of (G == a)(G == a)^T, an
+// int8 x int8 -> int32 product (exact), and different = sites - same.  Set aggregation,
+// count-normalisation and span-normalisation follow in fp64.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstring>
+
 #include "plan.cuh"
 
-using namespace tskb;
+namespace tskb {
 
-extern "C" {
+struct DecodeAux {
+    // parent-major CSR of all edges, sorted by (parent, left); pmax = running max of right
+    // within the parent's list, which bounds the backward scan of an interval-stabbing query
+    DevArray<uint32_t> off;  // [N + 1]
+    DevArray<double> left, right, pmax;
+    DevArray<int32_t> child;
+};
 
-int tskb_treeseq_divergence_matrix(const tskb_treeseq_t *self, uint64_t, const uint64_t *,
-    const int32_t *, uint64_t, const double *, uint32_t, double *) {
-    (void) self;
-    return TSKB_ERR_UNSUPPORTED;
+void free_decode_aux(DecodeAux *a) { delete a; }
+
+namespace {
+
+constexpr int TB = 256;
+
+__device__ inline uint64_t ordered_bits64(double x) {
+    uint64_t b = (uint64_t) __double_as_longlong(x);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
-int tskb_treeseq_genotype_matrix(const tskb_treeseq_t *self, const int32_t *, uint64_t, uint32_t,
-    int8_t *) {
-    (void) self;
-    return TSKB_ERR_UNSUPPORTED;
+__global__ void k_csr_child_keys(const uint32_t *coff, uint32_t N, const double *csr_left, uint32_t E,
+    uint64_t *key, uint32_t *val, int32_t *child_of) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= E) return;
+    key[j] = ordered_bits64(csr_left[j]);
+    val[j] = j;
+    child_of[j] = (int32_t) (upper_bound_dev(coff, N + 1, j) - 1);
 }
 
+__global__ void k_gather_u32(const uint32_t *perm, const int32_t *src, uint32_t n, uint32_t *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t) src[perm[i]];
 }
+
+__global__ void k_pm_gather(const uint32_t *perm, uint32_t E, const double *csr_left,
+    const double *csr_right, const int32_t *child_of, double *left, double *right, int32_t *child) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E) return;
+    uint32_t j = perm[i];
+    left[i] = csr_left[j];
+    right[i] = csr_right[j];
+    child[i] = child_of[j];
+}
+
+__global__ void k_lower_offsets(const uint32_t *sorted_keys, uint32_t n, uint32_t nq, uint32_t *out) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) out[q] = lower_bound_dev(sorted_keys, n, q);
+}
+
+struct MaxOp {
+    __device__ __forceinline__ double operator()(double a, double b) const { return a > b ? a : b; }
+};
+
+__global__ void k_fill_i32(int32_t *out, size_t n, int32_t v) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
+__global__ void k_set_cols(const int32_t *samples, uint32_t n, int32_t *col) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) col[samples[i]] = (int32_t) i;
+}
+
+// ---- isolated samples: no edge above and no edge below at the site's position
+__global__ void k_mark_isolated(const int32_t *samples, uint32_t n, const uint32_t *coff,
+    const double *csr_left, const double *csr_right, const uint32_t *pm_off, const double *pm_left,
+    const double *pm_right, const double *site_pos, uint32_t s0, uint32_t s1, double L, int8_t *G,
+    size_t stride_site, size_t stride_sample) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t u = samples[i];
+    // merge the two interval lists (both sorted by left); reach = right end of the coverage
+    uint32_t a = coff[u], a1 = coff[u + 1], b = pm_off[u], b1 = pm_off[u + 1];
+    double reach = 0.0;
+    while (true) {
+        double nl, nr;
+        bool ha = a < a1, hb = b < b1;
+        if (!ha && !hb) {
+            nl = L;
+            nr = L;
+        } else if (ha && (!hb || csr_left[a] <= pm_left[b])) {
+            nl = csr_left[a];
+            nr = csr_right[a];
+            a++;
+        } else {
+            nl = pm_left[b];
+            nr = pm_right[b];
+            b++;
+        }
+        if (nl > reach) {  // gap [reach, nl): isolated
+            uint32_t lo = lower_bound_dev(site_pos + s0, s1 - s0, reach) + s0;
+            uint32_t hi = lower_bound_dev(site_pos + s0, s1 - s0, nl) + s0;
+            for (uint32_t s = lo; s < hi; s++) G[(size_t) (s - s0) * stride_site + (size_t) i * stride_sample] = -1;
+        }
+        if (nr > reach) reach = nr;
+        if (!ha && !hb) break;
+    }
+}
+
+// ---- breadth-first expansion of (site, node) items
+__global__ void k_frontier_init(uint32_t r, uint32_t s0, uint32_t s1, const uint32_t *site_moff,
+    const int32_t *mut_node, uint2 *items, uint32_t *count) {
+    uint32_t s = s0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= s1) return;
+    uint32_t m0 = site_moff[s], m1 = site_moff[s + 1];
+    if (m1 - m0 > r) {
+        uint32_t idx = atomicAdd(count, 1u);
+        items[idx] = make_uint2(s, (uint32_t) mut_node[m0 + r]);
+    }
+}
+
+__global__ void k_expand(const uint2 *items, uint32_t nitems, uint32_t r, uint32_t s0,
+    const double *site_pos, const uint32_t *site_moff, const uint16_t *mut_allele,
+    const int32_t *col, const uint32_t *pm_off, const double *pm_left, const double *pm_right,
+    const double *pm_pmax, const int32_t *pm_child, int8_t *G, size_t stride_site,
+    size_t stride_sample, uint2 *next, uint32_t cap, uint32_t *next_count, int *overflow) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nitems) return;
+    const uint2 it = items[t];
+    const uint32_t s = it.x, u = it.y;
+    const double x = site_pos[s];
+    int32_t c = col[u];
+    if (c >= 0) {
+        G[(size_t) (s - s0) * stride_site + (size_t) c * stride_sample] = (int8_t) mut_allele[site_moff[s] + r];
+    }
+    uint32_t lo = pm_off[u], hi = pm_off[u + 1];
+    uint32_t k = upper_bound_dev(pm_left + lo, hi - lo, x);  // edges with left <= x
+    for (uint32_t j = lo + k; j-- > lo;) {
+        if (!(pm_pmax[j] > x)) break;  // nothing further left reaches x
+        if (pm_right[j] > x) {
+            uint32_t idx = atomicAdd(next_count, 1u);
+            if (idx < cap) {
+                next[idx] = make_uint2(s, (uint32_t) pm_child[j]);
+            } else {
+                *overflow = 1;
+            }
+        }
+    }
+}
+
+// ---- same-allele counts: C[i][j] += sum over sites k in [k_lo, k_hi) of [X[i][k] == a][X[j][k] == a]
+// X sample-major int8 [n x ld].  128 x 128 x 64 CTA tiles, 8 warps of 64 x 32, legacy int8
+// tensor path (mma.sync m16n8k32, exact int32 accumulation); only blocks with bi <= bj.
+constexpr int GM = 128, GK = 64, GLD = GK + 16;
+
+__device__ __forceinline__ void mma_s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+    uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void load_onehot_tile(const int8_t *X, size_t ld, uint32_t n, uint32_t row0,
+    uint32_t k0, uint32_t k_lo, uint32_t k_hi, uint32_t a_rep, unsigned char (*dst)[GLD]) {
+    // 128 rows x 64 bytes = 512 chunks of 16 bytes, 2 per thread
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        uint32_t chunk = threadIdx.x + c * TB;
+        uint32_t row = chunk >> 2, kc = (chunk & 3) * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        uint32_t k = k0 + kc;
+        if (row0 + row < n && k < k_hi && k + 16 > k_lo) {
+            uint4 raw = *reinterpret_cast<const uint4 *>(X + (size_t) (row0 + row) * ld + k);
+            uint32_t wds[4] = { raw.x, raw.y, raw.z, raw.w };
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t eq = __vcmpeq4(wds[q], a_rep) & 0x01010101u;
+                uint32_t kb = k + 4 * q;
+                if (kb < k_lo || kb + 4 > k_hi) {  // partial word at the range ends
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        if (kb + b >= k_lo && kb + b < k_hi) m |= 0xffu << (8 * b);
+                    }
+                    eq &= m;
+                }
+                wds[q] = eq;
+            }
+            v = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        }
+        *reinterpret_cast<uint4 *>(&dst[row][kc]) = v;
+    }
+}
+
+__global__ void __launch_bounds__(TB) k_same_gemm(const int8_t *X, size_t ld, uint32_t n, uint32_t k_lo,
+    uint32_t k_hi, int allele, int32_t *C) {
+    __shared__ __align__(16) unsigned char As[GM][GLD];
+    __shared__ __align__(16) unsigned char Bs[GM][GLD];
+    const uint32_t bi = blockIdx.y, bj = blockIdx.x;
+    if (bi > bj) return;
+    const uint32_t i0 = bi * GM, j0 = bj * GM;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t wm = warp >> 2, wn = warp & 3, g = lane >> 2, tig = lane & 3;
+    const uint32_t a_rep = 0x01010101u * (uint32_t) (allele & 0xff);
+    int acc[4][4][4];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[mi][ni][q] = 0;
+    for (uint32_t k0 = k_lo & ~15u; k0 < k_hi; k0 += GK) {
+        load_onehot_tile(X, ld, n, i0, k0, k_lo, k_hi, a_rep, As);
+        load_onehot_tile(X, ld, n, j0, k0, k_lo, k_hi, a_rep, Bs);
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < GK / 32; ks++) {
+            uint32_t bf[4][2];
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                const unsigned char *p = &Bs[wn * 32 + ni * 8 + g][ks * 32 + tig * 4];
+                bf[ni][0] = *reinterpret_cast<const uint32_t *>(p);
+                bf[ni][1] = *reinterpret_cast<const uint32_t *>(p + 16);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) {
+                const unsigned char *p = &As[wm * 64 + mi * 16 + g][ks * 32 + tig * 4];
+                uint32_t a0 = *reinterpret_cast<const uint32_t *>(p);
+                uint32_t a1 = *reinterpret_cast<const uint32_t *>(p + 8 * GLD);
+                uint32_t a2 = *reinterpret_cast<const uint32_t *>(p + 16);
+                uint32_t a3 = *reinterpret_cast<const uint32_t *>(p + 8 * GLD + 16);
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) mma_s8(acc[mi][ni], a0, a1, a2, a3, bf[ni][0], bf[ni][1]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            uint32_t r0 = i0 + wm * 64 + mi * 16 + g, c0 = j0 + wn * 32 + ni * 8 + 2 * tig;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t r = r0 + (q >> 1) * 8, c = c0 + (q & 1);
+                if (r < n && c < n) C[(size_t) r * n + c] += acc[mi][ni][q];
+            }
+        }
+    }
+}
+
+// D[a][b] = sum over j in set a, k in set b of (sites - same[j][k]) (j != k), count- and
+// span-normalised (trees.c:8876-8899, 1920-1934).  `same` holds blocks with row block <= col
+// block only: read the transposed entry otherwise.
+__global__ void k_divmat_finish(const int32_t *same, uint32_t n, const uint32_t *set_off,
+    uint32_t nsets, const double *set_size, uint32_t nsites, double span, int span_normalise,
+    double *D) {
+    typedef cub::BlockReduce<double, TB> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const uint32_t a = blockIdx.y, b = blockIdx.x;
+    if (a > b) return;
+    const uint32_t r0 = set_off[a], r1 = set_off[a + 1], c0 = set_off[b], c1 = set_off[b + 1];
+    const uint32_t nr = r1 - r0, nc = c1 - c0;
+    double sum = 0.0;
+    for (size_t t = threadIdx.x; t < (size_t) nr * nc; t += TB) {
+        uint32_t j = r0 + (uint32_t) (t / nc), k = c0 + (uint32_t) (t % nc);
+        if (j == k) continue;
+        uint32_t lo = j < k ? j : k, hi = j < k ? k : j;
+        // entries of the upper block triangle: (lo, hi) is stored iff block(lo) <= block(hi): always
+        sum += (double) ((int64_t) nsites - (int64_t) same[(size_t) lo * n + hi]);
+    }
+    double tot = BR(tmp).Sum(sum);
+    if (threadIdx.x == 0) {
+        double denom = a == b ? set_size[a] * (set_size[a] - 1) : set_size[a] * set_size[b];
+        if (!(a == b && denom == 0)) tot /= denom;
+        if (span_normalise) tot /= span;
+        D[(size_t) a * nsets + b] = tot;
+        D[(size_t) b * nsets + a] = tot;
+    }
+}
+
+struct Temp {
+    void *p = nullptr;
+    size_t cap = 0;
+    ~Temp() { if (p) cudaFree(p); }
+    void *need(size_t bytes) {
+        if (bytes > cap) {
+            if (p) cudaFree(p);
+            cap = bytes + 1024;
+            TSKB_CK(cudaMalloc(&p, cap));
+        }
+        return p;
+    }
+};
+
+const DecodeAux &ensure_aux(const Plan &P) {
+    if (P.decode_aux != nullptr) return *P.decode_aux;
+    cudaStream_t s = P.stream;
+    const uint32_t N = (uint32_t) P.N, E = (uint32_t) P.E;
+    std::unique_ptr<DecodeAux> A(new DecodeAux());
+    A->off.alloc(N + 1); A->left.alloc(E); A->right.alloc(E); A->pmax.alloc(E); A->child.alloc(E);
+    Temp tmp;
+    DevArray<uint64_t> k64, k64o;
+    DevArray<uint32_t> v, vo, pk, pko, perm;
+    DevArray<int32_t> child_of;
+    k64.alloc(E); k64o.alloc(E); v.alloc(E); vo.alloc(E); pk.alloc(E); pko.alloc(E); perm.alloc(E);
+    child_of.alloc(E);
+    if (E) {
+        k_csr_child_keys<<<grid_for(E, TB), TB, 0, s>>>(P.coff.p, N, P.csr_left.p, E, k64.p, v.p, child_of.p);
+        TSKB_CK_LAUNCH();
+        size_t bytes = 0;
+        TSKB_CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k64.p, k64o.p, v.p, vo.p, E, 0, 64, s));
+        TSKB_CK(cub::DeviceRadixSort::SortPairs(tmp.need(bytes), bytes, k64.p, k64o.p, v.p, vo.p, E, 0, 64, s));
+        k_gather_u32<<<grid_for(E, TB), TB, 0, s>>>(vo.p, P.csr_parent.p, E, pk.p);
+        TSKB_CK_LAUNCH();
+        int bits = (int) std::max(1u, ceil_log2(N));
+        TSKB_CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, pk.p, pko.p, vo.p, perm.p, E, 0, bits, s));
+        TSKB_CK(cub::DeviceRadixSort::SortPairs(tmp.need(bytes), bytes, pk.p, pko.p, vo.p, perm.p, E, 0, bits, s));
+        k_pm_gather<<<grid_for(E, TB), TB, 0, s>>>(perm.p, E, P.csr_left.p, P.csr_right.p, child_of.p,
+            A->left.p, A->right.p, A->child.p);
+        TSKB_CK_LAUNCH();
+        TSKB_CK(cub::DeviceScan::InclusiveScanByKey(nullptr, bytes, pko.p, A->right.p, A->pmax.p, MaxOp(), E,
+            ::cuda::std::equal_to<>(), s));
+        TSKB_CK(cub::DeviceScan::InclusiveScanByKey(tmp.need(bytes), bytes, pko.p, A->right.p, A->pmax.p,
+            MaxOp(), E, ::cuda::std::equal_to<>(), s));
+    }
+    k_lower_offsets<<<grid_for(N + 1, TB), TB, 0, s>>>(pko.p, E, N + 1, A->off.p);
+    TSKB_CK_LAUNCH();
+    TSKB_CK(cudaStreamSynchronize(s));
+    P.decode_aux = A.release();
+    return *P.decode_aux;
+}
+
+// genotypes of sites [s0, s1) for the listed samples into G (caller-zeroed), any strides
+void decode_sites(const Plan &P, const int32_t *d_samples, uint32_t n, uint32_t s0, uint32_t s1,
+    uint32_t options, int8_t *G, size_t stride_site, size_t stride_sample) {
+    if (s1 <= s0 || n == 0) return;
+    const DecodeAux &A = ensure_aux(P);
+    cudaStream_t s = P.stream;
+    const uint32_t N = (uint32_t) P.N;
+    DevArray<int32_t> col;
+    col.alloc(N);
+    k_fill_i32<<<grid_for(N, TB), TB, 0, s>>>(col.p, N, -1);
+    k_set_cols<<<grid_for(n, TB), TB, 0, s>>>(d_samples, n, col.p);
+    TSKB_CK_LAUNCH();
+    if (!(options & TSKB_ISOLATED_NOT_MISSING)) {
+        k_mark_isolated<<<grid_for(n, 128), 128, 0, s>>>(d_samples, n, P.coff.p, P.csr_left.p,
+            P.csr_right.p, A.off.p, A.left.p, A.right.p, P.site_pos.p, s0, s1, P.L, G, stride_site,
+            stride_sample);
+        TSKB_CK_LAUNCH();
+    }
+    // frontier buffers; a batch of sites is re-run with half the sites if a layer overflows
+    const uint32_t cap = 1u << 26;
+    DevArray<uint2> fa, fb;
+    DevArray<uint32_t> cnt;
+    DevArray<int> ovf;
+    fa.alloc(cap); fb.alloc(cap); cnt.alloc(2); ovf.alloc(1);
+    uint32_t batch = std::max<uint32_t>(1, std::min<uint32_t>(s1 - s0, cap / std::max<uint32_t>(1, n / 4)));
+    uint32_t b0 = s0;
+    while (b0 < s1) {
+        const uint32_t b1 = std::min(s1, b0 + batch);
+        bool overflow = false;
+        for (uint32_t r = 0; r < P.max_muts_per_site && !overflow; r++) {
+            uint32_t h_cnt = 0;
+            TSKB_CK(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(uint32_t), s));
+            TSKB_CK(cudaMemsetAsync(ovf.p, 0, sizeof(int), s));
+            k_frontier_init<<<grid_for(b1 - b0, TB), TB, 0, s>>>(r, b0, b1, P.site_moff.p, P.mut_node.p,
+                fa.p, cnt.p);
+            TSKB_CK_LAUNCH();
+            TSKB_CK(cudaMemcpyAsync(&h_cnt, cnt.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            TSKB_CK(cudaStreamSynchronize(s));
+            uint2 *cur = fa.p, *nxt = fb.p;
+            uint32_t guard = 0;
+            while (h_cnt > 0) {
+                TSKB_CK(cudaMemsetAsync(cnt.p + 1, 0, sizeof(uint32_t), s));
+                k_expand<<<grid_for(h_cnt, TB), TB, 0, s>>>(cur, h_cnt, r, s0, P.site_pos.p,
+                    P.site_moff.p, P.mut_allele.p, col.p, A.off.p, A.left.p, A.right.p, A.pmax.p,
+                    A.child.p, G, stride_site, stride_sample, nxt, cap, cnt.p + 1, ovf.p);
+                TSKB_CK_LAUNCH();
+                int h_ovf = 0;
+                TSKB_CK(cudaMemcpyAsync(&h_cnt, cnt.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+                TSKB_CK(cudaMemcpyAsync(&h_ovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+                TSKB_CK(cudaStreamSynchronize(s));
+                if (h_ovf) {
+                    overflow = true;
+                    break;
+                }
+                std::swap(cur, nxt);
+                if (++guard > (1u << 20)) throw (int) TSKB_ERR_BAD_PARAM_VALUE;  // cyclic input
+            }
+        }
+        if (overflow) {
+            if (batch == 1) throw (int) TSKB_ERR_NO_MEMORY;
+            batch = std::max<uint32_t>(1, batch / 2);
+            continue;  // redo this batch: rounds rewrite their genotypes in order
+        }
+        b0 = b1;
+    }
+}
+
+// tsk_treeseq_divergence_matrix argument checks (trees.c:8901-8990), same precedence
+int check_divmat_args(const Plan &P, uint64_t &nsets, const uint64_t *&sizes, const int32_t *&sets,
+    std::vector<uint64_t> &tmp_sizes, uint64_t &num_windows, const double *&windows,
+    double *default_windows, uint32_t &options, uint64_t &total) {
+    bool site = options & TSKB_STAT_SITE, branch = options & TSKB_STAT_BRANCH;
+    if (options & TSKB_STAT_NODE) return TSKB_ERR_UNSUPPORTED_STAT_MODE;
+    if (!(site || branch)) {
+        site = true;
+        options |= TSKB_STAT_SITE;
+    }
+    if (site + branch > 1) return TSKB_ERR_MULTIPLE_STAT_MODES;
+    if (options & TSKB_STAT_POLARISED) return TSKB_ERR_STAT_POLARISED_UNSUPPORTED;
+    if (windows == nullptr) {
+        num_windows = 1;
+        default_windows[0] = 0;
+        default_windows[1] = P.L;
+        windows = default_windows;
+    } else {
+        if (num_windows < 1) return TSKB_ERR_BAD_NUM_WINDOWS;
+        if (windows[0] < 0 || windows[num_windows] > P.L) return TSKB_ERR_BAD_WINDOWS;
+        for (uint64_t j = 0; j < num_windows; j++) {
+            if (windows[j] >= windows[j + 1]) return TSKB_ERR_BAD_WINDOWS;
+        }
+    }
+    if (sets == nullptr) {
+        sets = P.samples.data();
+        if (sizes == nullptr) nsets = P.num_samples;
+    }
+    if (sizes == nullptr) {
+        tmp_sizes.assign(nsets, 1);
+        sizes = tmp_sizes.data();
+    }
+    std::vector<int32_t> seen(P.N, -1);
+    total = 0;
+    uint64_t i = 0;
+    for (uint64_t j = 0; j < nsets; j++) {
+        total += sizes[j];
+        for (uint64_t k = 0; k < sizes[j]; k++, i++) {
+            int32_t u = sets[i];
+            if (u < 0 || u >= (int32_t) P.N) return TSKB_ERR_NODE_OUT_OF_BOUNDS;
+            if (P.sample_index_map[u] == -1) return TSKB_ERR_BAD_SAMPLES;
+            if (seen[u] != -1) return TSKB_ERR_DUPLICATE_SAMPLE;
+            seen[u] = (int32_t) j;
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+int run_genotype_matrix(const Plan *plan, const int32_t *samples, uint64_t num_samples,
+    uint32_t options, int8_t *genotypes) {
+    std::lock_guard<std::mutex> lock(plan->mu);
+    const Plan &P = *plan;
+    TSKB_CK(cudaSetDevice(P.device));
+    cudaStream_t s = P.stream;
+    const uint32_t S = (uint32_t) P.S;
+    DevArray<int32_t> d_s;
+    const int32_t *ds = P.d_samples.p;
+    uint32_t n = P.num_samples;
+    if (samples != nullptr) {
+        for (uint64_t j = 0; j < num_samples; j++) {
+            if (samples[j] < 0 || samples[j] >= (int32_t) P.N) return TSKB_ERR_NODE_OUT_OF_BOUNDS;
+        }
+        d_s.upload(samples, num_samples, s);
+        ds = d_s.p;
+        n = (uint32_t) num_samples;
+    }
+    if (S == 0 || n == 0) return 0;
+    DevArray<int8_t> G;
+    G.alloc((size_t) S * n);
+    TSKB_CK(cudaMemsetAsync(G.p, 0, (size_t) S * n, s));
+    decode_sites(P, ds, n, 0, S, options, G.p, n, 1);
+    TSKB_CK(cudaMemcpyAsync(genotypes, G.p, (size_t) S * n, cudaMemcpyDeviceToHost, s));
+    TSKB_CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *sizes, const int32_t *sets,
+    uint64_t num_windows, const double *windows, uint32_t options, double *result) {
+    const Plan &P = *plan;
+    std::vector<uint64_t> tmp_sizes;
+    double default_windows[2];
+    uint64_t total = 0;
+    int ret = check_divmat_args(P, nsets, sizes, sets, tmp_sizes, num_windows, windows, default_windows,
+        options, total);
+    if (ret != 0) return ret;
+    if (options & TSKB_STAT_BRANCH) {
+        if (P.time_uncalibrated && !(options & TSKB_STAT_ALLOW_TIME_UNCALIBRATED)) {
+            return TSKB_ERR_TIME_UNCALIBRATED;
+        }
+        return TSKB_ERR_UNSUPPORTED;  // branch-mode matrix (trees.c:8579-8676): not on the device yet
+    }
+    if (P.range_left != 0 || P.range_right != P.L) return TSKB_ERR_UNSUPPORTED;
+    std::lock_guard<std::mutex> lock(P.mu);
+    TSKB_CK(cudaSetDevice(P.device));
+    cudaStream_t s = P.stream;
+    const uint32_t n = (uint32_t) total, W = (uint32_t) num_windows, ns = (uint32_t) nsets;
+    memset(result, 0, (size_t) W * ns * ns * sizeof(double));
+    if (n == 0) return 0;
+    // sites covered by the windows
+    auto site_index = [&](double x) {
+        return (uint32_t) (std::lower_bound(P.h_site_pos.begin(), P.h_site_pos.end(), x) - P.h_site_pos.begin());
+    };
+    const uint32_t S0 = site_index(windows[0]), S1 = site_index(windows[W]);
+    const uint32_t ns_sites = S1 - S0;
+    const size_t ld = (((size_t) ns_sites + 15) & ~size_t(15)) + 16;
+    DevArray<int32_t> d_sets;
+    d_sets.upload(sets, n, s);
+    DevArray<int8_t> X;
+    X.alloc((size_t) n * ld);
+    TSKB_CK(cudaMemsetAsync(X.p, 0, (size_t) n * ld, s));
+    // FIXME-free: the reference decodes with TSK_ISOLATED_NOT_MISSING here (trees.c:8775)
+    decode_sites(P, d_sets.p, n, S0, S1, TSKB_ISOLATED_NOT_MISSING, X.p, 1, ld);
+    std::vector<uint32_t> h_off(ns + 1, 0);
+    std::vector<double> h_size(ns);
+    for (uint32_t a = 0; a < ns; a++) {
+        h_off[a + 1] = h_off[a] + (uint32_t) sizes[a];
+        h_size[a] = (double) sizes[a];
+    }
+    DevArray<uint32_t> d_off;
+    DevArray<double> d_size, d_D;
+    DevArray<int32_t> same;
+    d_off.upload(h_off.data(), ns + 1, s);
+    d_size.upload(h_size.data(), ns, s);
+    d_D.alloc((size_t) ns * ns);
+    same.alloc((size_t) n * n);
+    const uint32_t nb = (n + GM - 1) / GM;
+    for (uint32_t w = 0; w < W; w++) {
+        const uint32_t k_lo = site_index(windows[w]) - S0, k_hi = site_index(windows[w + 1]) - S0;
+        TSKB_CK(cudaMemsetAsync(same.p, 0, (size_t) n * n * sizeof(int32_t), s));
+        if (k_hi > k_lo) {
+            for (uint32_t a = 0; a < P.max_alleles_per_site; a++) {
+                k_same_gemm<<<dim3(nb, nb), TB, 0, s>>>(X.p, ld, n, k_lo, k_hi, (int) a, same.p);
+                TSKB_CK_LAUNCH();
+            }
+        }
+        k_divmat_finish<<<dim3(ns, ns), TB, 0, s>>>(same.p, n, d_off.p, ns, d_size.p, k_hi - k_lo,
+            windows[w + 1] - windows[w], (options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0, d_D.p);
+        TSKB_CK_LAUNCH();
+        TSKB_CK(cudaMemcpyAsync(result + (size_t) w * ns * ns, d_D.p, (size_t) ns * ns * sizeof(double),
+            cudaMemcpyDeviceToHost, s));
+    }
+    TSKB_CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // namespace tskb

@@ -19,6 +19,7 @@ std::string &last_error_string() {
 }
 
 Plan::~Plan() {
+    if (decode_aux != nullptr) free_decode_aux(decode_aux);
     arena.destroy();
     for (auto &e : ev) {
         if (e) cudaEventDestroy(e);
@@ -835,6 +836,8 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
                 if (alleles.size() > 65000) throw (int) TSKB_ERR_UNSUPPORTED;
             }
             aoff[j + 1] = aoff[j] + (uint32_t) alleles.size();
+            P.max_alleles_per_site = std::max<uint32_t>(P.max_alleles_per_site, (uint32_t) alleles.size());
+            P.max_muts_per_site = std::max<uint32_t>(P.max_muts_per_site, moff[j + 1] - moff[j]);
         }
         P.total_alleles = aoff[S];
         P.h_site_pos.assign(t->site_position, t->site_position + S);

@@ -52,6 +52,9 @@
 
 namespace tskb {
 
+struct DecodeAux;  // matrix.cu: parent-major edge CSR, built on the first decode
+void free_decode_aux(DecodeAux *a);
+
 constexpr uint32_t WTILE = 256;                      // addends per warp tile of the propagation
 constexpr uint32_t PROP_WARPS = 8;                   // warp tiles per CTA tile
 constexpr uint32_t PROP_TILE = WTILE * PROP_WARPS;   // addends per CTA tile
@@ -75,6 +78,7 @@ struct Plan {
     uint32_t num_samples = 0;
     uint32_t site_lo = 0, site_hi = 0;  // sites inside the range
     uint64_t total_alleles = 0;
+    uint32_t max_muts_per_site = 0, max_alleles_per_site = 1;
 
     // host copies needed for argument validation
     std::vector<int32_t> sample_index_map;  // node -> sample index or -1 (trees.c:404-453)
@@ -123,6 +127,7 @@ struct Plan {
     mutable std::mutex mu;
     mutable Arena arena;
     mutable tskb_stats_t stats = {};
+    mutable DecodeAux *decode_aux = nullptr;
     mutable unsigned long long *stats_trace = nullptr;  // TSKB_TRACE: per-tile timeline of the last call (arena)
     size_t scan_temp_bytes = 0;
 
@@ -163,5 +168,11 @@ enum StatId {
 int run_sample_count_stat(const Plan *plan, const StatSpec &spec);
 int run_trees_at(const Plan *plan, uint64_t nq, const double *positions, const int32_t *tracked,
     uint64_t num_tracked, int32_t *out_parent, int32_t *out_count);
+
+// matrix.cu
+int run_genotype_matrix(const Plan *plan, const int32_t *samples, uint64_t num_samples,
+    uint32_t options, int8_t *genotypes);
+int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *sizes, const int32_t *sets,
+    uint64_t num_windows, const double *windows, uint32_t options, double *result);
 
 }  // namespace tskb
