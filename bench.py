@@ -110,6 +110,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named phase's kernel, from the
+    committed ncu --set full capture (profiles/traffic.json, written by tools/ncu_summary.py)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    key = {"propagate": "k_propagate<1>", "summary": "k_branch_summary<0, 1, 1>"}.get(kernel)
+    return d.get(key)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -312,7 +323,7 @@ def run_ours(args):
         K_avg = 1.5  # one sweep with K = 1 state column and one with K = 2
         b_branch = 28 + dbar * (12 + 8 * K_avg)
         per_step_ms = phase_ms / args.steps
-        names = ["weights", "propagate", "summary", "scan", "windows", "d2h"]
+        names = ["weights", "propagate", "summary", "finalize", "idle", "d2h"]
         dom = int(np.argmax(per_step_ms))
         # algorithmic share of the dominant phase (DESIGN.md "Roofline accounting")
         share = {"propagate": 20 + dbar * (4 + 8 * K_avg), "summary": 8 + dbar * 8}.get(
@@ -347,7 +358,8 @@ def run_ours(args):
                     (world * stage_s + wall_e2e / args.steps)},
             "gpu_launches": int(launches[0]),
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(names[dom]),
+                         "traffic_note": "bytes per launch of the K=1 instantiation, ncu capture under profiles/",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_edge_diff": share,
                          "whole_sweep": {"achieved": sweep_achieved, "frac": sweep_achieved / peak,

@@ -45,6 +45,9 @@ def launches(path, out):
         f.write(f"{'TOTAL':50s} {sum(a[0] for a in agg.values()):8d} {tot:12.1f}\n")
 
 
+TRAFFIC = {}
+
+
 def full(path, out):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -55,6 +58,13 @@ def full(path, out):
             d = dict(zip(hdr, r))
             u = dict(zip(hdr, units))
             f.write("\n== " + d.get("Kernel Name", "?")[:150] + "\n")
+            try:
+                scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                tot = sum(float(d[k].replace(",", "")) * scale[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                nm = d["Kernel Name"].split("(")[0].replace("void ", "").replace("unnamed>::", "").replace("tskb::<", "").strip()
+                TRAFFIC.setdefault(nm, tot)
+            except (KeyError, ValueError):
+                pass
             for k in KEYS:
                 if k in d:
                     f.write(f"{k:70s} {d[k]:>18s} {u[k]}\n")
@@ -76,6 +86,13 @@ if __name__ == "__main__":
         launches(os.path.join(src, "launches.csv"), f"profiles/{tag}_launches.txt")
     for rep in glob.glob(os.path.join(src, "*.ncu-rep")):
         full(rep, f"profiles/{tag}_{os.path.basename(rep)[:-8]}.txt")
+    if TRAFFIC:
+        import json
+        p = "profiles/traffic.json"
+        cur = json.load(open(p)) if os.path.exists(p) else {}
+        cur.update(TRAFFIC)
+        cur["_source"] = tag
+        json.dump(cur, open(p, "w"), indent=1, sort_keys=True)
     for nm in ("bench.json", "bench_ref.json", "pytest_gpu.log", "smi.txt"):
         p = os.path.join(src, nm)
         if os.path.exists(p):
