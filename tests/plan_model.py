@@ -118,11 +118,39 @@ def build(t, a=None, b=None):
     kc = inv[eoff]
     ev_src = pidx[kc] - (ev_sign < 0)
     P = ends_total + N
-    # every level of the addend stream is padded with ZERO entries to whole tiles of 2048
+    # first iteration of a walk: +-state[child]; later iterations: the difference of the node
+    # visited just before, carried by the walk that owns that node's first entry at the breakpoint
+    i_k = em_ev[sorted_e]
+    e_k = sorted_e
+    first_visit = e_k == eoff[i_k] + 1 if Ve else np.zeros(0, dtype=bool)
+    later = ~em_child[e_k] & ~first_visit
+    kv = inv[np.maximum(e_k - 1, 0)]
+    owns = later & ((kv == 0) | end[np.maximum(kv - 1, 0)])
+    word = np.full(Ve, 3 << 30, dtype=np.uint32)
+    word[first_visit] = ((ev_sign[i_k[first_visit]] < 0).astype(np.uint32) << np.uint32(30)) \
+        | ev_src[i_k[first_visit]].astype(np.uint32)
+    word[owns] = np.uint32(2 << 30) | pidx[kv[owns]].astype(np.uint32)
+    # entries without a term leave the stream; a piece ends at its last term, or keeps one
+    # term-less END entry when it has none
+    real = word != np.uint32(3 << 30)
+    q = endscan[:-1]
+    kend = np.nonzero(end)[0]
+    realscan = np.cumsum(real)
+    if Ve:
+        before = np.where(q > 0, realscan[kend[np.maximum(q - 1, 0)]], 0)
+        nreal = realscan[kend[q]] - before
+        is_last = np.arange(Ve) == kend[q]
+        keep = real | ((nreal == 0) & is_last)
+        newend = (real & (realscan == realscan[kend[q]])) | (~real & keep)
+    else:
+        keep = newend = np.zeros(0, dtype=bool)
+    keepscan = np.concatenate([[0], np.cumsum(keep)]).astype(np.int64)
+    noffc = keepscan[noff]
+    # every level of the addend stream is padded with term-less entries to whole tiles of 2048
     nlevels = int(level.max()) + 1 if N else 1
     lvl_sorted = level[rank_node]
     lro = np.searchsorted(lvl_sorted, np.arange(nlevels + 1))
-    ub = noff[lro] + lro
+    ub = noffc[lro] + lro
     TILE = 2048
     ntile = -(-(ub[1:] - ub[:-1]) // TILE)
     level_begin = np.concatenate([[0], np.cumsum(ntile) * TILE]).astype(np.uint32)
@@ -134,24 +162,12 @@ def build(t, a=None, b=None):
     pc_bl = np.zeros(P_pad)
     pad_k = padoff[level[rank_node[sorted_key]]] if Ve else np.zeros(0, dtype=np.int64)
     pad_r = padoff[lvl_sorted] if N else np.zeros(0, dtype=np.int64)
-    i_k = em_ev[sorted_e]
-    # first iteration of a walk: +-state[child]; later iterations: the difference of the node
-    # visited just before, carried by the walk that owns that node's first entry at the breakpoint
-    e_k = sorted_e
-    first_visit = e_k == eoff[i_k] + 1
-    later = ~em_child[e_k] & ~first_visit
-    kv = inv[np.maximum(e_k - 1, 0)]
-    owns = later & ((kv == 0) | end[np.maximum(kv - 1, 0)])
-    word = np.full(Ve, 3 << 30, dtype=np.uint32)
-    word[first_visit] = ((ev_sign[i_k[first_visit]] < 0).astype(np.uint32) << np.uint32(30)) \
-        | ev_src[i_k[first_visit]].astype(np.uint32)
-    word[owns] = np.uint32(2 << 30) | pidx[kv[owns]].astype(np.uint32)
-    word = word | np.where(end, np.uint32(1 << 29), np.uint32(0))
-    ad[np.arange(Ve) + sorted_key + 1 + pad_k] = word
+    wordf = word | np.where(newend, np.uint32(1 << 29), np.uint32(0))
+    ad[(keepscan[:-1] + sorted_key + 1 + pad_k)[keep]] = wordf[keep]
     pc_x[pidx[end]] = ev_pos[i_k[end]]
     pc_bl[pidx[end]] = em_blv[sorted_e[end]]
     poff = np.concatenate([endscan[noff[:N]] if N else [], [ends_total]]).astype(np.int64) + np.arange(N + 1)
-    ad[noff[:N] + np.arange(N) + pad_r] = np.uint32((3 << 30) | (1 << 29) | (1 << 28)) | rank_node.astype(np.uint32)
+    ad[noffc[:N] + np.arange(N) + pad_r] = np.uint32((3 << 30) | (1 << 29) | (1 << 28)) | rank_node.astype(np.uint32)
     pc_x[poff[:N]] = -1.0
     # sites
     mut_src = np.zeros(t.num_mutations, dtype=np.int32)

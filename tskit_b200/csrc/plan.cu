@@ -284,17 +284,17 @@ __global__ void k_fill_u32(uint32_t *out, size_t n, uint32_t v) {
     if (i < n) out[i] = v;
 }
 
-__global__ void k_fill_entries(const uint32_t *sorted_e, const uint32_t *sorted_key,
+// Word (without the END bit) of every entry in node-major order k, and the piece arrays.
+__global__ void k_entry_words(const uint32_t *sorted_e, const uint32_t *sorted_key,
     const uint32_t *em_ev, const uint32_t *endflag, const uint32_t *endscan, const uint32_t *voff,
     const int8_t *ev_sign, const double *ev_sbl, const double *ev_pos, const uint32_t *ev_src,
-    const double *vis_bl, const uint32_t *inv, uint32_t Ve, const int32_t *rank_node,
-    const uint32_t *level, const uint32_t *padoff, uint32_t *ad, double *pc_x, double *pc_bl) {
+    const double *vis_bl, const uint32_t *inv, uint32_t Ve, uint32_t *wk, uint32_t *real,
+    uint32_t *kend, double *pc_x, double *pc_bl) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Ve) return;
     uint32_t e = sorted_e[k], r = sorted_key[k], i = em_ev[e];
     const uint32_t e0 = voff[i] + i;  // CHILD entry of the event; its visits follow bottom-up
     bool child = e == e0;
-    uint32_t end = endflag[k];
     uint32_t word = AD_ZERO_WORD;
     if (e == e0 + 1) {
         // first iteration of the walk: the edge's parent gains / loses state[child]
@@ -310,8 +310,9 @@ __global__ void k_fill_entries(const uint32_t *sorted_e, const uint32_t *sorted_
             word = (AD_DIFF << AD_KIND_SHIFT) | (endscan[kv] + rv + 1);
         }
     }
-    ad[k + r + 1 + padoff[level[rank_node[r]]]] = word | (end ? AD_END : 0u);
-    if (end) {
+    wk[k] = word;
+    real[k] = word != AD_ZERO_WORD;
+    if (endflag[k]) {
         // the piece's branch length is the one in force after the LAST diff of the breakpoint
         // that touches the node: its own insertion if there is one (trees.c:1455-1457), 0
         // after its removal (trees.c:1432), else the branch across x
@@ -319,12 +320,53 @@ __global__ void k_fill_entries(const uint32_t *sorted_e, const uint32_t *sorted_
         uint32_t p = endscan[k] + r + 1;
         pc_x[p] = ev_pos[i];
         pc_bl[p] = bl;
+        kend[endscan[k]] = k;
     }
 }
 
-__global__ void k_fill_init(const uint32_t *noff, const uint32_t *endscan, uint32_t Ve,
-    uint32_t ends_total, const int32_t *rank_node, const uint32_t *level, const uint32_t *padoff,
-    uint32_t N, uint32_t *ad, double *pc_x, double *pc_bl, uint32_t *poff) {
+// Entries that carry no term are dropped from the addend stream; a piece keeps its last term as
+// its END, or a single term-less END entry when it has none (the node is only the child of the
+// diff: new branch length, same state).
+__global__ void k_entry_keep(const uint32_t *real, const uint32_t *realscan, const uint32_t *endscan,
+    const uint32_t *kend, uint32_t Ve, uint32_t *keep, uint32_t *newend) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Ve) return;
+    uint32_t q = endscan[k];           // piece (in k order) of this entry
+    uint32_t ke = kend[q];             // its last entry
+    uint32_t before = q > 0 ? realscan[kend[q - 1]] : 0;
+    uint32_t nreal = realscan[ke] - before;
+    uint32_t kp = 0, ne = 0;
+    if (real[k]) {
+        kp = 1;
+        ne = realscan[k] == realscan[ke];  // last term of the piece
+    } else if (nreal == 0 && k == ke) {
+        kp = 1;
+        ne = 1;
+    }
+    keep[k] = kp;
+    newend[k] = ne;
+}
+
+__global__ void k_compact_offsets(const uint32_t *noff, const uint32_t *keepscan, uint32_t N,
+    uint32_t *noffc) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= N) noffc[r] = keepscan[noff[r]];
+}
+
+__global__ void k_scatter_entries(const uint32_t *sorted_key, const uint32_t *wk,
+    const uint32_t *keep, const uint32_t *newend, const uint32_t *keepscan, const uint32_t *endscan,
+    uint32_t Ve, const int32_t *rank_node, const uint32_t *level, const uint32_t *padoff,
+    uint32_t *ad, uint32_t *kpiece) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Ve || !keep[k]) return;
+    uint32_t r = sorted_key[k], kk = keepscan[k];
+    ad[kk + r + 1 + padoff[level[rank_node[r]]]] = wk[k] | (newend[k] ? AD_END : 0u);
+    kpiece[kk] = endscan[k];
+}
+
+__global__ void k_fill_init(const uint32_t *noff, const uint32_t *noffc, const uint32_t *endscan,
+    uint32_t Ve, uint32_t ends_total, const int32_t *rank_node, const uint32_t *level,
+    const uint32_t *padoff, uint32_t N, uint32_t *ad, double *pc_x, double *pc_bl, uint32_t *poff) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r > N) return;
     uint32_t k = r < N ? noff[r] : Ve;
@@ -332,7 +374,7 @@ __global__ void k_fill_init(const uint32_t *noff, const uint32_t *endscan, uint3
     poff[r] = p;
     if (r < N) {
         int32_t u = rank_node[r];
-        ad[k + r + padoff[level[u]]] = AD_INIT_WORD | (uint32_t) u;
+        ad[noffc[r] + r + padoff[level[u]]] = AD_INIT_WORD | (uint32_t) u;
         pc_x[p] = -1.0;
         pc_bl[p] = 0.0;
     }
@@ -341,30 +383,30 @@ __global__ void k_fill_init(const uint32_t *noff, const uint32_t *endscan, uint3
 // piece the first addend of each warp tile belongs to (= pieces that end before it).
 // tile_u0 / tile_uend: unpadded addend index of the CTA tile's start / of its level's end.
 __global__ void k_tile_piece(const uint32_t *tile_u0, const uint32_t *tile_uend, uint32_t nwt,
-    const uint32_t *noff, const uint32_t *endscan, const uint32_t *poff, uint32_t N, uint32_t Ve,
+    const uint32_t *noffc, const uint32_t *kpiece, const uint32_t *poff, uint32_t N, uint32_t Kc,
     uint32_t ends_total, uint32_t *wt_piece) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nwt) return;
     uint32_t tile = g / PROP_WARPS, wq = g % PROP_WARPS;
     uint32_t s = tile_u0[tile] + wq * WTILE;
     if (s > tile_uend[tile]) s = tile_uend[tile];
-    if (s >= Ve + N) {
+    if (s >= Kc + N) {
         wt_piece[g] = ends_total + N;
         return;
     }
-    // rank r of the node whose list contains addend s: last r with noff[r] + r <= s
+    // rank r of the node whose list contains addend s: last r with noffc[r] + r <= s
     uint32_t lo = 0, hi = N;
     while (lo < hi) {
         uint32_t mid = lo + ((hi - lo) >> 1);
-        if (noff[mid] + mid <= s) lo = mid + 1; else hi = mid;
+        if (noffc[mid] + mid <= s) lo = mid + 1; else hi = mid;
     }
     uint32_t r = lo - 1;
     uint32_t piece;
-    if (s == noff[r] + r) {
+    if (s == noffc[r] + r) {
         piece = poff[r];
     } else {
-        uint32_t k = s - r - 1;
-        piece = (k < Ve ? endscan[k] : ends_total) + r + 1;
+        uint32_t kk = s - r - 1;
+        piece = (kk < Kc ? kpiece[kk] : ends_total) + r + 1;
     }
     wt_piece[g] = piece;
 }
@@ -726,11 +768,53 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     if ((uint64_t) P.P >= AD_PAYLOAD || (uint64_t) N >= AD_PAYLOAD) {
         throw (int) TSKB_ERR_UNSUPPORTED;  // 29-bit piece indexes; shard the genome instead
     }
+    // ---- entry words, pieces, and the entries that stay in the addend stream
+    // pieces are streamed in whole tiles of 1024 by the summary kernel: pad with INIT markers
+    const size_t P_pad = ((size_t) P.P + 1023) / 1024 * 1024;
+    P.pc_x.alloc(P_pad); P.pc_bl.alloc(P_pad);
+    TSKB_CK(cudaMemsetAsync(P.pc_bl.p, 0, P_pad * sizeof(double), s));
+    k_fill_f64<<<grid_for(P_pad - P.P + 1, TB), TB, 0, s>>>(P.pc_x.p + P.P, P_pad - P.P, -1.0);
+    TSKB_CK_LAUNCH();
+    DevArray<uint32_t> wk, keep, newend, keepscan, noffc;
+    wk.alloc(Ve); keep.alloc(Ve + 1); newend.alloc(Ve); keepscan.alloc(Ve + 1); noffc.alloc(N + 1);
+    uint32_t Kc = 0;
+    {
+        DevArray<uint32_t> ev_src, real, realscan, kend;
+        ev_src.alloc(nev); real.alloc(Ve); realscan.alloc(Ve); kend.alloc(ends_total + 1);
+        if (nev) {
+            k_event_src<<<grid_for(nev, TB), TB, 0, s>>>(P.voff.p, P.ev_sign.p, inv.p,
+                sorted_key.p, endscan.p, nev, ev_src.p);
+            TSKB_CK_LAUNCH();
+        }
+        TSKB_CK(cudaMemsetAsync(keep.p, 0, (Ve + 1) * sizeof(uint32_t), s));
+        if (Ve) {
+            k_entry_words<<<grid_for(Ve, TB), TB, 0, s>>>(sorted_e.p, sorted_key.p, em_ev.p,
+                endflag.p, endscan.p, P.voff.p, P.ev_sign.p, ev_sbl.p, P.ev_pos.p, ev_src.p,
+                vis_bl.p, inv.p, Ve, wk.p, real.p, kend.p, P.pc_x.p, P.pc_bl.p);
+            TSKB_CK_LAUNCH();
+            size_t bytes = 0;
+            TSKB_CK(cub::DeviceScan::InclusiveSum(nullptr, bytes, real.p, realscan.p, Ve, s));
+            TSKB_CK(cub::DeviceScan::InclusiveSum(tmp.need(bytes), bytes, real.p, realscan.p, Ve, s));
+            k_entry_keep<<<grid_for(Ve, TB), TB, 0, s>>>(real.p, realscan.p, endscan.p, kend.p, Ve,
+                keep.p, newend.p);
+            TSKB_CK_LAUNCH();
+        }
+        size_t bytes = 0;
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, keep.p, keepscan.p, Ve + 1, s));
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(tmp.need(bytes), bytes, keep.p, keepscan.p, Ve + 1, s));
+        TSKB_CK(cudaMemcpyAsync(&Kc, keepscan.p + Ve, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        k_compact_offsets<<<grid_for(N + 1, TB), TB, 0, s>>>(noff.p, keepscan.p, N, noffc.p);
+        TSKB_CK_LAUNCH();
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
+    ev_sbl.release(); vis_bl.release(); inv.release(); em_ev.release(); sorted_e.release();
+    ev_bp.release(); endflag.release();
+
     // ---- level layout of the addend stream: every level padded to whole CTA tiles
     DevArray<uint32_t> padoff, tile_u0, tile_uend;
     {
         std::vector<uint32_t> h_lro = lvl_rank_off.download(s);
-        std::vector<uint32_t> h_noff = noff.download(s);
+        std::vector<uint32_t> h_noff = noffc.download(s);
         std::vector<uint32_t> ub(P.nlevels + 1), h_pad(P.nlevels + 1), h_dep, h_u0, h_uend;
         P.level_begin.resize(P.nlevels + 1);
         uint64_t padded = 0;
@@ -759,44 +843,32 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         tile_uend.upload(h_uend.data(), h_uend.size(), s);
         TSKB_CK(cudaStreamSynchronize(s));
     }
-    // pieces are streamed in whole tiles of 1024 by the summary kernel: pad with INIT markers
-    const size_t P_pad = ((size_t) P.P + 1023) / 1024 * 1024;
-    P.ad.alloc(P.Na); P.pc_x.alloc(P_pad); P.pc_bl.alloc(P_pad);
-    TSKB_CK(cudaMemsetAsync(P.pc_bl.p, 0, P_pad * sizeof(double), s));
-    k_fill_f64<<<grid_for(P_pad - P.P + 1, TB), TB, 0, s>>>(P.pc_x.p + P.P, P_pad - P.P, -1.0);
-    TSKB_CK_LAUNCH();
+    P.ad.alloc(P.Na);
     P.wt_piece.alloc((size_t) P.ntiles * PROP_WARPS);
     {
-        DevArray<uint32_t> ev_src;
-        ev_src.alloc(nev);
+        DevArray<uint32_t> kpiece;
+        kpiece.alloc(Kc + 1);
         if (P.Na) {
             k_fill_u32<<<grid_for(P.Na, TB), TB, 0, s>>>(P.ad.p, P.Na, AD_ZERO_WORD);
             TSKB_CK_LAUNCH();
         }
-        if (nev) {
-            k_event_src<<<grid_for(nev, TB), TB, 0, s>>>(P.voff.p, P.ev_sign.p, inv.p,
-                sorted_key.p, endscan.p, nev, ev_src.p);
-            TSKB_CK_LAUNCH();
-        }
         if (Ve) {
-            k_fill_entries<<<grid_for(Ve, TB), TB, 0, s>>>(sorted_e.p, sorted_key.p, em_ev.p,
-                endflag.p, endscan.p, P.voff.p, P.ev_sign.p, ev_sbl.p, P.ev_pos.p, ev_src.p,
-                vis_bl.p, inv.p, Ve, P.rank_node.p, P.level.p, padoff.p, P.ad.p, P.pc_x.p, P.pc_bl.p);
+            k_scatter_entries<<<grid_for(Ve, TB), TB, 0, s>>>(sorted_key.p, wk.p, keep.p, newend.p,
+                keepscan.p, endscan.p, Ve, P.rank_node.p, P.level.p, padoff.p, P.ad.p, kpiece.p);
             TSKB_CK_LAUNCH();
         }
-        k_fill_init<<<grid_for(N + 1, TB), TB, 0, s>>>(noff.p, endscan.p, Ve, ends_total,
+        k_fill_init<<<grid_for(N + 1, TB), TB, 0, s>>>(noff.p, noffc.p, endscan.p, Ve, ends_total,
             P.rank_node.p, P.level.p, padoff.p, N, P.ad.p, P.pc_x.p, P.pc_bl.p, poff.p);
         TSKB_CK_LAUNCH();
         if (P.ntiles) {
             const uint32_t nwt = P.ntiles * PROP_WARPS;
-            k_tile_piece<<<grid_for(nwt, TB), TB, 0, s>>>(tile_u0.p, tile_uend.p, nwt, noff.p,
-                endscan.p, poff.p, N, Ve, ends_total, P.wt_piece.p);
+            k_tile_piece<<<grid_for(nwt, TB), TB, 0, s>>>(tile_u0.p, tile_uend.p, nwt, noffc.p,
+                kpiece.p, poff.p, N, Kc, ends_total, P.wt_piece.p);
             TSKB_CK_LAUNCH();
         }
         TSKB_CK(cudaStreamSynchronize(s));
     }
-    ev_sbl.release(); vis_bl.release(); inv.release(); em_ev.release(); sorted_e.release();
-    ev_bp.release(); endflag.release();
+    wk.release(); keep.release(); newend.release(); keepscan.release(); noffc.release();
     sorted_key.release(); endscan.release();
 
     // ---- sites and mutations: allele strings -> small integer codes on the host
