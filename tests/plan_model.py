@@ -118,57 +118,69 @@ def build(t, a=None, b=None):
     kc = inv[eoff]
     ev_src = pidx[kc] - (ev_sign < 0)
     P = ends_total + N
-    # first iteration of a walk: +-state[child]; later iterations: the difference of the node
-    # visited just before, carried by the walk that owns that node's first entry at the breakpoint
     i_k = em_ev[sorted_e]
-    e_k = sorted_e
-    first_visit = e_k == eoff[i_k] + 1 if Ve else np.zeros(0, dtype=bool)
-    later = ~em_child[e_k] & ~first_visit
-    kv = inv[np.maximum(e_k - 1, 0)]
-    owns = later & ((kv == 0) | end[np.maximum(kv - 1, 0)])
-    word = np.full(Ve, 3 << 30, dtype=np.uint32)
-    word[first_visit] = ((ev_sign[i_k[first_visit]] < 0).astype(np.uint32) << np.uint32(30)) \
-        | ev_src[i_k[first_visit]].astype(np.uint32)
-    word[owns] = np.uint32(2 << 30) | pidx[kv[owns]].astype(np.uint32)
-    # entries without a term leave the stream; a piece ends at its last term, or keeps one
-    # term-less END entry when it has none
-    real = word != np.uint32(3 << 30)
-    q = endscan[:-1]
-    kend = np.nonzero(end)[0]
-    realscan = np.cumsum(real)
-    if Ve:
-        before = np.where(q > 0, realscan[kend[np.maximum(q - 1, 0)]], 0)
-        nreal = realscan[kend[q]] - before
-        is_last = np.arange(Ve) == kend[q]
-        keep = real | ((nreal == 0) & is_last)
-        newend = (real & (realscan == realscan[kend[q]])) | (~real & keep)
-    else:
-        keep = newend = np.zeros(0, dtype=bool)
-    keepscan = np.concatenate([[0], np.cumsum(keep)]).astype(np.int64)
-    noffc = keepscan[noff]
-    # every level of the addend stream is padded with term-less entries to whole tiles of 2048
-    nlevels = int(level.max()) + 1 if N else 1
-    lvl_sorted = level[rank_node]
-    lro = np.searchsorted(lvl_sorted, np.arange(nlevels + 1))
-    ub = noffc[lro] + lro
-    TILE = 2048
-    ntile = -(-(ub[1:] - ub[:-1]) // TILE)
-    level_begin = np.concatenate([[0], np.cumsum(ntile) * TILE]).astype(np.uint32)
-    padoff = level_begin[:-1].astype(np.int64) - ub[:-1]
-    Na = int(level_begin[-1])
-    ad = np.full(Na, 3 << 30, dtype=np.uint32)
     P_pad = -(-P // 1024) * 1024
     pc_x = np.full(P_pad, -1.0)
     pc_bl = np.zeros(P_pad)
-    pad_k = padoff[level[rank_node[sorted_key]]] if Ve else np.zeros(0, dtype=np.int64)
-    pad_r = padoff[lvl_sorted] if N else np.zeros(0, dtype=np.int64)
-    wordf = word | np.where(newend, np.uint32(1 << 29), np.uint32(0))
-    ad[(keepscan[:-1] + sorted_key + 1 + pad_k)[keep]] = wordf[keep]
     pc_x[pidx[end]] = ev_pos[i_k[end]]
     pc_bl[pidx[end]] = em_blv[sorted_e[end]]
+    piece_rank = np.zeros(P, dtype=np.int64)
+    piece_rank[pidx[end]] = sorted_key[end]
     poff = np.concatenate([endscan[noff[:N]] if N else [], [ends_total]]).astype(np.int64) + np.arange(N + 1)
-    ad[noffc[:N] + np.arange(N) + pad_r] = np.uint32((3 << 30) | (1 << 29) | (1 << 28)) | rank_node.astype(np.uint32)
-    pc_x[poff[:N]] = -1.0
+    piece_rank[poff[:N]] = np.arange(N)
+    # references of every real piece: own INIT piece if the node is a sample, then the children
+    # in the tree right of the piece's breakpoint (parent-major edge list scanned backwards)
+    is_sample = (t.nodes_flags & 1).astype(bool)
+    pm = np.lexsort((ec, el, ep))  # (parent, left, child)
+    pm_off = np.searchsorted(ep[pm], np.arange(N + 1))
+    pl, pr, pch = el[pm], er[pm], ec[pm]
+    ref_lists = [[] for _ in range(P)]
+    for p in range(P):
+        x = pc_x[p]
+        if x < 0:
+            continue
+        r = piece_rank[p]
+        u = rank_node[r]
+        lst = ref_lists[p]
+        if is_sample[u]:
+            lst.append(int(poff[r]))
+        lo, hi = pm_off[u], pm_off[u + 1]
+        k = np.searchsorted(pl[lo:hi], x, side="right")
+        for j in range(lo + k - 1, lo - 1, -1):
+            if pr[j] > x:
+                rc = rank[pch[j]]
+                q0, q1 = poff[rc], poff[rc + 1]
+                lst.append(int(q0 + np.searchsorted(pc_x[q0:q1], x, side="right") - 1))
+    height = np.zeros(P, dtype=np.int64)
+    changed = True
+    while changed:
+        changed = False
+        for p in range(P):
+            h = 0
+            for q in ref_lists[p]:
+                if pc_x[q] >= 0:
+                    h = max(h, height[q] + 1)
+            if h != height[p]:
+                height[p] = h
+                changed = True
+    real = np.nonzero(pc_x[:P] >= 0)[0]
+    order = real[np.argsort(height[real], kind="stable")]
+    nheights = int(height.max()) + 1 if P else 1
+    TILE = 1024
+    hs = height[order]
+    begin = np.searchsorted(hs, np.arange(nheights + 1))
+    ntile = -(-(begin[1:] - begin[:-1]) // TILE)
+    level_begin = np.concatenate([[0], np.cumsum(ntile) * TILE]).astype(np.uint32)
+    npp = int(level_begin[-1])
+    pp_piece = np.full(npp, 0xFFFFFFFF, dtype=np.uint32)
+    cnts = np.zeros(npp + 1, dtype=np.int64)
+    pos = level_begin[:-1].astype(np.int64)[hs] + (np.arange(len(order)) - begin[hs])
+    pp_piece[pos] = order
+    cnts[pos] = [len(ref_lists[p]) for p in order]
+    pp_off = np.concatenate([[0], np.cumsum(cnts[:-1])]).astype(np.uint32)
+    refs = np.zeros(int(cnts.sum()), dtype=np.uint32)
+    for j, p in zip(pos, order):
+        refs[pp_off[j]:pp_off[j] + len(ref_lists[p])] = ref_lists[p]
     # sites
     mut_src = np.zeros(t.num_mutations, dtype=np.int32)
     for m in range(t.num_mutations):
@@ -177,15 +189,16 @@ def build(t, a=None, b=None):
         lo, hi = poff[r], poff[r + 1]
         mut_src[m] = lo + np.searchsorted(pc_x[lo:hi], x, side="right") - 1
     return dict(ev_pos=ev_pos, ev_child=ev_child.astype(np.int32), ev_sign=ev_sign, voff=voff,
-                ad=ad, pc_x=pc_x, pc_bl=pc_bl, level=level, rank_node=rank_node,
-                level_begin=level_begin, mut_src=mut_src)
+                pp_piece=pp_piece, pp_off=pp_off, refs=refs, pc_x=pc_x, pc_bl=pc_bl, level=level,
+                rank_node=rank_node, level_begin=level_begin, mut_src=mut_src, poff=poff)
 
 
 DTYPES = dict(ev_pos=np.float64, ev_child=np.int32, ev_sign=np.int8, voff=np.uint32,
-              ad=np.uint32, pc_x=np.float64, pc_bl=np.float64, level=np.uint32,
-              rank_node=np.int32, level_begin=np.uint32, mut_src=np.int32)
-ORDER = ["ev_pos", "ev_child", "ev_sign", "voff", "level", "rank_node", "level_begin", "ad",
-         "pc_x", "pc_bl", "mut_src"]
+              pp_piece=np.uint32, pp_off=np.uint32, refs=np.uint32, pc_x=np.float64,
+              pc_bl=np.float64, level=np.uint32, rank_node=np.int32, level_begin=np.uint32,
+              mut_src=np.int32)
+ORDER = ["ev_pos", "ev_child", "ev_sign", "voff", "level", "rank_node", "pc_x", "pc_bl",
+         "level_begin", "pp_piece", "pp_off", "refs", "mut_src"]
 
 
 def compare(ll, t, a=None, b=None):
@@ -194,6 +207,8 @@ def compare(ll, t, a=None, b=None):
     bad = []
     for name in ORDER:
         got = ll.debug_array(name, DTYPES[name])
+        if name == "refs":
+            got = got[:len(m[name])]  # the device array is over-allocated
         if got.shape != m[name].shape or not np.array_equal(got, m[name]):
             bad.append(name)
     return bad

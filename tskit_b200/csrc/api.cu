@@ -334,12 +334,13 @@ int64_t tskb_treeseq_debug_array(const tskb_treeseq_t *self, const char *name, v
     std::string s(name);
 #define ARR(NAME, A) if (s == NAME) { src = P.A.p; n = P.A.n; esize = sizeof(*P.A.p); }
     ARR("ev_pos", ev_pos) ARR("ev_child", ev_child) ARR("ev_sign", ev_sign) ARR("voff", voff)
-    ARR("ad", ad) ARR("pc_x", pc_x) ARR("pc_bl", pc_bl) ARR("tile_dep", tile_dep) ARR("wt_piece", wt_piece)
+    ARR("pp_piece", pp_piece) ARR("pp_off", pp_off) ARR("refs", refs) ARR("pc_x", pc_x) ARR("pc_bl", pc_bl)
+    ARR("tile_dep", tile_dep)
     ARR("level", level) ARR("rank_node", rank_node) ARR("mut_src", mut_src)
     ARR("mut_allele", mut_allele) ARR("mut_alt", mut_alt)
 #undef ARR
     if (s == "trace" && P.stats_trace != nullptr) {
-        src = P.stats_trace; n = (size_t) P.ntiles * 6; esize = sizeof(unsigned long long);
+        src = P.stats_trace; n = (size_t) P.ntiles * 4; esize = sizeof(unsigned long long);
     }
     if (s == "level_begin") {
         src = P.level_begin.data(); n = P.level_begin.size(); esize = sizeof(uint32_t); host = true;

@@ -23,57 +23,9 @@
 
 namespace tskb {
 
-struct DecodeAux {
-    // parent-major CSR of all edges, sorted by (parent, left); pmax = running max of right
-    // within the parent's list, which bounds the backward scan of an interval-stabbing query
-    DevArray<uint32_t> off;  // [N + 1]
-    DevArray<double> left, right, pmax;
-    DevArray<int32_t> child;
-};
-
-void free_decode_aux(DecodeAux *a) { delete a; }
-
 namespace {
 
 constexpr int TB = 256;
-
-__device__ inline uint64_t ordered_bits64(double x) {
-    uint64_t b = (uint64_t) __double_as_longlong(x);
-    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-}
-
-__global__ void k_csr_child_keys(const uint32_t *coff, uint32_t N, const double *csr_left, uint32_t E,
-    uint64_t *key, uint32_t *val, int32_t *child_of) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= E) return;
-    key[j] = ordered_bits64(csr_left[j]);
-    val[j] = j;
-    child_of[j] = (int32_t) (upper_bound_dev(coff, N + 1, j) - 1);
-}
-
-__global__ void k_gather_u32(const uint32_t *perm, const int32_t *src, uint32_t n, uint32_t *out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (uint32_t) src[perm[i]];
-}
-
-__global__ void k_pm_gather(const uint32_t *perm, uint32_t E, const double *csr_left,
-    const double *csr_right, const int32_t *child_of, double *left, double *right, int32_t *child) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= E) return;
-    uint32_t j = perm[i];
-    left[i] = csr_left[j];
-    right[i] = csr_right[j];
-    child[i] = child_of[j];
-}
-
-__global__ void k_lower_offsets(const uint32_t *sorted_keys, uint32_t n, uint32_t nq, uint32_t *out) {
-    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq) out[q] = lower_bound_dev(sorted_keys, n, q);
-}
-
-struct MaxOp {
-    __device__ __forceinline__ double operator()(double a, double b) const { return a > b ? a : b; }
-};
 
 __global__ void k_fill_i32(int32_t *out, size_t n, int32_t v) {
     size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,49 +260,10 @@ struct Temp {
     }
 };
 
-const DecodeAux &ensure_aux(const Plan &P) {
-    if (P.decode_aux != nullptr) return *P.decode_aux;
-    cudaStream_t s = P.stream;
-    const uint32_t N = (uint32_t) P.N, E = (uint32_t) P.E;
-    std::unique_ptr<DecodeAux> A(new DecodeAux());
-    A->off.alloc(N + 1); A->left.alloc(E); A->right.alloc(E); A->pmax.alloc(E); A->child.alloc(E);
-    Temp tmp;
-    DevArray<uint64_t> k64, k64o;
-    DevArray<uint32_t> v, vo, pk, pko, perm;
-    DevArray<int32_t> child_of;
-    k64.alloc(E); k64o.alloc(E); v.alloc(E); vo.alloc(E); pk.alloc(E); pko.alloc(E); perm.alloc(E);
-    child_of.alloc(E);
-    if (E) {
-        k_csr_child_keys<<<grid_for(E, TB), TB, 0, s>>>(P.coff.p, N, P.csr_left.p, E, k64.p, v.p, child_of.p);
-        TSKB_CK_LAUNCH();
-        size_t bytes = 0;
-        TSKB_CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k64.p, k64o.p, v.p, vo.p, E, 0, 64, s));
-        TSKB_CK(cub::DeviceRadixSort::SortPairs(tmp.need(bytes), bytes, k64.p, k64o.p, v.p, vo.p, E, 0, 64, s));
-        k_gather_u32<<<grid_for(E, TB), TB, 0, s>>>(vo.p, P.csr_parent.p, E, pk.p);
-        TSKB_CK_LAUNCH();
-        int bits = (int) std::max(1u, ceil_log2(N));
-        TSKB_CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, pk.p, pko.p, vo.p, perm.p, E, 0, bits, s));
-        TSKB_CK(cub::DeviceRadixSort::SortPairs(tmp.need(bytes), bytes, pk.p, pko.p, vo.p, perm.p, E, 0, bits, s));
-        k_pm_gather<<<grid_for(E, TB), TB, 0, s>>>(perm.p, E, P.csr_left.p, P.csr_right.p, child_of.p,
-            A->left.p, A->right.p, A->child.p);
-        TSKB_CK_LAUNCH();
-        TSKB_CK(cub::DeviceScan::InclusiveScanByKey(nullptr, bytes, pko.p, A->right.p, A->pmax.p, MaxOp(), E,
-            ::cuda::std::equal_to<>(), s));
-        TSKB_CK(cub::DeviceScan::InclusiveScanByKey(tmp.need(bytes), bytes, pko.p, A->right.p, A->pmax.p,
-            MaxOp(), E, ::cuda::std::equal_to<>(), s));
-    }
-    k_lower_offsets<<<grid_for(N + 1, TB), TB, 0, s>>>(pko.p, E, N + 1, A->off.p);
-    TSKB_CK_LAUNCH();
-    TSKB_CK(cudaStreamSynchronize(s));
-    P.decode_aux = A.release();
-    return *P.decode_aux;
-}
-
 // genotypes of sites [s0, s1) for the listed samples into G (caller-zeroed), any strides
 void decode_sites(const Plan &P, const int32_t *d_samples, uint32_t n, uint32_t s0, uint32_t s1,
     uint32_t options, int8_t *G, size_t stride_site, size_t stride_sample) {
     if (s1 <= s0 || n == 0) return;
-    const DecodeAux &A = ensure_aux(P);
     cudaStream_t s = P.stream;
     const uint32_t N = (uint32_t) P.N;
     DevArray<int32_t> col;
@@ -360,7 +273,7 @@ void decode_sites(const Plan &P, const int32_t *d_samples, uint32_t n, uint32_t 
     TSKB_CK_LAUNCH();
     if (!(options & TSKB_ISOLATED_NOT_MISSING)) {
         k_mark_isolated<<<grid_for(n, 128), 128, 0, s>>>(d_samples, n, P.coff.p, P.csr_left.p,
-            P.csr_right.p, A.off.p, A.left.p, A.right.p, P.site_pos.p, s0, s1, P.L, G, stride_site,
+            P.csr_right.p, P.pm_off.p, P.pm_left.p, P.pm_right.p, P.site_pos.p, s0, s1, P.L, G, stride_site,
             stride_sample);
         TSKB_CK_LAUNCH();
     }
@@ -389,8 +302,8 @@ void decode_sites(const Plan &P, const int32_t *d_samples, uint32_t n, uint32_t 
             while (h_cnt > 0) {
                 TSKB_CK(cudaMemsetAsync(cnt.p + 1, 0, sizeof(uint32_t), s));
                 k_expand<<<grid_for(h_cnt, TB), TB, 0, s>>>(cur, h_cnt, r, s0, P.site_pos.p,
-                    P.site_moff.p, P.mut_allele.p, col.p, A.off.p, A.left.p, A.right.p, A.pmax.p,
-                    A.child.p, G, stride_site, stride_sample, nxt, cap, cnt.p + 1, ovf.p);
+                    P.site_moff.p, P.mut_allele.p, col.p, P.pm_off.p, P.pm_left.p, P.pm_right.p, P.pm_pmax.p,
+                    P.pm_child.p, G, stride_site, stride_sample, nxt, cap, cnt.p + 1, ovf.p);
                 TSKB_CK_LAUNCH();
                 int h_ovf = 0;
                 TSKB_CK(cudaMemcpyAsync(&h_cnt, cnt.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

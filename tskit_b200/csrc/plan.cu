@@ -19,7 +19,6 @@ std::string &last_error_string() {
 }
 
 Plan::~Plan() {
-    if (decode_aux != nullptr) free_decode_aux(decode_aux);
     arena.destroy();
     for (auto &e : ev) {
         if (e) cudaEventDestroy(e);
@@ -30,8 +29,9 @@ Plan::~Plan() {
 uint64_t Plan::device_bytes() const {
     return time.bytes() + d_samples.bytes() + coff.bytes() + csr_left.bytes() + csr_right.bytes()
            + csr_parent.bytes() + ev_pos.bytes() + ev_child.bytes() + ev_sign.bytes()
-           + voff.bytes() + ad.bytes() + pc_x.bytes() + pc_bl.bytes() + tile_dep.bytes() + wt_piece.bytes()
-           + rank_node.bytes() + level.bytes() + site_pos.bytes() + site_moff.bytes()
+           + voff.bytes() + pp_piece.bytes() + pp_off.bytes() + refs.bytes() + pc_x.bytes()
+           + pc_bl.bytes() + tile_dep.bytes() + d_poff.bytes() + pm_off.bytes() + pm_left.bytes()
+           + pm_right.bytes() + pm_pmax.bytes() + pm_child.bytes() + rank_node.bytes() + level.bytes() + site_pos.bytes() + site_moff.bytes()
            + site_aoff.bytes() + mut_node.bytes() + mut_src.bytes() + mut_allele.bytes()
            + mut_alt.bytes();
 }
@@ -261,154 +261,164 @@ __global__ void k_entry_ends(const uint32_t *sorted_e, const uint32_t *sorted_ke
     endflag[k] = end;
 }
 
-// src of event i: the piece holding state[child] when the reference reads it
-// (trees.c:1436/1462): the child's piece at this breakpoint for an insertion (state right of
-// x), the one before it for a removal (state left of x).  The child's own CHILD entry of
-// event i lies in its piece at this breakpoint.
-__global__ void k_event_src(const uint32_t *voff, const int8_t *ev_sign, const uint32_t *inv,
-    const uint32_t *sorted_key, const uint32_t *endscan, uint32_t nev, uint32_t *ev_src) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nev) return;
-    uint32_t k = inv[voff[i] + i];
-    uint32_t piece = endscan[k] + sorted_key[k] + 1;
-    ev_src[i] = ev_sign[i] < 0 ? piece - 1 : piece;
-}
-
 __global__ void k_fill_f64(double *out, size_t n, double v) {
     size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = v;
 }
-
 __global__ void k_fill_u32(uint32_t *out, size_t n, uint32_t v) {
     size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = v;
 }
 
-// Word (without the END bit) of every entry in node-major order k, and the piece arrays.
-__global__ void k_entry_words(const uint32_t *sorted_e, const uint32_t *sorted_key,
+// Pieces: one per (node, breakpoint) group of node-major entries, after the node's INIT piece.
+__global__ void k_piece_fill(const uint32_t *sorted_e, const uint32_t *sorted_key,
     const uint32_t *em_ev, const uint32_t *endflag, const uint32_t *endscan, const uint32_t *voff,
-    const int8_t *ev_sign, const double *ev_sbl, const double *ev_pos, const uint32_t *ev_src,
-    const double *vis_bl, const uint32_t *inv, uint32_t Ve, uint32_t *wk, uint32_t *real,
-    uint32_t *kend, double *pc_x, double *pc_bl) {
+    const int8_t *ev_sign, const double *ev_sbl, const double *ev_pos, const double *vis_bl,
+    uint32_t Ve, double *pc_x, double *pc_bl, uint32_t *piece_rank) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= Ve) return;
+    if (k >= Ve || !endflag[k]) return;
     uint32_t e = sorted_e[k], r = sorted_key[k], i = em_ev[e];
-    const uint32_t e0 = voff[i] + i;  // CHILD entry of the event; its visits follow bottom-up
-    bool child = e == e0;
-    uint32_t word = AD_ZERO_WORD;
-    if (e == e0 + 1) {
-        // first iteration of the walk: the edge's parent gains / loses state[child]
-        word = ((ev_sign[i] < 0 ? AD_NEG : AD_POS) << AD_KIND_SHIFT) | ev_src[i];
-    } else if (!child) {
-        // later iteration: the walk came up through v = the node visited just before.  All
-        // walks of this breakpoint through v add up to state(v, t) - state(v, t-); the one
-        // owning v's first entry at this breakpoint carries that term, the others nothing.
-        uint32_t kv = inv[e - 1];
-        bool first = kv == 0 || endflag[kv - 1] != 0;
-        if (first) {
-            uint32_t rv = sorted_key[kv];
-            word = (AD_DIFF << AD_KIND_SHIFT) | (endscan[kv] + rv + 1);
-        }
-    }
-    wk[k] = word;
-    real[k] = word != AD_ZERO_WORD;
-    if (endflag[k]) {
-        // the piece's branch length is the one in force after the LAST diff of the breakpoint
-        // that touches the node: its own insertion if there is one (trees.c:1455-1457), 0
-        // after its removal (trees.c:1432), else the branch across x
-        double bl = child ? (ev_sign[i] > 0 ? ev_sbl[i] : 0.0) : vis_bl[e - i - 1];
-        uint32_t p = endscan[k] + r + 1;
-        pc_x[p] = ev_pos[i];
-        pc_bl[p] = bl;
-        kend[endscan[k]] = k;
-    }
+    bool child = e == voff[i] + i;
+    // the piece's branch length is the one in force after the LAST diff of the breakpoint that
+    // touches the node: its own insertion if there is one (trees.c:1455-1457), 0 after its
+    // removal (trees.c:1432), else the branch across x
+    double bl = child ? (ev_sign[i] > 0 ? ev_sbl[i] : 0.0) : vis_bl[e - i - 1];
+    uint32_t p = endscan[k] + r + 1;
+    pc_x[p] = ev_pos[i];
+    pc_bl[p] = bl;
+    piece_rank[p] = r;
 }
 
-// Entries that carry no term are dropped from the addend stream; a piece keeps its last term as
-// its END, or a single term-less END entry when it has none (the node is only the child of the
-// diff: new branch length, same state).
-__global__ void k_entry_keep(const uint32_t *real, const uint32_t *realscan, const uint32_t *endscan,
-    const uint32_t *kend, uint32_t Ve, uint32_t *keep, uint32_t *newend) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= Ve) return;
-    uint32_t q = endscan[k];           // piece (in k order) of this entry
-    uint32_t ke = kend[q];             // its last entry
-    uint32_t before = q > 0 ? realscan[kend[q - 1]] : 0;
-    uint32_t nreal = realscan[ke] - before;
-    uint32_t kp = 0, ne = 0;
-    if (real[k]) {
-        kp = 1;
-        ne = realscan[k] == realscan[ke];  // last term of the piece
-    } else if (nreal == 0 && k == ke) {
-        kp = 1;
-        ne = 1;
-    }
-    keep[k] = kp;
-    newend[k] = ne;
-}
-
-__global__ void k_compact_offsets(const uint32_t *noff, const uint32_t *keepscan, uint32_t N,
-    uint32_t *noffc) {
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r <= N) noffc[r] = keepscan[noff[r]];
-}
-
-__global__ void k_scatter_entries(const uint32_t *sorted_key, const uint32_t *wk,
-    const uint32_t *keep, const uint32_t *newend, const uint32_t *keepscan, const uint32_t *endscan,
-    uint32_t Ve, const int32_t *rank_node, const uint32_t *level, const uint32_t *padoff,
-    uint32_t *ad, uint32_t *kpiece) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= Ve || !keep[k]) return;
-    uint32_t r = sorted_key[k], kk = keepscan[k];
-    ad[kk + r + 1 + padoff[level[rank_node[r]]]] = wk[k] | (newend[k] ? AD_END : 0u);
-    kpiece[kk] = endscan[k];
-}
-
-__global__ void k_fill_init(const uint32_t *noff, const uint32_t *noffc, const uint32_t *endscan,
-    uint32_t Ve, uint32_t ends_total, const int32_t *rank_node, const uint32_t *level,
-    const uint32_t *padoff, uint32_t N, uint32_t *ad, double *pc_x, double *pc_bl, uint32_t *poff) {
+__global__ void k_piece_init(const uint32_t *noff, const uint32_t *endscan, uint32_t Ve,
+    uint32_t ends_total, uint32_t N, double *pc_x, double *pc_bl, uint32_t *piece_rank,
+    uint32_t *poff) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r > N) return;
     uint32_t k = r < N ? noff[r] : Ve;
     uint32_t p = (k < Ve ? endscan[k] : ends_total) + r;
     poff[r] = p;
     if (r < N) {
-        int32_t u = rank_node[r];
-        ad[noffc[r] + r + padoff[level[u]]] = AD_INIT_WORD | (uint32_t) u;
         pc_x[p] = -1.0;
         pc_bl[p] = 0.0;
+        piece_rank[p] = r;
     }
 }
 
-// piece the first addend of each warp tile belongs to (= pieces that end before it).
-// tile_u0 / tile_uend: unpadded addend index of the CTA tile's start / of its level's end.
-__global__ void k_tile_piece(const uint32_t *tile_u0, const uint32_t *tile_uend, uint32_t nwt,
-    const uint32_t *noffc, const uint32_t *kpiece, const uint32_t *poff, uint32_t N, uint32_t Kc,
-    uint32_t ends_total, uint32_t *wt_piece) {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nwt) return;
-    uint32_t tile = g / PROP_WARPS, wq = g % PROP_WARPS;
-    uint32_t s = tile_u0[tile] + wq * WTILE;
-    if (s > tile_uend[tile]) s = tile_uend[tile];
-    if (s >= Kc + N) {
-        wt_piece[g] = ends_total + N;
-        return;
+// ---- parent-major CSR: edges sorted by (parent, left), running max of right per parent
+__global__ void k_pm_keys(const uint32_t *coff, uint32_t N, const double *csr_left, uint32_t E,
+    uint64_t *key, uint32_t *val, int32_t *child_of) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= E) return;
+    key[j] = ordered_bits(csr_left[j]);
+    val[j] = j;
+    child_of[j] = (int32_t) (upper_bound_dev(coff, N + 1, j) - 1);
+}
+__global__ void k_gather_parent(const uint32_t *perm, const int32_t *src, uint32_t n, uint32_t *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t) src[perm[i]];
+}
+__global__ void k_pm_gather(const uint32_t *perm, uint32_t E, const double *csr_left,
+    const double *csr_right, const int32_t *child_of, double *left, double *right, int32_t *child) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E) return;
+    uint32_t j = perm[i];
+    left[i] = csr_left[j];
+    right[i] = csr_right[j];
+    child[i] = child_of[j];
+}
+struct MaxOp {
+    __device__ __forceinline__ double operator()(double a, double b) const { return a > b ? a : b; }
+};
+
+// Children of a piece's node in the tree right of the piece's breakpoint (edges with
+// left <= x < right), as the pieces holding their state there; plus the node's own INIT piece
+// when it is a sample (its own weight, trees.c:1406-1415).
+template <bool FILL>
+__global__ void k_piece_children(uint32_t P, const double *pc_x, const uint32_t *piece_rank,
+    const int32_t *rank_node, const uint32_t *rank, const uint32_t *node_is_sample,
+    const uint32_t *poff, const uint32_t *pm_off, const double *pm_left, const double *pm_right,
+    const double *pm_pmax, const int32_t *pm_child, uint32_t *cnt, const uint32_t *ch_off,
+    uint32_t *refs) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const double x = pc_x[p];
+    uint32_t c = 0;
+    if (x >= 0.0) {  // INIT pieces have no references: they are written from the weights
+        const uint32_t r = piece_rank[p];
+        const int32_t u = rank_node[r];
+        uint32_t base = FILL ? ch_off[p] : 0;
+        if (node_is_sample[u]) {
+            if (FILL) refs[base] = poff[r];
+            c++;
+        }
+        uint32_t lo = pm_off[u], hi = pm_off[u + 1];
+        uint32_t k = upper_bound_dev(pm_left + lo, hi - lo, x);  // edges with left <= x
+        for (uint32_t j = lo + k; j-- > lo;) {
+            if (!(pm_pmax[j] > x)) break;  // nothing further left reaches x
+            if (pm_right[j] > x) {
+                if (FILL) {
+                    uint32_t rc = rank[pm_child[j]];
+                    uint32_t q0 = poff[rc], n = poff[rc + 1] - q0;
+                    // the child's last piece starting at or before x (its INIT piece starts at -1)
+                    refs[base + c] = q0 + upper_bound_dev(pc_x + q0, n, x) - 1;
+                }
+                c++;
+            }
+        }
     }
-    // rank r of the node whose list contains addend s: last r with noffc[r] + r <= s
-    uint32_t lo = 0, hi = N;
-    while (lo < hi) {
-        uint32_t mid = lo + ((hi - lo) >> 1);
-        if (noffc[mid] + mid <= s) lo = mid + 1; else hi = mid;
+    if (!FILL) cnt[p] = c;
+}
+
+// height of a piece = 1 + max height of the pieces it references, INIT pieces not counted (they
+// are available before the propagation starts); relaxed to a fixed point
+__global__ void k_relax_height(uint32_t P, const uint32_t *ch_off, const uint32_t *refs,
+    const double *pc_x, uint32_t *height, int *changed) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    uint32_t h = 0;
+    for (uint32_t i = ch_off[p]; i < ch_off[p + 1]; i++) {
+        uint32_t q = refs[i];
+        if (pc_x[q] >= 0.0) h = max(h, height[q] + 1);
     }
-    uint32_t r = lo - 1;
-    uint32_t piece;
-    if (s == noffc[r] + r) {
-        piece = poff[r];
-    } else {
-        uint32_t kk = s - r - 1;
-        piece = (kk < Kc ? kpiece[kk] : ends_total) + r + 1;
+    if (h != height[p]) {
+        height[p] = h;
+        *changed = 1;
     }
-    wt_piece[g] = piece;
+}
+
+__global__ void k_height_keys(uint32_t P, const double *pc_x, const uint32_t *height, uint32_t *key,
+    uint32_t *val, uint32_t init_key) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    key[p] = pc_x[p] >= 0.0 ? height[p] : init_key;  // INIT pieces sort last and are dropped
+    val[p] = p;
+}
+
+// processing order: pieces by (height, piece id); every height padded to whole tiles
+__global__ void k_order_fill(const uint32_t *sorted_piece, const uint32_t *sorted_h, uint32_t nreal,
+    const uint32_t *lvl_sorted_begin, const uint32_t *lvl_padded_begin, const uint32_t *cnt,
+    uint32_t *pp_piece, uint32_t *pp_cnt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nreal) return;
+    uint32_t h = sorted_h[i], p = sorted_piece[i];
+    uint32_t j = lvl_padded_begin[h] + (i - lvl_sorted_begin[h]);
+    pp_piece[j] = p;
+    pp_cnt[j] = cnt[p];
+}
+
+__global__ void k_refs_reorder(uint32_t npp, const uint32_t *pp_piece, const uint32_t *pp_off,
+    const uint32_t *ch_off, const uint32_t *refs, uint32_t *refs2) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npp) return;
+    uint32_t p = pp_piece[j];
+    if (p == 0xffffffffu) return;
+    uint32_t o = pp_off[j], n = pp_off[j + 1] - o, s0 = ch_off[p];
+    for (uint32_t i = 0; i < n; i++) refs2[o + i] = refs[s0 + i];
+}
+
+__global__ void k_flag_samples(const int32_t *samples, uint32_t n, uint32_t *flag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[samples[i]] = 1;
 }
 
 // state[mutation.node] at the site's tree = the node's last piece starting at or before the
@@ -722,7 +732,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
 
     // ---- node-major order of the entries (CHILD entries + visits), pieces, addends
     const uint32_t Ve = V + nev;
-    DevArray<uint32_t> sorted_e, sorted_key, em_ev, noff, endflag, endscan, inv, poff;
+    DevArray<uint32_t> sorted_e, sorted_key, em_ev, noff, endflag, endscan, inv, poff;  // poff -> P.d_poff
     sorted_e.alloc(Ve); sorted_key.alloc(Ve); em_ev.alloc(Ve); noff.alloc(N + 1);
     endflag.alloc(Ve + 1); endscan.alloc(Ve + 1); inv.alloc(Ve); poff.alloc(N + 1);
     {
@@ -765,111 +775,177 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK(cudaStreamSynchronize(s));
     }
     P.P = ends_total + N;
-    if ((uint64_t) P.P >= AD_PAYLOAD || (uint64_t) N >= AD_PAYLOAD) {
-        throw (int) TSKB_ERR_UNSUPPORTED;  // 29-bit piece indexes; shard the genome instead
+    if ((uint64_t) ends_total + N >= 0xfffffff0ull) {
+        throw (int) TSKB_ERR_UNSUPPORTED;  // 32-bit piece indexes; shard the genome instead
     }
-    // ---- entry words, pieces, and the entries that stay in the addend stream
+    // ---- pieces
     // pieces are streamed in whole tiles of 1024 by the summary kernel: pad with INIT markers
     const size_t P_pad = ((size_t) P.P + 1023) / 1024 * 1024;
     P.pc_x.alloc(P_pad); P.pc_bl.alloc(P_pad);
     TSKB_CK(cudaMemsetAsync(P.pc_bl.p, 0, P_pad * sizeof(double), s));
     k_fill_f64<<<grid_for(P_pad - P.P + 1, TB), TB, 0, s>>>(P.pc_x.p + P.P, P_pad - P.P, -1.0);
     TSKB_CK_LAUNCH();
-    DevArray<uint32_t> wk, keep, newend, keepscan, noffc;
-    wk.alloc(Ve); keep.alloc(Ve + 1); newend.alloc(Ve); keepscan.alloc(Ve + 1); noffc.alloc(N + 1);
-    uint32_t Kc = 0;
+    DevArray<uint32_t> piece_rank;
+    piece_rank.alloc(P.P);
+    if (Ve) {
+        k_piece_fill<<<grid_for(Ve, TB), TB, 0, s>>>(sorted_e.p, sorted_key.p, em_ev.p, endflag.p,
+            endscan.p, P.voff.p, P.ev_sign.p, ev_sbl.p, P.ev_pos.p, vis_bl.p, Ve, P.pc_x.p,
+            P.pc_bl.p, piece_rank.p);
+        TSKB_CK_LAUNCH();
+    }
+    k_piece_init<<<grid_for(N + 1, TB), TB, 0, s>>>(noff.p, endscan.p, Ve, ends_total, N, P.pc_x.p,
+        P.pc_bl.p, piece_rank.p, poff.p);
+    TSKB_CK_LAUNCH();
+    TSKB_CK(cudaStreamSynchronize(s));
+    ev_sbl.release(); vis_bl.release(); inv.release(); em_ev.release(); sorted_e.release();
+    ev_bp.release(); endflag.release(); sorted_key.release(); endscan.release(); noff.release();
+
+    // ---- parent-major edge CSR (children of a node at a position; also used by the decode)
+    P.pm_off.alloc(N + 1); P.pm_left.alloc(E); P.pm_right.alloc(E); P.pm_pmax.alloc(E);
+    P.pm_child.alloc(E);
     {
-        DevArray<uint32_t> ev_src, real, realscan, kend;
-        ev_src.alloc(nev); real.alloc(Ve); realscan.alloc(Ve); kend.alloc(ends_total + 1);
-        if (nev) {
-            k_event_src<<<grid_for(nev, TB), TB, 0, s>>>(P.voff.p, P.ev_sign.p, inv.p,
-                sorted_key.p, endscan.p, nev, ev_src.p);
+        DevArray<uint64_t> k64, k64o;
+        DevArray<uint32_t> v, vo, pk, pko, perm;
+        DevArray<int32_t> child_of;
+        k64.alloc(E); k64o.alloc(E); v.alloc(E); vo.alloc(E); pk.alloc(E); pko.alloc(E);
+        perm.alloc(E); child_of.alloc(E);
+        if (E) {
+            k_pm_keys<<<grid_for(E, TB), TB, 0, s>>>(P.coff.p, N, P.csr_left.p, E, k64.p, v.p,
+                child_of.p);
             TSKB_CK_LAUNCH();
-        }
-        TSKB_CK(cudaMemsetAsync(keep.p, 0, (Ve + 1) * sizeof(uint32_t), s));
-        if (Ve) {
-            k_entry_words<<<grid_for(Ve, TB), TB, 0, s>>>(sorted_e.p, sorted_key.p, em_ev.p,
-                endflag.p, endscan.p, P.voff.p, P.ev_sign.p, ev_sbl.p, P.ev_pos.p, ev_src.p,
-                vis_bl.p, inv.p, Ve, wk.p, real.p, kend.p, P.pc_x.p, P.pc_bl.p);
+            sort_pairs(tmp, k64.p, k64o.p, v.p, vo.p, E, 64, s);
+            k_gather_parent<<<grid_for(E, TB), TB, 0, s>>>(vo.p, P.csr_parent.p, E, pk.p);
+            TSKB_CK_LAUNCH();
+            sort_pairs(tmp, pk.p, pko.p, vo.p, perm.p, E, (int) std::max(1u, ceil_log2(N)), s);
+            k_pm_gather<<<grid_for(E, TB), TB, 0, s>>>(perm.p, E, P.csr_left.p, P.csr_right.p,
+                child_of.p, P.pm_left.p, P.pm_right.p, P.pm_child.p);
             TSKB_CK_LAUNCH();
             size_t bytes = 0;
-            TSKB_CK(cub::DeviceScan::InclusiveSum(nullptr, bytes, real.p, realscan.p, Ve, s));
-            TSKB_CK(cub::DeviceScan::InclusiveSum(tmp.need(bytes), bytes, real.p, realscan.p, Ve, s));
-            k_entry_keep<<<grid_for(Ve, TB), TB, 0, s>>>(real.p, realscan.p, endscan.p, kend.p, Ve,
-                keep.p, newend.p);
-            TSKB_CK_LAUNCH();
+            TSKB_CK(cub::DeviceScan::InclusiveScanByKey(nullptr, bytes, pko.p, P.pm_right.p,
+                P.pm_pmax.p, MaxOp(), E, ::cuda::std::equal_to<>(), s));
+            TSKB_CK(cub::DeviceScan::InclusiveScanByKey(tmp.need(bytes), bytes, pko.p, P.pm_right.p,
+                P.pm_pmax.p, MaxOp(), E, ::cuda::std::equal_to<>(), s));
         }
-        size_t bytes = 0;
-        TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, keep.p, keepscan.p, Ve + 1, s));
-        TSKB_CK(cub::DeviceScan::ExclusiveSum(tmp.need(bytes), bytes, keep.p, keepscan.p, Ve + 1, s));
-        TSKB_CK(cudaMemcpyAsync(&Kc, keepscan.p + Ve, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        k_compact_offsets<<<grid_for(N + 1, TB), TB, 0, s>>>(noff.p, keepscan.p, N, noffc.p);
+        k_offsets<<<grid_for(N + 1, TB), TB, 0, s>>>(pko.p, E, N + 1, P.pm_off.p);
         TSKB_CK_LAUNCH();
         TSKB_CK(cudaStreamSynchronize(s));
     }
-    ev_sbl.release(); vis_bl.release(); inv.release(); em_ev.release(); sorted_e.release();
-    ev_bp.release(); endflag.release();
 
-    // ---- level layout of the addend stream: every level padded to whole CTA tiles
-    DevArray<uint32_t> padoff, tile_u0, tile_uend;
+    // ---- references of every piece, heights, processing order
     {
-        std::vector<uint32_t> h_lro = lvl_rank_off.download(s);
-        std::vector<uint32_t> h_noff = noffc.download(s);
-        std::vector<uint32_t> ub(P.nlevels + 1), h_pad(P.nlevels + 1), h_dep, h_u0, h_uend;
-        P.level_begin.resize(P.nlevels + 1);
-        uint64_t padded = 0;
-        for (uint32_t l = 0; l <= P.nlevels; l++) {
-            ub[l] = h_noff[h_lro[l]] + h_lro[l];
+        const uint32_t Pn = P.P;
+        DevArray<uint32_t> is_sample, cnt, ch_off, refs, height;
+        is_sample.alloc(N); cnt.alloc((size_t) Pn + 1); ch_off.alloc((size_t) Pn + 1);
+        height.alloc(Pn);
+        TSKB_CK(cudaMemsetAsync(is_sample.p, 0, N * sizeof(uint32_t), s));
+        TSKB_CK(cudaMemsetAsync(cnt.p, 0, ((size_t) Pn + 1) * sizeof(uint32_t), s));
+        TSKB_CK(cudaMemsetAsync(height.p, 0, (size_t) Pn * sizeof(uint32_t), s));
+        if (P.num_samples) {
+            k_flag_samples<<<grid_for(P.num_samples, TB), TB, 0, s>>>(P.d_samples.p, P.num_samples,
+                is_sample.p);
+            TSKB_CK_LAUNCH();
         }
-        for (uint32_t l = 0; l < P.nlevels; l++) {
-            P.level_begin[l] = (uint32_t) padded;
-            h_pad[l] = (uint32_t) (padded - ub[l]);
-            const uint32_t dep = (uint32_t) h_dep.size();
-            for (uint32_t u = ub[l]; u < ub[l + 1]; u += PROP_TILE) {
-                h_dep.push_back(dep);
-                h_u0.push_back(u);
-                h_uend.push_back(ub[l + 1]);
+        k_piece_children<false><<<grid_for(Pn, TB), TB, 0, s>>>(Pn, P.pc_x.p, piece_rank.p,
+            P.rank_node.p, rank.p, is_sample.p, poff.p, P.pm_off.p, P.pm_left.p, P.pm_right.p,
+            P.pm_pmax.p, P.pm_child.p, cnt.p, nullptr, nullptr);
+        TSKB_CK_LAUNCH();
+        size_t bytes = 0;
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt.p, ch_off.p, (size_t) Pn + 1, s));
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(tmp.need(bytes), bytes, cnt.p, ch_off.p, (size_t) Pn + 1, s));
+        uint32_t nrefs = 0;
+        TSKB_CK(cudaMemcpyAsync(&nrefs, ch_off.p + Pn, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        TSKB_CK(cudaStreamSynchronize(s));
+        refs.alloc((size_t) nrefs + 1);
+        k_piece_children<true><<<grid_for(Pn, TB), TB, 0, s>>>(Pn, P.pc_x.p, piece_rank.p,
+            P.rank_node.p, rank.p, is_sample.p, poff.p, P.pm_off.p, P.pm_left.p, P.pm_right.p,
+            P.pm_pmax.p, P.pm_child.p, cnt.p, ch_off.p, refs.p);
+        TSKB_CK_LAUNCH();
+        {
+            DevArray<int> changed;
+            changed.alloc(1);
+            int h_changed = 1, rounds = 0;
+            while (h_changed) {
+                TSKB_CK(cudaMemsetAsync(changed.p, 0, sizeof(int), s));
+                for (int q = 0; q < 4; q++) {
+                    k_relax_height<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, ch_off.p, refs.p, P.pc_x.p,
+                        height.p, changed.p);
+                }
+                TSKB_CK_LAUNCH();
+                TSKB_CK(cudaMemcpyAsync(&h_changed, changed.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+                TSKB_CK(cudaStreamSynchronize(s));
+                if (++rounds > (1 << 20)) throw (int) TSKB_ERR_BAD_PARAM_VALUE;  // cyclic input
             }
+        }
+        uint32_t max_h = 0;
+        {
+            DevArray<uint32_t> mx;
+            mx.alloc(1);
+            if (Pn) {
+                TSKB_CK(cub::DeviceReduce::Max(nullptr, bytes, height.p, mx.p, Pn, s));
+                TSKB_CK(cub::DeviceReduce::Max(tmp.need(bytes), bytes, height.p, mx.p, Pn, s));
+                TSKB_CK(cudaMemcpyAsync(&max_h, mx.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+                TSKB_CK(cudaStreamSynchronize(s));
+            }
+        }
+        P.nheights = max_h + 1;
+        // sort pieces by height (stable: piece order within a height); INIT pieces last
+        DevArray<uint32_t> kin, kout, vin, vout, lvl_begin;
+        kin.alloc(Pn); kout.alloc(Pn); vin.alloc(Pn); vout.alloc(Pn); lvl_begin.alloc(P.nheights + 2);
+        if (Pn) {
+            k_height_keys<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, P.pc_x.p, height.p, kin.p, vin.p,
+                P.nheights);
+            TSKB_CK_LAUNCH();
+            sort_pairs(tmp, kin.p, kout.p, vin.p, vout.p, Pn,
+                (int) std::max(1u, ceil_log2(P.nheights + 2)), s);
+        }
+        k_offsets<<<grid_for(P.nheights + 2, TB), TB, 0, s>>>(kout.p, Pn, P.nheights + 2, lvl_begin.p);
+        TSKB_CK_LAUNCH();
+        std::vector<uint32_t> h_begin = lvl_begin.download(s);  // sorted offset of each height
+        const uint32_t nreal = h_begin[P.nheights];             // INIT pieces follow
+        std::vector<uint32_t> h_padded(P.nheights + 1), h_dep;
+        P.level_begin.assign(P.nheights + 1, 0);
+        uint64_t padded = 0;
+        for (uint32_t h = 0; h < P.nheights; h++) {
+            h_padded[h] = (uint32_t) padded;
+            P.level_begin[h] = (uint32_t) padded;
+            const uint32_t dep = (uint32_t) h_dep.size();
+            const uint32_t len = h_begin[h + 1] - h_begin[h];
+            for (uint32_t u = 0; u < len; u += PROP_TILE) h_dep.push_back(dep);
             padded = (uint64_t) h_dep.size() * PROP_TILE;
             if (padded >= 0xffffffffull) throw (int) TSKB_ERR_UNSUPPORTED;
         }
-        P.level_begin[P.nlevels] = (uint32_t) padded;
-        h_pad[P.nlevels] = 0;
-        P.Na = (uint32_t) padded;
+        h_padded[P.nheights] = (uint32_t) padded;
+        P.level_begin[P.nheights] = (uint32_t) padded;
+        P.npp = (uint32_t) padded;
         P.ntiles = (uint32_t) h_dep.size();
-        padoff.upload(h_pad.data(), h_pad.size(), s);
         P.tile_dep.upload(h_dep.data(), h_dep.size(), s);
-        tile_u0.upload(h_u0.data(), h_u0.size(), s);
-        tile_uend.upload(h_uend.data(), h_uend.size(), s);
-        TSKB_CK(cudaStreamSynchronize(s));
-    }
-    P.ad.alloc(P.Na);
-    P.wt_piece.alloc((size_t) P.ntiles * PROP_WARPS);
-    {
-        DevArray<uint32_t> kpiece;
-        kpiece.alloc(Kc + 1);
-        if (P.Na) {
-            k_fill_u32<<<grid_for(P.Na, TB), TB, 0, s>>>(P.ad.p, P.Na, AD_ZERO_WORD);
+        DevArray<uint32_t> d_padded, pp_cnt;
+        d_padded.upload(h_padded.data(), h_padded.size(), s);
+        P.pp_piece.alloc(P.npp); P.pp_off.alloc((size_t) P.npp + 1); pp_cnt.alloc((size_t) P.npp + 1);
+        TSKB_CK(cudaMemsetAsync(pp_cnt.p, 0, ((size_t) P.npp + 1) * sizeof(uint32_t), s));
+        if (P.npp) {
+            k_fill_u32<<<grid_for(P.npp, TB), TB, 0, s>>>(P.pp_piece.p, P.npp, 0xffffffffu);
             TSKB_CK_LAUNCH();
         }
-        if (Ve) {
-            k_scatter_entries<<<grid_for(Ve, TB), TB, 0, s>>>(sorted_key.p, wk.p, keep.p, newend.p,
-                keepscan.p, endscan.p, Ve, P.rank_node.p, P.level.p, padoff.p, P.ad.p, kpiece.p);
+        if (nreal) {
+            k_order_fill<<<grid_for(nreal, TB), TB, 0, s>>>(vout.p, kout.p, nreal, lvl_begin.p,
+                d_padded.p, cnt.p, P.pp_piece.p, pp_cnt.p);
             TSKB_CK_LAUNCH();
         }
-        k_fill_init<<<grid_for(N + 1, TB), TB, 0, s>>>(noff.p, noffc.p, endscan.p, Ve, ends_total,
-            P.rank_node.p, P.level.p, padoff.p, N, P.ad.p, P.pc_x.p, P.pc_bl.p, poff.p);
-        TSKB_CK_LAUNCH();
-        if (P.ntiles) {
-            const uint32_t nwt = P.ntiles * PROP_WARPS;
-            k_tile_piece<<<grid_for(nwt, TB), TB, 0, s>>>(tile_u0.p, tile_uend.p, nwt, noffc.p,
-                kpiece.p, poff.p, N, Kc, ends_total, P.wt_piece.p);
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, pp_cnt.p, P.pp_off.p, (size_t) P.npp + 1, s));
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(tmp.need(bytes), bytes, pp_cnt.p, P.pp_off.p,
+            (size_t) P.npp + 1, s));
+        P.nrefs = nrefs;
+        P.refs.alloc((size_t) nrefs + 16);
+        if (P.npp) {
+            k_refs_reorder<<<grid_for(P.npp, TB), TB, 0, s>>>(P.npp, P.pp_piece.p, P.pp_off.p,
+                ch_off.p, refs.p, P.refs.p);
             TSKB_CK_LAUNCH();
         }
         TSKB_CK(cudaStreamSynchronize(s));
     }
-    wk.release(); keep.release(); newend.release(); keepscan.release(); noffc.release();
-    sorted_key.release(); endscan.release();
+    P.d_poff = std::move(poff);
+
 
     // ---- sites and mutations: allele strings -> small integer codes on the host
     // (replaces the memcmp loops of get_allele_weights, trees.c:1557-1596)
@@ -926,7 +1002,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
             DevArray<int32_t> d_msite;
             d_msite.upload(t->mutation_site, Mu, s);
             k_mut_src<<<grid_for(Mu, TB), TB, 0, s>>>(d_msite.p, P.mut_node.p, Mu, P.site_pos.p,
-                rank.p, poff.p, P.pc_x.p, P.mut_src.p);
+                rank.p, P.d_poff.p, P.pc_x.p, P.mut_src.p);
             TSKB_CK_LAUNCH();
             TSKB_CK(cudaStreamSynchronize(s));
         }
@@ -936,7 +1012,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
 
     P.stats.num_events = nev;
     P.stats.num_visits = V;
-    P.stats.num_levels = P.nlevels;
+    P.stats.num_levels = P.nheights;
     P.stats.device_bytes = P.device_bytes();
     P.stats.stage_ms = std::chrono::duration<double, std::milli>(
         std::chrono::steady_clock::now() - t_start).count();

@@ -24,24 +24,17 @@
 //                    Branch statistics are sums over pieces of
 //                    branch_length * f(state) * |piece ^ window|; the reference's
 //                    running sum (trees.c:1339-1350) telescopes to exactly this;
-//   * addend       = one term of  state(u, t) = state(u, t-) + ...: for a diff at t whose
-//                    edge has parent u, +-state[child] (update_state, trees.c:1317-1327, first
-//                    iteration of the walk); for every child v of u across x that was itself
-//                    visited at t, state(v, t) - state(v, t-): the later iterations of all the
-//                    walks that reach u through v, summed.  Addends are listed node-major so
-//                    that a node's pieces are the running sum of its addend list ("ad"),
-//                    which starts with an INIT entry holding the node's own sample weight.
-//                    A parent reads its children's pieces in their own order, so the gathers
-//                    of the propagation walk sequentially through the piece array;
-//   * nodes are grouped into dependency levels (level[parent] > level[child]
-//                    over every edge): all lists of one level can be
-//                    prefix-summed in parallel once lower levels are done.
-//
-// Node-major order is (level, node id, event).  Entry encoding of ad[]:
-//   bits 31-30 kind: 0 +state[piece], 1 -state[piece], 2 state[piece] - state[piece - 1],
-//   3 no addend (with bit 28: INIT, payload = node id; without: the node is only the child of
-//   the diff, or the walk's contribution is already counted: new piece, no new term)
-//   bit 29: last addend of its piece;  bits 27-0: payload.
+//   * references   = state(u, t) is the node's own sample weight plus the states of its
+//                    children in the tree right of t: every piece lists the pieces that hold
+//                    those (the child's last piece starting at or before t, found at staging
+//                    time; the node's own INIT piece for its weight).  A piece is then just a
+//                    sum of a few earlier pieces -- no running state, no scan;
+//   * heights      = a piece's height is 1 + the largest height among the pieces it references
+//                    (its node's height in that tree).  Pieces of one height are independent
+//                    once the lower ones are done; there are as many dependent steps as the
+//                    tallest tree is high (39 for the C2 workload) instead of one per edge diff.
+//                    "pp" arrays list the pieces in processing order (height, piece id), every
+//                    height padded to whole tiles.
 #pragma once
 
 #include <mutex>
@@ -52,16 +45,8 @@
 
 namespace tskb {
 
-struct DecodeAux;  // matrix.cu: parent-major edge CSR, built on the first decode
-void free_decode_aux(DecodeAux *a);
-
-constexpr uint32_t WTILE = 256;                      // addends per warp tile of the propagation
-constexpr uint32_t PROP_WARPS = 8;                   // warp tiles per CTA tile
-constexpr uint32_t PROP_TILE = WTILE * PROP_WARPS;   // addends per CTA tile
-constexpr uint32_t AD_KIND_SHIFT = 30, AD_END = 1u << 29, AD_HEAD = 1u << 28, AD_PAYLOAD = AD_HEAD - 1;
-enum AdKind : uint32_t { AD_POS = 0, AD_NEG = 1, AD_DIFF = 2, AD_NONE = 3 };
-constexpr uint32_t AD_INIT_WORD = (AD_NONE << AD_KIND_SHIFT) | AD_HEAD | AD_END;  // | node id
-constexpr uint32_t AD_ZERO_WORD = AD_NONE << AD_KIND_SHIFT;
+constexpr uint32_t PROP_TILE = 1024;   // pieces per propagation tile
+constexpr uint32_t NO_PIECE = 0xffffffffu;  // padding entry of the processing order
 
 struct Plan {
     int device = 0;
@@ -83,7 +68,7 @@ struct Plan {
     // host copies needed for argument validation
     std::vector<int32_t> sample_index_map;  // node -> sample index or -1 (trees.c:404-453)
     std::vector<int32_t> samples;
-    std::vector<uint32_t> level_begin;  // (padded) ad offset of each level, size nlevels + 1
+    std::vector<uint32_t> level_begin;  // (padded) processing-order offset of each height
 
     // --- tables in HBM ---
     DevArray<double> time;            // [N]
@@ -97,20 +82,23 @@ struct Plan {
     DevArray<int32_t> ev_child;       // [nev]
     DevArray<int8_t> ev_sign;         // [nev] -1 removal, +1 insertion
     DevArray<uint32_t> voff;          // [nev + 1] visit offsets
-    // --- addend stream, node-major: V + nev + N entries, every level padded with ZERO
-    //     entries to a multiple of PROP_TILE so that tile t covers ad[t * PROP_TILE ...)
-    uint32_t Na = 0;
-    DevArray<uint32_t> ad;            // [Na] see encoding above
     // --- pieces, node-major: every node's INIT piece followed by one piece per touching breakpoint
     uint32_t P = 0;
     DevArray<double> pc_x;            // [P] left end of the piece (its breakpoint); -1 for INIT
     DevArray<double> pc_bl;           // [P] branch length above the node over the piece
-    // --- propagation tiles
-    uint32_t ntiles = 0;              // CTA tiles
-    DevArray<uint32_t> tile_dep;      // [ntiles] first tile of the tile's level = number of tiles
+    DevArray<uint32_t> d_poff;        // [N + 1] first (INIT) piece of each node rank
+    // --- processing order of the propagation: real pieces by (height, piece id)
+    uint32_t nheights = 0, npp = 0, nrefs = 0, ntiles = 0;
+    DevArray<uint32_t> pp_piece;      // [npp] piece to compute (NO_PIECE: padding)
+    DevArray<uint32_t> pp_off;        // [npp + 1] offsets into refs
+    DevArray<uint32_t> refs;          // [nrefs] pieces whose states add up to the piece's state
+    DevArray<uint32_t> tile_dep;      // [ntiles] first tile of the tile's height = number of tiles
                                       //  that must be complete before its gathers
-    DevArray<uint32_t> wt_piece;      // [ntiles * PROP_WARPS] piece the first addend of each warp
-                                      //  tile belongs to
+    // --- parent-major edge CSR, sorted by (parent, left); pmax = running max of right within the
+    //     parent's list, which bounds the backward scan of an interval-stabbing query
+    DevArray<uint32_t> pm_off;        // [N + 1]
+    DevArray<double> pm_left, pm_right, pm_pmax;
+    DevArray<int32_t> pm_child;
     DevArray<int32_t> rank_node;      // [N] rank -> node id (nodes sorted by (level, id))
     DevArray<uint32_t> level;         // [N]
     // --- sites ---
@@ -127,7 +115,6 @@ struct Plan {
     mutable std::mutex mu;
     mutable Arena arena;
     mutable tskb_stats_t stats = {};
-    mutable DecodeAux *decode_aux = nullptr;
     mutable unsigned long long *stats_trace = nullptr;  // TSKB_TRACE: per-tile timeline of the last call (arena)
     size_t scan_temp_bytes = 0;
 

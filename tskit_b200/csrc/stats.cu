@@ -173,53 +173,15 @@ __global__ void k_set_weights(const int32_t *sets, const uint32_t *set_off, uint
 }
 
 // ---------------------------------------------------------------- phase 1
-// state[u] over every piece = running sum over u's node-major addend list, whose first
-// (INIT) entry is u's own sample weight (trees.c:1406-1415) and whose other addends are
-// +-state[child of the diff] (update_state, trees.c:1317-1327).
-//
-// One launch covers every level.  Tiles are claimed in order through a ticket, so a tile only
-// ever waits on tiles claimed earlier, which are resident: (a) on the completion counter, until
-// every tile of the lower levels has published its states, then (b) within the level, by
-// decoupled look-back, on the carry of a node list that began in an earlier tile.
-// (value, head, ends) triples combine as
-//   a (+) b = b.head ? (b.value, 1, a.ends + b.ends) : (a.value + b.value, a.head, a.ends + b.ends).
-
-template <int KP>
-struct SegVal {
-    IVec<KP> v;
-    int head;
-    int ends;
-};
-template <int KP>
-struct SegOp {
-    __device__ __forceinline__ SegVal<KP> operator()(const SegVal<KP> &a, const SegVal<KP> &b) const {
-        SegVal<KP> r;
-        if (b.head) {
-            r.v = b.v;
-            r.head = 1;
-        } else {
-            r.v = a.v + b.v;
-            r.head = a.head;
-        }
-        r.ends = a.ends + b.ends;
-        return r;
-    }
-};
-
-// look-back descriptor of one warp tile: status 0 = empty, 1 = aggregate ready, 2 = prefix ready.
-// One state column packs (value, head, status) into a single 64-bit word so that publishing is
-// one store; wider states publish value, fence, then status.
-template <int KP>
-struct WDesc {
-    int agg[KP + 1];     // value, head
-    int prefix[KP + 1];
-    int status;
-    int pad[(KP + 1) % 2 == 0 ? 1 : 2];
-};
-template <>
-struct WDesc<1> {
-    unsigned long long word;  // bits 0-31 value, bit 32 head, bits 33-34 status
-};
+// state[u] over every piece (what update_state, trees.c:1317-1327, maintains incrementally):
+// a piece's state is the sum of the states of the pieces it references -- its children in the
+// tree right of its breakpoint, plus its own INIT piece (the sample weight, trees.c:1406-1415).
+// Pieces are processed by height; one cooperative launch of co-resident persistent CTAs covers
+// every height.  CTA b takes tiles b, b + G, ...; a tile loads its references, then waits on
+// the completion counter until every tile of the lower heights has published its states
+// (red.release / ld.acquire at gpu scope), gathers, sums and stores.  Every CTA processes its
+// tiles in increasing order and a tile only waits on lower-numbered tiles, so the lowest
+// unfinished tile can always run: no deadlock.  Integer sums: exact in any order.
 
 template <int KP>
 __device__ __forceinline__ IVec<KP> state_load(const IVec<KP> *p) {
@@ -241,257 +203,98 @@ __device__ __forceinline__ IVec<KP> state_load(const IVec<KP> *p) {
     return r;
 }
 
-constexpr int PROP_TB = 32 * PROP_WARPS;
-constexpr int PW_IPT = WTILE / 32;
-constexpr uint32_t SPIN_LIMIT = 1u << 22;  // ~seconds; a legitimate wait is < the kernel's own run time
-
-template <int KP>
-__device__ __forceinline__ SegVal<KP> seg_shfl_up(const SegVal<KP> &x, int delta) {
-    SegVal<KP> r;
-#pragma unroll
-    for (int c = 0; c < KP; c++) r.v.v[c] = __shfl_up_sync(0xffffffffu, x.v.v[c], delta);
-    r.head = __shfl_up_sync(0xffffffffu, x.head, delta);
-    r.ends = __shfl_up_sync(0xffffffffu, x.ends, delta);
-    return r;
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-
-template <int KP>
-__device__ __forceinline__ void desc_publish(WDesc<KP> *d, const SegVal<KP> &x, int status) {
-    if constexpr (KP == 1) {
-        unsigned long long wd = (unsigned long long) (uint32_t) x.v.v[0]
-                                | ((unsigned long long) (x.head ? 1 : 0) << 32)
-                                | ((unsigned long long) status << 33);
-        *(volatile unsigned long long *) &d->word = wd;
-    } else {
-        int *q = status == 1 ? d->agg : d->prefix;
-#pragma unroll
-        for (int c = 0; c < KP; c++) __stcg(q + c, x.v.v[c]);
-        __stcg(q + KP, x.head);
-        __threadfence();
-        *(volatile int *) &d->status = status;
-    }
+__device__ __forceinline__ void red_release_add(uint32_t *p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-
-// returns the status seen (0: nothing published yet); fills x from the matching slot
-template <int KP>
-__device__ __forceinline__ int desc_peek(WDesc<KP> *d, SegVal<KP> &x) {
-    x.ends = 0;
-    if constexpr (KP == 1) {
-        unsigned long long wd = *(volatile unsigned long long *) &d->word;
-        x.v.v[0] = (int32_t) (uint32_t) wd;
-        x.head = (int) ((wd >> 32) & 1);
-        return (int) ((wd >> 33) & 3);
-    } else {
-        int st = *(volatile int *) &d->status;
-        if (st == 0) return 0;
-        __threadfence();
-        const int *q = st == 2 ? d->prefix : d->agg;
-#pragma unroll
-        for (int c = 0; c < KP; c++) x.v.v[c] = __ldcg(q + c);
-        x.head = __ldcg(q + KP);
-        return st;
-    }
-}
-
-// transpose buffers: index i of a 256-entry warp tile lives at i + i / 32, which makes both the
-// striped (q * 32 + lane) and the blocked (lane * 8 + q) access pattern bank-conflict free
-constexpr int WBUF = WTILE + WTILE / 32;
 __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// optional per-tile timeline (TSKB_TRACE=1): 6 timestamps per CTA tile
-#define TRACE(slot) do { if (trace != nullptr && threadIdx.x == 0) trace[(size_t) tile * 6 + (slot)] = gtime(); } while (0)
-__device__ __forceinline__ int padi(int i) { return i + (i >> 5); }
+// optional per-tile timeline (TSKB_TRACE=1): 4 timestamps per tile
+#define TRACE(slot) do { if (trace != nullptr && threadIdx.x == 0) trace[(size_t) tile * 4 + (slot)] = gtime(); } while (0)
 
-template <int KP>
-constexpr size_t propagate_smem() {
-    // per warp: transpose buffers for values and words + two stages of prefetched addend words
-    return (size_t) PROP_WARPS * (WBUF * (sizeof(IVec<KP>) + sizeof(uint32_t)) + 2 * WTILE * sizeof(uint32_t));
-}
+constexpr int PROP_TB = 256;
+constexpr int PROP_IPT = PROP_TILE / PROP_TB;
+constexpr int PROP_PRE = 3;  // references fetched before the wait; more are rare (multifurcations)
+constexpr uint32_t SPIN_LIMIT = 1u << 22;  // ~seconds; a legitimate wait is < the kernel's own run time
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    unsigned sa = (unsigned) __cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
-// Persistent, co-resident CTAs (cooperative launch): CTA b processes tiles b, b + G, b + 2G, ...
-// and prefetches the next one's addend words into shared memory while it works on (or waits
-// for) the current one, so that a tile's gathers start the moment its level is released.  With
-// G larger than the tiles of a level, a level's tiles all sit in different CTAs.  Every CTA
-// processes its tiles in increasing order and a tile only waits on lower-numbered tiles, so the
-// lowest unfinished tile can always run: no deadlock.
 template <int KP>
 __global__ void __launch_bounds__(PROP_TB) k_propagate(uint32_t ntiles,
-    const uint32_t *__restrict__ tile_dep, const uint32_t *__restrict__ wt_piece,
-    const uint32_t *__restrict__ ad, uint32_t piece0, IVec<KP> *state, WDesc<KP> *desc,
+    const uint32_t *__restrict__ tile_dep, const uint32_t *__restrict__ pp_piece,
+    const uint32_t *__restrict__ pp_off, const uint32_t *__restrict__ refs, IVec<KP> *pval,
     uint32_t *counters, int *error_flag, unsigned long long *trace) {
-    // state[0 .. piece0) are the nodes' own sample weights (written by k_set_weights before this
-    // launch), state[piece0 + p] is piece p: one base address for both kinds of gather
-    IVec<KP> *pval = state + piece0;
-    extern __shared__ __align__(16) unsigned char prop_smem[];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    IVec<KP> *vbuf = reinterpret_cast<IVec<KP> *>(prop_smem) + (size_t) warp * WBUF;
-    uint32_t *wbuf = reinterpret_cast<uint32_t *>(prop_smem + (size_t) PROP_WARPS * WBUF * sizeof(IVec<KP>))
-                     + (size_t) warp * WBUF;
-    uint32_t *stage = reinterpret_cast<uint32_t *>(
-        prop_smem + (size_t) PROP_WARPS * WBUF * (sizeof(IVec<KP>) + sizeof(uint32_t)))
-                      + (size_t) warp * 2 * WTILE;
-    SegOp<KP> op;
-    SegVal<KP> identity;
-    identity.v = ivec_zero<KP>();
-    identity.head = 0;
-    identity.ends = 0;
-
-    if (blockIdx.x < ntiles) {
-        const uint32_t *src = ad + ((size_t) blockIdx.x * PROP_WARPS + warp) * WTILE;
-        for (uint32_t j = lane * 4; j < WTILE; j += 128) cp_async16(stage + j, src + j);
-    }
-    uint32_t buf = 0;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         TRACE(0);
-        cp_async_wait_all();  // this tile's words (issued one iteration ago)
-        __syncwarp();
-        // prefetch the next tile
-        const uint32_t next = tile + gridDim.x;
-        if (next < ntiles) {
-            const uint32_t *src = ad + ((size_t) next * PROP_WARPS + warp) * WTILE;
-            uint32_t *dst = stage + (buf ^ 1) * WTILE;
-            for (uint32_t j = lane * 4; j < WTILE; j += 128) cp_async16(dst + j, src + j);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        const uint32_t wt = tile * PROP_WARPS + warp;
         const uint32_t dep = __ldg(tile_dep + tile);
-        const uint32_t piece_base = __ldg(wt_piece + wt);
-        // striped: lane l holds addends q * 32 + l, so that one load instruction covers 32
-        // consecutive addends and its gathers (consecutive pieces of a child, mostly) share sectors
-        uint32_t ws[PW_IPT];
+        uint32_t piece[PROP_IPT], o0[PROP_IPT], o1[PROP_IPT], rf[PROP_IPT][PROP_PRE];
+        // everything that does not depend on other tiles is fetched before the wait
 #pragma unroll
-        for (int q = 0; q < PW_IPT; q++) ws[q] = stage[buf * WTILE + q * 32 + lane];
-        // (a) every lower level complete: one thread watches the global counter
+        for (int q = 0; q < PROP_IPT; q++) {
+            const uint32_t j = tile * PROP_TILE + q * PROP_TB + threadIdx.x;
+            piece[q] = __ldg(pp_piece + j);
+            o0[q] = __ldg(pp_off + j);
+            o1[q] = __ldg(pp_off + j + 1);
+        }
+#pragma unroll
+        for (int q = 0; q < PROP_IPT; q++) {
+#pragma unroll
+            for (int i = 0; i < PROP_PRE; i++) {
+                rf[q][i] = o0[q] + i < o1[q] ? __ldg(refs + o0[q] + i) : NO_PIECE;
+            }
+        }
         if (dep > 0) {
             if (threadIdx.x == 0) {
-                volatile uint32_t *done = counters + 1;
                 uint32_t spins = 0;
-                if (trace != nullptr) trace[(size_t) tile * 6 + 1] = gtime();
-                while (*done < dep) {
+                while (ld_acquire(counters + 1) < dep) {
                     if (++spins > SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int *) error_flag)) {
                         *error_flag = 1;
                         break;
                     }
                 }
-                __threadfence();
             }
             __syncthreads();
         }
+        TRACE(1);
+        IVec<KP> g[PROP_IPT][PROP_PRE];
+#pragma unroll
+        for (int q = 0; q < PROP_IPT; q++) {
+#pragma unroll
+            for (int i = 0; i < PROP_PRE; i++) {
+                g[q][i] = ivec_zero<KP>();
+                if (rf[q][i] != NO_PIECE) g[q][i] = state_load<KP>(pval + rf[q][i]);
+            }
+        }
         TRACE(2);
-        // gather (striped): issue every load of the lane before the first use, so the 8-16 loads
-        // are one round trip; then transpose words and values to blocked (lane l owns addends
-        // l * 8 + q)
-        {
-            IVec<KP> g0[PW_IPT], g1[PW_IPT];
-            uint32_t idx[PW_IPT];
 #pragma unroll
-            for (int q = 0; q < PW_IPT; q++) {
-                const uint32_t kind = ws[q] >> AD_KIND_SHIFT, pay = ws[q] & AD_PAYLOAD;
-                idx[q] = pay + (kind == AD_NONE ? 0u : piece0);
-                g0[q] = ivec_zero<KP>();
-                if (kind != AD_NONE || (ws[q] & AD_HEAD)) g0[q] = state_load<KP>(state + idx[q]);
+        for (int q = 0; q < PROP_IPT; q++) {
+            IVec<KP> sum = g[q][0];
+#pragma unroll
+            for (int i = 1; i < PROP_PRE; i++) sum = sum + g[q][i];
+            for (uint32_t o = o0[q] + PROP_PRE; o < o1[q]; o++) {
+                sum = sum + state_load<KP>(pval + __ldg(refs + o));
             }
-#pragma unroll
-            for (int q = 0; q < PW_IPT; q++) {
-                g1[q] = ivec_zero<KP>();
-                if ((ws[q] >> AD_KIND_SHIFT) == AD_DIFF) g1[q] = state_load<KP>(state + idx[q] - 1);
-            }
-#pragma unroll
-            for (int q = 0; q < PW_IPT; q++) {
-                const uint32_t kind = ws[q] >> AD_KIND_SHIFT;
-                IVec<KP> v = kind == AD_NEG ? g1[q] - g0[q] : g0[q] - g1[q];  // g1 is 0 unless DIFF
-                vbuf[padi(q * 32 + lane)] = v;
-                wbuf[padi(q * 32 + lane)] = ws[q];
-            }
+            if (piece[q] != NO_PIECE) pval[piece[q]] = sum;
         }
-        __syncwarp();
-        uint32_t word[PW_IPT];
-        SegVal<KP> item[PW_IPT];
-#pragma unroll
-        for (int q = 0; q < PW_IPT; q++) {
-            word[q] = wbuf[padi(lane * PW_IPT + q)];
-            item[q].v = vbuf[padi(lane * PW_IPT + q)];
-            item[q].head = (word[q] >> AD_KIND_SHIFT) == AD_NONE && (word[q] & AD_HEAD) ? 1 : 0;
-            item[q].ends = (word[q] & AD_END) ? 1 : 0;
-        }
-        __syncwarp();
-        TRACE(3);
-#pragma unroll
-        for (int q = 1; q < PW_IPT; q++) item[q] = op(item[q - 1], item[q]);
-        // warp scan of the lane aggregates
-        SegVal<KP> incl = item[PW_IPT - 1];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            SegVal<KP> up = seg_shfl_up<KP>(incl, d);
-            if (lane >= (uint32_t) d) incl = op(up, incl);
-        }
-        SegVal<KP> excl = seg_shfl_up<KP>(incl, 1);
-        if (lane == 0) excl = identity;
-
-        // (b) carry entering this warp tile: decoupled look-back within the level
-        SegVal<KP> carry = identity;
-        if (lane == 31) {
-            WDesc<KP> *me = desc + wt;
-            const uint32_t first = dep * PROP_WARPS;
-            if (wt == first) {
-                desc_publish<KP>(me, incl, 2);
-            } else {
-                desc_publish<KP>(me, incl, 1);
-                uint32_t p = wt - 1, spins = 0;
-                while (true) {
-                    SegVal<KP> got;
-                    int st = desc_peek<KP>(desc + p, got);
-                    if (st == 0) {
-                        if (++spins > SPIN_LIMIT
-                            || ((spins & 1023u) == 0 && *(volatile int *) error_flag)) {
-                            *error_flag = 1;
-                            break;
-                        }
-                        continue;
-                    }
-                    carry = op(got, carry);
-                    if (st == 2 || carry.head || p == first) break;
-                    p--;
-                }
-                desc_publish<KP>(me, op(carry, incl), 2);
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < KP; c++) carry.v.v[c] = __shfl_sync(0xffffffffu, carry.v.v[c], 31);
-        carry.head = __shfl_sync(0xffffffffu, carry.head, 31);
-        const uint32_t total_ends = (uint32_t) __shfl_sync(0xffffffffu, incl.ends, 31);
-        TRACE(4);
-        // values entering this lane: carry (+) excl; compact the state at every piece end, then
-        // publish the warp tile's pieces with coalesced stores
-        SegVal<KP> in = op(carry, excl);
-#pragma unroll
-        for (int q = 0; q < PW_IPT; q++) {
-            if (word[q] & AD_END) {
-                SegVal<KP> r = op(in, item[q]);
-                vbuf[excl.ends + item[q].ends - 1] = r.v;
-            }
-        }
-        __syncwarp();
-        for (uint32_t j = lane; j < total_ends; j += 32) pval[piece_base + j] = vbuf[j];
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence();
-            atomicAdd(&counters[1], 1u);
-            if (trace != nullptr) trace[(size_t) tile * 6 + 5] = gtime();
+            red_release_add(counters + 1, 1u);
+            if (trace != nullptr) trace[(size_t) tile * 4 + 3] = gtime();
         }
-        buf ^= 1;
     }
+}
+
+// INIT pieces hold the node's own sample weight (trees.c:1406-1415)
+template <int KP>
+__global__ void k_init_pieces(const IVec<KP> *__restrict__ w, const int32_t *__restrict__ rank_node,
+    const uint32_t *__restrict__ poff, uint32_t N, IVec<KP> *pval) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < N) pval[poff[r]] = w[rank_node[r]];
 }
 
 // ---------------------------------------------------------------- phase 2, branch mode
@@ -894,9 +697,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         total += sp.sizes[k];
         h_off[k + 1] = (uint32_t) total;
     }
-    const uint32_t Npad = (N + 3u) & ~3u;
-    IVec<KP> *state = A.get<IVec<KP>>((size_t) Npad + P.P + 2048);  // summary tiles read whole tiles
-    IVec<KP> *w = state;
+    IVec<KP> *w = A.get<IVec<KP>>(N);
     uint32_t *d_off = A.get<uint32_t>(K + 1);
     const int32_t *d_sets = sp.sets;
     if (!sp.sets_on_device) {
@@ -948,38 +749,33 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     TSKB_CK(cudaEventRecord(P.ev[1], s));
 
     // ---- phase 1: propagate
-    IVec<KP> *pval = state + Npad;
+    IVec<KP> *pval = A.get<IVec<KP>>((size_t) P.P + 2048);  // summary tiles read whole tiles
     int *d_err = A.get<int>(1);
     TSKB_CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
+    if (N) {
+        k_init_pieces<KP><<<grid_for(N, TB), TB, 0, s>>>(w, P.rank_node.p, P.d_poff.p, N, pval);
+        TSKB_CK_LAUNCH();
+        c.launches++;
+    }
     if (P.ntiles) {
-        const size_t nwt = (size_t) P.ntiles * PROP_WARPS;
-        WDesc<KP> *desc = A.get<WDesc<KP>>(nwt);
         uint32_t *counters = A.get<uint32_t>(2);
-        TSKB_CK(cudaMemsetAsync(desc, 0, nwt * sizeof(WDesc<KP>), s));
         TSKB_CK(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
         unsigned long long *trace = nullptr;
         if (getenv("TSKB_TRACE") != nullptr) {
-            trace = A.get<unsigned long long>((size_t) P.ntiles * 6);
-            TSKB_CK(cudaMemsetAsync(trace, 0, (size_t) P.ntiles * 6 * sizeof(unsigned long long), s));
+            trace = A.get<unsigned long long>((size_t) P.ntiles * 4);
+            TSKB_CK(cudaMemsetAsync(trace, 0, (size_t) P.ntiles * 4 * sizeof(unsigned long long), s));
             P.stats_trace = trace;
         }
-        TSKB_CK(cudaFuncSetAttribute(k_propagate<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (int) propagate_smem<KP>()));
         int per_sm = 1, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
-        TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<KP>, PROP_TB,
-            propagate_smem<KP>()));
+        TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<KP>, PROP_TB, 0));
         const uint32_t grid = std::min<uint32_t>(P.ntiles, (uint32_t) (sms * std::max(per_sm, 1)));
-        {
-            uint32_t a_ntiles = P.ntiles;
-            const uint32_t *a_dep = P.tile_dep.p, *a_wtp = P.wt_piece.p, *a_ad = P.ad.p;
-            uint32_t a_piece0 = Npad;
-            void *args[] = { &a_ntiles, &a_dep, &a_wtp, &a_ad, &a_piece0, &state, &desc, &counters,
-                &d_err, &trace };
-            TSKB_CK(cudaLaunchCooperativeKernel((const void *) k_propagate<KP>, dim3(grid),
-                dim3(PROP_TB), args, propagate_smem<KP>(), s));
-        }
-        TSKB_CK_LAUNCH();
+        uint32_t a_ntiles = P.ntiles;
+        const uint32_t *a_dep = P.tile_dep.p, *a_piece = P.pp_piece.p, *a_off = P.pp_off.p,
+                       *a_refs = P.refs.p;
+        void *args[] = { &a_ntiles, &a_dep, &a_piece, &a_off, &a_refs, &pval, &counters, &d_err, &trace };
+        TSKB_CK(cudaLaunchCooperativeKernel((const void *) k_propagate<KP>, dim3(grid), dim3(PROP_TB),
+            args, 0, s));
         c.launches++;
     }
     TSKB_CK(cudaEventRecord(P.ev[2], s));
