@@ -1,5 +1,7 @@
 """Pure numpy/Python model of the replay plan (tskit_b200/csrc/plan.cuh), used by
 the GPU tests to localise a failure to one staging step.  Small inputs only."""
+import os
+
 import numpy as np
 
 
@@ -164,6 +166,8 @@ def build(t, a=None, b=None):
                 height[p] = h
                 changed = True
     real = np.nonzero(pc_x[:P] >= 0)[0]
+    if os.environ.get("TSKB_ORDER", "").startswith("x"):
+        real = real[np.argsort(pc_x[real], kind="stable")]
     order = real[np.argsort(height[real], kind="stable")]
     nheights = int(height.max()) + 1 if P else 1
     TILE = 1024
@@ -172,33 +176,50 @@ def build(t, a=None, b=None):
     ntile = -(-(begin[1:] - begin[:-1]) // TILE)
     level_begin = np.concatenate([[0], np.cumsum(ntile) * TILE]).astype(np.uint32)
     npp = int(level_begin[-1])
-    pp_piece = np.full(npp, 0xFFFFFFFF, dtype=np.uint32)
-    cnts = np.zeros(npp + 1, dtype=np.int64)
+    # state slots: processing position of every real piece, then one INIT slot per sample, then
+    # the zero slot shared by the INIT pieces of nodes that are not samples
+    n = int(is_sample.sum())
+    sample_index = np.full(N, -1, dtype=np.int64)
+    sample_index[np.nonzero(is_sample)[0]] = np.arange(n)
     pos = level_begin[:-1].astype(np.int64)[hs] + (np.arange(len(order)) - begin[hs])
-    pp_piece[pos] = order
+    perm = np.zeros(P + 1, dtype=np.int64)
+    perm[order] = pos
+    si = sample_index[rank_node]
+    perm[poff[:N]] = np.where(si >= 0, npp + si, npp + n)
+    # breakpoints: distinct diff positions, then the end of the range
+    bp_pos = np.concatenate([np.unique(ev_pos), [b]])
+    T = len(bp_pos) - 1
+    q_bp0 = np.zeros(npp, dtype=np.uint32)
+    q_bp1 = np.full(npp, 0xFFFFFFFF, dtype=np.uint32)
+    q_bl = np.zeros(npp)
+    cnts = np.zeros(npp + 1, dtype=np.int64)
+    q_bp0[pos] = np.searchsorted(bp_pos[:T], pc_x[order])
+    nxt = pc_x[np.minimum(order + 1, P_pad - 1)]
+    q_bp1[pos] = np.where((order + 1 < P) & (nxt >= 0), np.searchsorted(bp_pos[:T], nxt), T)
+    q_bl[pos] = pc_bl[order]
     cnts[pos] = [len(ref_lists[p]) for p in order]
-    pp_off = np.concatenate([[0], np.cumsum(cnts[:-1])]).astype(np.uint32)
+    q_off = np.concatenate([[0], np.cumsum(cnts[:-1])]).astype(np.uint32)
     refs = np.zeros(int(cnts.sum()), dtype=np.uint32)
     for j, p in zip(pos, order):
-        refs[pp_off[j]:pp_off[j] + len(ref_lists[p])] = ref_lists[p]
+        refs[q_off[j]:q_off[j] + len(ref_lists[p])] = np.sort(perm[ref_lists[p]])
     # sites
     mut_src = np.zeros(t.num_mutations, dtype=np.int32)
     for m in range(t.num_mutations):
         x = t.sites_position[t.mutations_site[m]]
         r = rank[t.mutations_node[m]]
         lo, hi = poff[r], poff[r + 1]
-        mut_src[m] = lo + np.searchsorted(pc_x[lo:hi], x, side="right") - 1
+        mut_src[m] = perm[lo + np.searchsorted(pc_x[lo:hi], x, side="right") - 1]
     return dict(ev_pos=ev_pos, ev_child=ev_child.astype(np.int32), ev_sign=ev_sign, voff=voff,
-                pp_piece=pp_piece, pp_off=pp_off, refs=refs, pc_x=pc_x, pc_bl=pc_bl, level=level,
-                rank_node=rank_node, level_begin=level_begin, mut_src=mut_src, poff=poff)
+                q_off=q_off, refs=refs, q_bp0=q_bp0, q_bp1=q_bp1, q_bl=q_bl, bp_pos=bp_pos, level=level,
+                rank_node=rank_node, level_begin=level_begin, mut_src=mut_src)
 
 
 DTYPES = dict(ev_pos=np.float64, ev_child=np.int32, ev_sign=np.int8, voff=np.uint32,
-              pp_piece=np.uint32, pp_off=np.uint32, refs=np.uint32, pc_x=np.float64,
-              pc_bl=np.float64, level=np.uint32, rank_node=np.int32, level_begin=np.uint32,
+              q_off=np.uint32, refs=np.uint32, q_bp0=np.uint32, q_bp1=np.uint32, bp_pos=np.float64,
+              q_bl=np.float64, level=np.uint32, rank_node=np.int32, level_begin=np.uint32,
               mut_src=np.int32)
-ORDER = ["ev_pos", "ev_child", "ev_sign", "voff", "level", "rank_node", "pc_x", "pc_bl",
-         "level_begin", "pp_piece", "pp_off", "refs", "mut_src"]
+ORDER = ["ev_pos", "ev_child", "ev_sign", "voff", "level", "rank_node", "level_begin", "bp_pos", "q_bp0",
+         "q_bp1", "q_bl", "q_off", "refs", "mut_src"]
 
 
 def compare(ll, t, a=None, b=None):

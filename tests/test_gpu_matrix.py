@@ -111,7 +111,51 @@ def test_divmat_errors(wf_small, engines):
     internal = int(np.nonzero((wf_small.nodes_flags & 1) == 0)[0][0])
     assert code(lambda: ll.divergence_matrix([0, L], sample_sets=i32(internal), sample_set_sizes=u64(1))) == -601
     assert code(lambda: ll.divergence_matrix([0, L], sample_sets=i32(10 ** 7), sample_set_sizes=u64(1))) == -202
-    assert code(lambda: ll.divergence_matrix([0, L], mode="branch")) == -20003
+
+
+def test_divmat_branch_golden_single_tree():
+    from tskit_b200.lowlevel import LLTreeSequence
+    ll = LLTreeSequence(fx.load("single_tree"))
+    d = ll.divergence_matrix([0, 1.0], mode="branch", span_normalise=False)
+    assert np.allclose(d[0], fx.SINGLE_TREE_D_BRANCH, rtol=1e-12, atol=0)  # test_stats.c:1459-1473
+
+
+def test_divmat_branch_wright_fisher(wf_small, engines):
+    """Branch-mode matrix (trees.c:8579-8676) = the sweep engine's branch divergence over blocks of
+    sample sets; compared with the oracle's per-tree MRCA definition."""
+    ll, o = engines
+    L = wf_small.sequence_length
+    s = wf_small.samples
+    sub = s[::13].astype(np.int32)  # 24 singleton sets: several 4 x 4 blocks, a ragged last one
+    ones = np.ones(len(sub), dtype=np.uint64)
+    for windows in ([0, L], np.linspace(0, L, 5), [L * 0.1, L * 0.35, L * 0.8]):
+        for span in (True, False):
+            got = ll.divergence_matrix(windows, sample_sets=sub, sample_set_sizes=ones, mode="branch",
+                                       span_normalise=span)
+            want = o.divergence_matrix([[u] for u in sub], windows=windows, mode="branch",
+                                       span_normalise=span)
+            assert got.shape == want.shape
+            assert np.allclose(got, want, rtol=1e-9, atol=0)
+            assert np.all(got[:, np.arange(len(sub)), np.arange(len(sub))] == 0)
+    sets = [s[:40], s[40:41], s[50:120], s[120:130], s[140:200]]
+    sizes = np.array([len(x) for x in sets], dtype=np.uint64)
+    flat = np.concatenate(sets).astype(np.int32)
+    w = np.linspace(0, L, 4)
+    got = ll.divergence_matrix(w, sample_sets=flat, sample_set_sizes=sizes, mode="branch")
+    want = o.divergence_matrix(sets, windows=w, mode="branch")
+    assert np.allclose(got, want, rtol=1e-9, atol=0), (got[0], want[0])
+    assert np.all(got[:, 1, 1] == 0)  # singleton set: diagonal 0, not NaN (trees.c:8888-8891)
+
+
+@pytest.mark.parametrize("name", ["paper", "nonbinary", "multiroot", "internal_sample", "case_1"])
+def test_divmat_branch_fixtures(name):
+    from tskit_b200.lowlevel import LLTreeSequence
+    t = fx.load(name)
+    ll, o = LLTreeSequence(t), port.Oracle(t)
+    L = t.sequence_length
+    got = ll.divergence_matrix([0, L / 2, L], mode="branch")
+    want = o.divergence_matrix(None, windows=[0, L / 2, L], mode="branch")
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
 
 
 def test_genetic_relatedness_matrix_through_dropin(wf_small):
@@ -128,4 +172,12 @@ def test_genetic_relatedness_matrix_through_dropin(wf_small):
     got = acc.divergence_matrix(windows=w, mode="site")
     want = ts.divergence_matrix(windows=w, mode="site")
     assert np.allclose(got, want, rtol=1e-12)
+    # branch mode: the reference's per-tree MRCA loop against the sweep engine
+    got = acc.genetic_relatedness_matrix(sample_sets=sets, windows=w, mode="branch")
+    want = ts.genetic_relatedness_matrix(sample_sets=sets, windows=w, mode="branch")
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+    some = [[int(u)] for u in s[:11]]
+    got = acc.divergence_matrix(sample_sets=some, windows=w, mode="branch")
+    want = ts.divergence_matrix(sample_sets=some, windows=w, mode="branch")
+    assert np.allclose(got, want, rtol=1e-9)
     assert acc.accel_stats["forwarded"] == 0

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtskb.so")
+LIB_PATH = os.environ.get("TSKB_LIB") or os.path.join(_HERE, "libtskb.so")  # TSKB_LIB: A/B builds
 
 u64, i32p, u64p, f64p, vp = C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
 

@@ -334,7 +334,7 @@ int64_t tskb_treeseq_debug_array(const tskb_treeseq_t *self, const char *name, v
     std::string s(name);
 #define ARR(NAME, A) if (s == NAME) { src = P.A.p; n = P.A.n; esize = sizeof(*P.A.p); }
     ARR("ev_pos", ev_pos) ARR("ev_child", ev_child) ARR("ev_sign", ev_sign) ARR("voff", voff)
-    ARR("pp_piece", pp_piece) ARR("pp_off", pp_off) ARR("refs", refs) ARR("pc_x", pc_x) ARR("pc_bl", pc_bl)
+    ARR("q_off", q_off) ARR("refs", refs) ARR("q_bp0", q_bp0) ARR("q_bp1", q_bp1) ARR("q_bl", q_bl) ARR("bp_pos", bp_pos)
     ARR("tile_dep", tile_dep)
     ARR("level", level) ARR("rank_node", rank_node) ARR("mut_src", mut_src)
     ARR("mut_allele", mut_allele) ARR("mut_alt", mut_alt)

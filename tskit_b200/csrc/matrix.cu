@@ -374,6 +374,94 @@ int check_divmat_args(const Plan &P, uint64_t &nsets, const uint64_t *&sizes, co
     return 0;
 }
 
+// Divergence matrix, branch mode (tsk_treeseq_divergence_matrix_branch, trees.c:8579-8676).
+// The reference adds, per tree and per pair of samples (u, v), the path length between them
+// ((t_mrca - t_u) + (t_mrca - t_v), or the two distances to the roots when they are in different
+// subtrees) times the tree's span, then divides by the number of pairs (trees.c:8876-8899).
+// The path between u and v consists of exactly the branches that have one of the two below them,
+// so entry (j, k) is the branch-mode `divergence` statistic of sample sets j and k
+// (trees.c:4221-4264 with the branch summary of trees.c:1944-1972): sum over branches of
+// length * [x_j (n_k - x_k) + (n_j - x_j) x_k] / (n_j n_k), and 2 x_j (n_j - x_j) / (n_j (n_j - 1))
+// on the diagonal.  The matrix is therefore computed by the sweep engine itself, in blocks of
+// BLK x BLK sets (2 * BLK state columns per sweep), over the windows padded to [0, L].
+constexpr uint32_t BLK = 4;
+
+int run_branch_divergence_matrix(const Plan &P, uint64_t nsets, const uint64_t *sizes, const int32_t *sets,
+    uint64_t num_windows, const double *windows, uint32_t options, double *result) {
+    const uint32_t ns = (uint32_t) nsets, W = (uint32_t) num_windows;
+    memset(result, 0, (size_t) W * ns * ns * sizeof(double));
+    if (ns == 0) return 0;
+    // the sweep engine takes windows covering the whole genome (trees.c:2070); divergence_matrix
+    // windows need not (trees.c:8943): pad, and drop the padding windows from the output
+    std::vector<double> win;
+    const uint32_t lead = windows[0] > 0 ? 1 : 0;
+    if (lead) win.push_back(0.0);
+    win.insert(win.end(), windows, windows + W + 1);
+    if (windows[W] < P.L) win.push_back(P.L);
+    const uint32_t Wp = (uint32_t) win.size() - 1;
+    std::vector<uint64_t> off(ns + 1, 0);
+    for (uint32_t a = 0; a < ns; a++) off[a + 1] = off[a] + sizes[a];
+    const uint32_t nblk = (ns + BLK - 1) / BLK;
+    std::vector<uint64_t> b_sizes;
+    std::vector<int32_t> b_sets, tuples;
+    std::vector<uint32_t> tup_a, tup_b;
+    std::vector<double> out;
+    for (uint32_t ba = 0; ba < nblk; ba++) {
+        for (uint32_t bb = ba; bb < nblk; bb++) {
+            b_sizes.clear(); b_sets.clear(); tuples.clear(); tup_a.clear(); tup_b.clear();
+            const uint32_t a0 = ba * BLK, a1 = std::min(ns, a0 + BLK);
+            const uint32_t c0 = bb * BLK, c1 = std::min(ns, c0 + BLK);
+            auto push_set = [&](uint32_t a) {
+                b_sizes.push_back(sizes[a]);
+                b_sets.insert(b_sets.end(), sets + off[a], sets + off[a + 1]);
+            };
+            for (uint32_t a = a0; a < a1; a++) push_set(a);
+            if (bb != ba) {
+                for (uint32_t c = c0; c < c1; c++) push_set(c);
+            }
+            for (uint32_t a = a0; a < a1; a++) {
+                for (uint32_t c = std::max(a, c0); c < c1; c++) {
+                    // a singleton set has no pairs: the reference leaves 0 on the diagonal
+                    // (trees.c:8888-8891) where the statistic would be 0/0
+                    if (a == c && sizes[a] < 2) continue;
+                    tuples.push_back((int32_t) (a - a0));
+                    tuples.push_back((int32_t) (bb != ba ? (a1 - a0) + (c - c0) : c - a0));
+                    tup_a.push_back(a);
+                    tup_b.push_back(c);
+                }
+            }
+            const uint32_t M = (uint32_t) tup_a.size();
+            if (M == 0) continue;
+            out.assign((size_t) Wp * M, 0.0);
+            StatSpec sp = {};
+            sp.stat_id = STAT_DIVERGENCE;
+            sp.K = (uint32_t) b_sizes.size();
+            sp.M = M;
+            sp.tuple = 2;
+            sp.sizes = b_sizes.data();
+            sp.sets = b_sets.data();
+            sp.sets_on_device = false;
+            sp.indexes = tuples.data();
+            sp.W = Wp;
+            sp.windows = win.data();
+            sp.options = TSKB_STAT_BRANCH | (options & TSKB_STAT_SPAN_NORMALISE);
+            sp.result = out.data();
+            sp.result_on_device = false;
+            int ret = run_sample_count_stat(&P, sp);
+            if (ret != 0) return ret;
+            for (uint32_t w = 0; w < W; w++) {
+                double *D = result + (size_t) w * ns * ns;
+                for (uint32_t m = 0; m < M; m++) {
+                    const double v = out[(size_t) (w + lead) * M + m];
+                    D[(size_t) tup_a[m] * ns + tup_b[m]] = v;
+                    D[(size_t) tup_b[m] * ns + tup_a[m]] = v;
+                }
+            }
+        }
+    }
+    return 0;
+}
+
 }  // namespace
 
 int run_genotype_matrix(const Plan *plan, const int32_t *samples, uint64_t num_samples,
@@ -417,7 +505,7 @@ int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *size
         if (P.time_uncalibrated && !(options & TSKB_STAT_ALLOW_TIME_UNCALIBRATED)) {
             return TSKB_ERR_TIME_UNCALIBRATED;
         }
-        return TSKB_ERR_UNSUPPORTED;  // branch-mode matrix (trees.c:8579-8676): not on the device yet
+        return run_branch_divergence_matrix(P, nsets, sizes, sets, num_windows, windows, options, result);
     }
     if (P.range_left != 0 || P.range_right != P.L) return TSKB_ERR_UNSUPPORTED;
     std::lock_guard<std::mutex> lock(P.mu);

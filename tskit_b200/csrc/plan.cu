@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "plan.cuh"
@@ -29,8 +30,8 @@ Plan::~Plan() {
 uint64_t Plan::device_bytes() const {
     return time.bytes() + d_samples.bytes() + coff.bytes() + csr_left.bytes() + csr_right.bytes()
            + csr_parent.bytes() + ev_pos.bytes() + ev_child.bytes() + ev_sign.bytes()
-           + voff.bytes() + pp_piece.bytes() + pp_off.bytes() + refs.bytes() + pc_x.bytes()
-           + pc_bl.bytes() + tile_dep.bytes() + d_poff.bytes() + pm_off.bytes() + pm_left.bytes()
+           + voff.bytes() + q_off.bytes() + refs.bytes() + q_bp0.bytes() + q_bp1.bytes() + bp_pos.bytes()
+           + q_bl.bytes() + tile_dep.bytes() + d_sample_index.bytes() + pm_off.bytes() + pm_left.bytes()
            + pm_right.bytes() + pm_pmax.bytes() + pm_child.bytes() + rank_node.bytes() + level.bytes() + site_pos.bytes() + site_moff.bytes()
            + site_aoff.bytes() + mut_node.bytes() + mut_src.bytes() + mut_allele.bytes()
            + mut_alt.bytes();
@@ -394,26 +395,79 @@ __global__ void k_height_keys(uint32_t P, const double *pc_x, const uint32_t *he
     val[p] = p;
 }
 
-// processing order: pieces by (height, piece id); every height padded to whole tiles
+// processing order: pieces by (height, secondary order); every height padded to whole tiles.
+// perm[p] = processing position (= state slot) of node-major piece p.
 __global__ void k_order_fill(const uint32_t *sorted_piece, const uint32_t *sorted_h, uint32_t nreal,
     const uint32_t *lvl_sorted_begin, const uint32_t *lvl_padded_begin, const uint32_t *cnt,
-    uint32_t *pp_piece, uint32_t *pp_cnt) {
+    const double *pc_x, const double *pc_bl, uint32_t P, const double *bp_pos, uint32_t T,
+    uint32_t *q_bp0, uint32_t *q_bp1, double *q_bl, uint32_t *q_cnt, uint32_t *perm) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nreal) return;
     uint32_t h = sorted_h[i], p = sorted_piece[i];
     uint32_t j = lvl_padded_begin[h] + (i - lvl_sorted_begin[h]);
-    pp_piece[j] = p;
-    pp_cnt[j] = cnt[p];
+    perm[p] = j;
+    q_bp0[j] = lower_bound_dev(bp_pos, T, pc_x[p]);
+    // the piece ends where the node's next piece starts (the next node's list opens with an
+    // INIT marker, x = -1), else at the end of the range (breakpoint index T)
+    q_bp1[j] = (p + 1 < P && pc_x[p + 1] >= 0.0) ? lower_bound_dev(bp_pos, T, pc_x[p + 1]) : T;
+    q_bl[j] = pc_bl[p];
+    q_cnt[j] = cnt[p];
 }
 
-__global__ void k_refs_reorder(uint32_t npp, const uint32_t *pp_piece, const uint32_t *pp_off,
-    const uint32_t *ch_off, const uint32_t *refs, uint32_t *refs2) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= npp) return;
-    uint32_t p = pp_piece[j];
-    if (p == 0xffffffffu) return;
-    uint32_t o = pp_off[j], n = pp_off[j + 1] - o, s0 = ch_off[p];
-    for (uint32_t i = 0; i < n; i++) refs2[o + i] = refs[s0 + i];
+__global__ void k_bp_pos(const double *ev_pos, const uint32_t *ev_bp, uint32_t nev, uint32_t T,
+    double range_right, double *bp_pos) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) bp_pos[T] = range_right;
+    if (i < nev && (i + 1 == nev || ev_pos[i] != ev_pos[i + 1])) bp_pos[ev_bp[i]] = ev_pos[i];
+}
+
+// INIT pieces: the sample's weight slot, or the shared zero slot for a node that is not a sample
+__global__ void k_init_perm(uint32_t N, const uint32_t *poff, const int32_t *rank_node,
+    const int32_t *sample_index, uint32_t npp, uint32_t n, uint32_t *perm) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    int32_t si = sample_index[rank_node[r]];
+    perm[poff[r]] = si >= 0 ? npp + (uint32_t) si : npp + n;
+}
+
+__global__ void k_refs_reorder(uint32_t nreal, const uint32_t *sorted_piece, const uint32_t *perm,
+    const uint32_t *q_off, const uint32_t *ch_off, const uint32_t *refs, uint32_t *refs2) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nreal) return;
+    uint32_t p = sorted_piece[i];
+    uint32_t j = perm[p];
+    uint32_t o = q_off[j], n = q_off[j + 1] - o, s0 = ch_off[p];
+    // ascending state slot: consecutive pieces of a node then list the same children in the same
+    // order, so the lanes of a warp gather each slot from neighbouring addresses
+    for (uint32_t k = 0; k < n; k++) {
+        uint32_t v = perm[refs[s0 + k]];
+        uint32_t i = k;
+        while (i > 0 && refs2[o + i - 1] > v) {
+            refs2[o + i] = refs2[o + i - 1];
+            i--;
+        }
+        refs2[o + i] = v;
+    }
+}
+
+__global__ void k_x_keys(uint32_t P, const double *pc_x, uint64_t *key, uint32_t *val) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    key[p] = ordered_bits(pc_x[p]);
+    val[p] = p;
+}
+
+__global__ void k_height_keys_of(uint32_t P, const uint32_t *piece, const double *pc_x,
+    const uint32_t *height, uint32_t *key, uint32_t init_key) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    uint32_t p = piece[i];
+    key[i] = pc_x[p] >= 0.0 ? height[p] : init_key;
+}
+
+__global__ void k_translate(int32_t *a, uint32_t n, const uint32_t *perm) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (int32_t) perm[a[i]];
 }
 
 __global__ void k_flag_samples(const int32_t *samples, uint32_t n, uint32_t *flag) {
@@ -673,6 +727,9 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK(cudaMemcpyAsync(&T, ev_bp.p + nev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         TSKB_CK(cudaStreamSynchronize(s));
         P.T = T;
+        P.bp_pos.alloc((size_t) T + 1);
+        k_bp_pos<<<grid_for(nev + 1, TB), TB, 0, s>>>(P.ev_pos.p, ev_bp.p, nev, T, b, P.bp_pos.p);
+        TSKB_CK_LAUNCH();
     }
 
     // ---- dependency levels: level[parent] > level[child] over every edge
@@ -732,7 +789,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
 
     // ---- node-major order of the entries (CHILD entries + visits), pieces, addends
     const uint32_t Ve = V + nev;
-    DevArray<uint32_t> sorted_e, sorted_key, em_ev, noff, endflag, endscan, inv, poff;  // poff -> P.d_poff
+    DevArray<uint32_t> sorted_e, sorted_key, em_ev, noff, endflag, endscan, inv, poff;
     sorted_e.alloc(Ve); sorted_key.alloc(Ve); em_ev.alloc(Ve); noff.alloc(N + 1);
     endflag.alloc(Ve + 1); endscan.alloc(Ve + 1); inv.alloc(Ve); poff.alloc(N + 1);
     {
@@ -781,20 +838,22 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     // ---- pieces
     // pieces are streamed in whole tiles of 1024 by the summary kernel: pad with INIT markers
     const size_t P_pad = ((size_t) P.P + 1023) / 1024 * 1024;
-    P.pc_x.alloc(P_pad); P.pc_bl.alloc(P_pad);
-    TSKB_CK(cudaMemsetAsync(P.pc_bl.p, 0, P_pad * sizeof(double), s));
-    k_fill_f64<<<grid_for(P_pad - P.P + 1, TB), TB, 0, s>>>(P.pc_x.p + P.P, P_pad - P.P, -1.0);
+    // node-major construction arrays (dropped once the processing order is laid out)
+    DevArray<double> pc_x, pc_bl;
+    pc_x.alloc(P_pad); pc_bl.alloc(P_pad);
+    TSKB_CK(cudaMemsetAsync(pc_bl.p, 0, P_pad * sizeof(double), s));
+    k_fill_f64<<<grid_for(P_pad - P.P + 1, TB), TB, 0, s>>>(pc_x.p + P.P, P_pad - P.P, -1.0);
     TSKB_CK_LAUNCH();
     DevArray<uint32_t> piece_rank;
     piece_rank.alloc(P.P);
     if (Ve) {
         k_piece_fill<<<grid_for(Ve, TB), TB, 0, s>>>(sorted_e.p, sorted_key.p, em_ev.p, endflag.p,
-            endscan.p, P.voff.p, P.ev_sign.p, ev_sbl.p, P.ev_pos.p, vis_bl.p, Ve, P.pc_x.p,
-            P.pc_bl.p, piece_rank.p);
+            endscan.p, P.voff.p, P.ev_sign.p, ev_sbl.p, P.ev_pos.p, vis_bl.p, Ve, pc_x.p,
+            pc_bl.p, piece_rank.p);
         TSKB_CK_LAUNCH();
     }
-    k_piece_init<<<grid_for(N + 1, TB), TB, 0, s>>>(noff.p, endscan.p, Ve, ends_total, N, P.pc_x.p,
-        P.pc_bl.p, piece_rank.p, poff.p);
+    k_piece_init<<<grid_for(N + 1, TB), TB, 0, s>>>(noff.p, endscan.p, Ve, ends_total, N, pc_x.p,
+        pc_bl.p, piece_rank.p, poff.p);
     TSKB_CK_LAUNCH();
     TSKB_CK(cudaStreamSynchronize(s));
     ev_sbl.release(); vis_bl.release(); inv.release(); em_ev.release(); sorted_e.release();
@@ -832,6 +891,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     }
 
     // ---- references of every piece, heights, processing order
+    DevArray<uint32_t> perm;  // node-major piece -> state slot
     {
         const uint32_t Pn = P.P;
         DevArray<uint32_t> is_sample, cnt, ch_off, refs, height;
@@ -845,7 +905,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
                 is_sample.p);
             TSKB_CK_LAUNCH();
         }
-        k_piece_children<false><<<grid_for(Pn, TB), TB, 0, s>>>(Pn, P.pc_x.p, piece_rank.p,
+        k_piece_children<false><<<grid_for(Pn, TB), TB, 0, s>>>(Pn, pc_x.p, piece_rank.p,
             P.rank_node.p, rank.p, is_sample.p, poff.p, P.pm_off.p, P.pm_left.p, P.pm_right.p,
             P.pm_pmax.p, P.pm_child.p, cnt.p, nullptr, nullptr);
         TSKB_CK_LAUNCH();
@@ -856,7 +916,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK(cudaMemcpyAsync(&nrefs, ch_off.p + Pn, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         TSKB_CK(cudaStreamSynchronize(s));
         refs.alloc((size_t) nrefs + 1);
-        k_piece_children<true><<<grid_for(Pn, TB), TB, 0, s>>>(Pn, P.pc_x.p, piece_rank.p,
+        k_piece_children<true><<<grid_for(Pn, TB), TB, 0, s>>>(Pn, pc_x.p, piece_rank.p,
             P.rank_node.p, rank.p, is_sample.p, poff.p, P.pm_off.p, P.pm_left.p, P.pm_right.p,
             P.pm_pmax.p, P.pm_child.p, cnt.p, ch_off.p, refs.p);
         TSKB_CK_LAUNCH();
@@ -867,7 +927,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
             while (h_changed) {
                 TSKB_CK(cudaMemsetAsync(changed.p, 0, sizeof(int), s));
                 for (int q = 0; q < 4; q++) {
-                    k_relax_height<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, ch_off.p, refs.p, P.pc_x.p,
+                    k_relax_height<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, ch_off.p, refs.p, pc_x.p,
                         height.p, changed.p);
                 }
                 TSKB_CK_LAUNCH();
@@ -888,13 +948,29 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
             }
         }
         P.nheights = max_h + 1;
-        // sort pieces by height (stable: piece order within a height); INIT pieces last
+        // sort pieces by height (stable: node-major piece order within a height, or by
+        // position with TSKB_ORDER=x); INIT pieces last
         DevArray<uint32_t> kin, kout, vin, vout, lvl_begin;
         kin.alloc(Pn); kout.alloc(Pn); vin.alloc(Pn); vout.alloc(Pn); lvl_begin.alloc(P.nheights + 2);
+        const char *order_env = getenv("TSKB_ORDER");
+        const bool order_x = order_env != nullptr && order_env[0] == 'x';
         if (Pn) {
-            k_height_keys<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, P.pc_x.p, height.p, kin.p, vin.p,
-                P.nheights);
-            TSKB_CK_LAUNCH();
+            if (order_x) {
+                DevArray<uint64_t> k64, k64o;
+                DevArray<uint32_t> v0;
+                k64.alloc(Pn); k64o.alloc(Pn); v0.alloc(Pn);
+                k_x_keys<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, pc_x.p, k64.p, v0.p);
+                TSKB_CK_LAUNCH();
+                sort_pairs(tmp, k64.p, k64o.p, v0.p, vin.p, Pn, 64, s);
+                k_height_keys_of<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, vin.p, pc_x.p, height.p, kin.p,
+                    P.nheights);
+                TSKB_CK_LAUNCH();
+                TSKB_CK(cudaStreamSynchronize(s));
+            } else {
+                k_height_keys<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, pc_x.p, height.p, kin.p, vin.p,
+                    P.nheights);
+                TSKB_CK_LAUNCH();
+            }
             sort_pairs(tmp, kin.p, kout.p, vin.p, vout.p, Pn,
                 (int) std::max(1u, ceil_log2(P.nheights + 2)), s);
         }
@@ -912,40 +988,50 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
             const uint32_t len = h_begin[h + 1] - h_begin[h];
             for (uint32_t u = 0; u < len; u += PROP_TILE) h_dep.push_back(dep);
             padded = (uint64_t) h_dep.size() * PROP_TILE;
-            if (padded >= 0xffffffffull) throw (int) TSKB_ERR_UNSUPPORTED;
+            if (padded + P.num_samples + 1 >= 0x7fffffffull) throw (int) TSKB_ERR_UNSUPPORTED;
         }
         h_padded[P.nheights] = (uint32_t) padded;
         P.level_begin[P.nheights] = (uint32_t) padded;
         P.npp = (uint32_t) padded;
         P.ntiles = (uint32_t) h_dep.size();
         P.tile_dep.upload(h_dep.data(), h_dep.size(), s);
-        DevArray<uint32_t> d_padded, pp_cnt;
+        DevArray<uint32_t> d_padded, q_cnt;
         d_padded.upload(h_padded.data(), h_padded.size(), s);
-        P.pp_piece.alloc(P.npp); P.pp_off.alloc((size_t) P.npp + 1); pp_cnt.alloc((size_t) P.npp + 1);
-        TSKB_CK(cudaMemsetAsync(pp_cnt.p, 0, ((size_t) P.npp + 1) * sizeof(uint32_t), s));
+        P.d_sample_index.upload(P.sample_index_map.data(), N, s);
+        P.q_bp0.alloc(P.npp); P.q_bp1.alloc(P.npp); P.q_bl.alloc(P.npp);
+        P.q_off.alloc((size_t) P.npp + 1); q_cnt.alloc((size_t) P.npp + 1);
+        perm.alloc((size_t) Pn + 1);
+        TSKB_CK(cudaMemsetAsync(q_cnt.p, 0, ((size_t) P.npp + 1) * sizeof(uint32_t), s));
         if (P.npp) {
-            k_fill_u32<<<grid_for(P.npp, TB), TB, 0, s>>>(P.pp_piece.p, P.npp, 0xffffffffu);
+            TSKB_CK(cudaMemsetAsync(P.q_bp0.p, 0, (size_t) P.npp * sizeof(uint32_t), s));
+            TSKB_CK(cudaMemsetAsync(P.q_bl.p, 0, (size_t) P.npp * sizeof(double), s));
+            // padding entries are marked by their end breakpoint
+            k_fill_u32<<<grid_for(P.npp, TB), TB, 0, s>>>(P.q_bp1.p, P.npp, NO_PIECE);
             TSKB_CK_LAUNCH();
         }
         if (nreal) {
             k_order_fill<<<grid_for(nreal, TB), TB, 0, s>>>(vout.p, kout.p, nreal, lvl_begin.p,
-                d_padded.p, cnt.p, P.pp_piece.p, pp_cnt.p);
+                d_padded.p, cnt.p, pc_x.p, pc_bl.p, Pn, P.bp_pos.p, P.T, P.q_bp0.p, P.q_bp1.p,
+                P.q_bl.p, q_cnt.p, perm.p);
             TSKB_CK_LAUNCH();
         }
-        TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, pp_cnt.p, P.pp_off.p, (size_t) P.npp + 1, s));
-        TSKB_CK(cub::DeviceScan::ExclusiveSum(tmp.need(bytes), bytes, pp_cnt.p, P.pp_off.p,
+        if (N) {
+            k_init_perm<<<grid_for(N, TB), TB, 0, s>>>(N, poff.p, P.rank_node.p,
+                P.d_sample_index.p, P.npp, P.num_samples, perm.p);
+            TSKB_CK_LAUNCH();
+        }
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, q_cnt.p, P.q_off.p, (size_t) P.npp + 1, s));
+        TSKB_CK(cub::DeviceScan::ExclusiveSum(tmp.need(bytes), bytes, q_cnt.p, P.q_off.p,
             (size_t) P.npp + 1, s));
         P.nrefs = nrefs;
         P.refs.alloc((size_t) nrefs + 16);
-        if (P.npp) {
-            k_refs_reorder<<<grid_for(P.npp, TB), TB, 0, s>>>(P.npp, P.pp_piece.p, P.pp_off.p,
+        if (nreal) {
+            k_refs_reorder<<<grid_for(nreal, TB), TB, 0, s>>>(nreal, vout.p, perm.p, P.q_off.p,
                 ch_off.p, refs.p, P.refs.p);
             TSKB_CK_LAUNCH();
         }
         TSKB_CK(cudaStreamSynchronize(s));
     }
-    P.d_poff = std::move(poff);
-
 
     // ---- sites and mutations: allele strings -> small integer codes on the host
     // (replaces the memcmp loops of get_allele_weights, trees.c:1557-1596)
@@ -1002,7 +1088,8 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
             DevArray<int32_t> d_msite;
             d_msite.upload(t->mutation_site, Mu, s);
             k_mut_src<<<grid_for(Mu, TB), TB, 0, s>>>(d_msite.p, P.mut_node.p, Mu, P.site_pos.p,
-                rank.p, P.d_poff.p, P.pc_x.p, P.mut_src.p);
+                rank.p, poff.p, pc_x.p, P.mut_src.p);
+            k_translate<<<grid_for(Mu, TB), TB, 0, s>>>(P.mut_src.p, Mu, perm.p);
             TSKB_CK_LAUNCH();
             TSKB_CK(cudaStreamSynchronize(s));
         }

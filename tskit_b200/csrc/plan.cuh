@@ -33,8 +33,11 @@
 //                    (its node's height in that tree).  Pieces of one height are independent
 //                    once the lower ones are done; there are as many dependent steps as the
 //                    tallest tree is high (39 for the C2 workload) instead of one per edge diff.
-//                    "pp" arrays list the pieces in processing order (height, piece id), every
-//                    height padded to whole tiles.
+//                    The "q_" arrays hold the pieces in processing order (height, then node-major
+//                    piece id), every height padded to whole tiles; a piece carries the breakpoints
+//                    it starts and ends at, so the branch summary adds +G / -G to the
+//                    per-breakpoint deltas of the reference's running sum (trees.c:1339-1350)
+//                    without looking at any neighbour.
 #pragma once
 
 #include <mutex>
@@ -82,18 +85,21 @@ struct Plan {
     DevArray<int32_t> ev_child;       // [nev]
     DevArray<int8_t> ev_sign;         // [nev] -1 removal, +1 insertion
     DevArray<uint32_t> voff;          // [nev + 1] visit offsets
-    // --- pieces, node-major: every node's INIT piece followed by one piece per touching breakpoint
-    uint32_t P = 0;
-    DevArray<double> pc_x;            // [P] left end of the piece (its breakpoint); -1 for INIT
-    DevArray<double> pc_bl;           // [P] branch length above the node over the piece
-    DevArray<uint32_t> d_poff;        // [N + 1] first (INIT) piece of each node rank
-    // --- processing order of the propagation: real pieces by (height, piece id)
+    // --- pieces in processing order: real pieces by (height, node-major piece id), every height
+    //     padded to whole tiles (padding: no references, zero branch length).  The state array of
+    //     a call is [npp piece states | one INIT slot per sample (its weight) | one zero slot].
+    uint32_t P = 0;                   // real + INIT pieces of the node-major construction order
     uint32_t nheights = 0, npp = 0, nrefs = 0, ntiles = 0;
-    DevArray<uint32_t> pp_piece;      // [npp] piece to compute (NO_PIECE: padding)
-    DevArray<uint32_t> pp_off;        // [npp + 1] offsets into refs
-    DevArray<uint32_t> refs;          // [nrefs] pieces whose states add up to the piece's state
+    DevArray<uint32_t> q_bp0;         // [npp] breakpoint (index into bp_pos) the piece starts at
+    DevArray<uint32_t> q_bp1;         // [npp] breakpoint it ends at: the node's next piece, or T
+                                      //       (= range_right); NO_PIECE marks padding
+    DevArray<double> bp_pos;          // [T + 1] distinct diff positions, then range_right
+    DevArray<double> q_bl;            // [npp] branch length above the node over the piece
+    DevArray<uint32_t> q_off;         // [npp + 1] offsets into refs
+    DevArray<uint32_t> refs;          // [nrefs] state slots whose values add up to the piece's state
     DevArray<uint32_t> tile_dep;      // [ntiles] first tile of the tile's height = number of tiles
                                       //  that must be complete before its gathers
+    DevArray<int32_t> d_sample_index; // [N] node -> sample index or -1
     // --- parent-major edge CSR, sorted by (parent, left); pmax = running max of right within the
     //     parent's list, which bounds the backward scan of an interval-stabbing query
     DevArray<uint32_t> pm_off;        // [N + 1]
@@ -106,7 +112,7 @@ struct Plan {
     DevArray<uint32_t> site_moff;     // [S + 1] mutation CSR
     DevArray<uint32_t> site_aoff;     // [S + 1] allele-slot CSR
     DevArray<int32_t> mut_node;       // [Mu]
-    DevArray<int32_t> mut_src;        // [Mu] piece holding state[mutation.node] at the site
+    DevArray<int32_t> mut_src;        // [Mu] state slot holding state[mutation.node] at the site
     DevArray<uint16_t> mut_allele;    // [Mu] allele index of the derived state
     DevArray<uint16_t> mut_alt;       // [Mu] allele index the mutation's state is subtracted from
     std::vector<double> h_site_pos;

@@ -3,11 +3,12 @@
 //
 // Phases of one call (all on the plan's stream):
 //   0 weights    sample sets -> 0/1 int32 weight rows per node          (trees.c:2195-2213)
-//   1 propagate  ONE launch: addend gather + segmented prefix sum over the node-major addend
-//                lists = state[u] over every piece; tiles of a level wait on a completion
-//                counter for the levels below                           (trees.c:1317-1327)
-//   2 summary    branch: stream the pieces, G = branch_length * f(state), bin G - G_prev into
-//                the window holding the piece's left end                (trees.c:1339-1350, 1484-1504)
+//   1 sweep      ONE launch: state[u] over every piece = sum of the states it references; tiles of
+//                a height wait on a completion counter for the heights below
+//                                                                       (trees.c:1317-1327)
+//                branch: the same launch turns every piece into window contributions
+//                G = branch_length * f(state) over [x, xe)              (trees.c:1339-1350, 1484-1504)
+//   2 summary    branch: only when the window bins do not fit shared memory (second pass)
 //                site:   per site, allele states and sum of f           (trees.c:1525-1652)
 //   3 finalize   branch: prefix over windows + span-normalise; site: window sums
 //                                                                       (trees.c:1753-1762, 1920-1934)
@@ -62,6 +63,7 @@ struct SumP {
     int K;
     int M;
     int polarised;
+    int skip_zero_bl;       // every summary value is finite: pieces with zero branch length add nothing
     double n[8];            // sample set sizes
     const ColP *cols;       // device [M]
     const double *table;    // device [rows * M] (STAT_TABULATED)
@@ -162,26 +164,86 @@ __device__ __forceinline__ double F_branch(const SumP &P, const ColP &c, int m, 
 
 // ---------------------------------------------------------------- phase 0
 
+// sample sets -> 0/1 weight columns of the samples' INIT slots (trees.c:2195-2213)
 template <int KP>
 __global__ void k_set_weights(const int32_t *sets, const uint32_t *set_off, uint32_t K,
-    uint32_t total, IVec<KP> *w) {
+    uint32_t total, const int32_t *sample_index, IVec<KP> *init) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= total) return;
     uint32_t k = upper_bound_dev(set_off, K + 1, j) - 1;
     // a sample may be in several sets (trees.c:2201-2214): distinct columns, no race
-    w[sets[j]].v[k] = 1;
+    init[sample_index[sets[j]]].v[k] = 1;
 }
 
-// ---------------------------------------------------------------- phase 1
+// ---------------------------------------------------------------- branch-mode running sum
+// The reference keeps a running sum  S = sum over nodes of branch_length[u] * F(state[u]),
+// updates it at every edge diff, and adds S * (distance to the next breakpoint or window edge) to
+// the current window (trees.c:1339-1350, 1424-1507).  Here every piece [bp0, bp1) of a node adds
+// +G at breakpoint bp0 and -G at breakpoint bp1, G = branch_length * F(state), to the array D of
+// per-breakpoint deltas of S (native fp64 reductions in L2, spread over millions of addresses:
+// no shared-memory compare-and-swap loops, no window lookup per piece).  S is the prefix sum of D
+// and the windows integrate S (k_window_integrate).  NaN/inf summary values behave as in the
+// reference: S is NaN from the breakpoint that first meets one.
+
+struct DeltaOut {
+    double *D;        // [M][Tp1]
+    uint32_t Tp1;     // breakpoints + 1 (slot T = end of the range)
+    const ColP *cols; // [M]
+};
+
+// the NP pieces one thread holds (lane-adjacent in the processing order) -> D, columns outermost
+// (one column in registers at a time).  Where a piece ends at the breakpoint the next lane's
+// piece starts at -- consecutive pieces of one node, mostly -- the two reductions to that
+// address are merged into one of G_next - G (the reference's "subtract the old summary, add the
+// new one" of one node at one breakpoint).  Must be called by all 32 lanes of a warp.
+template <int STAT, int KP, int NP>
+__device__ __forceinline__ void pieces_to_deltas(const SumP &sp, const IVec<KP> &totals,
+    const IVec<KP> (&st)[NP], const double (&bl)[NP], const uint32_t (&bp0)[NP],
+    const uint32_t (&bp1)[NP], const DeltaOut &out, uint32_t m0, uint32_t m1) {
+    const uint32_t lane = threadIdx.x & 31u;
+    bool valid[NP], live[NP], merge_next[NP], merged_prev[NP];
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        valid[q] = bp1[q] != NO_PIECE;  // not padding of the processing order
+        // when every summary value is finite, roots and detached nodes add nothing: 0 * f (with
+        // NaN/inf summaries 0 * f is NaN in the reference too, trees.c:1339-1350: kept then)
+        live[q] = valid[q] && !(sp.skip_zero_bl && bl[q] == 0.0);
+        const uint32_t next_bp0 = __shfl_down_sync(0xffffffffu, bp0[q], 1);
+        const uint32_t prev_bp1 = __shfl_up_sync(0xffffffffu, bp1[q], 1);
+        const bool next_valid = __shfl_down_sync(0xffffffffu, (int) valid[q], 1) != 0;
+        merge_next[q] = valid[q] && lane < 31u && next_valid && next_bp0 == bp1[q];
+        merged_prev[q] = valid[q] && lane > 0u && prev_bp1 == bp0[q];  // prev_bp1 of padding never matches
+    }
+    for (uint32_t m = m0; m < m1; m++) {
+        const ColP col = out.cols[m];
+        double *Dm = out.D + (size_t) (m - m0) * out.Tp1;
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            double G = 0.0;
+            if (live[q]) G = bl[q] * F_branch<STAT, KP>(sp, col, m, st[q], totals);
+            const double G_next = __shfl_down_sync(0xffffffffu, G, 1);
+            if (!valid[q]) continue;
+            if (!merged_prev[q] && G != 0.0) atomicAdd(Dm + bp0[q], G);
+            const double v = merge_next[q] ? G_next - G : -G;
+            if (v != 0.0) atomicAdd(Dm + bp1[q], v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- phase 1 (+ 2, branch mode)
 // state[u] over every piece (what update_state, trees.c:1317-1327, maintains incrementally):
-// a piece's state is the sum of the states of the pieces it references -- its children in the
-// tree right of its breakpoint, plus its own INIT piece (the sample weight, trees.c:1406-1415).
+// a piece's state is the sum of the states it references -- its children in the tree right of
+// its breakpoint, plus its own INIT slot (the sample weight, trees.c:1406-1415).
 // Pieces are processed by height; one cooperative launch of co-resident persistent CTAs covers
 // every height.  CTA b takes tiles b, b + G, ...; a tile loads its references, then waits on
 // the completion counter until every tile of the lower heights has published its states
-// (red.release / ld.acquire at gpu scope), gathers, sums and stores.  Every CTA processes its
-// tiles in increasing order and a tile only waits on lower-numbered tiles, so the lowest
-// unfinished tile can always run: no deadlock.  Integer sums: exact in any order.
+// (red.release / ld.acquire at gpu scope), gathers, sums, stores (coalesced: the state slot of a
+// piece is its processing position) and publishes.  Every CTA processes its tiles in increasing
+// order and a tile only waits on lower-numbered tiles, so the lowest unfinished tile can always
+// run: no deadlock.  Integer sums: exact in any order.
+// FUSE: after publishing, the tile's pieces are turned into window contributions straight from
+// registers (shared-memory bins, flushed once per CTA) -- the branch summary costs no second
+// pass over the states.
 
 template <int KP>
 __device__ __forceinline__ IVec<KP> state_load(const IVec<KP> *p) {
@@ -224,36 +286,56 @@ constexpr int PROP_IPT = PROP_TILE / PROP_TB;
 constexpr int PROP_PRE = 3;  // references fetched before the wait; more are rare (multifurcations)
 constexpr uint32_t SPIN_LIMIT = 1u << 22;  // ~seconds; a legitimate wait is < the kernel's own run time
 
-template <int KP>
-__global__ void __launch_bounds__(PROP_TB) k_propagate(uint32_t ntiles,
-    const uint32_t *__restrict__ tile_dep, const uint32_t *__restrict__ pp_piece,
-    const uint32_t *__restrict__ pp_off, const uint32_t *__restrict__ refs, IVec<KP> *pval,
-    uint32_t *counters, int *error_flag, unsigned long long *trace) {
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+struct SweepArgs {
+    uint32_t ntiles;
+    const uint32_t *tile_dep, *q_off, *refs;
+    uint32_t *counters;
+    int *error_flag;
+    unsigned long long *trace;
+    // FUSE only
+    const uint32_t *q_bp0, *q_bp1;
+    const double *q_bl;
+    DeltaOut out;
+};
+
+template <int STAT, int KP, bool FUSE>
+__global__ void __launch_bounds__(PROP_TB, (FUSE && KP <= 2) ? 4 : 1) k_sweep(SweepArgs a, IVec<KP> *pval, SumP sp,
+    IVec<KP> totals) {
+    unsigned long long *trace = a.trace;
+    for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         TRACE(0);
-        const uint32_t dep = __ldg(tile_dep + tile);
-        uint32_t piece[PROP_IPT], o0[PROP_IPT], o1[PROP_IPT], rf[PROP_IPT][PROP_PRE];
+        const uint32_t dep = __ldg(a.tile_dep + tile);
+        const uint32_t j0 = tile * PROP_TILE + threadIdx.x;
+        uint32_t o0[PROP_IPT], o1[PROP_IPT], rf[PROP_IPT][PROP_PRE];
         // everything that does not depend on other tiles is fetched before the wait
+        double bl[PROP_IPT];
+        uint32_t bp0[PROP_IPT], bp1[PROP_IPT];
 #pragma unroll
         for (int q = 0; q < PROP_IPT; q++) {
-            const uint32_t j = tile * PROP_TILE + q * PROP_TB + threadIdx.x;
-            piece[q] = __ldg(pp_piece + j);
-            o0[q] = __ldg(pp_off + j);
-            o1[q] = __ldg(pp_off + j + 1);
+            o0[q] = __ldg(a.q_off + j0 + q * PROP_TB);
+            o1[q] = __ldg(a.q_off + j0 + q * PROP_TB + 1);
+            if (FUSE) {
+                bl[q] = __ldg(a.q_bl + j0 + q * PROP_TB);
+                bp0[q] = __ldg(a.q_bp0 + j0 + q * PROP_TB);
+                bp1[q] = __ldg(a.q_bp1 + j0 + q * PROP_TB);
+                // a piece without a branch above it is no other piece's child over its span, and
+                // with finite summaries it adds nothing itself: its state is not needed
+                if (sp.skip_zero_bl && bl[q] == 0.0) o1[q] = o0[q];
+            }
         }
 #pragma unroll
         for (int q = 0; q < PROP_IPT; q++) {
 #pragma unroll
             for (int i = 0; i < PROP_PRE; i++) {
-                rf[q][i] = o0[q] + i < o1[q] ? __ldg(refs + o0[q] + i) : NO_PIECE;
+                rf[q][i] = o0[q] + i < o1[q] ? __ldg(a.refs + o0[q] + i) : NO_PIECE;
             }
         }
         if (dep > 0) {
             if (threadIdx.x == 0) {
                 uint32_t spins = 0;
-                while (ld_acquire(counters + 1) < dep) {
-                    if (++spins > SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int *) error_flag)) {
-                        *error_flag = 1;
+                while (ld_acquire(a.counters + 1) < dep) {
+                    if (++spins > SPIN_LIMIT || ((spins & 1023u) == 0 && *(volatile int *) a.error_flag)) {
+                        *a.error_flag = 1;
                         break;
                     }
                 }
@@ -271,207 +353,84 @@ __global__ void __launch_bounds__(PROP_TB) k_propagate(uint32_t ntiles,
             }
         }
         TRACE(2);
+        IVec<KP> sum[PROP_IPT];
 #pragma unroll
         for (int q = 0; q < PROP_IPT; q++) {
-            IVec<KP> sum = g[q][0];
+            sum[q] = g[q][0];
 #pragma unroll
-            for (int i = 1; i < PROP_PRE; i++) sum = sum + g[q][i];
+            for (int i = 1; i < PROP_PRE; i++) sum[q] = sum[q] + g[q][i];
             for (uint32_t o = o0[q] + PROP_PRE; o < o1[q]; o++) {
-                sum = sum + state_load<KP>(pval + __ldg(refs + o));
+                sum[q] = sum[q] + state_load<KP>(pval + __ldg(a.refs + o));
             }
-            if (piece[q] != NO_PIECE) pval[piece[q]] = sum;
+            pval[j0 + q * PROP_TB] = sum[q];
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            red_release_add(counters + 1, 1u);
+            red_release_add(a.counters + 1, 1u);
             if (trace != nullptr) trace[(size_t) tile * 4 + 3] = gtime();
         }
+        if (FUSE) {
+            pieces_to_deltas<STAT, KP, PROP_IPT>(sp, totals, sum, bl, bp0, bp1, a.out, 0, (uint32_t) sp.M);
+        }
     }
 }
 
-// INIT pieces hold the node's own sample weight (trees.c:1406-1415)
-template <int KP>
-__global__ void k_init_pieces(const IVec<KP> *__restrict__ w, const int32_t *__restrict__ rank_node,
-    const uint32_t *__restrict__ poff, uint32_t N, IVec<KP> *pval) {
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < N) pval[poff[r]] = w[rank_node[r]];
-}
-
-// ---------------------------------------------------------------- phase 2, branch mode
-// Node u contributes  sum over its pieces of  G = branch_length * F(state)  times the overlap
-// of the piece with each window.  A piece ends where the next one starts, so this is the sum
-// over pieces of (G - G_prev) * |[x, range_right) ^ window|: every piece adds
-//   c = G - G_prev   to A[w(x)]  (all windows right of w(x) gain c * their span) and
-//   c * (right(w(x)) - x)  to B[w(x)].
-// This is the reference's running sum (trees.c:1339-1350, 1484-1504) with the updates of one
-// node at one breakpoint telescoped.
+// ---------------------------------------------------------------- phase 2, branch mode, unfused
+// Used when the delta arrays of all columns would be too large at once: the states are streamed
+// once more per chunk of columns (fully coalesced).
 
 constexpr int SUM_IPT = 4;
-constexpr int SUM_TILE = TB * SUM_IPT;   // pc_x / pc_bl / pval are padded to whole tiles
-constexpr uint32_t LUT_CELLS = 2048;     // uniform cells over the genome -> window index
+constexpr int SUM_TILE = TB * SUM_IPT;   // PROP_TILE: the processing order is padded to whole tiles
 
-// window holding x: start from the lookup cell, then walk (windows are sorted; exact for any
-// window layout, one step for evenly spaced windows)
-__device__ __forceinline__ uint32_t window_of(const double *win, const uint16_t *lut, uint32_t W,
-    double x, double inv_cell) {
-    uint32_t g = (uint32_t) (x * inv_cell);
-    if (g >= LUT_CELLS) g = LUT_CELLS - 1;
-    uint32_t u = lut[g];
-    while (u > 0 && x < win[u]) u--;
-    while (u + 1 < W && x >= win[u + 1]) u++;
-    return u;
-}
-
-template <int STAT, int KP, bool SMEM>
-__global__ void __launch_bounds__(TB, SMEM ? 4 : 2) k_branch_summary(uint32_t ntiles,
-    const double *__restrict__ pc_x, const double *__restrict__ pc_bl,
-    const IVec<KP> *__restrict__ pval, SumP sp, IVec<KP> totals,
-    const double *__restrict__ windows, uint32_t W, double range_right, uint32_t mc, double *gA,
-    double *gB) {
-    extern __shared__ double smem[];
-    double *s_win = smem;                              // [W + 1]
-    double *s_bins = smem + (W + 1);                   // [mc][W][2]: A, B interleaved
-    uint16_t *s_lut = reinterpret_cast<uint16_t *>(s_bins + (SMEM ? 2 * mc * W : 0));
-    const uint32_t m0 = blockIdx.y * mc;
-    const uint32_t m1 = min(m0 + mc, (uint32_t) sp.M);
-    double inv_cell = 0.0;
-    if (SMEM) {
-        for (uint32_t i = threadIdx.x; i <= W; i += TB) s_win[i] = windows[i];
-        for (uint32_t i = threadIdx.x; i < 2 * mc * W; i += TB) s_bins[i] = 0.0;
-        __syncthreads();
-        const double cell = (s_win[W] - s_win[0]) / (double) LUT_CELLS;
-        inv_cell = 1.0 / cell;
-        for (uint32_t g = threadIdx.x; g < LUT_CELLS; g += TB) {
-            uint32_t u = upper_bound_dev(s_win, W + 1, s_win[0] + g * cell);
-            u = u > 0 ? u - 1 : 0;
-            s_lut[g] = (uint16_t) (u < W ? u : W - 1);
-        }
-        __syncthreads();
-    }
+template <int STAT, int KP>
+__global__ void __launch_bounds__(TB) k_branch_summary(uint32_t ntiles,
+    const uint32_t *__restrict__ q_bp0, const uint32_t *__restrict__ q_bp1,
+    const double *__restrict__ q_bl, const IVec<KP> *__restrict__ pval, SumP sp, IVec<KP> totals,
+    DeltaOut out, uint32_t m0, uint32_t m1) {
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t first = tile * SUM_TILE + threadIdx.x * SUM_IPT;
-        double x[SUM_IPT], bl[SUM_IPT + 1];
-        IVec<KP> s[SUM_IPT + 1];
-        {
-            const double2 *qx = reinterpret_cast<const double2 *>(pc_x + first);
-            const double2 *qb = reinterpret_cast<const double2 *>(pc_bl + first);
-#pragma unroll
-            for (int q = 0; q < SUM_IPT / 2; q++) {
-                double2 t = qx[q];
-                x[2 * q] = t.x; x[2 * q + 1] = t.y;
-                t = qb[q];
-                bl[2 * q + 1] = t.x; bl[2 * q + 2] = t.y;
-            }
-            const int4 *qs = reinterpret_cast<const int4 *>(pval + first);
-            int flat[SUM_IPT * KP];
-#pragma unroll
-            for (int q = 0; q < KP; q++) {
-                int4 t = qs[q];
-                flat[4 * q] = t.x; flat[4 * q + 1] = t.y; flat[4 * q + 2] = t.z; flat[4 * q + 3] = t.w;
-            }
-#pragma unroll
-            for (int q = 0; q < SUM_IPT; q++) {
-#pragma unroll
-                for (int k = 0; k < KP; k++) s[q + 1].v[k] = flat[q * KP + k];
-            }
-        }
-        // predecessor of the first item (same node unless that item is an INIT piece)
-        bool prev_real = false;
-        s[0] = ivec_zero<KP>();
-        bl[0] = 0.0;
-        if (first > 0 && x[0] >= 0.0) {
-            prev_real = pc_x[first - 1] >= 0.0;
-            bl[0] = pc_bl[first - 1];
-            s[0] = pval[first - 1];
-        }
-        uint32_t wi[SUM_IPT];
-        double rem[SUM_IPT];
+        IVec<KP> st[SUM_IPT];
+        double bl[SUM_IPT];
+        uint32_t bp0[SUM_IPT], bp1[SUM_IPT];
 #pragma unroll
         for (int q = 0; q < SUM_IPT; q++) {
-            wi[q] = 0;
-            rem[q] = 0.0;
-            if (x[q] >= 0.0) {
-                uint32_t u;
-                double wr;
-                if (SMEM) {
-                    u = window_of(s_win, s_lut, W, x[q], inv_cell);
-                    wr = s_win[u + 1];
-                } else {
-                    u = upper_bound_dev(windows, W + 1, x[q]);
-                    u = u > 0 ? u - 1 : 0;
-                    if (u >= W) u = W - 1;
-                    wr = windows[u + 1];
-                }
-                wi[q] = u;
-                rem[q] = (wr < range_right ? wr : range_right) - x[q];
-            }
+            const uint32_t j = tile * SUM_TILE + q * TB + threadIdx.x;
+            st[q] = pval[j]; bl[q] = q_bl[j]; bp0[q] = q_bp0[j]; bp1[q] = q_bp1[j];
         }
-        for (uint32_t m = m0; m < m1; m++) {
-            const ColP col = sp.cols[m];
-            double prevG = prev_real ? bl[0] * F_branch<STAT, KP>(sp, col, m, s[0], totals) : 0.0;
-            double *binm = SMEM ? s_bins + 2 * (m - m0) * W : nullptr;
-#pragma unroll
-            for (int q = 0; q < SUM_IPT; q++) {
-                if (x[q] < 0.0) {  // INIT piece (or padding): the node is not in any tree yet
-                    prevG = 0.0;
-                    continue;
-                }
-                double G = bl[q + 1] * F_branch<STAT, KP>(sp, col, m, s[q + 1], totals);
-                double c = G - prevG;
-                prevG = G;
-                if (c != 0.0) {
-                    if (SMEM) {
-                        atomicAdd(binm + 2 * wi[q], c);
-                        atomicAdd(binm + 2 * wi[q] + 1, c * rem[q]);
-                    } else {
-                        atomicAdd(&gA[(size_t) m * W + wi[q]], c);
-                        atomicAdd(&gB[(size_t) m * W + wi[q]], c * rem[q]);
-                    }
-                }
-            }
-        }
-    }
-    if (SMEM) {
-        __syncthreads();
-        const uint32_t cols = m1 - m0;
-        for (uint32_t i = threadIdx.x; i < cols * W; i += TB) {
-            uint32_t m = m0 + i / W, wdx = i % W;
-            double a = s_bins[2 * i], b = s_bins[2 * i + 1];
-            if (a != 0.0) atomicAdd(&gA[(size_t) m * W + wdx], a);
-            if (b != 0.0) atomicAdd(&gB[(size_t) m * W + wdx], b);
-        }
+        pieces_to_deltas<STAT, KP, SUM_IPT>(sp, totals, st, bl, bp0, bp1, out, m0, m1);
     }
 }
 
-// result[w][m] = (sum of A[m][w'] over w' < w) * |window ^ range| + B[m][w], span-normalised
-// (trees.c:1920-1934).  One block per column, windows in chunks with a running carry.
-__global__ void __launch_bounds__(TB) k_branch_finalize(const double *gA, const double *gB,
-    const double *windows, uint32_t W, uint32_t M, double range_left, double range_right,
-    int span_normalise, double *result) {
-    typedef cub::BlockScan<double, TB> BS;
-    __shared__ typename BS::TempStorage tmp;
-    __shared__ double s_carry;
-    const uint32_t m = blockIdx.x;
-    if (threadIdx.x == 0) s_carry = 0.0;
-    __syncthreads();
-    for (uint32_t base = 0; base < W; base += TB) {
-        uint32_t wdx = base + threadIdx.x;
-        double a = wdx < W ? gA[(size_t) m * W + wdx] : 0.0;
-        double ex, total;
-        BS(tmp).ExclusiveSum(a, ex, total);
-        double carry = s_carry;
-        if (wdx < W) {
-            double wl = windows[wdx], wr = windows[wdx + 1];
-            double l = wl > range_left ? wl : range_left;
-            double r = wr < range_right ? wr : range_right;
-            double v = 0.0;
-            if (r > l) v = (carry + ex) * (r - l) + gB[(size_t) m * W + wdx];
-            if (span_normalise) v /= wr - wl;
-            result[(size_t) wdx * M + m] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_carry = carry + total;
-        __syncthreads();
+// ---------------------------------------------------------------- phase 3, branch mode
+// S = inclusive prefix sum of D over the breakpoints (the reference's running sum after the diffs
+// of breakpoint i, cub::DeviceScan per column); window w gets the integral of S over it:
+// sum over the breakpoint intervals [t_i, t_i+1) that meet it of S_i * overlap
+// (trees.c:1484-1504), span-normalised (trees.c:1920-1934).  One warp per (window, column).
+__global__ void __launch_bounds__(TB) k_window_integrate(const double *S, uint32_t Tp1,
+    const double *__restrict__ bp_pos, const double *__restrict__ windows, uint32_t W, uint32_t mcols,
+    uint32_t m0, uint32_t M, int span_normalise, double *result) {
+    const uint32_t T = Tp1 - 1;
+    const uint32_t lane = threadIdx.x & 31u;
+    const size_t warp = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= (size_t) W * mcols) return;
+    const uint32_t w = (uint32_t) (warp / mcols), mloc = (uint32_t) (warp % mcols);
+    const double wl = windows[w], wr = windows[w + 1];
+    const double *Sm = S + (size_t) mloc * Tp1;
+    // intervals meeting [wl, wr): from the one holding wl (or the first) to the last starting < wr
+    uint32_t lo = upper_bound_dev(bp_pos, T, wl);
+    lo = lo > 0 ? lo - 1 : 0;
+    const uint32_t hi = lower_bound_dev(bp_pos, T, wr);
+    double acc = 0.0;
+    for (uint32_t i = lo + lane; i < hi; i += 32) {
+        double a = bp_pos[i], b = bp_pos[i + 1];
+        a = a > wl ? a : wl;
+        b = b < wr ? b : wr;
+        if (b > a) acc += Sm[i] * (b - a);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    if (lane == 0) {
+        if (span_normalise) acc /= wr - wl;
+        result[(size_t) w * M + m0 + mloc] = acc;
     }
 }
 
@@ -587,7 +546,7 @@ __global__ void k_count_at(const int32_t *tracked, uint32_t nt, uint32_t nq, uin
 
 // ---------------------------------------------------------------- driver
 
-constexpr size_t SMEM_BIN_BUDGET = 96 * 1024;
+constexpr size_t DELTA_BUDGET = size_t(1) << 30;   // bytes of per-breakpoint deltas held at once
 
 struct CallCtx {
     const Plan *P;
@@ -596,56 +555,105 @@ struct CallCtx {
     SumP sumP;
     double *d_windows;
     double *d_result;
+    int *d_err;
     uint64_t launches;
 };
 
-template <int STAT, int KP>
-void launch_branch(CallCtx &c, const IVec<KP> *pval, IVec<KP> totals) {
+template <int STAT, int KP, bool FUSE>
+void launch_sweep(CallCtx &c, IVec<KP> *pval, IVec<KP> totals, DeltaOut out) {
+    const Plan &P = *c.P;
+    Arena &A = P.arena;
+    if (P.ntiles == 0) return;
+    uint32_t *counters = A.get<uint32_t>(2);
+    TSKB_CK(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), c.s));
+    unsigned long long *trace = nullptr;
+    if (getenv("TSKB_TRACE") != nullptr) {
+        trace = A.get<unsigned long long>((size_t) P.ntiles * 4);
+        TSKB_CK(cudaMemsetAsync(trace, 0, (size_t) P.ntiles * 4 * sizeof(unsigned long long), c.s));
+        P.stats_trace = trace;
+    }
+    auto kern = k_sweep<STAT, KP, FUSE>;
+    int per_sm = 1, sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
+    TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PROP_TB, 0));
+    const uint32_t grid = std::min<uint32_t>(P.ntiles, (uint32_t) (sms * std::max(per_sm, 1)));
+    SweepArgs a = {};
+    a.ntiles = P.ntiles;
+    a.tile_dep = P.tile_dep.p; a.q_off = P.q_off.p; a.refs = P.refs.p;
+    a.counters = counters; a.error_flag = c.d_err; a.trace = trace;
+    a.q_bp0 = P.q_bp0.p; a.q_bp1 = P.q_bp1.p; a.q_bl = P.q_bl.p;
+    a.out = out;
+    void *args[] = { &a, &pval, &c.sumP, &totals };
+    TSKB_CK(cudaLaunchCooperativeKernel((const void *) kern, dim3(grid), dim3(PROP_TB), args, 0, c.s));
+    c.launches++;
+}
+
+// D (deltas of mcols columns) -> running sums -> window integrals of columns [m0, m0 + mcols)
+inline void finish_columns(CallCtx &c, double *D, uint32_t Tp1, uint32_t m0, uint32_t mcols,
+    void *scan_tmp, size_t scan_bytes) {
     const Plan &P = *c.P;
     const uint32_t W = c.sp->W, M = c.sp->M;
-    Arena &A = P.arena;
-    double *gA = A.get<double>((size_t) 2 * M * W);
-    double *gB = gA + (size_t) M * W;
-    TSKB_CK(cudaMemsetAsync(gA, 0, (size_t) 2 * M * W * sizeof(double), c.s));
-    const uint32_t ntiles = (P.P + SUM_TILE - 1) / SUM_TILE;  // plan arrays are padded to this
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
-    const size_t win_bytes = (size_t) (W + 1) * sizeof(double) + LUT_CELLS * sizeof(uint16_t);
-    const size_t col_bytes = (size_t) 2 * W * sizeof(double);
-    if (P.P > 0) {
-        if (win_bytes + col_bytes <= SMEM_BIN_BUDGET && W < 65536) {
-            uint32_t mc = (uint32_t) std::min<size_t>(M, (SMEM_BIN_BUDGET - win_bytes) / col_bytes);
-            uint32_t chunks = (M + mc - 1) / mc;
-            size_t smem = win_bytes + mc * col_bytes;
-            auto kern = k_branch_summary<STAT, KP, true>;
-            TSKB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            int per_sm = 1;
-            TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, smem));
-            uint32_t gx = std::min<uint32_t>(ntiles, (uint32_t) (sms * std::max(per_sm, 1)));
-            kern<<<dim3(gx, chunks), TB, smem, c.s>>>(ntiles, P.pc_x.p, P.pc_bl.p, pval, c.sumP, totals,
-                c.d_windows, W, P.range_right, mc, gA, gB);
-        } else {
-            auto kern = k_branch_summary<STAT, KP, false>;
-            uint32_t gx = std::min<uint32_t>(ntiles, (uint32_t) sms * 8);
-            kern<<<dim3(gx, 1), TB, 0, c.s>>>(ntiles, P.pc_x.p, P.pc_bl.p, pval, c.sumP, totals,
-                c.d_windows, W, P.range_right, M, gA, gB);
-        }
-        TSKB_CK_LAUNCH();
+    for (uint32_t m = 0; m < mcols && Tp1 > 1; m++) {
+        double *Dm = D + (size_t) m * Tp1;
+        TSKB_CK(cub::DeviceScan::InclusiveSum(scan_tmp, scan_bytes, Dm, Dm, (int) (Tp1 - 1), c.s));
         c.launches++;
     }
-    TSKB_CK(cudaEventRecord(P.ev[3], c.s));
-    k_branch_finalize<<<M, TB, 0, c.s>>>(gA, gB, c.d_windows, W, M, P.range_left, P.range_right,
-        (c.sp->options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0, c.d_result);
+    const size_t warps = (size_t) W * mcols;
+    k_window_integrate<<<grid_for(warps * 32, TB), TB, 0, c.s>>>(D, Tp1, P.bp_pos.p, c.d_windows, W,
+        mcols, m0, M, (c.sp->options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0, c.d_result);
     TSKB_CK_LAUNCH();
     c.launches++;
+}
+
+template <int STAT, int KP>
+void run_branch(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
+    const Plan &P = *c.P;
+    const uint32_t M = c.sp->M;
+    Arena &A = P.arena;
+    const uint32_t Tp1 = P.T + 1;
+    const size_t col_bytes = (size_t) Tp1 * sizeof(double);
+    const uint32_t mc = (uint32_t) std::min<size_t>(M, std::max<size_t>(1, DELTA_BUDGET / col_bytes));
+    double *D = A.get<double>((size_t) mc * Tp1);
+    size_t scan_bytes = 0;
+    TSKB_CK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, D, D, (int) std::max<uint32_t>(Tp1 - 1, 1), c.s));
+    void *scan_tmp = A.get<char>(scan_bytes);
+    DeltaOut out = { D, Tp1, c.sumP.cols };
+    const bool fuse = mc == M && getenv("TSKB_NO_FUSE") == nullptr;
+    if (fuse) {
+        TSKB_CK(cudaMemsetAsync(D, 0, (size_t) mc * col_bytes, c.s));
+        launch_sweep<STAT, KP, true>(c, pval, totals, out);
+        TSKB_CK(cudaEventRecord(P.ev[2], c.s));
+        TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+        finish_columns(c, D, Tp1, 0, M, scan_tmp, scan_bytes);
+    } else {
+        launch_sweep<0, KP, false>(c, pval, totals, out);
+        TSKB_CK(cudaEventRecord(P.ev[2], c.s));
+        const uint32_t ntiles = P.npp / SUM_TILE;
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
+        for (uint32_t m0 = 0; m0 < M; m0 += mc) {
+            const uint32_t m1 = std::min(M, m0 + mc);
+            TSKB_CK(cudaMemsetAsync(D, 0, (size_t) (m1 - m0) * col_bytes, c.s));
+            if (ntiles > 0) {
+                k_branch_summary<STAT, KP><<<std::min<uint32_t>(ntiles, (uint32_t) sms * 8), TB, 0, c.s>>>(
+                    ntiles, P.q_bp0.p, P.q_bp1.p, P.q_bl.p, pval, c.sumP, totals, out, m0, m1);
+                TSKB_CK_LAUNCH();
+                c.launches++;
+            }
+            finish_columns(c, D, Tp1, m0, m1 - m0, scan_tmp, scan_bytes);
+        }
+        TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+    }
     TSKB_CK(cudaEventRecord(P.ev[4], c.s));
 }
 
 template <int STAT, int KP>
-void launch_site(CallCtx &c, const IVec<KP> *pval, IVec<KP> totals) {
+void run_site(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
     const Plan &P = *c.P;
     const uint32_t W = c.sp->W, M = c.sp->M;
     Arena &A = P.arena;
+    launch_sweep<0, KP, false>(c, pval, totals, DeltaOut{});
+    TSKB_CK(cudaEventRecord(P.ev[2], c.s));
     const uint32_t nsites = P.site_hi - P.site_lo;
     const uint32_t nsplit = std::max<uint32_t>(1, (592 + W - 1) / W);
     double *partial = A.get<double>((size_t) W * nsplit * M);
@@ -670,18 +678,18 @@ void launch_site(CallCtx &c, const IVec<KP> *pval, IVec<KP> totals) {
 }
 
 template <int STAT, int KP>
-void launch_summary(CallCtx &c, const IVec<KP> *pval, IVec<KP> totals) {
+void run_phases(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
     if (c.sp->options & TSKB_STAT_BRANCH) {
-        launch_branch<STAT, KP>(c, pval, totals);
+        run_branch<STAT, KP>(c, pval, totals);
     } else {
-        launch_site<STAT, KP>(c, pval, totals);
+        run_site<STAT, KP>(c, pval, totals);
     }
 }
 
 template <int KP>
 int run_impl(const Plan &P, const StatSpec &sp) {
     cudaStream_t s = P.stream;
-    const uint32_t K = sp.K, M = sp.M, W = sp.W, N = (uint32_t) P.N;
+    const uint32_t K = sp.K, M = sp.M, W = sp.W;
     Arena &A = P.arena;
     A.reset();
     CallCtx c = {};
@@ -690,14 +698,15 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     c.s = s;
     TSKB_CK(cudaEventRecord(P.ev[0], s));
 
-    // ---- phase 0: weights
+    // ---- phase 0: weights.  State slots: [npp pieces | one INIT slot per sample | zero slot]
     uint64_t total = 0;
     std::vector<uint32_t> h_off(K + 1, 0);
     for (uint32_t k = 0; k < K; k++) {
         total += sp.sizes[k];
         h_off[k + 1] = (uint32_t) total;
     }
-    IVec<KP> *w = A.get<IVec<KP>>(N);
+    IVec<KP> *pval = A.get<IVec<KP>>((size_t) P.npp + P.num_samples + 1);
+    IVec<KP> *init = pval + P.npp;
     uint32_t *d_off = A.get<uint32_t>(K + 1);
     const int32_t *d_sets = sp.sets;
     if (!sp.sets_on_device) {
@@ -708,15 +717,19 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     TSKB_CK(cudaMemcpyAsync(d_off, h_off.data(), (K + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     c.d_windows = A.get<double>(W + 1);
     TSKB_CK(cudaMemcpyAsync(c.d_windows, sp.windows, (W + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
-    TSKB_CK(cudaMemsetAsync(w, 0, (size_t) N * sizeof(IVec<KP>), s));
-    k_set_weights<KP><<<grid_for(total, TB), TB, 0, s>>>(d_sets, d_off, K, (uint32_t) total, w);
-    TSKB_CK_LAUNCH();
-    c.launches++;
+    TSKB_CK(cudaMemsetAsync(init, 0, ((size_t) P.num_samples + 1) * sizeof(IVec<KP>), s));
+    if (total) {
+        k_set_weights<KP><<<grid_for(total, TB), TB, 0, s>>>(d_sets, d_off, K, (uint32_t) total,
+            P.d_sample_index.p, init);
+        TSKB_CK_LAUNCH();
+        c.launches++;
+    }
 
     SumP &sumP = c.sumP;
     sumP.K = (int) K;
     sumP.M = (int) M;
     sumP.polarised = (sp.options & TSKB_STAT_POLARISED) ? 1 : 0;
+    sumP.skip_zero_bl = 1;
     IVec<KP> totals;
     for (int k = 0; k < KP; k++) totals.v[k] = 0;
     for (uint32_t k = 0; k < K; k++) {
@@ -734,6 +747,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
             q.ni = (double) sp.sizes[t[0]]; q.nj = (double) sp.sizes[t[1]];
             q.nk = (double) sp.sizes[t[2]]; q.nl = (double) sp.sizes[t[3]];
             q.inv = 1.0 / column_denominator(sp.stat_id, q);
+            if (!std::isfinite(q.inv)) sumP.skip_zero_bl = 0;
         }
         ColP *d_cols = A.get<ColP>(M);
         TSKB_CK(cudaMemcpyAsync(d_cols, cols.data(), M * sizeof(ColP), cudaMemcpyHostToDevice, s));
@@ -743,60 +757,33 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         double *d_tab = A.get<double>(sp.table_rows * M);
         TSKB_CK(cudaMemcpyAsync(d_tab, sp.f_table, sp.table_rows * M * sizeof(double),
             cudaMemcpyHostToDevice, s));
+        for (uint64_t i = 0; i < sp.table_rows * M; i++) {
+            if (!std::isfinite(sp.f_table[i])) sumP.skip_zero_bl = 0;
+        }
         sumP.table = d_tab;
         sumP.table_rows = (uint32_t) sp.table_rows;
     }
+    c.d_err = A.get<int>(1);
+    TSKB_CK(cudaMemsetAsync(c.d_err, 0, sizeof(int), s));
+    c.d_result = sp.result_on_device ? sp.result : A.get<double>((size_t) W * M);
     TSKB_CK(cudaEventRecord(P.ev[1], s));
 
-    // ---- phase 1: propagate
-    IVec<KP> *pval = A.get<IVec<KP>>((size_t) P.P + 2048);  // summary tiles read whole tiles
-    int *d_err = A.get<int>(1);
-    TSKB_CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
-    if (N) {
-        k_init_pieces<KP><<<grid_for(N, TB), TB, 0, s>>>(w, P.rank_node.p, P.d_poff.p, N, pval);
-        TSKB_CK_LAUNCH();
-        c.launches++;
-    }
-    if (P.ntiles) {
-        uint32_t *counters = A.get<uint32_t>(2);
-        TSKB_CK(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
-        unsigned long long *trace = nullptr;
-        if (getenv("TSKB_TRACE") != nullptr) {
-            trace = A.get<unsigned long long>((size_t) P.ntiles * 4);
-            TSKB_CK(cudaMemsetAsync(trace, 0, (size_t) P.ntiles * 4 * sizeof(unsigned long long), s));
-            P.stats_trace = trace;
-        }
-        int per_sm = 1, sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
-        TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<KP>, PROP_TB, 0));
-        const uint32_t grid = std::min<uint32_t>(P.ntiles, (uint32_t) (sms * std::max(per_sm, 1)));
-        uint32_t a_ntiles = P.ntiles;
-        const uint32_t *a_dep = P.tile_dep.p, *a_piece = P.pp_piece.p, *a_off = P.pp_off.p,
-                       *a_refs = P.refs.p;
-        void *args[] = { &a_ntiles, &a_dep, &a_piece, &a_off, &a_refs, &pval, &counters, &d_err, &trace };
-        TSKB_CK(cudaLaunchCooperativeKernel((const void *) k_propagate<KP>, dim3(grid), dim3(PROP_TB),
-            args, 0, s));
-        c.launches++;
-    }
-    TSKB_CK(cudaEventRecord(P.ev[2], s));
-
-    // ---- phases 2-3
-    c.d_result = sp.result_on_device ? sp.result : A.get<double>((size_t) W * M);
+    // ---- phases 1-3: sweep (+ branch summary), summary, finalize
     switch (sp.stat_id) {
-        case STAT_DIVERSITY: launch_summary<STAT_DIVERSITY, KP>(c, pval, totals); break;
-        case STAT_SEGSITES: launch_summary<STAT_SEGSITES, KP>(c, pval, totals); break;
-        case STAT_Y1: launch_summary<STAT_Y1, KP>(c, pval, totals); break;
-        case STAT_DIVERGENCE: launch_summary<STAT_DIVERGENCE, KP>(c, pval, totals); break;
-        case STAT_Y2: launch_summary<STAT_Y2, KP>(c, pval, totals); break;
-        case STAT_F2: launch_summary<STAT_F2, KP>(c, pval, totals); break;
-        case STAT_RELATEDNESS: launch_summary<STAT_RELATEDNESS, KP>(c, pval, totals); break;
-        case STAT_RELATEDNESS_NC: launch_summary<STAT_RELATEDNESS_NC, KP>(c, pval, totals); break;
-        case STAT_Y3: launch_summary<STAT_Y3, KP>(c, pval, totals); break;
-        case STAT_F3: launch_summary<STAT_F3, KP>(c, pval, totals); break;
-        case STAT_F4: launch_summary<STAT_F4, KP>(c, pval, totals); break;
+        case STAT_DIVERSITY: run_phases<STAT_DIVERSITY, KP>(c, pval, totals); break;
+        case STAT_SEGSITES: run_phases<STAT_SEGSITES, KP>(c, pval, totals); break;
+        case STAT_Y1: run_phases<STAT_Y1, KP>(c, pval, totals); break;
+        case STAT_DIVERGENCE: run_phases<STAT_DIVERGENCE, KP>(c, pval, totals); break;
+        case STAT_Y2: run_phases<STAT_Y2, KP>(c, pval, totals); break;
+        case STAT_F2: run_phases<STAT_F2, KP>(c, pval, totals); break;
+        case STAT_RELATEDNESS: run_phases<STAT_RELATEDNESS, KP>(c, pval, totals); break;
+        case STAT_RELATEDNESS_NC: run_phases<STAT_RELATEDNESS_NC, KP>(c, pval, totals); break;
+        case STAT_Y3: run_phases<STAT_Y3, KP>(c, pval, totals); break;
+        case STAT_F3: run_phases<STAT_F3, KP>(c, pval, totals); break;
+        case STAT_F4: run_phases<STAT_F4, KP>(c, pval, totals); break;
         case STAT_TABULATED:
             if constexpr (KP == 1) {
-                launch_summary<STAT_TABULATED, KP>(c, pval, totals);
+                run_phases<STAT_TABULATED, KP>(c, pval, totals);
                 break;
             }
             return TSKB_ERR_UNSUPPORTED;
@@ -804,7 +791,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     }
     TSKB_CK(cudaEventRecord(P.ev[5], s));
     int h_err = 0;
-    TSKB_CK(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    TSKB_CK(cudaMemcpyAsync(&h_err, c.d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
     if (!sp.result_on_device) {
         TSKB_CK(cudaMemcpyAsync(sp.result, c.d_result, (size_t) W * M * sizeof(double),
             cudaMemcpyDeviceToHost, s));
