@@ -117,7 +117,7 @@ def measured_traffic(kernel):
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
-    key = {"propagate": "k_propagate<1>", "summary": "k_branch_summary<0, 1, 1>"}.get(kernel)
+    key = {"sweep": "k_sweep<1>", "summary": "k_branch_summary<0, 1>"}.get(kernel)
     return d.get(key)
 
 
@@ -323,10 +323,10 @@ def run_ours(args):
         K_avg = 1.5  # one sweep with K = 1 state column and one with K = 2
         b_branch = 28 + dbar * (12 + 8 * K_avg)
         per_step_ms = phase_ms / args.steps
-        names = ["weights", "propagate", "summary", "finalize", "idle", "d2h"]
+        names = ["weights", "sweep", "summary", "integrate", "idle", "d2h"]
         dom = int(np.argmax(per_step_ms))
-        # algorithmic share of the dominant phase (DESIGN.md "Roofline accounting")
-        share = {"propagate": 20 + dbar * (4 + 8 * K_avg), "summary": 8 + dbar * 8}.get(
+        # algorithmic share of the dominant phase ("Roofline accounting")
+        share = {"sweep": 20 + dbar * (4 + 8 * K_avg), "summary": 8 + dbar * 8}.get(
             names[dom], b_branch)
         achieved = share * sweeps * nev / (per_step_ms[dom] / 1e3) / 1e9
         sweep_achieved = b_branch * sweeps * nev / (dev_ms / args.steps / 1e3) / 1e9

@@ -180,7 +180,7 @@ typedef struct {
     uint64_t num_levels;       /* dependency levels of the count propagation */
     double stage_ms;           /* wall time of tskb_treeseq_init */
     double last_call_ms;       /* device time of the last statistic call (CUDA events) */
-    double last_kernel_ms[8];  /* per phase: 0 weights, 1 propagate, 2 summary, 3 scan, 4 windows, 5 d2h */
+    double last_kernel_ms[8];  /* per phase: 0 weights, 1 sweep, 2 summary, 3 scan + window integration (site: window sums), 4 idle, 5 d2h */
     uint64_t last_launches;    /* kernels launched by the last statistic call */
     uint64_t device_bytes;     /* HBM held by the plan */
 } tskb_stats_t;

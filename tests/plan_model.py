@@ -165,6 +165,8 @@ def build(t, a=None, b=None):
             if h != height[p]:
                 height[p] = h
                 changed = True
+    if os.environ.get("TSKB_ORDER", "").startswith("l"):
+        height = level[rank_node[piece_rank]].astype(np.int64)
     real = np.nonzero(pc_x[:P] >= 0)[0]
     if os.environ.get("TSKB_ORDER", "").startswith("x"):
         real = real[np.argsort(pc_x[real], kind="stable")]

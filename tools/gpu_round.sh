@@ -14,13 +14,13 @@ if [ -z "$SKIP_REF" ]; then
 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref exit $?"
 cat $OUT/bench_ref.json
 fi
-KREGEX='regex:k_(set_weights|propagate|branch_summary|branch_finalize|window|site_summary)'
+KREGEX='regex:(k_set_weights|k_sweep|k_branch_summary|k_window|k_site_summary|DeviceScan)'
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 600 \
     --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_launch.log 2>&1
 echo "ncu launches exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_propagate -s 2 -c 2 \
-    -o $OUT/prof_propagate -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_prop.log 2>&1
-echo "ncu propagate exit $?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 2 -c 2 \
+    -o $OUT/prof_sweep -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_prop.log 2>&1
+echo "ncu sweep exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_branch_summary -s 2 -c 2 \
     -o $OUT/prof_summary -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_sum.log 2>&1
 echo "ncu summary exit $?"

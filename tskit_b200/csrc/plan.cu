@@ -465,6 +465,12 @@ __global__ void k_height_keys_of(uint32_t P, const uint32_t *piece, const double
     key[i] = pc_x[p] >= 0.0 ? height[p] : init_key;
 }
 
+__global__ void k_level_as_height(uint32_t P, const uint32_t *piece_rank, const int32_t *rank_node,
+    const uint32_t *level, uint32_t *height) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) height[p] = level[rank_node[piece_rank[p]]];
+}
+
 __global__ void k_translate(int32_t *a, uint32_t n, const uint32_t *perm) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = (int32_t) perm[a[i]];
@@ -936,6 +942,16 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
                 if (++rounds > (1 << 20)) throw (int) TSKB_ERR_BAD_PARAM_VALUE;  // cyclic input
             }
         }
+        const char *order_env = getenv("TSKB_ORDER");
+        const bool order_x = order_env != nullptr && order_env[0] == 'x';
+        const bool order_level = order_env != nullptr && order_env[0] == 'l';
+        if (order_level && Pn) {
+            // group by the node's static level instead of the piece's height: more dependent steps,
+            // but every node's pieces stay contiguous
+            k_level_as_height<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, piece_rank.p, P.rank_node.p, P.level.p,
+                height.p);
+            TSKB_CK_LAUNCH();
+        }
         uint32_t max_h = 0;
         {
             DevArray<uint32_t> mx;
@@ -952,8 +968,6 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         // position with TSKB_ORDER=x); INIT pieces last
         DevArray<uint32_t> kin, kout, vin, vout, lvl_begin;
         kin.alloc(Pn); kout.alloc(Pn); vin.alloc(Pn); vout.alloc(Pn); lvl_begin.alloc(P.nheights + 2);
-        const char *order_env = getenv("TSKB_ORDER");
-        const bool order_x = order_env != nullptr && order_env[0] == 'x';
         if (Pn) {
             if (order_x) {
                 DevArray<uint64_t> k64, k64o;

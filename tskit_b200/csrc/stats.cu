@@ -292,15 +292,10 @@ struct SweepArgs {
     uint32_t *counters;
     int *error_flag;
     unsigned long long *trace;
-    // FUSE only
-    const uint32_t *q_bp0, *q_bp1;
-    const double *q_bl;
-    DeltaOut out;
 };
 
-template <int STAT, int KP, bool FUSE>
-__global__ void __launch_bounds__(PROP_TB, (FUSE && KP <= 2) ? 4 : 1) k_sweep(SweepArgs a, IVec<KP> *pval, SumP sp,
-    IVec<KP> totals) {
+template <int KP>
+__global__ void __launch_bounds__(PROP_TB) k_sweep(SweepArgs a, IVec<KP> *pval) {
     unsigned long long *trace = a.trace;
     for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         TRACE(0);
@@ -308,20 +303,10 @@ __global__ void __launch_bounds__(PROP_TB, (FUSE && KP <= 2) ? 4 : 1) k_sweep(Sw
         const uint32_t j0 = tile * PROP_TILE + threadIdx.x;
         uint32_t o0[PROP_IPT], o1[PROP_IPT], rf[PROP_IPT][PROP_PRE];
         // everything that does not depend on other tiles is fetched before the wait
-        double bl[PROP_IPT];
-        uint32_t bp0[PROP_IPT], bp1[PROP_IPT];
 #pragma unroll
         for (int q = 0; q < PROP_IPT; q++) {
             o0[q] = __ldg(a.q_off + j0 + q * PROP_TB);
             o1[q] = __ldg(a.q_off + j0 + q * PROP_TB + 1);
-            if (FUSE) {
-                bl[q] = __ldg(a.q_bl + j0 + q * PROP_TB);
-                bp0[q] = __ldg(a.q_bp0 + j0 + q * PROP_TB);
-                bp1[q] = __ldg(a.q_bp1 + j0 + q * PROP_TB);
-                // a piece without a branch above it is no other piece's child over its span, and
-                // with finite summaries it adds nothing itself: its state is not needed
-                if (sp.skip_zero_bl && bl[q] == 0.0) o1[q] = o0[q];
-            }
         }
 #pragma unroll
         for (int q = 0; q < PROP_IPT; q++) {
@@ -353,50 +338,77 @@ __global__ void __launch_bounds__(PROP_TB, (FUSE && KP <= 2) ? 4 : 1) k_sweep(Sw
             }
         }
         TRACE(2);
-        IVec<KP> sum[PROP_IPT];
 #pragma unroll
         for (int q = 0; q < PROP_IPT; q++) {
-            sum[q] = g[q][0];
+            IVec<KP> sum = g[q][0];
 #pragma unroll
-            for (int i = 1; i < PROP_PRE; i++) sum[q] = sum[q] + g[q][i];
+            for (int i = 1; i < PROP_PRE; i++) sum = sum + g[q][i];
             for (uint32_t o = o0[q] + PROP_PRE; o < o1[q]; o++) {
-                sum[q] = sum[q] + state_load<KP>(pval + __ldg(a.refs + o));
+                sum = sum + state_load<KP>(pval + __ldg(a.refs + o));
             }
-            pval[j0 + q * PROP_TB] = sum[q];
+            pval[j0 + q * PROP_TB] = sum;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             red_release_add(a.counters + 1, 1u);
             if (trace != nullptr) trace[(size_t) tile * 4 + 3] = gtime();
         }
-        if (FUSE) {
-            pieces_to_deltas<STAT, KP, PROP_IPT>(sp, totals, sum, bl, bp0, bp1, a.out, 0, (uint32_t) sp.M);
-        }
     }
 }
 
-// ---------------------------------------------------------------- phase 2, branch mode, unfused
-// Used when the delta arrays of all columns would be too large at once: the states are streamed
-// once more per chunk of columns (fully coalesced).
+// ---------------------------------------------------------------- phase 2, branch mode
+// The states are streamed once (fully coalesced) per chunk of result columns; a chunk is as many
+// columns as fit the delta budget (all of them, normally).  Kept separate from the sweep: both are
+// bound by the rate at which an SM issues requests to L2 (measured: fusing them saved nothing), and
+// apart they keep their own register budgets.
 
-constexpr int SUM_IPT = 4;
-constexpr int SUM_TILE = TB * SUM_IPT;   // PROP_TILE: the processing order is padded to whole tiles
+#ifndef TSKB_SUM_IPT
+#define TSKB_SUM_IPT 4
+#endif
+constexpr int SUM_IPT = TSKB_SUM_IPT;    // pieces per thread and pipeline stage
+constexpr int SUM_TILE = TB * SUM_IPT;
 
-template <int STAT, int KP>
-__global__ void __launch_bounds__(TB) k_branch_summary(uint32_t ntiles,
-    const uint32_t *__restrict__ q_bp0, const uint32_t *__restrict__ q_bp1,
-    const double *__restrict__ q_bl, const IVec<KP> *__restrict__ pval, SumP sp, IVec<KP> totals,
-    DeltaOut out, uint32_t m0, uint32_t m1) {
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        IVec<KP> st[SUM_IPT];
-        double bl[SUM_IPT];
-        uint32_t bp0[SUM_IPT], bp1[SUM_IPT];
+template <int KP>
+struct PieceRegs {
+    IVec<KP> st[SUM_IPT];
+    double bl[SUM_IPT];
+    uint32_t bp0[SUM_IPT], bp1[SUM_IPT];
+    __device__ __forceinline__ void load(uint32_t tile, uint32_t npp, const uint32_t *__restrict__ q_bp0,
+        const uint32_t *__restrict__ q_bp1, const double *__restrict__ q_bl,
+        const IVec<KP> *__restrict__ pval) {
 #pragma unroll
         for (int q = 0; q < SUM_IPT; q++) {
             const uint32_t j = tile * SUM_TILE + q * TB + threadIdx.x;
-            st[q] = pval[j]; bl[q] = q_bl[j]; bp0[q] = q_bp0[j]; bp1[q] = q_bp1[j];
+            bp1[q] = NO_PIECE;  // past the end: padding
+            bp0[q] = 0;
+            bl[q] = 0.0;
+            st[q] = ivec_zero<KP>();
+            // the processing order is padded to whole PROP_TILEs: no bounds check when tiles coincide
+            if (SUM_TILE == PROP_TILE || j < npp) {
+                st[q] = pval[j]; bl[q] = q_bl[j]; bp0[q] = q_bp0[j]; bp1[q] = q_bp1[j];
+            }
         }
-        pieces_to_deltas<STAT, KP, SUM_IPT>(sp, totals, st, bl, bp0, bp1, out, m0, m1);
+    }
+};
+
+// Few warps with many loads in flight each beat many warps here (measured): the kernel is bound
+// by the rate at which an SM can issue requests to L2, and the reductions of a warp are 32
+// separate requests.
+template <int STAT, int KP>
+__global__ void __launch_bounds__(TB) k_branch_summary(uint32_t npp,
+    const uint32_t *__restrict__ q_bp0, const uint32_t *__restrict__ q_bp1,
+    const double *__restrict__ q_bl, const IVec<KP> *__restrict__ pval, SumP sp, IVec<KP> totals,
+    DeltaOut out, uint32_t m0, uint32_t m1) {
+    const uint32_t ntiles = (npp + SUM_TILE - 1) / SUM_TILE;
+    // software pipeline: the next tile's loads are in flight while this one is evaluated
+    PieceRegs<KP> cur, nxt;
+    uint32_t tile = blockIdx.x;
+    if (tile < ntiles) cur.load(tile, npp, q_bp0, q_bp1, q_bl, pval);
+    for (; tile < ntiles; tile += gridDim.x) {
+        const uint32_t tn = tile + gridDim.x;
+        if (tn < ntiles) nxt.load(tn, npp, q_bp0, q_bp1, q_bl, pval);
+        pieces_to_deltas<STAT, KP, SUM_IPT>(sp, totals, cur.st, cur.bl, cur.bp0, cur.bp1, out, m0, m1);
+        cur = nxt;
     }
 }
 
@@ -404,31 +416,48 @@ __global__ void __launch_bounds__(TB) k_branch_summary(uint32_t ntiles,
 // S = inclusive prefix sum of D over the breakpoints (the reference's running sum after the diffs
 // of breakpoint i, cub::DeviceScan per column); window w gets the integral of S over it:
 // sum over the breakpoint intervals [t_i, t_i+1) that meet it of S_i * overlap
-// (trees.c:1484-1504), span-normalised (trees.c:1920-1934).  One warp per (window, column).
+// (trees.c:1484-1504), span-normalised (trees.c:1920-1934).  G threads per (window, column):
+// a warp, or a whole block when there are few windows.
+template <int G>
 __global__ void __launch_bounds__(TB) k_window_integrate(const double *S, uint32_t Tp1,
     const double *__restrict__ bp_pos, const double *__restrict__ windows, uint32_t W, uint32_t mcols,
     uint32_t m0, uint32_t M, int span_normalise, double *result) {
+    __shared__ double s_part[TB / 32];
     const uint32_t T = Tp1 - 1;
     const uint32_t lane = threadIdx.x & 31u;
-    const size_t warp = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (warp >= (size_t) W * mcols) return;
-    const uint32_t w = (uint32_t) (warp / mcols), mloc = (uint32_t) (warp % mcols);
-    const double wl = windows[w], wr = windows[w + 1];
-    const double *Sm = S + (size_t) mloc * Tp1;
-    // intervals meeting [wl, wr): from the one holding wl (or the first) to the last starting < wr
-    uint32_t lo = upper_bound_dev(bp_pos, T, wl);
-    lo = lo > 0 ? lo - 1 : 0;
-    const uint32_t hi = lower_bound_dev(bp_pos, T, wr);
-    double acc = 0.0;
-    for (uint32_t i = lo + lane; i < hi; i += 32) {
-        double a = bp_pos[i], b = bp_pos[i + 1];
-        a = a > wl ? a : wl;
-        b = b < wr ? b : wr;
-        if (b > a) acc += Sm[i] * (b - a);
+    const size_t group = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const uint32_t gt = threadIdx.x % G;
+    const bool active = group < (size_t) W * mcols;  // uniform over the group
+    double acc = 0.0, wl = 0.0, wr = 1.0;
+    uint32_t w = 0, mloc = 0;
+    if (active) {
+        w = (uint32_t) (group / mcols);
+        mloc = (uint32_t) (group % mcols);
+        wl = windows[w];
+        wr = windows[w + 1];
+        const double *Sm = S + (size_t) mloc * Tp1;
+        // intervals meeting [wl, wr): from the one holding wl (or the first) to the last starting < wr
+        uint32_t lo = upper_bound_dev(bp_pos, T, wl);
+        lo = lo > 0 ? lo - 1 : 0;
+        const uint32_t hi = lower_bound_dev(bp_pos, T, wr);
+        for (uint32_t i = lo + gt; i < hi; i += G) {
+            double a = bp_pos[i], b = bp_pos[i + 1];
+            a = a > wl ? a : wl;
+            b = b < wr ? b : wr;
+            if (b > a) acc += Sm[i] * (b - a);
+        }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
-    if (lane == 0) {
+    if (G > 32) {
+        if (lane == 0) s_part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            acc = 0.0;
+            for (int i = 0; i < TB / 32; i++) acc += s_part[i];
+        }
+    }
+    if (active && gt == 0) {
         if (span_normalise) acc /= wr - wl;
         result[(size_t) w * M + m0 + mloc] = acc;
     }
@@ -559,8 +588,8 @@ struct CallCtx {
     uint64_t launches;
 };
 
-template <int STAT, int KP, bool FUSE>
-void launch_sweep(CallCtx &c, IVec<KP> *pval, IVec<KP> totals, DeltaOut out) {
+template <int KP>
+void launch_sweep(CallCtx &c, IVec<KP> *pval) {
     const Plan &P = *c.P;
     Arena &A = P.arena;
     if (P.ntiles == 0) return;
@@ -572,7 +601,7 @@ void launch_sweep(CallCtx &c, IVec<KP> *pval, IVec<KP> totals, DeltaOut out) {
         TSKB_CK(cudaMemsetAsync(trace, 0, (size_t) P.ntiles * 4 * sizeof(unsigned long long), c.s));
         P.stats_trace = trace;
     }
-    auto kern = k_sweep<STAT, KP, FUSE>;
+    auto kern = k_sweep<KP>;
     int per_sm = 1, sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
     TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PROP_TB, 0));
@@ -581,9 +610,7 @@ void launch_sweep(CallCtx &c, IVec<KP> *pval, IVec<KP> totals, DeltaOut out) {
     a.ntiles = P.ntiles;
     a.tile_dep = P.tile_dep.p; a.q_off = P.q_off.p; a.refs = P.refs.p;
     a.counters = counters; a.error_flag = c.d_err; a.trace = trace;
-    a.q_bp0 = P.q_bp0.p; a.q_bp1 = P.q_bp1.p; a.q_bl = P.q_bl.p;
-    a.out = out;
-    void *args[] = { &a, &pval, &c.sumP, &totals };
+    void *args[] = { &a, &pval };
     TSKB_CK(cudaLaunchCooperativeKernel((const void *) kern, dim3(grid), dim3(PROP_TB), args, 0, c.s));
     c.launches++;
 }
@@ -598,9 +625,15 @@ inline void finish_columns(CallCtx &c, double *D, uint32_t Tp1, uint32_t m0, uin
         TSKB_CK(cub::DeviceScan::InclusiveSum(scan_tmp, scan_bytes, Dm, Dm, (int) (Tp1 - 1), c.s));
         c.launches++;
     }
-    const size_t warps = (size_t) W * mcols;
-    k_window_integrate<<<grid_for(warps * 32, TB), TB, 0, c.s>>>(D, Tp1, P.bp_pos.p, c.d_windows, W,
-        mcols, m0, M, (c.sp->options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0, c.d_result);
+    const size_t groups = (size_t) W * mcols;
+    const int span = (c.sp->options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0;
+    if (groups * 32 < (size_t) 148 * 2048) {  // few windows: a block per (window, column)
+        k_window_integrate<TB><<<(unsigned) groups, TB, 0, c.s>>>(D, Tp1, P.bp_pos.p, c.d_windows, W,
+            mcols, m0, M, span, c.d_result);
+    } else {
+        k_window_integrate<32><<<grid_for(groups * 32, TB), TB, 0, c.s>>>(D, Tp1, P.bp_pos.p,
+            c.d_windows, W, mcols, m0, M, span, c.d_result);
+    }
     TSKB_CK_LAUNCH();
     c.launches++;
 }
@@ -618,31 +651,23 @@ void run_branch(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
     TSKB_CK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, D, D, (int) std::max<uint32_t>(Tp1 - 1, 1), c.s));
     void *scan_tmp = A.get<char>(scan_bytes);
     DeltaOut out = { D, Tp1, c.sumP.cols };
-    const bool fuse = mc == M && getenv("TSKB_NO_FUSE") == nullptr;
-    if (fuse) {
-        TSKB_CK(cudaMemsetAsync(D, 0, (size_t) mc * col_bytes, c.s));
-        launch_sweep<STAT, KP, true>(c, pval, totals, out);
-        TSKB_CK(cudaEventRecord(P.ev[2], c.s));
-        TSKB_CK(cudaEventRecord(P.ev[3], c.s));
-        finish_columns(c, D, Tp1, 0, M, scan_tmp, scan_bytes);
-    } else {
-        launch_sweep<0, KP, false>(c, pval, totals, out);
-        TSKB_CK(cudaEventRecord(P.ev[2], c.s));
-        const uint32_t ntiles = P.npp / SUM_TILE;
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
-        for (uint32_t m0 = 0; m0 < M; m0 += mc) {
-            const uint32_t m1 = std::min(M, m0 + mc);
-            TSKB_CK(cudaMemsetAsync(D, 0, (size_t) (m1 - m0) * col_bytes, c.s));
-            if (ntiles > 0) {
-                k_branch_summary<STAT, KP><<<std::min<uint32_t>(ntiles, (uint32_t) sms * 8), TB, 0, c.s>>>(
-                    ntiles, P.q_bp0.p, P.q_bp1.p, P.q_bl.p, pval, c.sumP, totals, out, m0, m1);
-                TSKB_CK_LAUNCH();
-                c.launches++;
-            }
-            finish_columns(c, D, Tp1, m0, m1 - m0, scan_tmp, scan_bytes);
+    launch_sweep<KP>(c, pval);
+    TSKB_CK(cudaEventRecord(P.ev[2], c.s));
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
+    TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_branch_summary<STAT, KP>, TB, 0));
+    const uint32_t ntiles = (P.npp + SUM_TILE - 1) / SUM_TILE;
+    for (uint32_t m0 = 0; m0 < M; m0 += mc) {
+        const uint32_t m1 = std::min(M, m0 + mc);
+        TSKB_CK(cudaMemsetAsync(D, 0, (size_t) (m1 - m0) * col_bytes, c.s));
+        if (ntiles > 0) {
+            k_branch_summary<STAT, KP><<<std::min<uint32_t>(ntiles, (uint32_t) (sms * std::max(per_sm, 1))), TB, 0, c.s>>>(
+                P.npp, P.q_bp0.p, P.q_bp1.p, P.q_bl.p, pval, c.sumP, totals, out, m0, m1);
+            TSKB_CK_LAUNCH();
+            c.launches++;
         }
-        TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+        if (m0 == 0) TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+        finish_columns(c, D, Tp1, m0, m1 - m0, scan_tmp, scan_bytes);
     }
     TSKB_CK(cudaEventRecord(P.ev[4], c.s));
 }
@@ -652,7 +677,7 @@ void run_site(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
     const Plan &P = *c.P;
     const uint32_t W = c.sp->W, M = c.sp->M;
     Arena &A = P.arena;
-    launch_sweep<0, KP, false>(c, pval, totals, DeltaOut{});
+    launch_sweep<KP>(c, pval);
     TSKB_CK(cudaEventRecord(P.ev[2], c.s));
     const uint32_t nsites = P.site_hi - P.site_lo;
     const uint32_t nsplit = std::max<uint32_t>(1, (592 + W - 1) / W);
