@@ -79,6 +79,22 @@ def test_divmat_site_wright_fisher(wf_small, engines):
     assert np.all(got[:, 1, 1] == 0)  # singleton set: diagonal 0, not NaN (trees.c:8888-8891)
 
 
+def test_divmat_site_1k_tensor_core_paths(wf_1k, monkeypatch):
+    """1000 samples = 8 x 8 blocks of 128 with a ragged last block, k-ranges that start and end
+    inside 16-byte chunks; the tcgen05 path and the legacy mma.sync path must both give the exact
+    integer counts of the oracle."""
+    from tskit_b200.lowlevel import LLTreeSequence
+    ll, o = LLTreeSequence(wf_1k), port.Oracle(wf_1k)
+    L = wf_1k.sequence_length
+    windows = [0, L * 0.013, L * 0.4, L * 0.41, L]
+    want = o.divergence_matrix(None, windows=windows, mode="site", span_normalise=False)
+    got = ll.divergence_matrix(windows, mode="site", span_normalise=False)
+    assert np.array_equal(got, want)
+    monkeypatch.setenv("TSKB_MATRIX_LEGACY", "1")
+    got = ll.divergence_matrix(windows, mode="site", span_normalise=False)
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("name", ["paper", "nonbinary", "multiroot", "missing", "case_1"])
 def test_divmat_site_fixtures(name):
     from tskit_b200.lowlevel import LLTreeSequence

