@@ -180,7 +180,8 @@ typedef struct {
     uint64_t num_levels;       /* dependency levels of the count propagation */
     double stage_ms;           /* wall time of tskb_treeseq_init */
     double last_call_ms;       /* device time of the last statistic call (CUDA events) */
-    double last_kernel_ms[8];  /* per phase: 0 weights, 1 sweep, 2 summary, 3 scan + window integration (site: window sums), 4 idle, 5 d2h */
+    double last_kernel_ms[8];  /* per phase: 0 weights, 1 sweep, 2 summary, 3 scan + window integration (site: window sums), 4 idle, 5 d2h;
+                                * after divergence_matrix(site): 0 decode, 1 contraction, 2 normalise + d2h, 7 alleles */
     uint64_t last_launches;    /* kernels launched by the last statistic call */
     uint64_t device_bytes;     /* HBM held by the plan */
 } tskb_stats_t;
@@ -194,9 +195,8 @@ int tskb_treeseq_stat_device(const tskb_treeseq_t *self, int stat_id,
     uint64_t num_windows, const double *windows, uint32_t options, double *d_result);
 
 /* Debug/test access to plan arrays (copied to host). name in: "ev_pos",
- * "ev_child", "ev_sign", "voff", "bp_pos", "bp_end", "em_idx", "em_bl",
- * "nm_src", "nm_flag", "nm_key", "level", "rank_node", "level_begin",
- * "mut_src", "mut_allele", "mut_alt".  Returns the element count, or <0 on error; copies at most
+ * "ev_child", "ev_sign", "voff", "bp_pos", "q_off", "refs", "q_bp0", "q_bp1", "q_bl",
+ * "tile_dep", "level", "rank_node", "level_begin", "mut_src", "mut_allele", "mut_alt", "trace".  Returns the element count, or <0 on error; copies at most
  * max_bytes. */
 int64_t tskb_treeseq_debug_array(const tskb_treeseq_t *self, const char *name, void *out,
     uint64_t max_bytes);

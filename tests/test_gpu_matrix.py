@@ -81,8 +81,8 @@ def test_divmat_site_wright_fisher(wf_small, engines):
 
 def test_divmat_site_1k_tensor_core_paths(wf_1k, monkeypatch):
     """1000 samples = 8 x 8 blocks of 128 with a ragged last block, k-ranges that start and end
-    inside 16-byte chunks; the tcgen05 path and the legacy mma.sync path must both give the exact
-    integer counts of the oracle."""
+    inside 16-byte chunks; the biallelic tcgen05 Gram kernel (256 x 256 tiles), the tcgen05 one-hot
+    kernel and the legacy mma.sync kernel must all give the exact integer counts of the oracle."""
     from tskit_b200.lowlevel import LLTreeSequence
     ll, o = LLTreeSequence(wf_1k), port.Oracle(wf_1k)
     L = wf_1k.sequence_length
@@ -90,9 +90,10 @@ def test_divmat_site_1k_tensor_core_paths(wf_1k, monkeypatch):
     want = o.divergence_matrix(None, windows=windows, mode="site", span_normalise=False)
     got = ll.divergence_matrix(windows, mode="site", span_normalise=False)
     assert np.array_equal(got, want)
-    monkeypatch.setenv("TSKB_MATRIX_LEGACY", "1")
-    got = ll.divergence_matrix(windows, mode="site", span_normalise=False)
-    assert np.array_equal(got, want)
+    for mode in ("onehot", "legacy"):  # tcgen05 one-hot kernel (any alleles), mma.sync kernel
+        monkeypatch.setenv("TSKB_MATRIX", mode)
+        got = ll.divergence_matrix(windows, mode="site", span_normalise=False)
+        assert np.array_equal(got, want), mode
 
 
 @pytest.mark.parametrize("name", ["paper", "nonbinary", "multiroot", "missing", "case_1"])

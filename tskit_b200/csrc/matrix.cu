@@ -90,7 +90,8 @@ __global__ void k_expand(const uint2 *items, uint32_t nitems, uint32_t r, uint32
     const double *site_pos, const uint32_t *site_moff, const uint16_t *mut_allele,
     const int32_t *col, const uint32_t *pm_off, const double *pm_left, const double *pm_right,
     const double *pm_pmax, const int32_t *pm_child, int8_t *G, size_t stride_site,
-    size_t stride_sample, uint2 *next, uint32_t cap, uint32_t *next_count, int *overflow) {
+    size_t stride_sample, const uint32_t *site_col, uint2 *next, uint32_t cap, uint32_t *next_count,
+    int *overflow) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nitems) return;
     const uint2 it = items[t];
@@ -98,7 +99,8 @@ __global__ void k_expand(const uint2 *items, uint32_t nitems, uint32_t r, uint32
     const double x = site_pos[s];
     int32_t c = col[u];
     if (c >= 0) {
-        G[(size_t) (s - s0) * stride_site + (size_t) c * stride_sample] = (int8_t) mut_allele[site_moff[s] + r];
+        const size_t column = site_col != nullptr ? site_col[s - s0] : s - s0;  // padded layouts
+        G[column * stride_site + (size_t) c * stride_sample] = (int8_t) mut_allele[site_moff[s] + r];
     }
     uint32_t lo = pm_off[u], hi = pm_off[u + 1];
     uint32_t k = upper_bound_dev(pm_left + lo, hi - lo, x);  // edges with left <= x
@@ -423,14 +425,170 @@ __global__ void __launch_bounds__(THREADS) k_same_umma(const int8_t *__restrict_
     }
 }
 
+// ---- biallelic sites: C = G G^T straight from the genotype bytes
+// With genotypes in {0, 1} the one-hot tile of allele 1 is the genotype tile itself and
+//   different[i][j] = C[i][i] + C[j][j] - 2 C[i][j]          (C[i][i] = number of 1s of sample i),
+// so the contraction needs neither the compare nor allele 0.  One CTA per 256 x 256 block of C (row
+// block <= column block): four 128 x 128 accumulators fill the 512 columns of tensor memory, which
+// halves the operand bytes per MAC against a 128 x 128 tile (the kernel is L2-bandwidth bound
+// otherwise).  Operand tiles go global -> shared with 16-byte cp.async copies placed directly in
+// the UMMA no-swizzle K-major layout, three stages deep; k ranges are whole 128-byte chunks (the
+// caller pads every window, padding bytes are 0 and add nothing).
+namespace gram {
+
+constexpr uint32_t CT = 256;                                // CTA tile (rows and columns of C)
+constexpr uint32_t SUB_BYTES = 128 * BK;                    // one 128-row operand sub-tile: 16 KB
+constexpr uint32_t STAGE_BYTES = 4 * SUB_BYTES;             // A0 A1 B0 B1
+constexpr uint32_t NSTAGE = 3;
+constexpr uint32_t SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024;
+constexpr uint32_t TMEM_ALL = 512;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_gram_umma(const int8_t *__restrict__ X, size_t ld, uint32_t n,
+    uint32_t k_lo, uint32_t k_hi, int32_t *__restrict__ C) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t s_bar[NSTAGE];
+    __shared__ uint32_t s_tmem;
+    const uint32_t bi = blockIdx.y, bj = blockIdx.x;
+    if (bi > bj) return;
+    const bool diag = bi == bj;
+    const uint32_t i0 = bi * CT, j0 = bj * CT;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tiles = smem_u32(smem_raw) + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+
+    if (tid == 0) {
+        for (uint32_t st = 0; st < NSTAGE; st++) mbar_init(&s_bar[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&s_tmem)), "r"(TMEM_ALL) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = s_tmem;
+
+    const uint32_t r8 = lane & 7, kq = lane >> 3;
+    const uint32_t nch = (k_hi - k_lo) / BK;  // whole chunks by contract
+    // copies of one k chunk into a stage: sub-tiles A0 A1 (rows i0 ...) and, off the diagonal, B0 B1
+    auto issue_copy = [&](uint32_t ch) {
+        const uint32_t stage = tiles + (ch % NSTAGE) * STAGE_BYTES;
+        const uint32_t k0 = k_lo + ch * BK;
+        const uint32_t nsub = diag ? 2 : 4;
+        for (uint32_t sub = 0; sub < nsub; sub++) {
+            const uint32_t row0 = (sub < 2 ? i0 : j0) + (sub & 1) * 128;
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const uint32_t u = warp + 8 * p, g = u >> 1, kc = (u & 1) * 4 + kq;
+                const uint32_t row = row0 + g * 8 + r8;
+                const bool ok = row < n;  // rows past the end: zero fill (src-size 0)
+                const int8_t *src = X + (size_t) (ok ? row : 0) * ld + k0 + kc * 16;
+                cp_async16(stage + sub * SUB_BYTES + g * SBO + kc * LBO + r8 * 16, src, ok ? 16u : 0u);
+            }
+        }
+    };
+    for (uint32_t ch = 0; ch + 1 < NSTAGE; ch++) {
+        if (ch < nch) issue_copy(ch);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (uint32_t ch = 0; ch < nch; ch++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(NSTAGE - 2) : "memory");  // chunk ch has landed
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t stage = tiles + (ch % NSTAGE) * STAGE_BYTES;
+#pragma unroll
+            for (uint32_t ks = 0; ks < BK / 32; ks++) {
+#pragma unroll
+                for (uint32_t a = 0; a < 2; a++) {
+#pragma unroll
+                    for (uint32_t b = 0; b < 2; b++) {
+                        if (diag && a > b) continue;  // lower triangle of a diagonal block: never read
+                        const uint32_t aaddr = stage + a * SUB_BYTES + ks * 2 * LBO;
+                        const uint32_t baddr = stage + (diag ? b : 2 + b) * SUB_BYTES + ks * 2 * LBO;
+                        umma_i8(tmem_acc + (a * 2 + b) * 128, umma_desc(aaddr), umma_desc(baddr),
+                            (ch > 0 || ks > 0) ? 1u : 0u);
+                    }
+                }
+            }
+            umma_commit(&s_bar[ch % NSTAGE]);
+        }
+        // refill the stage read by the MMAs of chunk ch - 1 once they are complete
+        const uint32_t nx = ch + NSTAGE - 1;
+        if (nx < nch) {
+            if (ch >= 1) mbar_wait(&s_bar[(ch - 1) % NSTAGE], ((ch - 1) / NSTAGE) & 1);
+            issue_copy(nx);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (nch > 0) mbar_wait(&s_bar[(nch - 1) % NSTAGE], ((nch - 1) / NSTAGE) & 1);  // commits complete in order
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: warp w owns TMEM lanes 32 (w % 4) .. + 31 and, of every accumulator, columns 64 (w / 4) ...
+    for (uint32_t a = 0; a < 2; a++) {
+        for (uint32_t b = 0; b < 2; b++) {
+            if (diag && a > b) continue;
+            const uint32_t row = i0 + a * 128 + 32 * (warp & 3) + lane;
+#pragma unroll
+            for (uint32_t half = 0; half < 2; half++) {
+                const uint32_t col0 = 64 * (warp >> 2) + 32 * half;
+                uint32_t v[32];
+                const uint32_t taddr = tmem_acc + ((32 * (warp & 3)) << 16) + (a * 2 + b) * 128 + col0;
+                if (nch > 0) {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; q++) v[q] = 0;
+                }
+                if (row < n) {
+#pragma unroll
+                    for (int q = 0; q < 32; q++) {
+                        const uint32_t col = j0 + b * 128 + col0 + q;
+                        if (col < n) C[(size_t) row * n + col] = (int32_t) v[q];
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(TMEM_ALL) : "memory");
+    }
+}
+
+}  // namespace gram
+
 }  // namespace tc
+
+// number of sites at which samples lo < hi differ, from the contraction's output
+__device__ __forceinline__ int64_t pair_different(const int32_t *same, uint32_t n, uint32_t lo, uint32_t hi,
+    uint32_t ncols, int biallelic) {
+    const int64_t c = same[(size_t) lo * n + hi];
+    if (biallelic) return (int64_t) same[(size_t) lo * n + lo] + (int64_t) same[(size_t) hi * n + hi] - 2 * c;
+    return (int64_t) ncols - c;
+}
 
 // D[a][b] = sum over j in set a, k in set b of (sites - same[j][k]) (j != k), count- and
 // span-normalised (trees.c:8876-8899, 1920-1934).  `same` holds blocks with row block <= col
 // block only: read the transposed entry otherwise.
 __global__ void k_divmat_finish(const int32_t *same, uint32_t n, const uint32_t *set_off,
-    uint32_t nsets, const double *set_size, uint32_t nsites, double span, int span_normalise,
-    double *D) {
+    uint32_t nsets, const double *set_size, uint32_t ncols, int biallelic, double span,
+    int span_normalise, double *D) {
     typedef cub::BlockReduce<double, TB> BR;
     __shared__ typename BR::TempStorage tmp;
     const uint32_t a = blockIdx.y, b = blockIdx.x;
@@ -443,7 +601,7 @@ __global__ void k_divmat_finish(const int32_t *same, uint32_t n, const uint32_t 
         if (j == k) continue;
         uint32_t lo = j < k ? j : k, hi = j < k ? k : j;
         // entries of the upper block triangle: (lo, hi) is stored iff block(lo) <= block(hi): always
-        sum += (double) ((int64_t) nsites - (int64_t) same[(size_t) lo * n + hi]);
+        sum += (double) pair_different(same, n, lo, hi, ncols, biallelic);
     }
     double tot = BR(tmp).Sum(sum);
     if (threadIdx.x == 0) {
@@ -453,6 +611,21 @@ __global__ void k_divmat_finish(const int32_t *same, uint32_t n, const uint32_t 
         D[(size_t) a * nsets + b] = tot;
         D[(size_t) b * nsets + a] = tot;
     }
+}
+
+// every set a single sample (the default of divergence_matrix)
+__global__ void k_divmat_pairs(const int32_t *same, uint32_t n, uint32_t ncols, int biallelic, double span,
+    int span_normalise, double *D) {
+    const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t) n * n) return;
+    const uint32_t j = (uint32_t) (t / n), k = (uint32_t) (t % n);
+    double v = 0.0;
+    if (j != k) {
+        const uint32_t lo = j < k ? j : k, hi = j < k ? k : j;
+        v = (double) pair_different(same, n, lo, hi, ncols, biallelic);
+        if (span_normalise) v /= span;
+    }
+    D[t] = v;
 }
 
 struct Temp {
@@ -471,7 +644,8 @@ struct Temp {
 
 // genotypes of sites [s0, s1) for the listed samples into G (caller-zeroed), any strides
 void decode_sites(const Plan &P, const int32_t *d_samples, uint32_t n, uint32_t s0, uint32_t s1,
-    uint32_t options, int8_t *G, size_t stride_site, size_t stride_sample) {
+    uint32_t options, int8_t *G, size_t stride_site, size_t stride_sample,
+    const uint32_t *site_col = nullptr) {
     if (s1 <= s0 || n == 0) return;
     cudaStream_t s = P.stream;
     const uint32_t N = (uint32_t) P.N;
@@ -512,7 +686,7 @@ void decode_sites(const Plan &P, const int32_t *d_samples, uint32_t n, uint32_t 
                 TSKB_CK(cudaMemsetAsync(cnt.p + 1, 0, sizeof(uint32_t), s));
                 k_expand<<<grid_for(h_cnt, TB), TB, 0, s>>>(cur, h_cnt, r, s0, P.site_pos.p,
                     P.site_moff.p, P.mut_allele.p, col.p, P.pm_off.p, P.pm_left.p, P.pm_right.p, P.pm_pmax.p,
-                    P.pm_child.p, G, stride_site, stride_sample, nxt, cap, cnt.p + 1, ovf.p);
+                    P.pm_child.p, G, stride_site, stride_sample, site_col, nxt, cap, cnt.p + 1, ovf.p);
                 TSKB_CK_LAUNCH();
                 int h_ovf = 0;
                 TSKB_CK(cudaMemcpyAsync(&h_cnt, cnt.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -728,15 +902,34 @@ int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *size
         return (uint32_t) (std::lower_bound(P.h_site_pos.begin(), P.h_site_pos.end(), x) - P.h_site_pos.begin());
     };
     const uint32_t S0 = site_index(windows[0]), S1 = site_index(windows[W]);
-    const uint32_t ns_sites = S1 - S0;
-    const size_t ld = (((size_t) ns_sites + 15) & ~size_t(15)) + 16;
+    // genotype columns: every window starts on a 128-byte boundary and is padded to whole 128-byte
+    // chunks with zeros (ancestral everywhere: the same for every pair), so k ranges never need masks
+    std::vector<uint32_t> w_lo(W + 1), col_lo(W + 1);
+    for (uint32_t w = 0; w <= W; w++) w_lo[w] = site_index(windows[w]);
+    uint64_t cols = 0;
+    for (uint32_t w = 0; w < W; w++) {
+        col_lo[w] = (uint32_t) cols;
+        cols += ((uint64_t) (w_lo[w + 1] - w_lo[w]) + 127) / 128 * 128;
+    }
+    col_lo[W] = (uint32_t) cols;
+    if (cols >= 0xffffff00ull) return TSKB_ERR_UNSUPPORTED;
+    const size_t ld = (size_t) cols + 128;
+    std::vector<uint32_t> h_site_col(S1 - S0);
+    for (uint32_t w = 0; w < W; w++) {
+        for (uint32_t sidx = w_lo[w]; sidx < w_lo[w + 1]; sidx++) h_site_col[sidx - S0] = col_lo[w] + (sidx - w_lo[w]);
+    }
+    DevArray<uint32_t> d_site_col;
+    d_site_col.upload(h_site_col.data(), h_site_col.size(), s);
     DevArray<int32_t> d_sets;
     d_sets.upload(sets, n, s);
     DevArray<int8_t> X;
     X.alloc((size_t) n * ld);
     TSKB_CK(cudaMemsetAsync(X.p, 0, (size_t) n * ld, s));
-    // FIXME-free: the reference decodes with TSK_ISOLATED_NOT_MISSING here (trees.c:8775)
-    decode_sites(P, d_sets.p, n, S0, S1, TSKB_ISOLATED_NOT_MISSING, X.p, 1, ld);
+    // the reference decodes with TSK_ISOLATED_NOT_MISSING here (trees.c:8775): genotypes are >= 0
+    TSKB_CK(cudaEventRecord(P.ev[0], s));
+    decode_sites(P, d_sets.p, n, S0, S1, TSKB_ISOLATED_NOT_MISSING, X.p, 1, ld, d_site_col.p);
+    TSKB_CK(cudaEventRecord(P.ev[1], s));
+    float gemm_ms = 0, finish_ms = 0;
     std::vector<uint32_t> h_off(ns + 1, 0);
     std::vector<double> h_size(ns);
     for (uint32_t a = 0; a < ns; a++) {
@@ -750,35 +943,76 @@ int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *size
     d_size.upload(h_size.data(), ns, s);
     d_D.alloc((size_t) ns * ns);
     same.alloc((size_t) n * n);
-    const uint32_t nb = (n + GM - 1) / GM;
-    // TSKB_MATRIX_LEGACY=1: the mma.sync path, kept for A/B measurements
-    const bool use_legacy = getenv("TSKB_MATRIX_LEGACY") != nullptr;
-    if (!use_legacy) {
+    // TSKB_MATRIX=legacy: mma.sync one-hot path; =onehot: tcgen05 one-hot path even for biallelic
+    // data (both kept for A/B measurements and as cross-checks in the tests)
+    const char *mode_env = getenv("TSKB_MATRIX");
+    const bool use_legacy = mode_env != nullptr && mode_env[0] == 'l';
+    const bool biallelic = P.max_alleles_per_site <= 2 && !use_legacy
+                           && !(mode_env != nullptr && mode_env[0] == 'o');
+    if (biallelic) {
+        TSKB_CK(cudaFuncSetAttribute(tc::gram::k_gram_umma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) tc::gram::SMEM_BYTES));
+    } else if (!use_legacy) {
         TSKB_CK(cudaFuncSetAttribute(tc::k_same_umma, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int) tc::SMEM_BYTES));
     }
     for (uint32_t w = 0; w < W; w++) {
-        const uint32_t k_lo = site_index(windows[w]) - S0, k_hi = site_index(windows[w + 1]) - S0;
+        const uint32_t k_lo = col_lo[w], k_hi = col_lo[w + 1];  // padded: whole 128-byte chunks
         TSKB_CK(cudaMemsetAsync(same.p, 0, (size_t) n * n * sizeof(int32_t), s));
         if (k_hi > k_lo) {
-            if (use_legacy) {
+            if (biallelic) {
+                const uint32_t nb = (n + tc::gram::CT - 1) / tc::gram::CT;
+                tc::gram::k_gram_umma<<<dim3(nb, nb), tc::THREADS, tc::gram::SMEM_BYTES, s>>>(X.p, ld, n,
+                    k_lo, k_hi, same.p);
+                TSKB_CK_LAUNCH();
+            } else if (use_legacy) {
+                const uint32_t nb = (n + GM - 1) / GM;
                 for (uint32_t a = 0; a < P.max_alleles_per_site; a++) {
                     k_same_gemm<<<dim3(nb, nb), TB, 0, s>>>(X.p, ld, n, k_lo, k_hi, (int) a, same.p);
                     TSKB_CK_LAUNCH();
                 }
             } else {
+                const uint32_t nb = (n + tc::TM - 1) / tc::TM;
                 tc::k_same_umma<<<dim3(nb, nb), tc::THREADS, tc::SMEM_BYTES, s>>>(X.p, ld, n, k_lo, k_hi,
                     P.max_alleles_per_site, same.p);
                 TSKB_CK_LAUNCH();
             }
         }
-        k_divmat_finish<<<dim3(ns, ns), TB, 0, s>>>(same.p, n, d_off.p, ns, d_size.p, k_hi - k_lo,
-            windows[w + 1] - windows[w], (options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0, d_D.p);
+        TSKB_CK(cudaEventRecord(P.ev[2], s));
+        // one-hot paths: different = columns - same (padding columns count as same for every pair);
+        // biallelic path: different = C[i][i] + C[j][j] - 2 C[i][j]
+        const uint32_t ncols = k_hi - k_lo;
+        const int span = (options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0;
+        if (ns == n) {
+            k_divmat_pairs<<<grid_for((size_t) n * n, TB), TB, 0, s>>>(same.p, n, ncols, biallelic ? 1 : 0,
+                windows[w + 1] - windows[w], span, d_D.p);
+        } else {
+            k_divmat_finish<<<dim3(ns, ns), TB, 0, s>>>(same.p, n, d_off.p, ns, d_size.p, ncols,
+                biallelic ? 1 : 0, windows[w + 1] - windows[w], span, d_D.p);
+        }
         TSKB_CK_LAUNCH();
         TSKB_CK(cudaMemcpyAsync(result + (size_t) w * ns * ns, d_D.p, (size_t) ns * ns * sizeof(double),
             cudaMemcpyDeviceToHost, s));
+        TSKB_CK(cudaEventRecord(P.ev[3], s));
+        TSKB_CK(cudaStreamSynchronize(s));
+        float ms = 0;
+        TSKB_CK(cudaEventElapsedTime(&ms, w == 0 ? P.ev[1] : P.ev[4], P.ev[2]));
+        gemm_ms += ms;
+        TSKB_CK(cudaEventElapsedTime(&ms, P.ev[2], P.ev[3]));
+        finish_ms += ms;
+        TSKB_CK(cudaEventRecord(P.ev[4], s));
     }
     TSKB_CK(cudaStreamSynchronize(s));
+    // phase times of the last matrix call: 0 decode, 1 contraction, 2 normalise + copy to host;
+    // 7 = alleles looped per site
+    float decode_ms = 0;
+    TSKB_CK(cudaEventElapsedTime(&decode_ms, P.ev[0], P.ev[1]));
+    for (double &v : P.stats.last_kernel_ms) v = 0;
+    P.stats.last_kernel_ms[0] = decode_ms;
+    P.stats.last_kernel_ms[1] = gemm_ms;
+    P.stats.last_kernel_ms[2] = finish_ms;
+    P.stats.last_kernel_ms[7] = biallelic ? 1 : P.max_alleles_per_site;
+    P.stats.last_call_ms = decode_ms + gemm_ms + finish_ms;
     return 0;
 }
 

@@ -334,6 +334,11 @@ class LLTreeSequence:
             _p(cnt)))
         return par, cnt
 
+    def matrix_phase_ms(self):
+        """Phase times of the last site-mode divergence_matrix call (CUDA events)."""
+        k = self.engine_stats()["last_kernel_ms"]
+        return {"decode": k[0], "gemm": k[1], "finish": k[2], "alleles": int(k[7])}
+
     def genotype_matrix(self, samples=None, isolated_as_missing=True):
         n = self.tables.num_samples if samples is None else len(samples)
         s = None if samples is None else np.ascontiguousarray(samples, dtype=np.int32)
