@@ -20,6 +20,11 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum"]
 
 
+EXTRA = ["sm__pipe_tensor_cycles_active_realtime.avg.pct", "imma_cycles_active", "lts__throughput.avg.pct",
+         "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum.per_second",
+         "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct"]
+
+
 def launches(path, out):
     rows = list(csv.reader(open(path)))
     h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
@@ -68,6 +73,9 @@ def full(path, out):
             for k in KEYS:
                 if k in d:
                     f.write(f"{k:70s} {d[k]:>18s} {u[k]}\n")
+            for k in d:  # tensor-pipe and L2 figures (names carry a section prefix in newer ncu)
+                if any(x in k for x in EXTRA) and d[k] not in ("", "0"):
+                    f.write(f"{k:100s} {d[k]:>18s} {u[k]}\n")
         det = subprocess.run(["ncu", "-i", path, "--page", "details"], capture_output=True, text=True).stdout
         keep = ("Duration", "DRAM Throughput", "L2 Hit", "L1/TEX Hit", "Issued Ipc", "Eligible",
                 "Warp Cycles Per Issued", "being stalled", "stall type", "Achieved Occ",

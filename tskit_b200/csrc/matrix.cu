@@ -448,12 +448,13 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 }
 
 __global__ void __launch_bounds__(THREADS, 1) k_gram_umma(const int8_t *__restrict__ X, size_t ld, uint32_t n,
-    uint32_t k_lo, uint32_t k_hi, int32_t *__restrict__ C) {
+    uint32_t k_lo, uint32_t k_hi, const ushort2 *__restrict__ tile_list, int32_t *__restrict__ C) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t s_bar[NSTAGE];
     __shared__ uint32_t s_tmem;
-    const uint32_t bi = blockIdx.y, bj = blockIdx.x;
-    if (bi > bj) return;
+    // tiles of the upper block triangle, listed super-block by super-block: the CTAs resident at
+    // one time share a few thousand rows of X, which then stay in L2
+    const uint32_t bi = tile_list[blockIdx.x].x, bj = tile_list[blockIdx.x].y;
     const bool diag = bi == bj;
     const uint32_t i0 = bi * CT, j0 = bj * CT;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -956,14 +957,28 @@ int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *size
         TSKB_CK(cudaFuncSetAttribute(tc::k_same_umma, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int) tc::SMEM_BYTES));
     }
+    std::vector<ushort2> h_tiles;
+    DevArray<ushort2> d_tiles;
+    if (biallelic) {
+        const uint32_t nb = (n + tc::gram::CT - 1) / tc::gram::CT, SB = 12;  // 12 x 12 tiles ~ one wave
+        for (uint32_t si = 0; si < nb; si += SB) {
+            for (uint32_t sj = si; sj < nb; sj += SB) {
+                for (uint32_t bi = si; bi < std::min(nb, si + SB); bi++) {
+                    for (uint32_t bj = std::max(bi, sj); bj < std::min(nb, sj + SB); bj++) {
+                        h_tiles.push_back(make_ushort2((unsigned short) bi, (unsigned short) bj));
+                    }
+                }
+            }
+        }
+        d_tiles.upload(h_tiles.data(), h_tiles.size(), s);
+    }
     for (uint32_t w = 0; w < W; w++) {
         const uint32_t k_lo = col_lo[w], k_hi = col_lo[w + 1];  // padded: whole 128-byte chunks
         TSKB_CK(cudaMemsetAsync(same.p, 0, (size_t) n * n * sizeof(int32_t), s));
         if (k_hi > k_lo) {
             if (biallelic) {
-                const uint32_t nb = (n + tc::gram::CT - 1) / tc::gram::CT;
-                tc::gram::k_gram_umma<<<dim3(nb, nb), tc::THREADS, tc::gram::SMEM_BYTES, s>>>(X.p, ld, n,
-                    k_lo, k_hi, same.p);
+                tc::gram::k_gram_umma<<<(unsigned) h_tiles.size(), tc::THREADS, tc::gram::SMEM_BYTES, s>>>(
+                    X.p, ld, n, k_lo, k_hi, d_tiles.p, same.p);
                 TSKB_CK_LAUNCH();
             } else if (use_legacy) {
                 const uint32_t nb = (n + GM - 1) / GM;
