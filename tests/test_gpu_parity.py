@@ -98,6 +98,26 @@ def test_overlapping_sample_sets_and_eight_sets(wf_small, engines):
                      o.stat("f2", sets, idx, mode=mode), cancelling=True)
 
 
+@pytest.mark.parametrize("mode", ["branch", "site"])
+def test_more_sample_sets_than_one_sweep_carries(wf_small, engines, mode):
+    """20 sample sets: result columns are computed in batches of tuples touching <= 8 sets."""
+    ll, o = engines
+    s = wf_small.samples
+    sets = [s[10 * i: 10 * i + 7 + (i % 3)] for i in range(20)]
+    sizes, flat = sets_args(sets)
+    w = np.linspace(0, wf_small.sequence_length, 6)
+    for nm in ONE_WAY:
+        assert close(getattr(ll, nm)(sizes, flat, windows=w, mode=mode), o.stat(nm, sets, windows=w, mode=mode))
+    rng = np.random.default_rng(3)
+    for nm, k in (("divergence", 2), ("Y2", 2), ("f2", 2), ("Y3", 3), ("f3", 3), ("f4", 4)):
+        idx = rng.integers(0, 20, size=(37, k)).astype(np.int32)
+        got = getattr(ll, nm)(sizes, flat, idx, windows=w, mode=mode)
+        assert close(got, o.stat(nm, sets, idx, windows=w, mode=mode), cancelling=True), nm
+    idx = np.array([[0, 19], [7, 7]], dtype=np.int32)
+    got = ll.genetic_relatedness(sizes, flat, idx, windows=w, mode=mode, centre=False)
+    assert close(got, o.stat("genetic_relatedness", sets, idx, windows=w, mode=mode, centre=False), cancelling=True)
+
+
 @pytest.mark.parametrize("name", list(fx.ALL))
 def test_reference_fixtures(name):
     from tskit_b200.lowlevel import LLTreeSequence

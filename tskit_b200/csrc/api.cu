@@ -4,6 +4,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "plan.cuh"
 
@@ -86,6 +87,82 @@ int tuple_width(int stat_id) {
     return 0;
 }
 
+constexpr uint64_t MAX_STATE_DIM = 8;  // sample sets (state columns) of one sweep
+
+// More sample sets than one sweep carries: the result columns are independent of each other (a
+// column reads only the sets of its own index tuple), so they are computed in batches whose
+// tuples touch at most MAX_STATE_DIM distinct sets, each batch one sweep over re-numbered sets.
+// The centred genetic_relatedness reads every set in every column (the mean over all sets,
+// trees.c:4899-4959) and cannot be split.
+int batched_sample_count_stat(const Plan &P, int stat_id, int tw, uint64_t K, const uint64_t *sizes,
+    const int32_t *sets, uint64_t M, const int32_t *tuples, uint64_t W, const double *windows,
+    uint32_t options, double *result) {
+    if (stat_id == STAT_RELATEDNESS) return TSKB_ERR_UNSUPPORTED;
+    std::vector<uint64_t> off(K + 1, 0);
+    for (uint64_t k = 0; k < K; k++) off[k + 1] = off[k] + sizes[k];
+    const int width = tw > 0 ? tw : 1;
+    std::vector<int32_t> local(K, -1), b_tuples, b_sets, used;
+    std::vector<uint64_t> b_sizes, b_cols;
+    std::vector<double> out;
+    auto flush = [&]() -> int {
+        if (b_cols.empty()) return 0;
+        const uint64_t Mb = b_cols.size();
+        out.assign(W * Mb, 0.0);
+        StatSpec sp = {};
+        sp.stat_id = stat_id;
+        sp.K = (uint32_t) b_sizes.size();
+        sp.M = (uint32_t) Mb;
+        sp.tuple = (uint32_t) tw;
+        sp.sizes = b_sizes.data();
+        sp.sets = b_sets.data();
+        sp.indexes = b_tuples.data();
+        sp.W = (uint32_t) W;
+        sp.windows = windows;
+        sp.options = options;
+        sp.result = out.data();
+        int ret = run_sample_count_stat(&P, sp);
+        if (ret != 0) return ret;
+        for (uint64_t w = 0; w < W; w++) {
+            for (uint64_t j = 0; j < Mb; j++) result[w * M + b_cols[j]] = out[w * Mb + j];
+        }
+        for (int32_t k : used) local[k] = -1;
+        used.clear(); b_tuples.clear(); b_sets.clear(); b_sizes.clear(); b_cols.clear();
+        return 0;
+    };
+    for (uint64_t m = 0; m < M; m++) {
+        // sets of column m: its tuple, or set m itself for a one-way statistic
+        int32_t need[4];
+        for (int a = 0; a < width; a++) need[a] = tw > 0 ? tuples[m * tw + a] : (int32_t) m;
+        uint64_t fresh = 0;
+        for (int a = 0; a < width; a++) {
+            bool seen = local[need[a]] >= 0;
+            for (int c = 0; c < a; c++) seen |= need[c] == need[a];
+            fresh += !seen;
+        }
+        if (b_sizes.size() + fresh > MAX_STATE_DIM) {
+            int ret = flush();
+            if (ret != 0) return ret;
+        }
+        for (int a = 0; a < width; a++) {
+            const int32_t k = need[a];
+            if (local[k] < 0) {
+                local[k] = (int32_t) b_sizes.size();
+                used.push_back(k);
+                b_sizes.push_back(sizes[k]);
+                b_sets.insert(b_sets.end(), sets + off[k], sets + off[k + 1]);
+            }
+            if (tw > 0) b_tuples.push_back(local[k]);
+        }
+        b_cols.push_back(m);
+        // a one-way batch must keep column j = set j: flush when full
+        if (tw == 0 && b_sizes.size() == MAX_STATE_DIM) {
+            int ret = flush();
+            if (ret != 0) return ret;
+        }
+    }
+    return flush();
+}
+
 // Common path of every sample-count statistic; check precedence follows the
 // reference call chain: index tuples (check_sample_stat_inputs, trees.c:4667)
 // -> sample sets (trees.c:2191) -> duplicates (2207) -> mode (2053) -> dims
@@ -139,6 +216,11 @@ int sample_count_stat(const tskb_treeseq_t *self, int stat_id, uint64_t K, const
             return TSKB_ERR_TIME_UNCALIBRATED;
         }
         if (stat_id == STAT_TABULATED && K != 1) return TSKB_ERR_UNSUPPORTED;
+        if (K > MAX_STATE_DIM) {
+            if (sets_on_device || result_on_device) return TSKB_ERR_UNSUPPORTED;
+            return batched_sample_count_stat(P, stat_id, tw, K, sizes, sets, M, tuples, num_windows,
+                windows, options, result);
+        }
         StatSpec sp = {};
         sp.stat_id = stat_id;
         sp.K = (uint32_t) K;

@@ -199,7 +199,7 @@ struct DeltaOut {
 template <int STAT, int KP, int NP>
 __device__ __forceinline__ void pieces_to_deltas(const SumP &sp, const IVec<KP> &totals,
     const IVec<KP> (&st)[NP], const double (&bl)[NP], const uint32_t (&bp0)[NP],
-    const uint32_t (&bp1)[NP], const DeltaOut &out, uint32_t m0, uint32_t m1) {
+    const uint32_t (&bp1)[NP], const DeltaOut &out, uint32_t m0, uint32_t m1, const ColP &first_col) {
     const uint32_t lane = threadIdx.x & 31u;
     bool valid[NP], live[NP], merge_next[NP], merged_prev[NP];
 #pragma unroll
@@ -215,7 +215,7 @@ __device__ __forceinline__ void pieces_to_deltas(const SumP &sp, const IVec<KP> 
         merged_prev[q] = valid[q] && lane > 0u && prev_bp1 == bp0[q];  // prev_bp1 of padding never matches
     }
     for (uint32_t m = m0; m < m1; m++) {
-        const ColP col = out.cols[m];
+        const ColP col = m == m0 ? first_col : out.cols[m];  // the first column stays in registers
         double *Dm = out.D + (size_t) (m - m0) * out.Tp1;
 #pragma unroll
         for (int q = 0; q < NP; q++) {
@@ -402,12 +402,13 @@ __global__ void __launch_bounds__(TB) k_branch_summary(uint32_t npp,
     const uint32_t ntiles = (npp + SUM_TILE - 1) / SUM_TILE;
     // software pipeline: the next tile's loads are in flight while this one is evaluated
     PieceRegs<KP> cur, nxt;
+    const ColP first_col = out.cols[m0];
     uint32_t tile = blockIdx.x;
     if (tile < ntiles) cur.load(tile, npp, q_bp0, q_bp1, q_bl, pval);
     for (; tile < ntiles; tile += gridDim.x) {
         const uint32_t tn = tile + gridDim.x;
         if (tn < ntiles) nxt.load(tn, npp, q_bp0, q_bp1, q_bl, pval);
-        pieces_to_deltas<STAT, KP, SUM_IPT>(sp, totals, cur.st, cur.bl, cur.bp0, cur.bp1, out, m0, m1);
+        pieces_to_deltas<STAT, KP, SUM_IPT>(sp, totals, cur.st, cur.bl, cur.bp0, cur.bp1, out, m0, m1, first_col);
         cur = nxt;
     }
 }
