@@ -167,7 +167,16 @@ def build(t, a=None, b=None):
                 changed = True
     if os.environ.get("TSKB_ORDER", "").startswith("l"):
         height = level[rank_node[piece_rank]].astype(np.int64)
-    real = np.nonzero(pc_x[:P] >= 0)[0]
+    # pieces that are computed: with a branch above them, or holding the state a mutation reads
+    mut_piece = np.zeros(t.num_mutations, dtype=np.int64)
+    for m in range(t.num_mutations):
+        x = t.sites_position[t.mutations_site[m]]
+        r = rank[t.mutations_node[m]]
+        lo, hi = poff[r], poff[r + 1]
+        mut_piece[m] = lo + np.searchsorted(pc_x[lo:hi], x, side="right") - 1
+    needed = (pc_x[:P] >= 0) & (pc_bl[:P] != 0)
+    needed[mut_piece[pc_x[mut_piece] >= 0]] = True
+    real = np.nonzero(needed)[0]
     if os.environ.get("TSKB_ORDER", "").startswith("x"):
         real = real[np.argsort(pc_x[real], kind="stable")]
     order = real[np.argsort(height[real], kind="stable")]
@@ -184,7 +193,7 @@ def build(t, a=None, b=None):
     sample_index = np.full(N, -1, dtype=np.int64)
     sample_index[np.nonzero(is_sample)[0]] = np.arange(n)
     pos = level_begin[:-1].astype(np.int64)[hs] + (np.arange(len(order)) - begin[hs])
-    perm = np.zeros(P + 1, dtype=np.int64)
+    perm = np.full(P + 1, npp + n, dtype=np.int64)
     perm[order] = pos
     si = sample_index[rank_node]
     perm[poff[:N]] = np.where(si >= 0, npp + si, npp + n)
@@ -205,12 +214,7 @@ def build(t, a=None, b=None):
     for j, p in zip(pos, order):
         refs[q_off[j]:q_off[j] + len(ref_lists[p])] = np.sort(perm[ref_lists[p]])
     # sites
-    mut_src = np.zeros(t.num_mutations, dtype=np.int32)
-    for m in range(t.num_mutations):
-        x = t.sites_position[t.mutations_site[m]]
-        r = rank[t.mutations_node[m]]
-        lo, hi = poff[r], poff[r + 1]
-        mut_src[m] = perm[lo + np.searchsorted(pc_x[lo:hi], x, side="right") - 1]
+    mut_src = perm[mut_piece].astype(np.int32)
     return dict(ev_pos=ev_pos, ev_child=ev_child.astype(np.int32), ev_sign=ev_sign, voff=voff,
                 q_off=q_off, refs=refs, q_bp0=q_bp0, q_bp1=q_bp1, q_bl=q_bl, bp_pos=bp_pos, level=level,
                 rank_node=rank_node, level_begin=level_begin, mut_src=mut_src)

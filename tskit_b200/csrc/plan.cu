@@ -387,12 +387,24 @@ __global__ void k_relax_height(uint32_t P, const uint32_t *ch_off, const uint32_
     }
 }
 
-__global__ void k_height_keys(uint32_t P, const double *pc_x, const uint32_t *height, uint32_t *key,
+__global__ void k_height_keys(uint32_t P, const uint8_t *needed, const uint32_t *height, uint32_t *key,
     uint32_t *val, uint32_t init_key) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
-    key[p] = pc_x[p] >= 0.0 ? height[p] : init_key;  // INIT pieces sort last and are dropped
+    key[p] = needed[p] ? height[p] : init_key;  // INIT and unneeded pieces sort last and are dropped
     val[p] = p;
+}
+
+// A piece without a branch above it (a root, or a detached node) is no other piece's child over
+// its span and adds nothing to a branch statistic: it is computed only if a mutation sits on it
+// (site mode reads state[mutation.node], trees.c:1744-1763).
+__global__ void k_needed_branch(uint32_t P, const double *pc_x, const double *pc_bl, uint8_t *needed) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) needed[p] = pc_x[p] >= 0.0 && pc_bl[p] != 0.0;
+}
+__global__ void k_needed_mutation(uint32_t Mu, const int32_t *mut_src, const double *pc_x, uint8_t *needed) {
+    uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < Mu && pc_x[mut_src[m]] >= 0.0) needed[mut_src[m]] = 1;
 }
 
 // processing order: pieces by (height, secondary order); every height padded to whole tiles.
@@ -457,12 +469,12 @@ __global__ void k_x_keys(uint32_t P, const double *pc_x, uint64_t *key, uint32_t
     val[p] = p;
 }
 
-__global__ void k_height_keys_of(uint32_t P, const uint32_t *piece, const double *pc_x,
+__global__ void k_height_keys_of(uint32_t P, const uint32_t *piece, const uint8_t *needed,
     const uint32_t *height, uint32_t *key, uint32_t init_key) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     uint32_t p = piece[i];
-    key[i] = pc_x[p] >= 0.0 ? height[p] : init_key;
+    key[i] = needed[p] ? height[p] : init_key;
 }
 
 __global__ void k_level_as_height(uint32_t P, const uint32_t *piece_rank, const int32_t *rank_node,
@@ -896,6 +908,25 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK(cudaStreamSynchronize(s));
     }
 
+    // ---- mutations: the (node-major) piece holding state[mutation.node] at the site; needed pieces
+    DevArray<uint8_t> needed;
+    needed.alloc((size_t) P.P + 1);
+    k_needed_branch<<<grid_for(P.P, TB), TB, 0, s>>>(P.P, pc_x.p, pc_bl.p, needed.p);
+    TSKB_CK_LAUNCH();
+    P.site_pos.upload(t->site_position, P.S, s);
+    P.mut_node.upload(t->mutation_node, P.Mu, s);
+    P.mut_src.alloc(P.Mu);
+    if (P.Mu) {
+        const uint32_t Mu = (uint32_t) P.Mu;
+        DevArray<int32_t> d_msite;
+        d_msite.upload(t->mutation_site, Mu, s);
+        k_mut_src<<<grid_for(Mu, TB), TB, 0, s>>>(d_msite.p, P.mut_node.p, Mu, P.site_pos.p, rank.p,
+            poff.p, pc_x.p, P.mut_src.p);
+        k_needed_mutation<<<grid_for(Mu, TB), TB, 0, s>>>(Mu, P.mut_src.p, pc_x.p, needed.p);
+        TSKB_CK_LAUNCH();
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
+
     // ---- references of every piece, heights, processing order
     DevArray<uint32_t> perm;  // node-major piece -> state slot
     {
@@ -976,12 +1007,12 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
                 k_x_keys<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, pc_x.p, k64.p, v0.p);
                 TSKB_CK_LAUNCH();
                 sort_pairs(tmp, k64.p, k64o.p, v0.p, vin.p, Pn, 64, s);
-                k_height_keys_of<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, vin.p, pc_x.p, height.p, kin.p,
+                k_height_keys_of<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, vin.p, needed.p, height.p, kin.p,
                     P.nheights);
                 TSKB_CK_LAUNCH();
                 TSKB_CK(cudaStreamSynchronize(s));
             } else {
-                k_height_keys<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, pc_x.p, height.p, kin.p, vin.p,
+                k_height_keys<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, needed.p, height.p, kin.p, vin.p,
                     P.nheights);
                 TSKB_CK_LAUNCH();
             }
@@ -1015,6 +1046,10 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         P.q_bp0.alloc(P.npp); P.q_bp1.alloc(P.npp); P.q_bl.alloc(P.npp);
         P.q_off.alloc((size_t) P.npp + 1); q_cnt.alloc((size_t) P.npp + 1);
         perm.alloc((size_t) Pn + 1);
+        // default: the zero slot (pieces that are not computed are never referenced)
+        k_fill_u32<<<grid_for((size_t) Pn + 1, TB), TB, 0, s>>>(perm.p, (size_t) Pn + 1,
+            P.npp + P.num_samples);
+        TSKB_CK_LAUNCH();
         TSKB_CK(cudaMemsetAsync(q_cnt.p, 0, ((size_t) P.npp + 1) * sizeof(uint32_t), s));
         if (P.npp) {
             TSKB_CK(cudaMemsetAsync(P.q_bp0.p, 0, (size_t) P.npp * sizeof(uint32_t), s));
@@ -1091,18 +1126,11 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         P.h_site_pos.assign(t->site_position, t->site_position + S);
         P.site_lo = (uint32_t) (std::lower_bound(P.h_site_pos.begin(), P.h_site_pos.end(), a) - P.h_site_pos.begin());
         P.site_hi = (uint32_t) (std::lower_bound(P.h_site_pos.begin(), P.h_site_pos.end(), b) - P.h_site_pos.begin());
-        P.site_pos.upload(t->site_position, S, s);
         P.site_moff.upload(moff.data(), S + 1, s);
         P.site_aoff.upload(aoff.data(), S + 1, s);
-        P.mut_node.upload(t->mutation_node, Mu, s);
         P.mut_allele.upload(m_allele.data(), Mu, s);
         P.mut_alt.upload(m_alt.data(), Mu, s);
-        P.mut_src.alloc(Mu);
         if (Mu) {
-            DevArray<int32_t> d_msite;
-            d_msite.upload(t->mutation_site, Mu, s);
-            k_mut_src<<<grid_for(Mu, TB), TB, 0, s>>>(d_msite.p, P.mut_node.p, Mu, P.site_pos.p,
-                rank.p, poff.p, pc_x.p, P.mut_src.p);
             k_translate<<<grid_for(Mu, TB), TB, 0, s>>>(P.mut_src.p, Mu, perm.p);
             TSKB_CK_LAUNCH();
             TSKB_CK(cudaStreamSynchronize(s));
