@@ -53,25 +53,34 @@ int check_windows(const Plan &P, uint64_t num_windows, const double *windows, bo
 // check of tsk_treeseq_sample_count_stat (trees.c:2195-2213)
 int check_sample_sets(const Plan &P, uint64_t K, const uint64_t *sizes, const int32_t *sets) {
     if (K == 0) return TSKB_ERR_INSUFFICIENT_SAMPLE_SETS;
+    // one pass; a duplicate is reported only if no set fails the earlier checks (the reference
+    // validates every set before it looks for duplicates).  `seen` persists across calls: an entry
+    // is current when it lies in this call's stamp range, so it is never cleared.
+    std::lock_guard<std::mutex> lock(P.mu);
+    std::vector<uint32_t> &seen = P.seen_stamp;
+    if (seen.size() != P.num_samples || P.seen_epoch > 0xffffffffu - 2 * K - 2) {
+        seen.assign(P.num_samples, 0);
+        P.seen_epoch = 0;
+    }
+    const uint32_t base = (uint32_t) P.seen_epoch + 1;
+    P.seen_epoch += K;
+    const int32_t N = (int32_t) P.N;
+    const int32_t *map = P.sample_index_map.data();
+    bool duplicate = false;
     uint64_t j = 0;
     for (uint64_t k = 0; k < K; k++) {
         if (sizes[k] == 0) return TSKB_ERR_EMPTY_SAMPLE_SET;
+        const uint32_t stamp = base + (uint32_t) k;
         for (uint64_t l = 0; l < sizes[k]; l++, j++) {
-            int32_t u = sets[j];
-            if (u < 0 || u >= (int32_t) P.N) return TSKB_ERR_NODE_OUT_OF_BOUNDS;
-            if (P.sample_index_map[u] == -1) return TSKB_ERR_BAD_SAMPLES;
+            const int32_t u = sets[j];
+            if (u < 0 || u >= N) return TSKB_ERR_NODE_OUT_OF_BOUNDS;
+            const int32_t si = map[u];
+            if (si == -1) return TSKB_ERR_BAD_SAMPLES;
+            duplicate |= seen[si] == stamp;
+            seen[si] = stamp;
         }
     }
-    std::vector<uint32_t> seen(P.num_samples, 0);
-    j = 0;
-    for (uint64_t k = 0; k < K; k++) {
-        for (uint64_t l = 0; l < sizes[k]; l++, j++) {
-            uint32_t &slot = seen[P.sample_index_map[sets[j]]];
-            if (slot == k + 1) return TSKB_ERR_DUPLICATE_SAMPLE;
-            slot = (uint32_t) k + 1;
-        }
-    }
-    return 0;
+    return duplicate ? TSKB_ERR_DUPLICATE_SAMPLE : 0;
 }
 
 int tuple_width(int stat_id) {

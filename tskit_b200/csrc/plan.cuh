@@ -119,6 +119,8 @@ struct Plan {
 
     // per-call scratch + statistics
     mutable std::mutex mu;
+    mutable std::vector<uint32_t> seen_stamp;  // argument validation scratch (api.cu:check_sample_sets)
+    mutable uint64_t seen_epoch = 0;
     mutable Arena arena;
     mutable tskb_stats_t stats = {};
     mutable unsigned long long *stats_trace = nullptr;  // TSKB_TRACE: per-tile timeline of the last call (arena)
