@@ -220,24 +220,12 @@ __device__ __forceinline__ void pieces_to_deltas(const SumP &sp, const IVec<KP> 
 #pragma unroll
         for (int q = 0; q < NP; q++) {
             double G = 0.0;
-#ifdef TSKB_DBG_NOF
-            if (live[q]) G = bl[q] * (double) st[q].v[0];
-#else
             if (live[q]) G = bl[q] * F_branch<STAT, KP>(sp, col, m, st[q], totals);
-#endif
             const double G_next = __shfl_down_sync(0xffffffffu, G, 1);
             if (!valid[q]) continue;
-#ifdef TSKB_DBG_NORED
-            if (G + G_next == 1.2345e-300) atomicAdd(Dm + bp0[q], G);
-#elif defined(TSKB_DBG_HASH)
-            if (!merged_prev[q] && G != 0.0) atomicAdd(Dm + (bp0[q] * 2654435761u) % (out.Tp1 - 1), G);
-            const double v = merge_next[q] ? G_next - G : -G;
-            if (v != 0.0) atomicAdd(Dm + (bp1[q] * 2654435761u) % (out.Tp1 - 1), v);
-#else
             if (!merged_prev[q] && G != 0.0) atomicAdd(Dm + bp0[q], G);
             const double v = merge_next[q] ? G_next - G : -G;
             if (v != 0.0) atomicAdd(Dm + bp1[q], v);
-#endif
         }
     }
 }
