@@ -98,6 +98,29 @@ def test_overlapping_sample_sets_and_eight_sets(wf_small, engines):
                      o.stat("f2", sets, idx, mode=mode), cancelling=True)
 
 
+def test_many_result_columns(wf_small, engines, monkeypatch):
+    """6 or more result columns take the lanes-are-columns branch summary (up to 32 columns per
+    pass, so 40 tuples need two passes); both kernels against the oracle."""
+    ll, o = engines
+    s = wf_small.samples
+    sets = [s[25 * i: 25 * i + 20 + i] for i in range(8)]
+    sizes, flat = sets_args(sets)
+    rng = np.random.default_rng(11)
+    for w in (np.linspace(0, wf_small.sequence_length, 12), np.array([0.0, wf_small.sequence_length])):
+        pairs = np.array([(i, j) for i in range(8) for j in range(i, 8)], dtype=np.int32)  # 36 columns
+        want = o.stat("divergence", sets, pairs, windows=w, mode="branch")
+        assert close(ll.divergence(sizes, flat, pairs, windows=w, mode="branch"), want)
+        quads = rng.integers(0, 8, size=(40, 4)).astype(np.int32)
+        want4 = o.stat("f4", sets, quads, windows=w, mode="branch")
+        assert close(ll.f4(sizes, flat, quads, windows=w, mode="branch"), want4, cancelling=True)
+        want1 = o.stat("Y1", sets, windows=w, mode="branch", polarised=True)
+        assert close(ll.Y1(sizes, flat, windows=w, mode="branch", polarised=True), want1)
+        monkeypatch.setenv("TSKB_NO_COLS_KERNEL", "1")
+        assert close(ll.divergence(sizes, flat, pairs, windows=w, mode="branch"), want)
+        assert close(ll.f4(sizes, flat, quads, windows=w, mode="branch"), want4, cancelling=True)
+        monkeypatch.delenv("TSKB_NO_COLS_KERNEL")
+
+
 @pytest.mark.parametrize("mode", ["branch", "site"])
 def test_more_sample_sets_than_one_sweep_carries(wf_small, engines, mode):
     """20 sample sets: result columns are computed in batches of tuples touching <= 8 sets."""

@@ -413,6 +413,72 @@ __global__ void __launch_bounds__(TB) k_branch_summary(uint32_t npp,
     }
 }
 
+// ---- many result columns: lanes are columns
+// With M columns the kernel above issues M reductions per piece, each lane of an instruction to
+// its own cache line.  Here a warp walks its pieces one after the other and lane m evaluates
+// column m: the reductions of one piece go to M consecutive doubles (D is laid out
+// [breakpoint][column] for this kernel), one or two L2 requests instead of M, and a piece that
+// starts where the previous one ends is merged with it in registers.  Up to 32 columns per pass.
+template <int STAT, int KP>
+__global__ void __launch_bounds__(TB) k_branch_summary_cols(uint32_t npp,
+    const uint32_t *__restrict__ q_bp0, const uint32_t *__restrict__ q_bp1,
+    const double *__restrict__ q_bl, const IVec<KP> *__restrict__ pval, SumP sp, IVec<KP> totals,
+    DeltaOut out, uint32_t m0, uint32_t ncols) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nchunks = (npp + 31) / 32;
+    const bool mine = lane < ncols;
+    const uint32_t m = m0 + (mine ? lane : 0);
+    const ColP col = out.cols[m];
+    double *Dl = out.D + lane;  // D[bp * ncols + lane]
+    for (uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += warps) {
+        const uint32_t j = chunk * 32 + lane;
+        IVec<KP> st = ivec_zero<KP>();
+        double bl = 0.0;
+        uint32_t bp0 = 0, bp1 = NO_PIECE;
+        if (j < npp) {
+            st = pval[j]; bl = q_bl[j]; bp0 = q_bp0[j]; bp1 = q_bp1[j];
+        }
+        double G_prev = 0.0;
+        uint32_t end_prev = NO_PIECE;  // breakpoint the previous piece ends at; NO_PIECE: none pending
+        for (int i = 0; i < 32; i++) {
+            IVec<KP> s_i;
+#pragma unroll
+            for (int k = 0; k < KP; k++) s_i.v[k] = __shfl_sync(0xffffffffu, st.v[k], i);
+            const double bl_i = __shfl_sync(0xffffffffu, bl, i);
+            const uint32_t b0 = __shfl_sync(0xffffffffu, bp0, i), b1 = __shfl_sync(0xffffffffu, bp1, i);
+            double G = 0.0;
+            const bool valid = b1 != NO_PIECE;  // warp-uniform
+            if (valid && !(sp.skip_zero_bl && bl_i == 0.0)) G = bl_i * F_branch<STAT, KP>(sp, col, m, s_i, totals);
+            if (valid && end_prev == b0) {
+                const double v = G - G_prev;
+                if (mine && v != 0.0) atomicAdd(Dl + (size_t) b0 * ncols, v);
+            } else {
+                if (end_prev != NO_PIECE && mine && G_prev != 0.0) atomicAdd(Dl + (size_t) end_prev * ncols, -G_prev);
+                if (valid && mine && G != 0.0) atomicAdd(Dl + (size_t) b0 * ncols, G);
+            }
+            G_prev = G;
+            end_prev = valid ? b1 : NO_PIECE;
+        }
+        if (end_prev != NO_PIECE && mine && G_prev != 0.0) atomicAdd(Dl + (size_t) end_prev * ncols, -G_prev);
+    }
+}
+
+// D[bp][col] -> Dt[col][bp]
+__global__ void k_transpose_deltas(const double *__restrict__ D, uint32_t Tp1, uint32_t ncols, double *Dt) {
+    __shared__ double tile[32][33];
+    const uint32_t b0 = blockIdx.x * 32;
+    for (uint32_t r = threadIdx.y; r < 32; r += blockDim.y) {
+        const uint32_t bp = b0 + r;
+        tile[r][threadIdx.x] = (bp < Tp1 && threadIdx.x < ncols) ? D[(size_t) bp * ncols + threadIdx.x] : 0.0;
+    }
+    __syncthreads();
+    for (uint32_t cidx = threadIdx.y; cidx < ncols; cidx += blockDim.y) {
+        const uint32_t bp = b0 + threadIdx.x;
+        if (bp < Tp1) Dt[(size_t) cidx * Tp1 + bp] = tile[threadIdx.x][cidx];
+    }
+}
+
 // ---------------------------------------------------------------- phase 3, branch mode
 // S = inclusive prefix sum of D over the breakpoints (the reference's running sum after the diffs
 // of breakpoint i, cub::DeviceScan per column); window w gets the integral of S over it:
@@ -577,6 +643,7 @@ __global__ void k_count_at(const int32_t *tracked, uint32_t nt, uint32_t nq, uin
 // ---------------------------------------------------------------- driver
 
 constexpr size_t DELTA_BUDGET = size_t(1) << 30;   // bytes of per-breakpoint deltas held at once
+constexpr uint32_t COLS_KERNEL_MIN = 6;            // result columns from which lanes-are-columns pays
 
 struct CallCtx {
     const Plan *P;
@@ -646,8 +713,12 @@ void run_branch(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
     Arena &A = P.arena;
     const uint32_t Tp1 = P.T + 1;
     const size_t col_bytes = (size_t) Tp1 * sizeof(double);
-    const uint32_t mc = (uint32_t) std::min<size_t>(M, std::max<size_t>(1, DELTA_BUDGET / col_bytes));
+    // 6 or more columns: lanes-are-columns kernel, at most 32 columns per pass
+    const bool by_cols = M >= COLS_KERNEL_MIN && getenv("TSKB_NO_COLS_KERNEL") == nullptr;
+    uint32_t mc = (uint32_t) std::min<size_t>(M, std::max<size_t>(1, DELTA_BUDGET / col_bytes));
+    if (by_cols) mc = std::min<uint32_t>(mc, 32);
     double *D = A.get<double>((size_t) mc * Tp1);
+    double *Dx = by_cols ? A.get<double>((size_t) mc * Tp1) : nullptr;  // [breakpoint][column] deltas
     size_t scan_bytes = 0;
     TSKB_CK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, D, D, (int) std::max<uint32_t>(Tp1 - 1, 1), c.s));
     void *scan_tmp = A.get<char>(scan_bytes);
@@ -660,6 +731,27 @@ void run_branch(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
     const uint32_t ntiles = (P.npp + SUM_TILE - 1) / SUM_TILE;
     for (uint32_t m0 = 0; m0 < M; m0 += mc) {
         const uint32_t m1 = std::min(M, m0 + mc);
+        if (by_cols) {
+            const uint32_t nc = m1 - m0;
+            TSKB_CK(cudaMemsetAsync(Dx, 0, (size_t) nc * col_bytes, c.s));
+            DeltaOut ox = { Dx, Tp1, c.sumP.cols };
+            int per_sm_c = 1;
+            TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_branch_summary_cols<STAT, KP>, TB, 0));
+            if (P.npp > 0) {
+                const uint32_t nchunks = (P.npp + 31) / 32;
+                const uint32_t grid = std::min<uint32_t>((nchunks + 7) / 8, (uint32_t) (sms * std::max(per_sm_c, 1)));
+                k_branch_summary_cols<STAT, KP><<<grid, TB, 0, c.s>>>(P.npp, P.q_bp0.p, P.q_bp1.p, P.q_bl.p,
+                    pval, c.sumP, totals, ox, m0, nc);
+                TSKB_CK_LAUNCH();
+                c.launches++;
+            }
+            k_transpose_deltas<<<(Tp1 + 31) / 32, dim3(32, 8), 0, c.s>>>(Dx, Tp1, nc, D);
+            TSKB_CK_LAUNCH();
+            c.launches++;
+            if (m0 == 0) TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+            finish_columns(c, D, Tp1, m0, nc, scan_tmp, scan_bytes);
+            continue;
+        }
         TSKB_CK(cudaMemsetAsync(D, 0, (size_t) (m1 - m0) * col_bytes, c.s));
         if (ntiles > 0) {
             // more CTAs than are resident: later ones start as earlier ones finish (measured 8 % faster
