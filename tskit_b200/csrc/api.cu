@@ -199,34 +199,47 @@ int sample_count_stat(const tskb_treeseq_t *self, int stat_id, uint64_t K, const
         } else if (stat_id != STAT_TABULATED) {
             M = K;
         }
-        if (host_sets_for_checks != nullptr || K == 0) {
-            int ret = check_sample_sets(P, K, sizes, host_sets_for_checks);
+        // Sample sets are validated on the device while their weights are written (stats.cu:
+        // k_set_weights) and the verdict is read back with the result.  The host loop runs only
+        // where it decides the precedence of an error found below, or for an empty set (whose
+        // position among element errors matters), or when there are too many sets for one sweep.
+        bool sets_checked = false;
+        auto host_check = [&]() -> int {
+            if (sets_checked || (host_sets_for_checks == nullptr && K != 0)) return 0;
+            sets_checked = true;
+            return check_sample_sets(P, K, sizes, host_sets_for_checks);
+        };
+        bool any_empty = K == 0 || K > MAX_STATE_DIM;
+        for (uint64_t k = 0; k < K; k++) any_empty |= sizes[k] == 0;
+        if (any_empty) {
+            int ret = host_check();
             if (ret != 0) return ret;
         }
+#define LATER(code) do { int r__ = host_check(); return r__ != 0 ? r__ : (code); } while (0)
         bool site = options & TSKB_STAT_SITE, branch = options & TSKB_STAT_BRANCH,
              node = options & TSKB_STAT_NODE;
         if (!(site || branch || node)) {
             site = true;
             options |= TSKB_STAT_SITE;
         }
-        if (site + branch + node > 1) return TSKB_ERR_MULTIPLE_STAT_MODES;
-        if (K < 1) return TSKB_ERR_BAD_STATE_DIMS;
-        if (M < 1) return TSKB_ERR_BAD_RESULT_DIMS;
+        if (site + branch + node > 1) LATER(TSKB_ERR_MULTIPLE_STAT_MODES);
+        if (K < 1) LATER(TSKB_ERR_BAD_STATE_DIMS);
+        if (M < 1) LATER(TSKB_ERR_BAD_RESULT_DIMS);
         double default_windows[2] = { 0, P.L };
         if (windows == nullptr) {
             num_windows = 1;
             windows = default_windows;
         } else {
             int ret = check_windows(P, num_windows, windows, true);
-            if (ret != 0) return ret;
+            if (ret != 0) LATER(ret);
         }
-        if (node) return TSKB_ERR_UNSUPPORTED;  // W x N x M output: not on this path
+        if (node) LATER(TSKB_ERR_UNSUPPORTED);  // W x N x M output: not on this path
         if (branch && P.time_uncalibrated && !(options & TSKB_STAT_ALLOW_TIME_UNCALIBRATED)) {
-            return TSKB_ERR_TIME_UNCALIBRATED;
+            LATER(TSKB_ERR_TIME_UNCALIBRATED);
         }
-        if (stat_id == STAT_TABULATED && K != 1) return TSKB_ERR_UNSUPPORTED;
+        if (stat_id == STAT_TABULATED && K != 1) LATER(TSKB_ERR_UNSUPPORTED);
         if (K > MAX_STATE_DIM) {
-            if (sets_on_device || result_on_device) return TSKB_ERR_UNSUPPORTED;
+            if (sets_on_device || result_on_device) LATER(TSKB_ERR_UNSUPPORTED);
             return batched_sample_count_stat(P, stat_id, tw, K, sizes, sets, M, tuples, num_windows,
                 windows, options, result);
         }
@@ -247,6 +260,7 @@ int sample_count_stat(const tskb_treeseq_t *self, int stat_id, uint64_t K, const
         sp.f_table = f_table;
         sp.table_rows = table_rows;
         return run_sample_count_stat(&P, sp);
+#undef LATER
     });
 }
 

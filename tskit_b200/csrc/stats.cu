@@ -164,15 +164,30 @@ __device__ __forceinline__ double F_branch(const SumP &P, const ColP &c, int m, 
 
 // ---------------------------------------------------------------- phase 0
 
-// sample sets -> 0/1 weight columns of the samples' INIT slots (trees.c:2195-2213)
+// sample sets -> 0/1 weight columns of the samples' INIT slots (trees.c:2195-2213), and the
+// argument checks of tsk_treeseq_check_sample_sets (trees.c:2114-2149) and of the duplicate scan
+// (trees.c:2201-2214) on the way: verr = smallest (position << 1 | kind) of an element that is out
+// of bounds (kind 0) or not a sample (kind 1) -- the reference reports the first one in order --
+// and dup = some sample listed twice in one set.
 template <int KP>
 __global__ void k_set_weights(const int32_t *sets, const uint32_t *set_off, uint32_t K,
-    uint32_t total, const int32_t *sample_index, IVec<KP> *init) {
+    uint32_t total, const int32_t *sample_index, int32_t N, IVec<KP> *init, unsigned long long *verr,
+    int *dup) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= total) return;
     uint32_t k = upper_bound_dev(set_off, K + 1, j) - 1;
-    // a sample may be in several sets (trees.c:2201-2214): distinct columns, no race
-    init[sample_index[sets[j]]].v[k] = 1;
+    const int32_t u = sets[j];
+    if (u < 0 || u >= N) {
+        atomicMin(verr, (unsigned long long) j << 1);
+        return;
+    }
+    const int32_t si = sample_index[u];
+    if (si < 0) {
+        atomicMin(verr, ((unsigned long long) j << 1) | 1ull);
+        return;
+    }
+    // a sample may be in several sets (trees.c:2201-2214): distinct columns
+    if (atomicExch(&init[si].v[k], 1) != 0) *dup = 1;
 }
 
 // ---------------------------------------------------------------- branch-mode running sum
@@ -838,9 +853,15 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     c.d_windows = A.get<double>(W + 1);
     TSKB_CK(cudaMemcpyAsync(c.d_windows, sp.windows, (W + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
     TSKB_CK(cudaMemsetAsync(init, 0, ((size_t) P.num_samples + 1) * sizeof(IVec<KP>), s));
+    // device flags, read back in one copy: [0] validation key, [1] duplicate flag | sweep error flag
+    unsigned long long *d_verr = A.get<unsigned long long>(2);
+    int *d_dup = reinterpret_cast<int *>(d_verr + 1);
+    c.d_err = d_dup + 1;
+    TSKB_CK(cudaMemsetAsync(d_verr, 0xff, sizeof(unsigned long long), s));
+    TSKB_CK(cudaMemsetAsync(d_dup, 0, 2 * sizeof(int), s));
     if (total) {
         k_set_weights<KP><<<grid_for(total, TB), TB, 0, s>>>(d_sets, d_off, K, (uint32_t) total,
-            P.d_sample_index.p, init);
+            P.d_sample_index.p, (int32_t) P.N, init, d_verr, d_dup);
         TSKB_CK_LAUNCH();
         c.launches++;
     }
@@ -883,8 +904,6 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         sumP.table = d_tab;
         sumP.table_rows = (uint32_t) sp.table_rows;
     }
-    c.d_err = A.get<int>(1);
-    TSKB_CK(cudaMemsetAsync(c.d_err, 0, sizeof(int), s));
     c.d_result = sp.result_on_device ? sp.result : A.get<double>((size_t) W * M);
     TSKB_CK(cudaEventRecord(P.ev[1], s));
 
@@ -910,8 +929,8 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         default: return TSKB_ERR_BAD_PARAM_VALUE;
     }
     TSKB_CK(cudaEventRecord(P.ev[5], s));
-    int h_err = 0;
-    TSKB_CK(cudaMemcpyAsync(&h_err, c.d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    unsigned long long h_flags[2] = { ~0ull, 0 };
+    TSKB_CK(cudaMemcpyAsync(h_flags, d_verr, sizeof(h_flags), cudaMemcpyDeviceToHost, s));
     if (!sp.result_on_device) {
         TSKB_CK(cudaMemcpyAsync(sp.result, c.d_result, (size_t) W * M * sizeof(double),
             cudaMemcpyDeviceToHost, s));
@@ -926,6 +945,11 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     TSKB_CK(cudaEventElapsedTime(&ms, P.ev[0], P.ev[6]));
     P.stats.last_call_ms = ms;
     P.stats.last_launches = c.launches;
+    // sample-set errors found on the device: same codes and precedence as the host check
+    const unsigned long long h_verr = h_flags[0];
+    const int h_dup = (int) (h_flags[1] & 0xffffffffull), h_err = (int) (h_flags[1] >> 32);
+    if (h_verr != ~0ull) return (h_verr & 1ull) ? TSKB_ERR_BAD_SAMPLES : TSKB_ERR_NODE_OUT_OF_BOUNDS;
+    if (h_dup) return TSKB_ERR_DUPLICATE_SAMPLE;
     if (h_err) {
         last_error_string() = "propagation wait timed out";
         return TSKB_ERR_CUDA;
