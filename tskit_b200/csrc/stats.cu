@@ -500,6 +500,28 @@ __global__ void k_transpose_deltas(const double *__restrict__ D, uint32_t Tp1, u
 // sum over the breakpoint intervals [t_i, t_i+1) that meet it of S_i * overlap
 // (trees.c:1484-1504), span-normalised (trees.c:1920-1934).  G threads per (window, column):
 // a warp, or a whole block when there are few windows.
+// first index in [0, n) with a[idx] > x (UPPER) or a[idx] >= x (!UPPER), searched by the whole block:
+// every round narrows the range by a factor of blockDim.x with one load per thread (3 dependent
+// loads for 4.4 M breakpoints instead of 22).  Must be called by all threads of the block.
+template <bool UPPER>
+__device__ __forceinline__ uint32_t block_bound(const double *__restrict__ a, uint32_t n, double x) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > blockDim.x) {
+        const uint32_t step = (hi - lo + blockDim.x - 1) / blockDim.x;
+        const uint32_t idx = lo + threadIdx.x * step;
+        bool below = false;  // a[idx] is still left of the bound
+        if (idx < hi) below = UPPER ? !(a[idx] > x) : !(a[idx] >= x);
+        const uint32_t f = (uint32_t) __syncthreads_count(below);  // samples are monotone: a prefix is below
+        if (f == 0) return lo;
+        const uint32_t nlo = lo + (f - 1) * step + 1;
+        hi = min(hi, lo + f * step);
+        lo = nlo;
+    }
+    bool below = false;
+    if (lo + threadIdx.x < hi) below = UPPER ? !(a[lo + threadIdx.x] > x) : !(a[lo + threadIdx.x] >= x);
+    return lo + (uint32_t) __syncthreads_count(below);
+}
+
 template <int G>
 __global__ void __launch_bounds__(TB) k_window_integrate(const double *S, uint32_t Tp1,
     const double *__restrict__ bp_pos, const double *__restrict__ windows, uint32_t W, uint32_t mcols,
@@ -519,9 +541,15 @@ __global__ void __launch_bounds__(TB) k_window_integrate(const double *S, uint32
         wr = windows[w + 1];
         const double *Sm = S + (size_t) mloc * Tp1;
         // intervals meeting [wl, wr): from the one holding wl (or the first) to the last starting < wr
-        uint32_t lo = upper_bound_dev(bp_pos, T, wl);
+        uint32_t lo, hi;
+        if (G == TB) {  // one window per block: the block searches together (active is block-uniform)
+            lo = block_bound<true>(bp_pos, T, wl);
+            hi = block_bound<false>(bp_pos, T, wr);
+        } else {
+            lo = upper_bound_dev(bp_pos, T, wl);
+            hi = lower_bound_dev(bp_pos, T, wr);
+        }
         lo = lo > 0 ? lo - 1 : 0;
-        const uint32_t hi = lower_bound_dev(bp_pos, T, wr);
         for (uint32_t i = lo + gt; i < hi; i += G) {
             double a = bp_pos[i], b = bp_pos[i + 1];
             a = a > wl ? a : wl;
@@ -546,8 +574,6 @@ __global__ void __launch_bounds__(TB) k_window_integrate(const double *S, uint32
 }
 
 // ---------------------------------------------------------------- phase 2, site mode
-
-constexpr int MC = 4;  // result columns evaluated per pass over a site's alleles
 
 template <int STAT, int KP>
 __global__ void k_site_summary(uint32_t site_lo, uint32_t nsites, const uint32_t *site_moff,
@@ -668,6 +694,7 @@ struct CallCtx {
     double *d_windows;
     double *d_result;
     int *d_err;
+    uint32_t *d_counters;
     uint64_t launches;
 };
 
@@ -676,8 +703,7 @@ void launch_sweep(CallCtx &c, IVec<KP> *pval) {
     const Plan &P = *c.P;
     Arena &A = P.arena;
     if (P.ntiles == 0) return;
-    uint32_t *counters = A.get<uint32_t>(2);
-    TSKB_CK(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), c.s));
+    uint32_t *counters = c.d_counters;  // zeroed with the per-call staging copy
     unsigned long long *trace = nullptr;
     if (getenv("TSKB_TRACE") != nullptr) {
         trace = A.get<unsigned long long>((size_t) P.ntiles * 4);
@@ -842,28 +868,11 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     }
     IVec<KP> *pval = A.get<IVec<KP>>((size_t) P.npp + P.num_samples + 1);
     IVec<KP> *init = pval + P.npp;
-    uint32_t *d_off = A.get<uint32_t>(K + 1);
     const int32_t *d_sets = sp.sets;
     if (!sp.sets_on_device) {
         int32_t *tmp_sets = A.get<int32_t>(total);
         TSKB_CK(cudaMemcpyAsync(tmp_sets, sp.sets, total * sizeof(int32_t), cudaMemcpyHostToDevice, s));
         d_sets = tmp_sets;
-    }
-    TSKB_CK(cudaMemcpyAsync(d_off, h_off.data(), (K + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    c.d_windows = A.get<double>(W + 1);
-    TSKB_CK(cudaMemcpyAsync(c.d_windows, sp.windows, (W + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
-    TSKB_CK(cudaMemsetAsync(init, 0, ((size_t) P.num_samples + 1) * sizeof(IVec<KP>), s));
-    // device flags, read back in one copy: [0] validation key, [1] duplicate flag | sweep error flag
-    unsigned long long *d_verr = A.get<unsigned long long>(2);
-    int *d_dup = reinterpret_cast<int *>(d_verr + 1);
-    c.d_err = d_dup + 1;
-    TSKB_CK(cudaMemsetAsync(d_verr, 0xff, sizeof(unsigned long long), s));
-    TSKB_CK(cudaMemsetAsync(d_dup, 0, 2 * sizeof(int), s));
-    if (total) {
-        k_set_weights<KP><<<grid_for(total, TB), TB, 0, s>>>(d_sets, d_off, K, (uint32_t) total,
-            P.d_sample_index.p, (int32_t) P.N, init, d_verr, d_dup);
-        TSKB_CK_LAUNCH();
-        c.launches++;
     }
 
     SumP &sumP = c.sumP;
@@ -877,22 +886,44 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         sumP.n[k] = (double) sp.sizes[k];
         totals.v[k] = (int32_t) sp.sizes[k];
     }
-    std::vector<ColP> cols(M);
-    {
-        for (uint32_t m = 0; m < M; m++) {
-            ColP &q = cols[m];
-            int32_t t[4] = { (int32_t) (m < K ? m : 0), 0, 0, 0 };
-            for (uint32_t a = 0; a < sp.tuple; a++) t[a] = sp.indexes[(size_t) m * sp.tuple + a];
-            if (sp.stat_id == STAT_TABULATED) t[0] = 0;
-            q.i = t[0]; q.j = t[1]; q.k = t[2]; q.l = t[3];
-            q.ni = (double) sp.sizes[t[0]]; q.nj = (double) sp.sizes[t[1]];
-            q.nk = (double) sp.sizes[t[2]]; q.nl = (double) sp.sizes[t[3]];
-            q.inv = 1.0 / column_denominator(sp.stat_id, q);
-            if (!std::isfinite(q.inv)) sumP.skip_zero_bl = 0;
-        }
-        ColP *d_cols = A.get<ColP>(M);
-        TSKB_CK(cudaMemcpyAsync(d_cols, cols.data(), M * sizeof(ColP), cudaMemcpyHostToDevice, s));
-        sumP.cols = d_cols;
+    // All small per-call inputs travel in ONE host-to-device copy:
+    //   [0] validation key (all ones)  [8] duplicate flag, sweep error flag  [16] completion counters
+    //   [24] set offsets (K + 1, padded)  | result columns (M)  | window edges (W + 1)
+    const size_t off_bytes = ((size_t) (K + 1) * sizeof(uint32_t) + 7) & ~size_t(7);
+    const size_t o_off = 24, o_cols = o_off + off_bytes, o_win = o_cols + (size_t) M * sizeof(ColP);
+    const size_t stage_bytes = o_win + (size_t) (W + 1) * sizeof(double);
+    std::vector<unsigned long long> stage((stage_bytes + 7) / 8, 0);
+    char *hs = reinterpret_cast<char *>(stage.data());
+    stage[0] = ~0ull;
+    memcpy(hs + o_off, h_off.data(), (K + 1) * sizeof(uint32_t));
+    ColP *cols = reinterpret_cast<ColP *>(hs + o_cols);
+    for (uint32_t m = 0; m < M; m++) {
+        ColP &q = cols[m];
+        int32_t t[4] = { (int32_t) (m < K ? m : 0), 0, 0, 0 };
+        for (uint32_t a = 0; a < sp.tuple; a++) t[a] = sp.indexes[(size_t) m * sp.tuple + a];
+        if (sp.stat_id == STAT_TABULATED) t[0] = 0;
+        q.i = t[0]; q.j = t[1]; q.k = t[2]; q.l = t[3];
+        q.ni = (double) sp.sizes[t[0]]; q.nj = (double) sp.sizes[t[1]];
+        q.nk = (double) sp.sizes[t[2]]; q.nl = (double) sp.sizes[t[3]];
+        q.inv = 1.0 / column_denominator(sp.stat_id, q);
+        if (!std::isfinite(q.inv)) sumP.skip_zero_bl = 0;
+    }
+    memcpy(hs + o_win, sp.windows, (W + 1) * sizeof(double));
+    char *ds = A.get<char>(stage_bytes);
+    TSKB_CK(cudaMemcpyAsync(ds, hs, stage_bytes, cudaMemcpyHostToDevice, s));
+    unsigned long long *d_verr = reinterpret_cast<unsigned long long *>(ds);
+    int *d_dup = reinterpret_cast<int *>(ds + 8);
+    c.d_err = d_dup + 1;
+    c.d_counters = reinterpret_cast<uint32_t *>(ds + 16);
+    uint32_t *d_off = reinterpret_cast<uint32_t *>(ds + o_off);
+    sumP.cols = reinterpret_cast<const ColP *>(ds + o_cols);
+    c.d_windows = reinterpret_cast<double *>(ds + o_win);
+    TSKB_CK(cudaMemsetAsync(init, 0, ((size_t) P.num_samples + 1) * sizeof(IVec<KP>), s));
+    if (total) {
+        k_set_weights<KP><<<grid_for(total, TB), TB, 0, s>>>(d_sets, d_off, K, (uint32_t) total,
+            P.d_sample_index.p, (int32_t) P.N, init, d_verr, d_dup);
+        TSKB_CK_LAUNCH();
+        c.launches++;
     }
     if (sp.stat_id == STAT_TABULATED) {
         double *d_tab = A.get<double>(sp.table_rows * M);
