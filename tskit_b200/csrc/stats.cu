@@ -714,6 +714,8 @@ void launch_sweep(CallCtx &c, IVec<KP> *pval) {
     int per_sm = 1, sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
     TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PROP_TB, 0));
+    // experiments only (tools/concurrency_probe.py): leave room for another stream's kernels
+    if (const char *cap = getenv("TSKB_SWEEP_MAX_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(cap)));
     const uint32_t grid = std::min<uint32_t>(P.ntiles, (uint32_t) (sms * std::max(per_sm, 1)));
     SweepArgs a = {};
     a.ntiles = P.ntiles;
