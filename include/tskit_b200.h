@@ -52,6 +52,7 @@ extern "C" {
 #define TSKB_ERR_UNSUPPORTED_STAT_MODE (-909)
 #define TSKB_ERR_TIME_UNCALIBRATED (-910)
 #define TSKB_ERR_STAT_POLARISED_UNSUPPORTED (-911)
+#define TSKB_ERR_INSUFFICIENT_WEIGHTS (-913)
 /* engine-specific codes, outside tskit's range */
 #define TSKB_ERR_CUDA (-20001)           /* a CUDA runtime call failed */
 #define TSKB_ERR_BAD_INDEX_ORDER (-20002) /* edge indexes not in canonical order */
@@ -142,6 +143,24 @@ int tskb_treeseq_f4(const tskb_treeseq_t *self, uint64_t num_sample_sets,
     const uint64_t *sample_set_sizes, const int32_t *sample_sets,
     uint64_t num_index_tuples, const int32_t *index_tuples, uint64_t num_windows,
     const double *windows, uint32_t options, double *result);
+
+/* Weighted statistics: fp64 node states = sums of per-sample weights.
+ * tsk_treeseq_trait_covariance / _trait_correlation: one_way_weighted_method
+ * (c/tskit/trees.h:1056-1061; trees.c:3976-4110), `weights` row-major
+ * [num_samples x num_weights], result [num_windows x num_weights].
+ * tsk_treeseq_genetic_relatedness_weighted: (trees.h:1079-1082;
+ * trees.c:4840-4897), result [num_windows x num_index_tuples]; note the reference's argument
+ * order (result before options).  At most 8 state columns (7 weights where a frequency column
+ * is appended): more return TSKB_ERR_UNSUPPORTED. */
+int tskb_treeseq_trait_covariance(const tskb_treeseq_t *self, uint64_t num_weights,
+    const double *weights, uint64_t num_windows, const double *windows, uint32_t options,
+    double *result);
+int tskb_treeseq_trait_correlation(const tskb_treeseq_t *self, uint64_t num_weights,
+    const double *weights, uint64_t num_windows, const double *windows, uint32_t options,
+    double *result);
+int tskb_treeseq_genetic_relatedness_weighted(const tskb_treeseq_t *self, uint64_t num_weights,
+    const double *weights, uint64_t num_index_tuples, const int32_t *index_tuples,
+    uint64_t num_windows, const double *windows, double *result, uint32_t options);
 
 /* tsk_treeseq_general_stat (c/tskit/trees.h:1035-1037) for the summary
  * functions a device can evaluate: the callback `f` is replaced by a table.

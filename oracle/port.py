@@ -137,6 +137,49 @@ class Oracle:
             raise OracleError(ret)
         return res
 
+    # ---- weighted statistics: the reference's weight pre-processing and summary functions
+    # restated in numpy on top of general_stat (pinned against the reference package in
+    # tests/test_oracle.py)
+    def trait_covariance(self, W, windows=None, mode="site", span_normalise=True):
+        """tsk_treeseq_trait_covariance, c/tskit/trees.c:3960-4022."""
+        W = np.asarray(W, dtype=np.float64)
+        n = self.t.num_samples
+        Wc = W - W.sum(axis=0) / n
+        return self.general_stat(Wc, lambda x: (x * x) / (2 * (n - 1) * (n - 1)), W.shape[1],
+                                 windows=windows, mode=mode, span_normalise=span_normalise)
+
+    def trait_correlation(self, W, windows=None, mode="site", span_normalise=True):
+        """tsk_treeseq_trait_correlation, c/tskit/trees.c:4024-4110."""
+        W = np.asarray(W, dtype=np.float64)
+        n, K = self.t.num_samples, W.shape[1]
+        means = W.sum(axis=0) / n
+        meansqs = ((W * W).sum(axis=0) - means * means * n) / (n - 1)
+        Ws = np.column_stack([(W - means) / np.sqrt(meansqs), np.full(n, 1.0 / n)])
+
+        def f(x):
+            p = x[K]
+            if 0.0 < p < 1.0:
+                return (x[:K] * x[:K]) / (2 * (p * (1 - p)) * n * (n - 1))
+            return np.zeros(K)
+        return self.general_stat(Ws, f, K, windows=windows, mode=mode, span_normalise=span_normalise)
+
+    def genetic_relatedness_weighted(self, W, indexes, windows=None, mode="site", span_normalise=True,
+                                     polarised=False, centre=True):
+        """tsk_treeseq_genetic_relatedness_weighted, c/tskit/trees.c:4800-4897."""
+        W = np.asarray(W, dtype=np.float64)
+        n, K = self.t.num_samples, W.shape[1]
+        idx = np.asarray(indexes, dtype=np.int64).reshape(-1, 2)
+        Wn = np.column_stack([W, np.full(n, 1.0 / n)])
+        tot = np.concatenate([W.sum(axis=0), [1.0]])
+
+        def f(x):
+            if centre:
+                pn = x[K]
+                return (x[idx[:, 0]] - tot[idx[:, 0]] * pn) * (x[idx[:, 1]] - tot[idx[:, 1]] * pn)
+            return x[idx[:, 0]] * x[idx[:, 1]]
+        return self.general_stat(Wn, f, len(idx), windows=windows, mode=mode,
+                                 span_normalise=span_normalise, polarised=polarised)
+
     def trees_at(self, positions, tracked=None):
         pos = np.ascontiguousarray(positions, dtype=np.float64)
         order = np.argsort(pos, kind="stable")

@@ -111,3 +111,46 @@ def test_public_api_matches_reference_on_gpu(ts):
     same(acc.diversity([s[:50]], mode="node"), ts.diversity([s[:50]], mode="node"))
     assert acc.accel_stats["forwarded"] == 1
     assert acc.first().num_samples() == ts.num_samples
+
+
+def test_oracle_weighted_statistics_pinned_to_reference(ts, wf_small):
+    """The oracle's weighted statistics (oracle/port.py, numpy restatement of trees.c:3960-4110,
+    4800-4897 on top of its general_stat) against the reference package itself (CPU)."""
+    from oracle import port
+    o = port.Oracle(wf_small)
+    rng = np.random.default_rng(5)
+    W = rng.normal(size=(ts.num_samples, 3)) + np.array([0.0, 2.0, -1.0])
+    w = np.linspace(0, ts.sequence_length, 5)
+    for mode in ("site", "branch"):
+        assert np.allclose(o.trait_covariance(W, windows=w, mode=mode),
+                           ts.trait_covariance(W, windows=w, mode=mode), rtol=1e-9, atol=1e-12)
+        assert np.allclose(o.trait_correlation(W, windows=w, mode=mode),
+                           ts.trait_correlation(W, windows=w, mode=mode), rtol=1e-9, atol=1e-12)
+        idx = [(0, 1), (2, 2), (1, 0)]
+        for centre in (True, False):
+            got = o.genetic_relatedness_weighted(W, idx, windows=w, mode=mode, centre=centre)
+            want = ts.genetic_relatedness_weighted(W, indexes=idx, windows=w, mode=mode, centre=centre)
+            assert np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max()), (mode, centre)
+
+
+@pytest.mark.gpu
+def test_weighted_statistics_through_dropin(ts):
+    acc = dropin.accelerate(ts)
+    rng = np.random.default_rng(7)
+    W = rng.normal(size=(ts.num_samples, 2)) * np.array([1.0, 30.0]) + np.array([5.0, -2.0])
+    w = np.linspace(0, ts.sequence_length, 7)
+
+    def same(a, b):
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-9 * np.abs(b).max())
+    for mode in ("site", "branch"):
+        same(acc.trait_covariance(W, windows=w, mode=mode), ts.trait_covariance(W, windows=w, mode=mode))
+        same(acc.trait_correlation(W, windows=w, mode=mode), ts.trait_correlation(W, windows=w, mode=mode))
+        same(acc.trait_covariance(W[:, :1], mode=mode, span_normalise=False),
+             ts.trait_covariance(W[:, :1], mode=mode, span_normalise=False))
+        for centre in (True, False):
+            same(acc.genetic_relatedness_weighted(W, indexes=[(0, 1), (1, 1)], windows=w, mode=mode, centre=centre),
+                 ts.genetic_relatedness_weighted(W, indexes=[(0, 1), (1, 1)], windows=w, mode=mode, centre=centre))
+    assert acc.accel_stats["forwarded"] == 0 and acc.accel_stats["accelerated"] == 10
+    W9 = rng.normal(size=(ts.num_samples, 9))  # more state columns than a sweep carries: forwarded
+    same(acc.trait_covariance(W9, mode="branch"), ts.trait_covariance(W9, mode="branch"))
+    assert acc.accel_stats["forwarded"] == 1

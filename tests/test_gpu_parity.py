@@ -98,6 +98,39 @@ def test_overlapping_sample_sets_and_eight_sets(wf_small, engines):
                      o.stat("f2", sets, idx, mode=mode), cancelling=True)
 
 
+@pytest.mark.parametrize("mode", ["branch", "site"])
+def test_weighted_statistics(wf_small, engines, mode):
+    """fp64-state sweep: trait covariance / correlation and weighted relatedness against the
+    oracle's restatement (rtol 1e-9 with an absolute floor: the weights are centred, so states and
+    summaries cancel)."""
+    from tskit_b200.lowlevel import LibraryError
+    ll, o = engines
+    n = wf_small.num_samples
+    rng = np.random.default_rng(17)
+    for K in (1, 2, 3, 7):
+        W = rng.normal(size=(n, K)) * (1 + np.arange(K)) + np.arange(K)
+        for w in (np.array([0.0, wf_small.sequence_length]), np.linspace(0, wf_small.sequence_length, 9)):
+            for span in (True, False):
+                got = ll.trait_covariance(W, w, mode=mode, span_normalise=span)
+                assert close(got, o.trait_covariance(W, windows=w, mode=mode, span_normalise=span), cancelling=True)
+                got = ll.trait_correlation(W, w, mode=mode, span_normalise=span)
+                assert close(got, o.trait_correlation(W, windows=w, mode=mode, span_normalise=span), cancelling=True)
+            idx = rng.integers(0, K, size=(5, 2)).astype(np.int32)
+            for centre in (True, False):
+                for pol in (False, True):
+                    got = ll.genetic_relatedness_weighted(W, idx, w, mode=mode, polarised=pol, centre=centre)
+                    want = o.genetic_relatedness_weighted(W, idx, windows=w, mode=mode, polarised=pol, centre=centre)
+                    assert close(got, want, cancelling=True), (K, centre, pol)
+    with pytest.raises(LibraryError) as e:
+        ll.trait_covariance(np.zeros((n, 0)), [0, wf_small.sequence_length], mode=mode)
+    assert e.value.code == -913
+    with pytest.raises(LibraryError) as e:
+        ll.trait_covariance(np.zeros((n, 1)), [0, 1.0], mode=mode)
+    assert e.value.code == -901
+    with pytest.raises(ValueError):
+        ll.trait_covariance(np.zeros((n + 1, 1)), [0, wf_small.sequence_length], mode=mode)
+
+
 def test_many_result_columns(wf_small, engines, monkeypatch):
     """6 or more result columns take the lanes-are-columns branch summary (up to 32 columns per
     pass, so 40 tuples need two passes); both kernels against the oracle."""

@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" boundary (include/tskit_b200.h): argument validation with the
 // reference's error codes and precedence, then dispatch to the device engine.
 // There is deliberately no host implementation of any statistic in this library.
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -327,6 +328,7 @@ const char *tskb_strerror(int err) {
         case TSKB_ERR_UNSUPPORTED_STAT_MODE: return "Requested statistics mode not supported for this method. (TSK_ERR_UNSUPPORTED_STAT_MODE)";
         case TSKB_ERR_TIME_UNCALIBRATED: return "Statistics using branch lengths cannot be calculated when time_units is 'uncalibrated'. (TSK_ERR_TIME_UNCALIBRATED)";
         case TSKB_ERR_STAT_POLARISED_UNSUPPORTED: return "The TSK_STAT_POLARISED option is not supported by this statistic. (TSK_ERR_STAT_POLARISED_UNSUPPORTED)";
+        case TSKB_ERR_INSUFFICIENT_WEIGHTS: return "Insufficient weights provided (at least 1 required). (TSK_ERR_INSUFFICIENT_WEIGHTS)";
         case TSKB_ERR_CUDA: return "CUDA runtime error (see tskb_last_cuda_error)";
         case TSKB_ERR_BAD_INDEX_ORDER: return "Edge indexes are not in the order tsk_table_collection_build_index produces";
         case TSKB_ERR_UNSUPPORTED: return "Valid tskit call that the B200 engine does not accelerate";
@@ -363,6 +365,130 @@ K_WAY(genetic_relatedness, STAT_RELATEDNESS)
 K_WAY(Y3, STAT_Y3)
 K_WAY(f3, STAT_F3)
 K_WAY(f4, STAT_F4)
+
+}  // extern "C" (reopened below)
+
+namespace {
+
+// Common path of the weighted statistics: `cols` state columns of pre-processed weights (what
+// the reference hands to tsk_treeseq_general_stat); checks in general_stat's order
+// (trees.c:2035-2095): mode -> dims -> windows -> time units.
+int weighted_stat(const tskb_treeseq_t *self, int stat_id, uint64_t cols, const std::vector<double> &W,
+    uint64_t result_dim, int tw, const int32_t *tuples, uint64_t num_windows, const double *windows,
+    uint32_t options, double *result) {
+    const Plan &P = *self->plan;
+    return guarded([&]() -> int {
+        bool site = options & TSKB_STAT_SITE, branch = options & TSKB_STAT_BRANCH,
+             node = options & TSKB_STAT_NODE;
+        if (!(site || branch || node)) {
+            site = true;
+            options |= TSKB_STAT_SITE;
+        }
+        if (site + branch + node > 1) return TSKB_ERR_MULTIPLE_STAT_MODES;
+        if (cols < 1) return TSKB_ERR_BAD_STATE_DIMS;
+        if (result_dim < 1) return TSKB_ERR_BAD_RESULT_DIMS;
+        double default_windows[2] = { 0, P.L };
+        if (windows == nullptr) {
+            num_windows = 1;
+            windows = default_windows;
+        } else {
+            int ret = check_windows(P, num_windows, windows, true);
+            if (ret != 0) return ret;
+        }
+        if (node) return TSKB_ERR_UNSUPPORTED;
+        if (branch && P.time_uncalibrated && !(options & TSKB_STAT_ALLOW_TIME_UNCALIBRATED)) {
+            return TSKB_ERR_TIME_UNCALIBRATED;
+        }
+        if (cols > MAX_STATE_DIM) return TSKB_ERR_UNSUPPORTED;
+        // total_weight of general_stat: summed over the samples in order (trees.c:2003-2010)
+        std::vector<double> totals(cols, 0.0);
+        for (uint64_t j = 0; j < P.num_samples; j++) {
+            for (uint64_t k = 0; k < cols; k++) totals[k] += W[j * cols + k];
+        }
+        StatSpec sp = {};
+        sp.stat_id = stat_id;
+        sp.K = (uint32_t) cols;
+        sp.M = (uint32_t) result_dim;
+        sp.tuple = (uint32_t) tw;
+        sp.indexes = tuples;
+        sp.W = (uint32_t) num_windows;
+        sp.windows = windows;
+        sp.options = options;
+        sp.result = result;
+        sp.weights = W.data();
+        sp.column_totals = totals.data();
+        return run_weighted_stat(&P, sp);
+    });
+}
+
+}  // namespace
+
+extern "C" {
+
+/* tsk_treeseq_trait_covariance (trees.c:3976-4022): centre the weights, state = their sums */
+int tskb_treeseq_trait_covariance(const tskb_treeseq_t *self, uint64_t num_weights, const double *weights,
+    uint64_t num_windows, const double *windows, uint32_t options, double *result) {
+    if (self == nullptr || self->plan == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    if (num_weights == 0) return TSKB_ERR_INSUFFICIENT_WEIGHTS;
+    const uint64_t n = self->plan->num_samples, K = num_weights;
+    std::vector<double> means(K, 0.0), W(n * K);
+    for (uint64_t j = 0; j < n; j++) {
+        for (uint64_t k = 0; k < K; k++) means[k] += weights[j * K + k];
+    }
+    for (uint64_t k = 0; k < K; k++) means[k] /= (double) n;
+    for (uint64_t j = 0; j < n; j++) {
+        for (uint64_t k = 0; k < K; k++) W[j * K + k] = weights[j * K + k] - means[k];
+    }
+    return weighted_stat(self, STAT_TRAIT_COV, K, W, K, 0, nullptr, num_windows, windows, options, result);
+}
+
+/* tsk_treeseq_trait_correlation (trees.c:4051-4110): standardise the weights, append 1/n */
+int tskb_treeseq_trait_correlation(const tskb_treeseq_t *self, uint64_t num_weights, const double *weights,
+    uint64_t num_windows, const double *windows, uint32_t options, double *result) {
+    if (self == nullptr || self->plan == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    if (num_weights < 1) return TSKB_ERR_INSUFFICIENT_WEIGHTS;
+    const uint64_t n = self->plan->num_samples, K = num_weights;
+    std::vector<double> means(K, 0.0), meansqs(K, 0.0), sds(K, 0.0), W(n * (K + 1));
+    for (uint64_t j = 0; j < n; j++) {
+        for (uint64_t k = 0; k < K; k++) {
+            means[k] += weights[j * K + k];
+            meansqs[k] += weights[j * K + k] * weights[j * K + k];
+        }
+    }
+    for (uint64_t k = 0; k < K; k++) {
+        means[k] /= (double) n;
+        meansqs[k] -= means[k] * means[k] * (double) n;
+        meansqs[k] /= (double) (n - 1);
+        sds[k] = sqrt(meansqs[k]);
+    }
+    for (uint64_t j = 0; j < n; j++) {
+        for (uint64_t k = 0; k < K; k++) W[j * (K + 1) + k] = (weights[j * K + k] - means[k]) / sds[k];
+        W[j * (K + 1) + K] = 1.0 / (double) n;  // frequency column
+    }
+    return weighted_stat(self, STAT_TRAIT_CORR, K + 1, W, K, 0, nullptr, num_windows, windows, options,
+        result);
+}
+
+/* tsk_treeseq_genetic_relatedness_weighted (trees.c:4840-4897): append the 1/n column */
+int tskb_treeseq_genetic_relatedness_weighted(const tskb_treeseq_t *self, uint64_t num_weights,
+    const double *weights, uint64_t num_index_tuples, const int32_t *index_tuples, uint64_t num_windows,
+    const double *windows, double *result, uint32_t options) {
+    if (self == nullptr || self->plan == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    if (num_weights == 0) return TSKB_ERR_INSUFFICIENT_WEIGHTS;
+    const uint64_t n = self->plan->num_samples, K = num_weights;
+    for (uint64_t j = 0; j < 2 * num_index_tuples; j++) {
+        // the reference indexes the state row unchecked; out of range is refused here
+        if (index_tuples[j] < 0 || index_tuples[j] > (int32_t) K) return TSKB_ERR_BAD_SAMPLE_SET_INDEX;
+    }
+    std::vector<double> W(n * (K + 1));
+    for (uint64_t j = 0; j < n; j++) {
+        for (uint64_t k = 0; k < K; k++) W[j * (K + 1) + k] = weights[j * K + k];
+        W[j * (K + 1) + K] = 1.0 / (double) n;
+    }
+    const int stat = (options & TSKB_STAT_NONCENTRED) ? STAT_REL_WEIGHTED_NC : STAT_REL_WEIGHTED;
+    return weighted_stat(self, stat, K + 1, W, num_index_tuples, 2, index_tuples, num_windows, windows,
+        options, result);
+}
 
 int tskb_treeseq_sample_count_stat_tabulated(const tskb_treeseq_t *self,
     uint64_t num_sample_sets, const uint64_t *sample_set_sizes, const int32_t *sample_sets,

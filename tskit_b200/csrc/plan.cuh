@@ -149,6 +149,10 @@ struct StatSpec {
     uint32_t options;
     double *result;              // host or device [W * M]
     bool result_on_device;
+    // weighted statistics (stat_id >= STAT_TRAIT_COV): K columns of per-sample weights, already
+    // pre-processed as the reference does (centred / standardised / frequency column appended)
+    const double *weights = nullptr;        // host [num_samples * K], row-major
+    const double *column_totals = nullptr;  // host [K]
     // tabulated summary (stat_id == STAT_TABULATED)
     const double *f_table = nullptr;
     uint64_t table_rows = 0;
@@ -157,10 +161,13 @@ struct StatSpec {
 enum StatId {
     STAT_DIVERSITY = 0, STAT_SEGSITES = 1, STAT_Y1 = 2, STAT_DIVERGENCE = 3, STAT_Y2 = 4,
     STAT_F2 = 5, STAT_RELATEDNESS = 6, STAT_Y3 = 7, STAT_F3 = 8, STAT_F4 = 9,
-    STAT_RELATEDNESS_NC = 10, STAT_TABULATED = 11
+    STAT_RELATEDNESS_NC = 10, STAT_TABULATED = 11,
+    // weighted statistics: fp64 states (trees.c:3960-4110, 4800-4897)
+    STAT_TRAIT_COV = 12, STAT_TRAIT_CORR = 13, STAT_REL_WEIGHTED = 14, STAT_REL_WEIGHTED_NC = 15
 };
 
 int run_sample_count_stat(const Plan *plan, const StatSpec &spec);
+int run_weighted_stat(const Plan *plan, const StatSpec &spec);
 int run_trees_at(const Plan *plan, uint64_t nq, const double *positions, const int32_t *tracked,
     uint64_t num_tracked, int32_t *out_parent, int32_t *out_count);
 

@@ -27,28 +27,33 @@ namespace {
 
 constexpr int TB = 256;
 
-template <int KP>
-struct alignas(KP >= 4 ? 16 : 4 * KP) IVec {
-    int32_t v[KP];
-    __host__ __device__ __forceinline__ IVec operator+(const IVec &o) const {
-        IVec r;
+// State of a node: one column per sample set (int32 counts) or per weight column (fp64 sums).
+template <typename T, int K>
+struct alignas(sizeof(T) * K >= 16 ? 16 : sizeof(T) * K) SVec {
+    using scalar = T;
+    static constexpr int N = K;
+    T v[K];
+    __host__ __device__ __forceinline__ SVec operator+(const SVec &o) const {
+        SVec r;
 #pragma unroll
-        for (int k = 0; k < KP; k++) r.v[k] = v[k] + o.v[k];
+        for (int k = 0; k < K; k++) r.v[k] = v[k] + o.v[k];
         return r;
     }
-    __host__ __device__ __forceinline__ IVec operator-(const IVec &o) const {
-        IVec r;
+    __host__ __device__ __forceinline__ SVec operator-(const SVec &o) const {
+        SVec r;
 #pragma unroll
-        for (int k = 0; k < KP; k++) r.v[k] = v[k] - o.v[k];
+        for (int k = 0; k < K; k++) r.v[k] = v[k] - o.v[k];
         return r;
     }
 };
+template <int K> using IVec = SVec<int32_t, K>;
+template <int K> using DVec = SVec<double, K>;
 
-template <int KP>
-__device__ __forceinline__ IVec<KP> ivec_zero() {
-    IVec<KP> r;
+template <class V>
+__host__ __device__ __forceinline__ V ivec_zero() {
+    V r;
 #pragma unroll
-    for (int k = 0; k < KP; k++) r.v[k] = 0;
+    for (int k = 0; k < V::N; k++) r.v[k] = 0;
     return r;
 }
 
@@ -71,11 +76,11 @@ struct SumP {
 };
 
 // x[i] without dynamic register indexing
-template <int KP>
-__device__ __forceinline__ double pick(const IVec<KP> &s, int i) {
-    int32_t r = s.v[0];
+template <class V>
+__device__ __forceinline__ double pick(const V &s, int i) {
+    typename V::scalar r = s.v[0];
 #pragma unroll
-    for (int k = 1; k < KP; k++) r = (i == k) ? s.v[k] : r;
+    for (int k = 1; k < V::N; k++) r = (i == k) ? s.v[k] : r;
     return (double) r;
 }
 
@@ -99,66 +104,81 @@ inline double column_denominator(int stat, const ColP &c) {
 
 // The summary functions, numerators in the reference's exact operation order
 // (c/tskit/trees.c:3934-3948, 4221-4264, 4690-4773, 4899-4959, 5177-5291).
-template <int STAT, int KP>
-__device__ __forceinline__ double f_eval(const SumP &P, const ColP &c, int m, const IVec<KP> &s) {
+template <int STAT, class V>
+__device__ __forceinline__ double f_eval(const SumP &P, const ColP &c, int m, const V &s) {
     if constexpr (STAT == STAT_DIVERSITY) {
-        double n = c.ni, x = pick<KP>(s, c.i);
+        double n = c.ni, x = pick<V>(s, c.i);
         return x * (n - x) * c.inv;
     } else if constexpr (STAT == STAT_SEGSITES) {
-        double n = c.ni, x = pick<KP>(s, c.i);
+        double n = c.ni, x = pick<V>(s, c.i);
         return (x > 0) * (1 - x / n);
     } else if constexpr (STAT == STAT_Y1) {
-        double ni = c.ni, xi = pick<KP>(s, c.i);
+        double ni = c.ni, xi = pick<V>(s, c.i);
         double numer = xi * (ni - xi) * (ni - xi - 1);
         return numer * c.inv;
     } else if constexpr (STAT == STAT_DIVERGENCE) {
-        return pick<KP>(s, c.i) * (c.nj - pick<KP>(s, c.j)) * c.inv;
+        return pick<V>(s, c.i) * (c.nj - pick<V>(s, c.j)) * c.inv;
     } else if constexpr (STAT == STAT_Y2) {
         double nj = c.nj;
-        double xi = pick<KP>(s, c.i), xj = pick<KP>(s, c.j);
+        double xi = pick<V>(s, c.i), xj = pick<V>(s, c.j);
         return xi * (nj - xj) * (nj - xj - 1) * c.inv;
     } else if constexpr (STAT == STAT_F2) {
         double ni = c.ni, nj = c.nj;
-        double xi = pick<KP>(s, c.i), xj = pick<KP>(s, c.j);
+        double xi = pick<V>(s, c.i), xj = pick<V>(s, c.j);
         double numer = xi * (xi - 1) * (nj - xj) * (nj - xj - 1) - xi * (ni - xi) * (nj - xj) * xj;
         return numer * c.inv;
     } else if constexpr (STAT == STAT_RELATEDNESS) {
         double sumx = 0;
 #pragma unroll
-        for (int k = 0; k < KP; k++) {
+        for (int k = 0; k < V::N; k++) {
             if (k < P.K) sumx += (double) s.v[k] / P.n[k];
         }
         double meanx = sumx / (double) P.K;
-        return (pick<KP>(s, c.i) / c.ni - meanx) * (pick<KP>(s, c.j) / c.nj - meanx);
+        return (pick<V>(s, c.i) / c.ni - meanx) * (pick<V>(s, c.j) / c.nj - meanx);
     } else if constexpr (STAT == STAT_RELATEDNESS_NC) {
-        return pick<KP>(s, c.i) * pick<KP>(s, c.j) * c.inv;
+        return pick<V>(s, c.i) * pick<V>(s, c.j) * c.inv;
     } else if constexpr (STAT == STAT_Y3) {
-        double numer = pick<KP>(s, c.i) * (c.nj - pick<KP>(s, c.j)) * (c.nk - pick<KP>(s, c.k));
+        double numer = pick<V>(s, c.i) * (c.nj - pick<V>(s, c.j)) * (c.nk - pick<V>(s, c.k));
         return numer * c.inv;
     } else if constexpr (STAT == STAT_F3) {
         double ni = c.ni, nj = c.nj, nk = c.nk;
-        double xi = pick<KP>(s, c.i), xj = pick<KP>(s, c.j), xk = pick<KP>(s, c.k);
+        double xi = pick<V>(s, c.i), xj = pick<V>(s, c.j), xk = pick<V>(s, c.k);
         double numer = xi * (xi - 1) * (nj - xj) * (nk - xk) - xi * (ni - xi) * (nj - xj) * xk;
         return numer * c.inv;
     } else if constexpr (STAT == STAT_F4) {
         double nj = c.nj, nk = c.nk, nl = c.nl;
-        double xi = pick<KP>(s, c.i), xj = pick<KP>(s, c.j), xk = pick<KP>(s, c.k),
-               xl = pick<KP>(s, c.l);
+        double xi = pick<V>(s, c.i), xj = pick<V>(s, c.j), xk = pick<V>(s, c.k),
+               xl = pick<V>(s, c.l);
         double numer = xi * xk * (nj - xj) * (nl - xl) - xi * xl * (nj - xj) * (nk - xk);
         return numer * c.inv;
+    } else if constexpr (STAT == STAT_TRAIT_COV) {
+        // trees.c:3960-3974; c.ni = 2 (n - 1)(n - 1) in the reference's operation order
+        const double x = pick<V>(s, c.i);
+        return (x * x) / c.ni;
+    } else if constexpr (STAT == STAT_TRAIT_CORR) {
+        // trees.c:4031-4049: the last state column is the frequency of the samples below
+        const double n = P.n[0], x = pick<V>(s, c.i), p = pick<V>(s, P.K - 1);
+        if ((p > 0.0) && (p < 1.0)) return (x * x) / (2 * (p * (1 - p)) * n * (n - 1));
+        return 0.0;
+    } else if constexpr (STAT == STAT_REL_WEIGHTED) {
+        // trees.c:4800-4820: c.ni, c.nj = total weights of the two columns
+        const double pn = pick<V>(s, P.K - 1);
+        return (pick<V>(s, c.i) - c.ni * pn) * (pick<V>(s, c.j) - c.nj * pn);
+    } else if constexpr (STAT == STAT_REL_WEIGHTED_NC) {
+        return pick<V>(s, c.i) * pick<V>(s, c.j);  // trees.c:4822-4838
     } else {  // STAT_TABULATED
-        uint32_t cnt = (uint32_t) s.v[0];
+        uint32_t cnt = (uint32_t) (long long) s.v[0];
         if (cnt >= P.table_rows) cnt = P.table_rows - 1;
         return __ldg(P.table + (size_t) cnt * P.M + m);
     }
 }
 
 // branch mode: f(x) + f(total - x) unless polarised (trees.c:1944-1972)
-template <int STAT, int KP>
-__device__ __forceinline__ double F_branch(const SumP &P, const ColP &c, int m, const IVec<KP> &s,
-    const IVec<KP> &totals) {
-    double r = f_eval<STAT, KP>(P, c, m, s);
-    if (!P.polarised) r += f_eval<STAT, KP>(P, c, m, totals - s);
+template <int STAT, class V>
+__device__ __forceinline__ double F_branch(const SumP &P, const ColP &c, int m, const V &s,
+    const V &totals) {
+    double r = f_eval<STAT, V>(P, c, m, s);
+    if (!P.polarised) r += f_eval<STAT, V>(P, c, m, totals - s);
     return r;
 }
 
@@ -169,9 +189,9 @@ __device__ __forceinline__ double F_branch(const SumP &P, const ColP &c, int m, 
 // (trees.c:2201-2214) on the way: verr = smallest (position << 1 | kind) of an element that is out
 // of bounds (kind 0) or not a sample (kind 1) -- the reference reports the first one in order --
 // and dup = some sample listed twice in one set.
-template <int KP>
+template <class V>
 __global__ void k_set_weights(const int32_t *sets, const uint32_t *set_off, uint32_t K,
-    uint32_t total, const int32_t *sample_index, int32_t N, IVec<KP> *init, unsigned long long *verr,
+    uint32_t total, const int32_t *sample_index, int32_t N, V *init, unsigned long long *verr,
     int *dup) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= total) return;
@@ -188,6 +208,20 @@ __global__ void k_set_weights(const int32_t *sets, const uint32_t *set_off, uint
     }
     // a sample may be in several sets (trees.c:2201-2214): distinct columns
     if (atomicExch(&init[si].v[k], 1) != 0) *dup = 1;
+}
+
+// weighted statistics: the samples' INIT slots hold their weight rows (trees.c:1406-1415 with
+// general_stat's W)
+template <class V>
+__global__ void k_init_weights(const double *W, uint32_t n, uint32_t K, V *init) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V r = ivec_zero<V>();
+#pragma unroll
+    for (int k = 0; k < V::N; k++) {
+        if ((uint32_t) k < K) r.v[k] = (typename V::scalar) W[(size_t) i * K + k];
+    }
+    init[i] = r;
 }
 
 // ---------------------------------------------------------------- branch-mode running sum
@@ -211,9 +245,9 @@ struct DeltaOut {
 // piece starts at -- consecutive pieces of one node, mostly -- the two reductions to that
 // address are merged into one of G_next - G (the reference's "subtract the old summary, add the
 // new one" of one node at one breakpoint).  Must be called by all 32 lanes of a warp.
-template <int STAT, int KP, int NP>
-__device__ __forceinline__ void pieces_to_deltas(const SumP &sp, const IVec<KP> &totals,
-    const IVec<KP> (&st)[NP], const double (&bl)[NP], const uint32_t (&bp0)[NP],
+template <int STAT, class V, int NP>
+__device__ __forceinline__ void pieces_to_deltas(const SumP &sp, const V &totals,
+    const V (&st)[NP], const double (&bl)[NP], const uint32_t (&bp0)[NP],
     const uint32_t (&bp1)[NP], const DeltaOut &out, uint32_t m0, uint32_t m1, const ColP &first_col) {
     const uint32_t lane = threadIdx.x & 31u;
     bool valid[NP], live[NP], merge_next[NP], merged_prev[NP];
@@ -235,7 +269,7 @@ __device__ __forceinline__ void pieces_to_deltas(const SumP &sp, const IVec<KP> 
 #pragma unroll
         for (int q = 0; q < NP; q++) {
             double G = 0.0;
-            if (live[q]) G = bl[q] * F_branch<STAT, KP>(sp, col, m, st[q], totals);
+            if (live[q]) G = bl[q] * F_branch<STAT, V>(sp, col, m, st[q], totals);
             const double G_next = __shfl_down_sync(0xffffffffu, G, 1);
             if (!valid[q]) continue;
             if (!merged_prev[q] && G != 0.0) atomicAdd(Dm + bp0[q], G);
@@ -260,24 +294,20 @@ __device__ __forceinline__ void pieces_to_deltas(const SumP &sp, const IVec<KP> 
 // registers (shared-memory bins, flushed once per CTA) -- the branch summary costs no second
 // pass over the states.
 
-template <int KP>
-__device__ __forceinline__ IVec<KP> state_load(const IVec<KP> *p) {
+template <class V>
+__device__ __forceinline__ V state_load(const V *p) {
     // states are written by other CTAs of the same launch: read through L2, never L1
-    IVec<KP> r;
-    if constexpr (KP >= 4) {
+    union { V val; int4 q[sizeof(V) >= 16 ? sizeof(V) / 16 : 1]; int2 d; int w; } u;
+    if constexpr (sizeof(V) >= 16) {
         const int4 *q = reinterpret_cast<const int4 *>(p);
 #pragma unroll
-        for (int c = 0; c < KP / 4; c++) {
-            int4 t = __ldcg(q + c);
-            r.v[4 * c] = t.x; r.v[4 * c + 1] = t.y; r.v[4 * c + 2] = t.z; r.v[4 * c + 3] = t.w;
-        }
-    } else if constexpr (KP == 2) {
-        int2 t = __ldcg(reinterpret_cast<const int2 *>(p));
-        r.v[0] = t.x; r.v[1] = t.y;
+        for (int c = 0; c < (int) (sizeof(V) / 16); c++) u.q[c] = __ldcg(q + c);
+    } else if constexpr (sizeof(V) == 8) {
+        u.d = __ldcg(reinterpret_cast<const int2 *>(p));
     } else {
-        r.v[0] = __ldcg(reinterpret_cast<const int *>(p));
+        u.w = __ldcg(reinterpret_cast<const int *>(p));
     }
-    return r;
+    return u.val;
 }
 
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p) {
@@ -309,8 +339,8 @@ struct SweepArgs {
     unsigned long long *trace;
 };
 
-template <int KP>
-__global__ void __launch_bounds__(PROP_TB) k_sweep(SweepArgs a, IVec<KP> *pval) {
+template <class V>
+__global__ void __launch_bounds__(PROP_TB) k_sweep(SweepArgs a, V *pval) {
     unsigned long long *trace = a.trace;
     for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         TRACE(0);
@@ -343,23 +373,23 @@ __global__ void __launch_bounds__(PROP_TB) k_sweep(SweepArgs a, IVec<KP> *pval) 
             __syncthreads();
         }
         TRACE(1);
-        IVec<KP> g[PROP_IPT][PROP_PRE];
+        V g[PROP_IPT][PROP_PRE];
 #pragma unroll
         for (int q = 0; q < PROP_IPT; q++) {
 #pragma unroll
             for (int i = 0; i < PROP_PRE; i++) {
-                g[q][i] = ivec_zero<KP>();
-                if (rf[q][i] != NO_PIECE) g[q][i] = state_load<KP>(pval + rf[q][i]);
+                g[q][i] = ivec_zero<V>();
+                if (rf[q][i] != NO_PIECE) g[q][i] = state_load<V>(pval + rf[q][i]);
             }
         }
         TRACE(2);
 #pragma unroll
         for (int q = 0; q < PROP_IPT; q++) {
-            IVec<KP> sum = g[q][0];
+            V sum = g[q][0];
 #pragma unroll
             for (int i = 1; i < PROP_PRE; i++) sum = sum + g[q][i];
             for (uint32_t o = o0[q] + PROP_PRE; o < o1[q]; o++) {
-                sum = sum + state_load<KP>(pval + __ldg(a.refs + o));
+                sum = sum + state_load<V>(pval + __ldg(a.refs + o));
             }
             pval[j0 + q * PROP_TB] = sum;
         }
@@ -383,21 +413,21 @@ __global__ void __launch_bounds__(PROP_TB) k_sweep(SweepArgs a, IVec<KP> *pval) 
 constexpr int SUM_IPT = TSKB_SUM_IPT;    // pieces per thread and pipeline stage
 constexpr int SUM_TILE = TB * SUM_IPT;
 
-template <int KP>
+template <class V>
 struct PieceRegs {
-    IVec<KP> st[SUM_IPT];
+    V st[SUM_IPT];
     double bl[SUM_IPT];
     uint32_t bp0[SUM_IPT], bp1[SUM_IPT];
     __device__ __forceinline__ void load(uint32_t tile, uint32_t npp, const uint32_t *__restrict__ q_bp0,
         const uint32_t *__restrict__ q_bp1, const double *__restrict__ q_bl,
-        const IVec<KP> *__restrict__ pval) {
+        const V *__restrict__ pval) {
 #pragma unroll
         for (int q = 0; q < SUM_IPT; q++) {
             const uint32_t j = tile * SUM_TILE + q * TB + threadIdx.x;
             bp1[q] = NO_PIECE;  // past the end: padding
             bp0[q] = 0;
             bl[q] = 0.0;
-            st[q] = ivec_zero<KP>();
+            st[q] = ivec_zero<V>();
             // the processing order is padded to whole PROP_TILEs: no bounds check when tiles coincide
             if (SUM_TILE == PROP_TILE || j < npp) {
                 st[q] = pval[j]; bl[q] = q_bl[j]; bp0[q] = q_bp0[j]; bp1[q] = q_bp1[j];
@@ -409,21 +439,21 @@ struct PieceRegs {
 // Few warps with many loads in flight each beat many warps here (measured): the kernel is bound
 // by the rate at which an SM can issue requests to L2, and the reductions of a warp are 32
 // separate requests.
-template <int STAT, int KP>
+template <int STAT, class V>
 __global__ void __launch_bounds__(TB) k_branch_summary(uint32_t npp,
     const uint32_t *__restrict__ q_bp0, const uint32_t *__restrict__ q_bp1,
-    const double *__restrict__ q_bl, const IVec<KP> *__restrict__ pval, SumP sp, IVec<KP> totals,
+    const double *__restrict__ q_bl, const V *__restrict__ pval, SumP sp, V totals,
     DeltaOut out, uint32_t m0, uint32_t m1) {
     const uint32_t ntiles = (npp + SUM_TILE - 1) / SUM_TILE;
     // software pipeline: the next tile's loads are in flight while this one is evaluated
-    PieceRegs<KP> cur, nxt;
+    PieceRegs<V> cur, nxt;
     const ColP first_col = out.cols[m0];
     uint32_t tile = blockIdx.x;
     if (tile < ntiles) cur.load(tile, npp, q_bp0, q_bp1, q_bl, pval);
     for (; tile < ntiles; tile += gridDim.x) {
         const uint32_t tn = tile + gridDim.x;
         if (tn < ntiles) nxt.load(tn, npp, q_bp0, q_bp1, q_bl, pval);
-        pieces_to_deltas<STAT, KP, SUM_IPT>(sp, totals, cur.st, cur.bl, cur.bp0, cur.bp1, out, m0, m1, first_col);
+        pieces_to_deltas<STAT, V, SUM_IPT>(sp, totals, cur.st, cur.bl, cur.bp0, cur.bp1, out, m0, m1, first_col);
         cur = nxt;
     }
 }
@@ -434,10 +464,10 @@ __global__ void __launch_bounds__(TB) k_branch_summary(uint32_t npp,
 // column m: the reductions of one piece go to M consecutive doubles (D is laid out
 // [breakpoint][column] for this kernel), one or two L2 requests instead of M, and a piece that
 // starts where the previous one ends is merged with it in registers.  Up to 32 columns per pass.
-template <int STAT, int KP>
+template <int STAT, class V>
 __global__ void __launch_bounds__(TB) k_branch_summary_cols(uint32_t npp,
     const uint32_t *__restrict__ q_bp0, const uint32_t *__restrict__ q_bp1,
-    const double *__restrict__ q_bl, const IVec<KP> *__restrict__ pval, SumP sp, IVec<KP> totals,
+    const double *__restrict__ q_bl, const V *__restrict__ pval, SumP sp, V totals,
     DeltaOut out, uint32_t m0, uint32_t ncols) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -448,7 +478,7 @@ __global__ void __launch_bounds__(TB) k_branch_summary_cols(uint32_t npp,
     double *Dl = out.D + lane;  // D[bp * ncols + lane]
     for (uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += warps) {
         const uint32_t j = chunk * 32 + lane;
-        IVec<KP> st = ivec_zero<KP>();
+        V st = ivec_zero<V>();
         double bl = 0.0;
         uint32_t bp0 = 0, bp1 = NO_PIECE;
         if (j < npp) {
@@ -457,14 +487,14 @@ __global__ void __launch_bounds__(TB) k_branch_summary_cols(uint32_t npp,
         double G_prev = 0.0;
         uint32_t end_prev = NO_PIECE;  // breakpoint the previous piece ends at; NO_PIECE: none pending
         for (int i = 0; i < 32; i++) {
-            IVec<KP> s_i;
+            V s_i;
 #pragma unroll
-            for (int k = 0; k < KP; k++) s_i.v[k] = __shfl_sync(0xffffffffu, st.v[k], i);
+            for (int k = 0; k < V::N; k++) s_i.v[k] = __shfl_sync(0xffffffffu, st.v[k], i);
             const double bl_i = __shfl_sync(0xffffffffu, bl, i);
             const uint32_t b0 = __shfl_sync(0xffffffffu, bp0, i), b1 = __shfl_sync(0xffffffffu, bp1, i);
             double G = 0.0;
             const bool valid = b1 != NO_PIECE;  // warp-uniform
-            if (valid && !(sp.skip_zero_bl && bl_i == 0.0)) G = bl_i * F_branch<STAT, KP>(sp, col, m, s_i, totals);
+            if (valid && !(sp.skip_zero_bl && bl_i == 0.0)) G = bl_i * F_branch<STAT, V>(sp, col, m, s_i, totals);
             if (valid && end_prev == b0) {
                 const double v = G - G_prev;
                 if (mine && v != 0.0) atomicAdd(Dl + (size_t) b0 * ncols, v);
@@ -575,10 +605,10 @@ __global__ void __launch_bounds__(TB) k_window_integrate(const double *S, uint32
 
 // ---------------------------------------------------------------- phase 2, site mode
 
-template <int STAT, int KP>
+template <int STAT, class V>
 __global__ void k_site_summary(uint32_t site_lo, uint32_t nsites, const uint32_t *site_moff,
     const uint32_t *site_aoff, const int32_t *mut_src, const uint16_t *mut_allele,
-    const uint16_t *mut_alt, const IVec<KP> *pval, IVec<KP> totals, IVec<KP> *scratch, SumP P,
+    const uint16_t *mut_alt, const V *pval, V totals, V *scratch, SumP P,
     double *R) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsites) return;
@@ -587,21 +617,21 @@ __global__ void k_site_summary(uint32_t site_lo, uint32_t nsites, const uint32_t
     const uint32_t mb = site_moff[site], me = site_moff[site + 1];
     if (na == 2 && me - mb == 1) {
         // one mutation, two alleles: no scratch traffic
-        IVec<KP> x = pval[mut_src[mb]];
-        IVec<KP> anc = totals - x;
+        V x = pval[mut_src[mb]];
+        V anc = totals - x;
         for (int m = 0; m < P.M; m++) {
             const ColP col = P.cols[m];
             double acc = 0.0;
-            if (!P.polarised) acc += f_eval<STAT, KP>(P, col, m, anc);
-            acc += f_eval<STAT, KP>(P, col, m, x);
+            if (!P.polarised) acc += f_eval<STAT, V>(P, col, m, anc);
+            acc += f_eval<STAT, V>(P, col, m, x);
             R[(size_t) m * nsites + t] = acc;
         }
         return;
     }
     scratch[a0] = totals;  // allele 0 starts at total_weight (trees.c:1548)
-    for (uint32_t al = 1; al < na; al++) scratch[a0 + al] = ivec_zero<KP>();
+    for (uint32_t al = 1; al < na; al++) scratch[a0 + al] = ivec_zero<V>();
     for (uint32_t m = mb; m < me; m++) {
-        IVec<KP> x = pval[mut_src[m]];
+        V x = pval[mut_src[m]];
         scratch[a0 + mut_allele[m]] = scratch[a0 + mut_allele[m]] + x;
         scratch[a0 + mut_alt[m]] = scratch[a0 + mut_alt[m]] - x;
     }
@@ -609,7 +639,7 @@ __global__ void k_site_summary(uint32_t site_lo, uint32_t nsites, const uint32_t
         const ColP col = P.cols[m];
         double acc = 0.0;
         for (uint32_t al = P.polarised ? 1 : 0; al < na; al++) {
-            acc += f_eval<STAT, KP>(P, col, m, scratch[a0 + al]);
+            acc += f_eval<STAT, V>(P, col, m, scratch[a0 + al]);
         }
         R[(size_t) m * nsites + t] = acc;
     }
@@ -698,8 +728,8 @@ struct CallCtx {
     uint64_t launches;
 };
 
-template <int KP>
-void launch_sweep(CallCtx &c, IVec<KP> *pval) {
+template <class V>
+void launch_sweep(CallCtx &c, V *pval) {
     const Plan &P = *c.P;
     Arena &A = P.arena;
     if (P.ntiles == 0) return;
@@ -710,7 +740,7 @@ void launch_sweep(CallCtx &c, IVec<KP> *pval) {
         TSKB_CK(cudaMemsetAsync(trace, 0, (size_t) P.ntiles * 4 * sizeof(unsigned long long), c.s));
         P.stats_trace = trace;
     }
-    auto kern = k_sweep<KP>;
+    auto kern = k_sweep<V>;
     int per_sm = 1, sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
     TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PROP_TB, 0));
@@ -749,8 +779,8 @@ inline void finish_columns(CallCtx &c, double *D, uint32_t Tp1, uint32_t m0, uin
     c.launches++;
 }
 
-template <int STAT, int KP>
-void run_branch(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
+template <int STAT, class V>
+void run_branch(CallCtx &c, V *pval, V totals) {
     const Plan &P = *c.P;
     const uint32_t M = c.sp->M;
     Arena &A = P.arena;
@@ -766,11 +796,11 @@ void run_branch(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
     TSKB_CK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, D, D, (int) std::max<uint32_t>(Tp1 - 1, 1), c.s));
     void *scan_tmp = A.get<char>(scan_bytes);
     DeltaOut out = { D, Tp1, c.sumP.cols };
-    launch_sweep<KP>(c, pval);
+    launch_sweep<V>(c, pval);
     TSKB_CK(cudaEventRecord(P.ev[2], c.s));
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
-    TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_branch_summary<STAT, KP>, TB, 0));
+    TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_branch_summary<STAT, V>, TB, 0));
     const uint32_t ntiles = (P.npp + SUM_TILE - 1) / SUM_TILE;
     for (uint32_t m0 = 0; m0 < M; m0 += mc) {
         const uint32_t m1 = std::min(M, m0 + mc);
@@ -779,11 +809,11 @@ void run_branch(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
             TSKB_CK(cudaMemsetAsync(Dx, 0, (size_t) nc * col_bytes, c.s));
             DeltaOut ox = { Dx, Tp1, c.sumP.cols };
             int per_sm_c = 1;
-            TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_branch_summary_cols<STAT, KP>, TB, 0));
+            TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_branch_summary_cols<STAT, V>, TB, 0));
             if (P.npp > 0) {
                 const uint32_t nchunks = (P.npp + 31) / 32;
                 const uint32_t grid = std::min<uint32_t>((nchunks + 7) / 8, (uint32_t) (sms * std::max(per_sm_c, 1)));
-                k_branch_summary_cols<STAT, KP><<<grid, TB, 0, c.s>>>(P.npp, P.q_bp0.p, P.q_bp1.p, P.q_bl.p,
+                k_branch_summary_cols<STAT, V><<<grid, TB, 0, c.s>>>(P.npp, P.q_bp0.p, P.q_bp1.p, P.q_bl.p,
                     pval, c.sumP, totals, ox, m0, nc);
                 TSKB_CK_LAUNCH();
                 c.launches++;
@@ -799,7 +829,7 @@ void run_branch(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
         if (ntiles > 0) {
             // more CTAs than are resident: later ones start as earlier ones finish (measured 8 % faster
             // than exactly-resident persistent CTAs)
-            k_branch_summary<STAT, KP><<<std::min<uint32_t>(ntiles, (uint32_t) (sms * std::max(per_sm, 8))), TB, 0, c.s>>>(
+            k_branch_summary<STAT, V><<<std::min<uint32_t>(ntiles, (uint32_t) (sms * std::max(per_sm, 8))), TB, 0, c.s>>>(
                 P.npp, P.q_bp0.p, P.q_bp1.p, P.q_bl.p, pval, c.sumP, totals, out, m0, m1);
             TSKB_CK_LAUNCH();
             c.launches++;
@@ -810,20 +840,20 @@ void run_branch(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
     TSKB_CK(cudaEventRecord(P.ev[4], c.s));
 }
 
-template <int STAT, int KP>
-void run_site(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
+template <int STAT, class V>
+void run_site(CallCtx &c, V *pval, V totals) {
     const Plan &P = *c.P;
     const uint32_t W = c.sp->W, M = c.sp->M;
     Arena &A = P.arena;
-    launch_sweep<KP>(c, pval);
+    launch_sweep<V>(c, pval);
     TSKB_CK(cudaEventRecord(P.ev[2], c.s));
     const uint32_t nsites = P.site_hi - P.site_lo;
     const uint32_t nsplit = std::max<uint32_t>(1, (592 + W - 1) / W);
     double *partial = A.get<double>((size_t) W * nsplit * M);
     double *R = A.get<double>((size_t) M * std::max<uint32_t>(nsites, 1));
-    IVec<KP> *scratch = A.get<IVec<KP>>(P.total_alleles + 1);
+    V *scratch = A.get<V>(P.total_alleles + 1);
     if (nsites) {
-        k_site_summary<STAT, KP><<<grid_for(nsites, 128), 128, 0, c.s>>>(P.site_lo, nsites,
+        k_site_summary<STAT, V><<<grid_for(nsites, 128), 128, 0, c.s>>>(P.site_lo, nsites,
             P.site_moff.p, P.site_aoff.p, P.mut_src.p, P.mut_allele.p, P.mut_alt.p, pval, totals,
             scratch, c.sumP, R);
         TSKB_CK_LAUNCH();
@@ -840,16 +870,16 @@ void run_site(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
     TSKB_CK(cudaEventRecord(P.ev[4], c.s));
 }
 
-template <int STAT, int KP>
-void run_phases(CallCtx &c, IVec<KP> *pval, IVec<KP> totals) {
+template <int STAT, class V>
+void run_phases(CallCtx &c, V *pval, V totals) {
     if (c.sp->options & TSKB_STAT_BRANCH) {
-        run_branch<STAT, KP>(c, pval, totals);
+        run_branch<STAT, V>(c, pval, totals);
     } else {
-        run_site<STAT, KP>(c, pval, totals);
+        run_site<STAT, V>(c, pval, totals);
     }
 }
 
-template <int KP>
+template <class V>
 int run_impl(const Plan &P, const StatSpec &sp) {
     cudaStream_t s = P.stream;
     const uint32_t K = sp.K, M = sp.M, W = sp.W;
@@ -862,16 +892,17 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     TSKB_CK(cudaEventRecord(P.ev[0], s));
 
     // ---- phase 0: weights.  State slots: [npp pieces | one INIT slot per sample | zero slot]
+    constexpr bool WEIGHTED = std::is_same<typename V::scalar, double>::value;
     uint64_t total = 0;
     std::vector<uint32_t> h_off(K + 1, 0);
-    for (uint32_t k = 0; k < K; k++) {
+    for (uint32_t k = 0; k < K && !WEIGHTED; k++) {
         total += sp.sizes[k];
         h_off[k + 1] = (uint32_t) total;
     }
-    IVec<KP> *pval = A.get<IVec<KP>>((size_t) P.npp + P.num_samples + 1);
-    IVec<KP> *init = pval + P.npp;
+    V *pval = A.get<V>((size_t) P.npp + P.num_samples + 1);
+    V *init = pval + P.npp;
     const int32_t *d_sets = sp.sets;
-    if (!sp.sets_on_device) {
+    if (!sp.sets_on_device && !WEIGHTED) {
         int32_t *tmp_sets = A.get<int32_t>(total);
         TSKB_CK(cudaMemcpyAsync(tmp_sets, sp.sets, total * sizeof(int32_t), cudaMemcpyHostToDevice, s));
         d_sets = tmp_sets;
@@ -882,11 +913,16 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     sumP.M = (int) M;
     sumP.polarised = (sp.options & TSKB_STAT_POLARISED) ? 1 : 0;
     sumP.skip_zero_bl = 1;
-    IVec<KP> totals;
-    for (int k = 0; k < KP; k++) totals.v[k] = 0;
+    V totals;
+    for (int k = 0; k < V::N; k++) totals.v[k] = 0;
     for (uint32_t k = 0; k < K; k++) {
-        sumP.n[k] = (double) sp.sizes[k];
-        totals.v[k] = (int32_t) sp.sizes[k];
+        if constexpr (WEIGHTED) {
+            sumP.n[k] = (double) P.num_samples;
+            totals.v[k] = sp.column_totals[k];  // total_weight of general_stat (trees.c:1406-1415)
+        } else {
+            sumP.n[k] = (double) sp.sizes[k];
+            totals.v[k] = (int32_t) sp.sizes[k];
+        }
     }
     // All small per-call inputs travel in ONE host-to-device copy:
     //   [0] validation key (all ones)  [8] duplicate flag, sweep error flag  [16] completion counters
@@ -905,6 +941,18 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         for (uint32_t a = 0; a < sp.tuple; a++) t[a] = sp.indexes[(size_t) m * sp.tuple + a];
         if (sp.stat_id == STAT_TABULATED) t[0] = 0;
         q.i = t[0]; q.j = t[1]; q.k = t[2]; q.l = t[3];
+        if constexpr (WEIGHTED) {
+            const double n = (double) P.num_samples;
+            q.ni = q.nj = q.nk = q.nl = 0.0;
+            q.inv = 1.0;
+            if (sp.stat_id == STAT_TRAIT_COV) {
+                q.ni = 2 * (n - 1) * (n - 1);  // trees.c:3972
+            } else if (sp.stat_id == STAT_REL_WEIGHTED || sp.stat_id == STAT_REL_WEIGHTED_NC) {
+                q.ni = sp.column_totals[t[0]];
+                q.nj = sp.column_totals[t[1]];
+            }
+            continue;
+        }
         q.ni = (double) sp.sizes[t[0]]; q.nj = (double) sp.sizes[t[1]];
         q.nk = (double) sp.sizes[t[2]]; q.nl = (double) sp.sizes[t[3]];
         q.inv = 1.0 / column_denominator(sp.stat_id, q);
@@ -920,9 +968,19 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     uint32_t *d_off = reinterpret_cast<uint32_t *>(ds + o_off);
     sumP.cols = reinterpret_cast<const ColP *>(ds + o_cols);
     c.d_windows = reinterpret_cast<double *>(ds + o_win);
-    TSKB_CK(cudaMemsetAsync(init, 0, ((size_t) P.num_samples + 1) * sizeof(IVec<KP>), s));
-    if (total) {
-        k_set_weights<KP><<<grid_for(total, TB), TB, 0, s>>>(d_sets, d_off, K, (uint32_t) total,
+    TSKB_CK(cudaMemsetAsync(init, 0, ((size_t) P.num_samples + 1) * sizeof(V), s));
+    if constexpr (WEIGHTED) {
+        (void) d_sets; (void) d_off; (void) d_verr; (void) total;
+        double *d_w = A.get<double>((size_t) P.num_samples * K);
+        TSKB_CK(cudaMemcpyAsync(d_w, sp.weights, (size_t) P.num_samples * K * sizeof(double),
+            cudaMemcpyHostToDevice, s));
+        if (P.num_samples) {
+            k_init_weights<V><<<grid_for(P.num_samples, TB), TB, 0, s>>>(d_w, P.num_samples, K, init);
+            TSKB_CK_LAUNCH();
+            c.launches++;
+        }
+    } else if (total) {
+        k_set_weights<V><<<grid_for(total, TB), TB, 0, s>>>(d_sets, d_off, K, (uint32_t) total,
             P.d_sample_index.p, (int32_t) P.N, init, d_verr, d_dup);
         TSKB_CK_LAUNCH();
         c.launches++;
@@ -941,21 +999,30 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     TSKB_CK(cudaEventRecord(P.ev[1], s));
 
     // ---- phases 1-3: sweep (+ branch summary), summary, finalize
+    if constexpr (WEIGHTED) {
+        switch (sp.stat_id) {
+            case STAT_TRAIT_COV: run_phases<STAT_TRAIT_COV, V>(c, pval, totals); break;
+            case STAT_TRAIT_CORR: run_phases<STAT_TRAIT_CORR, V>(c, pval, totals); break;
+            case STAT_REL_WEIGHTED: run_phases<STAT_REL_WEIGHTED, V>(c, pval, totals); break;
+            case STAT_REL_WEIGHTED_NC: run_phases<STAT_REL_WEIGHTED_NC, V>(c, pval, totals); break;
+            default: return TSKB_ERR_BAD_PARAM_VALUE;
+        }
+    } else
     switch (sp.stat_id) {
-        case STAT_DIVERSITY: run_phases<STAT_DIVERSITY, KP>(c, pval, totals); break;
-        case STAT_SEGSITES: run_phases<STAT_SEGSITES, KP>(c, pval, totals); break;
-        case STAT_Y1: run_phases<STAT_Y1, KP>(c, pval, totals); break;
-        case STAT_DIVERGENCE: run_phases<STAT_DIVERGENCE, KP>(c, pval, totals); break;
-        case STAT_Y2: run_phases<STAT_Y2, KP>(c, pval, totals); break;
-        case STAT_F2: run_phases<STAT_F2, KP>(c, pval, totals); break;
-        case STAT_RELATEDNESS: run_phases<STAT_RELATEDNESS, KP>(c, pval, totals); break;
-        case STAT_RELATEDNESS_NC: run_phases<STAT_RELATEDNESS_NC, KP>(c, pval, totals); break;
-        case STAT_Y3: run_phases<STAT_Y3, KP>(c, pval, totals); break;
-        case STAT_F3: run_phases<STAT_F3, KP>(c, pval, totals); break;
-        case STAT_F4: run_phases<STAT_F4, KP>(c, pval, totals); break;
+        case STAT_DIVERSITY: run_phases<STAT_DIVERSITY, V>(c, pval, totals); break;
+        case STAT_SEGSITES: run_phases<STAT_SEGSITES, V>(c, pval, totals); break;
+        case STAT_Y1: run_phases<STAT_Y1, V>(c, pval, totals); break;
+        case STAT_DIVERGENCE: run_phases<STAT_DIVERGENCE, V>(c, pval, totals); break;
+        case STAT_Y2: run_phases<STAT_Y2, V>(c, pval, totals); break;
+        case STAT_F2: run_phases<STAT_F2, V>(c, pval, totals); break;
+        case STAT_RELATEDNESS: run_phases<STAT_RELATEDNESS, V>(c, pval, totals); break;
+        case STAT_RELATEDNESS_NC: run_phases<STAT_RELATEDNESS_NC, V>(c, pval, totals); break;
+        case STAT_Y3: run_phases<STAT_Y3, V>(c, pval, totals); break;
+        case STAT_F3: run_phases<STAT_F3, V>(c, pval, totals); break;
+        case STAT_F4: run_phases<STAT_F4, V>(c, pval, totals); break;
         case STAT_TABULATED:
-            if constexpr (KP == 1) {
-                run_phases<STAT_TABULATED, KP>(c, pval, totals);
+            if constexpr (std::is_same<V, IVec<1>>::value) {
+                run_phases<STAT_TABULATED, V>(c, pval, totals);
                 break;
             }
             return TSKB_ERR_UNSUPPORTED;
@@ -995,10 +1062,20 @@ int run_impl(const Plan &P, const StatSpec &sp) {
 int run_sample_count_stat(const Plan *plan, const StatSpec &spec) {
     std::lock_guard<std::mutex> lock(plan->mu);
     TSKB_CK(cudaSetDevice(plan->device));
-    if (spec.K <= 1) return run_impl<1>(*plan, spec);
-    if (spec.K <= 2) return run_impl<2>(*plan, spec);
-    if (spec.K <= 4) return run_impl<4>(*plan, spec);
-    if (spec.K <= 8) return run_impl<8>(*plan, spec);
+    if (spec.K <= 1) return run_impl<IVec<1>>(*plan, spec);
+    if (spec.K <= 2) return run_impl<IVec<2>>(*plan, spec);
+    if (spec.K <= 4) return run_impl<IVec<4>>(*plan, spec);
+    if (spec.K <= 8) return run_impl<IVec<8>>(*plan, spec);
+    return TSKB_ERR_UNSUPPORTED;
+}
+
+int run_weighted_stat(const Plan *plan, const StatSpec &spec) {
+    std::lock_guard<std::mutex> lock(plan->mu);
+    TSKB_CK(cudaSetDevice(plan->device));
+    if (spec.K <= 1) return run_impl<DVec<1>>(*plan, spec);
+    if (spec.K <= 2) return run_impl<DVec<2>>(*plan, spec);
+    if (spec.K <= 4) return run_impl<DVec<4>>(*plan, spec);
+    if (spec.K <= 8) return run_impl<DVec<8>>(*plan, spec);
     return TSKB_ERR_UNSUPPORTED;
 }
 

@@ -41,7 +41,8 @@ K_WAY = ("divergence", "genetic_relatedness", "Y2", "f2", "Y3", "f3", "f4")
 PUBLIC_STATS = (
     "diversity", "divergence", "divergence_matrix", "genetic_relatedness",
     "genetic_relatedness_matrix", "segregating_sites", "Tajimas_D", "Fst", "Y1", "Y2", "Y3",
-    "f2", "f3", "f4", "sample_count_stat", "general_stat")
+    "f2", "f3", "f4", "sample_count_stat", "general_stat", "trait_covariance", "trait_correlation",
+    "genetic_relatedness_weighted")
 
 
 def tables_from_tree_sequence(ts):
@@ -102,7 +103,9 @@ def _make(name):
     return method
 
 
-for _n in ONE_WAY + K_WAY + ("divergence_matrix", "general_stat"):
+WEIGHTED = ("trait_covariance", "trait_correlation", "genetic_relatedness_weighted")
+
+for _n in ONE_WAY + K_WAY + WEIGHTED + ("divergence_matrix", "general_stat"):
     setattr(_Proxy, _n, _make(_n))
 
 

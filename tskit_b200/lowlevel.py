@@ -300,6 +300,67 @@ class LLTreeSequence:
             _p(w), options, _p(result)))
         return result
 
+    # ---- TreeSequence_one_way_weighted_method (_tskitmodule.c:6747-6830)
+    def _parse_weights(self, weights):
+        W = np.array(weights, dtype=np.float64, copy=True, order="C")
+        if W.ndim != 2:
+            raise ValueError("object of too small depth for desired array"
+                             if W.ndim < 2 else "object too deep for desired array")
+        if W.shape[0] != self.tables.num_samples:
+            raise ValueError("First dimension must be num_samples")
+        return W
+
+    def _one_way_weighted(self, name, weights, windows, mode, polarised, span_normalise):
+        options = parse_stats_mode(mode)
+        if polarised:
+            options |= STAT_POLARISED
+        if span_normalise:
+            options |= STAT_SPAN_NORMALISE
+        w = parse_windows(windows)
+        W = self._parse_weights(weights)
+        if options & STAT_NODE:
+            result = np.zeros((len(w) - 1, self.tables.num_nodes, W.shape[1]))
+        else:
+            result = np.zeros((len(w) - 1, W.shape[1]))
+        fn = getattr(_lib.lib(), "tskb_treeseq_" + name)
+        _handle(fn(self._h, W.shape[1], _p(W), len(w) - 1, _p(w), options, _p(result)))
+        return result
+
+    def trait_covariance(self, weights, windows, mode=None, polarised=False, span_normalise=False):
+        return self._one_way_weighted("trait_covariance", weights, windows, mode, polarised,
+                                      span_normalise)
+
+    def trait_correlation(self, weights, windows, mode=None, polarised=False, span_normalise=False):
+        return self._one_way_weighted("trait_correlation", weights, windows, mode, polarised,
+                                      span_normalise)
+
+    # ---- TreeSequence_k_way_weighted_stat_method (_tskitmodule.c:7280-7388)
+    def genetic_relatedness_weighted(self, weights, indexes, windows, mode=None,
+                                     span_normalise=True, polarised=False, centre=True):
+        options = parse_stats_mode(mode)
+        if span_normalise:
+            options |= STAT_SPAN_NORMALISE
+        if polarised:
+            options |= STAT_POLARISED
+        if not centre:
+            options |= STAT_NONCENTRED
+        w = parse_windows(windows)
+        W = self._parse_weights(weights)
+        idx = np.array(indexes, dtype=np.int32, copy=True, order="C")
+        if idx.ndim != 2:
+            raise ValueError("object of too small depth for desired array"
+                             if idx.ndim < 2 else "object too deep for desired array")
+        if idx.shape[0] < 1 or idx.shape[1] != 2:
+            raise ValueError("indexes must be a k x 2 array.")
+        if options & STAT_NODE:
+            result = np.zeros((len(w) - 1, self.tables.num_nodes, idx.shape[0]))
+        else:
+            result = np.zeros((len(w) - 1, idx.shape[0]))
+        _handle(_lib.lib().tskb_treeseq_genetic_relatedness_weighted(
+            self._h, W.shape[1], _p(W), idx.shape[0], _p(idx), len(w) - 1, _p(w), _p(result),
+            options))
+        return result
+
     # ---- TreeSequence_divergence_matrix (_tskitmodule.c:7435-7509)
     def divergence_matrix(self, windows, sample_sets=None, sample_set_sizes=None, mode=None,
                           span_normalise=True):
