@@ -151,7 +151,7 @@ int tskb_treeseq_f4(const tskb_treeseq_t *self, uint64_t num_sample_sets,
  * tsk_treeseq_genetic_relatedness_weighted: (trees.h:1079-1082;
  * trees.c:4840-4897), result [num_windows x num_index_tuples]; note the reference's argument
  * order (result before options).  At most 8 state columns (7 weights where a frequency column
- * is appended): more return TSKB_ERR_UNSUPPORTED. */
+ * is appended) per sweep; more columns are computed in batches. */
 int tskb_treeseq_trait_covariance(const tskb_treeseq_t *self, uint64_t num_weights,
     const double *weights, uint64_t num_windows, const double *windows, uint32_t options,
     double *result);

@@ -107,7 +107,7 @@ def test_weighted_statistics(wf_small, engines, mode):
     ll, o = engines
     n = wf_small.num_samples
     rng = np.random.default_rng(17)
-    for K in (1, 2, 3, 7):
+    for K in (1, 2, 3, 7, 13):  # 13 columns: batches of state columns
         W = rng.normal(size=(n, K)) * (1 + np.arange(K)) + np.arange(K)
         for w in (np.array([0.0, wf_small.sequence_length]), np.linspace(0, wf_small.sequence_length, 9)):
             for span in (True, False):
@@ -115,7 +115,7 @@ def test_weighted_statistics(wf_small, engines, mode):
                 assert close(got, o.trait_covariance(W, windows=w, mode=mode, span_normalise=span), cancelling=True)
                 got = ll.trait_correlation(W, w, mode=mode, span_normalise=span)
                 assert close(got, o.trait_correlation(W, windows=w, mode=mode, span_normalise=span), cancelling=True)
-            idx = rng.integers(0, K, size=(5, 2)).astype(np.int32)
+            idx = rng.integers(0, K, size=(9, 2)).astype(np.int32)
             for centre in (True, False):
                 for pol in (False, True):
                     got = ll.genetic_relatedness_weighted(W, idx, w, mode=mode, polarised=pol, centre=centre)

@@ -399,7 +399,67 @@ int weighted_stat(const tskb_treeseq_t *self, int stat_id, uint64_t cols, const 
         if (branch && P.time_uncalibrated && !(options & TSKB_STAT_ALLOW_TIME_UNCALIBRATED)) {
             return TSKB_ERR_TIME_UNCALIBRATED;
         }
-        if (cols > MAX_STATE_DIM) return TSKB_ERR_UNSUPPORTED;
+        if (cols > MAX_STATE_DIM) {
+            // Result columns are independent: batches whose columns read at most MAX_STATE_DIM state
+            // columns (the frequency column, where there is one, travels with every batch, last).
+            const bool freq = stat_id != STAT_TRAIT_COV;
+            const uint64_t n = P.num_samples, room = MAX_STATE_DIM - (freq ? 1 : 0);
+            const int width = tw > 0 ? tw : 1;
+            std::vector<int32_t> local(cols, -1), used, b_tuples;
+            std::vector<uint64_t> b_cols;
+            auto flush = [&]() -> int {
+                if (b_cols.empty()) return 0;
+                const uint64_t kb = used.size() + (freq ? 1 : 0), Mb = b_cols.size();
+                std::vector<double> Wb(n * kb), out(num_windows * Mb, 0.0);
+                for (uint64_t j = 0; j < n; j++) {
+                    for (uint64_t q = 0; q < used.size(); q++) Wb[j * kb + q] = W[j * cols + used[q]];
+                    if (freq) Wb[j * kb + kb - 1] = W[j * cols + cols - 1];
+                }
+                for (auto &x : b_tuples) {
+                    if (x < 0) x = (int32_t) kb - 1;
+                }
+                int ret = weighted_stat(self, stat_id, kb, Wb, Mb, tw, tw > 0 ? b_tuples.data() : nullptr,
+                    num_windows, windows, options, out.data());
+                if (ret != 0) return ret;
+                for (uint64_t w = 0; w < num_windows; w++) {
+                    for (uint64_t q = 0; q < Mb; q++) result[w * result_dim + b_cols[q]] = out[w * Mb + q];
+                }
+                for (int32_t k : used) local[k] = -1;
+                used.clear(); b_tuples.clear(); b_cols.clear();
+                return 0;
+            };
+            for (uint64_t m = 0; m < result_dim; m++) {
+                int32_t need[2];
+                for (int a = 0; a < width; a++) need[a] = tw > 0 ? tuples[m * tw + a] : (int32_t) m;
+                uint64_t fresh = 0;
+                for (int a = 0; a < width; a++) {
+                    bool seen = (freq && need[a] == (int32_t) cols - 1) || local[need[a]] >= 0;
+                    for (int c = 0; c < a; c++) seen |= need[c] == need[a];
+                    fresh += !seen;
+                }
+                if (used.size() + fresh > room) {
+                    int ret = flush();
+                    if (ret != 0) return ret;
+                }
+                for (int a = 0; a < width; a++) {
+                    const int32_t k = need[a];
+                    const bool is_freq = freq && k == (int32_t) cols - 1;
+                    if (!is_freq && local[k] < 0) {
+                        local[k] = (int32_t) used.size();
+                        used.push_back(k);
+                    }
+                    // the frequency column's local index is only known at flush time: mark it
+                    if (tw > 0) b_tuples.push_back(is_freq ? -1 : local[k]);
+                }
+                b_cols.push_back(m);
+                // one-way statistics keep result column q = state column q: flush when full
+                if (tw == 0 && used.size() == room) {
+                    int ret = flush();
+                    if (ret != 0) return ret;
+                }
+            }
+            return flush();
+        }
         // total_weight of general_stat: summed over the samples in order (trees.c:2003-2010)
         std::vector<double> totals(cols, 0.0);
         for (uint64_t j = 0; j < P.num_samples; j++) {
