@@ -117,7 +117,7 @@ def measured_traffic(kernel):
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
-    key = {"sweep": "k_sweep<1>", "summary": "k_branch_summary<0, 1>"}.get(kernel)
+    key = {"sweep": "k_sweep<SVec<int, 1>>", "summary": "k_branch_summary<0, SVec<int, 1>>"}.get(kernel)
     return d.get(key)
 
 
