@@ -158,6 +158,12 @@ int tskb_treeseq_trait_covariance(const tskb_treeseq_t *self, uint64_t num_weigh
 int tskb_treeseq_trait_correlation(const tskb_treeseq_t *self, uint64_t num_weights,
     const double *weights, uint64_t num_windows, const double *windows, uint32_t options,
     double *result);
+/* tsk_treeseq_trait_linear_model (trees.h:1068-1070; trees.c:4106-4219): `covariates` row-major
+ * [num_samples x num_covariates], already orthonormalised as the reference assumes;
+ * num_weights + num_covariates + 1 <= 8 state columns, else TSKB_ERR_UNSUPPORTED. */
+int tskb_treeseq_trait_linear_model(const tskb_treeseq_t *self, uint64_t num_weights,
+    const double *weights, uint64_t num_covariates, const double *covariates, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result);
 int tskb_treeseq_genetic_relatedness_weighted(const tskb_treeseq_t *self, uint64_t num_weights,
     const double *weights, uint64_t num_index_tuples, const int32_t *index_tuples,
     uint64_t num_windows, const double *windows, double *result, uint32_t options);

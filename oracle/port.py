@@ -163,6 +163,27 @@ class Oracle:
             return np.zeros(K)
         return self.general_stat(Ws, f, K, windows=windows, mode=mode, span_normalise=span_normalise)
 
+    def trait_linear_model(self, W, Z, windows=None, mode="site", span_normalise=True):
+        """tsk_treeseq_trait_linear_model, c/tskit/trees.c:4106-4219 (Z already orthonormalised, as
+        the low-level reference function assumes)."""
+        W = np.asarray(W, dtype=np.float64)
+        Z = np.asarray(Z, dtype=np.float64)
+        n, K, Cn = self.t.num_samples, W.shape[1], Z.shape[1]
+        V = W.T @ Z
+        Wn = np.column_stack([W, Z, np.ones(n)])
+
+        def f(x):
+            m = x[K + Cn]
+            out = np.zeros(K)
+            if 0.0 < m < n:
+                z = x[K:K + Cn]
+                for i in range(K):
+                    a = x[i] - (z * V[i]).sum()
+                    denom = m - (z * z).sum()
+                    out[i] = 0.0 if denom < 1e-8 else (a * a) / (2 * denom * denom)
+            return out
+        return self.general_stat(Wn, f, K, windows=windows, mode=mode, span_normalise=span_normalise)
+
     def genetic_relatedness_weighted(self, W, indexes, windows=None, mode="site", span_normalise=True,
                                      polarised=False, centre=True):
         """tsk_treeseq_genetic_relatedness_weighted, c/tskit/trees.c:4800-4897."""

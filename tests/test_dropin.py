@@ -126,6 +126,10 @@ def test_oracle_weighted_statistics_pinned_to_reference(ts, wf_small):
                            ts.trait_covariance(W, windows=w, mode=mode), rtol=1e-9, atol=1e-12)
         assert np.allclose(o.trait_correlation(W, windows=w, mode=mode),
                            ts.trait_correlation(W, windows=w, mode=mode), rtol=1e-9, atol=1e-12)
+        Z = np.linalg.qr(np.column_stack([np.ones(ts.num_samples), rng.normal(size=(ts.num_samples, 2))]))[0]
+        got = o.trait_linear_model(W, Z, windows=w, mode=mode)
+        want = ts.ll_tree_sequence.trait_linear_model(W, Z, w, mode=mode, span_normalise=True)
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
         idx = [(0, 1), (2, 2), (1, 0)]
         for centre in (True, False):
             got = o.genetic_relatedness_weighted(W, idx, windows=w, mode=mode, centre=centre)
@@ -150,7 +154,10 @@ def test_weighted_statistics_through_dropin(ts):
         for centre in (True, False):
             same(acc.genetic_relatedness_weighted(W, indexes=[(0, 1), (1, 1)], windows=w, mode=mode, centre=centre),
                  ts.genetic_relatedness_weighted(W, indexes=[(0, 1), (1, 1)], windows=w, mode=mode, centre=centre))
-    assert acc.accel_stats["forwarded"] == 0 and acc.accel_stats["accelerated"] == 10
+        Z = rng.normal(size=(ts.num_samples, 2))
+        same(acc.trait_linear_model(W, Z, windows=w, mode=mode), ts.trait_linear_model(W, Z, windows=w, mode=mode))
+        same(acc.trait_linear_model(W[:, :1], None, mode=mode), ts.trait_linear_model(W[:, :1], None, mode=mode))
+    assert acc.accel_stats["forwarded"] == 0 and acc.accel_stats["accelerated"] == 14
     W9 = rng.normal(size=(ts.num_samples, 9))  # more state columns than a sweep carries: batched
     same(acc.trait_covariance(W9, mode="branch"), ts.trait_covariance(W9, mode="branch"))
     same(acc.trait_correlation(W9, mode="site"), ts.trait_correlation(W9, mode="site"))

@@ -115,6 +115,10 @@ def test_weighted_statistics(wf_small, engines, mode):
                 assert close(got, o.trait_covariance(W, windows=w, mode=mode, span_normalise=span), cancelling=True)
                 got = ll.trait_correlation(W, w, mode=mode, span_normalise=span)
                 assert close(got, o.trait_correlation(W, windows=w, mode=mode, span_normalise=span), cancelling=True)
+            if K <= 3:
+                Z = np.linalg.qr(np.column_stack([np.ones(n), rng.normal(size=(n, 3))]))[0]
+                got = ll.trait_linear_model(W, Z, w, mode=mode, span_normalise=True)
+                assert close(got, o.trait_linear_model(W, Z, windows=w, mode=mode), cancelling=True), K
             idx = rng.integers(0, K, size=(9, 2)).astype(np.int32)
             for centre in (True, False):
                 for pol in (False, True):

@@ -375,7 +375,7 @@ namespace {
 // (trees.c:2035-2095): mode -> dims -> windows -> time units.
 int weighted_stat(const tskb_treeseq_t *self, int stat_id, uint64_t cols, const std::vector<double> &W,
     uint64_t result_dim, int tw, const int32_t *tuples, uint64_t num_windows, const double *windows,
-    uint32_t options, double *result) {
+    uint32_t options, double *result, const double *table = nullptr, uint64_t table_rows = 0) {
     const Plan &P = *self->plan;
     return guarded([&]() -> int {
         bool site = options & TSKB_STAT_SITE, branch = options & TSKB_STAT_BRANCH,
@@ -399,6 +399,7 @@ int weighted_stat(const tskb_treeseq_t *self, int stat_id, uint64_t cols, const 
         if (branch && P.time_uncalibrated && !(options & TSKB_STAT_ALLOW_TIME_UNCALIBRATED)) {
             return TSKB_ERR_TIME_UNCALIBRATED;
         }
+        if (cols > MAX_STATE_DIM && stat_id == STAT_TRAIT_LM) return TSKB_ERR_UNSUPPORTED;
         if (cols > MAX_STATE_DIM) {
             // Result columns are independent: batches whose columns read at most MAX_STATE_DIM state
             // columns (the frequency column, where there is one, travels with every batch, last).
@@ -477,6 +478,8 @@ int weighted_stat(const tskb_treeseq_t *self, int stat_id, uint64_t cols, const 
         sp.result = result;
         sp.weights = W.data();
         sp.column_totals = totals.data();
+        sp.f_table = table;
+        sp.table_rows = table_rows;
         return run_weighted_stat(&P, sp);
     });
 }
@@ -527,6 +530,29 @@ int tskb_treeseq_trait_correlation(const tskb_treeseq_t *self, uint64_t num_weig
     }
     return weighted_stat(self, STAT_TRAIT_CORR, K + 1, W, K, 0, nullptr, num_windows, windows, options,
         result);
+}
+
+/* tsk_treeseq_trait_linear_model (trees.c:4153-4219): covariates already orthonormalised by the
+ * caller (as the reference assumes); state = traits | covariates | number of samples below */
+int tskb_treeseq_trait_linear_model(const tskb_treeseq_t *self, uint64_t num_weights, const double *weights,
+    uint64_t num_covariates, const double *covariates, uint64_t num_windows, const double *windows,
+    uint32_t options, double *result) {
+    if (self == nullptr || self->plan == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    if (num_weights < 1) return TSKB_ERR_INSUFFICIENT_WEIGHTS;
+    const uint64_t n = self->plan->num_samples, K = num_weights, C = num_covariates, cols = K + C + 1;
+    std::vector<double> V(std::max<uint64_t>(C * K, 1), 0.0), W(n * cols);
+    for (uint64_t k = 0; k < n; k++) {  // V = weights^T covariates, in the reference's loop order
+        for (uint64_t i = 0; i < K; i++) {
+            for (uint64_t j = 0; j < C; j++) V[i * C + j] += weights[k * K + i] * covariates[k * C + j];
+        }
+    }
+    for (uint64_t k = 0; k < n; k++) {
+        for (uint64_t i = 0; i < K; i++) W[k * cols + i] = weights[k * K + i];
+        for (uint64_t i = 0; i < C; i++) W[k * cols + K + i] = covariates[k * C + i];
+        W[k * cols + K + C] = 1.0;
+    }
+    return weighted_stat(self, STAT_TRAIT_LM, cols, W, K, 0, nullptr, num_windows, windows, options, result,
+        V.data(), C);
 }
 
 /* tsk_treeseq_genetic_relatedness_weighted (trees.c:4840-4897): append the 1/n column */

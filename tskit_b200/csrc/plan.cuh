@@ -163,7 +163,8 @@ enum StatId {
     STAT_F2 = 5, STAT_RELATEDNESS = 6, STAT_Y3 = 7, STAT_F3 = 8, STAT_F4 = 9,
     STAT_RELATEDNESS_NC = 10, STAT_TABULATED = 11,
     // weighted statistics: fp64 states (trees.c:3960-4110, 4800-4897)
-    STAT_TRAIT_COV = 12, STAT_TRAIT_CORR = 13, STAT_REL_WEIGHTED = 14, STAT_REL_WEIGHTED_NC = 15
+    STAT_TRAIT_COV = 12, STAT_TRAIT_CORR = 13, STAT_REL_WEIGHTED = 14, STAT_REL_WEIGHTED_NC = 15,
+    STAT_TRAIT_LM = 16
 };
 
 int run_sample_count_stat(const Plan *plan, const StatSpec &spec);

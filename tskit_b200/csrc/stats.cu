@@ -164,6 +164,21 @@ __device__ __forceinline__ double f_eval(const SumP &P, const ColP &c, int m, co
         // trees.c:4800-4820: c.ni, c.nj = total weights of the two columns
         const double pn = pick<V>(s, P.K - 1);
         return (pick<V>(s, c.i) - c.ni * pn) * (pick<V>(s, c.j) - c.nj * pn);
+    } else if constexpr (STAT == STAT_TRAIT_LM) {
+        // trees.c:4106-4151: columns [0, M) traits, [M, K - 1) covariates, K - 1 the number of samples
+        // below; P.table = V [M x table_rows] (traits^T covariates), table_rows = number of covariates
+        const double num_samples = P.n[0], mm = pick<V>(s, P.K - 1);
+        if ((mm > 0.0) && (mm < num_samples)) {
+            double a = pick<V>(s, c.i), denom = mm;
+            for (uint32_t j = 0; j < P.table_rows; j++) {
+                const double z = pick<V>(s, P.M + (int) j);
+                a -= z * __ldg(P.table + (size_t) c.i * P.table_rows + j);
+                denom -= z * z;
+            }
+            if (denom < 1e-8) return 0.0;
+            return (a * a) / (2 * denom * denom);
+        }
+        return 0.0;
     } else if constexpr (STAT == STAT_REL_WEIGHTED_NC) {
         return pick<V>(s, c.i) * pick<V>(s, c.j);  // trees.c:4822-4838
     } else {  // STAT_TABULATED
@@ -985,6 +1000,13 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         TSKB_CK_LAUNCH();
         c.launches++;
     }
+    if (sp.stat_id == STAT_TRAIT_LM && sp.table_rows > 0) {
+        double *d_tab = A.get<double>(sp.table_rows * M);
+        TSKB_CK(cudaMemcpyAsync(d_tab, sp.f_table, sp.table_rows * M * sizeof(double),
+            cudaMemcpyHostToDevice, s));
+        sumP.table = d_tab;
+    }
+    if (sp.stat_id == STAT_TRAIT_LM) sumP.table_rows = (uint32_t) sp.table_rows;
     if (sp.stat_id == STAT_TABULATED) {
         double *d_tab = A.get<double>(sp.table_rows * M);
         TSKB_CK(cudaMemcpyAsync(d_tab, sp.f_table, sp.table_rows * M * sizeof(double),
@@ -1005,6 +1027,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
             case STAT_TRAIT_CORR: run_phases<STAT_TRAIT_CORR, V>(c, pval, totals); break;
             case STAT_REL_WEIGHTED: run_phases<STAT_REL_WEIGHTED, V>(c, pval, totals); break;
             case STAT_REL_WEIGHTED_NC: run_phases<STAT_REL_WEIGHTED_NC, V>(c, pval, totals); break;
+            case STAT_TRAIT_LM: run_phases<STAT_TRAIT_LM, V>(c, pval, totals); break;
             default: return TSKB_ERR_BAD_PARAM_VALUE;
         }
     } else

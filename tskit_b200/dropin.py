@@ -42,7 +42,7 @@ PUBLIC_STATS = (
     "diversity", "divergence", "divergence_matrix", "genetic_relatedness",
     "genetic_relatedness_matrix", "segregating_sites", "Tajimas_D", "Fst", "Y1", "Y2", "Y3",
     "f2", "f3", "f4", "sample_count_stat", "general_stat", "trait_covariance", "trait_correlation",
-    "genetic_relatedness_weighted")
+    "trait_linear_model", "genetic_relatedness_weighted")
 
 
 def tables_from_tree_sequence(ts):
@@ -103,7 +103,8 @@ def _make(name):
     return method
 
 
-WEIGHTED = ("trait_covariance", "trait_correlation", "genetic_relatedness_weighted")
+WEIGHTED = ("trait_covariance", "trait_correlation", "trait_linear_model",
+            "genetic_relatedness_weighted")
 
 for _n in ONE_WAY + K_WAY + WEIGHTED + ("divergence_matrix", "general_stat"):
     setattr(_Proxy, _n, _make(_n))

@@ -334,6 +334,25 @@ class LLTreeSequence:
         return self._one_way_weighted("trait_correlation", weights, windows, mode, polarised,
                                       span_normalise)
 
+    # ---- TreeSequence_one_way_covariates_method (_tskitmodule.c:6819-6905)
+    def trait_linear_model(self, weights, covariates, windows, mode=None, polarised=False,
+                           span_normalise=False):
+        options = parse_stats_mode(mode)
+        if polarised:
+            options |= STAT_POLARISED
+        if span_normalise:
+            options |= STAT_SPAN_NORMALISE
+        w = parse_windows(windows)
+        W = self._parse_weights(weights)
+        Z = self._parse_weights(covariates)
+        if options & STAT_NODE:
+            result = np.zeros((len(w) - 1, self.tables.num_nodes, W.shape[1]))
+        else:
+            result = np.zeros((len(w) - 1, W.shape[1]))
+        _handle(_lib.lib().tskb_treeseq_trait_linear_model(
+            self._h, W.shape[1], _p(W), Z.shape[1], _p(Z), len(w) - 1, _p(w), options, _p(result)))
+        return result
+
     # ---- TreeSequence_k_way_weighted_stat_method (_tskitmodule.c:7280-7388)
     def genetic_relatedness_weighted(self, weights, indexes, windows, mode=None,
                                      span_normalise=True, polarised=False, centre=True):
