@@ -31,6 +31,10 @@ extern "C" {
 #define TSKB_STAT_ALLOW_TIME_UNCALIBRATED (1u << 12)
 #define TSKB_STAT_PAIR_NORMALISE (1u << 13)
 #define TSKB_STAT_NONCENTRED (1u << 14)
+
+/* tskb_treeseq_init option: keep the pieces of nodes without a branch above them too, which
+ * mode="node" statistics need (every node has a value); costs ~16 % in the other modes. */
+#define TSKB_INIT_NODE_MODE (1u << 0)
 /* c/tskit/genotypes.h:35 */
 #define TSKB_ISOLATED_NOT_MISSING (1u << 1)
 

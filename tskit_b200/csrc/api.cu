@@ -234,7 +234,12 @@ int sample_count_stat(const tskb_treeseq_t *self, int stat_id, uint64_t K, const
             int ret = check_windows(P, num_windows, windows, true);
             if (ret != 0) LATER(ret);
         }
-        if (node) LATER(TSKB_ERR_UNSUPPORTED);  // W x N x M output: not on this path
+        // node mode needs the plan that keeps every piece (TSKB_INIT_NODE_MODE), a host result and
+        // one sweep's worth of sample sets; W x N x M doubles must fit the device
+        if (node && (!P.all_pieces || result_on_device || K > MAX_STATE_DIM
+                        || (double) num_windows * (double) P.N * (double) M > 1e9)) {
+            LATER(TSKB_ERR_UNSUPPORTED);
+        }
         if (branch && P.time_uncalibrated && !(options & TSKB_STAT_ALLOW_TIME_UNCALIBRATED)) {
             LATER(TSKB_ERR_TIME_UNCALIBRATED);
         }
@@ -395,7 +400,10 @@ int weighted_stat(const tskb_treeseq_t *self, int stat_id, uint64_t cols, const 
             int ret = check_windows(P, num_windows, windows, true);
             if (ret != 0) return ret;
         }
-        if (node) return TSKB_ERR_UNSUPPORTED;
+        if (node && (!P.all_pieces || cols > MAX_STATE_DIM
+                        || (double) num_windows * (double) P.N * (double) result_dim > 1e9)) {
+            return TSKB_ERR_UNSUPPORTED;
+        }
         if (branch && P.time_uncalibrated && !(options & TSKB_STAT_ALLOW_TIME_UNCALIBRATED)) {
             return TSKB_ERR_TIME_UNCALIBRATED;
         }

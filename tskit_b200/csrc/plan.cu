@@ -31,7 +31,7 @@ uint64_t Plan::device_bytes() const {
     return time.bytes() + d_samples.bytes() + coff.bytes() + csr_left.bytes() + csr_right.bytes()
            + csr_parent.bytes() + ev_pos.bytes() + ev_child.bytes() + ev_sign.bytes()
            + voff.bytes() + q_off.bytes() + refs.bytes() + q_bp0.bytes() + q_bp1.bytes() + bp_pos.bytes()
-           + q_bl.bytes() + tile_dep.bytes() + d_sample_index.bytes() + pm_off.bytes() + pm_left.bytes()
+           + q_bl.bytes() + q_node.bytes() + node_first_bp.bytes() + tile_dep.bytes() + d_sample_index.bytes() + pm_off.bytes() + pm_left.bytes()
            + pm_right.bytes() + pm_pmax.bytes() + pm_child.bytes() + rank_node.bytes() + level.bytes() + site_pos.bytes() + site_moff.bytes()
            + site_aoff.bytes() + mut_node.bytes() + mut_src.bytes() + mut_allele.bytes()
            + mut_alt.bytes();
@@ -398,9 +398,26 @@ __global__ void k_height_keys(uint32_t P, const uint8_t *needed, const uint32_t 
 // A piece without a branch above it (a root, or a detached node) is no other piece's child over
 // its span and adds nothing to a branch statistic: it is computed only if a mutation sits on it
 // (site mode reads state[mutation.node], trees.c:1744-1763).
-__global__ void k_needed_branch(uint32_t P, const double *pc_x, const double *pc_bl, uint8_t *needed) {
+__global__ void k_needed_branch(uint32_t P, const double *pc_x, const double *pc_bl, int keep_all,
+    uint8_t *needed) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < P) needed[p] = pc_x[p] >= 0.0 && pc_bl[p] != 0.0;
+    if (p < P) needed[p] = pc_x[p] >= 0.0 && (keep_all || pc_bl[p] != 0.0);
+}
+
+// node mode: the node of every piece in processing order, and where each node's pieces begin
+__global__ void k_piece_nodes(uint32_t P, const double *pc_x, const uint32_t *piece_rank,
+    const int32_t *rank_node, const uint32_t *perm, uint32_t npp, int32_t *q_node) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P || pc_x[p] < 0.0) return;
+    const uint32_t j = perm[p];
+    if (j < npp) q_node[j] = rank_node[piece_rank[p]];
+}
+__global__ void k_node_first_bp(uint32_t N, const uint32_t *poff, const int32_t *rank_node,
+    const double *pc_x, const double *bp_pos, uint32_t T, uint32_t *node_first_bp) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    const uint32_t p = poff[r] + 1;  // the piece after the INIT piece, if it is this node's
+    node_first_bp[rank_node[r]] = p < poff[r + 1] ? lower_bound_dev(bp_pos, T, pc_x[p]) : T;
 }
 __global__ void k_needed_mutation(uint32_t Mu, const int32_t *mut_src, const double *pc_x, uint8_t *needed) {
     uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -554,7 +571,7 @@ uint32_t host_lower_bound_indexed(const double *col, const int32_t *order, uint6
 // ------------------------------------------------------------------ build
 
 Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double range_right,
-    uint32_t /*options*/) {
+    uint32_t options) {
     auto t_start = std::chrono::steady_clock::now();
     TSKB_CK(cudaSetDevice(device));
     std::unique_ptr<Plan> plan(new Plan());
@@ -911,7 +928,8 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     // ---- mutations: the (node-major) piece holding state[mutation.node] at the site; needed pieces
     DevArray<uint8_t> needed;
     needed.alloc((size_t) P.P + 1);
-    k_needed_branch<<<grid_for(P.P, TB), TB, 0, s>>>(P.P, pc_x.p, pc_bl.p, needed.p);
+    P.all_pieces = (options & TSKB_INIT_NODE_MODE) != 0;
+    k_needed_branch<<<grid_for(P.P, TB), TB, 0, s>>>(P.P, pc_x.p, pc_bl.p, P.all_pieces ? 1 : 0, needed.p);
     TSKB_CK_LAUNCH();
     P.site_pos.upload(t->site_position, P.S, s);
     P.mut_node.upload(t->mutation_node, P.Mu, s);
@@ -1078,6 +1096,21 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
             k_refs_reorder<<<grid_for(nreal, TB), TB, 0, s>>>(nreal, vout.p, perm.p, P.q_off.p,
                 ch_off.p, refs.p, P.refs.p);
             TSKB_CK_LAUNCH();
+        }
+        if (P.all_pieces) {
+            P.q_node.alloc(P.npp);
+            P.node_first_bp.alloc(N);
+            if (P.npp) {
+                TSKB_CK(cudaMemsetAsync(P.q_node.p, 0xff, (size_t) P.npp * sizeof(int32_t), s));
+                k_piece_nodes<<<grid_for(Pn, TB), TB, 0, s>>>(Pn, pc_x.p, piece_rank.p, P.rank_node.p, perm.p,
+                    P.npp, P.q_node.p);
+                TSKB_CK_LAUNCH();
+            }
+            if (N) {
+                k_node_first_bp<<<grid_for(N, TB), TB, 0, s>>>(N, poff.p, P.rank_node.p, pc_x.p, P.bp_pos.p,
+                    P.T, P.node_first_bp.p);
+                TSKB_CK_LAUNCH();
+            }
         }
         TSKB_CK(cudaStreamSynchronize(s));
     }

@@ -100,6 +100,10 @@ struct Plan {
     DevArray<uint32_t> tile_dep;      // [ntiles] first tile of the tile's height = number of tiles
                                       //  that must be complete before its gathers
     DevArray<int32_t> d_sample_index; // [N] node -> sample index or -1
+    // --- node mode (TSKB_INIT_NODE_MODE): every piece is kept, and every piece knows its node
+    bool all_pieces = false;
+    DevArray<int32_t> q_node;         // [npp] node of the piece (-1: padding)
+    DevArray<uint32_t> node_first_bp; // [N] breakpoint of the node's first piece (T: it has none)
     // --- parent-major edge CSR, sorted by (parent, left); pmax = running max of right within the
     //     parent's list, which bounds the backward scan of an interval-stabbing query
     DevArray<uint32_t> pm_off;        // [N + 1]

@@ -695,6 +695,57 @@ __global__ void k_window_final(const double *partial, const double *windows, uin
     result[t] = sum;
 }
 
+// ---------------------------------------------------------------- node mode
+// tsk_treeseq_node_general_stat (trees.c:1788-1918): result[w][u] is the integral over window w of
+// the summary of node u's state -- no branch lengths, and every node counts, in a tree or not.
+// A node's state is constant over each of its pieces and equal to its own weight before its first
+// piece; the plan keeps every piece for this (TSKB_INIT_NODE_MODE).
+
+template <int STAT, class V>
+__device__ __forceinline__ void node_add(const SumP &sp, const V &totals, const V &st, int32_t node,
+    double x, double xe, const double *__restrict__ windows, uint32_t W, uint32_t N, int span_normalise,
+    double *result) {
+    if (!(xe > x)) return;
+    uint32_t w = upper_bound_dev(windows, W + 1, x);
+    w = w > 0 ? w - 1 : 0;
+    for (; w < W && windows[w] < xe; w++) {
+        const double wl = windows[w], wr = windows[w + 1];
+        double len = (xe < wr ? xe : wr) - (x > wl ? x : wl);
+        if (!(len > 0.0)) continue;
+        if (span_normalise) len /= wr - wl;
+        double *row = result + ((size_t) w * N + (size_t) node) * sp.M;
+        for (int m = 0; m < sp.M; m++) {
+            const double v = F_branch<STAT, V>(sp, sp.cols[m], m, st, totals);
+            if (v != 0.0) atomicAdd(row + m, v * len);
+        }
+    }
+}
+
+template <int STAT, class V>
+__global__ void k_node_pieces(uint32_t npp, const int32_t *__restrict__ q_node,
+    const uint32_t *__restrict__ q_bp0, const uint32_t *__restrict__ q_bp1,
+    const double *__restrict__ bp_pos, const V *__restrict__ pval, SumP sp, V totals,
+    const double *__restrict__ windows, uint32_t W, uint32_t N, int span_normalise, double *result) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npp) return;
+    const int32_t node = q_node[j];
+    if (node < 0) return;
+    node_add<STAT, V>(sp, totals, pval[j], node, bp_pos[q_bp0[j]], bp_pos[q_bp1[j]], windows, W, N,
+        span_normalise, result);
+}
+
+template <int STAT, class V>
+__global__ void k_node_initial(uint32_t N, const uint32_t *__restrict__ node_first_bp,
+    const int32_t *__restrict__ sample_index, const V *__restrict__ init, uint32_t zero_slot,
+    const double *__restrict__ bp_pos, double range_left, SumP sp, V totals,
+    const double *__restrict__ windows, uint32_t W, int span_normalise, double *result) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= N) return;
+    const int32_t si = sample_index[u];
+    node_add<STAT, V>(sp, totals, init[si >= 0 ? (uint32_t) si : zero_slot], (int32_t) u, range_left,
+        bp_pos[node_first_bp[u]], windows, W, N, span_normalise, result);
+}
+
 // ---------------------------------------------------------------- trees_at
 
 __global__ void k_parent_at(const double *positions, uint32_t nq, uint32_t N,
@@ -886,8 +937,35 @@ void run_site(CallCtx &c, V *pval, V totals) {
 }
 
 template <int STAT, class V>
+void run_node(CallCtx &c, V *pval, V totals) {
+    const Plan &P = *c.P;
+    const uint32_t W = c.sp->W, M = c.sp->M, N = (uint32_t) P.N;
+    launch_sweep<V>(c, pval);
+    TSKB_CK(cudaEventRecord(P.ev[2], c.s));
+    const int span = (c.sp->options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0;
+    TSKB_CK(cudaMemsetAsync(c.d_result, 0, (size_t) W * N * M * sizeof(double), c.s));
+    if (P.npp) {
+        k_node_pieces<STAT, V><<<grid_for(P.npp, TB), TB, 0, c.s>>>(P.npp, P.q_node.p, P.q_bp0.p, P.q_bp1.p,
+            P.bp_pos.p, pval, c.sumP, totals, c.d_windows, W, N, span, c.d_result);
+        TSKB_CK_LAUNCH();
+        c.launches++;
+    }
+    TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+    if (N) {
+        k_node_initial<STAT, V><<<grid_for(N, TB), TB, 0, c.s>>>(N, P.node_first_bp.p, P.d_sample_index.p,
+            pval + P.npp, P.num_samples, P.bp_pos.p, P.range_left, c.sumP, totals, c.d_windows, W, span,
+            c.d_result);
+        TSKB_CK_LAUNCH();
+        c.launches++;
+    }
+    TSKB_CK(cudaEventRecord(P.ev[4], c.s));
+}
+
+template <int STAT, class V>
 void run_phases(CallCtx &c, V *pval, V totals) {
-    if (c.sp->options & TSKB_STAT_BRANCH) {
+    if (c.sp->options & TSKB_STAT_NODE) {
+        run_node<STAT, V>(c, pval, totals);
+    } else if (c.sp->options & TSKB_STAT_BRANCH) {
         run_branch<STAT, V>(c, pval, totals);
     } else {
         run_site<STAT, V>(c, pval, totals);
@@ -1017,7 +1095,9 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         sumP.table = d_tab;
         sumP.table_rows = (uint32_t) sp.table_rows;
     }
-    c.d_result = sp.result_on_device ? sp.result : A.get<double>((size_t) W * M);
+    // node mode: one row per node and window (trees.c:1788-1918)
+    const size_t result_size = (size_t) W * M * ((sp.options & TSKB_STAT_NODE) ? (size_t) P.N : 1);
+    c.d_result = sp.result_on_device ? sp.result : A.get<double>(result_size);
     TSKB_CK(cudaEventRecord(P.ev[1], s));
 
     // ---- phases 1-3: sweep (+ branch summary), summary, finalize
@@ -1055,7 +1135,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     unsigned long long h_flags[2] = { ~0ull, 0 };
     TSKB_CK(cudaMemcpyAsync(h_flags, d_verr, sizeof(h_flags), cudaMemcpyDeviceToHost, s));
     if (!sp.result_on_device) {
-        TSKB_CK(cudaMemcpyAsync(sp.result, c.d_result, (size_t) W * M * sizeof(double),
+        TSKB_CK(cudaMemcpyAsync(sp.result, c.d_result, result_size * sizeof(double),
             cudaMemcpyDeviceToHost, s));
     }
     TSKB_CK(cudaEventRecord(P.ev[6], s));

@@ -18,7 +18,7 @@ GRM post-processing) runs unmodified on top.
     ts.diversity(sample_sets, windows=w, mode="branch")   # same call, same result, on the GPU
 
 There is no CPU fallback for the accelerated calls: an engine failure raises.  Calls the engine
-does not cover (``mode="node"``, float-weighted ``general_stat``) are forwarded to the
+does not cover (float-weighted ``general_stat`` with a Python summary, AFS) are forwarded to the
 reference object and counted in ``ts.accel_stats["forwarded"]`` so that tests can assert which
 path ran.
 """
@@ -78,11 +78,6 @@ class _Proxy:
         return getattr(self._real, name)
 
     def _run(self, name, args, kwargs):
-        mode = kwargs.get("mode")
-        if mode == "node":
-            # W x N x M output: outside the hot path; visibly forwarded
-            self._counters["forwarded"] += 1
-            return getattr(self._real, name)(*args, **kwargs)
         try:
             out = getattr(self._engine, name)(*args, **kwargs)
         except lowlevel.LibraryError as e:

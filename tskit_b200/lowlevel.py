@@ -18,6 +18,7 @@ STAT_SITE, STAT_BRANCH, STAT_NODE = 1, 2, 4
 STAT_POLARISED, STAT_SPAN_NORMALISE = 1 << 10, 1 << 11
 STAT_NONCENTRED = 1 << 14
 ISOLATED_NOT_MISSING = 1 << 1
+INIT_NODE_MODE = 1 << 0
 
 STAT_IDS = {"diversity": 0, "segregating_sites": 1, "Y1": 2, "divergence": 3, "Y2": 4,
             "f2": 5, "genetic_relatedness": 6, "Y3": 7, "f3": 8, "f4": 9}
@@ -82,10 +83,14 @@ def parse_sample_sets(sample_set_sizes, sample_sets):
 class LLTreeSequence:
     """Device-resident tree sequence exposing ``_tskit.TreeSequence``'s statistics methods."""
 
-    def __init__(self, tables: Tables, device=0, genome_range=None):
+    def __init__(self, tables: Tables, device=0, genome_range=None, node_mode=False):
         tables.ensure_derived()
         self.tables = tables
         self.device = device
+        # mode="node" statistics need a plan that keeps the pieces of parentless nodes too
+        # (TSKB_INIT_NODE_MODE); it is staged on first use, next to the faster default plan
+        self.node_mode = bool(node_mode)
+        self._node_engine = None
         lo, hi = (0.0, tables.sequence_length) if genome_range is None else genome_range
         self.genome_range = (float(lo), float(hi))
         t = _lib.Tables()
@@ -114,10 +119,23 @@ class LLTreeSequence:
         h = C.c_void_p()
         self._h = None
         _handle(_lib.lib().tskb_treeseq_init(C.byref(h), C.byref(t), int(device),
-                                             self.genome_range[0], self.genome_range[1], 0))
+                                             self.genome_range[0], self.genome_range[1],
+                                             INIT_NODE_MODE if self.node_mode else 0))
         self._h = h
 
+    def _for_mode(self, options):
+        """The engine a call with these option bits runs on."""
+        if (options & STAT_NODE) and not self.node_mode:
+            if self._node_engine is None:
+                self._node_engine = LLTreeSequence(self.tables, device=self.device,
+                                                   genome_range=self.genome_range, node_mode=True)
+            return self._node_engine
+        return self
+
     def close(self):
+        if getattr(self, "_node_engine", None) is not None:
+            self._node_engine.close()
+            self._node_engine = None
         if getattr(self, "_h", None) is not None:
             _lib.lib().tskb_treeseq_free(self._h)
             self._h = None
@@ -173,7 +191,7 @@ class LLTreeSequence:
         else:
             result = np.zeros((len(w) - 1, len(sizes)))
         fn = getattr(_lib.lib(), "tskb_treeseq_" + name)
-        _handle(fn(self._h, len(sizes), _p(sizes), _p(sets), len(w) - 1, _p(w), options,
+        _handle(fn(self._for_mode(options)._h, len(sizes), _p(sizes), _p(sets), len(w) - 1, _p(w), options,
                    _p(result)))
         return result
 
@@ -215,7 +233,7 @@ class LLTreeSequence:
         else:
             result = np.zeros((len(w) - 1, idx.shape[0]))
         fn = getattr(_lib.lib(), "tskb_treeseq_" + name)
-        _handle(fn(self._h, len(sizes), _p(sizes), _p(sets), idx.shape[0], _p(idx),
+        _handle(fn(self._for_mode(options)._h, len(sizes), _p(sizes), _p(sets), idx.shape[0], _p(idx),
                    len(w) - 1, _p(w), options, _p(result)))
         return result
 
@@ -296,7 +314,7 @@ class LLTreeSequence:
         else:
             result = np.zeros((len(w) - 1, output_dim))
         _handle(_lib.lib().tskb_treeseq_sample_count_stat_tabulated(
-            self._h, 1, _p(sizes), _p(members), output_dim, n + 1, _p(table), len(w) - 1,
+            self._for_mode(options)._h, 1, _p(sizes), _p(members), output_dim, n + 1, _p(table), len(w) - 1,
             _p(w), options, _p(result)))
         return result
 
@@ -323,7 +341,7 @@ class LLTreeSequence:
         else:
             result = np.zeros((len(w) - 1, W.shape[1]))
         fn = getattr(_lib.lib(), "tskb_treeseq_" + name)
-        _handle(fn(self._h, W.shape[1], _p(W), len(w) - 1, _p(w), options, _p(result)))
+        _handle(fn(self._for_mode(options)._h, W.shape[1], _p(W), len(w) - 1, _p(w), options, _p(result)))
         return result
 
     def trait_covariance(self, weights, windows, mode=None, polarised=False, span_normalise=False):
@@ -350,7 +368,8 @@ class LLTreeSequence:
         else:
             result = np.zeros((len(w) - 1, W.shape[1]))
         _handle(_lib.lib().tskb_treeseq_trait_linear_model(
-            self._h, W.shape[1], _p(W), Z.shape[1], _p(Z), len(w) - 1, _p(w), options, _p(result)))
+            self._for_mode(options)._h, W.shape[1], _p(W), Z.shape[1], _p(Z), len(w) - 1, _p(w), options,
+            _p(result)))
         return result
 
     # ---- TreeSequence_k_way_weighted_stat_method (_tskitmodule.c:7280-7388)
@@ -376,7 +395,7 @@ class LLTreeSequence:
         else:
             result = np.zeros((len(w) - 1, idx.shape[0]))
         _handle(_lib.lib().tskb_treeseq_genetic_relatedness_weighted(
-            self._h, W.shape[1], _p(W), idx.shape[0], _p(idx), len(w) - 1, _p(w), _p(result),
+            self._for_mode(options)._h, W.shape[1], _p(W), idx.shape[0], _p(idx), len(w) - 1, _p(w), _p(result),
             options))
         return result
 
