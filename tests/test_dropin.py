@@ -119,6 +119,15 @@ def test_public_api_matches_reference_on_gpu(ts):
     W2 = np.random.default_rng(3).normal(size=(ts.num_samples, 2))
     same(acc.trait_covariance(W2, windows=w, mode="node"), ts.trait_covariance(W2, windows=w, mode="node"))
     assert acc.accel_stats["forwarded"] == 0
+    # genotype decode behind the unchanged TreeSequence.genotype_matrix
+    assert np.array_equal(acc.genotype_matrix(), ts.genotype_matrix())
+    sub = s[[7, 3, 150, 20]]
+    assert np.array_equal(acc.genotype_matrix(samples=sub, isolated_as_missing=False),
+                          ts.genotype_matrix(samples=sub, isolated_as_missing=False))
+    assert acc.genotype_matrix().dtype == ts.genotype_matrix().dtype
+    assert acc.accel_stats["forwarded"] == 0
+    assert np.array_equal(acc.genotype_matrix(alleles=("0", "1")), ts.genotype_matrix(alleles=("0", "1")))
+    assert acc.accel_stats["forwarded"] == 1
     assert acc.first().num_samples() == ts.num_samples
 
 

@@ -153,6 +153,29 @@ if tskit is not None:
     for _n in PUBLIC_STATS:
         setattr(AccelTreeSequence, _n, _public(_n))
 
+    def _genotype_matrix(self, *, samples=None, isolated_as_missing=None, alleles=None,
+                         impute_missing_data=None):
+        """``TreeSequence.genotype_matrix`` (``trees.py:5563-5645``) from the device decode
+        (``genotypes.c:473-594``) when the allele coding is the default one (ancestral state 0,
+        derived states in mutation order); a user-supplied ``alleles`` mapping or the deprecated
+        ``impute_missing_data`` go to the reference."""
+        engine = self._accel_engine
+        if (alleles is not None or impute_missing_data is not None
+                or not isinstance(engine, lowlevel.LLTreeSequence)):
+            self.accel_stats["forwarded"] += 1
+            return tskit.TreeSequence.genotype_matrix(
+                self, samples=samples, isolated_as_missing=isolated_as_missing, alleles=alleles,
+                impute_missing_data=impute_missing_data)
+        if samples is not None:
+            samples = np.asarray(samples, dtype=np.int32)
+        g = engine.genotype_matrix(samples=samples,
+                                   isolated_as_missing=True if isolated_as_missing is None
+                                   else bool(isolated_as_missing))
+        self.accel_stats["accelerated"] += 1
+        return g.astype(np.int32)
+    _genotype_matrix.__name__ = "genotype_matrix"
+    AccelTreeSequence.genotype_matrix = _genotype_matrix
+
     def _unpickle(base):
         fn, args = base[0], base[1]
         return accelerate(fn(*args))
