@@ -206,7 +206,7 @@ int tskb_treeseq_trees_at(const tskb_treeseq_t *self, uint64_t num_positions,
 typedef struct {
     uint64_t num_events;       /* edge diffs replayed per sweep */
     uint64_t num_visits;       /* sum over edge diffs of ancestors visited (d-bar * events) */
-    uint64_t num_levels;       /* dependency levels of the count propagation */
+    uint64_t num_levels;       /* dependent steps of the sweep (piece heights) */
     double stage_ms;           /* wall time of tskb_treeseq_init */
     double last_call_ms;       /* device time of the last statistic call (CUDA events) */
     double last_kernel_ms[8];  /* per phase: 0 weights, 1 sweep, 2 summary, 3 scan + window integration (site: window sums), 4 idle, 5 d2h;

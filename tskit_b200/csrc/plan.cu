@@ -371,7 +371,7 @@ __global__ void k_piece_children(uint32_t P, const double *pc_x, const uint32_t 
 }
 
 // height of a piece = 1 + max height of the pieces it references, INIT pieces not counted (they
-// are available before the propagation starts); relaxed to a fixed point
+// are available before the sweep starts); relaxed to a fixed point
 __global__ void k_relax_height(uint32_t P, const uint32_t *ch_off, const uint32_t *refs,
     const double *pc_x, uint32_t *height, int *changed) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -730,7 +730,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     }
     P.V = V;
     if ((uint64_t) V + nev + N >= 0xffffffffull) {
-        throw (int) TSKB_ERR_UNSUPPORTED;  // 32-bit addend indexes; shard the genome instead
+        throw (int) TSKB_ERR_UNSUPPORTED;  // 32-bit piece indexes; shard the genome instead
     }
     DevArray<int32_t> vis_node;
     DevArray<double> vis_bl;
@@ -822,7 +822,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK(cudaStreamSynchronize(s));
     }
 
-    // ---- node-major order of the entries (CHILD entries + visits), pieces, addends
+    // ---- node-major order of the entries (CHILD entries + visits), pieces
     const uint32_t Ve = V + nev;
     DevArray<uint32_t> sorted_e, sorted_key, em_ev, noff, endflag, endscan, inv, poff;
     sorted_e.alloc(Ve); sorted_key.alloc(Ve); em_ev.alloc(Ve); noff.alloc(N + 1);

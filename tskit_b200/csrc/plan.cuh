@@ -48,7 +48,7 @@
 
 namespace tskb {
 
-constexpr uint32_t PROP_TILE = 1024;   // pieces per propagation tile
+constexpr uint32_t PROP_TILE = 1024;   // pieces per sweep tile
 constexpr uint32_t NO_PIECE = 0xffffffffu;  // padding entry of the processing order
 
 struct Plan {

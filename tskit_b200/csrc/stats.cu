@@ -1154,7 +1154,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     if (h_verr != ~0ull) return (h_verr & 1ull) ? TSKB_ERR_BAD_SAMPLES : TSKB_ERR_NODE_OUT_OF_BOUNDS;
     if (h_dup) return TSKB_ERR_DUPLICATE_SAMPLE;
     if (h_err) {
-        last_error_string() = "propagation wait timed out";
+        last_error_string() = "sweep: wait for the lower heights timed out";
         return TSKB_ERR_CUDA;
     }
     return 0;
