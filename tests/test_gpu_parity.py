@@ -406,3 +406,53 @@ def test_concurrent_calls_and_engine_lifecycle(wf_small):
         e.close()
     torch.cuda.synchronize()
     assert abs(torch.cuda.mem_get_info()[0] - free0) < 64 << 20
+
+
+def test_stacked_multiallelic_mutations(wf_small):
+    """Several mutations per site on nested and unrelated nodes, four derived states, back
+    mutations to the ancestral state: the general per-site allele path, the decode's overwrite
+    order and the one-hot tensor-core contraction with more than two alleles, against the oracle."""
+    import copy
+    from tskit_b200.lowlevel import LLTreeSequence
+    t = copy.deepcopy(wf_small)
+    rng = np.random.default_rng(23)
+    L = t.sequence_length
+    pos = np.sort(rng.choice(int(L) - 1, size=400, replace=False)).astype(np.float64) + 0.5
+    msite, mnode, mstate = [], [], []
+    for j, x in enumerate(pos):
+        alive = np.nonzero((t.edges_left <= x) & (t.edges_right > x))[0]
+        k = int(rng.integers(1, 6))
+        nodes = rng.choice(np.unique(np.concatenate([t.edges_child[alive], t.edges_parent[alive]])), size=k,
+                           replace=False)  # one mutation per node and site: table order is unambiguous
+        nodes = nodes[np.argsort(-t.nodes_time[nodes], kind="stable")]  # older first: parents precede
+        for u in nodes:
+            msite.append(j); mnode.append(int(u)); mstate.append(int(rng.integers(0, 4)))
+    S, Mu = len(pos), len(msite)
+    t.sites_position = pos
+    t.sites_ancestral_state = np.full(S, ord("0"), dtype=np.int8)
+    t.sites_ancestral_state_offset = np.arange(S + 1, dtype=np.uint64)
+    t.mutations_site = np.array(msite, dtype=np.int32)
+    t.mutations_node = np.array(mnode, dtype=np.int32)
+    t.mutations_derived_state = (np.array(mstate) + ord("0")).astype(np.int8)
+    t.mutations_derived_state_offset = np.arange(Mu + 1, dtype=np.uint64)
+    t.mutations_parent = None
+    t.ensure_derived()
+    ll, o = LLTreeSequence(t), port.Oracle(t)
+    for missing in (True, False):
+        assert np.array_equal(ll.genotype_matrix(isolated_as_missing=missing),
+                              o.genotype_matrix(isolated_as_missing=missing))
+    if ref.available():  # the oracle itself against the compiled reference on this input
+        assert np.array_equal(o.genotype_matrix(), ref.RefTreeSequence(t).genotype_matrix())
+    s = t.samples
+    sets = [s[:60], s[60:61], s[61:]]
+    sizes, flat = sets_args(sets)
+    w = np.linspace(0, L, 7)
+    for pol in (False, True):
+        for nm in ONE_WAY:
+            assert close(getattr(ll, nm)(sizes, flat, windows=w, mode="site", polarised=pol),
+                         o.stat(nm, sets, windows=w, mode="site", polarised=pol), cancelling=True), nm
+        for nm, idx in K_WAY.items():
+            got = getattr(ll, nm)(sizes, flat, np.array(idx, dtype=np.int32), windows=w, mode="site", polarised=pol)
+            assert close(got, o.stat(nm, sets, idx, windows=w, mode="site", polarised=pol), cancelling=True), nm
+    got = ll.divergence_matrix(w, mode="site", span_normalise=False)
+    assert np.array_equal(got, o.divergence_matrix(None, windows=w, mode="site", span_normalise=False))
