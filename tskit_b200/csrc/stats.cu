@@ -341,9 +341,13 @@ __device__ __forceinline__ unsigned long long gtime() {
 // optional per-tile timeline (TSKB_TRACE=1): 4 timestamps per tile
 #define TRACE(slot) do { if (trace != nullptr && threadIdx.x == 0) trace[(size_t) tile * 4 + (slot)] = gtime(); } while (0)
 
-constexpr int PROP_TB = 256;
-constexpr int PROP_IPT = PROP_TILE / PROP_TB;
-constexpr int PROP_PRE = 3;  // references fetched before the wait; more are rare (multifurcations)
+// threads per sweep CTA (a tile is always PROP_TILE pieces): 512 for small states (measured on C2,
+// ms per step: 128: 0.696, 256: 0.667, 512: 0.650, 1024: 0.871), 256 where a state is 16 bytes or more
+template <class V> constexpr int prop_tb() { return sizeof(V) <= 8 ? 512 : 256; }
+// references fetched before the wait: 4 for small states (measured on C2: 2: 0.729, 3: 0.692, 4: 0.663,
+// 5: 0.685, 6: 0.725 ms per step), 3 where a state is 16 bytes or more (registers); the rare piece
+// with more (multifurcations) finishes in a loop
+template <class V> constexpr int prop_pre() { return sizeof(V) <= 8 ? 4 : 3; }  // references fetched before the wait; more are rare (multifurcations)
 constexpr uint32_t SPIN_LIMIT = 1u << 22;  // ~seconds; a legitimate wait is < the kernel's own run time
 
 struct SweepArgs {
@@ -355,7 +359,9 @@ struct SweepArgs {
 };
 
 template <class V>
-__global__ void __launch_bounds__(PROP_TB) k_sweep(SweepArgs a, V *pval) {
+__global__ void __launch_bounds__(prop_tb<V>()) k_sweep(SweepArgs a, V *pval) {
+    constexpr int PROP_PRE = prop_pre<V>();
+    constexpr int PROP_TB = prop_tb<V>(), PROP_IPT = PROP_TILE / PROP_TB;
     unsigned long long *trace = a.trace;
     for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         TRACE(0);
@@ -423,10 +429,14 @@ __global__ void __launch_bounds__(PROP_TB) k_sweep(SweepArgs a, V *pval) {
 // apart they keep their own register budgets.
 
 #ifndef TSKB_SUM_IPT
-#define TSKB_SUM_IPT 4
+#define TSKB_SUM_IPT 2
+#endif
+#ifndef TSKB_SUM_TB
+#define TSKB_SUM_TB 512
 #endif
 constexpr int SUM_IPT = TSKB_SUM_IPT;    // pieces per thread and pipeline stage
-constexpr int SUM_TILE = TB * SUM_IPT;
+constexpr int SUM_TB = TSKB_SUM_TB;      // threads per summary CTA
+constexpr int SUM_TILE = SUM_TB * SUM_IPT;
 
 template <class V>
 struct PieceRegs {
@@ -438,7 +448,7 @@ struct PieceRegs {
         const V *__restrict__ pval) {
 #pragma unroll
         for (int q = 0; q < SUM_IPT; q++) {
-            const uint32_t j = tile * SUM_TILE + q * TB + threadIdx.x;
+            const uint32_t j = tile * SUM_TILE + q * SUM_TB + threadIdx.x;
             bp1[q] = NO_PIECE;  // past the end: padding
             bp0[q] = 0;
             bl[q] = 0.0;
@@ -455,7 +465,7 @@ struct PieceRegs {
 // by the rate at which an SM can issue requests to L2, and the reductions of a warp are 32
 // separate requests.
 template <int STAT, class V>
-__global__ void __launch_bounds__(TB) k_branch_summary(uint32_t npp,
+__global__ void __launch_bounds__(SUM_TB) k_branch_summary(uint32_t npp,
     const uint32_t *__restrict__ q_bp0, const uint32_t *__restrict__ q_bp1,
     const double *__restrict__ q_bl, const V *__restrict__ pval, SumP sp, V totals,
     DeltaOut out, uint32_t m0, uint32_t m1) {
@@ -807,6 +817,7 @@ void launch_sweep(CallCtx &c, V *pval) {
         P.stats_trace = trace;
     }
     auto kern = k_sweep<V>;
+    constexpr int PROP_TB = prop_tb<V>();
     int per_sm = 1, sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
     TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PROP_TB, 0));
@@ -866,7 +877,7 @@ void run_branch(CallCtx &c, V *pval, V totals) {
     TSKB_CK(cudaEventRecord(P.ev[2], c.s));
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
-    TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_branch_summary<STAT, V>, TB, 0));
+    TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_branch_summary<STAT, V>, SUM_TB, 0));
     const uint32_t ntiles = (P.npp + SUM_TILE - 1) / SUM_TILE;
     for (uint32_t m0 = 0; m0 < M; m0 += mc) {
         const uint32_t m1 = std::min(M, m0 + mc);
@@ -895,7 +906,7 @@ void run_branch(CallCtx &c, V *pval, V totals) {
         if (ntiles > 0) {
             // more CTAs than are resident: later ones start as earlier ones finish (measured 8 % faster
             // than exactly-resident persistent CTAs)
-            k_branch_summary<STAT, V><<<std::min<uint32_t>(ntiles, (uint32_t) (sms * std::max(per_sm, 8))), TB, 0, c.s>>>(
+            k_branch_summary<STAT, V><<<std::min<uint32_t>(ntiles, (uint32_t) (sms * std::max(per_sm, 8))), SUM_TB, 0, c.s>>>(
                 P.npp, P.q_bp0.p, P.q_bp1.p, P.q_bl.p, pval, c.sumP, totals, out, m0, m1);
             TSKB_CK_LAUNCH();
             c.launches++;
