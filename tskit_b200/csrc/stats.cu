@@ -904,9 +904,11 @@ void run_branch(CallCtx &c, V *pval, V totals) {
         }
         TSKB_CK(cudaMemsetAsync(D, 0, (size_t) (m1 - m0) * col_bytes, c.s));
         if (ntiles > 0) {
-            // more CTAs than are resident: later ones start as earlier ones finish (measured 8 % faster
+            // many more CTAs than are resident: later ones start as earlier ones finish (measured 8 % faster
             // than exactly-resident persistent CTAs)
-            k_branch_summary<STAT, V><<<std::min<uint32_t>(ntiles, (uint32_t) (sms * std::max(per_sm, 8))), SUM_TB, 0, c.s>>>(
+            int mult = std::max(per_sm, 16);
+            if (const char *e = getenv("TSKB_SUM_GRID_MULT")) mult = std::max(1, atoi(e));  // experiments
+            k_branch_summary<STAT, V><<<std::min<uint32_t>(ntiles, (uint32_t) (sms * mult)), SUM_TB, 0, c.s>>>(
                 P.npp, P.q_bp0.p, P.q_bp1.p, P.q_bl.p, pval, c.sumP, totals, out, m0, m1);
             TSKB_CK_LAUNCH();
             c.launches++;
