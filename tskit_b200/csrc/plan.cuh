@@ -48,7 +48,10 @@
 
 namespace tskb {
 
-constexpr uint32_t PROP_TILE = 1024;   // pieces per sweep tile
+#ifndef TSKB_PROP_TILE
+#define TSKB_PROP_TILE 1024
+#endif
+constexpr uint32_t PROP_TILE = TSKB_PROP_TILE;   // pieces per sweep tile
 constexpr uint32_t NO_PIECE = 0xffffffffu;  // padding entry of the processing order
 
 struct Plan {

@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(prop_tb<V>()) k_sweep(SweepArgs a, V *pval) {
 // apart they keep their own register budgets.
 
 #ifndef TSKB_SUM_IPT
-#define TSKB_SUM_IPT 2
+#define TSKB_SUM_IPT 1
 #endif
 #ifndef TSKB_SUM_TB
 #define TSKB_SUM_TB 512
@@ -453,8 +453,8 @@ struct PieceRegs {
             bp0[q] = 0;
             bl[q] = 0.0;
             st[q] = ivec_zero<V>();
-            // the processing order is padded to whole PROP_TILEs: no bounds check when tiles coincide
-            if (SUM_TILE == PROP_TILE || j < npp) {
+            // the processing order is padded to whole PROP_TILEs: no bounds check when tiles divide them
+            if (PROP_TILE % SUM_TILE == 0 || j < npp) {
                 st[q] = pval[j]; bl[q] = q_bl[j]; bp0[q] = q_bp0[j]; bp1[q] = q_bp1[j];
             }
         }
