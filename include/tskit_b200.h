@@ -57,6 +57,8 @@ extern "C" {
 #define TSKB_ERR_TIME_UNCALIBRATED (-910)
 #define TSKB_ERR_STAT_POLARISED_UNSUPPORTED (-911)
 #define TSKB_ERR_INSUFFICIENT_WEIGHTS (-913)
+#define TSKB_ERR_BAD_TIME_WINDOWS_DIM (-922)
+#define TSKB_ERR_BAD_TIME_WINDOWS (-924)
 /* engine-specific codes, outside tskit's range */
 #define TSKB_ERR_CUDA (-20001)           /* a CUDA runtime call failed */
 #define TSKB_ERR_BAD_INDEX_ORDER (-20002) /* edge indexes not in canonical order */
@@ -171,6 +173,15 @@ int tskb_treeseq_trait_linear_model(const tskb_treeseq_t *self, uint64_t num_wei
 int tskb_treeseq_genetic_relatedness_weighted(const tskb_treeseq_t *self, uint64_t num_weights,
     const double *weights, uint64_t num_index_tuples, const int32_t *index_tuples,
     uint64_t num_windows, const double *windows, double *result, uint32_t options);
+
+/* tsk_treeseq_allele_frequency_spectrum (c/tskit/trees.h:1112-1116; trees.c:3814-3928), site mode:
+ * result [num_windows x prod(sample_set_sizes[k] + 1)], row-major over the sets; folded unless
+ * TSK_STAT_POLARISED.  time_windows NULL or {0, inf}.  Branch mode and more than 7 sample sets return
+ * TSKB_ERR_UNSUPPORTED. */
+int tskb_treeseq_allele_frequency_spectrum(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets, uint64_t num_windows,
+    const double *windows, uint64_t num_time_windows, const double *time_windows, uint32_t options,
+    double *result);
 
 /* tsk_treeseq_general_stat (c/tskit/trees.h:1035-1037) for the summary
  * functions a device can evaluate: the callback `f` is replaced by a table.

@@ -201,6 +201,48 @@ class Oracle:
         return self.general_stat(Wn, f, len(idx), windows=windows, mode=mode,
                                  span_normalise=span_normalise, polarised=polarised)
 
+    def site_allele_frequency_spectrum(self, sample_sets, windows=None, span_normalise=True,
+                                       polarised=False):
+        """tsk_treeseq_allele_frequency_spectrum in site mode (c/tskit/trees.c:3469-3648, 3814-3928),
+        by definition: per site and allele carried by some but not all samples, +1 (polarised,
+        ancestral allele skipped) or +1/2 (folded, :3469-3495) at the vector of per-set allele
+        counts.  Pinned against the reference package in tests/test_dropin.py."""
+        t = self.t
+        w = self._windows(windows)
+        W = len(w) - 1
+        sets = [np.asarray(x, dtype=np.int64) for x in sample_sets]
+        dims = [len(x) + 1 for x in sets]
+        out = np.zeros([W] + dims)
+        n_all = t.num_samples
+
+        def fold(coord):
+            n = sum(d - 1 for d in dims) / 2
+            s = int(sum(coord))
+            k = len(dims)
+            while s == n and k > 0:
+                k -= 1
+                n -= (dims[k] - 1) / 2
+                s -= int(coord[k])
+            if s > n:
+                return tuple(dims[k] - 1 - int(coord[k]) for k in range(len(dims)))
+            return tuple(int(c) for c in coord)
+
+        G = self.genotype_matrix(isolated_as_missing=False)
+        col = {int(u): i for i, u in enumerate(t.samples)}
+        idx = [np.array([col[int(u)] for u in x], dtype=np.int64) for x in sets]
+        inc = 1.0 if polarised else 0.5
+        for j in range(t.num_sites):
+            win = int(np.searchsorted(w, t.sites_position[j], side="right")) - 1
+            g = G[j]
+            for a in range(1 if polarised else 0, int(g.max()) + 1):
+                tot = int((g == a).sum())
+                if 0 < tot < n_all:
+                    coord = [int((g[i] == a).sum()) for i in idx]
+                    out[(win,) + (tuple(coord) if polarised else fold(coord))] += inc
+        if span_normalise:
+            out /= (w[1:] - w[:-1]).reshape([W] + [1] * len(dims))
+        return out
+
     def trees_at(self, positions, tracked=None):
         pos = np.ascontiguousarray(positions, dtype=np.float64)
         order = np.argsort(pos, kind="stable")

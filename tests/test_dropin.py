@@ -183,3 +183,41 @@ def test_weighted_statistics_through_dropin(ts):
     same(acc.genetic_relatedness_weighted(W9, indexes=pairs, mode="branch"),
          ts.genetic_relatedness_weighted(W9, indexes=pairs, mode="branch"))
     assert acc.accel_stats["forwarded"] == 0
+
+
+def test_oracle_site_afs_pinned_to_reference(ts, wf_small):
+    """The oracle's by-definition site-mode AFS against the reference package (CPU)."""
+    from oracle import port
+    o = port.Oracle(wf_small)
+    s = ts.samples()
+    sets = [s[:3], s[3:7]]
+    w = np.linspace(0, ts.sequence_length, 4)
+    for pol in (False, True):
+        for span in (True, False):
+            got = o.site_allele_frequency_spectrum(sets, windows=w, polarised=pol, span_normalise=span)
+            want = ts.allele_frequency_spectrum(sets, windows=w, mode="site", polarised=pol, span_normalise=span)
+            assert got.shape == want.shape and np.array_equal(got, want), (pol, span)
+    assert np.array_equal(o.site_allele_frequency_spectrum([s], polarised=True)[0],
+                          ts.allele_frequency_spectrum([s], mode="site", polarised=True))
+
+
+@pytest.mark.gpu
+def test_site_afs_through_dropin(ts, wf_small):
+    from oracle import port
+    acc = dropin.accelerate(ts)
+    o = port.Oracle(wf_small)
+    s = ts.samples()
+    w = np.linspace(0, ts.sequence_length, 6)
+    for sets in ([s], [s[:50], s[50:]], [s[:3], s[3:10], s[20:22]], [s[::2]]):
+        for pol in (False, True):
+            for span in (True, False):
+                got = acc.allele_frequency_spectrum(sets, windows=w, mode="site", polarised=pol, span_normalise=span)
+                want = ts.allele_frequency_spectrum(sets, windows=w, mode="site", polarised=pol, span_normalise=span)
+                assert got.shape == want.shape and np.allclose(got, want, rtol=1e-12, atol=0), (len(sets), pol, span)
+    got = acc.allele_frequency_spectrum([s[:4], s[4:9]], mode="site", polarised=True, span_normalise=False)
+    assert np.array_equal(got, o.site_allele_frequency_spectrum([s[:4], s[4:9]], polarised=True, span_normalise=False)[0])
+    assert acc.accel_stats["forwarded"] == 0
+    # branch mode: forwarded, visibly (DESIGN.md 8)
+    b = acc.allele_frequency_spectrum([s[:50]], mode="branch")
+    assert np.allclose(b, ts.allele_frequency_spectrum([s[:50]], mode="branch"))
+    assert acc.accel_stats["forwarded"] == 1

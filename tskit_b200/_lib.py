@@ -64,6 +64,7 @@ SYMBOLS = [
     "tskb_treeseq_f4", "tskb_treeseq_sample_count_stat_tabulated",
     "tskb_treeseq_trait_covariance", "tskb_treeseq_trait_correlation",
     "tskb_treeseq_genetic_relatedness_weighted", "tskb_treeseq_trait_linear_model",
+    "tskb_treeseq_allele_frequency_spectrum",
     "tskb_treeseq_divergence_matrix", "tskb_treeseq_genotype_matrix",
     "tskb_treeseq_trees_at", "tskb_treeseq_get_stats", "tskb_treeseq_stat_device",
     "tskb_treeseq_debug_array",
@@ -100,6 +101,9 @@ def lib():
         for n in ("trait_covariance", "trait_correlation"):
             getattr(L, "tskb_treeseq_" + n).argtypes = [C.c_void_p, u64, C.c_void_p, u64, C.c_void_p,
                                                         C.c_uint32, C.c_void_p]
+        L.tskb_treeseq_allele_frequency_spectrum.argtypes = [
+            C.c_void_p, u64, C.c_void_p, C.c_void_p, u64, C.c_void_p, u64, C.c_void_p, C.c_uint32,
+            C.c_void_p]
         L.tskb_treeseq_trait_linear_model.argtypes = [C.c_void_p, u64, C.c_void_p, u64, C.c_void_p, u64,
                                                       C.c_void_p, C.c_uint32, C.c_void_p]
         L.tskb_treeseq_genetic_relatedness_weighted.argtypes = [

@@ -333,6 +333,8 @@ const char *tskb_strerror(int err) {
         case TSKB_ERR_UNSUPPORTED_STAT_MODE: return "Requested statistics mode not supported for this method. (TSK_ERR_UNSUPPORTED_STAT_MODE)";
         case TSKB_ERR_TIME_UNCALIBRATED: return "Statistics using branch lengths cannot be calculated when time_units is 'uncalibrated'. (TSK_ERR_TIME_UNCALIBRATED)";
         case TSKB_ERR_STAT_POLARISED_UNSUPPORTED: return "The TSK_STAT_POLARISED option is not supported by this statistic. (TSK_ERR_STAT_POLARISED_UNSUPPORTED)";
+        case TSKB_ERR_BAD_TIME_WINDOWS_DIM: return "Must have at least one time window. (TSK_ERR_BAD_TIME_WINDOWS_DIM)";
+        case TSKB_ERR_BAD_TIME_WINDOWS: return "Time windows must start at zero and be strictly increasing. (TSK_ERR_BAD_TIME_WINDOWS)";
         case TSKB_ERR_INSUFFICIENT_WEIGHTS: return "Insufficient weights provided (at least 1 required). (TSK_ERR_INSUFFICIENT_WEIGHTS)";
         case TSKB_ERR_CUDA: return "CUDA runtime error (see tskb_last_cuda_error)";
         case TSKB_ERR_BAD_INDEX_ORDER: return "Edge indexes are not in the order tsk_table_collection_build_index produces";
@@ -582,6 +584,69 @@ int tskb_treeseq_genetic_relatedness_weighted(const tskb_treeseq_t *self, uint64
     const int stat = (options & TSKB_STAT_NONCENTRED) ? STAT_REL_WEIGHTED_NC : STAT_REL_WEIGHTED;
     return weighted_stat(self, stat, K + 1, W, num_index_tuples, 2, index_tuples, num_windows, windows,
         options, result);
+}
+
+/* tsk_treeseq_allele_frequency_spectrum (trees.c:3814-3928), site mode; checks in its order */
+int tskb_treeseq_allele_frequency_spectrum(const tskb_treeseq_t *self, uint64_t num_sample_sets,
+    const uint64_t *sample_set_sizes, const int32_t *sample_sets, uint64_t num_windows, const double *windows,
+    uint64_t num_time_windows, const double *time_windows, uint32_t options, double *result) {
+    if (self == nullptr || self->plan == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    const Plan &P = *self->plan;
+    return guarded([&]() -> int {
+        bool site = options & TSKB_STAT_SITE, branch = options & TSKB_STAT_BRANCH;
+        if (options & TSKB_STAT_NODE) return TSKB_ERR_UNSUPPORTED_STAT_MODE;
+        if (!(site || branch)) {
+            site = true;
+            options |= TSKB_STAT_SITE;
+        }
+        if (site + branch > 1) return TSKB_ERR_MULTIPLE_STAT_MODES;
+        double default_windows[2] = { 0, P.L };
+        if (windows == nullptr) {
+            num_windows = 1;
+            windows = default_windows;
+        } else {
+            int ret = check_windows(P, num_windows, windows, true);
+            if (ret != 0) return ret;
+        }
+        if (time_windows != nullptr) {  // tsk_treeseq_check_time_windows (trees.c:1288-1313)
+            if (num_time_windows < 1) return TSKB_ERR_BAD_TIME_WINDOWS_DIM;
+            if (time_windows[0] != 0.0) return TSKB_ERR_BAD_TIME_WINDOWS;
+            for (uint64_t j = 0; j < num_time_windows; j++) {
+                if (time_windows[j] >= time_windows[j + 1]) return TSKB_ERR_BAD_TIME_WINDOWS;
+            }
+            if (site && !(time_windows[0] == 0.0 && std::isinf((float) time_windows[1]))) {
+                return TSKB_ERR_UNSUPPORTED_STAT_MODE;  // site mode has no time windows (trees.c:3868)
+            }
+        }
+        int ret = check_sample_sets(P, num_sample_sets, sample_set_sizes, sample_sets);
+        if (ret != 0) return ret;
+        // the branch-mode spectrum is not on the device yet; more than 7 sets need
+        // more than one sweep's state columns
+        if (branch || num_sample_sets + 1 > MAX_STATE_DIM) return TSKB_ERR_UNSUPPORTED;
+        // state columns: the sets, then all samples (trees.c:3890-3910)
+        std::vector<uint64_t> sizes(sample_set_sizes, sample_set_sizes + num_sample_sets);
+        uint64_t total = 0, afs_size = 1;
+        for (uint64_t k = 0; k < num_sample_sets; k++) {
+            total += sizes[k];
+            afs_size *= sizes[k] + 1;
+            if (afs_size * num_windows > (uint64_t) 2e9) return TSKB_ERR_UNSUPPORTED;
+        }
+        std::vector<int32_t> sets(sample_sets, sample_sets + total);
+        sets.insert(sets.end(), P.samples.begin(), P.samples.end());
+        sizes.push_back(P.num_samples);
+        StatSpec sp = {};
+        sp.stat_id = STAT_AFS;
+        sp.K = (uint32_t) sizes.size();
+        sp.M = 1;
+        sp.sizes = sizes.data();
+        sp.sets = sets.data();
+        sp.W = (uint32_t) num_windows;
+        sp.windows = windows;
+        sp.options = options;
+        sp.result = result;
+        sp.afs_size = afs_size;
+        return run_sample_count_stat(&P, sp);
+    });
 }
 
 int tskb_treeseq_sample_count_stat_tabulated(const tskb_treeseq_t *self,

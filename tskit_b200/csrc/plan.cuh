@@ -163,6 +163,8 @@ struct StatSpec {
     // tabulated summary (stat_id == STAT_TABULATED)
     const double *f_table = nullptr;
     uint64_t table_rows = 0;
+    // STAT_AFS: size of one window's spectrum = product of (set size + 1); result is [W x afs_size]
+    uint64_t afs_size = 0;
 };
 
 enum StatId {
@@ -171,7 +173,9 @@ enum StatId {
     STAT_RELATEDNESS_NC = 10, STAT_TABULATED = 11,
     // weighted statistics: fp64 states (trees.c:3960-4110, 4800-4897)
     STAT_TRAIT_COV = 12, STAT_TRAIT_CORR = 13, STAT_REL_WEIGHTED = 14, STAT_REL_WEIGHTED_NC = 15,
-    STAT_TRAIT_LM = 16
+    STAT_TRAIT_LM = 16,
+    // joint allele frequency spectrum, site mode (trees.c:3497-3648): K sets + the all-samples column
+    STAT_AFS = 17
 };
 
 int run_sample_count_stat(const Plan *plan, const StatSpec &spec);

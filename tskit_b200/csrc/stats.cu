@@ -705,6 +705,90 @@ __global__ void k_window_final(const double *partial, const double *windows, uin
     result[t] = sum;
 }
 
+// ---------------------------------------------------------------- allele frequency spectrum, site mode
+// tsk_treeseq_update_site_afs (trees.c:3497-3540): for every allele of a site carried by some but
+// not all samples, +1 (polarised; the ancestral allele is skipped) or +1/2 (folded) at the vector
+// of per-set allele counts in the window holding the site.  State columns: the K sample sets and,
+// last, all samples.
+
+// fold (trees.c:3469-3495): the lexicographically smaller of a coordinate and its mirror image
+template <int MAXK>
+__device__ __forceinline__ void afs_fold(uint32_t (&coord)[MAXK], const uint32_t (&dims)[MAXK], int K) {
+    double n = 0;
+    int s = 0;
+    for (int k = 0; k < K; k++) {
+        n += (double) dims[k] - 1;
+        s += (int) coord[k];
+    }
+    n /= 2;
+    int k = K;
+    while (s == n && k > 0) {
+        k--;
+        n -= ((double) (dims[k] - 1)) / 2;
+        s -= (int) coord[k];
+    }
+    if (s > n) {
+        for (k = 0; k < K; k++) coord[k] = dims[k] - 1 - coord[k];
+    }
+}
+
+template <class V>
+__device__ __forceinline__ void afs_add(const V &cnt, int K, const SumP &P, uint32_t num_samples, double inc,
+    double *afs) {
+    uint32_t coord[8], dims[8];
+    uint32_t total = 0;
+#pragma unroll
+    for (int k = 0; k < V::N; k++) {
+        if (k < K) {
+            coord[k] = (uint32_t) cnt.v[k];
+            dims[k] = (uint32_t) P.n[k] + 1;
+        } else {
+            coord[k] = 0;
+            dims[k] = 1;
+        }
+        if (k == K) total = (uint32_t) cnt.v[k];
+    }
+    if (!(total > 0 && total < num_samples)) return;
+    if (!P.polarised) afs_fold<8>(coord, dims, K);
+    size_t index = 0;
+    for (int k = 0; k < K; k++) index = index * dims[k] + coord[k];  // row-major (increment_nd_array_value)
+    atomicAdd(afs + index, inc);
+}
+
+template <class V>
+__global__ void k_site_afs(uint32_t site_lo, uint32_t nsites, const uint32_t *site_moff,
+    const uint32_t *site_aoff, const int32_t *mut_src, const uint16_t *mut_allele, const uint16_t *mut_alt,
+    const V *pval, V totals, V *scratch, SumP P, uint32_t num_samples, const double *site_pos,
+    const double *windows, uint32_t W, size_t afs_size, double *result) {
+    static_assert(V::N <= 8, "at most 7 sample sets and the all-samples column");
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsites) return;
+    const uint32_t site = site_lo + t;
+    const int K = P.K - 1;  // sample sets; column K counts all samples
+    uint32_t w = upper_bound_dev(windows, W + 1, site_pos[site]);
+    w = w > 0 ? w - 1 : 0;
+    if (w >= W) w = W - 1;
+    double *afs = result + (size_t) w * afs_size;
+    const double inc = P.polarised ? 1.0 : 0.5;
+    const uint32_t a0 = site_aoff[site], na = site_aoff[site + 1] - a0;
+    const uint32_t mb = site_moff[site], me = site_moff[site + 1];
+    scratch[a0] = totals;  // allele 0 starts at the totals (trees.c:1548)
+    for (uint32_t al = 1; al < na; al++) scratch[a0 + al] = ivec_zero<V>();
+    for (uint32_t m = mb; m < me; m++) {
+        V x = pval[mut_src[m]];
+        scratch[a0 + mut_allele[m]] = scratch[a0 + mut_allele[m]] + x;
+        scratch[a0 + mut_alt[m]] = scratch[a0 + mut_alt[m]] - x;
+    }
+    for (uint32_t al = P.polarised ? 1 : 0; al < na; al++) afs_add<V>(scratch[a0 + al], K, P, num_samples, inc, afs);
+}
+
+__global__ void k_afs_span_normalise(const double *windows, uint32_t W, size_t afs_size, double *result) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t) W * afs_size) return;
+    const uint32_t w = (uint32_t) (i / afs_size);
+    result[i] /= windows[w + 1] - windows[w];
+}
+
 // ---------------------------------------------------------------- node mode
 // tsk_treeseq_node_general_stat (trees.c:1788-1918): result[w][u] is the integral over window w of
 // the summary of node u's state -- no branch lengths, and every node counts, in a tree or not.
@@ -974,6 +1058,35 @@ void run_node(CallCtx &c, V *pval, V totals) {
     TSKB_CK(cudaEventRecord(P.ev[4], c.s));
 }
 
+// joint allele frequency spectrum, site mode
+template <class V>
+void run_afs_site(CallCtx &c, V *pval, V totals) {
+    const Plan &P = *c.P;
+    const uint32_t W = c.sp->W;
+    const size_t afs_size = c.sp->afs_size;
+    Arena &A = P.arena;
+    launch_sweep<V>(c, pval);
+    TSKB_CK(cudaEventRecord(P.ev[2], c.s));
+    const uint32_t nsites = P.site_hi - P.site_lo;
+    V *scratch = A.get<V>(P.total_alleles + 1);
+    TSKB_CK(cudaMemsetAsync(c.d_result, 0, (size_t) W * afs_size * sizeof(double), c.s));
+    if (nsites) {
+        k_site_afs<V><<<grid_for(nsites, 128), 128, 0, c.s>>>(P.site_lo, nsites, P.site_moff.p, P.site_aoff.p,
+            P.mut_src.p, P.mut_allele.p, P.mut_alt.p, pval, totals, scratch, c.sumP, P.num_samples,
+            P.site_pos.p, c.d_windows, W, afs_size, c.d_result);
+        TSKB_CK_LAUNCH();
+        c.launches++;
+    }
+    TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+    if (c.sp->options & TSKB_STAT_SPAN_NORMALISE) {
+        k_afs_span_normalise<<<grid_for((size_t) W * afs_size, TB), TB, 0, c.s>>>(c.d_windows, W, afs_size,
+            c.d_result);
+        TSKB_CK_LAUNCH();
+        c.launches++;
+    }
+    TSKB_CK(cudaEventRecord(P.ev[4], c.s));
+}
+
 template <int STAT, class V>
 void run_phases(CallCtx &c, V *pval, V totals) {
     if (c.sp->options & TSKB_STAT_NODE) {
@@ -1033,15 +1146,16 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     // All small per-call inputs travel in ONE host-to-device copy:
     //   [0] validation key (all ones)  [8] duplicate flag, sweep error flag  [16] completion counters
     //   [24] set offsets (K + 1, padded)  | result columns (M)  | window edges (W + 1)
+    const uint32_t Mc = sp.stat_id == STAT_AFS ? 0 : M;  // the spectrum has no per-column parameters
     const size_t off_bytes = ((size_t) (K + 1) * sizeof(uint32_t) + 7) & ~size_t(7);
-    const size_t o_off = 24, o_cols = o_off + off_bytes, o_win = o_cols + (size_t) M * sizeof(ColP);
+    const size_t o_off = 24, o_cols = o_off + off_bytes, o_win = o_cols + (size_t) Mc * sizeof(ColP);
     const size_t stage_bytes = o_win + (size_t) (W + 1) * sizeof(double);
     std::vector<unsigned long long> stage((stage_bytes + 7) / 8, 0);
     char *hs = reinterpret_cast<char *>(stage.data());
     stage[0] = ~0ull;
     memcpy(hs + o_off, h_off.data(), (K + 1) * sizeof(uint32_t));
     ColP *cols = reinterpret_cast<ColP *>(hs + o_cols);
-    for (uint32_t m = 0; m < M; m++) {
+    for (uint32_t m = 0; m < Mc; m++) {
         ColP &q = cols[m];
         int32_t t[4] = { (int32_t) (m < K ? m : 0), 0, 0, 0 };
         for (uint32_t a = 0; a < sp.tuple; a++) t[a] = sp.indexes[(size_t) m * sp.tuple + a];
@@ -1109,7 +1223,9 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         sumP.table_rows = (uint32_t) sp.table_rows;
     }
     // node mode: one row per node and window (trees.c:1788-1918)
-    const size_t result_size = (size_t) W * M * ((sp.options & TSKB_STAT_NODE) ? (size_t) P.N : 1);
+    const size_t result_size = sp.stat_id == STAT_AFS
+                                   ? (size_t) W * sp.afs_size
+                                   : (size_t) W * M * ((sp.options & TSKB_STAT_NODE) ? (size_t) P.N : 1);
     c.d_result = sp.result_on_device ? sp.result : A.get<double>(result_size);
     TSKB_CK(cudaEventRecord(P.ev[1], s));
 
@@ -1136,6 +1252,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         case STAT_Y3: run_phases<STAT_Y3, V>(c, pval, totals); break;
         case STAT_F3: run_phases<STAT_F3, V>(c, pval, totals); break;
         case STAT_F4: run_phases<STAT_F4, V>(c, pval, totals); break;
+        case STAT_AFS: run_afs_site<V>(c, pval, totals); break;
         case STAT_TABULATED:
             if constexpr (std::is_same<V, IVec<1>>::value) {
                 run_phases<STAT_TABULATED, V>(c, pval, totals);

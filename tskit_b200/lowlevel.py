@@ -318,6 +318,23 @@ class LLTreeSequence:
             _p(w), options, _p(result)))
         return result
 
+    # ---- TreeSequence_allele_frequency_spectrum (_tskitmodule.c:6977-7063)
+    def allele_frequency_spectrum(self, sample_set_sizes, sample_sets, windows, time_windows,
+                                  mode=None, span_normalise=True, polarised=False):
+        options = parse_stats_mode(mode)
+        if span_normalise:
+            options |= STAT_SPAN_NORMALISE
+        if polarised:
+            options |= STAT_POLARISED
+        sizes, sets = parse_sample_sets(sample_set_sizes, sample_sets)
+        w = parse_windows(windows)
+        tw = parse_windows(time_windows)
+        result = np.zeros([len(w) - 1, len(tw) - 1] + [int(x) + 1 for x in sizes])
+        _handle(_lib.lib().tskb_treeseq_allele_frequency_spectrum(
+            self._h, len(sizes), _p(sizes), _p(sets), len(w) - 1, _p(w), len(tw) - 1, _p(tw), options,
+            _p(result)))
+        return result
+
     # ---- TreeSequence_one_way_weighted_method (_tskitmodule.c:6747-6830)
     def _parse_weights(self, weights):
         W = np.array(weights, dtype=np.float64, copy=True, order="C")
