@@ -174,10 +174,10 @@ int tskb_treeseq_genetic_relatedness_weighted(const tskb_treeseq_t *self, uint64
     const double *weights, uint64_t num_index_tuples, const int32_t *index_tuples,
     uint64_t num_windows, const double *windows, double *result, uint32_t options);
 
-/* tsk_treeseq_allele_frequency_spectrum (c/tskit/trees.h:1112-1116; trees.c:3814-3928), site mode:
- * result [num_windows x prod(sample_set_sizes[k] + 1)], row-major over the sets; folded unless
- * TSK_STAT_POLARISED.  time_windows NULL or {0, inf}.  Branch mode and more than 7 sample sets return
- * TSKB_ERR_UNSUPPORTED. */
+/* tsk_treeseq_allele_frequency_spectrum (c/tskit/trees.h:1112-1116; trees.c:3814-3928), site and
+ * branch mode: result [num_windows x prod(sample_set_sizes[k] + 1)], row-major over the sets; folded
+ * unless TSK_STAT_POLARISED.  time_windows NULL or {0, inf}: other time windows in branch mode,
+ * negative node times in branch mode and more than 7 sample sets return TSKB_ERR_UNSUPPORTED. */
 int tskb_treeseq_allele_frequency_spectrum(const tskb_treeseq_t *self, uint64_t num_sample_sets,
     const uint64_t *sample_set_sizes, const int32_t *sample_sets, uint64_t num_windows,
     const double *windows, uint64_t num_time_windows, const double *time_windows, uint32_t options,

@@ -243,6 +243,92 @@ class Oracle:
             out /= (w[1:] - w[:-1]).reshape([W] + [1] * len(dims))
         return out
 
+    def branch_allele_frequency_spectrum(self, sample_sets, windows=None, span_normalise=True,
+                                         polarised=False):
+        """tsk_treeseq_branch_allele_frequency_spectrum + tsk_treeseq_update_branch_afs
+        (c/tskit/trees.c:3650-3812) restated step by step for the default time window [0, inf),
+        including the reference's bookkeeping of `last_update` (a node is credited from the last time
+        it was visited or flushed, which is earlier than the insertion of its edge when it was
+        parentless before).  Small inputs only.  Pinned against the reference package in
+        tests/test_dropin.py."""
+        t = self.t
+        w = self._windows(windows)
+        W = len(w) - 1
+        sets = [np.asarray(x, dtype=np.int64) for x in sample_sets]
+        K = len(sets)
+        dims = [len(x) + 1 for x in sets]
+        out = np.zeros([W] + dims)
+        N, n_all, L = t.num_nodes, t.num_samples, t.sequence_length
+        time = t.nodes_time
+        count = np.zeros((N, K + 1), dtype=np.int64)
+        for k, x in enumerate(sets):
+            count[x, k] = 1
+        count[t.samples, K] = 1
+        parent = np.full(N, -1, dtype=np.int64)
+        last_update = np.zeros(N)
+        el, er, ep, ec = t.edges_left, t.edges_right, t.edges_parent, t.edges_child
+        I, O = t.edge_insertion_order, t.edge_removal_order
+        E = t.num_edges
+
+        def fold(coord):
+            n = sum(d - 1 for d in dims) / 2
+            s = int(sum(coord))
+            k = len(dims)
+            while s == n and k > 0:
+                k -= 1
+                n -= (dims[k] - 1) / 2
+                s -= int(coord[k])
+            if s > n:
+                return tuple(dims[k] - 1 - int(coord[k]) for k in range(len(dims)))
+            return tuple(int(c) for c in coord)
+
+        def update(u, right, wi):
+            if parent[u] != -1:
+                t_u, t_v = time[u], time[parent[u]]
+                if 0 < count[u, K] < n_all and 0.0 < t_v:
+                    c = count[u, :K]
+                    c = tuple(int(v) for v in c) if polarised else fold(c)
+                    blen = max(0.0, min(np.inf, t_v) - max(0.0, t_u))
+                    out[(wi,) + c] += (right - last_update[u]) * blen
+            last_update[u] = right
+
+        tj = tk = 0
+        t_left = 0.0
+        wi = 0
+        while tj < E or t_left < L:
+            while tk < E and er[O[tk]] == t_left:
+                h = O[tk]
+                tk += 1
+                u, v = int(ec[h]), int(ep[h])
+                update(u, t_left, wi)
+                while v != -1:
+                    update(v, t_left, wi)
+                    count[v] -= count[u]
+                    v = int(parent[v])
+                parent[u] = -1
+            while tj < E and el[I[tj]] == t_left:
+                h = I[tj]
+                tj += 1
+                u, v = int(ec[h]), int(ep[h])
+                parent[u] = v
+                while v != -1:
+                    update(v, t_left, wi)
+                    count[v] += count[u]
+                    v = int(parent[v])
+            t_right = L
+            if tj < E:
+                t_right = min(t_right, el[I[tj]])
+            if tk < E:
+                t_right = min(t_right, er[O[tk]])
+            while wi < W and w[wi + 1] <= t_right:
+                for u in range(N):
+                    update(u, w[wi + 1], wi)
+                wi += 1
+            t_left = t_right
+        if span_normalise:
+            out /= (w[1:] - w[:-1]).reshape([W] + [1] * len(dims))
+        return out
+
     def trees_at(self, positions, tracked=None):
         pos = np.ascontiguousarray(positions, dtype=np.float64)
         order = np.argsort(pos, kind="stable")

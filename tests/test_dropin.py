@@ -201,6 +201,29 @@ def test_oracle_site_afs_pinned_to_reference(ts, wf_small):
                           ts.allele_frequency_spectrum([s], mode="site", polarised=True))
 
 
+def test_oracle_branch_afs_pinned_to_reference(ts, wf_small):
+    """The oracle's step-by-step restatement of the branch-mode AFS, `last_update` bookkeeping
+    included (several roots: nodes regain parents), against the reference package (CPU)."""
+    from oracle import port
+    from tests import fixtures as fx
+    o = port.Oracle(wf_small)
+    s = ts.samples()
+    sets = [s[:3], s[3:7]]
+    w = np.linspace(0, ts.sequence_length, 4)
+    for pol in (False, True):
+        for span in (True, False):
+            got = o.branch_allele_frequency_spectrum(sets, windows=w, polarised=pol, span_normalise=span)
+            want = ts.allele_frequency_spectrum(sets, windows=w, mode="branch", polarised=pol, span_normalise=span)
+            assert got.shape == want.shape
+            assert np.allclose(got, want, rtol=1e-12, atol=1e-12 * np.abs(want).max()), (pol, span)
+    t = fx.load("multiroot")
+    mts = dropin.from_tables(t)
+    ms = mts.samples()
+    got = port.Oracle(t).branch_allele_frequency_spectrum([ms[:2], ms[2:]], polarised=True, span_normalise=False)
+    want = mts.allele_frequency_spectrum([ms[:2], ms[2:]], mode="branch", polarised=True, span_normalise=False)
+    assert np.allclose(got[0], want, rtol=1e-12)
+
+
 @pytest.mark.gpu
 def test_site_afs_through_dropin(ts, wf_small):
     from oracle import port
@@ -216,8 +239,40 @@ def test_site_afs_through_dropin(ts, wf_small):
                 assert got.shape == want.shape and np.allclose(got, want, rtol=1e-12, atol=0), (len(sets), pol, span)
     got = acc.allele_frequency_spectrum([s[:4], s[4:9]], mode="site", polarised=True, span_normalise=False)
     assert np.array_equal(got, o.site_allele_frequency_spectrum([s[:4], s[4:9]], polarised=True, span_normalise=False)[0])
+    # branch mode, on an input with several roots (nodes regain parents: the reference credits them
+    # from their last update, trees.c:3650-3697)
+    for sets in ([s], [s[:50], s[50:]], [s[:3], s[3:10], s[20:22]]):
+        for pol in (False, True):
+            for span in (True, False):
+                for win in (w, None):
+                    got = acc.allele_frequency_spectrum(sets, windows=win, mode="branch", polarised=pol, span_normalise=span)
+                    want = ts.allele_frequency_spectrum(sets, windows=win, mode="branch", polarised=pol, span_normalise=span)
+                    assert got.shape == want.shape
+                    assert np.allclose(got, want, rtol=1e-9, atol=1e-12 * np.abs(want).max()), (len(sets), pol, span)
     assert acc.accel_stats["forwarded"] == 0
-    # branch mode: forwarded, visibly
-    b = acc.allele_frequency_spectrum([s[:50]], mode="branch")
-    assert np.allclose(b, ts.allele_frequency_spectrum([s[:50]], mode="branch"))
+    # time windows other than [0, inf): forwarded, visibly
+    tw = [0, 10.0, np.inf]
+    b = acc.allele_frequency_spectrum([s[:50]], mode="branch", time_windows=tw)
+    assert np.allclose(b, ts.allele_frequency_spectrum([s[:50]], mode="branch", time_windows=tw))
     assert acc.accel_stats["forwarded"] == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["multiroot", "paper", "internal_sample", "unary", "missing"])
+def test_branch_afs_fixtures(name):
+    from oracle import port
+    from tests import fixtures as fx
+    from tskit_b200.lowlevel import LLTreeSequence
+    t = fx.load(name)
+    ll, o = LLTreeSequence(t), port.Oracle(t)
+    s = t.samples
+    sets = [s[:2], s[2:]]
+    sizes = np.array([len(x) for x in sets], dtype=np.uint64)
+    flat = np.concatenate(sets).astype(np.int32)
+    L = t.sequence_length
+    for w in ([0, L], [0, L / 3, L]):
+        for pol in (False, True):
+            got = ll.allele_frequency_spectrum(sizes, flat, w, [0, np.inf], mode="branch", polarised=pol,
+                                               span_normalise=False)
+            want = o.branch_allele_frequency_spectrum(sets, windows=w, polarised=pol, span_normalise=False)
+            assert np.allclose(got[:, 0], want, rtol=1e-9, atol=1e-12), (name, pol)

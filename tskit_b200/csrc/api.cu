@@ -620,9 +620,16 @@ int tskb_treeseq_allele_frequency_spectrum(const tskb_treeseq_t *self, uint64_t 
         }
         int ret = check_sample_sets(P, num_sample_sets, sample_set_sizes, sample_sets);
         if (ret != 0) return ret;
-        // the branch-mode spectrum is not on the device yet; more than 7 sets need
-        // more than one sweep's state columns
-        if (branch || num_sample_sets + 1 > MAX_STATE_DIM) return TSKB_ERR_UNSUPPORTED;
+        if (branch && P.time_uncalibrated && !(options & TSKB_STAT_ALLOW_TIME_UNCALIBRATED)) {
+            return TSKB_ERR_TIME_UNCALIBRATED;  // trees.c:3727
+        }
+        // on the device: the default time window (with node times >= 0 the branch length inside it is
+        // the whole branch) and at most 7 sets (plus the all-samples column: one sweep's state)
+        const bool default_tw = time_windows == nullptr
+                                || (num_time_windows == 1 && time_windows[0] == 0.0 && std::isinf(time_windows[1]));
+        if ((branch && (!default_tw || P.has_negative_time)) || num_sample_sets + 1 > MAX_STATE_DIM) {
+            return TSKB_ERR_UNSUPPORTED;
+        }
         // state columns: the sets, then all samples (trees.c:3890-3910)
         std::vector<uint64_t> sizes(sample_set_sizes, sample_set_sizes + num_sample_sets);
         uint64_t total = 0, afs_size = 1;

@@ -31,7 +31,7 @@ uint64_t Plan::device_bytes() const {
     return time.bytes() + d_samples.bytes() + coff.bytes() + csr_left.bytes() + csr_right.bytes()
            + csr_parent.bytes() + ev_pos.bytes() + ev_child.bytes() + ev_sign.bytes()
            + voff.bytes() + q_off.bytes() + refs.bytes() + q_bp0.bytes() + q_bp1.bytes() + bp_pos.bytes()
-           + q_bl.bytes() + q_node.bytes() + node_first_bp.bytes() + tile_dep.bytes() + d_sample_index.bytes() + pm_off.bytes() + pm_left.bytes()
+           + q_bl.bytes() + q_eff.bytes() + q_node.bytes() + node_first_bp.bytes() + tile_dep.bytes() + d_sample_index.bytes() + pm_off.bytes() + pm_left.bytes()
            + pm_right.bytes() + pm_pmax.bytes() + pm_child.bytes() + rank_node.bytes() + level.bytes() + site_pos.bytes() + site_moff.bytes()
            + site_aoff.bytes() + mut_node.bytes() + mut_src.bytes() + mut_allele.bytes()
            + mut_alt.bytes();
@@ -290,6 +290,20 @@ __global__ void k_piece_fill(const uint32_t *sorted_e, const uint32_t *sorted_ke
     piece_rank[p] = r;
 }
 
+// Does the reference "update" the node at this breakpoint (a visit in some walk, or the removal of
+// its own edge) or is the node only the child of an inserted edge?  The branch-mode allele
+// frequency spectrum credits a node from its last update (tsk_treeseq_update_branch_afs,
+// trees.c:3650-3697: `last_update` is not refreshed for the child of an insertion).
+__global__ void k_piece_updates(const uint32_t *sorted_e, const uint32_t *sorted_key,
+    const uint32_t *em_ev, const uint32_t *endscan, const uint32_t *voff, const int8_t *ev_sign,
+    uint32_t Ve, uint8_t *piece_upd) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Ve) return;
+    uint32_t e = sorted_e[k], r = sorted_key[k], i = em_ev[e];
+    const bool child = e == voff[i] + i;
+    if (!child || ev_sign[i] < 0) piece_upd[endscan[k] + r + 1] = 1;
+}
+
 __global__ void k_piece_init(const uint32_t *noff, const uint32_t *endscan, uint32_t Ve,
     uint32_t ends_total, uint32_t N, double *pc_x, double *pc_bl, uint32_t *piece_rank,
     uint32_t *poff) {
@@ -429,7 +443,8 @@ __global__ void k_needed_mutation(uint32_t Mu, const int32_t *mut_src, const dou
 __global__ void k_order_fill(const uint32_t *sorted_piece, const uint32_t *sorted_h, uint32_t nreal,
     const uint32_t *lvl_sorted_begin, const uint32_t *lvl_padded_begin, const uint32_t *cnt,
     const double *pc_x, const double *pc_bl, uint32_t P, const double *bp_pos, uint32_t T,
-    uint32_t *q_bp0, uint32_t *q_bp1, double *q_bl, uint32_t *q_cnt, uint32_t *perm) {
+    const uint8_t *piece_upd, uint32_t *q_bp0, uint32_t *q_bp1, uint32_t *q_eff, double *q_bl,
+    uint32_t *q_cnt, uint32_t *perm) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nreal) return;
     uint32_t h = sorted_h[i], p = sorted_piece[i];
@@ -441,6 +456,12 @@ __global__ void k_order_fill(const uint32_t *sorted_piece, const uint32_t *sorte
     q_bp1[j] = (p + 1 < P && pc_x[p + 1] >= 0.0) ? lower_bound_dev(bp_pos, T, pc_x[p + 1]) : T;
     q_bl[j] = pc_bl[p];
     q_cnt[j] = cnt[p];
+    // where the reference's last_update of the node stands when this piece begins: the piece's own
+    // breakpoint if the node is updated there, else the start of the node's previous piece
+    // (necessarily an update: the node was parentless), else the start of the range
+    uint32_t eff = q_bp0[j];
+    if (!piece_upd[p]) eff = pc_x[p - 1] >= 0.0 ? lower_bound_dev(bp_pos, T, pc_x[p - 1]) : 0xffffffffu;
+    q_eff[j] = eff;
 }
 
 __global__ void k_bp_pos(const double *ev_pos, const uint32_t *ev_bp, uint32_t nev, uint32_t T,
@@ -602,6 +623,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     P.num_samples = (uint32_t) P.samples.size();
     P.d_samples.upload(P.samples.data(), P.samples.size(), s);
     P.time.upload(t->node_time, N, s);
+    for (uint32_t u = 0; u < N; u++) P.has_negative_time |= t->node_time[u] < 0.0;
 
     Temp tmp;
     DevArray<double> el, er;
@@ -887,6 +909,14 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
             pc_bl.p, piece_rank.p);
         TSKB_CK_LAUNCH();
     }
+    DevArray<uint8_t> piece_upd;
+    piece_upd.alloc((size_t) P.P + 1);
+    TSKB_CK(cudaMemsetAsync(piece_upd.p, 0, (size_t) P.P + 1, s));
+    if (Ve) {
+        k_piece_updates<<<grid_for(Ve, TB), TB, 0, s>>>(sorted_e.p, sorted_key.p, em_ev.p, endscan.p,
+            P.voff.p, P.ev_sign.p, Ve, piece_upd.p);
+        TSKB_CK_LAUNCH();
+    }
     k_piece_init<<<grid_for(N + 1, TB), TB, 0, s>>>(noff.p, endscan.p, Ve, ends_total, N, pc_x.p,
         pc_bl.p, piece_rank.p, poff.p);
     TSKB_CK_LAUNCH();
@@ -1061,7 +1091,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         DevArray<uint32_t> d_padded, q_cnt;
         d_padded.upload(h_padded.data(), h_padded.size(), s);
         P.d_sample_index.upload(P.sample_index_map.data(), N, s);
-        P.q_bp0.alloc(P.npp); P.q_bp1.alloc(P.npp); P.q_bl.alloc(P.npp);
+        P.q_bp0.alloc(P.npp); P.q_bp1.alloc(P.npp); P.q_bl.alloc(P.npp); P.q_eff.alloc(P.npp);
         P.q_off.alloc((size_t) P.npp + 1); q_cnt.alloc((size_t) P.npp + 1);
         perm.alloc((size_t) Pn + 1);
         // default: the zero slot (pieces that are not computed are never referenced)
@@ -1078,8 +1108,8 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         }
         if (nreal) {
             k_order_fill<<<grid_for(nreal, TB), TB, 0, s>>>(vout.p, kout.p, nreal, lvl_begin.p,
-                d_padded.p, cnt.p, pc_x.p, pc_bl.p, Pn, P.bp_pos.p, P.T, P.q_bp0.p, P.q_bp1.p,
-                P.q_bl.p, q_cnt.p, perm.p);
+                d_padded.p, cnt.p, pc_x.p, pc_bl.p, Pn, P.bp_pos.p, P.T, piece_upd.p, P.q_bp0.p, P.q_bp1.p,
+                P.q_eff.p, P.q_bl.p, q_cnt.p, perm.p);
             TSKB_CK_LAUNCH();
         }
         if (N) {

@@ -97,6 +97,9 @@ struct Plan {
     DevArray<uint32_t> q_bp1;         // [npp] breakpoint it ends at: the node's next piece, or T
                                       //       (= range_right); NO_PIECE marks padding
     DevArray<double> bp_pos;          // [T + 1] distinct diff positions, then range_right
+    DevArray<uint32_t> q_eff;         // [npp] breakpoint of the node's last update before the piece (branch AFS;
+                                      //       0xffffffff: start of the range)
+    bool has_negative_time = false;
     DevArray<double> q_bl;            // [npp] branch length above the node over the piece
     DevArray<uint32_t> q_off;         // [npp + 1] offsets into refs
     DevArray<uint32_t> refs;          // [nrefs] state slots whose values add up to the piece's state

@@ -782,6 +782,48 @@ __global__ void k_site_afs(uint32_t site_lo, uint32_t nsites, const uint32_t *si
     for (uint32_t al = P.polarised ? 1 : 0; al < na; al++) afs_add<V>(scratch[a0 + al], K, P, num_samples, inc, afs);
 }
 
+// Branch mode (tsk_treeseq_branch_allele_frequency_spectrum, trees.c:3699-3812, default time
+// window): every node with a parent adds (branch length) x (span) at the vector of per-set sample
+// counts below it.  The span of a piece runs from the node's last update -- q_eff, never before
+// the left edge of the window holding the piece's start, because every window end flushes all
+// nodes -- to the piece's end, split over the windows it crosses.
+template <class V>
+__global__ void k_branch_afs(uint32_t npp, const uint32_t *__restrict__ q_bp0,
+    const uint32_t *__restrict__ q_bp1, const uint32_t *__restrict__ q_eff,
+    const double *__restrict__ q_bl, const double *__restrict__ bp_pos, const V *__restrict__ pval, SumP P,
+    uint32_t num_samples, double range_left, const double *__restrict__ windows, uint32_t W,
+    size_t afs_size, double *result) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npp) return;
+    const uint32_t b1 = q_bp1[j];
+    const double bl = q_bl[j];
+    if (b1 == NO_PIECE || bl == 0.0) return;
+    const V cnt = pval[j];
+    const int K = P.K - 1;
+    uint32_t coord[8], dims[8], total = 0;
+#pragma unroll
+    for (int k = 0; k < V::N; k++) {
+        coord[k] = k < K ? (uint32_t) cnt.v[k] : 0;
+        dims[k] = k < K ? (uint32_t) P.n[k] + 1 : 1;
+        if (k == K) total = (uint32_t) cnt.v[k];
+    }
+    if (!(total > 0 && total < num_samples)) return;
+    if (!P.polarised) afs_fold<8>(coord, dims, K);
+    size_t index = 0;
+    for (int k = 0; k < K; k++) index = index * dims[k] + coord[k];
+    const double x = bp_pos[q_bp0[j]], xe = bp_pos[b1];
+    const uint32_t e = q_eff[j];
+    double start = e == NO_PIECE ? range_left : bp_pos[e];
+    uint32_t w = upper_bound_dev(windows, W + 1, x);
+    w = w > 0 ? w - 1 : 0;
+    if (start < windows[w]) start = windows[w];
+    for (; w < W && windows[w] < xe; w++) {
+        const double wl = windows[w], wr = windows[w + 1];
+        const double len = (xe < wr ? xe : wr) - (start > wl ? start : wl);
+        if (len > 0.0) atomicAdd(result + (size_t) w * afs_size + index, len * bl);
+    }
+}
+
 __global__ void k_afs_span_normalise(const double *windows, uint32_t W, size_t afs_size, double *result) {
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t) W * afs_size) return;
@@ -1087,6 +1129,30 @@ void run_afs_site(CallCtx &c, V *pval, V totals) {
     TSKB_CK(cudaEventRecord(P.ev[4], c.s));
 }
 
+template <class V>
+void run_afs_branch(CallCtx &c, V *pval) {
+    const Plan &P = *c.P;
+    const uint32_t W = c.sp->W;
+    const size_t afs_size = c.sp->afs_size;
+    launch_sweep<V>(c, pval);
+    TSKB_CK(cudaEventRecord(P.ev[2], c.s));
+    TSKB_CK(cudaMemsetAsync(c.d_result, 0, (size_t) W * afs_size * sizeof(double), c.s));
+    if (P.npp) {
+        k_branch_afs<V><<<grid_for(P.npp, TB), TB, 0, c.s>>>(P.npp, P.q_bp0.p, P.q_bp1.p, P.q_eff.p, P.q_bl.p,
+            P.bp_pos.p, pval, c.sumP, P.num_samples, P.range_left, c.d_windows, W, afs_size, c.d_result);
+        TSKB_CK_LAUNCH();
+        c.launches++;
+    }
+    TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+    if (c.sp->options & TSKB_STAT_SPAN_NORMALISE) {
+        k_afs_span_normalise<<<grid_for((size_t) W * afs_size, TB), TB, 0, c.s>>>(c.d_windows, W, afs_size,
+            c.d_result);
+        TSKB_CK_LAUNCH();
+        c.launches++;
+    }
+    TSKB_CK(cudaEventRecord(P.ev[4], c.s));
+}
+
 template <int STAT, class V>
 void run_phases(CallCtx &c, V *pval, V totals) {
     if (c.sp->options & TSKB_STAT_NODE) {
@@ -1252,7 +1318,13 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         case STAT_Y3: run_phases<STAT_Y3, V>(c, pval, totals); break;
         case STAT_F3: run_phases<STAT_F3, V>(c, pval, totals); break;
         case STAT_F4: run_phases<STAT_F4, V>(c, pval, totals); break;
-        case STAT_AFS: run_afs_site<V>(c, pval, totals); break;
+        case STAT_AFS:
+            if (sp.options & TSKB_STAT_BRANCH) {
+                run_afs_branch<V>(c, pval);
+            } else {
+                run_afs_site<V>(c, pval, totals);
+            }
+            break;
         case STAT_TABULATED:
             if constexpr (std::is_same<V, IVec<1>>::value) {
                 run_phases<STAT_TABULATED, V>(c, pval, totals);
