@@ -174,6 +174,17 @@ int tskb_treeseq_genetic_relatedness_weighted(const tskb_treeseq_t *self, uint64
     const double *weights, uint64_t num_index_tuples, const int32_t *index_tuples,
     uint64_t num_windows, const double *windows, double *result, uint32_t options);
 
+/* tsk_treeseq_genetic_relatedness_vector (c/tskit/trees.h:1091-1094; trees.c:10772-10816): the
+ * product of the branch-mode genetic relatedness matrix with `weights` (row-major
+ * [num_samples x num_weights]) without forming the matrix; result
+ * [num_windows x num_focal_nodes x num_weights].  Branch mode only (TSK_STAT_SITE / _NODE:
+ * TSKB_ERR_UNSUPPORTED_STAT_MODE, as the reference); `windows` need not span the sequence.
+ * Focal nodes that are not samples need an engine built with TSKB_INIT_NODE_MODE
+ * (TSKB_ERR_UNSUPPORTED otherwise).  fp64 atomics: equal to the reference within rounding. */
+int tskb_treeseq_genetic_relatedness_vector(const tskb_treeseq_t *self, uint64_t num_weights,
+    const double *weights, uint64_t num_windows, const double *windows, uint64_t num_focal_nodes,
+    const int32_t *focal_nodes, double *result, uint32_t options);
+
 /* tsk_treeseq_allele_frequency_spectrum (c/tskit/trees.h:1112-1116; trees.c:3814-3928), site and
  * branch mode: result [num_windows x prod(sample_set_sizes[k] + 1)], row-major over the sets; folded
  * unless TSK_STAT_POLARISED.  time_windows NULL or {0, inf}: other time windows in branch mode,

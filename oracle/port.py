@@ -243,6 +243,112 @@ class Oracle:
             out /= (w[1:] - w[:-1]).reshape([W] + [1] * len(dims))
         return out
 
+    def genetic_relatedness_vector(self, W, windows=None, nodes=None, centre=True, span_normalise=True):
+        """tsk_treeseq_genetic_relatedness_vector (c/tskit/trees.c:10445-10816) restated step by step:
+        the matvec calculator's per-node vectors w (summed weights below), v (accumulated
+        branch area x w, handed down on edge removal) and x (position of the last update), the edge
+        diffs between windows[0] and windows[-1], and the output pass over the focal nodes' ancestors.
+        Small inputs only.  Pinned against the reference package in tests/test_dropin.py."""
+        t = self.t
+        win = self._windows(windows)
+        nw = len(win) - 1
+        W = np.asarray(W, dtype=np.float64)
+        if W.ndim == 1:
+            W = W.reshape(-1, 1)
+        samples = t.samples
+        n, K = len(samples), W.shape[1]
+        focal = samples if nodes is None else np.asarray(nodes, dtype=np.int64)
+        N, E = t.num_nodes, t.num_edges
+        time = t.nodes_time
+        el, er, ep, ec = t.edges_left, t.edges_right, t.edges_parent, t.edges_child
+        I, O = t.edge_insertion_order, t.edge_removal_order
+        parent = np.full(N, -1, dtype=np.int64)
+        x = np.zeros(N)
+        v = np.zeros((N, K))
+        w = np.zeros((N, K))
+        means = np.zeros(K)
+        if centre:  # trees.c:10512-10523
+            for j in range(n):
+                means += W[j]
+            means /= n
+        for j in range(n):
+            w[samples[j]] = W[j] - means
+        result = np.zeros((nw, len(focal), K))
+        state = {"pos": win[0]}
+
+        def add_z(u):  # trees.c:10552-10571
+            p = parent[u]
+            if p != -1:
+                v[u] += (time[p] - time[u]) * (state["pos"] - x[u]) * w[u]
+            x[u] = state["pos"]
+
+        def adjust_path_up(p, c, sign):  # trees.c:10573-10608
+            while p != -1:
+                add_z(p)
+                v[c] -= sign * v[p]
+                w[p] += sign * w[c]
+                p = parent[p]
+
+        def remove_edge(p, c):  # trees.c:10610-10625
+            add_z(c)
+            parent[c] = -1
+            adjust_path_up(p, c, -1)
+
+        def insert_edge(p, c):  # trees.c:10627-10635
+            adjust_path_up(p, c, +1)
+            x[c] = state["pos"]
+            parent[c] = p
+
+        def write_output(m):  # trees.c:10637-10699
+            for j, u in enumerate(focal):
+                u = int(u)
+                while u != -1:
+                    if x[u] != state["pos"]:
+                        add_z(u)
+                    result[m, j] += v[u]
+                    u = parent[u]
+            if centre:
+                om = np.zeros(K)
+                for j in range(len(focal)):
+                    om += result[m, j]
+                om /= len(focal)
+                result[m] -= om
+            v[:] = 0
+
+        # the tree holding windows[0]: every edge with left <= windows[0] < right (trees.c:10733-10741)
+        j = 0
+        while j < E and el[I[j]] <= win[0]:
+            e = I[j]
+            if win[0] < er[e]:
+                insert_edge(int(ep[e]), int(ec[e]))
+            j += 1
+        k = 0
+        while k < E and er[O[k]] <= win[0]:
+            k += 1
+        m = 0
+        while m < nw:  # trees.c:10746-10782
+            pos = state["pos"]
+            while k < E and er[O[k]] == pos:
+                e = O[k]
+                remove_edge(int(ep[e]), int(ec[e]))
+                k += 1
+            while j < E and el[I[j]] == pos:
+                e = I[j]
+                insert_edge(int(ep[e]), int(ec[e]))
+                j += 1
+            nxt = win[m + 1]
+            if j < E:
+                nxt = min(nxt, el[I[j]])
+            if k < E:
+                nxt = min(nxt, er[O[k]])
+            state["pos"] = nxt
+            if nxt == win[m + 1]:
+                write_output(m)
+                m += 1
+        if span_normalise:
+            result /= (win[1:] - win[:-1]).reshape(nw, 1, 1)
+        return result
+
     def branch_allele_frequency_spectrum(self, sample_sets, windows=None, span_normalise=True,
                                          polarised=False):
         """tsk_treeseq_branch_allele_frequency_spectrum + tsk_treeseq_update_branch_afs

@@ -276,3 +276,120 @@ def test_branch_afs_fixtures(name):
                                                span_normalise=False)
             want = o.branch_allele_frequency_spectrum(sets, windows=w, polarised=pol, span_normalise=False)
             assert np.allclose(got[:, 0], want, rtol=1e-9, atol=1e-12), (name, pol)
+
+
+def _relvec_cases(ts):
+    rng = np.random.default_rng(11)
+    n, L = ts.num_samples, ts.sequence_length
+    return rng, n, L, ([0, L], np.linspace(0, L, 5), [L / 7, L / 3, 0.9 * L])
+
+
+def test_oracle_relatedness_vector_pinned_to_reference(ts, wf_small):
+    """The oracle's step-by-step restatement of the matvec calculator (trees.c:10445-10816) against the
+    reference package: centred and not, windows that do not span the sequence, focal nodes that are
+    not samples, several roots (CPU)."""
+    from oracle import port
+    from tests import fixtures as fx
+    o = port.Oracle(wf_small)
+    rng, n, L, wins = _relvec_cases(ts)
+    for K in (1, 3):
+        W = rng.normal(size=(n, K))
+        for w in wins:
+            for centre in (True, False):
+                for span in (True, False):
+                    got = o.genetic_relatedness_vector(W, windows=w, centre=centre, span_normalise=span)
+                    want = ts.genetic_relatedness_vector(W, windows=w, mode="branch", centre=centre,
+                                                         span_normalise=span)
+                    assert got.shape == want.shape
+                    assert np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max()), (K, centre, span)
+    nodes = np.array([0, 5, ts.num_nodes - 1, ts.num_nodes // 2, 5], dtype=np.int32)
+    W = rng.normal(size=(n, 2))
+    got = o.genetic_relatedness_vector(W, windows=wins[2], nodes=nodes, centre=False)
+    want = ts.genetic_relatedness_vector(W, windows=wins[2], mode="branch", centre=False, nodes=nodes)
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+    for name in ("multiroot", "internal_sample", "unary"):
+        t = fx.load(name)
+        mts = dropin.from_tables(t)
+        W = rng.normal(size=(mts.num_samples, 2))
+        for centre in (True, False):
+            got = port.Oracle(t).genetic_relatedness_vector(W, centre=centre)
+            want = mts.genetic_relatedness_vector(W, mode="branch", centre=centre)
+            assert np.allclose(got[0], want, rtol=1e-9, atol=1e-12), (name, centre)
+
+
+@pytest.mark.gpu
+def test_relatedness_vector_through_dropin(ts, wf_small):
+    """GRM x vector on the device (transposed sweep) == the reference package through the unchanged
+    public API, == the oracle; more weight columns than one sweep holds; focal nodes that are not
+    samples (node-of-piece engine); the reference's errors."""
+    from oracle import port
+    acc = dropin.accelerate(ts)
+    o = port.Oracle(wf_small)
+    rng, n, L, wins = _relvec_cases(ts)
+    for K in (1, 3, 11):
+        W = rng.normal(size=(n, K))
+        for w in wins:
+            for centre in (True, False):
+                for span in (True, False):
+                    got = acc.genetic_relatedness_vector(W, windows=w, mode="branch", centre=centre,
+                                                         span_normalise=span)
+                    want = ts.genetic_relatedness_vector(W, windows=w, mode="branch", centre=centre,
+                                                         span_normalise=span)
+                    assert got.shape == want.shape
+                    assert np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max()), (K, centre, span)
+    W = rng.normal(size=(n, 2))
+    got = acc.genetic_relatedness_vector(W, windows=wins[1], mode="branch", centre=False)
+    want = o.genetic_relatedness_vector(W, windows=wins[1], centre=False)
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+    # windows=None drops the window axis; a 1-d weight vector is one column
+    got = acc.genetic_relatedness_vector(W[:, 0], mode="branch")
+    assert got.shape == (n, 1) and np.allclose(got, ts.genetic_relatedness_vector(W[:, 0], mode="branch"), rtol=1e-9,
+                                               atol=1e-9 * np.abs(got).max())
+    # focal nodes: samples in any order with repeats; then internal nodes
+    s = ts.samples()
+    for nodes in (s[::-3], np.array([s[4], s[4], s[0]]), np.array([0, 5, ts.num_nodes - 1, ts.num_nodes // 2, 5])):
+        got = acc.genetic_relatedness_vector(W, windows=wins[2], mode="branch", centre=False, nodes=nodes)
+        want = ts.genetic_relatedness_vector(W, windows=wins[2], mode="branch", centre=False, nodes=nodes)
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+    assert acc.accel_stats["forwarded"] == 0
+    # the matrix-free product agrees with the dense branch GRM of the engine
+    G = acc.genetic_relatedness_matrix(mode="branch")
+    v = rng.normal(size=n)
+    assert np.allclose(acc.genetic_relatedness_vector(v, mode="branch")[:, 0], G @ v, rtol=1e-8,
+                       atol=1e-9 * np.abs(G @ v).max())
+    # errors, as the reference: site and node mode are refused, bad windows, bad nodes
+    for bad in ("site", "node"):
+        with pytest.raises(tskit.LibraryError) as e1:
+            ts.genetic_relatedness_vector(W, mode=bad)
+        with pytest.raises(tskit.LibraryError) as e2:
+            acc.genetic_relatedness_vector(W, mode=bad)
+        assert str(e1.value) == str(e2.value)
+    for kw in (dict(windows=[0, L + 1]), dict(windows=[0, L / 2, L / 2, L]),
+               dict(nodes=[ts.num_nodes], centre=False), dict(nodes=[-1], centre=False)):
+        with pytest.raises(tskit.LibraryError) as e1:
+            ts.genetic_relatedness_vector(W, mode="branch", **kw)
+        with pytest.raises(tskit.LibraryError) as e2:
+            acc.genetic_relatedness_vector(W, mode="branch", **kw)
+        assert str(e1.value) == str(e2.value), kw
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["multiroot", "paper", "internal_sample", "unary", "missing"])
+def test_relatedness_vector_fixtures(name):
+    from oracle import port
+    from tests import fixtures as fx
+    from tskit_b200.lowlevel import LLTreeSequence
+    t = fx.load(name)
+    ll, o = LLTreeSequence(t), port.Oracle(t)
+    rng = np.random.default_rng(5)
+    W = rng.normal(size=(t.num_samples, 2))
+    L = t.sequence_length
+    for w in ([0, L], [0, L / 3, L], [L / 4, L / 2]):
+        for centre in (True, False):
+            got = ll.genetic_relatedness_vector(W, w, mode="branch", centre=centre, nodes=t.samples)
+            want = o.genetic_relatedness_vector(W, windows=w, centre=centre)
+            assert np.allclose(got, want, rtol=1e-9, atol=1e-12), (name, centre)
+        nodes = np.arange(t.num_nodes, dtype=np.int32)[::-1]
+        got = ll.genetic_relatedness_vector(W, w, mode="branch", centre=False, nodes=nodes)
+        want = o.genetic_relatedness_vector(W, windows=w, centre=False, nodes=nodes)
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-12), name

@@ -1,0 +1,49 @@
+"""Timing of genetic_relatedness_vector (GRM x vector, branch mode) on the cached C2 ARG: the C-ABI call
+with host buffers on one B200 (best of 3), and the reference package's own call on the same tables on
+one host core, with the largest relative difference between the two results."""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+import bench
+from tskit_b200.lowlevel import LLTreeSequence
+
+
+def timed(fn, reps=3):
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter(); r = fn(); dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return r, best * 1e3
+
+
+t, W, _ = bench.load_workload("c2")
+ll = LLTreeSequence(t)
+L, s = t.sequence_length, t.samples
+n = len(s)
+rng = np.random.default_rng(1)
+out = {"num_samples": n, "num_edges": int(t.num_edges)}
+res = {}
+for K in (1, 8):
+    Wt = rng.normal(size=(n, K))
+    for nw in (1, 10):
+        w = np.linspace(0, L, nw + 1)
+        r, ms = timed(lambda: ll.genetic_relatedness_vector(Wt, w, mode="branch", centre=True, nodes=s))
+        out[f"relvec_{K}cols_{nw}windows_ms"] = ms
+        res[(K, nw)] = (Wt, w, r)
+        st = ll.engine_stats()
+        out[f"relvec_{K}cols_{nw}windows_launches"] = int(st["last_launches"])
+        out[f"relvec_{K}cols_{nw}windows_device_ms"] = float(st["last_call_ms"])
+try:
+    from tskit_b200 import dropin
+    ts = dropin.from_tables(t)
+    for key in ((1, 1), (8, 1)):
+        Wt, w, got = res[key]
+        t0 = time.perf_counter()
+        want = ts.genetic_relatedness_vector(Wt, windows=w, mode="branch", centre=True)
+        out[f"reference_{key[0]}cols_{key[1]}windows_ms"] = (time.perf_counter() - t0) * 1e3
+        out[f"max_rel_diff_{key[0]}cols"] = float(np.abs(got - want).max() / np.abs(want).max())
+except Exception as e:  # the reference package did not travel
+    out["reference"] = f"unavailable: {e!r}"
+print(json.dumps(out))

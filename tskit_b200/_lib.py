@@ -63,7 +63,7 @@ SYMBOLS = [
     "tskb_treeseq_genetic_relatedness", "tskb_treeseq_Y3", "tskb_treeseq_f3",
     "tskb_treeseq_f4", "tskb_treeseq_sample_count_stat_tabulated",
     "tskb_treeseq_trait_covariance", "tskb_treeseq_trait_correlation",
-    "tskb_treeseq_genetic_relatedness_weighted", "tskb_treeseq_trait_linear_model",
+    "tskb_treeseq_genetic_relatedness_weighted", "tskb_treeseq_genetic_relatedness_vector", "tskb_treeseq_trait_linear_model",
     "tskb_treeseq_allele_frequency_spectrum",
     "tskb_treeseq_divergence_matrix", "tskb_treeseq_genotype_matrix",
     "tskb_treeseq_trees_at", "tskb_treeseq_get_stats", "tskb_treeseq_stat_device",
@@ -107,6 +107,8 @@ def lib():
         L.tskb_treeseq_trait_linear_model.argtypes = [C.c_void_p, u64, C.c_void_p, u64, C.c_void_p, u64,
                                                       C.c_void_p, C.c_uint32, C.c_void_p]
         L.tskb_treeseq_genetic_relatedness_weighted.argtypes = [
+            C.c_void_p, u64, C.c_void_p, u64, C.c_void_p, u64, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.tskb_treeseq_genetic_relatedness_vector.argtypes = [
             C.c_void_p, u64, C.c_void_p, u64, C.c_void_p, u64, C.c_void_p, C.c_void_p, C.c_uint32]
         L.tskb_treeseq_genotype_matrix.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_uint32,
                                                    C.c_void_p]

@@ -586,6 +586,89 @@ int tskb_treeseq_genetic_relatedness_weighted(const tskb_treeseq_t *self, uint64
         options, result);
 }
 
+/* tsk_treeseq_genetic_relatedness_vector (trees.c:10772-10816): branch mode only; checks in the
+ * reference's order (mode -> windows, which need not span the sequence -> focal nodes).  Weights are
+ * centred before and the output rows after the device pass exactly as tsk_matvec_calculator_init /
+ * _write_output do (trees.c:10512-10535, 10692-10713); span normalisation as trees.c:1920-1934. */
+int tskb_treeseq_genetic_relatedness_vector(const tskb_treeseq_t *self, uint64_t num_weights,
+    const double *weights, uint64_t num_windows, const double *windows, uint64_t num_focal_nodes,
+    const int32_t *focal_nodes, double *result, uint32_t options) {
+    if (self == nullptr || self->plan == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    const Plan &P = *self->plan;
+    return guarded([&]() -> int {
+        if (options & (TSKB_STAT_SITE | TSKB_STAT_NODE)) return TSKB_ERR_UNSUPPORTED_STAT_MODE;
+        if (windows == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+        int ret = check_windows(P, num_windows, windows, false);
+        if (ret != 0) return ret;
+        const uint64_t n = P.num_samples, K = num_weights, nf = num_focal_nodes;
+        bool needs_nodes = false;
+        for (uint64_t j = 0; j < nf; j++) {
+            if (focal_nodes[j] < 0 || (uint64_t) focal_nodes[j] >= P.N) return TSKB_ERR_NODE_OUT_OF_BOUNDS;
+            needs_nodes |= P.sample_index_map[focal_nodes[j]] < 0;
+        }
+        if (needs_nodes && !P.all_pieces) return TSKB_ERR_UNSUPPORTED;  // needs TSKB_INIT_NODE_MODE
+        const uint64_t row = nf * K;
+        if ((double) num_windows * (double) row > 2e9 || row > 0xffffffffull) return TSKB_ERR_UNSUPPORTED;
+        for (uint64_t i = 0; i < num_windows * row; i++) result[i] = 0.0;
+        if (row == 0) return 0;
+        std::vector<double> means(K, 0.0);
+        if (!(options & TSKB_STAT_NONCENTRED)) {
+            for (uint64_t j = 0; j < n; j++) {
+                for (uint64_t k = 0; k < K; k++) means[k] += weights[j * K + k];
+            }
+            for (uint64_t k = 0; k < K; k++) means[k] /= (double) n;
+        }
+        // state columns in batches of one sweep's width
+        for (uint64_t k0 = 0; k0 < K; k0 += MAX_STATE_DIM) {
+            const uint64_t kb = K - k0 < MAX_STATE_DIM ? K - k0 : MAX_STATE_DIM;
+            std::vector<double> Wb(n * kb), out(num_windows * nf * kb), totals(kb, 0.0);
+            for (uint64_t j = 0; j < n; j++) {
+                for (uint64_t k = 0; k < kb; k++) Wb[j * kb + k] = weights[j * K + k0 + k] - means[k0 + k];
+            }
+            StatSpec sp = {};
+            sp.stat_id = STAT_REL_VECTOR;
+            sp.K = (uint32_t) kb;
+            sp.M = (uint32_t) (nf * kb);
+            sp.W = (uint32_t) num_windows;
+            sp.windows = windows;
+            sp.options = TSKB_STAT_BRANCH;
+            sp.result = out.data();
+            sp.weights = Wb.data();
+            sp.column_totals = totals.data();
+            sp.focal = focal_nodes;
+            sp.num_focal = nf;
+            sp.focal_needs_nodes = needs_nodes;
+            ret = run_weighted_stat(&P, sp);
+            if (ret != 0) return ret;
+            for (uint64_t w = 0; w < num_windows; w++) {
+                for (uint64_t j = 0; j < nf; j++) {
+                    for (uint64_t k = 0; k < kb; k++) {
+                        result[(w * nf + j) * K + k0 + k] = out[(w * nf + j) * kb + k];
+                    }
+                }
+            }
+        }
+        for (uint64_t w = 0; w < num_windows; w++) {
+            double *y = result + w * row;
+            if (!(options & TSKB_STAT_NONCENTRED)) {
+                std::vector<double> out_means(K, 0.0);
+                for (uint64_t j = 0; j < nf; j++) {
+                    for (uint64_t k = 0; k < K; k++) out_means[k] += y[j * K + k];
+                }
+                for (uint64_t k = 0; k < K; k++) out_means[k] /= (double) nf;
+                for (uint64_t j = 0; j < nf; j++) {
+                    for (uint64_t k = 0; k < K; k++) y[j * K + k] -= out_means[k];
+                }
+            }
+            if (options & TSKB_STAT_SPAN_NORMALISE) {
+                const double span = windows[w + 1] - windows[w];
+                for (uint64_t i = 0; i < row; i++) y[i] /= span;
+            }
+        }
+        return 0;
+    });
+}
+
 /* tsk_treeseq_allele_frequency_spectrum (trees.c:3814-3928), site mode; checks in its order */
 int tskb_treeseq_allele_frequency_spectrum(const tskb_treeseq_t *self, uint64_t num_sample_sets,
     const uint64_t *sample_set_sizes, const int32_t *sample_sets, uint64_t num_windows, const double *windows,

@@ -168,6 +168,11 @@ struct StatSpec {
     uint64_t table_rows = 0;
     // STAT_AFS: size of one window's spectrum = product of (set size + 1); result is [W x afs_size]
     uint64_t afs_size = 0;
+    // STAT_REL_VECTOR: focal nodes (host); M = num_focal * K; focal_needs_nodes: some focal node is
+    // not a sample (needs the node of every piece: a node-mode plan)
+    const int32_t *focal = nullptr;
+    uint64_t num_focal = 0;
+    bool focal_needs_nodes = false;
 };
 
 enum StatId {
@@ -178,7 +183,9 @@ enum StatId {
     STAT_TRAIT_COV = 12, STAT_TRAIT_CORR = 13, STAT_REL_WEIGHTED = 14, STAT_REL_WEIGHTED_NC = 15,
     STAT_TRAIT_LM = 16,
     // joint allele frequency spectrum, site mode (trees.c:3497-3648): K sets + the all-samples column
-    STAT_AFS = 17
+    STAT_AFS = 17,
+    // GRM x vector, branch mode (trees.c:10445-10816): fp64 states, result [W x num_focal x K]
+    STAT_REL_VECTOR = 18
 };
 
 int run_sample_count_stat(const Plan *plan, const StatSpec &spec);

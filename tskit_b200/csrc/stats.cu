@@ -831,6 +831,79 @@ __global__ void k_afs_span_normalise(const double *windows, uint32_t W, size_t a
     result[i] /= windows[w + 1] - windows[w];
 }
 
+// ---------------------------------------------------------------- relatedness vector
+// tsk_treeseq_genetic_relatedness_vector (trees.c:10445-10816), branch mode: out[focal][k] is the
+// integral over the window of  sum over the ancestors-or-self u of the focal node of
+// branch_length[u] * w_u[k],  w_u = the summed weights of the samples below u (the sweep's state).
+// The reference carries this as lazily updated per-node v/x vectors along its sequential sweep; here
+// it is the transpose of the sweep: G[piece] = branch_length * |piece ^ window| * state[piece] + the
+// G of every piece that references it (a parent piece lies inside the span of each piece it
+// references, see plan.cuh), pushed down one height per launch, tallest first.  A sample's INIT slot
+// collects the G of all its pieces = its output row.  Focal nodes that are not samples need the
+// node of every piece (node-mode plan): their pieces are summed per node.
+template <class V>
+__global__ void k_relvec_push(uint32_t lo, uint32_t count, const uint32_t *__restrict__ q_bp0,
+    const uint32_t *__restrict__ q_bp1, const double *__restrict__ q_bl, const double *__restrict__ bp_pos,
+    const uint32_t *__restrict__ q_off, const uint32_t *__restrict__ refs, const V *__restrict__ pval,
+    V *G, const double *__restrict__ windows, uint32_t w, const int32_t *__restrict__ q_node, double *Gn,
+    uint32_t K) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const uint32_t j = lo + t;
+    const uint32_t b1 = q_bp1[j];
+    if (b1 == NO_PIECE) return;
+    V g = G[j];  // complete: every piece referencing j is taller and was pushed by an earlier launch
+    const double bl = q_bl[j];
+    if (bl != 0.0) {
+        const double x0 = bp_pos[q_bp0[j]], x1 = bp_pos[b1];
+        const double wl = windows[w], wr = windows[w + 1];
+        const double len = (x1 < wr ? x1 : wr) - (x0 > wl ? x0 : wl);
+        if (len > 0.0) {
+            const double area = bl * len;
+            const V st = pval[j];
+#pragma unroll
+            for (int k = 0; k < V::N; k++) g.v[k] += area * st.v[k];
+        }
+    }
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < V::N; k++) any |= g.v[k] != 0.0;
+    if (!any) return;
+    if (Gn != nullptr) {
+        const int32_t u = q_node[j];
+#pragma unroll
+        for (int k = 0; k < V::N; k++) {
+            if ((uint32_t) k < K) atomicAdd(Gn + (size_t) u * K + k, g.v[k]);
+        }
+    }
+    const uint32_t r1 = q_off[j + 1];
+    for (uint32_t r = q_off[j]; r < r1; r++) {
+        double *dst = reinterpret_cast<double *>(G + refs[r]);
+#pragma unroll
+        for (int k = 0; k < V::N; k++) {
+            if ((uint32_t) k < K) atomicAdd(dst + k, g.v[k]);
+        }
+    }
+}
+
+template <class V>
+__global__ void k_relvec_out(const int32_t *__restrict__ focal, uint32_t nf, uint32_t K,
+    const int32_t *__restrict__ sample_index, const V *__restrict__ init, const double *__restrict__ Gn,
+    double *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf * K) return;
+    const uint32_t j = i / K, k = i % K;
+    const int32_t u = focal[j];
+    const int32_t si = sample_index[u];
+    double r = 0.0;
+    if (si >= 0) {
+        r = reinterpret_cast<const double *>(init + si)[k];
+    } else if (Gn != nullptr) {
+        r = Gn[(size_t) u * K + k];
+    }
+    out[i] = r;
+}
+
 // ---------------------------------------------------------------- node mode
 // tsk_treeseq_node_general_stat (trees.c:1788-1918): result[w][u] is the integral over window w of
 // the summary of node u's state -- no branch lengths, and every node counts, in a tree or not.
@@ -1153,6 +1226,44 @@ void run_afs_branch(CallCtx &c, V *pval) {
     TSKB_CK(cudaEventRecord(P.ev[4], c.s));
 }
 
+// relatedness vector: sweep, then one push launch per height and window, tallest height first
+template <class V>
+void run_relvec(CallCtx &c, V *pval) {
+    if constexpr (std::is_same<typename V::scalar, double>::value) {
+        const Plan &P = *c.P;
+        const StatSpec &sp = *c.sp;
+        const uint32_t W = sp.W, K = sp.K, nf = (uint32_t) sp.num_focal;
+        Arena &A = P.arena;
+        launch_sweep<V>(c, pval);
+        TSKB_CK(cudaEventRecord(P.ev[2], c.s));
+        const size_t slots = (size_t) P.npp + P.num_samples + 1;
+        V *G = A.get<V>(slots);
+        int32_t *d_focal = A.get<int32_t>(nf + 1);
+        TSKB_CK(cudaMemcpyAsync(d_focal, sp.focal, (size_t) nf * sizeof(int32_t), cudaMemcpyHostToDevice, c.s));
+        double *Gn = sp.focal_needs_nodes ? A.get<double>((size_t) P.N * K) : nullptr;
+        for (uint32_t w = 0; w < W; w++) {
+            TSKB_CK(cudaMemsetAsync(G, 0, slots * sizeof(V), c.s));
+            if (Gn) TSKB_CK(cudaMemsetAsync(Gn, 0, (size_t) P.N * K * sizeof(double), c.s));
+            for (uint32_t h = P.nheights; h-- > 0;) {
+                const uint32_t lo = P.level_begin[h], cnt = P.level_begin[h + 1] - lo;
+                if (cnt == 0) continue;
+                k_relvec_push<V><<<grid_for(cnt, TB), TB, 0, c.s>>>(lo, cnt, P.q_bp0.p, P.q_bp1.p, P.q_bl.p,
+                    P.bp_pos.p, P.q_off.p, P.refs.p, pval, G, c.d_windows, w, P.q_node.p, Gn, K);
+                TSKB_CK_LAUNCH();
+                c.launches++;
+            }
+            if (nf * K) {
+                k_relvec_out<V><<<grid_for((size_t) nf * K, TB), TB, 0, c.s>>>(d_focal, nf, K,
+                    P.d_sample_index.p, G + P.npp, Gn, c.d_result + (size_t) w * nf * K);
+                TSKB_CK_LAUNCH();
+                c.launches++;
+            }
+        }
+        TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+        TSKB_CK(cudaEventRecord(P.ev[4], c.s));
+    }
+}
+
 template <int STAT, class V>
 void run_phases(CallCtx &c, V *pval, V totals) {
     if (c.sp->options & TSKB_STAT_NODE) {
@@ -1212,7 +1323,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     // All small per-call inputs travel in ONE host-to-device copy:
     //   [0] validation key (all ones)  [8] duplicate flag, sweep error flag  [16] completion counters
     //   [24] set offsets (K + 1, padded)  | result columns (M)  | window edges (W + 1)
-    const uint32_t Mc = sp.stat_id == STAT_AFS ? 0 : M;  // the spectrum has no per-column parameters
+    const uint32_t Mc = (sp.stat_id == STAT_AFS || sp.stat_id == STAT_REL_VECTOR) ? 0 : M;  // the spectrum has no per-column parameters
     const size_t off_bytes = ((size_t) (K + 1) * sizeof(uint32_t) + 7) & ~size_t(7);
     const size_t o_off = 24, o_cols = o_off + off_bytes, o_win = o_cols + (size_t) Mc * sizeof(ColP);
     const size_t stage_bytes = o_win + (size_t) (W + 1) * sizeof(double);
@@ -1303,6 +1414,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
             case STAT_REL_WEIGHTED: run_phases<STAT_REL_WEIGHTED, V>(c, pval, totals); break;
             case STAT_REL_WEIGHTED_NC: run_phases<STAT_REL_WEIGHTED_NC, V>(c, pval, totals); break;
             case STAT_TRAIT_LM: run_phases<STAT_TRAIT_LM, V>(c, pval, totals); break;
+            case STAT_REL_VECTOR: run_relvec<V>(c, pval); break;
             default: return TSKB_ERR_BAD_PARAM_VALUE;
         }
     } else

@@ -42,7 +42,8 @@ PUBLIC_STATS = (
     "diversity", "divergence", "divergence_matrix", "genetic_relatedness",
     "genetic_relatedness_matrix", "segregating_sites", "Tajimas_D", "Fst", "Y1", "Y2", "Y3",
     "f2", "f3", "f4", "sample_count_stat", "general_stat", "trait_covariance", "trait_correlation",
-    "trait_linear_model", "genetic_relatedness_weighted", "allele_frequency_spectrum")
+    "trait_linear_model", "genetic_relatedness_weighted", "allele_frequency_spectrum",
+    "genetic_relatedness_vector")
 
 
 def tables_from_tree_sequence(ts):
@@ -101,7 +102,8 @@ def _make(name):
 WEIGHTED = ("trait_covariance", "trait_correlation", "trait_linear_model",
             "genetic_relatedness_weighted")
 
-for _n in ONE_WAY + K_WAY + WEIGHTED + ("divergence_matrix", "general_stat", "allele_frequency_spectrum"):
+for _n in ONE_WAY + K_WAY + WEIGHTED + ("divergence_matrix", "general_stat", "allele_frequency_spectrum",
+                                           "genetic_relatedness_vector"):
     setattr(_Proxy, _n, _make(_n))
 
 

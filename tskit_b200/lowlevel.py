@@ -416,6 +416,32 @@ class LLTreeSequence:
             options))
         return result
 
+    # ---- TreeSequence_weighted_stat_vector_method (_tskitmodule.c:7197-7282)
+    def genetic_relatedness_vector(self, weights, windows, mode=None, span_normalise=True,
+                                   centre=True, nodes=None):
+        options = parse_stats_mode(mode)
+        if span_normalise:
+            options |= STAT_SPAN_NORMALISE
+        if not centre:
+            options |= STAT_NONCENTRED
+        w = parse_windows(windows)
+        W = self._parse_weights(weights)
+        focal = np.array(nodes, dtype=np.int32, copy=True, order="C")
+        if focal.ndim != 1:
+            raise ValueError("object of too small depth for desired array"
+                             if focal.ndim < 1 else "object too deep for desired array")
+        result = np.zeros((len(w) - 1, focal.shape[0], W.shape[1]))
+        # focal nodes that are not samples: the engine that keeps the node of every piece
+        engine = self
+        in_range = (focal >= 0) & (focal < self.tables.num_nodes)
+        if in_range.all() and focal.size and not (options & (STAT_SITE | STAT_NODE)):
+            if not np.isin(focal, self.tables.samples).all():
+                engine = self._for_mode(STAT_NODE)
+        _handle(_lib.lib().tskb_treeseq_genetic_relatedness_vector(
+            engine._h, W.shape[1], _p(W), len(w) - 1, _p(w), focal.shape[0], _p(focal), _p(result),
+            options))
+        return result
+
     # ---- TreeSequence_divergence_matrix (_tskitmodule.c:7435-7509)
     def divergence_matrix(self, windows, sample_sets=None, sample_set_sizes=None, mode=None,
                           span_normalise=True):
