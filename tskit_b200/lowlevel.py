@@ -435,7 +435,7 @@ class LLTreeSequence:
         engine = self
         in_range = (focal >= 0) & (focal < self.tables.num_nodes)
         if in_range.all() and focal.size and not (options & (STAT_SITE | STAT_NODE)):
-            if not np.isin(focal, self.tables.samples).all():
+            if not ((self.tables.nodes_flags[focal] & 1) != 0).all():  # NODE_IS_SAMPLE
                 engine = self._for_mode(STAT_NODE)
         _handle(_lib.lib().tskb_treeseq_genetic_relatedness_vector(
             engine._h, W.shape[1], _p(W), len(w) - 1, _p(w), focal.shape[0], _p(focal), _p(result),
