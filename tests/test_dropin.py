@@ -393,3 +393,24 @@ def test_relatedness_vector_fixtures(name):
         got = ll.genetic_relatedness_vector(W, w, mode="branch", centre=False, nodes=nodes)
         want = o.genetic_relatedness_vector(W, windows=w, centre=False, nodes=nodes)
         assert np.allclose(got, want, rtol=1e-9, atol=1e-12), name
+
+
+@pytest.mark.gpu
+def test_pca_iterates_on_the_engine(ts):
+    """`TreeSequence.pca` (trees.py:9284-9557) is a randomised SVD whose operator is the relatedness
+    vector product: under the drop-in every product runs on the device, and the result is the
+    reference's (same seed; eigenvectors up to sign)."""
+    acc = dropin.accelerate(ts)
+    L = ts.sequence_length
+    for kw in (dict(num_components=3), dict(num_components=2, windows=[0, L / 2, L], samples=ts.samples()[:50]),
+               dict(num_components=2, centre=False)):
+        want = ts.pca(random_seed=7, **kw)
+        before = acc.accel_stats["accelerated"]
+        got = acc.pca(random_seed=7, **kw)
+        assert acc.accel_stats["accelerated"] > before and acc.accel_stats["forwarded"] == 0
+        assert got.factors.shape == want.factors.shape
+        assert np.allclose(got.eigenvalues, want.eigenvalues, rtol=1e-7)
+        f, g = got.factors.reshape(-1, *got.factors.shape[-2:]), want.factors.reshape(-1, *want.factors.shape[-2:])
+        for a, b in zip(f, g):
+            sign = np.sign(np.sum(a * b, axis=0))
+            assert np.allclose(a * sign, b, atol=1e-6), kw

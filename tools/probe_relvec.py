@@ -25,17 +25,21 @@ n = len(s)
 rng = np.random.default_rng(1)
 out = {"num_samples": n, "num_edges": int(t.num_edges)}
 res = {}
-for K in (1, 8):
+QUICK = os.environ.get("PROBE_QUICK") is not None  # one call only (under ncu)
+for K in ((1,) if QUICK else (1, 8)):
     Wt = rng.normal(size=(n, K))
-    for nw in (1, 10):
+    for nw in ((1,) if QUICK else (1, 10)):
         w = np.linspace(0, L, nw + 1)
-        r, ms = timed(lambda: ll.genetic_relatedness_vector(Wt, w, mode="branch", centre=True, nodes=s))
+        r, ms = timed(lambda: ll.genetic_relatedness_vector(Wt, w, mode="branch", centre=True, nodes=s),
+                      reps=1 if QUICK else 3)
         out[f"relvec_{K}cols_{nw}windows_ms"] = ms
         res[(K, nw)] = (Wt, w, r)
         st = ll.engine_stats()
         out[f"relvec_{K}cols_{nw}windows_launches"] = int(st["last_launches"])
         out[f"relvec_{K}cols_{nw}windows_device_ms"] = float(st["last_call_ms"])
 try:
+    if QUICK:
+        raise RuntimeError("quick run")
     from tskit_b200 import dropin
     ts = dropin.from_tables(t)
     for key in ((1, 1), (8, 1)):

@@ -845,61 +845,71 @@ template <class V>
 __global__ void k_relvec_push(uint32_t lo, uint32_t count, const uint32_t *__restrict__ q_bp0,
     const uint32_t *__restrict__ q_bp1, const double *__restrict__ q_bl, const double *__restrict__ bp_pos,
     const uint32_t *__restrict__ q_off, const uint32_t *__restrict__ refs, const V *__restrict__ pval,
-    V *G, const double *__restrict__ windows, uint32_t w, const int32_t *__restrict__ q_node, double *Gn,
-    uint32_t K) {
+    V *G, size_t slots, const double *__restrict__ windows, uint32_t W, uint32_t w0, uint32_t wc,
+    const int32_t *__restrict__ q_node, double *Gn, size_t gn_stride, uint32_t K) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     const uint32_t j = lo + t;
     const uint32_t b1 = q_bp1[j];
     if (b1 == NO_PIECE) return;
-    V g = G[j];  // complete: every piece referencing j is taller and was pushed by an earlier launch
+    // G of window w is zero unless the piece meets w (the pieces that reference it lie inside its
+    // span): only those windows of this launch's chunk [w0, w0 + wc) are touched
+    const double x0 = bp_pos[q_bp0[j]], x1 = bp_pos[b1];
+    uint32_t w = upper_bound_dev(windows, W + 1, x0);
+    w = w > 0 ? w - 1 : 0;
+    if (w < w0) w = w0;
+    const uint32_t wend = w0 + wc;
+    if (w >= wend || !(windows[w] < x1)) return;
     const double bl = q_bl[j];
-    if (bl != 0.0) {
-        const double x0 = bp_pos[q_bp0[j]], x1 = bp_pos[b1];
+    const V st = pval[j];
+    const uint32_t r0 = q_off[j], r1 = q_off[j + 1];
+    for (; w < wend && windows[w] < x1; w++) {
+        V *Gw = G + (size_t) (w - w0) * slots;
+        V g = Gw[j];  // complete: every piece referencing j is taller and was pushed by an earlier launch
         const double wl = windows[w], wr = windows[w + 1];
         const double len = (x1 < wr ? x1 : wr) - (x0 > wl ? x0 : wl);
-        if (len > 0.0) {
+        if (bl != 0.0 && len > 0.0) {
             const double area = bl * len;
-            const V st = pval[j];
 #pragma unroll
             for (int k = 0; k < V::N; k++) g.v[k] += area * st.v[k];
         }
-    }
-    bool any = false;
+        bool any = false;
 #pragma unroll
-    for (int k = 0; k < V::N; k++) any |= g.v[k] != 0.0;
-    if (!any) return;
-    if (Gn != nullptr) {
-        const int32_t u = q_node[j];
+        for (int k = 0; k < V::N; k++) any |= g.v[k] != 0.0;
+        if (!any) continue;
+        if (Gn != nullptr) {
+            double *dst = Gn + (size_t) (w - w0) * gn_stride + (size_t) q_node[j] * K;
 #pragma unroll
-        for (int k = 0; k < V::N; k++) {
-            if ((uint32_t) k < K) atomicAdd(Gn + (size_t) u * K + k, g.v[k]);
+            for (int k = 0; k < V::N; k++) {
+                if ((uint32_t) k < K) atomicAdd(dst + k, g.v[k]);
+            }
         }
-    }
-    const uint32_t r1 = q_off[j + 1];
-    for (uint32_t r = q_off[j]; r < r1; r++) {
-        double *dst = reinterpret_cast<double *>(G + refs[r]);
+        for (uint32_t r = r0; r < r1; r++) {
+            double *dst = reinterpret_cast<double *>(Gw + refs[r]);
 #pragma unroll
-        for (int k = 0; k < V::N; k++) {
-            if ((uint32_t) k < K) atomicAdd(dst + k, g.v[k]);
+            for (int k = 0; k < V::N; k++) {
+                if ((uint32_t) k < K) atomicAdd(dst + k, g.v[k]);
+            }
         }
     }
 }
 
+// rows of the focal nodes, for the wc windows of one chunk: out[c][j][k]
 template <class V>
-__global__ void k_relvec_out(const int32_t *__restrict__ focal, uint32_t nf, uint32_t K,
-    const int32_t *__restrict__ sample_index, const V *__restrict__ init, const double *__restrict__ Gn,
-    double *out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nf * K) return;
-    const uint32_t j = i / K, k = i % K;
+__global__ void k_relvec_out(const int32_t *__restrict__ focal, uint32_t nf, uint32_t K, uint32_t wc,
+    const int32_t *__restrict__ sample_index, const V *__restrict__ G, size_t slots, uint32_t npp,
+    const double *__restrict__ Gn, size_t gn_stride, double *out) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t row = (size_t) nf * K;
+    if (i >= row * wc) return;
+    const uint32_t c = (uint32_t) (i / row), j = (uint32_t) ((i % row) / K), k = (uint32_t) (i % K);
     const int32_t u = focal[j];
     const int32_t si = sample_index[u];
     double r = 0.0;
     if (si >= 0) {
-        r = reinterpret_cast<const double *>(init + si)[k];
+        r = reinterpret_cast<const double *>(G + (size_t) c * slots + npp + si)[k];
     } else if (Gn != nullptr) {
-        r = Gn[(size_t) u * K + k];
+        r = Gn[(size_t) c * gn_stride + (size_t) u * K + k];
     }
     out[i] = r;
 }
@@ -1237,24 +1247,31 @@ void run_relvec(CallCtx &c, V *pval) {
         launch_sweep<V>(c, pval);
         TSKB_CK(cudaEventRecord(P.ev[2], c.s));
         const size_t slots = (size_t) P.npp + P.num_samples + 1;
-        V *G = A.get<V>(slots);
+        const size_t gn_stride = sp.focal_needs_nodes ? (size_t) P.N * K : 0;
+        // windows in chunks whose accumulators fit 2 GB; one push launch per height and chunk
+        const size_t per_window = slots * sizeof(V) + gn_stride * sizeof(double);
+        uint32_t wc_max = (uint32_t) std::max<size_t>(1, (size_t(2) << 30) / per_window);
+        if (wc_max > W) wc_max = W;
+        V *G = A.get<V>(slots * wc_max);
         int32_t *d_focal = A.get<int32_t>(nf + 1);
         TSKB_CK(cudaMemcpyAsync(d_focal, sp.focal, (size_t) nf * sizeof(int32_t), cudaMemcpyHostToDevice, c.s));
-        double *Gn = sp.focal_needs_nodes ? A.get<double>((size_t) P.N * K) : nullptr;
-        for (uint32_t w = 0; w < W; w++) {
-            TSKB_CK(cudaMemsetAsync(G, 0, slots * sizeof(V), c.s));
-            if (Gn) TSKB_CK(cudaMemsetAsync(Gn, 0, (size_t) P.N * K * sizeof(double), c.s));
+        double *Gn = gn_stride ? A.get<double>(gn_stride * wc_max) : nullptr;
+        for (uint32_t w0 = 0; w0 < W; w0 += wc_max) {
+            const uint32_t wc = W - w0 < wc_max ? W - w0 : wc_max;
+            TSKB_CK(cudaMemsetAsync(G, 0, slots * wc * sizeof(V), c.s));
+            if (Gn) TSKB_CK(cudaMemsetAsync(Gn, 0, gn_stride * wc * sizeof(double), c.s));
             for (uint32_t h = P.nheights; h-- > 0;) {
                 const uint32_t lo = P.level_begin[h], cnt = P.level_begin[h + 1] - lo;
                 if (cnt == 0) continue;
                 k_relvec_push<V><<<grid_for(cnt, TB), TB, 0, c.s>>>(lo, cnt, P.q_bp0.p, P.q_bp1.p, P.q_bl.p,
-                    P.bp_pos.p, P.q_off.p, P.refs.p, pval, G, c.d_windows, w, P.q_node.p, Gn, K);
+                    P.bp_pos.p, P.q_off.p, P.refs.p, pval, G, slots, c.d_windows, W, w0, wc, P.q_node.p, Gn,
+                    gn_stride, K);
                 TSKB_CK_LAUNCH();
                 c.launches++;
             }
-            if (nf * K) {
-                k_relvec_out<V><<<grid_for((size_t) nf * K, TB), TB, 0, c.s>>>(d_focal, nf, K,
-                    P.d_sample_index.p, G + P.npp, Gn, c.d_result + (size_t) w * nf * K);
+            if ((size_t) nf * K) {
+                k_relvec_out<V><<<grid_for((size_t) nf * K * wc, TB), TB, 0, c.s>>>(d_focal, nf, K, wc,
+                    P.d_sample_index.p, G, slots, P.npp, Gn, gn_stride, c.d_result + (size_t) w0 * nf * K);
                 TSKB_CK_LAUNCH();
                 c.launches++;
             }
