@@ -37,6 +37,16 @@ for K in ((1,) if QUICK else (1, 8)):
         st = ll.engine_stats()
         out[f"relvec_{K}cols_{nw}windows_launches"] = int(st["last_launches"])
         out[f"relvec_{K}cols_{nw}windows_device_ms"] = float(st["last_call_ms"])
+# the C-ABI call alone (arrays prepared once), to separate the ctypes mirror's share of the wall time
+import ctypes as C
+from tskit_b200 import _lib
+Wt, w, _ = res[(1, 1)]
+focal = np.ascontiguousarray(s, dtype=np.int32)
+result = np.zeros((1, n, 1))
+p = lambda a: a.ctypes.data_as(C.c_void_p)
+_, out["relvec_1cols_1windows_cabi_only_ms"] = timed(lambda: _lib.lib().tskb_treeseq_genetic_relatedness_vector(
+    ll._h, 1, p(Wt), 1, p(w), n, p(focal), p(result), 2), reps=5)
+out["relvec_1cols_1windows_phase_ms"] = [float(x) for x in ll.engine_stats()["last_kernel_ms"]]
 try:
     if QUICK:
         raise RuntimeError("quick run")

@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" boundary (include/tskit_b200.h): argument validation with the
 // reference's error codes and precedence, then dispatch to the device engine.
 // There is deliberately no host implementation of any statistic in this library.
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -596,6 +597,8 @@ int tskb_treeseq_genetic_relatedness_vector(const tskb_treeseq_t *self, uint64_t
     if (self == nullptr || self->plan == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
     const Plan &P = *self->plan;
     return guarded([&]() -> int {
+        const auto t0 = std::chrono::steady_clock::now();
+        double ms_device_calls = 0;
         if (options & (TSKB_STAT_SITE | TSKB_STAT_NODE)) return TSKB_ERR_UNSUPPORTED_STAT_MODE;
         if (windows == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
         int ret = check_windows(P, num_windows, windows, false);
@@ -609,8 +612,7 @@ int tskb_treeseq_genetic_relatedness_vector(const tskb_treeseq_t *self, uint64_t
         if (needs_nodes && !P.all_pieces) return TSKB_ERR_UNSUPPORTED;  // needs TSKB_INIT_NODE_MODE
         const uint64_t row = nf * K;
         if ((double) num_windows * (double) row > 2e9 || row > 0xffffffffull) return TSKB_ERR_UNSUPPORTED;
-        for (uint64_t i = 0; i < num_windows * row; i++) result[i] = 0.0;
-        if (row == 0) return 0;
+        if (row == 0) return 0;  // nothing to write (the engine writes every entry otherwise)
         std::vector<double> means(K, 0.0);
         if (!(options & TSKB_STAT_NONCENTRED)) {
             for (uint64_t j = 0; j < n; j++) {
@@ -618,13 +620,23 @@ int tskb_treeseq_genetic_relatedness_vector(const tskb_treeseq_t *self, uint64_t
             }
             for (uint64_t k = 0; k < K; k++) means[k] /= (double) n;
         }
-        // state columns in batches of one sweep's width
+        // state columns in batches of one sweep's width; a single batch reads the caller's weights
+        // (when they are not centred) and writes the caller's result directly
+        const bool centred = !(options & TSKB_STAT_NONCENTRED);
+        const bool one_batch = K <= MAX_STATE_DIM;
+        std::vector<double> Wb, out;
         for (uint64_t k0 = 0; k0 < K; k0 += MAX_STATE_DIM) {
             const uint64_t kb = K - k0 < MAX_STATE_DIM ? K - k0 : MAX_STATE_DIM;
-            std::vector<double> Wb(n * kb), out(num_windows * nf * kb), totals(kb, 0.0);
-            for (uint64_t j = 0; j < n; j++) {
-                for (uint64_t k = 0; k < kb; k++) Wb[j * kb + k] = weights[j * K + k0 + k] - means[k0 + k];
+            std::vector<double> totals(kb, 0.0);
+            const double *w_in = weights;
+            if (centred || !one_batch) {
+                Wb.resize(n * kb);
+                for (uint64_t j = 0; j < n; j++) {
+                    for (uint64_t k = 0; k < kb; k++) Wb[j * kb + k] = weights[j * K + k0 + k] - means[k0 + k];
+                }
+                w_in = Wb.data();
             }
+            if (!one_batch) out.resize(num_windows * nf * kb);
             StatSpec sp = {};
             sp.stat_id = STAT_REL_VECTOR;
             sp.K = (uint32_t) kb;
@@ -632,14 +644,17 @@ int tskb_treeseq_genetic_relatedness_vector(const tskb_treeseq_t *self, uint64_t
             sp.W = (uint32_t) num_windows;
             sp.windows = windows;
             sp.options = TSKB_STAT_BRANCH;
-            sp.result = out.data();
-            sp.weights = Wb.data();
+            sp.result = one_batch ? result : out.data();
+            sp.weights = w_in;
             sp.column_totals = totals.data();
             sp.focal = focal_nodes;
             sp.num_focal = nf;
             sp.focal_needs_nodes = needs_nodes;
+            const auto t1 = std::chrono::steady_clock::now();
             ret = run_weighted_stat(&P, sp);
+            ms_device_calls += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
             if (ret != 0) return ret;
+            if (one_batch) break;
             for (uint64_t w = 0; w < num_windows; w++) {
                 for (uint64_t j = 0; j < nf; j++) {
                     for (uint64_t k = 0; k < kb; k++) {
@@ -664,6 +679,10 @@ int tskb_treeseq_genetic_relatedness_vector(const tskb_treeseq_t *self, uint64_t
                 const double span = windows[w + 1] - windows[w];
                 for (uint64_t i = 0; i < row; i++) y[i] /= span;
             }
+        }
+        if (getenv("TSKB_TIMING") != nullptr) {
+            fprintf(stderr, "tskb timing: relatedness_vector total %.3f ms, of which engine calls %.3f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), ms_device_calls);
         }
         return 0;
     });

@@ -13,6 +13,7 @@
 //   3 finalize   branch: prefix over windows + span-normalise; site: window sums
 //                                                                       (trees.c:1753-1762, 1920-1934)
 //   5 d2h        result -> host
+#include <chrono>
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -1248,9 +1249,9 @@ void run_relvec(CallCtx &c, V *pval) {
         TSKB_CK(cudaEventRecord(P.ev[2], c.s));
         const size_t slots = (size_t) P.npp + P.num_samples + 1;
         const size_t gn_stride = sp.focal_needs_nodes ? (size_t) P.N * K : 0;
-        // windows in chunks whose accumulators fit 2 GB; one push launch per height and chunk
+        // windows in chunks whose accumulators fit 8 GB; one push launch per height and chunk
         const size_t per_window = slots * sizeof(V) + gn_stride * sizeof(double);
-        uint32_t wc_max = (uint32_t) std::max<size_t>(1, (size_t(2) << 30) / per_window);
+        uint32_t wc_max = (uint32_t) std::max<size_t>(1, (size_t(8) << 30) / per_window);
         if (wc_max > W) wc_max = W;
         V *G = A.get<V>(slots * wc_max);
         int32_t *d_focal = A.get<int32_t>(nf + 1);
@@ -1296,6 +1297,8 @@ template <class V>
 int run_impl(const Plan &P, const StatSpec &sp) {
     cudaStream_t s = P.stream;
     const uint32_t K = sp.K, M = sp.M, W = sp.W;
+    const bool timing = getenv("TSKB_TIMING") != nullptr;  // host-side phases of the call, to stderr
+    const auto t_enter = std::chrono::steady_clock::now();
     Arena &A = P.arena;
     A.reset();
     CallCtx c = {};
@@ -1470,7 +1473,14 @@ int run_impl(const Plan &P, const StatSpec &sp) {
             cudaMemcpyDeviceToHost, s));
     }
     TSKB_CK(cudaEventRecord(P.ev[6], s));
+    const auto t_enqueued = std::chrono::steady_clock::now();
     TSKB_CK(cudaStreamSynchronize(s));
+    if (timing) {
+        const auto t_done = std::chrono::steady_clock::now();
+        fprintf(stderr, "tskb timing: stat %d enqueue %.3f ms, wait %.3f ms\n", sp.stat_id,
+            std::chrono::duration<double, std::milli>(t_enqueued - t_enter).count(),
+            std::chrono::duration<double, std::milli>(t_done - t_enqueued).count());
+    }
     float ms = 0;
     for (int q = 0; q < 6; q++) {
         TSKB_CK(cudaEventElapsedTime(&ms, P.ev[q], P.ev[q + 1]));
