@@ -340,6 +340,28 @@ def test_genome_range_shards_sum_to_whole(wf_small, engines):
                                    span_normalise=False))
 
 
+def test_relatedness_vector_genome_range_shards_sum_to_whole(wf_small, engines):
+    """the relatedness vector over [a, b) shards: un-normalised rows add up (also when centred: centring
+    the output rows is linear), which is what tskit_b200.sharding sums over the ranks"""
+    from tskit_b200.lowlevel import LLTreeSequence
+    ll, o = engines
+    s = wf_small.samples
+    L = wf_small.sequence_length
+    w = np.linspace(0, L, 6)
+    cuts = [0.0, 21000.5, w[2], 77777.0, L]
+    wt = np.random.default_rng(2).normal(size=(len(s), 3))
+    for centre in (True, False):
+        whole = ll.genetic_relatedness_vector(wt, w, mode="branch", span_normalise=False, centre=centre, nodes=s)
+        acc = np.zeros_like(whole)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            part = LLTreeSequence(wf_small, genome_range=(a, b))
+            acc += part.genetic_relatedness_vector(wt, w, mode="branch", span_normalise=False, centre=centre,
+                                                   nodes=s)
+        assert np.allclose(acc, whole, rtol=1e-9, atol=1e-9 * np.abs(whole).max())
+        want = o.genetic_relatedness_vector(wt, windows=w, centre=centre, span_normalise=False)
+        assert np.allclose(whole, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+
+
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
 def test_against_compiled_reference_1k(wf_1k):
     from tskit_b200.lowlevel import LLTreeSequence

@@ -43,6 +43,19 @@ class OracleRangeEngine:
         assert span_normalise is False
         return self._run("divergence", sets, indexes, windows, mode)
 
+    def genetic_relatedness_vector(self, weights, windows, mode, span_normalise, centre, nodes):
+        assert span_normalise is False and mode == "branch"
+        w = np.asarray(windows, dtype=np.float64)
+        fine = np.unique(np.concatenate([w, [self.lo, self.hi]]))
+        r = self.o.genetic_relatedness_vector(weights, windows=fine, nodes=nodes, centre=centre,
+                                              span_normalise=False)
+        out = np.zeros((len(w) - 1,) + r.shape[1:])
+        mid = 0.5 * (fine[:-1] + fine[1:])
+        inside = (mid >= self.lo) & (mid < self.hi)
+        owner = np.searchsorted(w, mid, side="right") - 1
+        np.add.at(out, owner[inside], r[inside])
+        return out
+
 
 def _worker(rank, world, port_no, W, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -57,6 +70,10 @@ def _worker(rank, world, port_no, W, q):
     for mode in ("branch", "site"):
         out[("diversity", mode)] = sh.stat("diversity", sets, windows=windows, mode=mode)
         out[("divergence", mode)] = sh.stat("divergence", sets, [[0, 1]], windows=windows, mode=mode)
+    wt = np.random.default_rng(3).normal(size=(len(s), 2))
+    for centre in (True, False):
+        out[("relvec", centre)] = sh.stat("genetic_relatedness_vector", wt, windows=windows, mode="branch",
+                                          centre=centre, nodes=s)
     q.put((rank, sh.ranges, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -89,6 +106,12 @@ def test_two_rank_gloo_matches_whole_genome(W):
             assert np.allclose(out[("diversity", mode)], want, rtol=1e-11)
             want = o.stat("divergence", sets, [[0, 1]], windows=windows, mode=mode)
             assert np.allclose(out[("divergence", mode)], want, rtol=1e-11)
+        wt = np.random.default_rng(3).normal(size=(len(s), 2))
+        for centre in (True, False):
+            want = o.genetic_relatedness_vector(wt, windows=windows, centre=centre)
+            got_v = out[("relvec", centre)]
+            assert got_v.shape == want.shape
+            assert np.allclose(got_v, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
 
 
 def test_plan_shards_balanced_and_covering(wf_1k):

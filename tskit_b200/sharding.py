@@ -7,7 +7,9 @@ rank seeds the state at its range's left edge locally from the replicated tables
 sum of the per-window partial results -- windows owned by one rank receive zeros from the
 others, windows straddling a cut are the sum of their parts -- done with one ``all_reduce`` of
 ``W x M`` doubles (NCCL on GPUs, gloo in the CPU tests), before span normalisation
-(``trees.c:1920-1934`` divides after accumulation).
+(``trees.c:1920-1934`` divides after accumulation).  The relatedness vector shards the same way:
+its rows are integrals over the genome, and centring the output rows is linear, so the ranks'
+centred partial rows add up to the centred whole.
 """
 import numpy as np
 
@@ -49,7 +51,8 @@ def plan_shards(tables, windows, world):
 
 
 def combine(local, windows, span_normalise, group=None, device=None):
-    """Sum the ranks' un-normalised ``(W, M)`` partial results and span-normalise.  ``local`` is
+    """Sum the ranks' un-normalised ``(W, M)`` (relatedness vector: ``(W, nodes, K)``) partial results
+    and span-normalise.  ``local`` is
     this rank's result computed with ``span_normalise=False`` over its own genome range."""
     import torch
     import torch.distributed as dist
@@ -62,7 +65,7 @@ def combine(local, windows, span_normalise, group=None, device=None):
     out = total.numpy().copy()
     if span_normalise:
         w = np.asarray(windows, dtype=np.float64)
-        out /= (w[1:] - w[:-1])[:, None]
+        out /= (w[1:] - w[:-1]).reshape((-1,) + (1,) * (out.ndim - 1))
     return out
 
 
