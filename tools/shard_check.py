@@ -34,6 +34,13 @@ for name, idx in calls:
         r = sh.stat(name, sizes, flat, idx, windows=windows, mode="branch")
         torch.cuda.synchronize(); barrier(); dt = time.perf_counter() - t0
     out[name], times[name] = r, dt
+# relatedness vector (GRM x vector), 10 windows, 2 weight columns: the ranks' rows are summed the same way
+w10 = np.linspace(0, t.sequence_length, 11)
+wt = np.random.default_rng(1).normal(size=(len(s), 2))
+for rep in range(3):
+    barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    rv = sh.stat("genetic_relatedness_vector", wt, windows=w10, mode="branch", centre=True, nodes=s)
+    torch.cuda.synchronize(); barrier(); rv_dt = time.perf_counter() - t0
 if rank == 0:
     whole = LLTreeSequence(t, device=local)
     res = {"world": world, "ranges": sh.ranges, "workload": bench.workload_name("c2", t, W), "calls": {}}
@@ -44,6 +51,12 @@ if rank == 0:
         res["calls"][name] = {"tuples": len(idx), "sharded_ms": times[name] * 1e3, "single_gpu_ms": d1 * 1e3,
                               "max_abs_err_over_max": err}
         assert err < 1e-10, (name, err)
+    for rep in range(2):
+        t0 = time.perf_counter(); ref = whole.genetic_relatedness_vector(wt, w10, mode="branch", centre=True, nodes=s); d1 = time.perf_counter() - t0
+    err = float(np.max(np.abs(rv - ref)) / np.max(np.abs(ref)))
+    res["calls"]["genetic_relatedness_vector"] = {"columns": 2, "windows": 10, "sharded_ms": rv_dt * 1e3,
+                                                   "single_gpu_ms": d1 * 1e3, "max_abs_err_over_max": err}
+    assert err < 1e-10, ("genetic_relatedness_vector", err)
     print(json.dumps(res))
 if world > 1:
     dist.destroy_process_group()
