@@ -362,6 +362,19 @@ def test_relatedness_vector_genome_range_shards_sum_to_whole(wf_small, engines):
         assert np.allclose(whole, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
 
 
+def test_relatedness_vector_golden(wf_small, engines):
+    """the device path against the committed vectors of the reference package (tests/golden/)"""
+    from tests.test_oracle import relvec_golden_cases, relvec_golden_weights
+    ll, _ = engines
+    W = relvec_golden_weights(wf_small.num_samples)
+    for key, kw, want in relvec_golden_cases():
+        nodes = wf_small.samples if kw["nodes"] is None else kw["nodes"]
+        got = ll.genetic_relatedness_vector(W, kw["windows"], mode="branch", span_normalise=kw["span_normalise"],
+                                            centre=kw["centre"], nodes=nodes)
+        assert got.shape == want.shape
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max()), key
+
+
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
 def test_against_compiled_reference_1k(wf_1k):
     from tskit_b200.lowlevel import LLTreeSequence
