@@ -18,9 +18,11 @@ GRM post-processing) runs unmodified on top.
     ts.diversity(sample_sets, windows=w, mode="branch")   # same call, same result, on the GPU
 
 There is no CPU fallback for the accelerated calls: an engine failure raises.  Calls the engine
-does not cover (float-weighted ``general_stat`` with a Python summary, AFS) are forwarded to the
-reference object and counted in ``ts.accel_stats["forwarded"]`` so that tests can assert which
-path ran.
+does not cover (float-weighted ``general_stat`` with a Python summary, branch-mode allele frequency
+spectra with time windows other than ``[0, inf)``, more sample sets or output than one call holds)
+are forwarded to the reference object and counted in ``ts.accel_stats["forwarded"]`` so that tests
+can assert which path ran.  ``genetic_relatedness_vector`` is routed too, so ``ts.pca`` -- whose
+randomised SVD iterates that product (``trees.py:9284-9557``) -- runs its products on the device.
 """
 import threading
 
