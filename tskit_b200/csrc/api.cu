@@ -595,6 +595,10 @@ int tskb_treeseq_genetic_relatedness_vector(const tskb_treeseq_t *self, uint64_t
     const double *weights, uint64_t num_windows, const double *windows, uint64_t num_focal_nodes,
     const int32_t *focal_nodes, double *result, uint32_t options) {
     if (self == nullptr || self->plan == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    if ((weights == nullptr && num_weights > 0) || (focal_nodes == nullptr && num_focal_nodes > 0)
+        || result == nullptr) {
+        return TSKB_ERR_BAD_PARAM_VALUE;
+    }
     const Plan &P = *self->plan;
     return guarded([&]() -> int {
         const auto t0 = std::chrono::steady_clock::now();
