@@ -41,7 +41,29 @@ extern "C" {
 /* ---- error codes: identical values to c/tskit/core.h:259-698 ---- */
 #define TSKB_ERR_NO_MEMORY (-2)
 #define TSKB_ERR_BAD_PARAM_VALUE (-4)
+/* table integrity, checked by tskb_treeseq_init as tsk_treeseq_init does through
+ * tsk_table_collection_check_integrity (c/tskit/tables.c:10362-10640, 10894-10930) */
+#define TSKB_ERR_BAD_OFFSET (-200)
 #define TSKB_ERR_NODE_OUT_OF_BOUNDS (-202)
+#define TSKB_ERR_EDGE_OUT_OF_BOUNDS (-203)
+#define TSKB_ERR_SITE_OUT_OF_BOUNDS (-205)
+#define TSKB_ERR_MUTATION_OUT_OF_BOUNDS (-206)
+#define TSKB_ERR_TIME_NONFINITE (-210)
+#define TSKB_ERR_GENOME_COORDS_NONFINITE (-211)
+#define TSKB_ERR_NULL_PARENT (-300)
+#define TSKB_ERR_NULL_CHILD (-301)
+#define TSKB_ERR_BAD_NODE_TIME_ORDERING (-306)
+#define TSKB_ERR_BAD_EDGE_INTERVAL (-307)
+#define TSKB_ERR_RIGHT_GREATER_SEQ_LENGTH (-309)
+#define TSKB_ERR_LEFT_LESS_ZERO (-310)
+#define TSKB_ERR_UNSORTED_SITES (-400)
+#define TSKB_ERR_DUPLICATE_SITE_POSITION (-401)
+#define TSKB_ERR_BAD_SITE_POSITION (-402)
+#define TSKB_ERR_MUTATION_PARENT_DIFFERENT_SITE (-500)
+#define TSKB_ERR_MUTATION_PARENT_EQUAL (-501)
+#define TSKB_ERR_MUTATION_PARENT_AFTER_CHILD (-502)
+#define TSKB_ERR_UNSORTED_MUTATIONS (-504)
+#define TSKB_ERR_BAD_SEQUENCE_LENGTH (-701)
 #define TSKB_ERR_DUPLICATE_SAMPLE (-600)
 #define TSKB_ERR_BAD_SAMPLES (-601)
 #define TSKB_ERR_BAD_NUM_WINDOWS (-900)

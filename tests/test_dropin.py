@@ -66,6 +66,51 @@ def test_node_mode_goes_to_the_engine(ts):
     assert eng.calls == ["diversity"]
 
 
+def test_seam_is_per_thread(ts):
+    """While one thread is inside a statistic, other threads using the same object keep seeing the
+    real low-level object (the C constructors of Tree / Variant type-check it)."""
+    import threading
+    import time
+
+    inside, release = threading.Event(), threading.Event()
+
+    class SlowEngine(EchoEngine):
+        def __getattr__(self, name):
+            f = EchoEngine.__getattr__(self, name)
+
+            def g(*a, **k):
+                inside.set()
+                assert release.wait(30)
+                return f(*a, **k)
+            g.__name__ = name
+            return g
+
+    acc = dropin.accelerate(ts, engine=SlowEngine(ts.ll_tree_sequence))
+    out = {}
+    worker = threading.Thread(target=lambda: out.setdefault("pi", acc.diversity(mode="branch")))
+    worker.start()
+    assert inside.wait(30)
+    try:
+        # the statistic is in flight on the other thread: this thread must not see the proxy
+        assert acc._ll_tree_sequence is ts.ll_tree_sequence
+        assert acc.first().num_samples() == ts.num_samples
+        assert sum(1 for _ in acc.variants()) == ts.num_sites
+        assert tskit.Tree(acc).tree_sequence is acc
+    finally:
+        release.set()
+        worker.join(30)
+    assert np.array_equal(out["pi"], ts.diversity(mode="branch"))
+    # the reference's thread-pool chunking (trees.py:8671-8706) is replaced by one engine call
+    eng = EchoEngine(ts.ll_tree_sequence)
+    acc2 = dropin.accelerate(ts, engine=eng)
+    s = ts.samples()[:12]
+    w = np.linspace(0, ts.sequence_length, 5)
+    got = acc2.divergence_matrix([[int(u)] for u in s], windows=w, num_threads=3, mode="site")
+    assert np.array_equal(got, ts.divergence_matrix([[int(u)] for u in s], windows=w, mode="site"))
+    assert eng.calls == ["divergence_matrix"]
+    time.sleep(0)
+
+
 def test_errors_keep_reference_type(ts):
     import _tskit
     acc = dropin.accelerate(ts, engine=EchoEngine(ts.ll_tree_sequence))

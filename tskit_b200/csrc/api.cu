@@ -184,6 +184,8 @@ int sample_count_stat(const tskb_treeseq_t *self, int stat_id, uint64_t K, const
     const double *f_table, uint64_t num_windows, const double *windows, uint32_t options,
     double *result, bool result_on_device) {
     if (self == nullptr || self->plan == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    if (K > 0 && (sizes == nullptr || sets == nullptr)) return TSKB_ERR_BAD_PARAM_VALUE;
+    if (result == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
     const Plan &P = *self->plan;
     return guarded([&]() -> int {
         int tw = tuple_width(stat_id);
@@ -320,6 +322,26 @@ const char *tskb_strerror(int err) {
         case TSKB_ERR_NO_MEMORY: return "Out of memory. (TSK_ERR_NO_MEMORY)";
         case TSKB_ERR_BAD_PARAM_VALUE: return "Bad parameter value provided. (TSK_ERR_BAD_PARAM_VALUE)";
         case TSKB_ERR_NODE_OUT_OF_BOUNDS: return "Node out of bounds. (TSK_ERR_NODE_OUT_OF_BOUNDS)";
+        case TSKB_ERR_BAD_OFFSET: return "Bad offset provided in input array. (TSK_ERR_BAD_OFFSET)";
+        case TSKB_ERR_EDGE_OUT_OF_BOUNDS: return "Edge out of bounds. (TSK_ERR_EDGE_OUT_OF_BOUNDS)";
+        case TSKB_ERR_SITE_OUT_OF_BOUNDS: return "Site out of bounds. (TSK_ERR_SITE_OUT_OF_BOUNDS)";
+        case TSKB_ERR_MUTATION_OUT_OF_BOUNDS: return "Mutation out of bounds. (TSK_ERR_MUTATION_OUT_OF_BOUNDS)";
+        case TSKB_ERR_TIME_NONFINITE: return "Times must be finite. (TSK_ERR_TIME_NONFINITE)";
+        case TSKB_ERR_GENOME_COORDS_NONFINITE: return "Genome coordinates must be finite numbers. (TSK_ERR_GENOME_COORDS_NONFINITE)";
+        case TSKB_ERR_NULL_PARENT: return "Edge parent is null. (TSK_ERR_NULL_PARENT)";
+        case TSKB_ERR_NULL_CHILD: return "Edge child is null. (TSK_ERR_NULL_CHILD)";
+        case TSKB_ERR_BAD_NODE_TIME_ORDERING: return "time[parent] must be greater than time[child]. (TSK_ERR_BAD_NODE_TIME_ORDERING)";
+        case TSKB_ERR_BAD_EDGE_INTERVAL: return "Bad edge interval where right <= left. (TSK_ERR_BAD_EDGE_INTERVAL)";
+        case TSKB_ERR_RIGHT_GREATER_SEQ_LENGTH: return "Right coordinate > sequence length. (TSK_ERR_RIGHT_GREATER_SEQ_LENGTH)";
+        case TSKB_ERR_LEFT_LESS_ZERO: return "Left coordinate must be >= 0. (TSK_ERR_LEFT_LESS_ZERO)";
+        case TSKB_ERR_UNSORTED_SITES: return "Sites must be provided in strictly increasing position order. (TSK_ERR_UNSORTED_SITES)";
+        case TSKB_ERR_DUPLICATE_SITE_POSITION: return "Duplicate site positions. (TSK_ERR_DUPLICATE_SITE_POSITION)";
+        case TSKB_ERR_BAD_SITE_POSITION: return "Site positions must be between 0 and sequence_length. (TSK_ERR_BAD_SITE_POSITION)";
+        case TSKB_ERR_MUTATION_PARENT_DIFFERENT_SITE: return "Specified parent mutation is at a different site. (TSK_ERR_MUTATION_PARENT_DIFFERENT_SITE)";
+        case TSKB_ERR_MUTATION_PARENT_EQUAL: return "Parent mutation refers to itself. (TSK_ERR_MUTATION_PARENT_EQUAL)";
+        case TSKB_ERR_MUTATION_PARENT_AFTER_CHILD: return "Parent mutation ID must be < current ID. (TSK_ERR_MUTATION_PARENT_AFTER_CHILD)";
+        case TSKB_ERR_UNSORTED_MUTATIONS: return "Mutations must be provided in non-decreasing site order and non-increasing time order within each site. (TSK_ERR_UNSORTED_MUTATIONS)";
+        case TSKB_ERR_BAD_SEQUENCE_LENGTH: return "Sequence length must be > 0. (TSK_ERR_BAD_SEQUENCE_LENGTH)";
         case TSKB_ERR_DUPLICATE_SAMPLE: return "Duplicate sample value. (TSK_ERR_DUPLICATE_SAMPLE)";
         case TSKB_ERR_BAD_SAMPLES: return "The nodes provided are not samples. (TSK_ERR_BAD_SAMPLES)";
         case TSKB_ERR_BAD_NUM_WINDOWS: return "Must have at least one window, [0, L]. (TSK_ERR_BAD_NUM_WINDOWS)";
@@ -766,7 +788,10 @@ int tskb_treeseq_sample_count_stat_tabulated(const tskb_treeseq_t *self,
     uint64_t num_sample_sets, const uint64_t *sample_set_sizes, const int32_t *sample_sets,
     uint64_t result_dim, uint64_t table_rows, const double *f_table, uint64_t num_windows,
     const double *windows, uint32_t options, double *result) {
-    if (f_table == nullptr || (num_sample_sets == 1 && table_rows < sample_set_sizes[0] + 1)) {
+    if (f_table == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    // the table must cover every count of the set; the sample-set arguments themselves are checked
+    // (null pointers, K, empty sets ...) by sample_count_stat in the reference's precedence
+    if (num_sample_sets == 1 && sample_set_sizes != nullptr && table_rows < sample_set_sizes[0] + 1) {
         return TSKB_ERR_BAD_PARAM_VALUE;
     }
     return sample_count_stat(self, STAT_TABULATED, num_sample_sets, sample_set_sizes,

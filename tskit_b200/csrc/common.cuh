@@ -95,12 +95,17 @@ struct Arena {
             if (base) cudaFree(base);
             base = nullptr; cap = 0;
         }
+        off = 0;
         if (high > cap) {
             if (base) { cudaDeviceSynchronize(); cudaFree(base); base = nullptr; }
-            cap = high + (high >> 3) + (1 << 20);
-            TSKB_CK(cudaMalloc(&base, cap));
+            cap = 0;
+            const size_t want = high + (high >> 3) + (1 << 20);
+            high = 0;
+            char *q = nullptr;
+            TSKB_CK(cudaMalloc(&q, want));  // on failure the arena stays empty and consistent
+            base = q;
+            cap = want;
         }
-        off = 0;
         high = 0;
     }
     template <typename T>

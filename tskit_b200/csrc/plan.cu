@@ -544,6 +544,75 @@ __global__ void k_mut_src(const int32_t *mut_site, const int32_t *mut_node, uint
     mut_src[m] = (int32_t) (lo + upper_bound_dev(pc_x + lo, n, x) - 1);
 }
 
+// ------------------------------------------------------------ table integrity
+// The checks of tsk_table_collection_check_integrity (c/tskit/tables.c:10362-10640, 10894-10930)
+// that this path relies on -- every id it later uses as an index, every interval, the node time
+// ordering -- in the reference's order: nodes, edges, sites, mutations, indexes; within a table the
+// first failing row, within a row the first failing check.  key = table << 56 | row << 8 | check.
+enum : uint32_t { CK_NODE_TIME = 0, CK_NULL_PARENT, CK_PARENT_BOUNDS, CK_NULL_CHILD, CK_CHILD_BOUNDS,
+    CK_COORDS, CK_LEFT, CK_RIGHT, CK_INTERVAL, CK_TIME_ORDER, CK_SITE_POS, CK_SITE_UNSORTED, CK_SITE_DUP,
+    CK_MUT_SITE, CK_MUT_NODE, CK_MUT_PARENT_BOUNDS, CK_MUT_PARENT_EQUAL, CK_MUT_PARENT_AFTER,
+    CK_MUT_PARENT_SITE, CK_MUT_UNSORTED, CK_INDEX };
+
+__device__ __forceinline__ void ck_fail(unsigned long long *key, uint32_t table, uint64_t row, uint32_t check) {
+    atomicMin(key, ((unsigned long long) table << 56) | ((unsigned long long) row << 8) | check);
+}
+
+__global__ void k_check_nodes_edges(uint32_t N, const double *time, uint32_t E, const double *el,
+    const double *er, const int32_t *ep, const int32_t *ec, const int32_t *I, const int32_t *O, double L,
+    unsigned long long *key) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < N && !isfinite(time[j])) ck_fail(key, 0, j, CK_NODE_TIME);
+    if (j >= E) return;
+    const int32_t p = ep[j], c = ec[j];
+    const double l = el[j], r = er[j];
+    if (p == -1) ck_fail(key, 1, j, CK_NULL_PARENT);
+    else if (p < 0 || (uint32_t) p >= N) ck_fail(key, 1, j, CK_PARENT_BOUNDS);
+    else if (c == -1) ck_fail(key, 1, j, CK_NULL_CHILD);
+    else if (c < 0 || (uint32_t) c >= N) ck_fail(key, 1, j, CK_CHILD_BOUNDS);
+    else if (!(isfinite(l) && isfinite(r))) ck_fail(key, 1, j, CK_COORDS);
+    else if (l < 0) ck_fail(key, 1, j, CK_LEFT);
+    else if (r > L) ck_fail(key, 1, j, CK_RIGHT);
+    else if (l >= r) ck_fail(key, 1, j, CK_INTERVAL);
+    else if (time[c] >= time[p]) ck_fail(key, 1, j, CK_TIME_ORDER);
+    if (I[j] < 0 || (uint32_t) I[j] >= E || O[j] < 0 || (uint32_t) O[j] >= E) ck_fail(key, 4, j, CK_INDEX);
+}
+
+__global__ void k_check_sites_mutations(uint32_t N, uint32_t S, const double *pos, double L, uint32_t Mu,
+    const int32_t *msite, const int32_t *mnode, const int32_t *mparent, unsigned long long *key) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < S) {
+        const double x = pos[j];
+        if (!isfinite(x) || x < 0 || x >= L) ck_fail(key, 2, j, CK_SITE_POS);
+        else if (j > 0 && pos[j - 1] == x) ck_fail(key, 2, j, CK_SITE_DUP);
+        else if (j > 0 && pos[j - 1] > x) ck_fail(key, 2, j, CK_SITE_UNSORTED);
+    }
+    if (j >= Mu) return;
+    const int32_t st = msite[j], nd = mnode[j], pm = mparent != nullptr ? mparent[j] : -1;
+    if (st < 0 || (uint32_t) st >= S) ck_fail(key, 3, j, CK_MUT_SITE);
+    else if (nd < 0 || (uint32_t) nd >= N) ck_fail(key, 3, j, CK_MUT_NODE);
+    else if (pm < -1 || (pm >= 0 && (uint32_t) pm >= Mu)) ck_fail(key, 3, j, CK_MUT_PARENT_BOUNDS);
+    else if (pm == (int32_t) j) ck_fail(key, 3, j, CK_MUT_PARENT_EQUAL);
+    else if (pm > (int32_t) j) ck_fail(key, 3, j, CK_MUT_PARENT_AFTER);
+    else if (pm >= 0 && msite[pm] != st) ck_fail(key, 3, j, CK_MUT_PARENT_SITE);
+    else if (j > 0 && msite[j - 1] > st) ck_fail(key, 3, j, CK_MUT_UNSORTED);
+}
+
+int check_code(unsigned long long key) {
+    static const int codes[] = { -210 /*TIME_NONFINITE*/, -300 /*NULL_PARENT*/, -202, -301 /*NULL_CHILD*/, -202,
+        -211 /*GENOME_COORDS_NONFINITE*/, -310 /*LEFT_LESS_ZERO*/, -309 /*RIGHT_GREATER_SEQ_LENGTH*/,
+        -307 /*BAD_EDGE_INTERVAL*/, -306 /*BAD_NODE_TIME_ORDERING*/, -402 /*BAD_SITE_POSITION*/,
+        -400 /*UNSORTED_SITES*/, -401 /*DUPLICATE_SITE_POSITION*/, -205 /*SITE_OUT_OF_BOUNDS*/, -202,
+        -206 /*MUTATION_OUT_OF_BOUNDS*/, -501 /*MUTATION_PARENT_EQUAL*/, -502 /*MUTATION_PARENT_AFTER_CHILD*/,
+        -500 /*MUTATION_PARENT_DIFFERENT_SITE*/, -504 /*UNSORTED_MUTATIONS*/, -203 /*EDGE_OUT_OF_BOUNDS*/ };
+    return codes[key & 0xffu];
+}
+
+// sum of a uint32 array in 64 bits (the 32-bit scans below must not wrap unnoticed)
+struct U32ToU64 {
+    __host__ __device__ uint64_t operator()(uint32_t x) const { return (uint64_t) x; }
+};
+
 // ------------------------------------------------------------ CUB wrappers
 
 struct Temp {
@@ -559,6 +628,20 @@ struct Temp {
         return p;
     }
 };
+
+uint64_t sum_u64(Temp &tmp, const uint32_t *p, size_t n, cudaStream_t s) {
+    if (n == 0) return 0;
+    DevArray<uint64_t> out;
+    out.alloc(1);
+    cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(p, U32ToU64());
+    size_t bytes = 0;
+    TSKB_CK(cub::DeviceReduce::Sum(nullptr, bytes, it, out.p, (int64_t) n, s));
+    TSKB_CK(cub::DeviceReduce::Sum(tmp.need(bytes), bytes, it, out.p, (int64_t) n, s));
+    uint64_t h = 0;
+    TSKB_CK(cudaMemcpyAsync(&h, out.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    TSKB_CK(cudaStreamSynchronize(s));
+    return h;
+}
 
 template <typename K, typename Vt>
 void sort_pairs(Temp &tmp, const K *kin, K *kout, const Vt *vin, Vt *vout, uint32_t n, int end_bit,
@@ -611,6 +694,18 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     P.time_uncalibrated = t->time_uncalibrated;
     const uint32_t N = (uint32_t) P.N, E = (uint32_t) P.E;
     const double a = range_left, b = range_right;
+    // TSKB_TIMING=1: wall time of every staging phase, to stderr (the stream is drained at each mark)
+    const bool timing = getenv("TSKB_TIMING") != nullptr;
+    auto t_mark = t_start;
+    auto mark = [&](const char *what) {
+        if (!timing) return;
+        cudaStreamSynchronize(s);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "tskb init: %-28s %8.2f ms\n", what,
+            std::chrono::duration<double, std::milli>(now - t_mark).count());
+        t_mark = now;
+    };
+    mark("context + stream");
 
     // samples / sample_index_map exactly as init_nodes (trees.c:404-453)
     P.sample_index_map.assign(N, -1);
@@ -634,7 +729,51 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     ec.upload(t->edge_child, E, s);
     dI.upload(t->edge_insertion_order, E, s);
     dO.upload(t->edge_removal_order, E, s);
+    P.site_pos.upload(t->site_position, P.S, s);
+    P.mut_node.upload(t->mutation_node, P.Mu, s);
+    DevArray<int32_t> d_msite;
+    d_msite.upload(t->mutation_site, P.Mu, s);
 
+    mark("host loops + table upload");
+    // ---- table integrity, before anything is used as an index on the host or the device
+    {
+        if (!(P.L > 0)) throw (int) -701;  // TSK_ERR_BAD_SEQUENCE_LENGTH
+        if (P.N >= 0x7fffffffull || P.E >= 0x7fffffffull || P.S >= 0x7fffffffull || P.Mu >= 0x7fffffffull) {
+            throw (int) TSKB_ERR_UNSUPPORTED;  // tsk_id_t rows
+        }
+        DevArray<unsigned long long> key;
+        DevArray<int32_t> d_mpar;
+        key.alloc(1);
+        TSKB_CK(cudaMemsetAsync(key.p, 0xff, sizeof(unsigned long long), s));
+        if (t->mutation_parent != nullptr) d_mpar.upload(t->mutation_parent, P.Mu, s);
+        const uint32_t S = (uint32_t) P.S, Mu = (uint32_t) P.Mu;
+        if (std::max(N, E)) {
+            k_check_nodes_edges<<<grid_for(std::max(N, E), TB), TB, 0, s>>>(N, P.time.p, E, el.p, er.p, ep.p,
+                ec.p, dI.p, dO.p, P.L, key.p);
+            TSKB_CK_LAUNCH();
+        }
+        if (std::max(S, Mu)) {
+            k_check_sites_mutations<<<grid_for(std::max(S, Mu), TB), TB, 0, s>>>(N, S, P.site_pos.p, P.L, Mu,
+                d_msite.p, P.mut_node.p, d_mpar.p, key.p);
+            TSKB_CK_LAUNCH();
+        }
+        unsigned long long h_key = 0;
+        TSKB_CK(cudaMemcpyAsync(&h_key, key.p, sizeof(h_key), cudaMemcpyDeviceToHost, s));
+        TSKB_CK(cudaStreamSynchronize(s));
+        if (h_key != ~0ull) throw (int) check_code(h_key);
+        // ragged columns (host only): offsets start at 0 and never decrease (TSK_ERR_BAD_OFFSET)
+        for (int col = 0; col < 2; col++) {
+            const uint64_t *off = col == 0 ? t->site_ancestral_state_offset : t->mutation_derived_state_offset;
+            const uint64_t rows = col == 0 ? P.S : P.Mu;
+            if (rows == 0) continue;
+            if (off == nullptr || off[0] != 0) throw (int) -200;
+            for (uint64_t j = 0; j < rows; j++) {
+                if (off[j + 1] < off[j]) throw (int) -200;
+            }
+        }
+    }
+
+    mark("integrity checks");
     // ---- event lists (host binary searches over the borrowed host columns)
     const uint32_t i0 = host_upper_bound_indexed(t->edge_left, t->edge_insertion_order, E, a);
     const uint32_t i1 = host_lower_bound_indexed(t->edge_left, t->edge_insertion_order, E, b);
@@ -713,6 +852,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         }
     }
 
+    mark("event lists + order check");
     // ---- child-major CSR over all edges, sorted by (child, left)
     P.coff.alloc(N + 1);
     P.csr_left.alloc(E); P.csr_right.alloc(E); P.csr_parent.alloc(E);
@@ -732,6 +872,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK(cudaStreamSynchronize(s));
     }
 
+    mark("child-major CSR");
     // ---- chains: count, scan, fill
     P.voff.alloc(nev + 1);
     uint32_t V = 0;
@@ -743,6 +884,10 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
             k_chain_count<<<grid_for(nev, TB), TB, 0, s>>>(ev_parent.p, P.ev_pos.p, nev, a,
                 P.coff.p, P.csr_left.p, P.csr_right.p, P.csr_parent.p, cnt.p);
             TSKB_CK_LAUNCH();
+        }
+        // the scan below is 32-bit: refuse (instead of wrapping) when the visits do not fit
+        if (sum_u64(tmp, cnt.p, (size_t) nev + 1, s) + nev + N >= 0xffffffffull) {
+            throw (int) TSKB_ERR_UNSUPPORTED;  // 32-bit piece indexes; shard the genome instead
         }
         size_t bytes = 0;
         TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt.p, P.voff.p, nev + 1, s));
@@ -766,6 +911,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     }
     ev_parent.release();
 
+    mark("chains");
     // ---- breakpoint index of every event (distinct event positions)
     DevArray<uint32_t> ev_bp;
     ev_bp.alloc(nev + 1);
@@ -789,6 +935,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK_LAUNCH();
     }
 
+    mark("breakpoints");
     // ---- dependency levels: level[parent] > level[child] over every edge
     P.level.alloc(N);
     TSKB_CK(cudaMemsetAsync(P.level.p, 0, N * sizeof(uint32_t), s));
@@ -822,6 +969,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     }
     P.nlevels = max_level + 1;
 
+    mark("node levels");
     // ---- node rank: nodes sorted by (level, id)
     DevArray<uint32_t> rank, lvl_rank_off;
     rank.alloc(N);
@@ -844,6 +992,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK(cudaStreamSynchronize(s));
     }
 
+    mark("node rank");
     // ---- node-major order of the entries (CHILD entries + visits), pieces
     const uint32_t Ve = V + nev;
     DevArray<uint32_t> sorted_e, sorted_key, em_ev, noff, endflag, endscan, inv, poff;
@@ -924,6 +1073,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     ev_sbl.release(); vis_bl.release(); inv.release(); em_ev.release(); sorted_e.release();
     ev_bp.release(); endflag.release(); sorted_key.release(); endscan.release(); noff.release();
 
+    mark("entries + pieces");
     // ---- parent-major edge CSR (children of a node at a position; also used by the decode)
     P.pm_off.alloc(N + 1); P.pm_left.alloc(E); P.pm_right.alloc(E); P.pm_pmax.alloc(E);
     P.pm_child.alloc(E);
@@ -955,19 +1105,16 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK(cudaStreamSynchronize(s));
     }
 
+    mark("parent-major CSR");
     // ---- mutations: the (node-major) piece holding state[mutation.node] at the site; needed pieces
     DevArray<uint8_t> needed;
     needed.alloc((size_t) P.P + 1);
     P.all_pieces = (options & TSKB_INIT_NODE_MODE) != 0;
     k_needed_branch<<<grid_for(P.P, TB), TB, 0, s>>>(P.P, pc_x.p, pc_bl.p, P.all_pieces ? 1 : 0, needed.p);
     TSKB_CK_LAUNCH();
-    P.site_pos.upload(t->site_position, P.S, s);
-    P.mut_node.upload(t->mutation_node, P.Mu, s);
     P.mut_src.alloc(P.Mu);
     if (P.Mu) {
         const uint32_t Mu = (uint32_t) P.Mu;
-        DevArray<int32_t> d_msite;
-        d_msite.upload(t->mutation_site, Mu, s);
         k_mut_src<<<grid_for(Mu, TB), TB, 0, s>>>(d_msite.p, P.mut_node.p, Mu, P.site_pos.p, rank.p,
             poff.p, pc_x.p, P.mut_src.p);
         k_needed_mutation<<<grid_for(Mu, TB), TB, 0, s>>>(Mu, P.mut_src.p, pc_x.p, needed.p);
@@ -975,6 +1122,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK(cudaStreamSynchronize(s));
     }
 
+    mark("mutation sources");
     // ---- references of every piece, heights, processing order
     DevArray<uint32_t> perm;  // node-major piece -> state slot
     {
@@ -994,6 +1142,9 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
             P.rank_node.p, rank.p, is_sample.p, poff.p, P.pm_off.p, P.pm_left.p, P.pm_right.p,
             P.pm_pmax.p, P.pm_child.p, cnt.p, nullptr, nullptr);
         TSKB_CK_LAUNCH();
+        if (sum_u64(tmp, cnt.p, (size_t) Pn + 1, s) >= 0xfffffff0ull) {
+            throw (int) TSKB_ERR_UNSUPPORTED;  // 32-bit reference offsets; shard the genome instead
+        }
         size_t bytes = 0;
         TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt.p, ch_off.p, (size_t) Pn + 1, s));
         TSKB_CK(cub::DeviceScan::ExclusiveSum(tmp.need(bytes), bytes, cnt.p, ch_off.p, (size_t) Pn + 1, s));
@@ -1145,6 +1296,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
         TSKB_CK(cudaStreamSynchronize(s));
     }
 
+    mark("references + heights + order");
     // ---- sites and mutations: allele strings -> small integer codes on the host
     // (replaces the memcmp loops of get_allele_weights, trees.c:1557-1596)
     {
@@ -1202,6 +1354,7 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     }
     TSKB_CK(cudaStreamSynchronize(s));
 
+    mark("allele codes");
     P.stats.num_events = nev;
     P.stats.num_visits = V;
     P.stats.num_levels = P.nheights;

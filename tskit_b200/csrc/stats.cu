@@ -484,6 +484,94 @@ __global__ void __launch_bounds__(SUM_TB) k_branch_summary(uint32_t npp,
     }
 }
 
+// ---- thread-contiguous variant (default): a thread holds SUMC_IPT consecutive pieces of the processing
+// order, fetched with 16-byte loads, and merges the reductions of abutting pieces in its own registers;
+// only the boundary between two lanes goes through the shuffle network (4 SHFL per 4 pieces instead
+// of 6 per piece: the shuffles share the MIO queue with the reductions).  Same reductions, same
+// addresses and values as pieces_to_deltas.
+#ifndef TSKB_SUMC_TB
+#define TSKB_SUMC_TB 256
+#endif
+constexpr int SUMC_TB = TSKB_SUMC_TB;
+constexpr int SUMC_IPT = 4;
+
+template <class V>
+struct Quad {
+    V st[SUMC_IPT];
+    double bl[SUMC_IPT];
+    uint32_t bp0[SUMC_IPT], bp1[SUMC_IPT];
+    __device__ __forceinline__ void load(uint32_t qd, const uint32_t *__restrict__ q_bp0,
+        const uint32_t *__restrict__ q_bp1, const double *__restrict__ q_bl, const V *__restrict__ pval) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(q_bp0) + qd);
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(q_bp1) + qd);
+        bp0[0] = a.x; bp0[1] = a.y; bp0[2] = a.z; bp0[3] = a.w;
+        bp1[0] = b.x; bp1[1] = b.y; bp1[2] = b.z; bp1[3] = b.w;
+        const double2 l0 = __ldg(reinterpret_cast<const double2 *>(q_bl) + 2 * (size_t) qd);
+        const double2 l1 = __ldg(reinterpret_cast<const double2 *>(q_bl) + 2 * (size_t) qd + 1);
+        bl[0] = l0.x; bl[1] = l0.y; bl[2] = l1.x; bl[3] = l1.y;
+        constexpr int NQ = (int) (sizeof(V) * SUMC_IPT / 16);
+        union { V s[SUMC_IPT]; int4 q[NQ]; } u;
+        const int4 *src = reinterpret_cast<const int4 *>(pval + (size_t) qd * SUMC_IPT);
+#pragma unroll
+        for (int i = 0; i < NQ; i++) u.q[i] = src[i];
+#pragma unroll
+        for (int i = 0; i < SUMC_IPT; i++) st[i] = u.s[i];
+    }
+};
+
+template <int STAT, class V>
+__global__ void __launch_bounds__(SUMC_TB) k_branch_summary_c4(uint32_t npp,
+    const uint32_t *__restrict__ q_bp0, const uint32_t *__restrict__ q_bp1,
+    const double *__restrict__ q_bl, const V *__restrict__ pval, SumP sp, V totals,
+    DeltaOut out, uint32_t m0, uint32_t m1) {
+    // npp is a multiple of PROP_TILE = 1024: whole warps of quads, no bounds checks
+    const uint32_t nquads = npp / SUMC_IPT;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const ColP first_col = out.cols[m0];
+    uint32_t qd = blockIdx.x * blockDim.x + threadIdx.x;
+    Quad<V> cur, nxt;
+    if (qd < nquads) cur.load(qd, q_bp0, q_bp1, q_bl, pval);
+    for (; qd < nquads; qd += stride) {
+        const uint32_t qn = qd + stride;
+        if (qn < nquads) nxt.load(qn, q_bp0, q_bp1, q_bl, pval);
+        bool valid[SUMC_IPT], live[SUMC_IPT];
+#pragma unroll
+        for (int q = 0; q < SUMC_IPT; q++) {
+            valid[q] = cur.bp1[q] != NO_PIECE;
+            live[q] = valid[q] && !(sp.skip_zero_bl && cur.bl[q] == 0.0);
+        }
+        // the neighbouring lanes' abutting pieces; padding has bp0 = 0 and bp1 = NO_PIECE, which never
+        // match a real piece's bp1 >= 1 and bp0 <= T
+        uint32_t prev_bp1 = __shfl_up_sync(0xffffffffu, cur.bp1[SUMC_IPT - 1], 1);
+        uint32_t next_bp0 = __shfl_down_sync(0xffffffffu, cur.bp0[0], 1);
+        if (lane == 0u) prev_bp1 = NO_PIECE;
+        if (lane == 31u) next_bp0 = NO_PIECE;
+        for (uint32_t m = m0; m < m1; m++) {
+            const ColP col = m == m0 ? first_col : out.cols[m];
+            double *Dm = out.D + (size_t) (m - m0) * out.Tp1;
+            double G[SUMC_IPT];
+#pragma unroll
+            for (int q = 0; q < SUMC_IPT; q++) {
+                G[q] = live[q] ? cur.bl[q] * F_branch<STAT, V>(sp, col, m, cur.st[q], totals) : 0.0;
+            }
+            const double G_left = __shfl_up_sync(0xffffffffu, G[SUMC_IPT - 1], 1);
+#pragma unroll
+            for (int q = 0; q < SUMC_IPT; q++) {
+                if (!valid[q]) continue;
+                const bool merged_prev = q == 0 ? prev_bp1 == cur.bp0[0] : cur.bp1[q > 0 ? q - 1 : 0] == cur.bp0[q];
+                const double before = q == 0 ? G_left : G[q > 0 ? q - 1 : 0];
+                const double v = merged_prev ? G[q] - before : G[q];
+                if (v != 0.0) atomicAdd(Dm + cur.bp0[q], v);
+                const bool merged_next = q == SUMC_IPT - 1 ? next_bp0 == cur.bp1[q]
+                                                           : cur.bp0[q < SUMC_IPT - 1 ? q + 1 : q] == cur.bp1[q];
+                if (!merged_next && G[q] != 0.0) atomicAdd(Dm + cur.bp1[q], -G[q]);
+            }
+        }
+        cur = nxt;
+    }
+}
+
 // ---- many result columns: lanes are columns
 // With M columns the kernel above issues M reductions per piece, each lane of an instruction to
 // its own cache line.  Here a warp walks its pieces one after the other and lane m evaluates
@@ -1118,8 +1206,15 @@ void run_branch(CallCtx &c, V *pval, V totals) {
             // than exactly-resident persistent CTAs)
             int mult = std::max(per_sm, 16);
             if (const char *e = getenv("TSKB_SUM_GRID_MULT")) mult = std::max(1, atoi(e));  // experiments
-            k_branch_summary<STAT, V><<<std::min<uint32_t>(ntiles, (uint32_t) (sms * mult)), SUM_TB, 0, c.s>>>(
-                P.npp, P.q_bp0.p, P.q_bp1.p, P.q_bl.p, pval, c.sumP, totals, out, m0, m1);
+            const char *variant = getenv("TSKB_SUM_VARIANT");  // experiments: "lane" = one piece per lane
+            if (variant != nullptr && variant[0] == 'l') {
+                k_branch_summary<STAT, V><<<std::min<uint32_t>(ntiles, (uint32_t) (sms * mult)), SUM_TB, 0, c.s>>>(
+                    P.npp, P.q_bp0.p, P.q_bp1.p, P.q_bl.p, pval, c.sumP, totals, out, m0, m1);
+            } else {
+                const uint32_t nblocks = (P.npp / SUMC_IPT + SUMC_TB - 1) / SUMC_TB;
+                k_branch_summary_c4<STAT, V><<<std::min<uint32_t>(nblocks, (uint32_t) (sms * mult)), SUMC_TB, 0, c.s>>>(
+                    P.npp, P.q_bp0.p, P.q_bp1.p, P.q_bl.p, pval, c.sumP, totals, out, m0, m1);
+            }
             TSKB_CK_LAUNCH();
             c.launches++;
         }

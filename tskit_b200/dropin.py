@@ -115,8 +115,11 @@ if tskit is not None:
         """``tskit.TreeSequence`` whose statistics run on the B200 engine."""
 
         def __init__(self, ll_tree_sequence, device=0, engine=None):
-            self._accel_depth = 0
-            self._accel_lock = threading.Lock()  # divergence_matrix(num_threads>0) calls from a pool
+            # Depth of nested public statistics calls, PER THREAD: only the thread inside a statistics
+            # method sees the proxy; any other thread using the same object concurrently (ts.first(),
+            # ts.variants(), tskit.Tree(ts): C constructors that type-check their argument) keeps
+            # seeing the real _tskit.TreeSequence.
+            self._accel_tls = threading.local()
             self._accel_proxy = None
             self.accel_stats = {"accelerated": 0, "forwarded": 0}
             super().__init__(ll_tree_sequence)
@@ -127,7 +130,7 @@ if tskit is not None:
 
         @property
         def _ll_tree_sequence(self):
-            if self._accel_depth > 0 and self._accel_proxy is not None:
+            if self._accel_proxy is not None and getattr(self._accel_tls, "depth", 0) > 0:
                 return self._accel_proxy
             return self._ll_real
 
@@ -136,13 +139,17 @@ if tskit is not None:
             self._ll_real = value
 
         def _accel_call(self, name, args, kwargs):
-            with self._accel_lock:
-                self._accel_depth += 1
+            tls = self._accel_tls
+            tls.depth = getattr(tls, "depth", 0) + 1
             try:
+                if name in ("divergence_matrix", "genetic_relatedness_matrix") and kwargs.get("num_threads"):
+                    # the reference splits the windows / trees over a thread pool whose workers look
+                    # the low-level object up themselves (trees.py:8671-8706); one device call does
+                    # the whole job, so the chunking is dropped ("Threading")
+                    kwargs = dict(kwargs, num_threads=0)
                 return getattr(super(), name)(*args, **kwargs)
             finally:
-                with self._accel_lock:
-                    self._accel_depth -= 1
+                tls.depth -= 1
 
         def __reduce__(self):
             return (_unpickle, (super().__reduce__(),))

@@ -303,6 +303,10 @@ class LLTreeSequence:
         members = samples[W[:, 0] == 1].astype(np.int32)
         sizes = np.array([len(members)], dtype=np.uint64)
         n = len(members)
+        if n == 0:
+            # the reference accepts an all-zero weight column (every state is 0); as a sample set it
+            # would be TSK_ERR_EMPTY_SAMPLE_SET, so this call is handed back to the reference
+            raise LibraryError(-20003, "general_stat with an all-zero weight column is not accelerated")
         table = np.empty((n + 1, output_dim), dtype=np.float64)
         for c in range(n + 1):
             y = np.asarray(summary_func(np.array([float(c)])), dtype=np.float64)
