@@ -7,10 +7,17 @@ One step = one diversity call (1 sample set) + one divergence call (2 sample set
 sweeps, i.e. 2 x num_edge_diffs edge diffs.  Metric: edge-diffs/s (whole job).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--small]
+                  [--config c2|c3]
 
-N > 1 is launched by torchrun, one rank per GPU.  Windows (genome) shard naturally: every rank
-owns one 100 Mb chromosome-sized shard of windows (weak scaling) and the per-window results are
-gathered with one NCCL all_gather; there is no collective on the data path.
+N > 1 (launched by torchrun, one rank per GPU) is weak scaling over GENOME SHARDS of one tree
+sequence: the genome is N x 100 Mb (the C2 ARG repeated along the genome, tskit_b200.sim.
+repeat_genome: N unlinked chromosomes over the same 100k samples, N x 10^7 edges, N x 1000
+windows), tskit_b200.sharding.plan_shards cuts it into N ranges of equal edge-diff count, every
+rank stages only its range (tskb_treeseq_init(range_left, range_right) on the rows meeting it)
+and computes un-normalised per-window partials; ONE all_reduce (NCCL) of the device-resident
+W x M partials per statistic, INSIDE the timed region, gives every rank the whole result.
+--config c3 runs BASELINE.json configs[2] (f2/f3/f4 + Fst over 8 sample sets, 10^6 samples,
+1 Gb) as a strong-scaling study over the same sharding (see run_c3).
 """
 import argparse
 import json
@@ -25,8 +32,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from tskit_b200.sim import add_mutations, wright_fisher  # noqa: E402
+from tskit_b200.sim import add_mutations, repeat_genome, wright_fisher  # noqa: E402
 from tskit_b200.tables import Tables  # noqa: E402
+
+METRIC = "edge-diffs/s (branch-mode general stat: diversity + 2-set divergence, windowed)"
+UNIT = "edge-diffs/s"
+RTOL = 1e-9  # north_star: fp64 statistics within relative 1e-9 of the C reference
 
 CONFIGS = {
     # name: (samples, generations, L, crossovers per meiosis, mutation draws, windows)
@@ -75,10 +86,11 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.index)],
+                 "-lms", "50", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            time.sleep(0.3)  # first samples arrive before the timed region starts
         except Exception:
             self.proc = None
 
@@ -91,7 +103,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -99,6 +111,7 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
@@ -107,7 +120,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 def measured_traffic(kernel):
@@ -117,8 +130,12 @@ def measured_traffic(kernel):
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
-    key = {"sweep": "k_sweep<SVec<int, 1>>", "summary": "k_branch_summary<0, SVec<int, 1>>"}.get(kernel)
-    return d.get(key)
+    for key in {"sweep": ("k_sweep<SVec<int, 1>>",),
+                "summary": ("k_branch_summary_c4<0, SVec<int, 1>>", "k_branch_summary<0, SVec<int, 1>>")
+                }.get(kernel, ()):
+        if key in d:
+            return d[key]
+    return None
 
 
 def peaks():
@@ -128,18 +145,46 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# ------------------------------------------------------------------ reference arm
+def workload_name(name, t, W, copies=1):
+    rep = "" if copies == 1 else f" x {copies} along the genome (one tree sequence, genome-sharded)"
+    return (f"{name}: branch diversity + divergence, n={t.num_samples}, L={t.sequence_length:.0f}, "
+            f"E={t.num_edges}, N={t.num_nodes}, {W} windows{rep}")
 
-def reference_step_fn(t, W):
-    """The reference's own C implementation (oracle/_ref) of one sweep: branch diversity."""
-    from oracle import ref
-    r = ref.RefTreeSequence(t)
+
+def rel_err(got, want):
+    """Largest |got - want| / |want| over the entries (0 where both are 0; inf where only one is
+    finite or they differ in NaN-ness)."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    if got.shape != want.shape:
+        return float("inf")
+    bad = np.isnan(got) != np.isnan(want)
+    if bad.any():
+        return float("inf")
+    m = ~np.isnan(want)
+    d = np.abs(got[m] - want[m])
+    den = np.abs(want[m])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = np.where(d == 0, 0.0, d / den)
+    return float(r.max()) if r.size else 0.0
+
+
+# ------------------------------------------------------------------ the reference (checker / CPU arm)
+
+def reference_step(r, t, W):
+    """One step of the workload on the reference's own C implementation (oracle/_ref):
+    tsk_treeseq_diversity (trees.c:3950) + tsk_treeseq_divergence (trees.c:4711), branch mode."""
     s = t.samples
+    n = len(s)
     windows = np.linspace(0, t.sequence_length, W + 1)
+    a = r.one_way("diversity", [s], windows=windows, mode="branch")
+    b = r.k_way("divergence", [s[: n // 2], s[n // 2:]], [[0, 1]], windows=windows, mode="branch")
+    return a, b
 
-    def one():
-        return r.one_way("diversity", [s], windows=windows, mode="branch")
-    return one, r
+
+def edge_diffs_per_sweep(t):
+    """Edge diffs of one sweep exactly as the reference replays them (trees.c:1424-1507): every edge
+    inserted, every edge that ends before L removed."""
+    return int(t.num_edges + np.count_nonzero(t.edges_right < t.sequence_length))
 
 
 def run_reference(args):
@@ -153,54 +198,69 @@ def run_reference(args):
         return
     name = "small" if args.small else "c2"
     t, W, _ = load_workload(name)
-    one, r = reference_step_fn(t, W)
-    # edge diffs per sweep, exactly as the reference counts them: edges removed before L + inserted
-    nev = int(t.num_edges + np.count_nonzero(t.edges_right < t.sequence_length))
+    r = ref.RefTreeSequence(t)
+    nev = edge_diffs_per_sweep(t)
     cores = os.cpu_count() or 1
     pool = ThreadPoolExecutor(cores)
 
     def step():
-        # every host thread runs one full sweep (the reference path is single-threaded and
-        # re-entrant on a const tree sequence; ctypes releases the GIL)
-        list(pool.map(lambda _: one(), range(cores)))
+        # every host thread runs one full step (the reference path is single-threaded and re-entrant on
+        # a const tree sequence; ctypes releases the GIL): the same two calls as the GPU arm's step
+        list(pool.map(lambda _: reference_step(r, t, W), range(cores)))
 
-    for _ in range(min(args.warmup, 1)):
+    budget_s = 240.0  # the whole run stays within a few minutes
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    warmup = max(0, min(args.warmup, int(budget_s * 0.2 / first)))
+    steps = max(1, min(args.steps, int(budget_s * 0.8 / first)))
+    for _ in range(max(0, warmup - 1)):  # the probe step above was the first warm-up step
         step()
-    steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    value = cores * nev * steps / dt
-    unit = "edge-diffs/s"
-    print(json.dumps({
-        "impl": "reference", "metric": "branch-mode general-stat throughput", "value": value,
-        "unit": unit, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
-        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+    value = cores * 2 * nev * steps / dt
+    note = None
+    if steps != args.steps or warmup != args.warmup:
+        note = (f"one step = {first:.1f} s on {cores} threads: --steps {args.steps} --warmup {args.warmup} "
+                f"bounded to {steps} / {max(warmup, 1)} to stay within {budget_s:.0f} s")
+    copies = max(1, args.gpus)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": max(warmup, 1), "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
         "config": {"workload": workload_name(name, t, W),
-                   "step": "one branch-diversity sweep per host thread (bounded sample: "
-                           "1 of the 2 sweeps of the GPU arm's step)"},
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "reference",
-                         "sample": f"{steps} steps x {cores} concurrent full sweeps of "
-                                   "tsk_treeseq_diversity (branch, 1000 windows)"},
-        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
-
-
-def workload_name(name, t, W):
-    return (f"{name}: branch diversity + divergence, n={t.num_samples}, L={t.sequence_length:.0f}, "
-            f"E={t.num_edges}, N={t.num_nodes}, {W} windows")
+                   "step": "diversity(branch, 1 set) + divergence(branch, 2 sets): 2 sweeps, one "
+                           "full step per host thread, all threads concurrently",
+                   "edge_diffs_per_sweep": nev},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": f"{steps} steps x {cores} concurrent full steps of "
+                                   f"tsk_treeseq_diversity + tsk_treeseq_divergence (branch, {W} windows) "
+                                   f"on the {name} ARG"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    if copies > 1:
+        line["config"]["sample_note"] = (
+            f"the GPU arm at {copies} GPUs runs this ARG repeated {copies} x along the genome; the "
+            "reference's rate per edge diff does not depend on the genome length, so the bounded "
+            "sample is one copy")
+    if note:
+        line["config"]["steps_note"] = note
+    print(json.dumps(line))
 
 
 # ------------------------------------------------------------------ our arm
 
 def run_ours(args):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
-    from tskit_b200 import _lib
-    from tskit_b200.lowlevel import LLTreeSequence, STAT_BRANCH, STAT_SPAN_NORMALISE
-    import ctypes as C
+
+    from tskit_b200 import _lib, sharding
+    from tskit_b200.lowlevel import STAT_BRANCH, STAT_SPAN_NORMALISE
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,6 +268,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -216,16 +277,24 @@ def run_ours(args):
             dist.barrier()
 
     name = "small" if args.small else "c2"
-    t, W, gen_s = load_workload(name, rank, barrier)
+    base, W1, gen_s = load_workload(name, rank, barrier)
+    t0 = time.perf_counter()
+    t = repeat_genome(base, world)          # world == 1: the C2 ARG itself
+    W = W1 * world
     windows = np.linspace(0, t.sequence_length, W + 1)
+    tile_s = time.perf_counter() - t0
     s = t.samples
     n = len(s)
     t0 = time.perf_counter()
-    ll = LLTreeSequence(t, device=local)
-    stage_s = time.perf_counter() - t0
+    sh = sharding.ShardedTreeSequence(t, windows, rank, world, device=local)
+    stage_s = time.perf_counter() - t0      # plan_shards + restrict_tables + tskb_treeseq_init(range)
+    ll = sh.engine
     st = ll.engine_stats()
-    nev, visits, levels = st["num_events"], st["num_visits"], st["num_levels"]
-    dbar = visits / max(nev, 1)
+    init_s = st["stage_ms"] / 1e3
+    nev_local, visits_local, levels = st["num_events"], st["num_visits"], st["num_levels"]
+    nev_base = edge_diffs_per_sweep(base)
+    nev_total = edge_diffs_per_sweep(t)     # what the reference would replay over the whole genome
+    dbar = visits_local / max(nev_local, 1)
 
     sizes1 = np.array([n], dtype=np.uint64)
     sizes2 = np.array([n // 2, n - n // 2], dtype=np.uint64)
@@ -234,9 +303,9 @@ def run_ours(args):
     L = _lib.lib()
 
     # inputs resident in HBM for the kernel-only number (torch owns the buffers)
-    d_sets = torch.from_numpy(s.copy()).to(f"cuda:{local}")
-    d_res1 = torch.empty(W * 1, dtype=torch.float64, device=f"cuda:{local}")
-    d_res2 = torch.empty(W * 1, dtype=torch.float64, device=f"cuda:{local}")
+    d_sets = torch.from_numpy(s.copy()).to(dev)
+    d_res1 = torch.empty((W, 1), dtype=torch.float64, device=dev)
+    d_res2 = torch.empty((W, 1), dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
 
     def p(a):
@@ -244,43 +313,79 @@ def run_ours(args):
 
     phase_ms = np.zeros(6)
     launches = [0]
+    coll_ev = []
 
     def step_device():
+        """One step with inputs and outputs in HBM; returns the engine's device time (CUDA events on
+        the engine's stream); the collective is timed by events on torch's stream (coll_ev)."""
         ms = 0.0
-        for stat_id, sizes, ntup, tup, out in ((0, sizes1, 0, None, d_res1), (3, sizes2, 1, idx, d_res2)):
-            ret = L.tskb_treeseq_stat_device(ll._h, stat_id, len(sizes), p(sizes),
-                                             C.c_void_p(d_sets.data_ptr()), ntup,
-                                             None if tup is None else p(tup), W, p(windows),
-                                             options, C.c_void_p(out.data_ptr()))
-            if ret != 0:
-                raise RuntimeError(L.tskb_strerror(ret).decode() + L.tskb_last_cuda_error().decode())
+        for nm, sizes, tup, out in (("diversity", sizes1, None, d_res1), ("divergence", sizes2, idx, d_res2)):
+            if world == 1:
+                ll.stat_device(nm, sizes, d_sets.data_ptr(), tup, windows, options, out.data_ptr())
+            else:
+                ll.stat_device(nm, sizes, d_sets.data_ptr(), tup, windows, STAT_BRANCH, out.data_ptr())
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                sharding.combine(out, windows, True)      # all_reduce over NCCL + span normalisation
+                e1.record()
+                coll_ev.append((e0, e1))
             es = ll.engine_stats()
             ms += es["last_call_ms"]
             phase_ms[:] += np.array(es["last_kernel_ms"][:6])
             launches[0] += es["last_launches"]
         return ms
 
-    # pinned host buffers for the end-to-end number through the C ABI
+    # host buffers for the end-to-end number: the reference-facing C ABI at one GPU, the sharded host
+    # API (pinned staging, all_reduce on the device, one read-back) at several
     h_sets = torch.from_numpy(s.copy()).pin_memory()
     h_res1 = torch.empty((W, 1), dtype=torch.float64).pin_memory()
     h_res2 = torch.empty((W, 1), dtype=torch.float64).pin_memory()
     h2d = int(h_sets.numel() * 4 * 2 + (W + 1) * 8 * 2 + idx.nbytes + 16 + 8)
     d2h = int(W * 8 * 2)
+    e2e_out = {}
 
     def step_e2e():
-        for fn, sizes, tup, out in ((L.tskb_treeseq_diversity, sizes1, None, h_res1),
-                                    (L.tskb_treeseq_divergence, sizes2, idx, h_res2)):
-            a = [ll._h, len(sizes), p(sizes), C.c_void_p(h_sets.data_ptr())]
-            if tup is not None:
-                a += [1, p(tup)]
-            a += [W, p(windows), options, C.c_void_p(out.data_ptr())]
-            ret = fn(*a)
-            if ret != 0:
-                raise RuntimeError(L.tskb_strerror(ret).decode())
+        if world == 1:
+            for fn, sizes, tup, out in ((L.tskb_treeseq_diversity, sizes1, None, h_res1),
+                                        (L.tskb_treeseq_divergence, sizes2, idx, h_res2)):
+                a = [ll._h, len(sizes), p(sizes), C.c_void_p(h_sets.data_ptr())]
+                if tup is not None:
+                    a += [1, p(tup)]
+                a += [W, p(windows), options, C.c_void_p(out.data_ptr())]
+                ret = fn(*a)
+                if ret != 0:
+                    raise RuntimeError(L.tskb_strerror(ret).decode())
+            e2e_out["res"] = (h_res1.numpy(), h_res2.numpy())
+        else:
+            a = sh.stat_host("diversity", sizes1, h_sets.numpy(), None, windows, options)
+            b = sh.stat_host("divergence", sizes2, h_sets.numpy(), idx, windows, options)
+            e2e_out["res"] = (a, b)
 
-    for _ in range(max(args.warmup, 3)):
+    def collective_ms():
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in coll_ev)
+        coll_ev.clear()
+        return ms
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_device()
         step_e2e()
+    collective_ms()
+    # calibration: the timed region lasts at least ~1 s (blocks of exactly --steps steps)
+    t0 = time.perf_counter()
+    step_device()
+    torch.cuda.synchronize()
+    one = max(time.perf_counter() - t0, 1e-4)
+    collective_ms()
+    blocks = max(1, int(np.ceil(1.0 / (one * args.steps))))
+    if world > 1:
+        b_t = torch.tensor([blocks], device=dev)
+        dist.all_reduce(b_t, op=dist.ReduceOp.MAX)
+        blocks = int(b_t.item())
+    blocks = min(blocks, 500)
+    if os.environ.get("TSKB_BENCH_BLOCKS"):  # profiler runs: a short timed region
+        blocks = max(1, int(os.environ["TSKB_BENCH_BLOCKS"]))
     phase_ms[:] = 0
     launches[0] = 0
     sampler = ClockSampler(local)
@@ -290,122 +395,299 @@ def run_ours(args):
     torch.cuda.synchronize()
     dev_ms = 0.0
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        dev_ms += step_device()
-    torch.cuda.synchronize()
+    for _ in range(blocks):
+        for _ in range(args.steps):
+            dev_ms += step_device()
+    coll_ms = collective_ms()
+    dev_ms += coll_ms
     wall_dev = time.perf_counter() - t0
     barrier()
     torch.cuda.synchronize()
+    e2e_blocks = max(1, blocks // 2)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_blocks * args.steps):
         step_e2e()
     torch.cuda.synchronize()
     wall_e2e = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    nsteps = blocks * args.steps
+    nsteps_e2e = e2e_blocks * args.steps
 
-    # per-window results of every shard -> all ranks (the only collective on this path)
-    gathered = None
     if world > 1:
-        out = [torch.empty_like(d_res1) for _ in range(world)]
-        dist.all_gather(out, d_res1)
-        gathered = torch.stack(out)
-        times = torch.tensor([dev_ms, wall_e2e, wall_dev], dtype=torch.float64, device=f"cuda:{local}")
+        times = torch.tensor([dev_ms, wall_e2e, wall_dev, coll_ms, stage_s, init_s], dtype=torch.float64,
+                             device=dev)
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        dev_ms, wall_e2e, wall_dev = [float(x) for x in times.cpu()]
+        dev_ms, wall_e2e, wall_dev, coll_ms, stage_s, init_s = [float(x) for x in times.cpu()]
+        counts = torch.tensor([nev_local, visits_local], dtype=torch.float64, device=dev)
+        gathered = [torch.empty_like(counts) for _ in range(world)]
+        dist.all_gather(gathered, counts)
+        nev_ranks = [int(g[0].item()) for g in gathered]
+    else:
+        nev_ranks = [nev_local]
 
     if rank == 0:
         sweeps = 2
-        diffs_per_step = sweeps * nev * world
-        value = diffs_per_step * args.steps / (dev_ms / 1e3)
-        e2e_value = diffs_per_step * args.steps / wall_e2e
+        diffs_per_step = sweeps * nev_total
+        value = diffs_per_step * nsteps / (dev_ms / 1e3)
+        e2e_value = diffs_per_step * nsteps_e2e / wall_e2e
         peak, peak_src = peaks()
         K_avg = 1.5  # one sweep with K = 1 state column and one with K = 2
         b_branch = 28 + dbar * (12 + 8 * K_avg)
-        per_step_ms = phase_ms / args.steps
+        per_step_ms = phase_ms / nsteps
         names = ["weights", "sweep", "summary", "integrate", "idle", "d2h"]
         dom = int(np.argmax(per_step_ms))
-        # algorithmic share of the dominant phase ("Roofline accounting")
-        share = {"sweep": 20 + dbar * (4 + 8 * K_avg), "summary": 8 + dbar * 8}.get(
-            names[dom], b_branch)
-        achieved = share * sweeps * nev / (per_step_ms[dom] / 1e3) / 1e9
-        sweep_achieved = b_branch * sweeps * nev / (dev_ms / args.steps / 1e3) / 1e9
-        cpu = None
+        # algorithmic share of the dominant phase ("Roofline accounting"): per launch =
+        # share x the edge diffs one launch covers (this rank's range), / its mean duration
+        share = {"sweep": 20 + dbar * (4 + 8 * K_avg), "summary": 8 + dbar * 8}.get(names[dom], b_branch)
+        achieved = share * sweeps * nev_local / (per_step_ms[dom] / 1e3) / 1e9
+        step_achieved = b_branch * diffs_per_step / world / (dev_ms / nsteps / 1e3) / 1e9
+
+        # parity of THIS run's result against the reference C library on the same tables
+        got1, got2 = e2e_out["res"]
+        parity, cpu = None, None
         if not args.no_cpu_baseline:
-            cpu = cpu_baseline(t, W, nev)
+            cpu, want = cpu_baseline(base, W1, nev_base, best_of=2 if world == 1 else 1)
+            if want is not None:
+                # every copy of the genome repeats the base ARG: each block of W1 windows is the base result
+                e1 = max(rel_err(got1.reshape(world, W1), np.broadcast_to(want[0].reshape(1, W1), (world, W1))),
+                         rel_err(d_res1.cpu().numpy().reshape(world, W1),
+                                 np.broadcast_to(want[0].reshape(1, W1), (world, W1))))
+                e2 = max(rel_err(got2.reshape(world, W1), np.broadcast_to(want[1].reshape(1, W1), (world, W1))),
+                         rel_err(d_res2.cpu().numpy().reshape(world, W1),
+                                 np.broadcast_to(want[1].reshape(1, W1), (world, W1))))
+                parity = {"max_rel_err": max(e1, e2), "rtol": RTOL, "ok": bool(max(e1, e2) <= RTOL),
+                          "against": "oracle/_ref (reference C library) on the same tables: "
+                                     "tsk_treeseq_diversity + tsk_treeseq_divergence, every window, "
+                                     "device-resident and host-buffer results",
+                          "windows_checked": int(2 * 2 * W)}
+            if world > 1:
+                cpu = None  # the CPU baseline is reported at one GPU only
         line = {
-            "metric": "branch-mode general-stat throughput (edge-diffs/s)", "value": value,
-            "unit": "edge-diffs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": dev_ms / nsteps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": workload_name(name, t, W),
+                "workload": workload_name(name, base, W1, world),
                 "step": "diversity(branch, 1 set) + divergence(branch, 2 sets): 2 sweeps",
-                "edge_diffs_per_sweep": nev, "visits_per_sweep": visits, "d_bar": dbar,
-                "levels": levels, "l2": "inputs larger than L2 (plan arrays %.2f GB)" %
-                                        (st["device_bytes"] / 1e9),
-                "sharding": "one 100 Mb window shard per rank (same synthetic ARG per rank), "
-                            "per-window results all_gathered over NCCL",
-                "stage_s": stage_s, "generate_s": gen_s,
+                "edge_diffs_per_sweep": nev_total, "edge_diffs_per_sweep_by_rank": nev_ranks,
+                "visits_per_sweep_rank0": visits_local, "d_bar": dbar, "levels": levels,
+                "l2": "inputs larger than L2 (plan arrays %.2f GB per rank)" % (st["device_bytes"] / 1e9),
+                "sharding": ("whole genome on one GPU" if world == 1 else
+                             f"genome ranges from sharding.plan_shards, one per rank; per statistic one "
+                             f"all_reduce of {W} x 1 doubles on device-resident partials inside the timed "
+                             f"region ({coll_ms / nsteps:.3f} ms per step incl. waiting for the slowest rank)"),
+                "timed_blocks": blocks, "timed_steps": nsteps, "timed_seconds_device": dev_ms / 1e3,
+                "stage_s": stage_s, "init_s": init_s, "tile_s": tile_s, "generate_s": gen_s,
                 "phase_ms_per_step": dict(zip(names, [float(x) for x in per_step_ms])),
-                "wall_ms_per_step_device_inputs": wall_dev / args.steps * 1e3,
+                "collective_ms_per_step": coll_ms / nsteps,
+                "wall_ms_per_step_device_inputs": wall_dev / nsteps * 1e3,
             },
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "edge-diffs/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": wall_e2e / args.steps * 1e3,
-                    "cold_including_staging_value": diffs_per_step /
-                    (world * stage_s + wall_e2e / args.steps)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": wall_e2e / nsteps_e2e * 1e3,
+                    "steps": nsteps_e2e,
+                    "through": ("tskb_treeseq_diversity / tskb_treeseq_divergence (C ABI, host pointers)"
+                                if world == 1 else "sharding.ShardedTreeSequence.stat_host (pinned "
+                                "staging, all_reduce on the device, one read-back)"),
+                    "cold_including_staging_value": diffs_per_step / (stage_s + wall_e2e / nsteps_e2e)},
             "gpu_launches": int(launches[0]),
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(names[dom]),
                          "traffic_note": "bytes per launch of the K=1 instantiation, ncu capture under profiles/",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_edge_diff": share,
-                         "whole_sweep": {"achieved": sweep_achieved, "frac": sweep_achieved / peak,
-                                         "algorithmic_bytes_per_edge_diff": b_branch}},
+                         "whole_step": {"achieved": step_achieved, "frac": step_achieved / peak,
+                                        "algorithmic_bytes_per_edge_diff": b_branch}},
+            "parity": parity,
             "cpu_baseline": cpu,
         }
-        if gathered is not None:
-            line["config"]["gathered_shape"] = list(gathered.shape)
+        if world == 1 and not args.no_secondary:
+            try:
+                line["site_and_matrix"] = secondary(ll, base, W1, args)
+            except Exception as e:  # the headline line is still printed
+                line["site_and_matrix"] = {"error": repr(e)}
         print(json.dumps(line))
+        if parity is not None and not parity["ok"]:
+            if world > 1:
+                dist.destroy_process_group()
+            raise SystemExit(f"bench.py: parity against the reference failed: {parity}")
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def cpu_baseline(t, W, nev):
+def cpu_baseline(t, W, nev, best_of=2):
     """The reference C implementation (oracle/_ref) on this box's host: one core, the full
-    workload step (2 sweeps), best of 2."""
+    workload step (2 sweeps).  Also returns its results: the in-run parity check."""
     from oracle import ref
     if not ref.available():
-        return {"value": None, "unit": "edge-diffs/s", "cores": 1, "kind": "reference",
-                "sample": "oracle/_ref not built"}
+        return ({"value": None, "unit": UNIT, "cores": 1, "kind": "reference",
+                 "sample": "oracle/_ref not built"}, None)
     r = ref.RefTreeSequence(t)
-    s = t.samples
-    n = len(s)
-    windows = np.linspace(0, t.sequence_length, W + 1)
-    best = None
-    for _ in range(2):
+    best, res = None, None
+    for _ in range(best_of):
         t0 = time.perf_counter()
-        r.one_way("diversity", [s], windows=windows, mode="branch")
-        r.k_way("divergence", [s[: n // 2], s[n // 2:]], [[0, 1]], windows=windows, mode="branch")
+        res = reference_step(r, t, W)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return {"value": 2 * nev / best, "unit": "edge-diffs/s", "cores": 1, "kind": "reference",
-            "sample": "full step (tsk_treeseq_diversity + tsk_treeseq_divergence, branch, "
-                      f"{W} windows), best of 2, {best:.2f} s"}
+    return ({"value": 2 * nev / best, "unit": UNIT, "cores": 1, "kind": "reference",
+             "sample": "full step (tsk_treeseq_diversity + tsk_treeseq_divergence, branch, "
+                       f"{W} windows), best of {best_of}, {best:.2f} s"}, res)
+
+
+# ------------------------------------------------------------------ site mode, decode, matrix (sample.sites/s)
+
+def int8_peak():
+    """Dense int8 tensor-core throughput of this GPU through cuBLASLt (torch._int_mm, 8192^3),
+    best of 10 and sustained over ~2 s: the denominator of the matrix path's roofline."""
+    import torch
+    n = 8192
+    a = torch.randint(-8, 8, (n, n), dtype=torch.int8, device="cuda")
+    b = torch.randint(-8, 8, (n, n), dtype=torch.int8, device="cuda")
+    for _ in range(3):
+        torch._int_mm(a, b)
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch._int_mm(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(10, int(2000 / best))
+    e0.record()
+    for _ in range(reps):
+        torch._int_mm(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    ops = 2.0 * n ** 3
+    return {"burst_tops": ops / (best / 1e3) / 1e12, "sustained_tops": ops * reps / (e0.elapsed_time(e1) / 1e3) / 1e12,
+            "how": "torch._int_mm (cuBLASLt int8 -> int32) 8192^3, best of 10 / back to back for ~2 s"}
+
+
+def secondary(ll, t, W, args):
+    """The sample.sites/s half of BASELINE.json's metric on the same ARG, one B200: site-mode
+    statistics (virtual rate: genotypes are never formed), genotype decode, and the site-mode
+    divergence matrix (tcgen05 int8) against a measured int8 peak."""
+    import torch
+    from oracle import ref
+    out = {}
+    s = t.samples
+    n, S = len(s), t.num_sites
+    windows = np.linspace(0, t.sequence_length, W + 1)
+    peak, _ = peaks()
+    # ---- site-mode diversity + divergence through the mirror of the reference's low-level interface
+    sizes2 = np.array([n // 2, n - n // 2], dtype=np.uint64)
+    best, phases = None, None
+    for _ in range(5):
+        t0 = time.perf_counter()
+        a = ll.diversity(np.array([n], dtype=np.uint64), s, windows=windows, mode="site")
+        p1 = ll.engine_stats()["last_kernel_ms"][:6]
+        b = ll.divergence(sizes2, s, [[0, 1]], windows=windows, mode="site")
+        p2 = ll.engine_stats()["last_kernel_ms"][:6]
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, phases = dt, [float(x + y) for x, y in zip(p1, p2)]
+    st = ll.engine_stats()
+    nev, dbar = st["num_events"], st["num_visits"] / max(st["num_events"], 1)
+    dev_s = sum(phases) / 1e3
+    b_site = 20 + dbar * (4 + 8 * 1.5)
+    site = {"calls": "diversity(site, 1 set) + divergence(site, 2 sets), %d windows, host buffers" % W,
+            "sites": S, "samples": n, "seconds_e2e": best, "seconds_device": dev_s,
+            "sample_sites_per_s_e2e": 2.0 * n * S / best, "sample_sites_per_s_device": 2.0 * n * S / dev_s,
+            "edge_diffs_per_s_device": 2.0 * nev / dev_s,
+            "roofline": {"bound": "hbm", "achieved": b_site * 2 * nev / dev_s / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": b_site * 2 * nev / dev_s / 1e9 / peak,
+                         "algorithmic_bytes_per_edge_diff": b_site},
+            "phase_ms": dict(zip(["weights", "sweep", "site_summary", "window_sums", "idle", "d2h"], phases))}
+    if ref.available() and not args.no_cpu_baseline:
+        r = ref.RefTreeSequence(t)
+        t0 = time.perf_counter()
+        wa = r.one_way("diversity", [s], windows=windows, mode="site")
+        wb = r.k_way("divergence", [s[: n // 2], s[n // 2:]], [[0, 1]], windows=windows, mode="site")
+        cpu_s = time.perf_counter() - t0
+        e = max(rel_err(a, wa), rel_err(b, wb))
+        site["parity"] = {"max_rel_err": e, "rtol": RTOL, "ok": bool(e <= RTOL)}
+        site["cpu_reference_1core"] = {"seconds": cpu_s, "sample_sites_per_s": 2.0 * n * S / cpu_s}
+    out["site_stats"] = site
+    # ---- genotype decode (genotypes.c:473-594): int8 [sites x samples] for a sample subset
+    sub = s[:: max(1, n // 2048)][:2048].copy()
+    g = None
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        g = ll.genotype_matrix(samples=sub)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    dec = {"samples": len(sub), "sites": S, "seconds_e2e": best,
+           "sample_sites_per_s_e2e": len(sub) * S / best,
+           "note": "includes the read-back of the %.1f GB int8 matrix into pageable host memory" % (g.nbytes / 1e9)}
+    if ref.available() and not args.no_cpu_baseline:
+        # bit-exact against tsk_variant_decode over every site, for a 512-sample subset
+        chk = s[:: max(1, n // 512)][:512].copy()
+        r = ref.RefTreeSequence(t)
+        t0 = time.perf_counter()
+        want = r.genotype_matrix(samples=chk)
+        cpu_s = time.perf_counter() - t0
+        got = ll.genotype_matrix(samples=chk)
+        dec["parity"] = {"bit_exact": bool(np.array_equal(got, want)), "samples": len(chk), "sites": S}
+        dec["cpu_reference_1core"] = {"seconds": cpu_s, "sample_sites_per_s": len(chk) * S / cpu_s}
+        del want, got
+    out["decode"] = dec
+    del g
+    # ---- site-mode divergence matrix of a sample subset: decode + tcgen05 int8 Gram + fp64 epilogue
+    nm = 8192 if n >= 8192 else n
+    subm = s[:: max(1, n // nm)][:nm].copy()
+    sets = subm.astype(np.int32)
+    sizes = np.ones(len(subm), dtype=np.uint64)
+    w1 = np.array([0.0, t.sequence_length])
+    best, ph = None, None
+    D = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        D = ll.divergence_matrix(w1, sample_sets=sets, sample_set_sizes=sizes, mode="site", span_normalise=False)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, ph = dt, ll.matrix_phase_ms()
+    nm = len(subm)
+    ops = float(nm) * (nm + 1) * S
+    pk = int8_peak()
+    gemm_s = ph["gemm"] / 1e3
+    D = D[0]
+    mat = {"samples": nm, "sites": S, "alleles": ph["alleles"], "seconds_e2e": best, "phase_ms": ph,
+           "sample_sites_per_s_e2e": nm * S / best,
+           "useful_int_ops": ops, "contraction_tops": ops / gemm_s / 1e12,
+           "int8_peak": pk,
+           "roofline": {"bound": "tensor", "achieved": ops / gemm_s / 1e12, "peak": pk["sustained_tops"],
+                        "unit": "Tint8op/s", "frac": ops / gemm_s / 1e12 / pk["sustained_tops"],
+                        "note": "useful ops n(n+1)S of the upper triangle over the contraction kernel's time"},
+           "properties": {"symmetric": bool(np.array_equal(D, D.T)), "zero_diagonal": bool((np.diag(D) == 0).all()),
+                          "integers": bool(np.array_equal(D, np.round(D)))}}
+    out["site_divergence_matrix"] = mat
+    torch.cuda.synchronize()
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--small", action="store_true", help="tiny workload (smoke test of the bench)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true",
+                    help="skip the CPU reference legs (and with them the in-run parity check)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the site / decode / matrix block")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3"])
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.config == "c3":
+        from tools import bench_c3
+        bench_c3.main(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -491,3 +491,88 @@ def test_stacked_multiallelic_mutations(wf_small):
             assert close(got, o.stat(nm, sets, idx, windows=w, mode="site", polarised=pol), cancelling=True), nm
     got = ll.divergence_matrix(w, mode="site", span_normalise=False)
     assert np.array_equal(got, o.divergence_matrix(None, windows=w, mode="site", span_normalise=False))
+
+
+def test_init_rejects_malformed_tables(wf_small):
+    """tskb_treeseq_init replaces tsk_treeseq_init: tables that tsk_table_collection_check_integrity
+    (tables.c:10362-10640, 10894-10930) refuses are refused with the same code, before any row is
+    used as an index on the host or the device."""
+    import copy
+    from tskit_b200.lowlevel import LibraryError, LLTreeSequence
+
+    def broken(**cols):
+        t = copy.copy(wf_small)
+        for k, v in cols.items():
+            setattr(t, k, v)
+        return t
+
+    def poke(col, i, v):
+        a = getattr(wf_small, col).copy()
+        a[i] = v
+        return {col: a}
+
+    E, N, S, Mu = wf_small.num_edges, wf_small.num_nodes, wf_small.num_sites, wf_small.num_mutations
+    assert S > 3 and Mu > 3
+    cases = [
+        (poke("edges_parent", 5, N), -202), (poke("edges_parent", 5, -1), -300),
+        (poke("edges_child", 7, -1), -301), (poke("edges_child", 7, N + 3), -202),
+        (poke("edges_left", 3, -1.0), -310), (poke("edges_right", 3, wf_small.sequence_length + 1), -309),
+        (poke("edges_left", 9, np.inf), -211),
+        (poke("edges_right", 11, wf_small.edges_left[11]), -307),
+        (poke("edges_child", 2, int(wf_small.edges_parent[2])), -306),
+        (poke("nodes_time", N - 1, np.nan), -210),
+        (poke("edge_insertion_order", 4, E), -203), (poke("edge_removal_order", 4, -2), -203),
+        (poke("sites_position", 2, -3.0), -402),
+        (poke("sites_position", 2, float(wf_small.sites_position[1])), -401),
+        (poke("sites_position", 2, float(wf_small.sites_position[0])), -400),
+        (poke("mutations_site", 1, S), -205), (poke("mutations_node", 1, N), -202),
+        (poke("mutations_parent", 1, Mu), -206), (poke("mutations_parent", 1, 1), -501),
+        (poke("mutations_parent", 1, 3), -502),
+        (poke("mutations_derived_state_offset", 2, 10**9), -200),
+    ]
+    for cols, code in cases:
+        with pytest.raises(LibraryError) as e:
+            LLTreeSequence(broken(**cols))
+        assert e.value.code == code, (list(cols), e.value.code, code)
+    # the first failing row of the first failing table wins, as in the reference's loop
+    both = {**poke("edges_parent", 8, N), **poke("mutations_node", 0, -5)}
+    with pytest.raises(LibraryError) as e:
+        LLTreeSequence(broken(**both))
+    assert e.value.code == -202
+    LLTreeSequence(wf_small).close()  # and the device is still usable afterwards
+
+
+def test_restricted_range_engines_on_a_repeated_genome(wf_small):
+    """What bench.py --gpus N does on every rank, here one range after the other on one GPU: the
+    genome repeated 3 x (sim.repeat_genome), cut by sharding.plan_shards, every range staged from the
+    restricted tables (sharding.restrict_tables) and evaluated with inputs and partials in HBM; the sum
+    of the partials equals the oracle on the whole tables, and the host path of the sharded wrapper
+    (pinned staging, device-side normalisation) equals it too."""
+    import torch
+    from tskit_b200 import sharding
+    from tskit_b200.lowlevel import STAT_BRANCH, STAT_SITE, STAT_SPAN_NORMALISE, LLTreeSequence
+    from tskit_b200.sim import repeat_genome
+    t = repeat_genome(wf_small, 3)
+    W = 12
+    windows = np.linspace(0, t.sequence_length, W + 1)
+    o = port.Oracle(t)
+    s = t.samples
+    sets = [s[:70], s[70:]]
+    sizes, flat = sets_args(sets)
+    idx = np.array([[0, 1], [1, 1]], dtype=np.int32)
+    d_sets = torch.from_numpy(flat).cuda()
+    ranges = sharding.plan_shards(t, windows, 4)
+    for mode, flag in (("branch", STAT_BRANCH), ("site", STAT_SITE)):
+        total = torch.zeros((W, 2), dtype=torch.float64, device="cuda")
+        part = torch.empty_like(total)
+        for rng in ranges:
+            local = sharding.restrict_tables(t, *rng)
+            ll = LLTreeSequence(local, genome_range=rng)
+            ll.stat_device("divergence", sizes, d_sets.data_ptr(), idx, windows, flag, part.data_ptr())
+            total += part
+            ll.close()
+        want = o.stat("divergence", sets, idx, windows=windows, mode=mode, span_normalise=False)
+        assert close(total.cpu().numpy(), want)
+        sh = sharding.ShardedTreeSequence(t, windows, 0, 1)
+        got = sh.stat_host("divergence", sizes, flat, idx, windows, flag | STAT_SPAN_NORMALISE)
+        assert close(got, o.stat("divergence", sets, idx, windows=windows, mode=mode))

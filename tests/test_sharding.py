@@ -124,3 +124,33 @@ def test_plan_shards_balanced_and_covering(wf_1k):
         assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
         counts = [np.count_nonzero((pos >= lo) & (pos < hi)) for lo, hi in r]
         assert max(counts) < 1.5 * len(pos) / world
+
+
+def test_restricted_tables_of_a_repeated_genome_sum_to_whole(wf_small):
+    """The pieces bench.py --gpus N is built from: repeat_genome (weak-scaling workload),
+    plan_shards on the edge indexes, restrict_tables per range.  Every range evaluated by the oracle
+    on its restricted tables; the sum over ranges is the oracle on the whole tables, and every copy
+    of the genome repeats the statistic of the original."""
+    from oracle import port
+    from tskit_b200.sim import repeat_genome
+    base = wf_small
+    copies, W = 3, 5
+    t = repeat_genome(base, copies)
+    assert t.num_edges == copies * base.num_edges and t.num_samples == base.num_samples
+    windows = np.linspace(0, t.sequence_length, copies * W + 1)
+    ranges = sharding.plan_shards(t, windows, 4)
+    s = t.samples
+    sets = [s[: len(s) // 3], s[len(s) // 3:]]
+    whole = port.Oracle(t)
+    for mode in ("branch", "site"):
+        want = whole.stat("divergence", sets, [[0, 1]], windows=windows, mode=mode, span_normalise=False)
+        total = np.zeros_like(want)
+        for rng in ranges:
+            local = sharding.restrict_tables(t, *rng)
+            assert local.num_edges < t.num_edges and local.num_nodes == t.num_nodes
+            total += OracleRangeEngine(local, rng).divergence(sets, [[0, 1]], windows, mode, False)
+        assert np.allclose(total, want, rtol=1e-11, atol=0)
+        one = port.Oracle(base).stat("divergence", sets, [[0, 1]],
+                                     windows=np.linspace(0, base.sequence_length, W + 1), mode=mode,
+                                     span_normalise=False)
+        assert np.allclose(want.reshape(copies, W), one.reshape(1, W), rtol=1e-11, atol=0)

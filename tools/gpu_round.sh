@@ -1,32 +1,55 @@
 #!/bin/bash
-# One GPU-box visit: parity suite, bench (both arms), ncu launch list, ncu full capture.
-# Usage: gpurun --timeout 1800 -- 'bash tools/gpu_round.sh r01a'
-TAG=${1:-r01}
+# One GPU-box visit: parity suite, bench (both arms), A/B of kernel variants, init phases, ncu.
+# Usage: gpurun --timeout 1800 -- 'bash tools/gpu_round.sh r2a [quick]'
+TAG=${1:-r2}
+MODE=${2:-full}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi > $OUT/smi.txt 2>&1
-nproc > $OUT/nproc.txt; lscpu | head -20 >> $OUT/nproc.txt
+(nproc; free -g; lscpu | head -20; df -h /tmp | tail -1) > $OUT/host.txt 2>&1
 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a $OUT/pytest_gpu.log
 tail -3 $OUT/pytest_gpu.log
-python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
-cat $OUT/bench.json
-if [ -z "$SKIP_REF" ]; then
-python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref exit $?"
+python bench.py --steps 20 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
+head -c 3000 $OUT/bench.json; echo
+# A/B of the branch-summary variants (same box, same plan; device-timed, no CPU legs)
+for v in "c4:" "lane:TSKB_SUM_VARIANT=lane" "c4m8:TSKB_SUM_GRID_MULT=8" "c4m32:TSKB_SUM_GRID_MULT=32" \
+         "tb128:TSKB_LIB=$PWD/tskit_b200/libtskb_tb128.so" "tb512:TSKB_LIB=$PWD/tskit_b200/libtskb_tb512.so"; do
+    name=${v%%:*}; envs=${v#*:}
+    if [ -n "$envs" ] && [[ "$envs" == TSKB_LIB=* ]] && [ ! -f "${envs#TSKB_LIB=}" ]; then continue; fi
+    env $envs python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ab_$name.json 2> $OUT/ab_$name.err
+    python - "$OUT/ab_$name.json" "$name" <<'EOF'
+import json, sys
+try:
+    d = json.load(open(sys.argv[1]))
+    print(sys.argv[2], "ms/step %.4f" % d["ms_per_step"], {k: round(v, 4) for k, v in d["config"]["phase_ms_per_step"].items()})
+except Exception as e:
+    print(sys.argv[2], "failed", e)
+EOF
+done
+# phases of tskb_treeseq_init on C2 (second init in the process: context and modules already loaded)
+TSKB_TIMING=1 python - > $OUT/init_phases.txt 2>&1 <<'EOF'
+import time, bench
+from tskit_b200.lowlevel import LLTreeSequence
+t, W, _ = bench.load_workload("c2")
+for i in range(3):
+    t0 = time.perf_counter(); ll = LLTreeSequence(t); dt = time.perf_counter() - t0
+    print("init %d: %.3f s (engine %.3f s)" % (i, dt, ll.engine_stats()["stage_ms"] / 1e3), flush=True)
+    ll.close()
+EOF
+grep -E "^init|tskb init" $OUT/init_phases.txt | tail -24
+if [ "$MODE" != "quick" ]; then
+python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref exit $?"
 cat $OUT/bench_ref.json
-fi
-timeout 300 python tools/probe_relvec.py > $OUT/probe_relvec.json 2> $OUT/probe_relvec.err; echo "relvec probe exit $?"
-cat $OUT/probe_relvec.json
-PROBE_QUICK=1 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-    -k regex:'(k_relvec|k_sweep|k_init_weights)' -c 100 --csv --log-file $OUT/relvec_launches.csv python tools/probe_relvec.py > $OUT/ncu_relvec.log 2>&1
-echo "ncu relvec exit $?"
+timeout 300 python tools/piece_stats.py > $OUT/piece_stats.txt 2>&1; tail -12 $OUT/piece_stats.txt
 KREGEX='regex:(k_set_weights|k_sweep|k_branch_summary|k_window|k_site_summary|DeviceScan)'
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 600 \
-    --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_launch.log 2>&1
+TSKB_BENCH_BLOCKS=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 600 \
+    --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_launch.log 2>&1
 echo "ncu launches exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 2 -c 2 \
-    -o $OUT/prof_sweep -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_prop.log 2>&1
-echo "ncu sweep exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_branch_summary -s 2 -c 2 \
-    -o $OUT/prof_summary -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_sum.log 2>&1
+TSKB_BENCH_BLOCKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_branch_summary -s 6 -c 2 \
+    -o $OUT/prof_summary -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_sum.log 2>&1
 echo "ncu summary exit $?"
+TSKB_BENCH_BLOCKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 6 -c 2 \
+    -o $OUT/prof_sweep -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_prop.log 2>&1
+echo "ncu sweep exit $?"
+fi
 ls -la $OUT

@@ -1,43 +1,47 @@
-"""Piece statistics of a cached workload (from the device plan): how many pieces lie inside one
-window, run lengths of equal windows in processing order, zero branch lengths, reference counts."""
-import os, sys
+"""Piece statistics of a cached workload (from the device plan): sizes of the heights, how many
+pieces abut the next slot (reductions merged in registers), piece lengths in windows, zero branch
+lengths, reference counts."""
+import os
+import sys
+
 import numpy as np
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench
-from tskit_b200.lowlevel import LLTreeSequence
+import bench  # noqa: E402
+from tskit_b200.lowlevel import LLTreeSequence  # noqa: E402
+
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 t, W, _ = bench.load_workload(name)
 ll = LLTreeSequence(t)
-x = ll.debug_array("q_x", np.float64)
-xe = ll.debug_array("q_xe", np.float64)
+bp0 = ll.debug_array("q_bp0", np.uint32)
+bp1 = ll.debug_array("q_bp1", np.uint32)
 bl = ll.debug_array("q_bl", np.float64)
 off = ll.debug_array("q_off", np.uint32)
 lb = ll.debug_array("level_begin", np.uint32)
-real = xe >= 0
-n = real.sum()
-print("slots", len(x), "real", n, "padding", (~real).sum(), "heights", len(lb) - 1)
-print("height sizes (first 12):", np.diff(lb)[:12], "last:", np.diff(lb)[-5:])
-wid = t.sequence_length / W
-w0 = np.floor(x / wid).astype(np.int64)
-w1 = np.minimum(np.floor(xe / wid), W - 1).astype(np.int64)
-same = real & (w0 == w1)
+pos = ll.debug_array("bp_pos", np.float64)
+real = bp1 != 0xFFFFFFFF
+n = int(real.sum())
+T = len(pos) - 1
+print("slots", len(bp0), "real", n, "padding", int((~real).sum()), "heights", len(lb) - 1, "breakpoints", T)
+print("height sizes:", np.diff(lb.astype(np.int64)).tolist())
 zero = real & (bl == 0)
-print("same-window %.3f  zero-bl %.3f  same&nonzero %.3f  multi&nonzero %.3f" % (
-    same.sum() / n, zero.sum() / n, (same & ~zero).sum() / n, (real & ~same & ~zero).sum() / n))
-ln = (xe - x)[real]
-print("piece length percentiles (bp):", np.percentile(ln, [10, 50, 90, 99]).round(1), "mean", ln.mean().round(1))
-# runs of equal window among consecutive slots (active = real, nonzero, same-window)
-act = same & ~zero
-key = np.where(act, w0, -1 - np.arange(len(x)))  # inactive slots never match
-brk = np.flatnonzero(key[1:] != key[:-1])
-runs = np.diff(np.concatenate([[-1], brk, [len(key) - 1]]))
-ract = runs[key[np.concatenate([brk, [len(key) - 1]])] >= 0]
-print("active pieces", act.sum(), "runs", len(ract), "mean run", ract.mean().round(2),
-      "run percentiles", np.percentile(ract, [50, 90, 99]))
-# per warp of 128 consecutive slots: distinct windows among active
-k128 = key[: len(key) // 128 * 128].reshape(-1, 128)
-a128 = act[: len(key) // 128 * 128].reshape(-1, 128)
-d = [(len(np.unique(r[m]))) for r, m in zip(k128[::997], a128[::997])]
-print("distinct windows per 128 slots (sampled): mean %.1f" % np.mean(d), "active per 128: %.1f" % a128[::997].sum(1).mean())
+print("zero branch length: %.4f" % (zero.sum() / n))
+merged = real[:-1] & real[1:] & (bp1[:-1] == bp0[1:])
+print("pieces abutting the next slot: %.4f  -> reductions per piece ~ %.3f" % (
+    merged.sum() / n, (2 * n - merged.sum()) / n))
+x0 = pos[bp0[real]]
+x1 = pos[np.minimum(bp1[real], T)]
+wid = t.sequence_length / W
+nw = np.floor(x1 / wid) - np.floor(x0 / wid)
+print("windows crossed per piece: mean %.2f, zero %.3f, percentiles 50/90/99:" % (nw.mean(), (nw == 0).mean()),
+      np.percentile(nw, [50, 90, 99]).tolist())
+ln = bp1[real].astype(np.int64) - bp0[real]
+print("piece length in breakpoints: mean %.0f, percentiles 10/50/90/99:" % ln.mean(),
+      np.percentile(ln, [10, 50, 90, 99]).tolist())
 cnt = np.diff(off.astype(np.int64))
-print("refs per real piece: mean %.2f  >3: %.4f" % (cnt[real].mean(), (cnt[real] > 3).mean()))
+print("refs per real piece: mean %.3f  >3: %.4f  >4: %.4f" % (cnt[real[:len(cnt)]].mean(),
+      (cnt[real[:len(cnt)]] > 3).mean(), (cnt[real[:len(cnt)]] > 4).mean()))
+# distinct 32-byte sectors of the delta array touched per warp of 32 consecutive slots (start side)
+s = (bp0[: len(bp0) // 32 * 32].reshape(-1, 32) // 4)
+d = np.array([len(np.unique(r)) for r in s[:: max(1, len(s) // 20000)]])
+print("distinct delta sectors per 32 slots (start breakpoints): mean %.1f" % d.mean())

@@ -168,6 +168,18 @@ class LLTreeSequence:
             "last_call_ms": s.last_call_ms, "last_kernel_ms": list(s.last_kernel_ms),
             "last_launches": s.last_launches, "device_bytes": s.device_bytes}
 
+    def stat_device(self, name, sizes, d_sets_ptr, indexes, windows, options, d_result_ptr):
+        """``tskb_treeseq_stat_device``: a sample-count statistic with the sample sets (int32) and the
+        ``(W, M)`` result (float64) already resident in HBM, given as device addresses.  Synchronous:
+        the result is complete when the call returns."""
+        idx = None if indexes is None else np.ascontiguousarray(indexes, dtype=np.int32)
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
+        w = np.ascontiguousarray(windows, dtype=np.float64)
+        _handle(_lib.lib().tskb_treeseq_stat_device(
+            self._h, STAT_IDS[name], len(sizes), _p(sizes), C.c_void_p(d_sets_ptr),
+            0 if idx is None else idx.shape[0], _p(idx), len(w) - 1, _p(w), options,
+            C.c_void_p(d_result_ptr)))
+
     def debug_array(self, name, dtype):
         n = _lib.lib().tskb_treeseq_debug_array(self._h, name.encode(), None, 0)
         if n < 0:

@@ -2,16 +2,18 @@
 contiguous ranges balanced by edge-diff count.
 
 The path shards naturally: a window's value depends only on the trees overlapping it, and each
-rank seeds the state at its range's left edge locally from the replicated tables (the engine's
+rank seeds the state at its range's left edge locally from the tables (the engine's
 ``genome_range``).  There is no collective on the data path.  The only exchange is the final
 sum of the per-window partial results -- windows owned by one rank receive zeros from the
 others, windows straddling a cut are the sum of their parts -- done with one ``all_reduce`` of
-``W x M`` doubles (NCCL on GPUs, gloo in the CPU tests), before span normalisation
-(``trees.c:1920-1934`` divides after accumulation).  The relatedness vector shards the same way:
-its rows are integrals over the genome, and centring the output rows is linear, so the ranks'
-centred partial rows add up to the centred whole.
+``W x M`` doubles (NCCL on device-resident partials; gloo in the CPU tests), before span
+normalisation (``trees.c:1920-1934`` divides after accumulation).  The relatedness vector shards
+the same way: its rows are integrals over the genome, and centring the output rows is linear, so
+the ranks' centred partial rows add up to the centred whole.
 """
 import numpy as np
+
+from .tables import Tables
 
 
 def edge_diff_positions(tables):
@@ -24,6 +26,18 @@ def edge_diff_positions(tables):
     return pos
 
 
+def _diffs_up_to(tables):
+    """x -> number of edge diffs at positions <= x, from the two edge indexes (already sorted by
+    left / right: no sort of the 2 E positions)."""
+    tables.ensure_derived()
+    L = tables.sequence_length
+    lefts = tables.edges_left[tables.edge_insertion_order]
+    rights = tables.edges_right[tables.edge_removal_order]
+    rights = rights[:np.searchsorted(rights, L, side="left")]  # edges reaching L are never removed
+    return (lambda x: np.searchsorted(lefts, x, side="right") + np.searchsorted(rights, x, side="right"),
+            len(lefts) + len(rights))
+
+
 def plan_shards(tables, windows, world):
     """``world`` contiguous genome ranges covering [0, L) with ~equal edge-diff counts; cuts are
     snapped to window edges when there are at least ``world`` windows (every rank then owns
@@ -31,17 +45,23 @@ def plan_shards(tables, windows, world):
     L = float(tables.sequence_length)
     if world <= 1:
         return [(0.0, L)]
-    pos = edge_diff_positions(tables)
     windows = np.asarray(windows, dtype=np.float64)
-    targets = [pos[min(len(pos) - 1, (len(pos) * r) // world)] if len(pos) else L * r / world
-               for r in range(1, world)]
-    cuts = []
     inner = windows[1:-1]
-    for x in targets:
-        if len(inner) >= world - 1:
-            j = int(np.argmin(np.abs(inner - x)))
-            x = float(inner[j])
-        cuts.append(float(x))
+    count, total = _diffs_up_to(tables)
+    cuts = []
+    if total and len(inner) >= world - 1:
+        # the window edge whose cumulative diff count is nearest each target
+        c = count(inner)
+        for r in range(1, world):
+            target = total * r / world
+            j = int(np.searchsorted(c, target))
+            if j > 0 and (j == len(c) or target - c[j - 1] <= c[j] - target):
+                j -= 1
+            cuts.append(float(inner[j]))
+    elif total:
+        # fewer windows than ranks: cut inside windows, at the position of the target diff
+        pos = edge_diff_positions(tables)
+        cuts = [float(pos[min(len(pos) - 1, (len(pos) * r) // world)]) for r in range(1, world)]
     cuts = sorted(set(c for c in cuts if 0.0 < c < L))
     # degenerate inputs: fall back to even cuts so that every rank has a non-empty range
     if len(cuts) != world - 1:
@@ -50,23 +70,80 @@ def plan_shards(tables, windows, world):
     return list(zip(edges[:-1], edges[1:]))
 
 
+def restrict_tables(tables, a, b):
+    """The rows a rank needs for the genome range [a, b): the edges meeting it (coordinates
+    untouched: the engine clips and seeds the tree at ``a`` itself), the sites inside it with their
+    mutations, and the whole node table (ids are global).  Edge indexes are the sub-sequences of
+    the global ones, so the order of the diffs is the reference's."""
+    tables.ensure_derived()
+    keep = (tables.edges_left < b) & (tables.edges_right > a)
+    new_id = np.cumsum(keep, dtype=np.int64) - 1
+
+    def sub_order(order):
+        o = order[keep[order]]
+        return new_id[o].astype(np.int32)
+
+    kw = {}
+    if tables.num_sites:
+        s0 = int(np.searchsorted(tables.sites_position, a, side="left"))
+        s1 = int(np.searchsorted(tables.sites_position, b, side="left"))
+        m0 = int(np.searchsorted(tables.mutations_site, s0, side="left"))
+        m1 = int(np.searchsorted(tables.mutations_site, s1, side="left"))
+        ao, do = tables.sites_ancestral_state_offset, tables.mutations_derived_state_offset
+        kw = dict(
+            sites_position=tables.sites_position[s0:s1],
+            sites_ancestral_state=tables.sites_ancestral_state[int(ao[s0]):int(ao[s1])],
+            sites_ancestral_state_offset=ao[s0:s1 + 1] - ao[s0],
+            mutations_site=tables.mutations_site[m0:m1] - s0,
+            mutations_node=tables.mutations_node[m0:m1],
+            mutations_parent=np.where(tables.mutations_parent[m0:m1] >= 0,
+                                      tables.mutations_parent[m0:m1] - m0, -1),
+            mutations_derived_state=tables.mutations_derived_state[int(do[m0]):int(do[m1])],
+            mutations_derived_state_offset=do[m0:m1 + 1] - do[m0])
+    return Tables(tables.sequence_length, tables.nodes_flags, tables.nodes_time,
+                  tables.edges_left[keep], tables.edges_right[keep], tables.edges_parent[keep],
+                  tables.edges_child[keep], time_uncalibrated=tables.time_uncalibrated,
+                  edge_insertion_order=sub_order(tables.edge_insertion_order),
+                  edge_removal_order=sub_order(tables.edge_removal_order), **kw)
+
+
+_SPANS = {}
+
+
+def _spans(windows, like):
+    """Window spans as a tensor on ``like``'s device, broadcastable against it (cached: the same
+    windows are used call after call)."""
+    import torch
+    w = np.ascontiguousarray(windows, dtype=np.float64)
+    key = (hash(w.tobytes()), str(like.device), like.dim())
+    t = _SPANS.get(key)
+    if t is None:
+        if len(_SPANS) > 16:
+            _SPANS.clear()
+        t = torch.from_numpy((w[1:] - w[:-1]).reshape((-1,) + (1,) * (like.dim() - 1))).to(like.device)
+        _SPANS[key] = t
+    return t
+
+
 def combine(local, windows, span_normalise, group=None, device=None):
     """Sum the ranks' un-normalised ``(W, M)`` (relatedness vector: ``(W, nodes, K)``) partial results
-    and span-normalise.  ``local`` is
-    this rank's result computed with ``span_normalise=False`` over its own genome range."""
+    and span-normalise.  ``local`` is this rank's result computed with ``span_normalise=False`` over
+    its own genome range: a numpy array (moved to ``device`` for NCCL, returned as numpy) or a
+    tensor already resident on the device (summed and normalised in place, returned as is: no host
+    round trip)."""
     import torch
     import torch.distributed as dist
-    total = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
+    on_device = isinstance(local, torch.Tensor)
+    total = local if on_device else torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        if device is not None:
+        if not on_device and device is not None:
             total = total.to(device)
         dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
-        total = total.cpu()
-    out = total.numpy().copy()
     if span_normalise:
-        w = np.asarray(windows, dtype=np.float64)
-        out /= (w[1:] - w[:-1]).reshape((-1,) + (1,) * (out.ndim - 1))
-    return out
+        total /= _spans(windows, total)
+    if on_device:
+        return total
+    return total.cpu().numpy().copy()
 
 
 class ShardedTreeSequence:
@@ -74,15 +151,19 @@ class ShardedTreeSequence:
     genome range, every rank returns the full result."""
 
     def __init__(self, tables, windows_for_cuts, rank, world, device=0, engine_factory=None,
-                 group=None):
+                 group=None, restrict=True):
         self.ranges = plan_shards(tables, windows_for_cuts, world)
         self.range = self.ranges[rank]
         self.rank, self.world, self.group = rank, world, group
         self.device = device
+        self.num_samples = tables.num_samples
         if engine_factory is None:
             from .lowlevel import LLTreeSequence
             engine_factory = lambda t, rng: LLTreeSequence(t, device=device, genome_range=rng)  # noqa: E731
-        self.engine = engine_factory(tables, self.range)
+        local = restrict_tables(tables, *self.range) if (restrict and world > 1) else tables
+        self.local_tables = local
+        self.engine = engine_factory(local, self.range)
+        self._bufs = {}
 
     def stat(self, name, *args, windows, span_normalise=True, **kwargs):
         local = getattr(self.engine, name)(*args, windows=windows, span_normalise=False, **kwargs)
@@ -94,3 +175,47 @@ class ShardedTreeSequence:
         except Exception:
             pass
         return combine(local, windows, span_normalise, group=self.group, device=dev)
+
+    # ---- device-resident path (sample-count statistics): sets in, result out through pinned host
+    # memory once each; the partial result never leaves HBM before the all_reduce
+    def _buf(self, key, shape, dtype, pinned=False):
+        import torch
+        b = self._bufs.get(key)
+        if b is None or tuple(b.shape) != tuple(shape):
+            if pinned:
+                b = torch.empty(shape, dtype=dtype).pin_memory()
+            else:
+                b = torch.empty(shape, dtype=dtype, device=f"cuda:{self.device}")
+            self._bufs[key] = b
+        return b
+
+    def stat_device(self, name, sizes, d_sets, indexes, windows, options, out=None):
+        """This rank's partial of a sample-count statistic over sets already in HBM (``d_sets``: int32
+        tensor), summed over the ranks and span-normalised on the device.  Returns the ``(W, M)``
+        result tensor (``out`` if given)."""
+        import torch
+        from .lowlevel import STAT_SPAN_NORMALISE
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
+        idx = None if indexes is None else np.ascontiguousarray(indexes, dtype=np.int32)
+        w = np.ascontiguousarray(windows, dtype=np.float64)
+        M = len(sizes) if idx is None else idx.shape[0]
+        if out is None:
+            out = self._buf(("res", name, M), (len(w) - 1, M), torch.float64)
+        self.engine.stat_device(name, sizes, d_sets.data_ptr(), idx, w,
+                                options & ~STAT_SPAN_NORMALISE, out.data_ptr())
+        return combine(out, w, bool(options & STAT_SPAN_NORMALISE), group=self.group)
+
+    def stat_host(self, name, sizes, sets, indexes, windows, options):
+        """The call a user makes: host sample sets in, full host result out on every rank."""
+        import torch
+        sets = np.ascontiguousarray(sets, dtype=np.int32)
+        h_sets = self._buf(("hsets", len(sets)), (len(sets),), torch.int32, pinned=True)
+        h_sets.numpy()[:] = sets
+        d_sets = self._buf(("dsets", len(sets)), (len(sets),), torch.int32)
+        d_sets.copy_(h_sets, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the engine runs on its own stream
+        res = self.stat_device(name, sizes, d_sets, indexes, windows, options)
+        h_res = self._buf(("hres", name, tuple(res.shape)), tuple(res.shape), torch.float64, pinned=True)
+        h_res.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return h_res.numpy()
