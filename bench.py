@@ -672,6 +672,205 @@ def secondary(ll, t, W, args):
     return out
 
 
+# ------------------------------------------------------------------ C3: f2/f3/f4 + Fst, 8 sets, 10^6 samples, 1 Gb
+
+C3 = dict(samples=1_000_000, generations=40, arms=8, arm_length=1.25e8, ncross=1, windows=10_000)
+C3_SMALL = dict(samples=4_000, generations=40, arms=8, arm_length=1.25e6, ncross=1, windows=400)
+
+
+def c3_workload(cfg, rank, world, barrier):
+    """BASELINE.json configs[2]: one tree sequence of `arms` unlinked chromosome arms over the same 10^6
+    samples (seeded Wright-Fisher, ancestry seed 42 + arm; 40 generations back: every local tree is a
+    forest of ~n / 21 subtrees, which is a valid input -- a fully coalesced 10^6-sample, 1 Gb ARG has
+    ~10^9+ edges and fits neither the generator's time budget nor one GPU).  The ranks simulate the arms
+    between them, exchange them through the local disk and every rank assembles the whole tables."""
+    from concurrent.futures import ThreadPoolExecutor
+    from tskit_b200.sim import concat_genomes
+    tag = "c3_n%d_g%d_a%d_L%d" % (cfg["samples"], cfg["generations"], cfg["arms"], int(cfg["arm_length"]))
+
+    def path(a):
+        return os.path.join(cache_dir(), f"{tag}_arm{a}.npz")
+
+    def make(a):
+        if not os.path.exists(path(a)):
+            t = wright_fisher(cfg["samples"], cfg["generations"], cfg["arm_length"], ncross=cfg["ncross"],
+                              seed=42 + a, num_threads=1)
+            t.save(path(a) + ".tmp.npz")
+            os.replace(path(a) + ".tmp.npz", path(a))
+
+    t0 = time.time()
+    mine = [a for a in range(cfg["arms"]) if a % world == rank]
+    threads = max(1, (os.cpu_count() or 1) // world)
+    with ThreadPoolExecutor(min(threads, max(1, len(mine)))) as pool:
+        list(pool.map(make, mine))
+    gen_s = time.time() - t0
+    barrier()
+    t0 = time.time()
+    t = concat_genomes([Tables.load(path(a)) for a in range(cfg["arms"])])
+    return t, gen_s, time.time() - t0
+
+
+def run_c3(args):
+    """Strong scaling of BASELINE.json configs[2] over genome shards: one step = f2 (28 pairs) + f3 (8
+    triples) + f4 (2 quadruples) + Fst (= diversity of the 8 sets + divergence of the 28 pairs,
+    trees.py:10076-10126), branch mode, 10^4 windows: 5 sweeps.  Every rank stages its genome range
+    and computes un-normalised partials; per statistic one all_reduce of the device-resident W x M
+    partials inside the timed region."""
+    import torch
+    import torch.distributed as dist
+
+    from tskit_b200 import sharding
+    from tskit_b200.lowlevel import STAT_BRANCH, STAT_SPAN_NORMALISE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    cfg = C3_SMALL if args.small else C3
+    t, gen_s, concat_s = c3_workload(cfg, rank, world, barrier)
+    W = cfg["windows"]
+    windows = np.linspace(0, t.sequence_length, W + 1)
+    s = t.samples
+    sets = np.array_split(s, 8)
+    sizes = np.array([len(x) for x in sets], dtype=np.uint64)
+    pairs = np.array([(i, j) for i in range(8) for j in range(i + 1, 8)], dtype=np.int32)
+    triples = np.array([(i, (i + 1) % 8, (i + 2) % 8) for i in range(8)], dtype=np.int32)
+    quads = np.array([(0, 1, 2, 3), (4, 5, 6, 7)], dtype=np.int32)
+    calls = [("f2", pairs), ("f3", triples), ("f4", quads), ("diversity", None), ("divergence", pairs)]
+    t0 = time.perf_counter()
+    sh = sharding.ShardedTreeSequence(t, windows, rank, world, device=local)
+    stage_s = time.perf_counter() - t0
+    ll = sh.engine
+    st = ll.engine_stats()
+    nev_total = edge_diffs_per_sweep(t)
+    d_sets = torch.from_numpy(s.copy()).to(dev)
+    outs = {nm: torch.empty((W, len(sizes) if ix is None else len(ix)), dtype=torch.float64, device=dev)
+            for nm, ix in calls}
+    phase = {}
+    coll_ev = []
+
+    def step():
+        ms = 0.0
+        for nm, ix in calls:
+            ll.stat_device(nm, sizes, d_sets.data_ptr(), ix, windows, STAT_BRANCH, outs[nm].data_ptr())
+            es = ll.engine_stats()
+            ms += es["last_call_ms"]
+            phase[nm] = phase.get(nm, 0.0) + es["last_call_ms"]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sharding.combine(outs[nm], windows, True)
+            if nm == "divergence":  # Fst = 1 - 2 (pi_u + pi_v) / (pi_u + pi_v + 2 d_uv)
+                pi = outs["diversity"]
+                su = pi[:, pairs[:, 0]] + pi[:, pairs[:, 1]]
+                outs["Fst"] = 1 - 2 * su / (su + 2 * outs["divergence"])
+            e1.record()
+            coll_ev.append((e0, e1))
+        return ms
+
+    def collective_ms():
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in coll_ev)
+        coll_ev.clear()
+        return ms
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    collective_ms()
+    phase.clear()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dev_ms += step()
+    coll_ms = collective_ms()
+    dev_ms += coll_ms
+    wall = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        times = torch.tensor([dev_ms, wall, coll_ms, stage_s, gen_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dev_ms, wall, coll_ms, stage_s, gen_s = [float(x) for x in times.cpu()]
+        mem = torch.tensor([st["device_bytes"], st["num_events"]], dtype=torch.float64, device=dev)
+        g = [torch.empty_like(mem) for _ in range(world)]
+        dist.all_gather(g, mem)
+        per_rank = [[int(x[0].item()), int(x[1].item())] for x in g]
+    else:
+        per_rank = [[st["device_bytes"], st["num_events"]]]
+    if rank == 0:
+        # parity on a subsample: the reference C library on the rows meeting the first windows
+        parity = None
+        if not args.no_cpu_baseline:
+            parity = c3_parity(t, windows, sets, calls, {k: v.cpu().numpy() for k, v in outs.items()})
+        checksum = {k: float(torch.nan_to_num(v).sum().item()) for k, v in outs.items()}
+        sweeps = len(calls)
+        value = sweeps * nev_total * args.steps / (dev_ms / 1e3)
+        line = {
+            "metric": "edge-diffs/s (branch-mode f2 + f3 + f4 + Fst over 8 sample sets, windowed)",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": ("c3: f2 (28 pairs) + f3 (8) + f4 (2) + Fst (28 pairs), 8 sample sets, branch mode, "
+                             f"n={t.num_samples}, L={t.sequence_length:.0f}, E={t.num_edges}, N={t.num_nodes}, "
+                             f"{W} windows; {cfg['arms']} arms x {cfg['generations']} generations"),
+                "edge_diffs_per_sweep": nev_total, "sweeps_per_step": sweeps,
+                "sharding": ("whole genome on one GPU" if world == 1 else
+                             f"{world} genome ranges from sharding.plan_shards; per statistic one all_reduce "
+                             f"of the device-resident partials inside the timed region"),
+                "per_rank_plan_bytes_and_edge_diffs": per_rank,
+                "ms_per_step_by_statistic": {k: v / args.steps for k, v in phase.items()},
+                "collective_ms_per_step": coll_ms / args.steps, "wall_ms_per_step": wall / args.steps * 1e3,
+                "generate_s": gen_s, "concat_s": concat_s, "stage_s": stage_s, "levels": st["num_levels"],
+                "checksum": checksum},
+            "clocks": clocks, "parity": parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def c3_parity(t, windows, sets, calls, got, nwin=3):
+    """The first `nwin` windows of every statistic against the reference C library (oracle/_ref) run on
+    the rows of the tables that meet those windows."""
+    from oracle import ref
+    from tskit_b200 import sharding
+    if not ref.available():
+        return None
+    hi = float(windows[nwin])
+    sub = sharding.restrict_tables(t, 0.0, hi)
+    r = ref.RefTreeSequence(sub)
+    w = np.concatenate([windows[: nwin + 1], [t.sequence_length]])
+    worst = 0.0
+    t0 = time.perf_counter()
+    want = {}
+    for nm, ix in calls:
+        if ix is None:
+            want[nm] = r.one_way(nm, sets, windows=w, mode="branch")[:nwin]
+        else:
+            want[nm] = r.k_way(nm, sets, ix, windows=w, mode="branch")[:nwin]
+        scale = np.nanmax(np.abs(want[nm]))
+        d = np.abs(got[nm][:nwin] - want[nm])
+        # f2/f3/f4 are differences of large terms: absolute floor of rtol x the largest entry
+        worst = max(worst, float(np.nanmax(d / np.maximum(np.abs(want[nm]), scale))))
+    return {"max_rel_err": worst, "rtol": RTOL, "ok": bool(worst <= RTOL), "windows": nwin,
+            "against": "oracle/_ref on the rows meeting the first windows (sharding.restrict_tables)",
+            "edges_in_subsample": int(sub.num_edges), "reference_seconds": time.perf_counter() - t0}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -685,8 +884,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c2", "c3"])
     args = ap.parse_args()
     if args.config == "c3":
-        from tools import bench_c3
-        bench_c3.main(args)
+        run_c3(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

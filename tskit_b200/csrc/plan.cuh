@@ -127,6 +127,13 @@ struct Plan {
     DevArray<uint16_t> mut_alt;       // [Mu] allele index the mutation's state is subtracted from
     std::vector<double> h_site_pos;
 
+    // --- summary order (built on the first many-column branch call, stats.cu:ensure_summary_order):
+    //     the real pieces sorted by the breakpoint they start at, with the state slot of each
+    mutable bool so_built = false;
+    mutable uint32_t nsp = 0;
+    mutable DevArray<uint32_t> so_slot, so_bp0, so_bp1;  // [nsp]
+    mutable DevArray<double> so_bl;                      // [nsp]
+
     // per-call scratch + statistics
     mutable std::mutex mu;
     mutable std::vector<uint32_t> seen_stamp;  // argument validation scratch (api.cu:check_sample_sets)

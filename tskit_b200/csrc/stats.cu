@@ -638,6 +638,177 @@ __global__ void k_transpose_deltas(const double *__restrict__ D, uint32_t Tp1, u
     }
 }
 
+// ---- many result columns, pieces in the order of their start breakpoints (the summary order)
+// With M columns the deltas are M x 8 bytes per breakpoint -- 1 GB for 28 columns on the C2 ARG, far
+// past L2, so reductions scattered over all of it run at DRAM speed.  Wide states are a whole
+// 32-byte sector per piece, so reading them through a permutation costs nothing extra: here the
+// pieces are walked in the order of their START breakpoint.  Lanes are columns; the contributions of
+// the pieces that start at one breakpoint (11 on average) are summed in registers and leave as one
+// reduction per breakpoint, and the reductions at the END breakpoints land a piece length ahead of
+// the walk -- a moving front of a few tens of MB that stays in L2.
+constexpr uint32_t BYPOS_CHUNK = 256;  // pieces per warp
+
+__global__ void k_so_keys(uint32_t npp, const uint32_t *__restrict__ q_bp0, const uint32_t *__restrict__ q_bp1,
+    uint32_t *key, uint32_t *val, uint32_t pad_key) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npp) return;
+    key[j] = q_bp1[j] != NO_PIECE ? q_bp0[j] : pad_key;  // padding sorts last
+    val[j] = j;
+}
+
+__global__ void k_so_gather(uint32_t n, const uint32_t *__restrict__ slot, const uint32_t *__restrict__ q_bp0,
+    const uint32_t *__restrict__ q_bp1, const double *__restrict__ q_bl, uint32_t *bp0, uint32_t *bp1, double *bl) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = slot[i];
+    bp0[i] = q_bp0[j]; bp1[i] = q_bp1[j]; bl[i] = q_bl[j];
+}
+
+template <int STAT, class V>
+__global__ void __launch_bounds__(TB) k_branch_summary_bypos(uint32_t nsp,
+    const uint32_t *__restrict__ so_slot, const uint32_t *__restrict__ so_bp0,
+    const uint32_t *__restrict__ so_bp1, const double *__restrict__ so_bl, const V *__restrict__ pval,
+    SumP sp, V totals, DeltaOut out, uint32_t m0, uint32_t ncols) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t c0 = warp * BYPOS_CHUNK;
+    if (c0 >= nsp) return;
+    const uint32_t c1 = min(nsp, c0 + BYPOS_CHUNK);
+    const bool mine = lane < ncols;
+    const uint32_t m = m0 + (mine ? lane : 0);
+    const ColP col = out.cols[m];
+    double *Dl = out.D + lane;  // D[bp * ncols + lane]
+    double acc = 0.0;
+    uint32_t cur = NO_PIECE;    // breakpoint the register accumulator belongs to
+    for (uint32_t base = c0; base < c1; base += 32) {
+        const uint32_t j = base + lane;
+        V st = ivec_zero<V>();
+        double bl = 0.0;
+        uint32_t bp0 = 0, bp1 = NO_PIECE;
+        if (j < c1) {
+            bl = so_bl[j]; bp0 = so_bp0[j]; bp1 = so_bp1[j];
+            st = pval[so_slot[j]];
+        }
+        const int cnt = (int) min(32u, c1 - base);
+        for (int i = 0; i < cnt; i++) {
+            V s_i;
+#pragma unroll
+            for (int k = 0; k < V::N; k++) s_i.v[k] = __shfl_sync(0xffffffffu, st.v[k], i);
+            const double bl_i = __shfl_sync(0xffffffffu, bl, i);
+            const uint32_t b0 = __shfl_sync(0xffffffffu, bp0, i), b1 = __shfl_sync(0xffffffffu, bp1, i);
+            double G = 0.0;
+            if (!(sp.skip_zero_bl && bl_i == 0.0)) G = bl_i * F_branch<STAT, V>(sp, col, m, s_i, totals);
+            if (b0 != cur) {
+                if (cur != NO_PIECE && mine && acc != 0.0) atomicAdd(Dl + (size_t) cur * ncols, acc);
+                cur = b0;
+                acc = 0.0;
+            }
+            acc += G;
+            if (mine && G != 0.0) atomicAdd(Dl + (size_t) b1 * ncols, -G);
+        }
+    }
+    if (cur != NO_PIECE && mine && acc != 0.0) atomicAdd(Dl + (size_t) cur * ncols, acc);
+}
+
+// ---- running sums and window integrals of deltas laid out [breakpoint][column], lanes = columns:
+// a warp owns COLSCAN_ROWS consecutive breakpoints.  Pass 1: column sums of every chunk; pass 2: their
+// exclusive prefix over the chunks (one warp); pass 3: the warp walks its breakpoints again with the
+// running sum S and adds S x (overlap of [t_i, t_i+1) with the window) to the windows it meets
+// (trees.c:1484-1504) -- S is never written back.
+constexpr uint32_t COLSCAN_ROWS = 512;
+
+__global__ void __launch_bounds__(TB) k_colscan_partial(const double *__restrict__ D, uint32_t T, uint32_t ncols,
+    double *partial) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t r0 = warp * COLSCAN_ROWS;
+    if (r0 >= T || lane >= ncols) return;
+    const uint32_t r1 = min(T, r0 + COLSCAN_ROWS);
+    const double *p = D + (size_t) r0 * ncols + lane;
+    double sum = 0.0;
+    uint32_t r = r0;
+    for (; r + 8 <= r1; r += 8, p += (size_t) 8 * ncols) {
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = p[(size_t) q * ncols];  // eight loads in flight
+#pragma unroll
+        for (int q = 0; q < 8; q++) sum += v[q];                  // summed in breakpoint order
+    }
+    for (; r < r1; r++, p += ncols) sum += p[0];
+    partial[(size_t) warp * ncols + lane] = sum;
+}
+
+// exclusive prefix of the chunk sums over the chunks, per column; one block of 32 warps, lanes = columns
+__global__ void __launch_bounds__(1024) k_colscan_offsets(double *partial, uint32_t nchunks, uint32_t ncols) {
+    __shared__ double tot[32][33];
+    const uint32_t lane = threadIdx.x & 31u, wp = threadIdx.x >> 5;
+    const uint32_t per = (nchunks + 31) / 32;
+    const uint32_t c0 = min(nchunks, wp * per), c1 = min(nchunks, c0 + per);
+    double sum = 0.0;
+    if (lane < ncols) {
+#pragma unroll 8
+        for (uint32_t c = c0; c < c1; c++) sum += partial[(size_t) c * ncols + lane];
+    }
+    tot[wp][lane] = sum;
+    __syncthreads();
+    double run = 0.0;
+    for (uint32_t q = 0; q < wp; q++) run += tot[q][lane];
+    if (lane < ncols) {
+#pragma unroll 8
+        for (uint32_t c = c0; c < c1; c++) {
+            const double v = partial[(size_t) c * ncols + lane];
+            partial[(size_t) c * ncols + lane] = run;
+            run += v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TB) k_colscan_integrate(const double *__restrict__ D, uint32_t T,
+    uint32_t ncols, const double *__restrict__ partial, const double *__restrict__ bp_pos,
+    const double *__restrict__ windows, uint32_t W, uint32_t m0, uint32_t M, double *result) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t r0 = warp * COLSCAN_ROWS;
+    if (r0 >= T) return;
+    const uint32_t r1 = min(T, r0 + COLSCAN_ROWS);
+    const bool mine = lane < ncols;
+    double S = mine ? partial[(size_t) warp * ncols + lane] : 0.0;
+    // window holding the first interval's left end (warp-uniform)
+    double a = bp_pos[r0];
+    uint32_t w = upper_bound_dev(windows, W + 1, a);
+    w = w > 0 ? w - 1 : 0;
+    if (w >= W) return;  // the chunk starts at or beyond the last window edge
+    double wl = windows[w], wr = windows[w + 1];
+    double acc = 0.0;
+    const double *p = D + (size_t) r0 * ncols + (mine ? lane : 0);
+    for (uint32_t r = r0; r < r1; r++, p += ncols) {
+        if (mine) S += p[0];
+        const double b = bp_pos[r + 1];
+        // the interval [a, b) against the windows it meets
+        while (true) {
+            const double lo = a > wl ? a : wl, hi = b < wr ? b : wr;
+            if (hi > lo) acc += S * (hi - lo);
+            if (b < wr) break;  // the window goes on past this interval
+            if (mine && acc != 0.0) atomicAdd(result + (size_t) w * M + m0 + lane, acc);
+            acc = 0.0;
+            w++;
+            if (w >= W) return;
+            wl = wr;
+            wr = windows[w + 1];
+        }
+        a = b;
+    }
+    if (mine && acc != 0.0) atomicAdd(result + (size_t) w * M + m0 + lane, acc);
+}
+
+__global__ void k_span_divide(const double *__restrict__ windows, uint32_t W, uint32_t M, uint32_t m0,
+    uint32_t ncols, double *result) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t) W * ncols) return;
+    const uint32_t w = (uint32_t) (i / ncols), c = (uint32_t) (i % ncols);
+    result[(size_t) w * M + m0 + c] /= windows[w + 1] - windows[w];
+}
+
 // ---------------------------------------------------------------- phase 3, branch mode
 // S = inclusive prefix sum of D over the breakpoints (the reference's running sum after the diffs
 // of breakpoint i, cub::DeviceScan per column); window w gets the integral of S over it:
@@ -1154,6 +1325,51 @@ inline void finish_columns(CallCtx &c, double *D, uint32_t Tp1, uint32_t m0, uin
     c.launches++;
 }
 
+// the summary order of the plan (pieces by start breakpoint), built once on first use
+__global__ void k_so_count(uint32_t npp, const uint32_t *__restrict__ key_sorted, uint32_t pad_key, uint32_t *nsp) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npp) return;
+    const bool real = key_sorted[i] != pad_key;
+    if (i == 0 && !real) *nsp = 0;
+    if (real && (i + 1 == npp || key_sorted[i + 1] == pad_key)) *nsp = i + 1;
+}
+
+void ensure_summary_order(const Plan &P, cudaStream_t s) {
+    if (P.so_built) return;
+    const uint32_t npp = P.npp;
+    P.nsp = 0;
+    if (npp > 0) {
+        DevArray<uint32_t> key, key_out, val, d_nsp;
+        key.alloc(npp); key_out.alloc(npp); val.alloc(npp); d_nsp.alloc(1);
+        P.so_slot.alloc(npp);
+        const uint32_t pad_key = P.T + 1;
+        k_so_keys<<<grid_for(npp, TB), TB, 0, s>>>(npp, P.q_bp0.p, P.q_bp1.p, key.p, val.p, pad_key);
+        TSKB_CK_LAUNCH();
+        size_t bytes = 0;
+        const int bits = (int) std::max(1u, ceil_log2((uint64_t) pad_key + 1));
+        TSKB_CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key.p, key_out.p, val.p, P.so_slot.p, npp, 0, bits, s));
+        DevArray<char> tmp;
+        tmp.alloc(bytes);
+        TSKB_CK(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, key.p, key_out.p, val.p, P.so_slot.p, npp, 0, bits, s));
+        TSKB_CK(cudaMemsetAsync(d_nsp.p, 0, sizeof(uint32_t), s));
+        k_so_count<<<grid_for(npp, TB), TB, 0, s>>>(npp, key_out.p, pad_key, d_nsp.p);
+        TSKB_CK_LAUNCH();
+        uint32_t h = 0;
+        TSKB_CK(cudaMemcpyAsync(&h, d_nsp.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+        TSKB_CK(cudaStreamSynchronize(s));
+        P.nsp = h;
+        P.so_bp0.alloc(h); P.so_bp1.alloc(h); P.so_bl.alloc(h);
+        if (h) {
+            k_so_gather<<<grid_for(h, TB), TB, 0, s>>>(h, P.so_slot.p, P.q_bp0.p, P.q_bp1.p, P.q_bl.p,
+                P.so_bp0.p, P.so_bp1.p, P.so_bl.p);
+            TSKB_CK_LAUNCH();
+        }
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
+    P.so_built = true;
+    P.stats.device_bytes = P.device_bytes();
+}
+
 template <int STAT, class V>
 void run_branch(CallCtx &c, V *pval, V totals) {
     const Plan &P = *c.P;
@@ -1163,8 +1379,59 @@ void run_branch(CallCtx &c, V *pval, V totals) {
     const size_t col_bytes = (size_t) Tp1 * sizeof(double);
     // 6 or more columns: lanes-are-columns kernel, at most 32 columns per pass
     const bool by_cols = M >= COLS_KERNEL_MIN && getenv("TSKB_NO_COLS_KERNEL") == nullptr;
-    uint32_t mc = (uint32_t) std::min<size_t>(M, std::max<size_t>(1, DELTA_BUDGET / col_bytes));
+    const char *cols_variant = getenv("TSKB_COLS_VARIANT");  // experiments: "old" = processing-order walk
+    const bool by_pos = by_cols && !(cols_variant != nullptr && cols_variant[0] == 'o');
+    size_t budget = DELTA_BUDGET;
+    if (by_pos) {
+        // the deltas of a column group may be large (their hot front stays in L2): up to a third of
+        // the free memory, so that all columns go through in as few walks over the pieces as possible
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            budget = std::max(budget, std::min<size_t>((free_b + A.cap) / 3, size_t(24) << 30));
+        }
+    }
+    uint32_t mc = (uint32_t) std::min<size_t>(M, std::max<size_t>(1, budget / col_bytes));
     if (by_cols) mc = std::min<uint32_t>(mc, 32);
+    if (by_pos) {
+        ensure_summary_order(P, c.s);
+        double *Dp = A.get<double>((size_t) mc * Tp1);  // [breakpoint][column] deltas
+        const uint32_t T = Tp1 - 1;
+        const uint32_t nchunks = (T + COLSCAN_ROWS - 1) / COLSCAN_ROWS;
+        double *partial = A.get<double>((size_t) std::max<uint32_t>(nchunks, 1) * mc);
+        launch_sweep<V>(c, pval);
+        TSKB_CK(cudaEventRecord(P.ev[2], c.s));
+        TSKB_CK(cudaMemsetAsync(c.d_result, 0, (size_t) c.sp->W * M * sizeof(double), c.s));
+        for (uint32_t m0 = 0; m0 < M; m0 += mc) {
+            const uint32_t nc = std::min(M, m0 + mc) - m0;
+            TSKB_CK(cudaMemsetAsync(Dp, 0, (size_t) nc * col_bytes, c.s));
+            DeltaOut ox = { Dp, Tp1, c.sumP.cols };
+            if (P.nsp > 0) {
+                const uint32_t nwarps = (P.nsp + BYPOS_CHUNK - 1) / BYPOS_CHUNK;
+                k_branch_summary_bypos<STAT, V><<<grid_for((size_t) nwarps * 32, TB), TB, 0, c.s>>>(P.nsp,
+                    P.so_slot.p, P.so_bp0.p, P.so_bp1.p, P.so_bl.p, pval, c.sumP, totals, ox, m0, nc);
+                TSKB_CK_LAUNCH();
+                c.launches++;
+            }
+            if (m0 == 0) TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+            if (T > 0) {
+                const int g = grid_for((size_t) nchunks * 32, TB);
+                k_colscan_partial<<<g, TB, 0, c.s>>>(Dp, T, nc, partial);
+                k_colscan_offsets<<<1, 1024, 0, c.s>>>(partial, nchunks, nc);
+                k_colscan_integrate<<<g, TB, 0, c.s>>>(Dp, T, nc, partial, P.bp_pos.p, c.d_windows, c.sp->W,
+                    m0, M, c.d_result);
+                TSKB_CK_LAUNCH();
+                c.launches += 3;
+            }
+            if (c.sp->options & TSKB_STAT_SPAN_NORMALISE) {
+                k_span_divide<<<grid_for((size_t) c.sp->W * nc, TB), TB, 0, c.s>>>(c.d_windows, c.sp->W, M, m0, nc,
+                    c.d_result);
+                TSKB_CK_LAUNCH();
+                c.launches++;
+            }
+        }
+        TSKB_CK(cudaEventRecord(P.ev[4], c.s));
+        return;
+    }
     double *D = A.get<double>((size_t) mc * Tp1);
     double *Dx = by_cols ? A.get<double>((size_t) mc * Tp1) : nullptr;  // [breakpoint][column] deltas
     size_t scan_bytes = 0;
@@ -1206,8 +1473,13 @@ void run_branch(CallCtx &c, V *pval, V totals) {
             // than exactly-resident persistent CTAs)
             int mult = std::max(per_sm, 16);
             if (const char *e = getenv("TSKB_SUM_GRID_MULT")) mult = std::max(1, atoi(e));  // experiments
-            const char *variant = getenv("TSKB_SUM_VARIANT");  // experiments: "lane" = one piece per lane
-            if (variant != nullptr && variant[0] == 'l') {
+            // default: one piece per lane (k_branch_summary).  TSKB_SUM_VARIANT=c4 selects the
+            // thread-contiguous kernel: measured on C2 (profiles/r2a_ab_summary.txt) it removes the MIO-throttle
+            // stalls (19.6 -> 1.1 cycles per issue) and a third of the instructions, and is 5 % SLOWER
+            // (1.014 vs 0.967 ms per step): the kernel is bound by the rate of scattered fp64 reductions in
+            // L2 (half of them cross the die-to-die fabric), not by instruction issue.
+            const char *variant = getenv("TSKB_SUM_VARIANT");
+            if (variant == nullptr || variant[0] != 'c') {
                 k_branch_summary<STAT, V><<<std::min<uint32_t>(ntiles, (uint32_t) (sms * mult)), SUM_TB, 0, c.s>>>(
                     P.npp, P.q_bp0.p, P.q_bp1.p, P.q_bl.p, pval, c.sumP, totals, out, m0, m1);
             } else {

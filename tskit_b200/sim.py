@@ -78,55 +78,77 @@ def repeat_genome(t: Tables, copies: int) -> Tables:
     own ancestors -- a genome of ``copies`` unlinked, identically distributed chromosomes.  Used to
     grow a workload along the genome (weak scaling over genome shards) at the cost of one
     simulation; any window statistic over copy r equals the statistic of ``t`` over the same
-    windows.  The result is in canonical order with its edge indexes built."""
+    windows."""
     t.ensure_derived()
     if copies <= 1:
         return t
-    L = float(t.sequence_length)
-    N0, E0, S0, M0 = t.num_nodes, t.num_edges, t.num_sites, t.num_mutations
-    is_s = (t.nodes_flags & 1).astype(bool)
-    ns = int(is_s.sum())
-    ni = N0 - ns
-    if is_s[t.edges_parent].any():
-        raise ValueError("repeat_genome needs sample nodes without children")
-    # node ids: samples first (shared by all copies), then the ancestors of copy 0, copy 1, ...
-    shared = np.cumsum(is_s) - 1
-    inner = ns + np.cumsum(~is_s) - 1
-    flags = np.concatenate([t.nodes_flags[is_s]] + [t.nodes_flags[~is_s]] * copies)
-    time = np.concatenate([t.nodes_time[is_s]] + [t.nodes_time[~is_s]] * copies)
+    return concat_genomes([t] * copies)
 
-    def node_map(u, r):
-        return np.where(is_s[u], shared[u], inner[u] + r * ni).astype(np.int32)
 
-    left = np.concatenate([t.edges_left + r * L for r in range(copies)])
-    right = np.concatenate([t.edges_right + r * L for r in range(copies)])
-    parent = np.concatenate([node_map(t.edges_parent, r) for r in range(copies)])
-    child = np.concatenate([node_map(t.edges_child, r) for r in range(copies)])
-    # canonical order (time[parent], parent, child, left): every copy is already sorted and parent
-    # ids grow with the copy, so a stable sort on the parent's time is enough
+def concat_genomes(parts) -> Tables:
+    """One tree sequence whose genome is the ``parts`` laid end to end (part r over
+    ``[sum of the lengths before it, ...)``): unlinked chromosomes of the same samples.  Every part
+    must have the same sample nodes (same flags and times, in the same order among the samples) and
+    no sample with children; ancestors are private to their part.  The result is in canonical order
+    with its edge indexes built from the parts' indexes (no global sort of the edges)."""
+    parts = [p.ensure_derived() for p in parts]
+    first = parts[0]
+    is_s0 = (first.nodes_flags & 1).astype(bool)
+    ns = int(is_s0.sum())
+    flags = [first.nodes_flags[is_s0]]
+    time = [first.nodes_time[is_s0]]
+    left, right, parent, child, ins, rem = [], [], [], [], [], []
+    sites = {k: [] for k in ("pos", "anc", "anc_off", "msite", "mnode", "mpar", "der", "der_off")}
+    x0, n_inner, e0, s0, m0, a0, d0 = 0.0, 0, 0, 0, 0, 0, 0
+    for t in parts:
+        is_s = (t.nodes_flags & 1).astype(bool)
+        if int(is_s.sum()) != ns or not np.array_equal(t.nodes_time[is_s], time[0]):
+            raise ValueError("concat_genomes needs the same samples in every part")
+        if t.num_edges and is_s[t.edges_parent].any():
+            raise ValueError("concat_genomes needs sample nodes without children")
+        shared = np.cumsum(is_s) - 1
+        inner = ns + n_inner + np.cumsum(~is_s) - 1
+        node_map = np.where(is_s, shared, inner).astype(np.int32)
+        flags.append(t.nodes_flags[~is_s])
+        time.append(t.nodes_time[~is_s])
+        left.append(t.edges_left + x0)
+        right.append(t.edges_right + x0)
+        parent.append(node_map[t.edges_parent])
+        child.append(node_map[t.edges_child])
+        ins.append(t.edge_insertion_order.astype(np.int64) + e0)
+        rem.append(t.edge_removal_order.astype(np.int64) + e0)
+        if t.num_sites:
+            sites["pos"].append(t.sites_position + x0)
+            sites["anc"].append(t.sites_ancestral_state)
+            sites["anc_off"].append(t.sites_ancestral_state_offset[:-1] + np.uint64(a0))
+            sites["msite"].append(t.mutations_site + s0)
+            sites["mnode"].append(node_map[t.mutations_node])
+            sites["mpar"].append(np.where(t.mutations_parent >= 0, t.mutations_parent + m0, -1))
+            sites["der"].append(t.mutations_derived_state)
+            sites["der_off"].append(t.mutations_derived_state_offset[:-1] + np.uint64(d0))
+            a0 += int(t.sites_ancestral_state_offset[-1])
+            d0 += int(t.mutations_derived_state_offset[-1])
+        x0 += float(t.sequence_length)
+        n_inner += int((~is_s).sum())
+        e0 += t.num_edges
+        s0 += t.num_sites
+        m0 += t.num_mutations
+    flags, time = np.concatenate(flags), np.concatenate(time)
+    parent = np.concatenate(parent)
+    # canonical order (time[parent], parent, child, left): every part is already sorted and parent
+    # ids grow with the part, so a stable sort on the parent's time is enough
     perm = np.argsort(time[parent], kind="stable")
     inv = np.empty(len(perm), dtype=np.int64)
     inv[perm] = np.arange(len(perm))
-    ins = inv[np.concatenate([t.edge_insertion_order.astype(np.int64) + r * E0 for r in range(copies)])]
-    rem = inv[np.concatenate([t.edge_removal_order.astype(np.int64) + r * E0 for r in range(copies)])]
     kw = {}
-    if S0:
-        kw["sites_position"] = np.concatenate([t.sites_position + r * L for r in range(copies)])
-        kw["sites_ancestral_state"] = np.tile(t.sites_ancestral_state, copies)
-        a_len = int(t.sites_ancestral_state_offset[-1])
-        kw["sites_ancestral_state_offset"] = np.concatenate(
-            [t.sites_ancestral_state_offset[:-1] + np.uint64(r * a_len) for r in range(copies)]
-            + [np.array([copies * a_len], dtype=np.uint64)])
-        kw["mutations_site"] = np.concatenate([t.mutations_site + r * S0 for r in range(copies)])
-        kw["mutations_node"] = np.concatenate([node_map(t.mutations_node, r) for r in range(copies)])
-        kw["mutations_parent"] = np.concatenate(
-            [np.where(t.mutations_parent >= 0, t.mutations_parent + r * M0, -1) for r in range(copies)])
-        kw["mutations_derived_state"] = np.tile(t.mutations_derived_state, copies)
-        d_len = int(t.mutations_derived_state_offset[-1])
-        kw["mutations_derived_state_offset"] = np.concatenate(
-            [t.mutations_derived_state_offset[:-1] + np.uint64(r * d_len) for r in range(copies)]
-            + [np.array([copies * d_len], dtype=np.uint64)])
-    return Tables(copies * L, flags, time, left[perm], right[perm], parent[perm], child[perm],
-                  time_uncalibrated=t.time_uncalibrated,
-                  edge_insertion_order=ins.astype(np.int32), edge_removal_order=rem.astype(np.int32),
-                  **kw)
+    if s0:
+        cat = np.concatenate
+        kw = dict(sites_position=cat(sites["pos"]), sites_ancestral_state=cat(sites["anc"]),
+                  sites_ancestral_state_offset=cat(sites["anc_off"] + [np.array([a0], dtype=np.uint64)]),
+                  mutations_site=cat(sites["msite"]), mutations_node=cat(sites["mnode"]),
+                  mutations_parent=cat(sites["mpar"]), mutations_derived_state=cat(sites["der"]),
+                  mutations_derived_state_offset=cat(sites["der_off"] + [np.array([d0], dtype=np.uint64)]))
+    return Tables(x0, flags, time, np.concatenate(left)[perm], np.concatenate(right)[perm], parent[perm],
+                  np.concatenate(child)[perm], time_uncalibrated=first.time_uncalibrated,
+                  edge_insertion_order=inv[np.concatenate(ins)].astype(np.int32),
+                  edge_removal_order=inv[np.concatenate(rem)].astype(np.int32), **kw)
