@@ -74,6 +74,28 @@ def test_all_statistics_wright_fisher(wf_small, engines, mode, polarised):
         assert close(got, want, cancelling=True)
 
 
+@pytest.mark.parametrize("variant", ["lane", "c4"])
+def test_branch_summary_kernel_variants(wf_small, engines, monkeypatch, variant):
+    """The default branch summary is the shared-memory window-bin kernel; the per-breakpoint delta
+    kernels (one piece per lane; four pieces per thread) stay selectable and must agree with the oracle."""
+    ll, o = engines
+    s = wf_small.samples
+    sets = [s[:50], s[50:120], s[120:]]
+    sizes, flat = sets_args(sets)
+    monkeypatch.setenv("TSKB_SUM_VARIANT", variant)
+    for windows in (np.linspace(0, wf_small.sequence_length, 8),
+                    np.array([0.0, 10.5, 11.0, 50000.25, wf_small.sequence_length])):
+        for polarised in (False, True):
+            for name in ONE_WAY:
+                got = getattr(ll, name)(sizes, flat, windows=windows, mode="branch", polarised=polarised)
+                assert close(got, o.stat(name, sets, windows=windows, mode="branch", polarised=polarised)), name
+            for name, idx in K_WAY.items():
+                got = getattr(ll, name)(sizes, flat, np.array(idx, dtype=np.int32), windows=windows,
+                                        mode="branch", polarised=polarised)
+                want = o.stat(name, sets, idx, windows=windows, mode="branch", polarised=polarised)
+                assert close(got, want, cancelling=True), name
+
+
 @pytest.mark.parametrize("mode", ["branch", "site"])
 def test_span_normalise_off_and_many_windows(wf_small, engines, mode):
     ll, o = engines
@@ -152,10 +174,25 @@ def test_many_result_columns(wf_small, engines, monkeypatch):
         assert close(ll.f4(sizes, flat, quads, windows=w, mode="branch"), want4, cancelling=True)
         want1 = o.stat("Y1", sets, windows=w, mode="branch", polarised=True)
         assert close(ll.Y1(sizes, flat, windows=w, mode="branch", polarised=True), want1)
-        monkeypatch.setenv("TSKB_NO_COLS_KERNEL", "1")
-        assert close(ll.divergence(sizes, flat, pairs, windows=w, mode="branch"), want)
-        assert close(ll.f4(sizes, flat, quads, windows=w, mode="branch"), want4, cancelling=True)
-        monkeypatch.delenv("TSKB_NO_COLS_KERNEL")
+        # the calls above fit the shared-memory window bins; the per-breakpoint delta formulation:
+        # pieces walked by start breakpoint (default for many columns), in processing order with
+        # lanes = columns (the earlier kernel), and one column at a time
+        monkeypatch.setenv("TSKB_SUM_VARIANT", "lane")
+        for extra in ({}, {"TSKB_COLS_VARIANT": "old"}, {"TSKB_NO_COLS_KERNEL": "1"}):
+            for k, v in extra.items():
+                monkeypatch.setenv(k, v)
+            assert close(ll.divergence(sizes, flat, pairs, windows=w, mode="branch"), want), extra
+            assert close(ll.f4(sizes, flat, quads, windows=w, mode="branch"), want4, cancelling=True), extra
+            assert close(ll.Y1(sizes, flat, windows=w, mode="branch", polarised=True), want1), extra
+            for k in extra:
+                monkeypatch.delenv(k)
+        monkeypatch.delenv("TSKB_SUM_VARIANT")
+    # many columns AND too many windows for the bins: the walk by start breakpoint on its own merits
+    w = np.linspace(0, wf_small.sequence_length, 3001)
+    pairs = np.array([(i, j) for i in range(8) for j in range(i, 8)], dtype=np.int32)
+    for sn in (True, False):
+        assert close(ll.divergence(sizes, flat, pairs, windows=w, mode="branch", span_normalise=sn),
+                     o.stat("divergence", sets, pairs, windows=w, mode="branch", span_normalise=sn))
 
 
 @pytest.mark.parametrize("mode", ["branch", "site"])

@@ -34,7 +34,7 @@ uint64_t Plan::device_bytes() const {
            + q_bl.bytes() + q_eff.bytes() + q_node.bytes() + node_first_bp.bytes() + tile_dep.bytes() + d_sample_index.bytes() + pm_off.bytes() + pm_left.bytes()
            + pm_right.bytes() + pm_pmax.bytes() + pm_child.bytes() + rank_node.bytes() + level.bytes() + site_pos.bytes() + site_moff.bytes()
            + site_aoff.bytes() + mut_node.bytes() + mut_src.bytes() + mut_allele.bytes()
-           + mut_alt.bytes() + so_slot.bytes() + so_bp0.bytes() + so_bp1.bytes() + so_bl.bytes();
+           + mut_alt.bytes() + so_slot.bytes() + so_bp0.bytes() + so_bp1.bytes() + so_bl.bytes() + q_x0.bytes() + q_x1.bytes();
 }
 
 namespace {

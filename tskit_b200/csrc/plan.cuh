@@ -133,6 +133,10 @@ struct Plan {
     mutable uint32_t nsp = 0;
     mutable DevArray<uint32_t> so_slot, so_bp0, so_bp1;  // [nsp]
     mutable DevArray<double> so_bl;                      // [nsp]
+    // --- positions of every piece's ends (built on the first call of the window-bin summary,
+    //     stats.cu:ensure_piece_positions): bp_pos[q_bp0], bp_pos[q_bp1] in processing order
+    mutable bool qx_built = false;
+    mutable DevArray<double> q_x0, q_x1;                 // [npp]
 
     // per-call scratch + statistics
     mutable std::mutex mu;

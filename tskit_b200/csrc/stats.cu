@@ -572,6 +572,142 @@ __global__ void __launch_bounds__(SUMC_TB) k_branch_summary_c4(uint32_t npp,
     }
 }
 
+// ---- window bins in shared memory (few windows, finite summaries): no per-breakpoint deltas at all
+// A piece [x0, x1) with G = branch_length x F(state) adds G x |[x0, x1) meet window| to every window.
+// Written as two EVENTS -- (x0, +G) and (x1, -G) -- an event (x, v) in window w adds
+//     C[w] += v,   P[w] -= v (x - left edge of w)
+// and window w's integral is  P[w] + span(w) x (C[0] + ... + C[w])  (k_bins_finalize): the prefix of C is
+// the running sum S at the window's right edge, P takes back what lies left of each event.  Abutting
+// pieces of neighbouring lanes share an event of G_next - G.  The bins of a CTA live in shared memory
+// (compare-and-swap additions: few and mostly uncontended), and are added to the global bins once per
+// CTA: the scattered fp64 reductions in L2 of the delta formulation, which bound it at ~100 G/s,
+// are gone, and so are the scan over the breakpoints and the window integration.
+struct BinArgs {
+    const double *windows;  // [W + 1] (device)
+    uint32_t W;
+    double w0, inv_width;   // uniform windows: index guess (x - w0) * inv_width, then corrected
+    int uniform;
+    double *gP, *gC;        // [ncols][W] global bins
+};
+
+__device__ __forceinline__ uint32_t bin_of(const double *win, const BinArgs &b, double x) {
+    uint32_t w;
+    if (b.uniform) {
+        const double g = (x - b.w0) * b.inv_width;
+        w = g <= 0.0 ? 0u : (g >= (double) b.W ? b.W : (uint32_t) g);
+        while (w > 0 && x < win[w]) w--;
+        while (w < b.W && x >= win[w + 1]) w++;
+    } else {
+        w = upper_bound_dev(win, b.W + 1, x);
+        w = w > 0 ? w - 1 : 0;
+    }
+    return w;  // == W: at or beyond the last edge (no window)
+}
+
+__device__ __forceinline__ void bin_event(double *sP, double *sC, const double *win, const BinArgs &b,
+    double x, double v) {
+    const uint32_t w = bin_of(win, b, x);
+    if (w < b.W) {
+        atomicAdd(sC + w, v);
+        atomicAdd(sP + w, -(v * (x - win[w])));
+    }
+}
+
+template <class V>
+struct PieceX {
+    V st;
+    double bl, x0, x1;
+    __device__ __forceinline__ void load(uint32_t j, const double *__restrict__ q_x0,
+        const double *__restrict__ q_x1, const double *__restrict__ q_bl, const V *__restrict__ pval) {
+        st = pval[j]; bl = q_bl[j]; x0 = q_x0[j]; x1 = q_x1[j];
+    }
+};
+
+template <int STAT, class V>
+__global__ void __launch_bounds__(SUM_TB) k_branch_summary_bins(uint32_t npp,
+    const double *__restrict__ q_x0, const double *__restrict__ q_x1, const double *__restrict__ q_bl,
+    const V *__restrict__ pval, SumP sp, V totals, const ColP *cols, uint32_t m0, uint32_t ncols, BinArgs b) {
+    extern __shared__ double smem_bins[];
+    double *win = smem_bins;                       // [W + 1]
+    double *sP = win + b.W + 1;                    // [ncols][W]
+    double *sC = sP + (size_t) ncols * b.W;        // [ncols][W]
+    for (uint32_t i = threadIdx.x; i <= b.W; i += blockDim.x) win[i] = b.windows[i];
+    for (uint32_t i = threadIdx.x; i < 2 * ncols * b.W; i += blockDim.x) sP[i] = 0.0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ntiles = npp / SUM_TB;  // npp is a multiple of PROP_TILE, itself a multiple of SUM_TB
+    const ColP first_col = cols[m0];
+    PieceX<V> cur, nxt;
+    uint32_t tile = blockIdx.x;
+    if (tile < ntiles) cur.load(tile * SUM_TB + threadIdx.x, q_x0, q_x1, q_bl, pval);
+    for (; tile < ntiles; tile += gridDim.x) {
+        const uint32_t tn = tile + gridDim.x;
+        if (tn < ntiles) nxt.load(tn * SUM_TB + threadIdx.x, q_x0, q_x1, q_bl, pval);
+        // padding has x1 < 0; pieces without a branch above them add nothing (finite summaries only here)
+        const bool valid = cur.x1 >= 0.0;
+        const bool live = valid && cur.bl != 0.0;
+        const double next_x0 = __shfl_down_sync(0xffffffffu, cur.x0, 1);
+        const double prev_x1 = __shfl_up_sync(0xffffffffu, cur.x1, 1);
+        const bool merged_next = valid && lane < 31u && next_x0 == cur.x1;
+        const bool merged_prev = valid && lane > 0u && prev_x1 == cur.x0;
+        for (uint32_t c = 0; c < ncols; c++) {
+            const uint32_t m = m0 + c;
+            const ColP col = c == 0 ? first_col : cols[m];
+            double G = 0.0;
+            if (live) G = cur.bl * F_branch<STAT, V>(sp, col, m, cur.st, totals);
+            const double G_prev = __shfl_up_sync(0xffffffffu, G, 1);
+            if (!valid) continue;
+            double *cP = sP + (size_t) c * b.W, *cC = sC + (size_t) c * b.W;
+            const double v = merged_prev ? G - G_prev : G;
+            if (v != 0.0) bin_event(cP, cC, win, b, cur.x0, v);
+            if (!merged_next && G != 0.0) bin_event(cP, cC, win, b, cur.x1, -G);
+        }
+        cur = nxt;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < ncols * b.W; i += blockDim.x) {
+        const double p = sP[i], q = sC[i];
+        if (p != 0.0) atomicAdd(b.gP + i, p);
+        if (q != 0.0) atomicAdd(b.gC + i, q);
+    }
+}
+
+__global__ void k_piece_positions(uint32_t npp, const uint32_t *__restrict__ q_bp0,
+    const uint32_t *__restrict__ q_bp1, const double *__restrict__ bp_pos, double *x0, double *x1) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npp) return;
+    const uint32_t b1 = q_bp1[j];
+    x0[j] = b1 == NO_PIECE ? 0.0 : bp_pos[q_bp0[j]];
+    x1[j] = b1 == NO_PIECE ? -1.0 : bp_pos[b1];  // bp_pos[T] = end of the range
+}
+
+// window w of column c: P + span x (inclusive prefix of C); one warp per column
+__global__ void k_bins_finalize(const double *__restrict__ gP, const double *__restrict__ gC,
+    const double *__restrict__ windows, uint32_t W, uint32_t ncols, uint32_t m0, uint32_t M, int span_normalise,
+    double *result) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncols) return;
+    double run = 0.0;
+    for (uint32_t base = 0; base < W; base += 32) {
+        const uint32_t w = base + lane;
+        double v = w < W ? gC[(size_t) c * W + w] : 0.0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double u = __shfl_up_sync(0xffffffffu, v, d);
+            if ((int) lane >= d) v += u;
+        }
+        const double S = run + v;
+        run += __shfl_sync(0xffffffffu, v, 31);
+        if (w < W) {
+            const double span = windows[w + 1] - windows[w];
+            double r = gP[(size_t) c * W + w] + span * S;
+            if (span_normalise) r /= span;
+            result[(size_t) w * M + m0 + c] = r;
+        }
+    }
+}
+
 // ---- many result columns: lanes are columns
 // With M columns the kernel above issues M reductions per piece, each lane of an instruction to
 // its own cache line.  Here a warp walks its pieces one after the other and lane m evaluates
@@ -1370,8 +1506,82 @@ void ensure_summary_order(const Plan &P, cudaStream_t s) {
     P.stats.device_bytes = P.device_bytes();
 }
 
+void ensure_piece_positions(const Plan &P, cudaStream_t s) {
+    if (P.qx_built) return;
+    P.q_x0.alloc(P.npp);
+    P.q_x1.alloc(P.npp);
+    if (P.npp) {
+        k_piece_positions<<<grid_for(P.npp, TB), TB, 0, s>>>(P.npp, P.q_bp0.p, P.q_bp1.p, P.bp_pos.p, P.q_x0.p,
+            P.q_x1.p);
+        TSKB_CK_LAUNCH();
+        TSKB_CK(cudaStreamSynchronize(s));
+    }
+    P.qx_built = true;
+    P.stats.device_bytes = P.device_bytes();
+}
+
+constexpr size_t BINS_SMEM_MAX = 160 * 1024;  // leaves room for more than one CTA of small-W calls per SM
+
+// Window bins in shared memory: finite summaries, and windows x columns small enough.  Returns false
+// when the call does not qualify (the delta formulation runs instead).
+template <int STAT, class V>
+bool run_branch_bins(CallCtx &c, V *pval, V totals) {
+    const Plan &P = *c.P;
+    const uint32_t M = c.sp->M, W = c.sp->W;
+    const char *variant = getenv("TSKB_SUM_VARIANT");
+    if (variant != nullptr && variant[0] != 'b') return false;  // experiments: force another kernel
+    if (!c.sumP.skip_zero_bl || P.npp == 0 || P.T == 0) return false;
+    if ((size_t) (3 * (size_t) W + 1) * sizeof(double) > BINS_SMEM_MAX) return false;
+    const uint32_t mc = (uint32_t) std::min<size_t>(M, (BINS_SMEM_MAX / sizeof(double) - W - 1) / (2 * (size_t) W));
+    // many columns that do not fit one pass: the walk by start breakpoint (lanes = columns) reads the
+    // states once for up to 32 columns
+    if (M >= COLS_KERNEL_MIN && mc < M) return false;
+    Arena &A = P.arena;
+    ensure_piece_positions(P, c.s);
+    double *gP = A.get<double>((size_t) 2 * mc * W);
+    double *gC = gP + (size_t) mc * W;
+    // uniform windows (np.linspace): the window of a position is a multiplication away
+    const double *w = c.sp->windows;
+    BinArgs b = {};
+    b.windows = c.d_windows; b.W = W; b.w0 = w[0]; b.inv_width = (double) W / (w[W] - w[0]); b.uniform = 1;
+    for (uint32_t i = 0; i <= W && b.uniform; i++) {
+        const double ideal = w[0] + (w[W] - w[0]) * ((double) i / (double) W);
+        if (fabs(w[i] - ideal) * b.inv_width > 0.25) b.uniform = 0;
+    }
+    b.gP = gP; b.gC = gC;
+    launch_sweep<V>(c, pval);
+    TSKB_CK(cudaEventRecord(P.ev[2], c.s));
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
+    auto kern = k_branch_summary_bins<STAT, V>;
+    TSKB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) BINS_SMEM_MAX));
+    for (uint32_t m0 = 0; m0 < M; m0 += mc) {
+        const uint32_t nc = std::min(M, m0 + mc) - m0;
+        const size_t smem = ((size_t) W + 1 + 2 * (size_t) nc * W) * sizeof(double);
+        TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SUM_TB, smem));
+        int mult = std::max(per_sm, 1);
+        if (const char *e = getenv("TSKB_BINS_GRID_MULT")) mult = std::max(1, atoi(e));  // experiments
+        const uint32_t ntiles = P.npp / SUM_TB;
+        TSKB_CK(cudaMemsetAsync(gP, 0, (size_t) 2 * mc * W * sizeof(double), c.s));
+        // gC of this column group must follow its gP: both live in one block of 2 * mc * W doubles
+        b.gP = gP; b.gC = gP + (size_t) nc * W;
+        kern<<<std::min<uint32_t>(ntiles, (uint32_t) (sms * mult)), SUM_TB, smem, c.s>>>(P.npp, P.q_x0.p, P.q_x1.p,
+            P.q_bl.p, pval, c.sumP, totals, c.sumP.cols, m0, nc, b);
+        TSKB_CK_LAUNCH();
+        c.launches++;
+        if (m0 == 0) TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+        k_bins_finalize<<<grid_for((size_t) nc * 32, TB), TB, 0, c.s>>>(b.gP, b.gC, c.d_windows, W, nc, m0, M,
+            (c.sp->options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0, c.d_result);
+        TSKB_CK_LAUNCH();
+        c.launches++;
+    }
+    TSKB_CK(cudaEventRecord(P.ev[4], c.s));
+    return true;
+}
+
 template <int STAT, class V>
 void run_branch(CallCtx &c, V *pval, V totals) {
+    if (run_branch_bins<STAT, V>(c, pval, totals)) return;
     const Plan &P = *c.P;
     const uint32_t M = c.sp->M;
     Arena &A = P.arena;
