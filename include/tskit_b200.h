@@ -209,8 +209,11 @@ int tskb_treeseq_genetic_relatedness_vector(const tskb_treeseq_t *self, uint64_t
 
 /* tsk_treeseq_allele_frequency_spectrum (c/tskit/trees.h:1112-1116; trees.c:3814-3928), site and
  * branch mode: result [num_windows x prod(sample_set_sizes[k] + 1)], row-major over the sets; folded
- * unless TSK_STAT_POLARISED.  time_windows NULL or {0, inf}: other time windows in branch mode,
- * negative node times in branch mode and more than 7 sample sets return TSKB_ERR_UNSUPPORTED. */
+ * [num_windows x num_time_windows x prod(...)] with time windows (branch mode; trees.c:3663-3680);
+ * folded unless TSK_STAT_POLARISED.  Any number of sample sets up to 64 (beyond 7 the spectrum
+ * coordinate travels as one fp64 state column).  Time windows other than {0, inf}, or negative node
+ * times, need an engine built with TSKB_INIT_NODE_MODE (TSKB_ERR_UNSUPPORTED otherwise); more than
+ * 2e9 output cells: TSKB_ERR_UNSUPPORTED. */
 int tskb_treeseq_allele_frequency_spectrum(const tskb_treeseq_t *self, uint64_t num_sample_sets,
     const uint64_t *sample_set_sizes, const int32_t *sample_sets, uint64_t num_windows,
     const double *windows, uint64_t num_time_windows, const double *time_windows, uint32_t options,

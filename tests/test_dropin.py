@@ -295,11 +295,31 @@ def test_site_afs_through_dropin(ts, wf_small):
                     assert got.shape == want.shape
                     assert np.allclose(got, want, rtol=1e-9, atol=1e-12 * np.abs(want).max()), (len(sets), pol, span)
     assert acc.accel_stats["forwarded"] == 0
-    # time windows other than [0, inf): forwarded, visibly
-    tw = [0, 10.0, np.inf]
-    b = acc.allele_frequency_spectrum([s[:50]], mode="branch", time_windows=tw)
-    assert np.allclose(b, ts.allele_frequency_spectrum([s[:50]], mode="branch", time_windows=tw))
-    assert acc.accel_stats["forwarded"] == 1
+    # time windows other than [0, inf) (trees.c:3663-3680): every branch is split by time, on the engine
+    # that keeps the node of every piece (staged on first use)
+    tmax = float(ts.nodes_time.max())
+    for tw in ([0, 10.0, np.inf], [0, 3.0, 25.0, 100.0], [0, 0.5 * tmax, tmax, 2 * tmax]):
+        for sets in ([s[:50]], [s[:20], s[20:45]]):
+            for pol in (False, True):
+                for win in (w, None):
+                    got = acc.allele_frequency_spectrum(sets, windows=win, mode="branch", time_windows=tw,
+                                                        polarised=pol)
+                    want = ts.allele_frequency_spectrum(sets, windows=win, mode="branch", time_windows=tw,
+                                                        polarised=pol)
+                    assert got.shape == want.shape
+                    assert np.allclose(got, want, rtol=1e-9, atol=1e-12 * np.abs(want).max()), (tw, len(sets), pol)
+    # more than 7 sample sets: the spectrum coordinate travels as one state column
+    many = [s[3 * i: 3 * i + 2 + (i % 2)] for i in range(9)]  # 9 sets of 2-3 samples: 3^5 4^4 cells
+    for mode in ("site", "branch"):
+        for pol in (False, True):
+            got = acc.allele_frequency_spectrum(many, windows=w, mode=mode, polarised=pol)
+            want = ts.allele_frequency_spectrum(many, windows=w, mode=mode, polarised=pol)
+            assert got.shape == want.shape
+            assert np.allclose(got, want, rtol=1e-9, atol=1e-12 * np.abs(want).max()), (mode, pol)
+    got = acc.allele_frequency_spectrum(many, windows=w, mode="branch", time_windows=[0, 5.0, np.inf])
+    want = ts.allele_frequency_spectrum(many, windows=w, mode="branch", time_windows=[0, 5.0, np.inf])
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-12 * np.abs(want).max())
+    assert acc.accel_stats["forwarded"] == 0
 
 
 @pytest.mark.gpu

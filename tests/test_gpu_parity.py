@@ -213,6 +213,12 @@ def test_more_sample_sets_than_one_sweep_carries(wf_small, engines, mode):
     idx = np.array([[0, 19], [7, 7]], dtype=np.int32)
     got = ll.genetic_relatedness(sizes, flat, idx, windows=w, mode=mode, centre=False)
     assert close(got, o.stat("genetic_relatedness", sets, idx, windows=w, mode=mode, centre=False), cancelling=True)
+    # centred: the mean over ALL 20 sets (trees.c:4729-4753) travels as one extra fp64 state column
+    idx = rng.integers(0, 20, size=(23, 2)).astype(np.int32)
+    for polarised in (True, False):
+        got = ll.genetic_relatedness(sizes, flat, idx, windows=w, mode=mode, centre=True, polarised=polarised)
+        want = o.stat("genetic_relatedness", sets, idx, windows=w, mode=mode, centre=True, polarised=polarised)
+        assert close(got, want, cancelling=True), polarised
 
 
 @pytest.mark.parametrize("name", list(fx.ALL))

@@ -12,8 +12,7 @@ tail -3 $OUT/pytest_gpu.log
 python bench.py --steps 20 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
 head -c 3000 $OUT/bench.json; echo
 # A/B of the branch-summary variants (same box, same plan; device-timed, no CPU legs)
-for v in "c4:" "lane:TSKB_SUM_VARIANT=lane" "c4m8:TSKB_SUM_GRID_MULT=8" "c4m32:TSKB_SUM_GRID_MULT=32" \
-         "tb128:TSKB_LIB=$PWD/tskit_b200/libtskb_tb128.so" "tb512:TSKB_LIB=$PWD/tskit_b200/libtskb_tb512.so"; do
+for v in "lane:" "bins:TSKB_SUM_VARIANT=bins"; do
     name=${v%%:*}; envs=${v#*:}
     if [ -n "$envs" ] && [[ "$envs" == TSKB_LIB=* ]] && [ ! -f "${envs#TSKB_LIB=}" ]; then continue; fi
     env $envs python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ab_$name.json 2> $OUT/ab_$name.err
@@ -26,6 +25,21 @@ except Exception as e:
     print(sys.argv[2], "failed", e)
 EOF
 done
+# the other config shapes (C1, C3 shape on the C2 ARG, C5), and the many-column path old vs new
+timeout 600 python tools/probe_configs.py > $OUT/probe_configs.json 2> $OUT/probe_configs.err; echo "probe exit $?"
+TSKB_COLS_VARIANT=old TSKB_SUM_VARIANT=lane timeout 600 python tools/probe_configs.py > $OUT/probe_configs_oldcols.json 2> $OUT/probe_configs_oldcols.err
+TSKB_COLS_MIN=2 timeout 600 python tools/probe_configs.py > $OUT/probe_configs_colsmin2.json 2> $OUT/probe_configs_colsmin2.err
+python - $OUT <<'EOF2'
+import json, sys
+for f in ("probe_configs.json", "probe_configs_oldcols.json", "probe_configs_colsmin2.json"):
+    try:
+        d = json.load(open(sys.argv[1] + "/" + f))
+        c3 = d["c3_shape_on_c2_arg_8_sets"]
+        print(f, {k: (round(v, 3) if isinstance(v, float) else [round(x, 3) for x in v]) for k, v in c3.items() if "branch" in k})
+        print("   c5", d["c5_custom_summary_1e6_windows"])
+    except Exception as e:
+        print(f, "failed", e)
+EOF2
 # phases of tskb_treeseq_init on C2 (second init in the process: context and modules already loaded)
 TSKB_TIMING=1 python - > $OUT/init_phases.txt 2>&1 <<'EOF'
 import time, bench
@@ -45,10 +59,10 @@ KREGEX='regex:(k_set_weights|k_sweep|k_branch_summary|k_window|k_site_summary|De
 TSKB_BENCH_BLOCKS=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 600 \
     --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_launch.log 2>&1
 echo "ncu launches exit $?"
-TSKB_BENCH_BLOCKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_branch_summary -s 6 -c 2 \
+TSKB_BENCH_BLOCKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_branch_summary -s 6 -c 1 \
     -o $OUT/prof_summary -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_sum.log 2>&1
 echo "ncu summary exit $?"
-TSKB_BENCH_BLOCKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 6 -c 2 \
+TSKB_BENCH_BLOCKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 6 -c 1 \
     -o $OUT/prof_sweep -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_prop.log 2>&1
 echo "ncu sweep exit $?"
 fi

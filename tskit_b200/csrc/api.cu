@@ -105,10 +105,37 @@ constexpr uint64_t MAX_STATE_DIM = 8;  // sample sets (state columns) of one swe
 // tuples touch at most MAX_STATE_DIM distinct sets, each batch one sweep over re-numbered sets.
 // The centred genetic_relatedness reads every set in every column (the mean over all sets,
 // trees.c:4899-4959) and cannot be split.
+int weighted_stat(const tskb_treeseq_t *self, int stat_id, uint64_t cols, const std::vector<double> &W,
+    uint64_t result_dim, int tw, const int32_t *tuples, uint64_t num_windows, const double *windows,
+    uint32_t options, double *result, const double *table = nullptr, uint64_t table_rows = 0);
+
+// The centred genetic_relatedness reads every set in every column: the mean over all K sets
+// (trees.c:4729-4753).  Beyond one sweep's worth of sets that mean travels as ONE extra fp64 state
+// column -- per sample, the sum of 1/n_k over the sets holding it -- next to the 0/1 indicator
+// columns of the sets a batch of columns needs (counts are exact in fp64), through the weighted
+// engine and its column batching.
+int centred_relatedness_many_sets(const tskb_treeseq_t *self, uint64_t K, const uint64_t *sizes,
+    const int32_t *sets, uint64_t M, const int32_t *tuples, uint64_t W, const double *windows,
+    uint32_t options, double *result) {
+    const Plan &P = *self->plan;
+    const uint64_t n = P.num_samples, cols = K + 1;
+    std::vector<double> Wt(n * cols, 0.0);
+    uint64_t j = 0;
+    for (uint64_t k = 0; k < K; k++) {
+        const double inv = 1.0 / (double) sizes[k];
+        for (uint64_t l = 0; l < sizes[k]; l++, j++) {
+            const int32_t si = P.sample_index_map[sets[j]];  // validated by check_sample_sets
+            Wt[(uint64_t) si * cols + k] = 1.0;
+            Wt[(uint64_t) si * cols + K] += inv;
+        }
+    }
+    return weighted_stat(self, STAT_REL_SIDE, cols, Wt, M, 2, tuples, W, windows, options, result, nullptr, K);
+}
+
 int batched_sample_count_stat(const Plan &P, int stat_id, int tw, uint64_t K, const uint64_t *sizes,
     const int32_t *sets, uint64_t M, const int32_t *tuples, uint64_t W, const double *windows,
     uint32_t options, double *result) {
-    if (stat_id == STAT_RELATEDNESS) return TSKB_ERR_UNSUPPORTED;
+    if (stat_id == STAT_RELATEDNESS) return TSKB_ERR_UNSUPPORTED;  // centred_relatedness_many_sets
     std::vector<uint64_t> off(K + 1, 0);
     for (uint64_t k = 0; k < K; k++) off[k + 1] = off[k] + sizes[k];
     const int width = tw > 0 ? tw : 1;
@@ -249,6 +276,10 @@ int sample_count_stat(const tskb_treeseq_t *self, int stat_id, uint64_t K, const
         if (stat_id == STAT_TABULATED && K != 1) LATER(TSKB_ERR_UNSUPPORTED);
         if (K > MAX_STATE_DIM) {
             if (sets_on_device || result_on_device) LATER(TSKB_ERR_UNSUPPORTED);
+            if (stat_id == STAT_RELATEDNESS) {
+                return centred_relatedness_many_sets(self, K, sizes, sets, M, tuples, num_windows, windows,
+                    options, result);
+            }
             return batched_sample_count_stat(P, stat_id, tw, K, sizes, sets, M, tuples, num_windows,
                 windows, options, result);
         }
@@ -405,7 +436,7 @@ namespace {
 // (trees.c:2035-2095): mode -> dims -> windows -> time units.
 int weighted_stat(const tskb_treeseq_t *self, int stat_id, uint64_t cols, const std::vector<double> &W,
     uint64_t result_dim, int tw, const int32_t *tuples, uint64_t num_windows, const double *windows,
-    uint32_t options, double *result, const double *table = nullptr, uint64_t table_rows = 0) {
+    uint32_t options, double *result, const double *table, uint64_t table_rows) {
     const Plan &P = *self->plan;
     return guarded([&]() -> int {
         bool site = options & TSKB_STAT_SITE, branch = options & TSKB_STAT_BRANCH,
@@ -453,7 +484,7 @@ int weighted_stat(const tskb_treeseq_t *self, int stat_id, uint64_t cols, const 
                     if (x < 0) x = (int32_t) kb - 1;
                 }
                 int ret = weighted_stat(self, stat_id, kb, Wb, Mb, tw, tw > 0 ? b_tuples.data() : nullptr,
-                    num_windows, windows, options, out.data());
+                    num_windows, windows, options, out.data(), table, table_rows);
                 if (ret != 0) return ret;
                 for (uint64_t w = 0; w < num_windows; w++) {
                     for (uint64_t q = 0; q < Mb; q++) result[w * result_dim + b_cols[q]] = out[w * Mb + q];
@@ -751,35 +782,70 @@ int tskb_treeseq_allele_frequency_spectrum(const tskb_treeseq_t *self, uint64_t 
         if (branch && P.time_uncalibrated && !(options & TSKB_STAT_ALLOW_TIME_UNCALIBRATED)) {
             return TSKB_ERR_TIME_UNCALIBRATED;  // trees.c:3727
         }
-        // on the device: the default time window (with node times >= 0 the branch length inside it is
-        // the whole branch) and at most 7 sets (plus the all-samples column: one sweep's state)
+        // the default time window with node times >= 0: the branch length inside it is the whole branch;
+        // any other time windows split every branch by time, which needs the node of every piece
+        // (TSKB_INIT_NODE_MODE plans keep it; lowlevel.py stages one on first use)
         const bool default_tw = time_windows == nullptr
                                 || (num_time_windows == 1 && time_windows[0] == 0.0 && std::isinf(time_windows[1]));
-        if ((branch && (!default_tw || P.has_negative_time)) || num_sample_sets + 1 > MAX_STATE_DIM) {
-            return TSKB_ERR_UNSUPPORTED;
+        const bool by_time = branch && (!default_tw || P.has_negative_time);
+        if (by_time && !P.all_pieces) return TSKB_ERR_UNSUPPORTED;
+        const double default_tws[2] = { 0.0, INFINITY };
+        if (time_windows == nullptr) {
+            num_time_windows = 1;
+            time_windows = default_tws;
         }
-        // state columns: the sets, then all samples (trees.c:3890-3910)
-        std::vector<uint64_t> sizes(sample_set_sizes, sample_set_sizes + num_sample_sets);
         uint64_t total = 0, afs_size = 1;
+        std::vector<uint32_t> dims;
         for (uint64_t k = 0; k < num_sample_sets; k++) {
-            total += sizes[k];
-            afs_size *= sizes[k] + 1;
-            if (afs_size * num_windows > (uint64_t) 2e9) return TSKB_ERR_UNSUPPORTED;
+            total += sample_set_sizes[k];
+            afs_size *= sample_set_sizes[k] + 1;
+            dims.push_back((uint32_t) sample_set_sizes[k] + 1);
+            if (afs_size * num_windows * num_time_windows > (uint64_t) 2e9) return TSKB_ERR_UNSUPPORTED;
         }
-        std::vector<int32_t> sets(sample_sets, sample_sets + total);
-        sets.insert(sets.end(), P.samples.begin(), P.samples.end());
-        sizes.push_back(P.num_samples);
         StatSpec sp = {};
         sp.stat_id = STAT_AFS;
-        sp.K = (uint32_t) sizes.size();
         sp.M = 1;
-        sp.sizes = sizes.data();
-        sp.sets = sets.data();
         sp.W = (uint32_t) num_windows;
         sp.windows = windows;
         sp.options = options;
         sp.result = result;
         sp.afs_size = afs_size;
+        sp.num_time_windows = (uint32_t) num_time_windows;
+        sp.time_windows = by_time ? time_windows : nullptr;
+        if (num_sample_sets + 1 > MAX_STATE_DIM) {
+            // more than 7 sets: the spectrum's row-major coordinate is linear in the per-set counts, so it
+            // travels as one fp64 state column (exact), next to the all-samples count
+            if (num_sample_sets > 64 || afs_size >= (uint64_t(1) << 52)) return TSKB_ERR_UNSUPPORTED;
+            const uint64_t n = P.num_samples;
+            std::vector<double> Wt(n * 2, 0.0), totals(2, 0.0);
+            std::vector<double> stride(num_sample_sets, 1.0);
+            for (uint64_t k = num_sample_sets; k-- > 1;) stride[k - 1] = stride[k] * (double) dims[k];
+            uint64_t j = 0;
+            for (uint64_t k = 0; k < num_sample_sets; k++) {
+                for (uint64_t l = 0; l < sample_set_sizes[k]; l++, j++) {
+                    Wt[(uint64_t) P.sample_index_map[sample_sets[j]] * 2] += stride[k];
+                }
+            }
+            for (uint64_t q = 0; q < n; q++) {
+                Wt[q * 2 + 1] = 1.0;
+                totals[0] += Wt[q * 2];
+                totals[1] += 1.0;
+            }
+            sp.K = 2;
+            sp.weights = Wt.data();
+            sp.column_totals = totals.data();
+            sp.afs_dims = dims.data();
+            sp.afs_nsets = (uint32_t) num_sample_sets;
+            return run_weighted_stat(&P, sp);
+        }
+        // state columns: the sets, then all samples (trees.c:3890-3910)
+        std::vector<uint64_t> sizes(sample_set_sizes, sample_set_sizes + num_sample_sets);
+        std::vector<int32_t> sets(sample_sets, sample_sets + total);
+        sets.insert(sets.end(), P.samples.begin(), P.samples.end());
+        sizes.push_back(P.num_samples);
+        sp.K = (uint32_t) sizes.size();
+        sp.sizes = sizes.data();
+        sp.sets = sets.data();
         return run_sample_count_stat(&P, sp);
     });
 }

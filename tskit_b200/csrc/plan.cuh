@@ -177,8 +177,16 @@ struct StatSpec {
     // tabulated summary (stat_id == STAT_TABULATED)
     const double *f_table = nullptr;
     uint64_t table_rows = 0;
-    // STAT_AFS: size of one window's spectrum = product of (set size + 1); result is [W x afs_size]
+    // STAT_AFS: size of one window's spectrum = product of (set size + 1); result is
+    // [W x num_time_windows x afs_size]
     uint64_t afs_size = 0;
+    // more than 7 sample sets: fp64 states (linear spectrum coordinate, all-samples count); afs_dims =
+    // set sizes + 1 (host [afs_nsets])
+    const uint32_t *afs_dims = nullptr;
+    uint32_t afs_nsets = 0;
+    // branch mode with time windows other than [0, inf) (needs the node of every piece: a node-mode plan)
+    const double *time_windows = nullptr;   // host [num_time_windows + 1]; nullptr: the default window
+    uint32_t num_time_windows = 1;
     // STAT_REL_VECTOR: focal nodes (host); M = num_focal * K; focal_needs_nodes: some focal node is
     // not a sample (needs the node of every piece: a node-mode plan)
     const int32_t *focal = nullptr;
@@ -196,7 +204,10 @@ enum StatId {
     // joint allele frequency spectrum, site mode (trees.c:3497-3648): K sets + the all-samples column
     STAT_AFS = 17,
     // GRM x vector, branch mode (trees.c:10445-10816): fp64 states, result [W x num_focal x K]
-    STAT_REL_VECTOR = 18
+    STAT_REL_VECTOR = 18,
+    // centred genetic_relatedness over more sample sets than a sweep carries (trees.c:4729-4753): fp64
+    // states = indicator columns of the batch's sets + one column summing 1/n_k over ALL sets
+    STAT_REL_SIDE = 19
 };
 
 int run_sample_count_stat(const Plan *plan, const StatSpec &spec);

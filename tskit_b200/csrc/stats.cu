@@ -76,6 +76,15 @@ struct SumP {
     uint32_t table_rows;
 };
 
+// x[i] without dynamic register indexing, in the state's own type
+template <class V>
+__device__ __forceinline__ typename V::scalar pick_t(const V &s, int i) {
+    typename V::scalar r = s.v[0];
+#pragma unroll
+    for (int k = 1; k < V::N; k++) r = (i == k) ? s.v[k] : r;
+    return r;
+}
+
 // x[i] without dynamic register indexing
 template <class V>
 __device__ __forceinline__ double pick(const V &s, int i) {
@@ -180,6 +189,11 @@ __device__ __forceinline__ double f_eval(const SumP &P, const ColP &c, int m, co
             return (a * a) / (2 * denom * denom);
         }
         return 0.0;
+    } else if constexpr (STAT == STAT_REL_SIDE) {
+        // trees.c:4729-4753 with the mean over all table_rows sample sets carried as the last state
+        // column (sum over the samples below of sum_k [sample in set k] / n_k)
+        const double meanx = pick<V>(s, P.K - 1) / (double) P.table_rows;
+        return (pick<V>(s, c.i) / c.ni - meanx) * (pick<V>(s, c.j) / c.nj - meanx);
     } else if constexpr (STAT == STAT_REL_WEIGHTED_NC) {
         return pick<V>(s, c.i) * pick<V>(s, c.j);  // trees.c:4822-4838
     } else {  // STAT_TABULATED
@@ -800,40 +814,86 @@ __global__ void k_so_gather(uint32_t n, const uint32_t *__restrict__ slot, const
     bp0[i] = q_bp0[j]; bp1[i] = q_bp1[j]; bl[i] = q_bl[j];
 }
 
+// statistics whose column reads only the (at most four) sets of its own index tuple: the lane's
+// column then works on a 4-column excerpt of the state, fetched from shared memory
+template <int STAT>
+constexpr bool stat_reads_tuple_only() {
+    return STAT == STAT_DIVERSITY || STAT == STAT_SEGSITES || STAT == STAT_Y1 || STAT == STAT_DIVERGENCE
+           || STAT == STAT_Y2 || STAT == STAT_F2 || STAT == STAT_RELATEDNESS_NC || STAT == STAT_Y3
+           || STAT == STAT_F3 || STAT == STAT_F4;
+}
+
+// A warp takes BYPOS_CHUNK consecutive pieces of the summary order, 32 at a time through shared memory
+// (state, branch length, breakpoints).  The lanes are split into 32 / CP groups of CP >= ncols lanes
+// (CP a power of two): group g walks the g-th part of the 32 pieces, lane c of the group evaluates
+// column c.  No shuffles: every lane reads what it needs from the warp's tile.
 template <int STAT, class V>
 __global__ void __launch_bounds__(TB) k_branch_summary_bypos(uint32_t nsp,
     const uint32_t *__restrict__ so_slot, const uint32_t *__restrict__ so_bp0,
     const uint32_t *__restrict__ so_bp1, const double *__restrict__ so_bl, const V *__restrict__ pval,
-    SumP sp, V totals, DeltaOut out, uint32_t m0, uint32_t ncols) {
-    const uint32_t lane = threadIdx.x & 31u;
+    SumP sp, V totals, DeltaOut out, uint32_t m0, uint32_t ncols, uint32_t CP) {
+    using T = typename V::scalar;
+    using V4 = SVec<T, 4>;
+    __shared__ T s_state[TB / 32][32][V::N];
+    __shared__ double s_bl[TB / 32][32];
+    __shared__ uint32_t s_bp0[TB / 32][32], s_bp1[TB / 32][32];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t c0 = warp * BYPOS_CHUNK;
     if (c0 >= nsp) return;
     const uint32_t c1 = min(nsp, c0 + BYPOS_CHUNK);
-    const bool mine = lane < ncols;
-    const uint32_t m = m0 + (mine ? lane : 0);
-    const ColP col = out.cols[m];
-    double *Dl = out.D + lane;  // D[bp * ncols + lane]
+    const uint32_t groups = 32u / CP, per_group = 32u / groups;  // pieces of a tile each group walks
+    const uint32_t g = lane / CP, cl = lane % CP;
+    const bool mine = cl < ncols;
+    const uint32_t m = m0 + (mine ? cl : 0);
+    ColP col = out.cols[m];
+    V4 tot4 = ivec_zero<V4>();
+    int idx4[4] = { col.i, col.j, col.k, col.l };
+    if constexpr (stat_reads_tuple_only<STAT>()) {
+        // the tuple's sets renumbered 0..3 (one-way statistics: the column's own set)
+        if (STAT == STAT_DIVERSITY || STAT == STAT_SEGSITES || STAT == STAT_Y1) idx4[0] = col.i;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            idx4[a] = idx4[a] < 0 || idx4[a] >= V::N ? 0 : idx4[a];
+            tot4.v[a] = pick_t<V>(totals, idx4[a]);
+        }
+        col.i = 0; col.j = 1; col.k = 2; col.l = 3;
+    }
+    double *Dl = out.D + cl;  // D[bp * ncols + column]
     double acc = 0.0;
     uint32_t cur = NO_PIECE;    // breakpoint the register accumulator belongs to
     for (uint32_t base = c0; base < c1; base += 32) {
         const uint32_t j = base + lane;
-        V st = ivec_zero<V>();
-        double bl = 0.0;
-        uint32_t bp0 = 0, bp1 = NO_PIECE;
+        __syncwarp();
         if (j < c1) {
-            bl = so_bl[j]; bp0 = so_bp0[j]; bp1 = so_bp1[j];
-            st = pval[so_slot[j]];
-        }
-        const int cnt = (int) min(32u, c1 - base);
-        for (int i = 0; i < cnt; i++) {
-            V s_i;
+            const V st = pval[so_slot[j]];
 #pragma unroll
-            for (int k = 0; k < V::N; k++) s_i.v[k] = __shfl_sync(0xffffffffu, st.v[k], i);
-            const double bl_i = __shfl_sync(0xffffffffu, bl, i);
-            const uint32_t b0 = __shfl_sync(0xffffffffu, bp0, i), b1 = __shfl_sync(0xffffffffu, bp1, i);
+            for (int k = 0; k < V::N; k++) s_state[wib][lane][k] = st.v[k];
+            s_bl[wib][lane] = so_bl[j]; s_bp0[wib][lane] = so_bp0[j]; s_bp1[wib][lane] = so_bp1[j];
+        } else {
+            s_bp1[wib][lane] = NO_PIECE;
+        }
+        __syncwarp();
+        for (uint32_t q = 0; q < per_group; q++) {
+            const uint32_t i = g * per_group + q;
+            const uint32_t b1 = s_bp1[wib][i];
+            if (b1 == NO_PIECE) break;  // past the end of the chunk (group-uniform)
+            const uint32_t b0 = s_bp0[wib][i];
+            const double bl_i = s_bl[wib][i];
             double G = 0.0;
-            if (!(sp.skip_zero_bl && bl_i == 0.0)) G = bl_i * F_branch<STAT, V>(sp, col, m, s_i, totals);
+            if (!(sp.skip_zero_bl && bl_i == 0.0)) {
+                if constexpr (stat_reads_tuple_only<STAT>()) {
+                    V4 t4;
+#pragma unroll
+                    for (int a = 0; a < 4; a++) t4.v[a] = s_state[wib][i][idx4[a]];
+                    G = bl_i * F_branch<STAT, V4>(sp, col, (int) m, t4, tot4);
+                } else {
+                    V s_i;
+#pragma unroll
+                    for (int k = 0; k < V::N; k++) s_i.v[k] = s_state[wib][i][k];
+                    G = bl_i * F_branch<STAT, V>(sp, col, (int) m, s_i, totals);
+                }
+            }
             if (b0 != cur) {
                 if (cur != NO_PIECE && mine && acc != 0.0) atomicAdd(Dl + (size_t) cur * ncols, acc);
                 cur = b0;
@@ -1108,8 +1168,7 @@ __global__ void k_window_final(const double *partial, const double *windows, uin
 // last, all samples.
 
 // fold (trees.c:3469-3495): the lexicographically smaller of a coordinate and its mirror image
-template <int MAXK>
-__device__ __forceinline__ void afs_fold(uint32_t (&coord)[MAXK], const uint32_t (&dims)[MAXK], int K) {
+__device__ __forceinline__ void afs_fold(uint32_t *coord, const uint32_t *dims, int K) {
     double n = 0;
     int s = 0;
     for (int k = 0; k < K; k++) {
@@ -1128,39 +1187,69 @@ __device__ __forceinline__ void afs_fold(uint32_t (&coord)[MAXK], const uint32_t
     }
 }
 
+// Up to 7 sample sets: one int32 state column per set, then the all-samples column.  More sets
+// (packed): the spectrum's row-major coordinate is itself a linear function of the per-set counts, so
+// it is carried as ONE state column (fp64, exact) next to the all-samples count.
+constexpr int AFS_MAX_PACKED_SETS = 64;
+struct AfsShape {
+    int packed;
+    uint32_t nsets;
+    const uint32_t *dims;  // device [nsets], packed only
+};
+
+// row-major index (increment_nd_array_value) of the state's coordinate, folded unless polarised; false
+// when the allele / branch is carried by no sample or by all (trees.c:3519, 3622)
 template <class V>
-__device__ __forceinline__ void afs_add(const V &cnt, int K, const SumP &P, uint32_t num_samples, double inc,
-    double *afs) {
-    uint32_t coord[8], dims[8];
-    uint32_t total = 0;
+__device__ __forceinline__ bool afs_index(const V &cnt, const SumP &P, const AfsShape &sh, uint32_t num_samples,
+    size_t &index) {
+    if (!sh.packed) {
+        const int K = P.K - 1;
+        uint32_t coord[8], dims[8], total = 0;
 #pragma unroll
-    for (int k = 0; k < V::N; k++) {
-        if (k < K) {
-            coord[k] = (uint32_t) cnt.v[k];
-            dims[k] = (uint32_t) P.n[k] + 1;
-        } else {
+        for (int k = 0; k < 8; k++) {
             coord[k] = 0;
             dims[k] = 1;
         }
-        if (k == K) total = (uint32_t) cnt.v[k];
+#pragma unroll
+        for (int k = 0; k < V::N; k++) {
+            if (k < K) {
+                coord[k] = (uint32_t) cnt.v[k];
+                dims[k] = (uint32_t) P.n[k] + 1;
+            }
+            if (k == K) total = (uint32_t) cnt.v[k];
+        }
+        if (!(total > 0 && total < num_samples)) return false;
+        if (!P.polarised) afs_fold(coord, dims, K);
+        index = 0;
+        for (int k = 0; k < K; k++) index = index * dims[k] + coord[k];
+        return true;
     }
-    if (!(total > 0 && total < num_samples)) return;
-    if (!P.polarised) afs_fold<8>(coord, dims, K);
-    size_t index = 0;
-    for (int k = 0; k < K; k++) index = index * dims[k] + coord[k];  // row-major (increment_nd_array_value)
-    atomicAdd(afs + index, inc);
+    unsigned long long lin = (unsigned long long) cnt.v[0];
+    const uint32_t total = (uint32_t) cnt.v[V::N > 1 ? 1 : 0];
+    if (!(total > 0 && total < num_samples)) return false;
+    if (!P.polarised) {
+        uint32_t coord[AFS_MAX_PACKED_SETS];
+        const int K = (int) sh.nsets;
+        for (int k = K - 1; k >= 0; k--) {
+            coord[k] = (uint32_t) (lin % sh.dims[k]);
+            lin /= sh.dims[k];
+        }
+        afs_fold(coord, sh.dims, K);
+        lin = 0;
+        for (int k = 0; k < K; k++) lin = lin * sh.dims[k] + coord[k];
+    }
+    index = (size_t) lin;
+    return true;
 }
 
 template <class V>
 __global__ void k_site_afs(uint32_t site_lo, uint32_t nsites, const uint32_t *site_moff,
     const uint32_t *site_aoff, const int32_t *mut_src, const uint16_t *mut_allele, const uint16_t *mut_alt,
-    const V *pval, V totals, V *scratch, SumP P, uint32_t num_samples, const double *site_pos,
+    const V *pval, V totals, V *scratch, SumP P, AfsShape sh, uint32_t num_samples, const double *site_pos,
     const double *windows, uint32_t W, size_t afs_size, double *result) {
-    static_assert(V::N <= 8, "at most 7 sample sets and the all-samples column");
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsites) return;
     const uint32_t site = site_lo + t;
-    const int K = P.K - 1;  // sample sets; column K counts all samples
     uint32_t w = upper_bound_dev(windows, W + 1, site_pos[site]);
     w = w > 0 ? w - 1 : 0;
     if (w >= W) w = W - 1;
@@ -1175,48 +1264,58 @@ __global__ void k_site_afs(uint32_t site_lo, uint32_t nsites, const uint32_t *si
         scratch[a0 + mut_allele[m]] = scratch[a0 + mut_allele[m]] + x;
         scratch[a0 + mut_alt[m]] = scratch[a0 + mut_alt[m]] - x;
     }
-    for (uint32_t al = P.polarised ? 1 : 0; al < na; al++) afs_add<V>(scratch[a0 + al], K, P, num_samples, inc, afs);
+    for (uint32_t al = P.polarised ? 1 : 0; al < na; al++) {
+        size_t index;
+        if (afs_index<V>(scratch[a0 + al], P, sh, num_samples, index)) atomicAdd(afs + index, inc);
+    }
 }
 
-// Branch mode (tsk_treeseq_branch_allele_frequency_spectrum, trees.c:3699-3812, default time
-// window): every node with a parent adds (branch length) x (span) at the vector of per-set sample
+// Branch mode (tsk_treeseq_branch_allele_frequency_spectrum, trees.c:3699-3812): every node with a
+// parent adds (span) x (branch length inside each time window) at the vector of per-set sample
 // counts below it.  The span of a piece runs from the node's last update -- q_eff, never before
 // the left edge of the window holding the piece's start, because every window end flushes all
-// nodes -- to the piece's end, split over the windows it crosses.
+// nodes -- to the piece's end, split over the windows it crosses.  Time windows (trees.c:3663-3680):
+// window k takes max(0, min(tw[k+1], t_v) - max(tw[k], t_u)) of the branch from t_u up to t_v, for
+// every k with tw[k] < t_v; q_node == nullptr: the default window [0, inf) with node times >= 0, where
+// that is the whole branch.
 template <class V>
 __global__ void k_branch_afs(uint32_t npp, const uint32_t *__restrict__ q_bp0,
     const uint32_t *__restrict__ q_bp1, const uint32_t *__restrict__ q_eff,
     const double *__restrict__ q_bl, const double *__restrict__ bp_pos, const V *__restrict__ pval, SumP P,
-    uint32_t num_samples, double range_left, const double *__restrict__ windows, uint32_t W,
-    size_t afs_size, double *result) {
+    AfsShape sh, uint32_t num_samples, double range_left, const double *__restrict__ windows, uint32_t W,
+    size_t afs_size, const int32_t *__restrict__ q_node, const double *__restrict__ time,
+    const double *__restrict__ tw, uint32_t NTW, double *result) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= npp) return;
     const uint32_t b1 = q_bp1[j];
     const double bl = q_bl[j];
     if (b1 == NO_PIECE || bl == 0.0) return;
-    const V cnt = pval[j];
-    const int K = P.K - 1;
-    uint32_t coord[8], dims[8], total = 0;
-#pragma unroll
-    for (int k = 0; k < V::N; k++) {
-        coord[k] = k < K ? (uint32_t) cnt.v[k] : 0;
-        dims[k] = k < K ? (uint32_t) P.n[k] + 1 : 1;
-        if (k == K) total = (uint32_t) cnt.v[k];
-    }
-    if (!(total > 0 && total < num_samples)) return;
-    if (!P.polarised) afs_fold<8>(coord, dims, K);
-    size_t index = 0;
-    for (int k = 0; k < K; k++) index = index * dims[k] + coord[k];
+    size_t index;
+    if (!afs_index<V>(pval[j], P, sh, num_samples, index)) return;
     const double x = bp_pos[q_bp0[j]], xe = bp_pos[b1];
     const uint32_t e = q_eff[j];
     double start = e == NO_PIECE ? range_left : bp_pos[e];
     uint32_t w = upper_bound_dev(windows, W + 1, x);
     w = w > 0 ? w - 1 : 0;
     if (start < windows[w]) start = windows[w];
+    double t_u = 0.0, t_v = 0.0;
+    if (q_node != nullptr) {
+        t_u = time[q_node[j]];
+        t_v = t_u + bl;  // bl = time[parent] - time[node]
+    }
     for (; w < W && windows[w] < xe; w++) {
         const double wl = windows[w], wr = windows[w + 1];
         const double len = (xe < wr ? xe : wr) - (start > wl ? start : wl);
-        if (len > 0.0) atomicAdd(result + (size_t) w * afs_size + index, len * bl);
+        if (!(len > 0.0)) continue;
+        if (q_node == nullptr) {
+            atomicAdd(result + (size_t) w * afs_size + index, len * bl);
+            continue;
+        }
+        for (uint32_t k = 0; k < NTW && tw[k] < t_v; k++) {
+            const double hi = tw[k + 1] < t_v ? tw[k + 1] : t_v, lo = tw[k] > t_u ? tw[k] : t_u;
+            const double tbl = hi - lo > 0.0 ? hi - lo : 0.0;
+            if (tbl > 0.0) atomicAdd(result + ((size_t) w * NTW + k) * afs_size + index, len * tbl);
+        }
     }
 }
 
@@ -1528,8 +1627,11 @@ template <int STAT, class V>
 bool run_branch_bins(CallCtx &c, V *pval, V totals) {
     const Plan &P = *c.P;
     const uint32_t M = c.sp->M, W = c.sp->W;
+    // Measured on C2 (profiles/r2b_ab_summary.txt): 1.52 ms per step against 0.98 ms for the delta
+    // formulation -- the compare-and-swap additions in shared memory (ATOMS.CAST.SPIN) serialise the
+    // lanes of a warp that hit one window, which is most of them.  Kept selectable: TSKB_SUM_VARIANT=bins.
     const char *variant = getenv("TSKB_SUM_VARIANT");
-    if (variant != nullptr && variant[0] != 'b') return false;  // experiments: force another kernel
+    if (variant == nullptr || variant[0] != 'b') return false;
     if (!c.sumP.skip_zero_bl || P.npp == 0 || P.T == 0) return false;
     if ((size_t) (3 * (size_t) W + 1) * sizeof(double) > BINS_SMEM_MAX) return false;
     const uint32_t mc = (uint32_t) std::min<size_t>(M, (BINS_SMEM_MAX / sizeof(double) - W - 1) / (2 * (size_t) W));
@@ -1588,7 +1690,9 @@ void run_branch(CallCtx &c, V *pval, V totals) {
     const uint32_t Tp1 = P.T + 1;
     const size_t col_bytes = (size_t) Tp1 * sizeof(double);
     // 6 or more columns: lanes-are-columns kernel, at most 32 columns per pass
-    const bool by_cols = M >= COLS_KERNEL_MIN && getenv("TSKB_NO_COLS_KERNEL") == nullptr;
+    uint32_t cols_min = COLS_KERNEL_MIN;
+    if (const char *e = getenv("TSKB_COLS_MIN")) cols_min = (uint32_t) std::max(1, atoi(e));  // experiments
+    const bool by_cols = M >= cols_min && getenv("TSKB_NO_COLS_KERNEL") == nullptr;
     const char *cols_variant = getenv("TSKB_COLS_VARIANT");  // experiments: "old" = processing-order walk
     const bool by_pos = by_cols && !(cols_variant != nullptr && cols_variant[0] == 'o');
     size_t budget = DELTA_BUDGET;
@@ -1617,8 +1721,10 @@ void run_branch(CallCtx &c, V *pval, V totals) {
             DeltaOut ox = { Dp, Tp1, c.sumP.cols };
             if (P.nsp > 0) {
                 const uint32_t nwarps = (P.nsp + BYPOS_CHUNK - 1) / BYPOS_CHUNK;
+                uint32_t CP = 1;
+                while (CP < nc) CP <<= 1;  // lanes per piece: the columns rounded up to a power of two
                 k_branch_summary_bypos<STAT, V><<<grid_for((size_t) nwarps * 32, TB), TB, 0, c.s>>>(P.nsp,
-                    P.so_slot.p, P.so_bp0.p, P.so_bp1.p, P.so_bl.p, pval, c.sumP, totals, ox, m0, nc);
+                    P.so_slot.p, P.so_bp0.p, P.so_bp1.p, P.so_bl.p, pval, c.sumP, totals, ox, m0, nc, CP);
                 TSKB_CK_LAUNCH();
                 c.launches++;
             }
@@ -1761,6 +1867,20 @@ void run_node(CallCtx &c, V *pval, V totals) {
     TSKB_CK(cudaEventRecord(P.ev[4], c.s));
 }
 
+// the spectrum's shape on the device (packed coordinates: the sets' dimensions)
+inline AfsShape afs_shape(CallCtx &c) {
+    AfsShape sh = {};
+    const StatSpec &sp = *c.sp;
+    if (sp.afs_dims != nullptr) {
+        uint32_t *d = c.P->arena.get<uint32_t>(sp.afs_nsets);
+        TSKB_CK(cudaMemcpyAsync(d, sp.afs_dims, sp.afs_nsets * sizeof(uint32_t), cudaMemcpyHostToDevice, c.s));
+        sh.packed = 1;
+        sh.nsets = sp.afs_nsets;
+        sh.dims = d;
+    }
+    return sh;
+}
+
 // joint allele frequency spectrum, site mode
 template <class V>
 void run_afs_site(CallCtx &c, V *pval, V totals) {
@@ -1768,6 +1888,7 @@ void run_afs_site(CallCtx &c, V *pval, V totals) {
     const uint32_t W = c.sp->W;
     const size_t afs_size = c.sp->afs_size;
     Arena &A = P.arena;
+    const AfsShape sh = afs_shape(c);
     launch_sweep<V>(c, pval);
     TSKB_CK(cudaEventRecord(P.ev[2], c.s));
     const uint32_t nsites = P.site_hi - P.site_lo;
@@ -1775,7 +1896,7 @@ void run_afs_site(CallCtx &c, V *pval, V totals) {
     TSKB_CK(cudaMemsetAsync(c.d_result, 0, (size_t) W * afs_size * sizeof(double), c.s));
     if (nsites) {
         k_site_afs<V><<<grid_for(nsites, 128), 128, 0, c.s>>>(P.site_lo, nsites, P.site_moff.p, P.site_aoff.p,
-            P.mut_src.p, P.mut_allele.p, P.mut_alt.p, pval, totals, scratch, c.sumP, P.num_samples,
+            P.mut_src.p, P.mut_allele.p, P.mut_alt.p, pval, totals, scratch, c.sumP, sh, P.num_samples,
             P.site_pos.p, c.d_windows, W, afs_size, c.d_result);
         TSKB_CK_LAUNCH();
         c.launches++;
@@ -1793,21 +1914,31 @@ void run_afs_site(CallCtx &c, V *pval, V totals) {
 template <class V>
 void run_afs_branch(CallCtx &c, V *pval) {
     const Plan &P = *c.P;
-    const uint32_t W = c.sp->W;
+    const uint32_t W = c.sp->W, NTW = c.sp->num_time_windows;
     const size_t afs_size = c.sp->afs_size;
+    const AfsShape sh = afs_shape(c);
+    const double *d_tw = nullptr;
+    const int32_t *q_node = nullptr;
+    if (c.sp->time_windows != nullptr) {  // the caller made sure this plan keeps the node of every piece
+        double *t = P.arena.get<double>(NTW + 1);
+        TSKB_CK(cudaMemcpyAsync(t, c.sp->time_windows, (NTW + 1) * sizeof(double), cudaMemcpyHostToDevice, c.s));
+        d_tw = t;
+        q_node = P.q_node.p;
+    }
     launch_sweep<V>(c, pval);
     TSKB_CK(cudaEventRecord(P.ev[2], c.s));
-    TSKB_CK(cudaMemsetAsync(c.d_result, 0, (size_t) W * afs_size * sizeof(double), c.s));
+    TSKB_CK(cudaMemsetAsync(c.d_result, 0, (size_t) W * NTW * afs_size * sizeof(double), c.s));
     if (P.npp) {
         k_branch_afs<V><<<grid_for(P.npp, TB), TB, 0, c.s>>>(P.npp, P.q_bp0.p, P.q_bp1.p, P.q_eff.p, P.q_bl.p,
-            P.bp_pos.p, pval, c.sumP, P.num_samples, P.range_left, c.d_windows, W, afs_size, c.d_result);
+            P.bp_pos.p, pval, c.sumP, sh, P.num_samples, P.range_left, c.d_windows, W, afs_size, q_node, P.time.p,
+            d_tw, NTW, c.d_result);
         TSKB_CK_LAUNCH();
         c.launches++;
     }
     TSKB_CK(cudaEventRecord(P.ev[3], c.s));
     if (c.sp->options & TSKB_STAT_SPAN_NORMALISE) {
-        k_afs_span_normalise<<<grid_for((size_t) W * afs_size, TB), TB, 0, c.s>>>(c.d_windows, W, afs_size,
-            c.d_result);
+        k_afs_span_normalise<<<grid_for((size_t) W * NTW * afs_size, TB), TB, 0, c.s>>>(c.d_windows, W,
+            NTW * afs_size, c.d_result);
         TSKB_CK_LAUNCH();
         c.launches++;
     }
@@ -1941,7 +2072,8 @@ int run_impl(const Plan &P, const StatSpec &sp) {
             q.inv = 1.0;
             if (sp.stat_id == STAT_TRAIT_COV) {
                 q.ni = 2 * (n - 1) * (n - 1);  // trees.c:3972
-            } else if (sp.stat_id == STAT_REL_WEIGHTED || sp.stat_id == STAT_REL_WEIGHTED_NC) {
+            } else if (sp.stat_id == STAT_REL_WEIGHTED || sp.stat_id == STAT_REL_WEIGHTED_NC
+                       || sp.stat_id == STAT_REL_SIDE) {
                 q.ni = sp.column_totals[t[0]];
                 q.nj = sp.column_totals[t[1]];
             }
@@ -1985,7 +2117,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
             cudaMemcpyHostToDevice, s));
         sumP.table = d_tab;
     }
-    if (sp.stat_id == STAT_TRAIT_LM) sumP.table_rows = (uint32_t) sp.table_rows;
+    if (sp.stat_id == STAT_TRAIT_LM || sp.stat_id == STAT_REL_SIDE) sumP.table_rows = (uint32_t) sp.table_rows;
     if (sp.stat_id == STAT_TABULATED) {
         double *d_tab = A.get<double>(sp.table_rows * M);
         TSKB_CK(cudaMemcpyAsync(d_tab, sp.f_table, sp.table_rows * M * sizeof(double),
@@ -1998,7 +2130,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     }
     // node mode: one row per node and window (trees.c:1788-1918)
     const size_t result_size = sp.stat_id == STAT_AFS
-                                   ? (size_t) W * sp.afs_size
+                                   ? (size_t) W * sp.num_time_windows * sp.afs_size
                                    : (size_t) W * M * ((sp.options & TSKB_STAT_NODE) ? (size_t) P.N : 1);
     c.d_result = sp.result_on_device ? sp.result : A.get<double>(result_size);
     TSKB_CK(cudaEventRecord(P.ev[1], s));
@@ -2010,8 +2142,16 @@ int run_impl(const Plan &P, const StatSpec &sp) {
             case STAT_TRAIT_CORR: run_phases<STAT_TRAIT_CORR, V>(c, pval, totals); break;
             case STAT_REL_WEIGHTED: run_phases<STAT_REL_WEIGHTED, V>(c, pval, totals); break;
             case STAT_REL_WEIGHTED_NC: run_phases<STAT_REL_WEIGHTED_NC, V>(c, pval, totals); break;
+            case STAT_REL_SIDE: run_phases<STAT_REL_SIDE, V>(c, pval, totals); break;
             case STAT_TRAIT_LM: run_phases<STAT_TRAIT_LM, V>(c, pval, totals); break;
             case STAT_REL_VECTOR: run_relvec<V>(c, pval); break;
+            case STAT_AFS:  // packed spectrum coordinates (more than 7 sample sets)
+                if (sp.options & TSKB_STAT_BRANCH) {
+                    run_afs_branch<V>(c, pval);
+                } else {
+                    run_afs_site<V>(c, pval, totals);
+                }
+                break;
             default: return TSKB_ERR_BAD_PARAM_VALUE;
         }
     } else

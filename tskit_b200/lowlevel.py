@@ -346,9 +346,13 @@ class LLTreeSequence:
         w = parse_windows(windows)
         tw = parse_windows(time_windows)
         result = np.zeros([len(w) - 1, len(tw) - 1] + [int(x) + 1 for x in sizes])
-        _handle(_lib.lib().tskb_treeseq_allele_frequency_spectrum(
-            self._h, len(sizes), _p(sizes), _p(sets), len(w) - 1, _p(w), len(tw) - 1, _p(tw), options,
-            _p(result)))
+        args = (len(sizes), _p(sizes), _p(sets), len(w) - 1, _p(w), len(tw) - 1, _p(tw), options, _p(result))
+        ret = _lib.lib().tskb_treeseq_allele_frequency_spectrum(self._h, *args)
+        if ret == -20003 and (options & STAT_BRANCH) and not self.node_mode:
+            # time windows other than [0, inf) split every branch by time: the engine that keeps the
+            # node of every piece (staged on first use) does it
+            ret = _lib.lib().tskb_treeseq_allele_frequency_spectrum(self._for_mode(STAT_NODE)._h, *args)
+        _handle(ret)
         return result
 
     # ---- TreeSequence_one_way_weighted_method (_tskitmodule.c:6747-6830)
