@@ -198,3 +198,50 @@ def test_genetic_relatedness_matrix_through_dropin(wf_small):
     want = ts.divergence_matrix(sample_sets=some, windows=w, mode="branch")
     assert np.allclose(got, want, rtol=1e-9)
     assert acc.accel_stats["forwarded"] == 0
+
+
+def test_matrices_shard_by_genome_range(wf_small):
+    """SURVEY 8e rows 2-4 on one GPU, one range after the other: the per-range partial divergence
+    matrices (site mode: integer counts, so the sum is exact; branch mode: within rounding) add up to
+    the oracle's whole-genome matrix, and the per-range genotype blocks concatenate to the whole decode.
+    Ranges are staged from the restricted tables, as the ranks of sharding.ShardedTreeSequence do."""
+    from tskit_b200 import sharding
+    from tskit_b200.lowlevel import LLTreeSequence
+    t = wf_small
+    o = port.Oracle(t)
+    L = t.sequence_length
+    windows = np.array([0.0, 0.2 * L, 0.55 * L, L])
+    s = t.samples
+    sets = [s[:30], s[30:31], s[40:90], s[100:]]
+    sizes = np.array([len(x) for x in sets], dtype=np.uint64)
+    flat = np.concatenate(sets).astype(np.int32)
+    ranges = sharding.plan_shards(t, np.linspace(0, L, 41), 3)
+    for mode in ("site", "branch"):
+        total = np.zeros((3, 4, 4))
+        total_all = np.zeros((3, 40, 40))
+        for rng in ranges:
+            ll = LLTreeSequence(sharding.restrict_tables(t, *rng), genome_range=rng)
+            total += ll.divergence_matrix(windows, sample_sets=flat, sample_set_sizes=sizes, mode=mode,
+                                          span_normalise=False)
+            total_all += ll.divergence_matrix(windows, sample_sets=s[:40], sample_set_sizes=np.ones(40, dtype=np.uint64),
+                                              mode=mode, span_normalise=False)
+            ll.close()
+        want = o.divergence_matrix(sets, windows=windows, mode=mode, span_normalise=False)
+        want_all = o.divergence_matrix([[u] for u in s[:40]], windows=windows, mode=mode, span_normalise=False)
+        if mode == "site":
+            assert np.array_equal(total_all, want_all)      # integer counts: exact for any number of ranges
+            assert np.allclose(total, want, rtol=1e-12, atol=0)
+        else:
+            assert np.allclose(total, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+            assert np.allclose(total_all, want_all, rtol=1e-9, atol=1e-9 * np.abs(want_all).max())
+    blocks = []
+    for rng in ranges:
+        ll = LLTreeSequence(sharding.restrict_tables(t, *rng), genome_range=rng)
+        blocks.append(ll.genotype_matrix(samples=s[::3]))
+        ll.close()
+    assert np.array_equal(np.concatenate(blocks, axis=0), o.genotype_matrix(samples=s[::3]))
+    # the sharded wrapper itself, one rank: same calls, whole results
+    sh = sharding.ShardedTreeSequence(t, windows, 0, 1)
+    got = sh.divergence_matrix(windows, sample_sets=flat, sample_set_sizes=sizes, mode="site")
+    assert np.allclose(got, o.divergence_matrix(sets, windows=windows, mode="site"), rtol=1e-12, atol=0)
+    assert np.array_equal(sh.genotype_matrix(), o.genotype_matrix())

@@ -57,6 +57,81 @@ class OracleRangeEngine:
         return out
 
 
+    def divergence_matrix(self, windows, sample_sets, sample_set_sizes, mode, span_normalise):
+        assert span_normalise is False
+        w = np.asarray(windows, dtype=np.float64)
+        fine = np.unique(np.concatenate([w, [self.lo, self.hi]]))
+        fine = fine[(fine >= w[0]) & (fine <= w[-1])]
+        off = np.concatenate([[0], np.cumsum(sample_set_sizes)]).astype(int)
+        sets = [sample_sets[off[i]:off[i + 1]] for i in range(len(sample_set_sizes))]
+        r = self.o.divergence_matrix(sets, windows=fine, mode=mode, span_normalise=False)
+        out = np.zeros((len(w) - 1,) + r.shape[1:])
+        mid = 0.5 * (fine[:-1] + fine[1:])
+        inside = (mid >= self.lo) & (mid < self.hi)
+        owner = np.searchsorted(w, mid, side="right") - 1
+        np.add.at(out, owner[inside], r[inside])
+        return out
+
+    def genotype_matrix(self, samples=None, isolated_as_missing=True):
+        return self.o.genotype_matrix(samples=samples, isolated_as_missing=isolated_as_missing).astype(np.int8)
+
+
+def _matrix_worker(rank, world, port_no, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t = Tables.load(DATA).ensure_derived()
+    L = t.sequence_length
+    windows = np.array([0.0, 0.3 * L, L])
+    sh = sharding.ShardedTreeSequence(t, np.linspace(0, L, 21), rank, world, engine_factory=OracleRangeEngine)
+    s = t.samples
+    sets = [s[:12], s[12:13], s[20:45]]
+    sizes = np.array([len(x) for x in sets], dtype=np.uint64)
+    flat = np.concatenate(sets).astype(np.int32)
+    out = {}
+    for mode in ("site", "branch"):
+        out[mode] = sh.divergence_matrix(windows, sample_sets=flat, sample_set_sizes=sizes, mode=mode)
+    out["genotypes"] = sh.genotype_matrix(samples=s[::4])
+    out["block"] = sh.genotype_matrix(samples=s[::4], gather=False)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_matrices_and_decode():
+    """site / branch divergence matrix summed over genome ranges, genotype decode
+    sharded by site -- the product's sharding module over gloo, engines standing in from the oracle."""
+    from oracle import port
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = 29500 + (os.getpid() + 977) % 2000
+    procs = [ctx.Process(target=_matrix_worker, args=(r, 2, port_no, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    t = Tables.load(DATA).ensure_derived()
+    o = port.Oracle(t)
+    L = t.sequence_length
+    windows = np.array([0.0, 0.3 * L, L])
+    s = t.samples
+    sets = [s[:12], s[12:13], s[20:45]]
+    G = o.genotype_matrix(samples=s[::4])
+    firsts = {}
+    for rank, out in got:
+        want = o.divergence_matrix(sets, windows=windows, mode="site")
+        assert np.allclose(out["site"], want, rtol=1e-12, atol=0)
+        want = o.divergence_matrix(sets, windows=windows, mode="branch")
+        assert np.allclose(out["branch"], want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+        assert np.array_equal(out["genotypes"], G)
+        first, block = out["block"]
+        assert np.array_equal(block, G[first:first + len(block)])
+        firsts[rank] = (first, len(block))
+    assert firsts[0][0] == 0 and firsts[1][0] == firsts[0][1] and sum(v[1] for v in firsts.values()) == len(G)
+
+
 def _worker(rank, world, port_no, W, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)

@@ -41,6 +41,23 @@ for rep in range(3):
     barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
     rv = sh.stat("genetic_relatedness_vector", wt, windows=w10, mode="branch", centre=True, nodes=s)
     torch.cuda.synchronize(); barrier(); rv_dt = time.perf_counter() - t0
+# matrices and decode: site / branch divergence matrix of 2000 / 64 samples, genotype
+# decode of 1024 samples, sharded by genome range / site
+sub = s[:: len(s) // 2000][:2000].astype(np.int32)
+sub_b = s[:: len(s) // 64][:64].astype(np.int32)
+w4 = np.linspace(0, t.sequence_length, 5)
+mat = {}
+for mode, ss in (("site", sub), ("branch", sub_b)):
+    for rep in range(2):
+        barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+        m = sh.divergence_matrix(w4, sample_sets=ss, sample_set_sizes=np.ones(len(ss), dtype=np.uint64), mode=mode)
+        torch.cuda.synchronize(); barrier(); dt = time.perf_counter() - t0
+    mat[mode] = (m, dt)
+dsub = s[:: len(s) // 1024][:1024].astype(np.int32)
+for rep in range(2):
+    barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    first, block = sh.genotype_matrix(samples=dsub, gather=False)
+    torch.cuda.synchronize(); barrier(); dec_dt = time.perf_counter() - t0
 if rank == 0:
     whole = LLTreeSequence(t, device=local)
     res = {"world": world, "ranges": sh.ranges, "workload": bench.workload_name("c2", t, W), "calls": {}}
@@ -57,6 +74,23 @@ if rank == 0:
     res["calls"]["genetic_relatedness_vector"] = {"columns": 2, "windows": 10, "sharded_ms": rv_dt * 1e3,
                                                    "single_gpu_ms": d1 * 1e3, "max_abs_err_over_max": err}
     assert err < 1e-10, ("genetic_relatedness_vector", err)
+    for mode, ss in (("site", sub), ("branch", sub_b)):
+        for rep in range(2):
+            t0 = time.perf_counter()
+            ref = whole.divergence_matrix(w4, sample_sets=ss, sample_set_sizes=np.ones(len(ss), dtype=np.uint64), mode=mode)
+            d1 = time.perf_counter() - t0
+        got = mat[mode][0]
+        err = float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
+        res["calls"]["divergence_matrix_" + mode] = {
+            "samples": len(ss), "windows": 4, "sharded_ms": mat[mode][1] * 1e3, "single_gpu_ms": d1 * 1e3,
+            "max_abs_err_over_max": err, "bit_identical": bool(np.array_equal(got, ref))}
+        assert err < 1e-10, (mode, err)
+    for rep in range(2):
+        t0 = time.perf_counter(); G = whole.genotype_matrix(samples=dsub); d1 = time.perf_counter() - t0
+    res["calls"]["genotype_matrix"] = {
+        "samples": len(dsub), "sites": int(t.num_sites), "sharded_ms_rows_stay_sharded": dec_dt * 1e3,
+        "single_gpu_ms": d1 * 1e3, "rank0_block_bit_exact": bool(np.array_equal(block, G[first:first + len(block)]))}
+    assert res["calls"]["genotype_matrix"]["rank0_block_bit_exact"]
     print(json.dumps(res))
 if world > 1:
     dist.destroy_process_group()

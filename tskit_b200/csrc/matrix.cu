@@ -891,7 +891,6 @@ int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *size
         }
         return run_branch_divergence_matrix(P, nsets, sizes, sets, num_windows, windows, options, result);
     }
-    if (P.range_left != 0 || P.range_right != P.L) return TSKB_ERR_UNSUPPORTED;
     std::lock_guard<std::mutex> lock(P.mu);
     TSKB_CK(cudaSetDevice(P.device));
     cudaStream_t s = P.stream;
@@ -899,8 +898,11 @@ int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *size
     memset(result, 0, (size_t) W * ns * ns * sizeof(double));
     if (n == 0) return 0;
     // sites covered by the windows
+    // (a plan staged for a genome range contracts the sites inside its range only: the per-range
+    // partial matrices of a sharded call add up to the whole, exactly -- they are integer counts)
     auto site_index = [&](double x) {
-        return (uint32_t) (std::lower_bound(P.h_site_pos.begin(), P.h_site_pos.end(), x) - P.h_site_pos.begin());
+        const uint32_t i = (uint32_t) (std::lower_bound(P.h_site_pos.begin(), P.h_site_pos.end(), x) - P.h_site_pos.begin());
+        return std::min(std::max(i, P.site_lo), P.site_hi);
     };
     const uint32_t S0 = site_index(windows[0]), S1 = site_index(windows[W]);
     // genotype columns: every window starts on a 128-byte boundary and is padded to whole 128-byte

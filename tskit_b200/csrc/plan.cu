@@ -6,9 +6,12 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <thread>
 
 #include "plan.cuh"
 
@@ -42,6 +45,11 @@ namespace {
 constexpr int TB = 256;
 
 // ------------------------------------------------------------------ kernels
+
+__global__ void k_adjacent_diff(const uint32_t *off, uint32_t n, uint32_t *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = off[i + 1] - off[i];
+}
 
 __global__ void k_iota(uint32_t *out, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -544,6 +552,49 @@ __global__ void k_mut_src(const int32_t *mut_site, const int32_t *mut_node, uint
     mut_src[m] = (int32_t) (lo + upper_bound_dev(pc_x + lo, n, x) - 1);
 }
 
+// ------------------------------------------------------------ allele codes
+// Allele strings -> small integer codes, one thread per site (replaces the memcmp loops of
+// get_allele_weights, trees.c:1557-1596): allele 0 is the ancestral state, new derived states are
+// numbered in order of first appearance among the site's mutations (genotypes.c:533-580).  A
+// mutation's "alt" allele -- the one its node's samples are taken from -- is its parent mutation's
+// allele, or the ancestral state.  Quadratic in the mutations of one site, which are few.
+__device__ __forceinline__ bool bytes_equal(const char *a, uint64_t na, const char *b, uint64_t nb) {
+    if (na != nb) return false;
+    for (uint64_t i = 0; i < na; i++) {
+        if (a[i] != b[i]) return false;
+    }
+    return true;
+}
+
+__global__ void k_allele_codes(uint32_t S, const uint32_t *__restrict__ moff, const char *__restrict__ anc,
+    const uint64_t *__restrict__ anc_off, const char *__restrict__ der, const uint64_t *__restrict__ der_off,
+    const int32_t *__restrict__ mparent, uint16_t *m_allele, uint16_t *m_alt, uint32_t *nalleles, int *overflow) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= S) return;
+    const uint32_t m0 = moff[j], m1 = moff[j + 1];
+    const char *a = anc + anc_off[j];
+    const uint64_t na = anc_off[j + 1] - anc_off[j];
+    uint32_t count = 1;
+    for (uint32_t m = m0; m < m1; m++) {
+        const char *d = der + der_off[m];
+        const uint64_t nd = der_off[m + 1] - der_off[m];
+        int k = bytes_equal(d, nd, a, na) ? 0 : -1;
+        // an earlier mutation of the site that introduced the same string
+        for (uint32_t q = m0; k < 0 && q < m; q++) {
+            if (bytes_equal(d, nd, der + der_off[q], der_off[q + 1] - der_off[q])) k = (int) m_allele[q];
+        }
+        if (k < 0) k = (int) count++;
+        if (count > 65000u) {
+            *overflow = 1;
+            return;
+        }
+        m_allele[m] = (uint16_t) k;
+        const int32_t pm = mparent != nullptr ? mparent[m] : -1;
+        m_alt[m] = pm >= (int32_t) m0 && pm < (int32_t) m ? m_allele[pm] : (uint16_t) 0;
+    }
+    nalleles[j] = count;
+}
+
 // ------------------------------------------------------------ table integrity
 // The checks of tsk_table_collection_check_integrity (c/tskit/tables.c:10362-10640, 10894-10930)
 // that this path relies on -- every id it later uses as an index, every interval, the node time
@@ -643,6 +694,101 @@ uint64_t sum_u64(Temp &tmp, const uint32_t *p, size_t n, cudaStream_t s) {
     return h;
 }
 
+// ---- table upload: pageable host columns -> HBM through pinned staging buffers
+// cudaMemcpy from pageable memory is staged by the driver on one thread (5-8 GB/s here); the borrowed
+// table columns cannot be pinned in place cheaply.  A few host threads copy 4 MB chunks into their own
+// pinned buffers (kept for the life of the process) and launch the DMA of each on their own stream, so
+// the host copies run in parallel and overlap the transfers.
+struct UploadJob {
+    void *dst;
+    const void *src;
+    size_t bytes;
+};
+
+struct PinnedPool {
+    static constexpr size_t CHUNK = size_t(4) << 20;
+    static constexpr int MAX_THREADS = 8;
+    std::mutex mu;
+    char *buf[MAX_THREADS][2] = {};
+    char *get(int t, int b) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (buf[t][b] == nullptr) {
+            if (cudaHostAlloc((void **) &buf[t][b], CHUNK, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                buf[t][b] = nullptr;
+            }
+        }
+        return buf[t][b];
+    }
+};
+
+PinnedPool &pinned_pool() {
+    static PinnedPool *p = new PinnedPool();  // never destroyed: the buffers outlive every plan
+    return *p;
+}
+
+void staged_upload(int device, const std::vector<UploadJob> &jobs, cudaStream_t fallback) {
+    struct Chunk { char *dst; const char *src; size_t n; };
+    std::vector<Chunk> chunks;
+    size_t total = 0;
+    for (const UploadJob &j : jobs) {
+        for (size_t o = 0; o < j.bytes; o += PinnedPool::CHUNK) {
+            chunks.push_back({ (char *) j.dst + o, (const char *) j.src + o, std::min(PinnedPool::CHUNK, j.bytes - o) });
+        }
+        total += j.bytes;
+    }
+    int nt = (int) std::min<size_t>({ (size_t) PinnedPool::MAX_THREADS, std::max<size_t>(1, std::thread::hardware_concurrency() / 2),
+        std::max<size_t>(1, chunks.size() / 4) });
+    if (getenv("TSKB_UPLOAD_THREADS") != nullptr) nt = std::max(1, std::min(atoi(getenv("TSKB_UPLOAD_THREADS")), (int) PinnedPool::MAX_THREADS));
+    if (total < (size_t(16) << 20) || nt <= 1) {  // small tables: the plain copy
+        for (const UploadJob &j : jobs) {
+            if (j.bytes) TSKB_CK(cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyHostToDevice, fallback));
+        }
+        return;
+    }
+    std::atomic<size_t> next{ 0 };
+    std::atomic<int> failed{ 0 };
+    auto worker = [&](int t) {
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev[2] = { nullptr, nullptr };
+        char *b[2] = { pinned_pool().get(t, 0), pinned_pool().get(t, 1) };
+        bool ok = cudaSetDevice(device) == cudaSuccess && b[0] != nullptr && b[1] != nullptr
+                  && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess
+                  && cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) == cudaSuccess
+                  && cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) == cudaSuccess;
+        bool used[2] = { false, false };
+        int cur = 0;
+        while (ok) {
+            const size_t i = next.fetch_add(1);
+            if (i >= chunks.size()) break;
+            if (used[cur]) ok = cudaEventSynchronize(ev[cur]) == cudaSuccess;
+            if (!ok) break;
+            memcpy(b[cur], chunks[i].src, chunks[i].n);
+            ok = cudaMemcpyAsync(chunks[i].dst, b[cur], chunks[i].n, cudaMemcpyHostToDevice, st) == cudaSuccess
+                 && cudaEventRecord(ev[cur], st) == cudaSuccess;
+            used[cur] = true;
+            cur ^= 1;
+        }
+        if (st != nullptr && cudaStreamSynchronize(st) != cudaSuccess) ok = false;
+        if (!ok) failed.store(1);
+        for (auto &e : ev) {
+            if (e) cudaEventDestroy(e);
+        }
+        if (st) cudaStreamDestroy(st);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(worker, t);
+    worker(0);
+    for (auto &x : th) x.join();
+    if (failed.load()) {
+        // a worker could not stage (no pinned memory left ...): the plain copy of everything
+        cudaGetLastError();
+        for (const UploadJob &j : jobs) {
+            if (j.bytes) TSKB_CK(cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyHostToDevice, fallback));
+        }
+    }
+}
+
 template <typename K, typename Vt>
 void sort_pairs(Temp &tmp, const K *kin, K *kout, const Vt *vin, Vt *vout, uint32_t n, int end_bit,
     cudaStream_t s) {
@@ -717,22 +863,24 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     }
     P.num_samples = (uint32_t) P.samples.size();
     P.d_samples.upload(P.samples.data(), P.samples.size(), s);
-    P.time.upload(t->node_time, N, s);
     for (uint32_t u = 0; u < N; u++) P.has_negative_time |= t->node_time[u] < 0.0;
 
     Temp tmp;
     DevArray<double> el, er;
     DevArray<int32_t> ep, ec, dI, dO;
-    el.upload(t->edge_left, E, s);
-    er.upload(t->edge_right, E, s);
-    ep.upload(t->edge_parent, E, s);
-    ec.upload(t->edge_child, E, s);
-    dI.upload(t->edge_insertion_order, E, s);
-    dO.upload(t->edge_removal_order, E, s);
-    P.site_pos.upload(t->site_position, P.S, s);
-    P.mut_node.upload(t->mutation_node, P.Mu, s);
     DevArray<int32_t> d_msite;
-    d_msite.upload(t->mutation_site, P.Mu, s);
+    P.time.alloc(N);
+    el.alloc(E); er.alloc(E); ep.alloc(E); ec.alloc(E); dI.alloc(E); dO.alloc(E);
+    P.site_pos.alloc(P.S); P.mut_node.alloc(P.Mu); d_msite.alloc(P.Mu);
+    staged_upload(device, {
+        { P.time.p, t->node_time, (size_t) N * sizeof(double) },
+        { el.p, t->edge_left, (size_t) E * sizeof(double) }, { er.p, t->edge_right, (size_t) E * sizeof(double) },
+        { ep.p, t->edge_parent, (size_t) E * sizeof(int32_t) }, { ec.p, t->edge_child, (size_t) E * sizeof(int32_t) },
+        { dI.p, t->edge_insertion_order, (size_t) E * sizeof(int32_t) },
+        { dO.p, t->edge_removal_order, (size_t) E * sizeof(int32_t) },
+        { P.site_pos.p, t->site_position, (size_t) P.S * sizeof(double) },
+        { P.mut_node.p, t->mutation_node, (size_t) P.Mu * sizeof(int32_t) },
+        { d_msite.p, t->mutation_site, (size_t) P.Mu * sizeof(int32_t) } }, s);
 
     mark("host loops + table upload");
     // ---- table integrity, before anything is used as an index on the host or the device
@@ -1297,58 +1445,67 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     }
 
     mark("references + heights + order");
-    // ---- sites and mutations: allele strings -> small integer codes on the host
-    // (replaces the memcmp loops of get_allele_weights, trees.c:1557-1596)
+    // ---- sites and mutations: allele strings -> small integer codes (k_allele_codes)
     {
         const uint32_t S = (uint32_t) P.S, Mu = (uint32_t) P.Mu;
-        std::vector<uint32_t> moff(S + 1, 0), aoff(S + 1, 0);
-        std::vector<uint16_t> m_allele(Mu), m_alt(Mu);
-        for (uint32_t m = 0; m < Mu; m++) moff[t->mutation_site[m] + 1]++;
-        for (uint32_t j = 0; j < S; j++) moff[j + 1] += moff[j];
-        struct Str { const char *p; uint64_t n; };
-        std::vector<Str> alleles;
-        auto find = [&](const Str &q) -> int {
-            for (size_t k = 0; k < alleles.size(); k++) {
-                if (alleles[k].n == q.n && memcmp(alleles[k].p, q.p, q.n) == 0) return (int) k;
-            }
-            return -1;
-        };
-        for (uint32_t j = 0; j < S; j++) {
-            alleles.clear();
-            uint64_t o0 = t->site_ancestral_state_offset[j], o1 = t->site_ancestral_state_offset[j + 1];
-            alleles.push_back({ t->site_ancestral_state + o0, o1 - o0 });
-            for (uint32_t m = moff[j]; m < moff[j + 1]; m++) {
-                uint64_t d0 = t->mutation_derived_state_offset[m], d1 = t->mutation_derived_state_offset[m + 1];
-                Str der{ t->mutation_derived_state + d0, d1 - d0 };
-                int k = find(der);
-                if (k < 0) { k = (int) alleles.size(); alleles.push_back(der); }
-                m_allele[m] = (uint16_t) k;
-                Str alt = alleles[0];
-                int32_t pm = t->mutation_parent ? t->mutation_parent[m] : -1;
-                if (pm >= 0) {
-                    uint64_t p0 = t->mutation_derived_state_offset[pm], p1 = t->mutation_derived_state_offset[pm + 1];
-                    alt = Str{ t->mutation_derived_state + p0, p1 - p0 };
-                }
-                int ka = find(alt);
-                m_alt[m] = (uint16_t) (ka < 0 ? 0 : ka);
-                if (alleles.size() > 65000) throw (int) TSKB_ERR_UNSUPPORTED;
-            }
-            aoff[j + 1] = aoff[j] + (uint32_t) alleles.size();
-            P.max_alleles_per_site = std::max<uint32_t>(P.max_alleles_per_site, (uint32_t) alleles.size());
-            P.max_muts_per_site = std::max<uint32_t>(P.max_muts_per_site, moff[j + 1] - moff[j]);
-        }
-        P.total_alleles = aoff[S];
         P.h_site_pos.assign(t->site_position, t->site_position + S);
         P.site_lo = (uint32_t) (std::lower_bound(P.h_site_pos.begin(), P.h_site_pos.end(), a) - P.h_site_pos.begin());
         P.site_hi = (uint32_t) (std::lower_bound(P.h_site_pos.begin(), P.h_site_pos.end(), b) - P.h_site_pos.begin());
-        P.site_moff.upload(moff.data(), S + 1, s);
-        P.site_aoff.upload(aoff.data(), S + 1, s);
-        P.mut_allele.upload(m_allele.data(), Mu, s);
-        P.mut_alt.upload(m_alt.data(), Mu, s);
+        P.site_moff.alloc((size_t) S + 1);
+        P.site_aoff.alloc((size_t) S + 1);
+        P.mut_allele.alloc(Mu);
+        P.mut_alt.alloc(Mu);
+        // mutation CSR by site: mutation_site is sorted (checked above)
+        k_offsets<<<grid_for((size_t) S + 1, TB), TB, 0, s>>>((const uint32_t *) d_msite.p, Mu, S + 1, P.site_moff.p);
+        TSKB_CK_LAUNCH();
+        P.total_alleles = 0;
+        if (S) {
+            DevArray<char> d_anc, d_der;
+            DevArray<uint64_t> d_anc_off, d_der_off;
+            DevArray<uint32_t> nall, red;
+            DevArray<int32_t> d_mpar;
+            DevArray<int> ovf;
+            d_anc.upload(t->site_ancestral_state, t->site_ancestral_state_offset[S], s);
+            d_anc_off.upload(t->site_ancestral_state_offset, (size_t) S + 1, s);
+            if (Mu) {
+                d_der.upload(t->mutation_derived_state, t->mutation_derived_state_offset[Mu], s);
+                d_der_off.upload(t->mutation_derived_state_offset, (size_t) Mu + 1, s);
+                if (t->mutation_parent != nullptr) d_mpar.upload(t->mutation_parent, Mu, s);
+            }
+            nall.alloc((size_t) S + 1); red.alloc(2); ovf.alloc(1);
+            TSKB_CK(cudaMemsetAsync(nall.p, 0, ((size_t) S + 1) * sizeof(uint32_t), s));
+            TSKB_CK(cudaMemsetAsync(ovf.p, 0, sizeof(int), s));
+            k_allele_codes<<<grid_for(S, 128), 128, 0, s>>>(S, P.site_moff.p, d_anc.p, d_anc_off.p, d_der.p,
+                d_der_off.p, d_mpar.p, P.mut_allele.p, P.mut_alt.p, nall.p, ovf.p);
+            TSKB_CK_LAUNCH();
+            size_t bytes = 0;
+            TSKB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, nall.p, P.site_aoff.p, (size_t) S + 1, s));
+            TSKB_CK(cub::DeviceScan::ExclusiveSum(tmp.need(bytes), bytes, nall.p, P.site_aoff.p, (size_t) S + 1, s));
+            TSKB_CK(cub::DeviceReduce::Max(nullptr, bytes, nall.p, red.p, S, s));
+            TSKB_CK(cub::DeviceReduce::Max(tmp.need(bytes), bytes, nall.p, red.p, S, s));
+            // mutations per site: differences of the CSR offsets
+            DevArray<uint32_t> nm;
+            nm.alloc(S);
+            k_adjacent_diff<<<grid_for(S, TB), TB, 0, s>>>(P.site_moff.p, S, nm.p);
+            TSKB_CK_LAUNCH();
+            TSKB_CK(cub::DeviceReduce::Max(nullptr, bytes, nm.p, red.p + 1, S, s));
+            TSKB_CK(cub::DeviceReduce::Max(tmp.need(bytes), bytes, nm.p, red.p + 1, S, s));
+            uint32_t h_red[2] = { 1, 0 }, h_total = 0;
+            int h_ovf = 0;
+            TSKB_CK(cudaMemcpyAsync(h_red, red.p, sizeof(h_red), cudaMemcpyDeviceToHost, s));
+            TSKB_CK(cudaMemcpyAsync(&h_total, P.site_aoff.p + S, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            TSKB_CK(cudaMemcpyAsync(&h_ovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+            TSKB_CK(cudaStreamSynchronize(s));
+            if (h_ovf) throw (int) TSKB_ERR_UNSUPPORTED;
+            P.max_alleles_per_site = std::max<uint32_t>(1, h_red[0]);
+            P.max_muts_per_site = h_red[1];
+            P.total_alleles = h_total;
+        } else {
+            TSKB_CK(cudaMemsetAsync(P.site_aoff.p, 0, sizeof(uint32_t), s));
+        }
         if (Mu) {
             k_translate<<<grid_for(Mu, TB), TB, 0, s>>>(P.mut_src.p, Mu, perm.p);
             TSKB_CK_LAUNCH();
-            TSKB_CK(cudaStreamSynchronize(s));
         }
         TSKB_CK(cudaStreamSynchronize(s));
     }

@@ -219,3 +219,37 @@ class ShardedTreeSequence:
         h_res.copy_(res, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return h_res.numpy()
+
+    # ---- matrices
+    def divergence_matrix(self, windows, sample_sets=None, sample_set_sizes=None, mode=None,
+                          span_normalise=True):
+        """``divergence_matrix`` over the whole genome from per-range partials: this rank contracts the
+        sites (site mode: exact integer counts of differences, so the sum is bit-identical for any
+        number of ranks) or sweeps the trees (branch mode) of its own range, one ``all_reduce`` adds
+        the ``(W, n, n)`` partials, span normalisation follows the sum (``trees.c:8876-8899``)."""
+        return self.stat("divergence_matrix", windows=windows, sample_sets=sample_sets,
+                         sample_set_sizes=sample_set_sizes, mode=mode, span_normalise=span_normalise)
+
+    def genotype_matrix(self, samples=None, isolated_as_missing=True, gather=True):
+        """Genotype decode sharded by site (``genotypes.c:473-594``; sites are independent): this rank
+        decodes the sites of its range.  ``gather=False`` returns ``(first_site, block)`` -- the rows
+        stay sharded -- else every rank gets the whole ``(num_sites, n)`` int8 matrix (all_gather of
+        the blocks, padded to the largest)."""
+        import torch
+        import torch.distributed as dist
+        block = self.engine.genotype_matrix(samples=samples, isolated_as_missing=isolated_as_missing)
+        counts = [self.local_tables.num_sites]
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if multi:
+            counts = [None] * self.world
+            dist.all_gather_object(counts, self.local_tables.num_sites, group=self.group)
+        first = int(sum(counts[: self.rank])) if multi else 0
+        if not gather or not multi:
+            return (first, block) if not gather else block
+        rows, n = max(counts), block.shape[1]
+        dev = f"cuda:{self.device}" if torch.cuda.is_available() else "cpu"
+        pad = torch.zeros((rows, n), dtype=torch.int8, device=dev)
+        pad[: block.shape[0]] = torch.from_numpy(block).to(dev)
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(out, pad, group=self.group)
+        return np.concatenate([o[:c].cpu().numpy() for o, c in zip(out, counts)], axis=0)
