@@ -304,8 +304,11 @@ def run_ours(args):
 
     # inputs resident in HBM for the kernel-only number (torch owns the buffers)
     d_sets = torch.from_numpy(s.copy()).to(dev)
-    d_res1 = torch.empty((W, 1), dtype=torch.float64, device=dev)
-    d_res2 = torch.empty((W, 1), dtype=torch.float64, device=dev)
+    # the step's two (W x 1) results; two buffers, alternating: with several GPUs the all_reduce of
+    # one step is still in flight on torch's stream while the next step's sweeps write their results
+    d_bufs = [torch.empty((2, W), dtype=torch.float64, device=dev) for _ in range(2)]
+    pending = [None, None]   # event after the last collective that used each buffer
+    step_no = [0]
     torch.cuda.synchronize()
 
     def p(a):
@@ -315,24 +318,32 @@ def run_ours(args):
     launches = [0]
     coll_ev = []
 
-    def step_device():
+    def step_device(collect=True):
         """One step with inputs and outputs in HBM; returns the engine's device time (CUDA events on
-        the engine's stream); the collective is timed by events on torch's stream (coll_ev)."""
+        the engine's stream).  Several GPUs: both statistics' un-normalised partials go through ONE
+        all_reduce (NCCL, on torch's stream: it overlaps the next step's first sweep on the engine's
+        stream) followed by the span normalisation; coll_ev brackets it."""
         ms = 0.0
-        for nm, sizes, tup, out in (("diversity", sizes1, None, d_res1), ("divergence", sizes2, idx, d_res2)):
-            if world == 1:
-                ll.stat_device(nm, sizes, d_sets.data_ptr(), tup, windows, options, out.data_ptr())
-            else:
-                ll.stat_device(nm, sizes, d_sets.data_ptr(), tup, windows, STAT_BRANCH, out.data_ptr())
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                sharding.combine(out, windows, True)      # all_reduce over NCCL + span normalisation
-                e1.record()
-                coll_ev.append((e0, e1))
-            es = ll.engine_stats()
-            ms += es["last_call_ms"]
-            phase_ms[:] += np.array(es["last_kernel_ms"][:6])
-            launches[0] += es["last_launches"]
+        b = step_no[0] & 1
+        step_no[0] += 1
+        d_both = d_bufs[b]
+        if pending[b] is not None:
+            pending[b].synchronize()   # the collective of two steps ago has released this buffer
+        for nm, sizes, tup, out in (("diversity", sizes1, None, d_both[0]), ("divergence", sizes2, idx, d_both[1])):
+            ll.stat_device(nm, sizes, d_sets.data_ptr(), tup, windows, options if world == 1 else STAT_BRANCH,
+                           out.data_ptr())
+            if collect:
+                es = ll.engine_stats()
+                ms += es["last_call_ms"]
+                phase_ms[:] += np.array(es["last_kernel_ms"][:6])
+                launches[0] += es["last_launches"]
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sharding.combine(d_both, windows, True, window_axis=1)
+            e1.record()
+            coll_ev.append((e0, e1))
+            pending[b] = e1
         return ms
 
     # host buffers for the end-to-end number: the reference-facing C ABI at one GPU, the sharded host
@@ -394,13 +405,26 @@ def run_ours(args):
     barrier()
     torch.cuda.synchronize()
     dev_ms = 0.0
+    span0, span1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    span0.record()
     for _ in range(blocks):
         for _ in range(args.steps):
-            dev_ms += step_device()
-    coll_ms = collective_ms()
-    dev_ms += coll_ms
+            dev_ms += step_device(collect=world == 1)
+    span1.record()          # follows the last all_reduce + normalisation; the engine calls are synchronous
+    torch.cuda.synchronize()
     wall_dev = time.perf_counter() - t0
+    coll_ms = collective_ms()
+    if world > 1:
+        # Engine work (its own stream) and collectives (torch's stream) overlap and cannot be added up:
+        # the device time of the timed region is the span between two events that bracket it.  The
+        # per-phase engine times come from a few extra steps outside the timed region.
+        dev_ms = span0.elapsed_time(span1)
+        for _ in range(5):
+            step_device(collect=True)
+        phase_ms *= nsteps_scale(blocks * args.steps, 5)
+        launches[0] = int(launches[0] * nsteps_scale(blocks * args.steps, 5))
+        collective_ms()
     barrier()
     torch.cuda.synchronize()
     e2e_blocks = max(1, blocks // 2)
@@ -450,6 +474,8 @@ def run_ours(args):
             cpu, want = cpu_baseline(base, W1, nev_base, best_of=2 if world == 1 else 1)
             if want is not None:
                 # every copy of the genome repeats the base ARG: each block of W1 windows is the base result
+                d_last = d_bufs[(step_no[0] - 1) & 1]   # the last device-resident step's results
+                d_res1, d_res2 = d_last[0], d_last[1]
                 e1 = max(rel_err(got1.reshape(world, W1), np.broadcast_to(want[0].reshape(1, W1), (world, W1))),
                          rel_err(d_res1.cpu().numpy().reshape(world, W1),
                                  np.broadcast_to(want[0].reshape(1, W1), (world, W1))))
@@ -475,8 +501,10 @@ def run_ours(args):
                 "l2": "inputs larger than L2 (plan arrays %.2f GB per rank)" % (st["device_bytes"] / 1e9),
                 "sharding": ("whole genome on one GPU" if world == 1 else
                              f"genome ranges from sharding.plan_shards, one per rank; per statistic one "
-                             f"all_reduce of {W} x 1 doubles on device-resident partials inside the timed "
-                             f"region ({coll_ms / nsteps:.3f} ms per step incl. waiting for the slowest rank)"),
+                             f"all_reduce of both statistics' {W} x 1 device-resident partials inside the "
+                             f"timed region ({coll_ms / nsteps:.3f} ms per step on torch's stream incl. waiting "
+                             "for the slowest rank; it overlaps the next step's first sweep); value = edge "
+                             "diffs / device span of the timed region (CUDA events around it)"),
                 "timed_blocks": blocks, "timed_steps": nsteps, "timed_seconds_device": dev_ms / 1e3,
                 "stage_s": stage_s, "init_s": init_s, "tile_s": tile_s, "generate_s": gen_s,
                 "phase_ms_per_step": dict(zip(names, [float(x) for x in per_step_ms])),
@@ -515,6 +543,11 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def nsteps_scale(timed_steps, sampled_steps):
+    """Per-phase engine times are sampled over a few steps and reported per timed step."""
+    return timed_steps / float(sampled_steps)
 
 
 def cpu_baseline(t, W, nev, best_of=2):
@@ -756,6 +789,8 @@ def run_c3(args):
             for nm, ix in calls}
     phase = {}
     coll_ev = []
+    p0 = torch.from_numpy(pairs[:, 0].astype(np.int64)).to(dev)
+    p1 = torch.from_numpy(pairs[:, 1].astype(np.int64)).to(dev)
 
     def step():
         ms = 0.0
@@ -769,7 +804,7 @@ def run_c3(args):
             sharding.combine(outs[nm], windows, True)
             if nm == "divergence":  # Fst = 1 - 2 (pi_u + pi_v) / (pi_u + pi_v + 2 d_uv)
                 pi = outs["diversity"]
-                su = pi[:, pairs[:, 0]] + pi[:, pairs[:, 1]]
+                su = pi[:, p0] + pi[:, p1]
                 outs["Fst"] = 1 - 2 * su / (su + 2 * outs["divergence"])
             e1.record()
             coll_ev.append((e0, e1))
@@ -790,13 +825,19 @@ def run_c3(args):
         sampler.start()
     barrier()
     torch.cuda.synchronize()
-    dev_ms = 0.0
+    engine_ms = 0.0
+    span0, span1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    span0.record()
     for _ in range(args.steps):
-        dev_ms += step()
-    coll_ms = collective_ms()
-    dev_ms += coll_ms
+        engine_ms += step()
+    span1.record()
+    torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    coll_ms = collective_ms()
+    # device time of the timed region: the span between the two events that bracket it (the engine's
+    # calls are synchronous, the collectives run on torch's stream and may overlap the next sweep)
+    dev_ms = span0.elapsed_time(span1)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -833,6 +874,7 @@ def run_c3(args):
                 "per_rank_plan_bytes_and_edge_diffs": per_rank,
                 "ms_per_step_by_statistic": {k: v / args.steps for k, v in phase.items()},
                 "collective_ms_per_step": coll_ms / args.steps, "wall_ms_per_step": wall / args.steps * 1e3,
+                "engine_ms_per_step_rank0": engine_ms / args.steps,
                 "generate_s": gen_s, "concat_s": concat_s, "stage_s": stage_s, "levels": st["num_levels"],
                 "checksum": checksum},
             "clocks": clocks, "parity": parity,

@@ -230,6 +230,20 @@ int tskb_treeseq_sample_count_stat_tabulated(const tskb_treeseq_t *self,
     const double *f_table, uint64_t num_windows, const double *windows,
     uint32_t options, double *result);
 
+/* tsk_treeseq_general_stat (c/tskit/trees.h:1035-1037; trees.c:2035-2095) with the reference's own
+ * callback type general_stat_func_t (trees.h:1032-1033): `weights` row-major [num_samples x
+ * state_dim], `f(state_dim, state, result_dim, result, params)` returns 0 or an error code, which
+ * aborts the call and is returned (trees.c:1396-1399, 1441).  The engine sweeps first, then calls `f`
+ * on the host ONCE PER DISTINCT state vector (branch mode: also at total - state unless
+ * TSK_STAT_POLARISED; site mode: the allele states) instead of once per node update, and integrates
+ * the tabulated values on the device.  Site and branch mode, state_dim <= 8; node mode and wider
+ * states: TSKB_ERR_UNSUPPORTED. */
+typedef int tskb_general_stat_func_t(uint64_t state_dim, const double *state, uint64_t result_dim,
+    double *result, void *params);
+int tskb_treeseq_general_stat(const tskb_treeseq_t *self, uint64_t state_dim, const double *weights,
+    uint64_t result_dim, tskb_general_stat_func_t *f, void *f_params, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result);
+
 /* tsk_treeseq_divergence_matrix, c/tskit/trees.h:1241 (trees.c:8901-9001) */
 int tskb_treeseq_divergence_matrix(const tskb_treeseq_t *self, uint64_t num_sample_sets,
     const uint64_t *sample_set_sizes, const int32_t *sample_sets, uint64_t num_windows,

@@ -362,6 +362,56 @@ def test_custom_summary_function_tabulated(wf_small, engines):
     assert np.allclose(g[:, 0], d[:, 0], rtol=1e-12)
 
 
+def test_general_stat_with_a_callback(wf_small, engines):
+    """tsk_treeseq_general_stat with a Python summary over several state columns and over float
+    weights (trees.py:7917-8004): the engine sweeps, collects the distinct state vectors on the device and
+    calls f once per vector.  Against the oracle's restatement, which calls f at every node update."""
+    ll, o = engines
+    s = wf_small.samples
+    n = len(s)
+    rng = np.random.default_rng(5)
+    windows = np.linspace(0, wf_small.sequence_length, 6)
+    # two overlapping sample sets as 0/1 columns: divergence + a non-linear column
+    W2 = np.zeros((n, 2))
+    W2[:120, 0] = 1
+    W2[80:, 1] = 1
+    n0, n1 = W2.sum(axis=0)
+    calls = [0]
+
+    def f2(x):
+        calls[0] += 1
+        return np.array([x[0] * (n1 - x[1]) / (n0 * n1), float(x[0] > 0) * x[1] ** 2, x[0] + 2 * x[1]])
+
+    for mode in ("branch", "site"):
+        for pol in (False, True):
+            for sn in (True, False):
+                got = ll.general_stat(W2, f2, 3, windows=windows, mode=mode, polarised=pol, span_normalise=sn)
+                want = o.general_stat(W2, f2, 3, windows=windows, mode=mode, polarised=pol, span_normalise=sn)
+                assert close(got, want, cancelling=True), (mode, pol, sn)
+    # the callback runs once per distinct vector, not once per node update
+    calls[0] = 0
+    ll.general_stat(W2, f2, 3, windows=windows, mode="branch", polarised=True)
+    distinct_calls = calls[0]
+    calls[0] = 0
+    o.general_stat(W2, f2, 3, windows=windows, mode="branch", polarised=True)
+    assert 0 < distinct_calls < calls[0] / 5
+    # float weights, three columns; many result columns (the by-column summary path)
+    Wf = rng.normal(size=(n, 3))
+
+    def f3(x):
+        return np.concatenate([x * x, [x[0] * x[1], np.abs(x).sum(), 1.0, x[2] - x[0]]])
+
+    for mode in ("branch", "site"):
+        got = ll.general_stat(Wf, f3, 7, windows=windows, mode=mode, polarised=False)
+        want = o.general_stat(Wf, f3, 7, windows=windows, mode=mode, polarised=False)
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max()), mode
+    # failures of the callback surface as they are
+    with pytest.raises(ZeroDivisionError):
+        ll.general_stat(W2, lambda x: np.array([1 / 0]), 1, windows=windows, mode="branch")
+    with pytest.raises(ValueError, match="wrong dimension"):
+        ll.general_stat(W2, lambda x: np.array([1.0, 2.0]), 1, windows=windows, mode="branch")
+
+
 def test_genome_range_shards_sum_to_whole(wf_small, engines):
     """multi-GPU decomposition: shards over [a, b) computed independently add up per window"""
     from tskit_b200.lowlevel import LLTreeSequence

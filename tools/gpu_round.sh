@@ -51,7 +51,11 @@ for i in range(3):
     ll.close()
 EOF
 grep -E "^init|tskb init" $OUT/init_phases.txt | tail -24
-if [ "$MODE" != "quick" ]; then
+if [ "$MODE" == "c3" ]; then
+timeout 1500 python bench.py --config c3 --steps 3 --warmup 1 > $OUT/c3_n1.json 2> $OUT/c3_n1.err; echo "c3 N=1 exit $?"
+head -c 3000 $OUT/c3_n1.json; echo; tail -5 $OUT/c3_n1.err
+fi
+if [ "$MODE" == "full" ]; then
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref exit $?"
 cat $OUT/bench_ref.json
 timeout 300 python tools/piece_stats.py > $OUT/piece_stats.txt 2>&1; tail -12 $OUT/piece_stats.txt

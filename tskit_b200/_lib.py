@@ -55,6 +55,10 @@ class Stats(C.Structure):
     ]
 
 
+# tskb_general_stat_func_t = general_stat_func_t of c/tskit/trees.h:1032-1033
+GENERAL_STAT_FUNC = C.CFUNCTYPE(C.c_int, C.c_uint64, C.POINTER(C.c_double), C.c_uint64, C.POINTER(C.c_double),
+                                C.c_void_p)
+
 # every symbol include/tskit_b200.h declares
 SYMBOLS = [
     "tskb_treeseq_init", "tskb_treeseq_free", "tskb_strerror", "tskb_last_cuda_error",
@@ -66,6 +70,7 @@ SYMBOLS = [
     "tskb_treeseq_genetic_relatedness_weighted", "tskb_treeseq_genetic_relatedness_vector", "tskb_treeseq_trait_linear_model",
     "tskb_treeseq_allele_frequency_spectrum",
     "tskb_treeseq_divergence_matrix", "tskb_treeseq_genotype_matrix",
+    "tskb_treeseq_general_stat",
     "tskb_treeseq_trees_at", "tskb_treeseq_get_stats", "tskb_treeseq_stat_device",
     "tskb_treeseq_debug_array",
 ]
@@ -118,6 +123,8 @@ def lib():
         L.tskb_treeseq_stat_device.argtypes = [C.c_void_p, C.c_int, u64, C.c_void_p, C.c_void_p,
                                                u64, C.c_void_p, u64, C.c_void_p, C.c_uint32,
                                                C.c_void_p]
+        L.tskb_treeseq_general_stat.argtypes = [C.c_void_p, u64, C.c_void_p, u64, GENERAL_STAT_FUNC, C.c_void_p,
+                                                u64, C.c_void_p, C.c_uint32, C.c_void_p]
         L.tskb_treeseq_debug_array.restype = C.c_int64
         L.tskb_treeseq_debug_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, u64]
         _lib = L

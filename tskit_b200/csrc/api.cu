@@ -865,6 +865,42 @@ int tskb_treeseq_sample_count_stat_tabulated(const tskb_treeseq_t *self,
         num_windows, windows, options, result, false);
 }
 
+int tskb_treeseq_general_stat(const tskb_treeseq_t *self, uint64_t state_dim, const double *weights,
+    uint64_t result_dim, tskb_general_stat_func_t *f, void *f_params, uint64_t num_windows,
+    const double *windows, uint32_t options, double *result) {
+    if (self == nullptr || self->plan == nullptr || f == nullptr || result == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    if (state_dim > 0 && weights == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    const Plan &P = *self->plan;
+    return guarded([&]() -> int {
+        // checks in tsk_treeseq_general_stat's order (trees.c:2035-2095)
+        bool site = options & TSKB_STAT_SITE, branch = options & TSKB_STAT_BRANCH, node = options & TSKB_STAT_NODE;
+        if (!(site || branch || node)) {
+            site = true;
+            options |= TSKB_STAT_SITE;
+        }
+        if (site + branch + node > 1) return TSKB_ERR_MULTIPLE_STAT_MODES;
+        if (state_dim < 1) return TSKB_ERR_BAD_STATE_DIMS;
+        if (result_dim < 1) return TSKB_ERR_BAD_RESULT_DIMS;
+        double default_windows[2] = { 0, P.L };
+        if (windows == nullptr) {
+            num_windows = 1;
+            windows = default_windows;
+        } else {
+            int ret = check_windows(P, num_windows, windows, true);
+            if (ret != 0) return ret;
+        }
+        if (branch && P.time_uncalibrated && !(options & TSKB_STAT_ALLOW_TIME_UNCALIBRATED)) {
+            return TSKB_ERR_TIME_UNCALIBRATED;
+        }
+        if (node || state_dim > MAX_STATE_DIM) return TSKB_ERR_UNSUPPORTED;
+        GeneralSpec g = {};
+        g.K = (uint32_t) state_dim; g.M = (uint32_t) result_dim; g.W = (uint32_t) num_windows;
+        g.weights = weights; g.f = (general_stat_func) f; g.params = f_params;
+        g.windows = windows; g.options = options; g.result = result;
+        return run_general_stat(&P, g);
+    });
+}
+
 int tskb_treeseq_stat_device(const tskb_treeseq_t *self, int stat_id, uint64_t num_sample_sets,
     const uint64_t *sample_set_sizes, const int32_t *d_sample_sets, uint64_t num_index_tuples,
     const int32_t *index_tuples, uint64_t num_windows, const double *windows, uint32_t options,

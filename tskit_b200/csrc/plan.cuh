@@ -210,6 +210,19 @@ enum StatId {
     STAT_REL_SIDE = 19
 };
 
+// tsk_treeseq_general_stat with a host callback (general_stat_func_t, trees.h:1032-1033)
+typedef int (*general_stat_func)(uint64_t state_dim, const double *state, uint64_t result_dim, double *result,
+    void *params);
+struct GeneralSpec {
+    uint32_t K, M, W;
+    const double *weights;   // host [num_samples x K]
+    general_stat_func f;
+    void *params;
+    const double *windows;   // host [W + 1]
+    uint32_t options;
+    double *result;          // host [W x M]
+};
+int run_general_stat(const Plan *plan, const GeneralSpec &spec);
 int run_sample_count_stat(const Plan *plan, const StatSpec &spec);
 int run_weighted_stat(const Plan *plan, const StatSpec &spec);
 int run_trees_at(const Plan *plan, uint64_t nq, const double *positions, const int32_t *tracked,

@@ -1506,13 +1506,14 @@ struct CallCtx {
     int *d_err;
     uint32_t *d_counters;
     uint64_t launches;
+    bool skip_sweep;  // the "states" handed to the summary are already final (run_general_stat)
 };
 
 template <class V>
 void launch_sweep(CallCtx &c, V *pval) {
     const Plan &P = *c.P;
     Arena &A = P.arena;
-    if (P.ntiles == 0) return;
+    if (P.ntiles == 0 || c.skip_sweep) return;
     uint32_t *counters = c.d_counters;  // zeroed with the per-call staging copy
     unsigned long long *trace = nullptr;
     if (getenv("TSKB_TRACE") != nullptr) {
@@ -2218,7 +2219,285 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     return 0;
 }
 
+// ---------------------------------------------------------------- general_stat with a host callback
+// tsk_treeseq_general_stat (trees.c:2035-2095) calls the summary function f at every node update.  Here
+// the sweep runs first (fp64 states: sums of the weight rows), the DISTINCT state vectors are collected
+// on the device (K stable radix sorts of a permutation, one per state column, then a head scan), f is
+// called on the host once per distinct vector (branch mode: f(x) + f(total - x) unless polarised,
+// trees.c:1944-1972), and the table of its values is read back by the ordinary summary kernels, whose
+// "state" is then the index of the piece's vector.  Site mode does the same over the allele states.
+__device__ __forceinline__ unsigned long long gs_ordered_bits(double x) {
+    unsigned long long b = (unsigned long long) __double_as_longlong(x);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+template <class V>
+__global__ void k_gs_keys(uint32_t n, const uint32_t *__restrict__ perm, const V *__restrict__ vals, int k,
+    unsigned long long *keys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = gs_ordered_bits((double) pick<V>(vals[perm[i]], k));
+}
+
+template <class V>
+__global__ void k_gs_heads(uint32_t n, const uint32_t *__restrict__ perm, const V *__restrict__ vals,
+    uint32_t *head) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool h = i == 0;
+    if (!h) {
+        const V a = vals[perm[i]], b = vals[perm[i - 1]];
+#pragma unroll
+        for (int k = 0; k < V::N; k++) h |= __double_as_longlong(a.v[k]) != __double_as_longlong(b.v[k]);
+    }
+    head[i] = h ? 1u : 0u;
+}
+
+template <class V>
+__global__ void k_gs_scatter(uint32_t n, const uint32_t *__restrict__ perm, const V *__restrict__ vals,
+    const uint32_t *__restrict__ head, const uint32_t *__restrict__ rank_incl, int K, int32_t *idx, double *distinct) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t r = rank_incl[i] - 1;
+    idx[perm[i]] = (int32_t) r;
+    if (head[i]) {
+        const V a = vals[perm[i]];
+        for (int k = 0; k < K; k++) distinct[(size_t) r * K + k] = pick<V>(a, k);
+    }
+}
+
+__global__ void k_gs_valid(uint32_t npp, const uint32_t *__restrict__ q_bp1, uint8_t *flag) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < npp) flag[j] = q_bp1[j] != NO_PIECE;
+}
+
+// allele states of every site (the loop of k_site_summary, states kept)
+template <class V>
+__global__ void k_site_states(uint32_t site_lo, uint32_t nsites, const uint32_t *site_moff,
+    const uint32_t *site_aoff, const int32_t *mut_src, const uint16_t *mut_allele, const uint16_t *mut_alt,
+    const V *pval, V totals, V *scratch) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsites) return;
+    const uint32_t site = site_lo + t;
+    const uint32_t a0 = site_aoff[site], na = site_aoff[site + 1] - a0;
+    scratch[a0] = totals;  // allele 0 starts at total_weight (trees.c:1548)
+    for (uint32_t al = 1; al < na; al++) scratch[a0 + al] = ivec_zero<V>();
+    for (uint32_t m = site_moff[site]; m < site_moff[site + 1]; m++) {
+        const V x = pval[mut_src[m]];
+        scratch[a0 + mut_allele[m]] = scratch[a0 + mut_allele[m]] + x;
+        scratch[a0 + mut_alt[m]] = scratch[a0 + mut_alt[m]] - x;
+    }
+}
+
+__global__ void k_site_apply(uint32_t site_lo, uint32_t nsites, const uint32_t *site_aoff,
+    const int32_t *__restrict__ idx, const double *__restrict__ table, uint32_t M, int polarised, double *R) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsites) return;
+    const uint32_t site = site_lo + t;
+    const uint32_t a0 = site_aoff[site], na = site_aoff[site + 1] - a0;
+    for (uint32_t m = 0; m < M; m++) {
+        double acc = 0.0;
+        for (uint32_t al = polarised ? 1 : 0; al < na; al++) acc += table[(size_t) idx[a0 + al] * M + m];
+        R[(size_t) m * nsites + t] = acc;
+    }
+}
+
+// items (state slots) -> index of their distinct vector; the distinct vectors on the host
+template <class V>
+uint32_t distinct_states(const Plan &P, cudaStream_t s, const V *vals, const uint32_t *items, uint32_t n,
+    int K, int32_t *idx, std::vector<double> &h_distinct) {
+    if (n == 0) return 0;
+    DevArray<uint32_t> perm_a, perm_b, head, rank;
+    DevArray<unsigned long long> key_a, key_b;
+    DevArray<char> tmp;
+    perm_a.alloc(n); perm_b.alloc(n); head.alloc(n); rank.alloc(n); key_a.alloc(n); key_b.alloc(n);
+    TSKB_CK(cudaMemcpyAsync(perm_a.p, items, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    size_t bytes = 0, scan_bytes = 0;
+    TSKB_CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key_a.p, key_b.p, perm_a.p, perm_b.p, n, 0, 64, s));
+    TSKB_CK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, head.p, rank.p, n, s));
+    tmp.alloc(std::max(bytes, scan_bytes));
+    uint32_t *pa = perm_a.p, *pb = perm_b.p;
+    for (int k = K - 1; k >= 0; k--) {  // least significant column first: stable sorts
+        k_gs_keys<V><<<grid_for(n, TB), TB, 0, s>>>(n, pa, vals, k, key_a.p);
+        TSKB_CK_LAUNCH();
+        TSKB_CK(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, key_a.p, key_b.p, pa, pb, n, 0, 64, s));
+        std::swap(pa, pb);
+    }
+    k_gs_heads<V><<<grid_for(n, TB), TB, 0, s>>>(n, pa, vals, head.p);
+    TSKB_CK_LAUNCH();
+    TSKB_CK(cub::DeviceScan::InclusiveSum(tmp.p, scan_bytes, head.p, rank.p, n, s));
+    uint32_t D = 0;
+    TSKB_CK(cudaMemcpyAsync(&D, rank.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    TSKB_CK(cudaStreamSynchronize(s));
+    DevArray<double> d_distinct;
+    d_distinct.alloc((size_t) D * K);
+    k_gs_scatter<V><<<grid_for(n, TB), TB, 0, s>>>(n, pa, vals, head.p, rank.p, K, idx, d_distinct.p);
+    TSKB_CK_LAUNCH();
+    h_distinct.resize((size_t) D * K);
+    TSKB_CK(cudaMemcpyAsync(h_distinct.data(), d_distinct.p, (size_t) D * K * sizeof(double), cudaMemcpyDeviceToHost, s));
+    TSKB_CK(cudaStreamSynchronize(s));
+    return D;
+}
+
+template <class V>
+int run_general_impl(const Plan &P, const GeneralSpec &g) {
+    cudaStream_t s = P.stream;
+    const uint32_t K = g.K, M = g.M, W = g.W;
+    const bool branch = (g.options & TSKB_STAT_BRANCH) != 0;
+    const int polarised = (g.options & TSKB_STAT_POLARISED) ? 1 : 0;
+    Arena &A = P.arena;
+    A.reset();
+    CallCtx c = {};
+    StatSpec sp = {};
+    sp.stat_id = STAT_TABULATED; sp.K = 1; sp.M = M; sp.W = W; sp.windows = g.windows; sp.options = g.options;
+    c.P = &P; c.sp = &sp; c.s = s;
+    TSKB_CK(cudaEventRecord(P.ev[0], s));
+    // per-call inputs: [0] flags / counters, then the window edges
+    const size_t o_win = 32, stage_bytes = o_win + (size_t) (W + 1) * sizeof(double);
+    std::vector<unsigned long long> stage((stage_bytes + 7) / 8, 0);
+    memcpy(reinterpret_cast<char *>(stage.data()) + o_win, g.windows, (W + 1) * sizeof(double));
+    char *ds = A.get<char>(stage_bytes);
+    TSKB_CK(cudaMemcpyAsync(ds, stage.data(), stage_bytes, cudaMemcpyHostToDevice, s));
+    c.d_err = reinterpret_cast<int *>(ds + 8);
+    c.d_counters = reinterpret_cast<uint32_t *>(ds + 16);
+    c.d_windows = reinterpret_cast<double *>(ds + o_win);
+    // states: the weight rows of the samples (trees.c:1406-1415)
+    V *pval = A.get<V>((size_t) P.npp + P.num_samples + 1);
+    V *init = pval + P.npp;
+    TSKB_CK(cudaMemsetAsync(init, 0, ((size_t) P.num_samples + 1) * sizeof(V), s));
+    double *d_w = A.get<double>((size_t) P.num_samples * K);
+    TSKB_CK(cudaMemcpyAsync(d_w, g.weights, (size_t) P.num_samples * K * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (P.num_samples) {
+        k_init_weights<V><<<grid_for(P.num_samples, TB), TB, 0, s>>>(d_w, P.num_samples, K, init);
+        TSKB_CK_LAUNCH();
+        c.launches++;
+    }
+    std::vector<double> total(K, 0.0);  // total_weight, summed over the samples in order (trees.c:2003-2010)
+    for (uint64_t j = 0; j < P.num_samples; j++) {
+        for (uint32_t k = 0; k < K; k++) total[k] += g.weights[j * K + k];
+    }
+    V totals = ivec_zero<V>();
+    for (uint32_t k = 0; k < K; k++) totals.v[k] = total[k];
+    TSKB_CK(cudaEventRecord(P.ev[1], s));
+    launch_sweep<V>(c, pval);
+    TSKB_CK(cudaEventRecord(P.ev[2], s));
+    // the vectors f is evaluated at: branch mode the states of the pieces, site mode the allele states
+    const uint32_t nsites = P.site_hi - P.site_lo;
+    const V *vals = pval;
+    uint32_t n_items = 0;
+    DevArray<uint32_t> items;
+    int32_t *idx = nullptr;
+    if (branch) {
+        DevArray<uint8_t> flag;
+        DevArray<uint32_t> iota, cnt;
+        flag.alloc(P.npp); iota.alloc(P.npp); cnt.alloc(1); items.alloc(P.npp);
+        idx = reinterpret_cast<int32_t *>(A.get<IVec<1>>((size_t) P.npp + P.num_samples + 1));
+        TSKB_CK(cudaMemsetAsync(idx, 0, ((size_t) P.npp + P.num_samples + 1) * sizeof(int32_t), s));
+        if (P.npp) {
+            k_gs_valid<<<grid_for(P.npp, TB), TB, 0, s>>>(P.npp, P.q_bp1.p, flag.p);
+            TSKB_CK_LAUNCH();
+            size_t bytes = 0;
+            cub::CountingInputIterator<uint32_t> it(0);
+            TSKB_CK(cub::DeviceSelect::Flagged(nullptr, bytes, it, flag.p, items.p, cnt.p, (int) P.npp, s));
+            DevArray<char> tmp;
+            tmp.alloc(bytes);
+            TSKB_CK(cub::DeviceSelect::Flagged(tmp.p, bytes, it, flag.p, items.p, cnt.p, (int) P.npp, s));
+            TSKB_CK(cudaMemcpyAsync(&n_items, cnt.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            TSKB_CK(cudaStreamSynchronize(s));
+        }
+    } else {
+        V *scratch = A.get<V>(P.total_alleles + 1);
+        idx = A.get<int32_t>(P.total_alleles + 1);
+        // the allele slots of the sites inside this plan's range are contiguous
+        uint32_t a_lo = 0, a_hi = 0;
+        TSKB_CK(cudaMemcpyAsync(&a_lo, P.site_aoff.p + P.site_lo, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        TSKB_CK(cudaMemcpyAsync(&a_hi, P.site_aoff.p + P.site_hi, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        TSKB_CK(cudaStreamSynchronize(s));
+        n_items = a_hi - a_lo;
+        items.alloc(std::max<uint32_t>(n_items, 1));
+        if (n_items) {
+            k_site_states<V><<<grid_for(nsites, 128), 128, 0, s>>>(P.site_lo, nsites, P.site_moff.p, P.site_aoff.p,
+                P.mut_src.p, P.mut_allele.p, P.mut_alt.p, pval, totals, scratch);
+            TSKB_CK_LAUNCH();
+            std::vector<uint32_t> h(n_items);
+            for (uint32_t i = 0; i < n_items; i++) h[i] = a_lo + i;
+            TSKB_CK(cudaMemcpyAsync(items.p, h.data(), (size_t) n_items * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            TSKB_CK(cudaStreamSynchronize(s));
+        }
+        vals = scratch;
+    }
+    std::vector<double> h_distinct;
+    const uint32_t D = distinct_states<V>(P, s, vals, items.p, n_items, (int) K, idx, h_distinct);
+    // f on the host, once per distinct vector; a non-zero return aborts the call and is handed back
+    // (trees.c:1396-1399, 1441)
+    std::vector<double> table((size_t) std::max<uint32_t>(D, 1) * M, 0.0), tmp_out(M), other(K);
+    bool finite = true;
+    for (uint32_t d = 0; d < D; d++) {
+        double *row = table.data() + (size_t) d * M;
+        int ret = g.f(K, h_distinct.data() + (size_t) d * K, M, row, g.params);
+        if (ret != 0) return ret;
+        if (branch && !polarised) {
+            for (uint32_t k = 0; k < K; k++) other[k] = total[k] - h_distinct[(size_t) d * K + k];
+            ret = g.f(K, other.data(), M, tmp_out.data(), g.params);
+            if (ret != 0) return ret;
+            for (uint32_t m = 0; m < M; m++) row[m] += tmp_out[m];
+        }
+        for (uint32_t m = 0; m < M; m++) finite &= std::isfinite(row[m]);
+    }
+    double *d_tab = A.get<double>(table.size());
+    TSKB_CK(cudaMemcpyAsync(d_tab, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    c.d_result = A.get<double>((size_t) W * M);
+    SumP &sumP = c.sumP;
+    sumP.K = 1; sumP.M = (int) M; sumP.polarised = 1;  // the table already holds f(x) + f(total - x)
+    sumP.skip_zero_bl = finite ? 1 : 0;
+    sumP.table = d_tab; sumP.table_rows = std::max<uint32_t>(D, 1);
+    // result columns: only their number matters to a tabulated summary
+    std::vector<ColP> cols(M);
+    for (uint32_t m = 0; m < M; m++) {
+        cols[m] = ColP{};
+        cols[m].inv = 1.0;
+    }
+    ColP *d_cols = A.get<ColP>(M);
+    TSKB_CK(cudaMemcpyAsync(d_cols, cols.data(), M * sizeof(ColP), cudaMemcpyHostToDevice, s));
+    sumP.cols = d_cols;
+    if (branch) {
+        c.skip_sweep = true;
+        IVec<1> zero = ivec_zero<IVec<1>>();
+        run_branch<STAT_TABULATED, IVec<1>>(c, reinterpret_cast<IVec<1> *>(idx), zero);
+    } else {
+        const uint32_t nsplit = std::max<uint32_t>(1, (592 + W - 1) / W);
+        double *partial = A.get<double>((size_t) W * nsplit * M);
+        double *R = A.get<double>((size_t) M * std::max<uint32_t>(nsites, 1));
+        if (nsites) {
+            k_site_apply<<<grid_for(nsites, 128), 128, 0, s>>>(P.site_lo, nsites, P.site_aoff.p, idx, d_tab, M, polarised, R);
+            TSKB_CK_LAUNCH();
+        }
+        TSKB_CK(cudaEventRecord(P.ev[3], s));
+        k_window_site<<<dim3(W, nsplit), TB, 0, s>>>(c.d_windows, nsplit, P.site_pos.p, P.site_lo, nsites, R, M, partial);
+        k_window_final<<<grid_for((size_t) W * M, TB), TB, 0, s>>>(partial, c.d_windows, W, nsplit, M,
+            (g.options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0, c.d_result);
+        TSKB_CK_LAUNCH();
+        TSKB_CK(cudaEventRecord(P.ev[4], s));
+    }
+    TSKB_CK(cudaEventRecord(P.ev[5], s));
+    TSKB_CK(cudaMemcpyAsync(g.result, c.d_result, (size_t) W * M * sizeof(double), cudaMemcpyDeviceToHost, s));
+    TSKB_CK(cudaEventRecord(P.ev[6], s));
+    TSKB_CK(cudaStreamSynchronize(s));
+    P.stats.last_launches = c.launches;
+    P.stats.last_kernel_ms[7] = (double) D;  // distinct state vectors = calls of f (x 2 when not polarised)
+    return 0;
+}
+
 }  // namespace
+
+int run_general_stat(const Plan *plan, const GeneralSpec &g) {
+    std::lock_guard<std::mutex> lock(plan->mu);
+    TSKB_CK(cudaSetDevice(plan->device));
+    if (g.K <= 1) return run_general_impl<DVec<1>>(*plan, g);
+    if (g.K <= 2) return run_general_impl<DVec<2>>(*plan, g);
+    if (g.K <= 4) return run_general_impl<DVec<4>>(*plan, g);
+    if (g.K <= 8) return run_general_impl<DVec<8>>(*plan, g);
+    return TSKB_ERR_UNSUPPORTED;
+}
 
 int run_sample_count_stat(const Plan *plan, const StatSpec &spec) {
     std::lock_guard<std::mutex> lock(plan->mu);

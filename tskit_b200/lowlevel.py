@@ -304,13 +304,8 @@ class LLTreeSequence:
             options |= STAT_SPAN_NORMALISE
         if polarised:
             options |= STAT_POLARISED
-        if not np.all((W == 0) | (W == 1)):
-            raise LibraryError(-20003, "general_stat on the B200 engine needs 0/1 sample "
-                               "weights (sample_count_stat); weighted statistics are not "
-                               "accelerated")
-        if W.shape[1] != 1:
-            raise LibraryError(-20003, "general_stat with a Python summary function is "
-                               "accelerated for one sample set (state_dim == 1) only")
+        if W.shape[1] != 1 or not np.all((W == 0) | (W == 1)):
+            return self._general_stat_callback(W, summary_func, output_dim, w, options)
         samples = self.tables.samples
         members = samples[W[:, 0] == 1].astype(np.int32)
         sizes = np.array([len(members)], dtype=np.uint64)
@@ -332,6 +327,36 @@ class LLTreeSequence:
         _handle(_lib.lib().tskb_treeseq_sample_count_stat_tabulated(
             self._for_mode(options)._h, 1, _p(sizes), _p(members), output_dim, n + 1, _p(table), len(w) - 1,
             _p(w), options, _p(result)))
+        return result
+
+    def _general_stat_callback(self, W, summary_func, output_dim, w, options):
+        """Several state columns or arbitrary weights: ``tskb_treeseq_general_stat`` with the Python
+        callable behind a C callback (``general_stat_func``, ``_tskitmodule.c:6532-6586``).  The engine
+        calls it once per distinct state vector, on the host."""
+        if options & STAT_NODE:
+            raise LibraryError(-20003, "node-mode general_stat with a Python summary function is not accelerated")
+        if W.shape[1] > 8:
+            raise LibraryError(-20003, "general_stat is accelerated for at most 8 state columns")
+        K, M = W.shape[1], int(output_dim)
+        failure = []
+
+        def trampoline(k, state, m, out, params):
+            try:
+                y = np.asarray(summary_func(np.ctypeslib.as_array(state, shape=(k,)).copy()), dtype=np.float64)
+                if y.shape != (m,):
+                    raise ValueError("summary_func returned array of wrong dimension")
+                np.ctypeslib.as_array(out, shape=(m,))[:] = y
+                return 0
+            except BaseException as e:  # handed back after the call, as _tskitmodule.c:6528, 6731 does
+                failure.append(e)
+                return -100000
+        cb = _lib.GENERAL_STAT_FUNC(trampoline)
+        result = np.zeros((len(w) - 1, M))
+        ret = _lib.lib().tskb_treeseq_general_stat(self._h, K, _p(W), M, cb, None, len(w) - 1, _p(w), options,
+                                                   _p(result))
+        if failure:
+            raise failure[0]
+        _handle(ret)
         return result
 
     # ---- TreeSequence_allele_frequency_spectrum (_tskitmodule.c:6977-7063)

@@ -110,27 +110,30 @@ def restrict_tables(tables, a, b):
 _SPANS = {}
 
 
-def _spans(windows, like):
-    """Window spans as a tensor on ``like``'s device, broadcastable against it (cached: the same
-    windows are used call after call)."""
+def _spans(windows, like, window_axis=0):
+    """Window spans as a tensor on ``like``'s device, broadcastable against it along ``window_axis``
+    (cached: the same windows are used call after call)."""
     import torch
     w = np.ascontiguousarray(windows, dtype=np.float64)
-    key = (hash(w.tobytes()), str(like.device), like.dim())
+    key = (hash(w.tobytes()), str(like.device), like.dim(), window_axis)
     t = _SPANS.get(key)
     if t is None:
         if len(_SPANS) > 16:
             _SPANS.clear()
-        t = torch.from_numpy((w[1:] - w[:-1]).reshape((-1,) + (1,) * (like.dim() - 1))).to(like.device)
+        shape = [1] * like.dim()
+        shape[window_axis] = len(w) - 1
+        t = torch.from_numpy((w[1:] - w[:-1]).reshape(shape)).to(like.device)
         _SPANS[key] = t
     return t
 
 
-def combine(local, windows, span_normalise, group=None, device=None):
+def combine(local, windows, span_normalise, group=None, device=None, window_axis=0):
     """Sum the ranks' un-normalised ``(W, M)`` (relatedness vector: ``(W, nodes, K)``) partial results
     and span-normalise.  ``local`` is this rank's result computed with ``span_normalise=False`` over
     its own genome range: a numpy array (moved to ``device`` for NCCL, returned as numpy) or a
     tensor already resident on the device (summed and normalised in place, returned as is: no host
-    round trip)."""
+    round trip; several statistics stacked along another axis go through in ONE all_reduce, with
+    ``window_axis`` naming the axis of the windows)."""
     import torch
     import torch.distributed as dist
     on_device = isinstance(local, torch.Tensor)
@@ -140,7 +143,7 @@ def combine(local, windows, span_normalise, group=None, device=None):
             total = total.to(device)
         dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     if span_normalise:
-        total /= _spans(windows, total)
+        total /= _spans(windows, total, window_axis)
     if on_device:
         return total
     return total.cpu().numpy().copy()
