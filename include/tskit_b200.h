@@ -254,6 +254,12 @@ int tskb_treeseq_divergence_matrix(const tskb_treeseq_t *self, uint64_t num_samp
  * (samples == NULL: all samples, in tsk_treeseq_get_samples order). */
 int tskb_treeseq_genotype_matrix(const tskb_treeseq_t *self, const int32_t *samples,
     uint64_t num_samples, uint32_t options, int8_t *genotypes);
+/* The same decode for the sites [first_site, first_site + num_sites): what a loop of
+ * tsk_variant_decode(&var, site_id, 0) over that interval fills (genotypes.c:473-594; the Variant
+ * iterator of python/tskit/trees.py:5444-5560 decodes site after site).  int8 [num_sites x
+ * num_samples]; TSK_ERR_SITE_OUT_OF_BOUNDS (-205) for an interval outside the site table. */
+int tskb_treeseq_decode_sites(const tskb_treeseq_t *self, uint64_t first_site, uint64_t num_sites,
+    const int32_t *samples, uint64_t num_samples, uint32_t options, int8_t *genotypes);
 
 /* Integer parity outputs: parent array and per-node tracked-sample counts of
  * the tree covering each position (tsk_tree_seek + tsk_tree_t.parent /

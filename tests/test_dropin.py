@@ -479,3 +479,45 @@ def test_pca_iterates_on_the_engine(ts):
         for a, b in zip(f, g):
             sign = np.sign(np.sum(a * b, axis=0))
             assert np.allclose(a * sign, b, atol=1e-6), kw
+
+
+@pytest.mark.gpu
+def test_variants_and_haplotypes_on_the_device_decode(ts):
+    """TreeSequence.variants / haplotypes (trees.py:5288-5560) through the device decode: real
+    tskit.Variant objects, the reference's genotypes, alleles and missing-data conventions."""
+    from tests import fixtures as fx
+    acc = dropin.accelerate(ts)
+    s = ts.samples()
+    L = ts.sequence_length
+    cases = [dict(), dict(samples=s[::3]), dict(isolated_as_missing=False), dict(left=0.2 * L, right=0.7 * L),
+             dict(samples=s[[5, 2, 9]], copy=False)]
+    for kw in cases:
+        got = [(v.site.id, v.alleles, v.genotypes.copy(), v.has_missing_data, v.num_alleles) for v in acc.variants(**kw)]
+        want = [(v.site.id, v.alleles, v.genotypes.copy(), v.has_missing_data, v.num_alleles) for v in ts.variants(**kw)]
+        assert len(got) == len(want) and len(got) > 0
+        for a, b in zip(got, want):
+            assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2]) and a[3:] == b[3:], (kw, a[0])
+    assert acc.accel_stats["forwarded"] == 0 and acc.accel_stats["accelerated"] > 0
+    v = next(acc.variants())
+    assert isinstance(v, tskit.Variant) and v.genotypes.dtype == np.int32
+    assert v.counts() == next(ts.variants()).counts() and v.states().tolist() == next(ts.variants()).states().tolist()
+    with pytest.raises(Exception):
+        v.decode(0)  # a copy cannot be decoded again, as in the reference
+    assert list(acc.haplotypes()) == list(ts.haplotypes())
+    assert list(acc.haplotypes(samples=s[:7], left=0.1 * L, right=0.5 * L)) == \
+        list(ts.haplotypes(samples=s[:7], left=0.1 * L, right=0.5 * L))
+    # a user-supplied allele coding goes to the reference, visibly
+    a = [v.genotypes.copy() for v in acc.variants(alleles=("0", "1"))]
+    b = [v.genotypes.copy() for v in ts.variants(alleles=("0", "1"))]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and acc.accel_stats["forwarded"] == 1
+    # reference fixtures: stacked / back mutations, several alleles, isolated samples (missing data)
+    for name in ("single_tree", "paper", "missing", "multiroot", "internal_sample"):
+        t = fx.load(name)
+        if t.num_sites == 0:
+            continue
+        rts = dropin.from_tables(t)
+        racc = dropin.accelerate(rts)
+        for iso in (True, False):
+            got = [(v.site.id, v.alleles, v.genotypes.tolist()) for v in racc.variants(isolated_as_missing=iso)]
+            want = [(v.site.id, v.alleles, v.genotypes.tolist()) for v in rts.variants(isolated_as_missing=iso)]
+            assert got == want, (name, iso)

@@ -69,7 +69,7 @@ SYMBOLS = [
     "tskb_treeseq_trait_covariance", "tskb_treeseq_trait_correlation",
     "tskb_treeseq_genetic_relatedness_weighted", "tskb_treeseq_genetic_relatedness_vector", "tskb_treeseq_trait_linear_model",
     "tskb_treeseq_allele_frequency_spectrum",
-    "tskb_treeseq_divergence_matrix", "tskb_treeseq_genotype_matrix",
+    "tskb_treeseq_divergence_matrix", "tskb_treeseq_genotype_matrix", "tskb_treeseq_decode_sites",
     "tskb_treeseq_general_stat",
     "tskb_treeseq_trees_at", "tskb_treeseq_get_stats", "tskb_treeseq_stat_device",
     "tskb_treeseq_debug_array",
@@ -117,6 +117,7 @@ def lib():
             C.c_void_p, u64, C.c_void_p, u64, C.c_void_p, u64, C.c_void_p, C.c_void_p, C.c_uint32]
         L.tskb_treeseq_genotype_matrix.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_uint32,
                                                    C.c_void_p]
+        L.tskb_treeseq_decode_sites.argtypes = [C.c_void_p, u64, u64, C.c_void_p, u64, C.c_uint32, C.c_void_p]
         L.tskb_treeseq_trees_at.argtypes = [C.c_void_p, u64, C.c_void_p, C.c_void_p, u64,
                                             C.c_void_p, C.c_void_p]
         L.tskb_treeseq_get_stats.argtypes = [C.c_void_p, C.c_void_p]

@@ -942,7 +942,16 @@ int tskb_treeseq_genotype_matrix(const tskb_treeseq_t *self, const int32_t *samp
     uint64_t num_samples, uint32_t options, int8_t *genotypes) {
     if (self == nullptr || self->plan == nullptr || genotypes == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
     return guarded([&]() -> int {
-        return run_genotype_matrix(self->plan, samples, num_samples, options, genotypes);
+        return run_genotype_matrix(self->plan, samples, num_samples, options, genotypes, 0, self->plan->S);
+    });
+}
+
+int tskb_treeseq_decode_sites(const tskb_treeseq_t *self, uint64_t first_site, uint64_t num_sites,
+    const int32_t *samples, uint64_t num_samples, uint32_t options, int8_t *genotypes) {
+    if (self == nullptr || self->plan == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    if (num_sites > 0 && genotypes == nullptr) return TSKB_ERR_BAD_PARAM_VALUE;
+    return guarded([&]() -> int {
+        return run_genotype_matrix(self->plan, samples, num_samples, options, genotypes, first_site, num_sites);
     });
 }
 

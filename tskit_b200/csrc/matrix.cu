@@ -849,12 +849,13 @@ int run_branch_divergence_matrix(const Plan &P, uint64_t nsets, const uint64_t *
 }  // namespace
 
 int run_genotype_matrix(const Plan *plan, const int32_t *samples, uint64_t num_samples,
-    uint32_t options, int8_t *genotypes) {
+    uint32_t options, int8_t *genotypes, uint64_t first_site, uint64_t num_sites) {
     std::lock_guard<std::mutex> lock(plan->mu);
     const Plan &P = *plan;
     TSKB_CK(cudaSetDevice(P.device));
     cudaStream_t s = P.stream;
-    const uint32_t S = (uint32_t) P.S;
+    if (first_site > P.S || num_sites > P.S - first_site) return -205;  // TSK_ERR_SITE_OUT_OF_BOUNDS
+    const uint32_t S0 = (uint32_t) first_site, S = (uint32_t) num_sites;
     DevArray<int32_t> d_s;
     const int32_t *ds = P.d_samples.p;
     uint32_t n = P.num_samples;
@@ -870,7 +871,7 @@ int run_genotype_matrix(const Plan *plan, const int32_t *samples, uint64_t num_s
     DevArray<int8_t> G;
     G.alloc((size_t) S * n);
     TSKB_CK(cudaMemsetAsync(G.p, 0, (size_t) S * n, s));
-    decode_sites(P, ds, n, 0, S, options, G.p, n, 1);
+    decode_sites(P, ds, n, S0, S0 + S, options, G.p, n, 1);
     TSKB_CK(cudaMemcpyAsync(genotypes, G.p, (size_t) S * n, cudaMemcpyDeviceToHost, s));
     TSKB_CK(cudaStreamSynchronize(s));
     return 0;

@@ -746,6 +746,8 @@ void staged_upload(int device, const std::vector<UploadJob> &jobs, cudaStream_t 
         }
         return;
     }
+    static std::mutex pool_mu;  // the pinned buffers are shared by every plan of the process
+    std::lock_guard<std::mutex> pool_lock(pool_mu);
     std::atomic<size_t> next{ 0 };
     std::atomic<int> failed{ 0 };
     auto worker = [&](int t) {

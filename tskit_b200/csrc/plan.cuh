@@ -230,7 +230,7 @@ int run_trees_at(const Plan *plan, uint64_t nq, const double *positions, const i
 
 // matrix.cu
 int run_genotype_matrix(const Plan *plan, const int32_t *samples, uint64_t num_samples,
-    uint32_t options, int8_t *genotypes);
+    uint32_t options, int8_t *genotypes, uint64_t first_site, uint64_t num_sites);
 int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *sizes, const int32_t *sets,
     uint64_t num_windows, const double *windows, uint32_t options, double *result);
 

@@ -187,6 +187,108 @@ if tskit is not None:
     _genotype_matrix.__name__ = "genotype_matrix"
     AccelTreeSequence.genotype_matrix = _genotype_matrix
 
+    class _DeviceLLVariant:
+        """Stands in for ``_tskit.Variant`` inside a ``tskit.Variant`` (``genotypes.py:118-127`` is the
+        only place that constructs one): ``decode(site_id)`` serves the genotypes from blocks of sites
+        decoded on the device (``tskb_treeseq_decode_sites``), the alleles from the tables in the
+        reference's order -- ancestral state first, derived states in order of first appearance among
+        the site's mutations, ``None`` appended when a requested node is missing
+        (``genotypes.c:533-594``)."""
+
+        BLOCK_BYTES = 256 << 20
+
+        def __init__(self, acc, samples, isolated_as_missing):
+            self._acc = acc
+            self._engine = acc._accel_engine
+            t = acc._accel_engine.tables
+            self.samples = t.samples.copy() if samples is None else np.array(samples, dtype=np.int32)
+            self._samples_arg = None if samples is None else self.samples
+            self.isolated_as_missing = bool(isolated_as_missing)
+            self.site_id = tskit.NULL
+            self.genotypes = np.zeros(len(self.samples), dtype=np.int32)
+            self.alleles = ()
+            self._lo = self._hi = 0
+            self._block = None
+            n = max(1, len(self.samples))
+            self._block_sites = max(1, min(t.num_sites, self.BLOCK_BYTES // n))
+            # mutation rows of every site (mutation_site is sorted)
+            self._moff = np.searchsorted(t.mutations_site, np.arange(t.num_sites + 1))
+
+        def _allele_strings(self, site_id):
+            t = self._engine.tables
+            a, ao = t.sites_ancestral_state, t.sites_ancestral_state_offset
+            d, do = t.mutations_derived_state, t.mutations_derived_state_offset
+            out = [a[int(ao[site_id]):int(ao[site_id + 1])].tobytes().decode()]
+            for m in range(self._moff[site_id], self._moff[site_id + 1]):
+                x = d[int(do[m]):int(do[m + 1])].tobytes().decode()
+                if x not in out:
+                    out.append(x)
+            return out
+
+        def decode(self, site_id):
+            t = self._engine.tables
+            site_id = int(site_id)
+            if site_id < 0 or site_id >= t.num_sites:
+                raise _tskit.LibraryError("Site out of bounds. (TSK_ERR_SITE_OUT_OF_BOUNDS)")
+            if self._block is None or not (self._lo <= site_id < self._hi):
+                self._lo = site_id
+                self._hi = min(t.num_sites, site_id + self._block_sites)
+                self._block = self._engine.decode_sites(self._lo, self._hi - self._lo, samples=self._samples_arg,
+                                                        isolated_as_missing=self.isolated_as_missing)
+                self._acc.accel_stats["accelerated"] += 1
+            self.genotypes = self._block[site_id - self._lo].astype(np.int32)
+            alleles = self._allele_strings(site_id)
+            if (self.genotypes == tskit.MISSING_DATA).any():
+                alleles.append(None)
+            self.alleles = tuple(alleles)
+            self.site_id = site_id
+
+        def restricted_copy(self):
+            c = _DeviceLLVariant.__new__(_DeviceLLVariant)
+            c.__dict__.update(self.__dict__)
+            c.genotypes = self.genotypes.copy()
+            c._block = None  # a copy keeps its site; decoding it again is an error in the reference too
+            c.decode = c._no_decode
+            return c
+
+        def _no_decode(self, site_id):
+            raise _tskit.LibraryError("Can't decode a copy of a variant. (TSK_ERR_VARIANT_CANT_DECODE_COPY)")
+
+    def _variants(self, *, samples=None, isolated_as_missing=None, alleles=None, impute_missing_data=None,
+                  copy=None, left=None, right=None):
+        """``TreeSequence.variants`` (``trees.py:5444-5560``) over the device decode: the iterator yields
+        real ``tskit.Variant`` objects whose low-level half is ``_DeviceLLVariant``; ``haplotypes`` and
+        ``alignments`` iterate this method and so run on the device decode too.  A user-supplied
+        ``alleles`` coding, the deprecated ``impute_missing_data`` and requested nodes that are not
+        samples go to the reference."""
+        engine = self._accel_engine
+        forward = (alleles is not None or impute_missing_data is not None
+                   or not isinstance(engine, lowlevel.LLTreeSequence))
+        if samples is not None and not forward:
+            sm = np.asarray(samples, dtype=np.int64)
+            ok = sm.ndim == 1 and ((sm >= 0) & (sm < self.num_nodes)).all()
+            forward = not ok or not ((self.nodes_flags[sm] & 1) != 0).all()
+        if forward:
+            self.accel_stats["forwarded"] += 1
+            yield from tskit.TreeSequence.variants(
+                self, samples=samples, isolated_as_missing=isolated_as_missing, alleles=alleles,
+                impute_missing_data=impute_missing_data, copy=copy, left=left, right=right)
+            return
+        interval = self._check_genomic_range(left, right)
+        if isolated_as_missing is None:
+            isolated_as_missing = True
+        if copy is None:
+            copy = True
+        variant = tskit.Variant.__new__(tskit.Variant)
+        variant.tree_sequence = self
+        variant._ll_variant = _DeviceLLVariant(self, samples, isolated_as_missing)
+        start, stop = np.searchsorted(self.sites_position, interval)
+        for site_id in range(int(start), int(stop)):
+            variant.decode(site_id)
+            yield variant.copy() if copy else variant
+    _variants.__name__ = "variants"
+    AccelTreeSequence.variants = _variants
+
     def _unpickle(base):
         fn, args = base[0], base[1]
         return accelerate(fn(*args))

@@ -8,6 +8,7 @@ the drop-in proxy (``tskit_b200.dropin``) puts in place of
 ``ts._ll_tree_sequence`` while a statistic runs.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -91,6 +92,7 @@ class LLTreeSequence:
         # (TSKB_INIT_NODE_MODE); it is staged on first use, next to the faster default plan
         self.node_mode = bool(node_mode)
         self._node_engine = None
+        self._node_lock = threading.Lock()  # one node-mode engine, however many threads ask first
         lo, hi = (0.0, tables.sequence_length) if genome_range is None else genome_range
         self.genome_range = (float(lo), float(hi))
         t = _lib.Tables()
@@ -126,9 +128,10 @@ class LLTreeSequence:
     def _for_mode(self, options):
         """The engine a call with these option bits runs on."""
         if (options & STAT_NODE) and not self.node_mode:
-            if self._node_engine is None:
-                self._node_engine = LLTreeSequence(self.tables, device=self.device,
-                                                   genome_range=self.genome_range, node_mode=True)
+            with self._node_lock:
+                if self._node_engine is None:
+                    self._node_engine = LLTreeSequence(self.tables, device=self.device,
+                                                       genome_range=self.genome_range, node_mode=True)
             return self._node_engine
         return self
 
@@ -525,6 +528,16 @@ class LLTreeSequence:
         """Phase times of the last site-mode divergence_matrix call (CUDA events)."""
         k = self.engine_stats()["last_kernel_ms"]
         return {"decode": k[0], "gemm": k[1], "finish": k[2], "alleles": int(k[7])}
+
+    def decode_sites(self, first_site, num_sites, samples=None, isolated_as_missing=True):
+        """int8 genotypes ``[num_sites, n]`` of the sites ``[first_site, first_site + num_sites)``."""
+        n = self.tables.num_samples if samples is None else len(samples)
+        s = None if samples is None else np.ascontiguousarray(samples, dtype=np.int32)
+        out = np.empty((int(num_sites), n), dtype=np.int8)
+        _handle(_lib.lib().tskb_treeseq_decode_sites(
+            self._h, int(first_site), int(num_sites), _p(s), 0 if s is None else n,
+            0 if isolated_as_missing else ISOLATED_NOT_MISSING, _p(out)))
+        return out
 
     def genotype_matrix(self, samples=None, isolated_as_missing=True):
         n = self.tables.num_samples if samples is None else len(samples)
