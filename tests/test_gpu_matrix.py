@@ -245,3 +245,43 @@ def test_matrices_shard_by_genome_range(wf_small):
     got = sh.divergence_matrix(windows, sample_sets=flat, sample_set_sizes=sizes, mode="site")
     assert np.allclose(got, o.divergence_matrix(sets, windows=windows, mode="site"), rtol=1e-12, atol=0)
     assert np.array_equal(sh.genotype_matrix(), o.genotype_matrix())
+
+
+@pytest.mark.skipif(not __import__("oracle.ref", fromlist=["ref"]).available(), reason="oracle/_ref not built")
+def test_divmat_8192_samples_against_the_compiled_reference(monkeypatch):
+    """The tensor-core contraction at a size that crosses the super-block tile order (32 tile rows of
+    256, super-blocks of 12) and runs several waves of CTAs: 8192 samples, biallelic (G G^T through TMA;
+    the cp.async kernel as cross-check) and with three alleles per site (one-hot tcgen05 path), exact
+    against tsk_treeseq_divergence_matrix (trees.c:8684-8826) compiled from the reference sources."""
+    from oracle import ref
+    from tskit_b200.lowlevel import LLTreeSequence
+    from tskit_b200.sim import add_mutations, wright_fisher
+    from tskit_b200.tables import Tables
+    t = add_mutations(wright_fisher(8192, 60, 1e5, ncross=1, seed=5), 300, seed=2).ensure_derived()
+    s = t.samples
+    w = np.array([0.0, 0.4 * t.sequence_length, t.sequence_length])
+    want = ref.RefTreeSequence(t).divergence_matrix([[u] for u in s], windows=w, mode="site", span_normalise=False)
+    ll = LLTreeSequence(t)
+    got = ll.divergence_matrix(w, mode="site", span_normalise=False)
+    assert np.array_equal(got, want)
+    monkeypatch.setenv("TSKB_MATRIX", "cpasync")
+    assert np.array_equal(ll.divergence_matrix(w, mode="site", span_normalise=False), want)
+    monkeypatch.delenv("TSKB_MATRIX")
+    # sample sets of unequal sizes over the same contraction
+    sets = [s[:3000], s[3000:3001], s[4000:8192]]
+    sizes = np.array([len(x) for x in sets], dtype=np.uint64)
+    got = ll.divergence_matrix(w, sample_sets=np.concatenate(sets).astype(np.int32), sample_set_sizes=sizes, mode="site")
+    assert np.allclose(got, ref.RefTreeSequence(t).divergence_matrix(sets, windows=w, mode="site"), rtol=1e-12, atol=0)
+    ll.close()
+    # three alleles: neighbouring sites merged in pairs, the second mutation of a pair derives "2"
+    S = t.num_sites // 2 * 2
+    t3 = Tables(t.sequence_length, t.nodes_flags, t.nodes_time, t.edges_left, t.edges_right, t.edges_parent,
+                t.edges_child, sites_position=t.sites_position[:S:2],
+                mutations_site=(np.arange(S) // 2).astype(np.int32), mutations_node=t.mutations_node[:S],
+                mutations_derived_state=np.where(np.arange(S) % 2 == 0, ord("1"), ord("2")).astype(np.int8),
+                mutations_derived_state_offset=np.arange(S + 1, dtype=np.uint64),
+                edge_insertion_order=t.edge_insertion_order, edge_removal_order=t.edge_removal_order).ensure_derived()
+    want3 = ref.RefTreeSequence(t3).divergence_matrix([[u] for u in s], windows=w, mode="site", span_normalise=False)
+    ll3 = LLTreeSequence(t3)
+    assert np.array_equal(ll3.divergence_matrix(w, mode="site", span_normalise=False), want3)
+    ll3.close()

@@ -14,6 +14,7 @@
 // genotypes sample-major, "same allele" counts are  sum over alleles a of (G == a)(G == a)^T, an
 // int8 x int8 -> int32 product (exact), and different = sites - same.  Set aggregation,
 // count-normalisation and span-normalisation follow in fp64.
+#include <cuda.h>
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -574,6 +575,185 @@ __global__ void __launch_bounds__(THREADS, 1) k_gram_umma(const int8_t *__restri
 
 }  // namespace gram
 
+// ---- G G^T through TMA: operand delivery by the bulk-tensor copy engine, warp-specialised
+// One CTA per 256 x 256 block of C as above (four 128 x 128 accumulators = all 512 TMEM columns).
+// Warp 0 (one lane) is the PRODUCER: per 128-byte K chunk it arms the stage's "full" barrier with the
+// byte count and issues four cp.async.bulk.tensor.2d loads (A0 A1 B0 B1, 128 rows x 128 bytes each,
+// SWIZZLE_128B: the canonical K-major UMMA layout, rows past n filled with zeros by the copy engine).
+// Warp 1 (one lane) is the MMA ISSUER: waits for "full", issues 16 tcgen05.mma (kind::i8, M 128, N 128,
+// K 32) and tcgen05.commit's to the stage's "empty" barrier, which the producer waits on before it
+// refills.  No __syncthreads and no thread-issued copies in the main loop.  Diagonal blocks load and
+// multiply like the others (their lower half is simply not stored), so that all resident CTAs walk K
+// in step and a chunk fetched by one is still in L2 for the others.
+namespace gram_tma {
+
+constexpr uint32_t CT = 256, SUB_BYTES = 128 * 128, STAGE_BYTES = 4 * SUB_BYTES, NSTAGE = 3;
+constexpr uint32_t SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024;
+constexpr uint32_t TMEM_ALL = 512;
+constexpr uint32_t SPIN_MAX = 1u << 28;  // a lost copy must not hang the GPU: trap instead
+
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > SPIN_MAX) asm volatile("trap;");
+    }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): 8-row x 128-byte atoms, 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t) ((smem_addr >> 4) & 0x3fffu);
+    d |= (uint64_t) 1 << 16;                      // leading byte offset: unused for swizzled K-major
+    d |= (uint64_t) ((1024u >> 4) & 0x3fffu) << 32;  // stride byte offset between 8-row groups
+    d |= (uint64_t) 1 << 46;                      // descriptor version
+    d |= (uint64_t) 2 << 61;                      // SWIZZLE_128B
+    return d;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_gram_tma(const __grid_constant__ CUtensorMap tmap, uint32_t n,
+    uint32_t k_lo, uint32_t k_hi, const ushort2 *__restrict__ tile_list, int32_t *__restrict__ C) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t s_full[NSTAGE], s_empty[NSTAGE], s_done;
+    __shared__ uint32_t s_tmem;
+    const uint32_t bi = tile_list[blockIdx.x].x, bj = tile_list[blockIdx.x].y;
+    const bool diag = bi == bj;
+    const uint32_t i0 = bi * CT, j0 = bj * CT;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tiles = smem_u32(smem_raw) + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    if (tid == 0) {
+        for (uint32_t st = 0; st < NSTAGE; st++) {
+            mbar_init(&s_full[st], 1);
+            mbar_init(&s_empty[st], 1);
+        }
+        mbar_init(&s_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&s_tmem)), "r"(TMEM_ALL) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = s_tmem;
+    const uint32_t nch = (k_hi - k_lo) / 128;  // whole 128-byte chunks by contract
+
+    if (warp == 0 && lane == 0) {
+        // ---- producer
+        for (uint32_t ch = 0; ch < nch; ch++) {
+            const uint32_t st = ch % NSTAGE, round = ch / NSTAGE;
+            if (round > 0) mbar_wait_bounded(&s_empty[st], (round - 1) & 1);
+            mbar_expect_tx(&s_full[st], STAGE_BYTES);
+            const uint32_t stage = tiles + st * STAGE_BYTES;
+            const int32_t k0 = (int32_t) (k_lo + ch * 128);
+            tma_load_2d(stage + 0 * SUB_BYTES, &tmap, &s_full[st], k0, (int32_t) i0);
+            tma_load_2d(stage + 1 * SUB_BYTES, &tmap, &s_full[st], k0, (int32_t) (i0 + 128));
+            tma_load_2d(stage + 2 * SUB_BYTES, &tmap, &s_full[st], k0, (int32_t) j0);
+            tma_load_2d(stage + 3 * SUB_BYTES, &tmap, &s_full[st], k0, (int32_t) (j0 + 128));
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer
+        for (uint32_t ch = 0; ch < nch; ch++) {
+            const uint32_t st = ch % NSTAGE, round = ch / NSTAGE;
+            mbar_wait_bounded(&s_full[st], round & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t stage = tiles + st * STAGE_BYTES;
+#pragma unroll
+            for (uint32_t ks = 0; ks < 4; ks++) {  // 32 bytes of K per instruction, inside the 128-byte swizzle row
+#pragma unroll
+                for (uint32_t a = 0; a < 2; a++) {
+#pragma unroll
+                    for (uint32_t b = 0; b < 2; b++) {
+                        umma_i8(tmem_acc + (a * 2 + b) * 128, umma_desc_sw128(stage + a * SUB_BYTES + ks * 32),
+                            umma_desc_sw128(stage + (2 + b) * SUB_BYTES + ks * 32), (ch > 0 || ks > 0) ? 1u : 0u);
+                    }
+                }
+            }
+            umma_commit(&s_empty[st]);  // arrives when these MMAs have read the stage
+        }
+        umma_commit(&s_done);           // ... and when every MMA of the block is complete
+    }
+    // ---- epilogue: all warps; warp w owns TMEM lanes 32 (w % 4) .. + 31 and columns 64 (w / 4) ... of every accumulator
+    __syncwarp();
+    if (nch > 0) mbar_wait_bounded(&s_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (uint32_t a = 0; a < 2; a++) {
+        for (uint32_t b = 0; b < 2; b++) {
+            if (diag && a > b) continue;  // lower half of a diagonal block: never read
+            const uint32_t row = i0 + a * 128 + 32 * (warp & 3) + lane;
+#pragma unroll
+            for (uint32_t half = 0; half < 2; half++) {
+                const uint32_t col0 = 64 * (warp >> 2) + 32 * half;
+                uint32_t v[32];
+                const uint32_t taddr = tmem_acc + ((32 * (warp & 3)) << 16) + (a * 2 + b) * 128 + col0;
+                if (nch > 0) {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; q++) v[q] = 0;
+                }
+                if (row < n) {
+#pragma unroll
+                    for (int q = 0; q < 32; q++) {
+                        const uint32_t col = j0 + b * 128 + col0 + q;
+                        if (col < n) C[(size_t) row * n + col] = (int32_t) v[q];
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(TMEM_ALL) : "memory");
+    }
+}
+
+// tensor map of X [n rows][ld bytes] for 128-row x 128-byte boxes, SWIZZLE_128B; the driver entry point
+// is looked up at run time (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline bool make_tensor_map(CUtensorMap *map, const int8_t *X, size_t ld, uint32_t n) {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess
+            || q != cudaDriverEntryPointSuccess || p == nullptr) {
+            cudaGetLastError();
+            return false;
+        }
+        fn = (EncodeTiledFn) p;
+    }
+    const cuuint64_t dims[2] = { (cuuint64_t) ld, (cuuint64_t) n };
+    const cuuint64_t strides[1] = { (cuuint64_t) ld };
+    const cuuint32_t box[2] = { 128, 128 }, elem[2] = { 1, 1 };
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *) X, dims, strides, box, elem,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace gram_tma
+
 }  // namespace tc
 
 // number of sites at which samples lo < hi differ, from the contraction's output
@@ -953,7 +1133,14 @@ int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *size
     const bool use_legacy = mode_env != nullptr && mode_env[0] == 'l';
     const bool biallelic = P.max_alleles_per_site <= 2 && !use_legacy
                            && !(mode_env != nullptr && mode_env[0] == 'o');
-    if (biallelic) {
+    // operand delivery: TMA (default) or thread-issued cp.async (TSKB_MATRIX=cpasync, the earlier kernel)
+    CUtensorMap tmap;
+    bool use_tma = biallelic && !(mode_env != nullptr && mode_env[0] == 'c');
+    if (use_tma) use_tma = tc::gram_tma::make_tensor_map(&tmap, X.p, ld, n);
+    if (biallelic && use_tma) {
+        TSKB_CK(cudaFuncSetAttribute(tc::gram_tma::k_gram_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) tc::gram_tma::SMEM_BYTES));
+    } else if (biallelic) {
         TSKB_CK(cudaFuncSetAttribute(tc::gram::k_gram_umma, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int) tc::gram::SMEM_BYTES));
     } else if (!use_legacy) {
@@ -979,7 +1166,11 @@ int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *size
         const uint32_t k_lo = col_lo[w], k_hi = col_lo[w + 1];  // padded: whole 128-byte chunks
         TSKB_CK(cudaMemsetAsync(same.p, 0, (size_t) n * n * sizeof(int32_t), s));
         if (k_hi > k_lo) {
-            if (biallelic) {
+            if (biallelic && use_tma) {
+                tc::gram_tma::k_gram_tma<<<(unsigned) h_tiles.size(), tc::THREADS, tc::gram_tma::SMEM_BYTES, s>>>(
+                    tmap, n, k_lo, k_hi, d_tiles.p, same.p);
+                TSKB_CK_LAUNCH();
+            } else if (biallelic) {
                 tc::gram::k_gram_umma<<<(unsigned) h_tiles.size(), tc::THREADS, tc::gram::SMEM_BYTES, s>>>(
                     X.p, ld, n, k_lo, k_hi, d_tiles.p, same.p);
                 TSKB_CK_LAUNCH();
