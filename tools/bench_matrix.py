@@ -13,7 +13,7 @@ ap.add_argument("--samples", type=int, default=20000)
 ap.add_argument("--sites", type=int, default=1000000)
 ap.add_argument("--generations", type=int, default=2000)
 ap.add_argument("--length", type=float, default=1e8)
-ap.add_argument("--path", default="", choices=["", "onehot", "legacy"])
+ap.add_argument("--path", default="", choices=["", "cpasync", "onehot", "legacy"])
 ap.add_argument("--reps", type=int, default=2)
 args = ap.parse_args()
 if args.path:
@@ -40,7 +40,9 @@ D = d[0]
 assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0) and np.array_equal(D, np.round(D))
 print(json.dumps({
     "workload": f"site divergence matrix, n={n}, sites={S}, edges={t.num_edges}",
-    "impl": {"": "tcgen05 kind::i8, biallelic G G^T, 256x256 tiles", "onehot": "tcgen05 kind::i8, one-hot per allele",
+    "impl": {"": "tcgen05 kind::i8, biallelic G G^T, 256x256 tiles, TMA operand delivery, warp-specialised",
+             "cpasync": "tcgen05 kind::i8, biallelic G G^T, 256x256 tiles, cp.async operand delivery",
+             "onehot": "tcgen05 kind::i8, one-hot per allele",
              "legacy": "mma.sync one-hot"}[args.path],
     "generate_s": round(gen_s, 1), "call_s": dt, "phase_ms": ph,
     "sample_sites_per_s_call": n * S / dt,

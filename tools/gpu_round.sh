@@ -51,6 +51,28 @@ for i in range(3):
     ll.close()
 EOF
 grep -E "^init|tskb init" $OUT/init_phases.txt | tail -24
+if [ "$MODE" == "matrix" ]; then
+# C4: 20 000 samples x 10^6 biallelic sites; TMA kernel vs the cp.async kernel, then the ncu capture
+timeout 900 python tools/bench_matrix.py > $OUT/bench_matrix_c4.json 2> $OUT/bench_matrix_c4.err; echo "matrix exit $?"; cat $OUT/bench_matrix_c4.json
+timeout 900 python tools/bench_matrix.py --path cpasync > $OUT/bench_matrix_c4_cpasync.json 2> $OUT/bench_matrix_c4_cpasync.err; cat $OUT/bench_matrix_c4_cpasync.json
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_gram -c 1 -o $OUT/prof_gram -f \
+    python tools/bench_matrix.py --samples 16000 --sites 500000 --reps 1 > $OUT/ncu_gram.log 2>&1; echo "ncu gram exit $?"
+ncu -i $OUT/prof_gram.ncu-rep --page raw --csv > $OUT/prof_gram_raw.csv 2>/dev/null
+python - $OUT/prof_gram_raw.csv <<'EOF2'
+import csv, sys
+rows = list(csv.reader(open(sys.argv[1])))
+if len(rows) > 2:
+    d = dict(zip(rows[0], rows[2]))
+    for k in ("Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active",
+              "sm__inst_executed_pipe_tensor.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct",
+              "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"):
+        print(k, d.get(k))
+    for k, v in d.items():
+        if "tensor" in k and "pct" in k:
+            print(k, v)
+EOF2
+rm -f $OUT/prof_gram.ncu-rep.tmp
+fi
 if [ "$MODE" == "c3" ]; then
 timeout 1500 python bench.py --config c3 --steps 3 --warmup 1 > $OUT/c3_n1.json 2> $OUT/c3_n1.err; echo "c3 N=1 exit $?"
 head -c 3000 $OUT/c3_n1.json; echo; tail -5 $OUT/c3_n1.err

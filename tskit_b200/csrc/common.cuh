@@ -29,7 +29,16 @@ std::string &last_error_string();
 
 #define TSKB_CK_LAUNCH() TSKB_CK(cudaGetLastError())
 
-// Owning device array (cudaMalloc/cudaFree); sized once at plan build.
+// While a plan is being built its many temporaries come from the device's stream-ordered memory pool
+// (cudaMallocAsync / cudaFreeAsync on the build stream): a freed block is handed to the next
+// allocation without a trip to the driver, and nothing synchronises the device.  Outside a build the
+// arrays fall back to cudaMalloc / cudaFree.
+inline cudaStream_t &alloc_stream() {
+    static thread_local cudaStream_t s = nullptr;
+    return s;
+}
+
+// Owning device array; sized once at plan build.
 template <typename T>
 struct DevArray {
     T *p = nullptr;
@@ -47,11 +56,22 @@ struct DevArray {
         release();
         n = count;
         if (count > 0) {
-            TSKB_CK(cudaMalloc(&p, count * sizeof(T)));
+            if (alloc_stream() != nullptr) {
+                TSKB_CK(cudaMallocAsync((void **) &p, count * sizeof(T), alloc_stream()));
+            } else {
+                TSKB_CK(cudaMalloc(&p, count * sizeof(T)));
+            }
         }
     }
     void release() {
-        if (p != nullptr) { cudaFree(p); p = nullptr; }
+        if (p != nullptr) {
+            if (alloc_stream() != nullptr) {
+                cudaFreeAsync(p, alloc_stream());
+            } else {
+                cudaFree(p);
+            }
+            p = nullptr;
+        }
         n = 0;
     }
     size_t bytes() const { return n * sizeof(T); }

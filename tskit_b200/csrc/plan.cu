@@ -667,16 +667,10 @@ struct U32ToU64 {
 // ------------------------------------------------------------ CUB wrappers
 
 struct Temp {
-    void *p = nullptr;
-    size_t cap = 0;
-    ~Temp() { if (p) cudaFree(p); }
+    DevArray<char> buf;  // pool-backed during a build (common.cuh: alloc_stream)
     void *need(size_t bytes) {
-        if (bytes > cap) {
-            if (p) cudaFree(p);
-            cap = bytes + (bytes >> 2) + 1024;
-            TSKB_CK(cudaMalloc(&p, cap));
-        }
-        return p;
+        if (bytes > buf.n) buf.alloc(bytes + (bytes >> 2) + 1024);
+        return buf.p;
     }
 };
 
@@ -748,6 +742,7 @@ void staged_upload(int device, const std::vector<UploadJob> &jobs, cudaStream_t 
     }
     static std::mutex pool_mu;  // the pinned buffers are shared by every plan of the process
     std::lock_guard<std::mutex> pool_lock(pool_mu);
+    TSKB_CK(cudaStreamSynchronize(fallback));  // the destinations were allocated in this stream's order
     std::atomic<size_t> next{ 0 };
     std::atomic<int> failed{ 0 };
     auto worker = [&](int t) {
@@ -832,6 +827,30 @@ Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double r
     TSKB_CK(cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking));
     for (auto &e : P.ev) TSKB_CK(cudaEventCreate(&e));
     cudaStream_t s = P.stream;
+    // temporaries of the build: stream-ordered pool, kept warm until the build is over
+    struct PoolScope {
+        cudaMemPool_t pool = nullptr;
+        cudaStream_t stream;
+        explicit PoolScope(int device, cudaStream_t st) : stream(st) {
+            if (getenv("TSKB_NO_POOL") == nullptr && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                alloc_stream() = st;
+            } else {
+                cudaGetLastError();
+                pool = nullptr;
+            }
+        }
+        ~PoolScope() {
+            alloc_stream() = nullptr;
+            if (pool != nullptr) {
+                cudaStreamSynchronize(stream);
+                unsigned long long keep = 0;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                cudaMemPoolTrimTo(pool, 0);  // what the plan does not hold goes back to the device
+            }
+        }
+    } pool_scope(device, s);
     P.N = t->num_nodes;
     P.E = t->num_edges;
     P.S = t->num_sites;
