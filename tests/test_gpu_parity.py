@@ -362,6 +362,40 @@ def test_custom_summary_function_tabulated(wf_small, engines):
     assert np.allclose(g[:, 0], d[:, 0], rtol=1e-12)
 
 
+def test_custom_summary_that_is_nan_only_at_the_roots(wf_small, engines):
+    """The reference's running sum takes 0 x f(state) from nodes without a branch above them as well
+    (trees.c:1339-1350): a summary that is NaN (or inf) only at the state of a root still turns the
+    windows NaN.  The default plan drops those pieces, so such calls run on the plan that keeps every
+    piece; results equal the oracle's restatement of the reference loop."""
+    ll, o = engines
+    s = wf_small.samples
+    n = len(s)
+    windows = np.linspace(0, wf_small.sequence_length, 5)
+
+    def f_nan(x):   # NaN where a node has every sample below it, as only roots do
+        return np.array([np.nan if x[0] == n else x[0] * (n - x[0])])
+
+    def f_inf(x):
+        return np.array([np.inf if x[0] == n else float(x[0])])
+
+    W1 = np.ones((n, 1))
+    for f in (f_nan, f_inf):
+        for pol in (True, False):
+            got = ll.general_stat(W1, f, 1, windows=windows, mode="branch", polarised=pol)
+            want = o.general_stat(W1, f, 1, windows=windows, mode="branch", polarised=pol)
+            assert close(got, want), (f.__name__, pol, got, want)
+    # two state columns: through the callback entry point
+    W2 = np.ones((n, 2))
+    W2[: n // 2, 1] = 0
+
+    def f2(x):
+        return np.array([np.nan if x[0] == n else x[0] + x[1]])
+
+    got = ll.general_stat(W2, f2, 1, windows=windows, mode="branch", polarised=True)
+    want = o.general_stat(W2, f2, 1, windows=windows, mode="branch", polarised=True)
+    assert close(got, want)
+
+
 def test_general_stat_with_a_callback(wf_small, engines):
     """tsk_treeseq_general_stat with a Python summary over several state columns and over float
     weights (trees.py:7917-8004): the engine sweeps, collects the distinct state vectors on the device and

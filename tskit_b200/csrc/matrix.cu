@@ -680,10 +680,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gram_tma(const __grid_constant__
             umma_commit(&s_empty[st]);  // arrives when these MMAs have read the stage
         }
         umma_commit(&s_done);           // ... and when every MMA of the block is complete
+        if (nch > 0) mbar_wait_bounded(&s_done, 0);
     }
-    // ---- epilogue: all warps; warp w owns TMEM lanes 32 (w % 4) .. + 31 and columns 64 (w / 4) ... of every accumulator
+    // ---- epilogue: all warps; warp w owns TMEM lanes 32 (w % 4) .. + 31 and columns 64 (w / 4) ... of every accumulator.
+    // The warps without a role sleep in the block barrier during the main loop (no polling); the MMA
+    // issuer arrives once the last commit has completed.
     __syncwarp();
-    if (nch > 0) mbar_wait_bounded(&s_done, 0);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (uint32_t a = 0; a < 2; a++) {
         for (uint32_t b = 0; b < 2; b++) {
@@ -1076,8 +1080,10 @@ int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *size
     TSKB_CK(cudaSetDevice(P.device));
     cudaStream_t s = P.stream;
     const uint32_t n = (uint32_t) total, W = (uint32_t) num_windows, ns = (uint32_t) nsets;
-    memset(result, 0, (size_t) W * ns * ns * sizeof(double));
-    if (n == 0) return 0;
+    if (n == 0) {  // (every window's matrix is otherwise written whole by the read-back below)
+        memset(result, 0, (size_t) W * ns * ns * sizeof(double));
+        return 0;
+    }
     // sites covered by the windows
     // (a plan staged for a genome range contracts the sites inside its range only: the per-range
     // partial matrices of a sharded call add up to the whole, exactly -- they are integer counts)

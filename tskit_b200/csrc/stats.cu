@@ -2126,6 +2126,10 @@ int run_impl(const Plan &P, const StatSpec &sp) {
         for (uint64_t i = 0; i < sp.table_rows * M; i++) {
             if (!std::isfinite(sp.f_table[i])) sumP.skip_zero_bl = 0;
         }
+        // A summary that is NaN / inf at some state: the reference's running sum takes 0 x f = NaN from a
+        // node WITHOUT a branch above it too (trees.c:1339-1350).  The default plan drops those pieces; the
+        // plan that keeps every piece (TSKB_INIT_NODE_MODE) reproduces it -- lowlevel.py retries there.
+        if (!sumP.skip_zero_bl && (sp.options & TSKB_STAT_BRANCH) && !P.all_pieces) return TSKB_ERR_UNSUPPORTED;
         sumP.table = d_tab;
         sumP.table_rows = (uint32_t) sp.table_rows;
     }
@@ -2443,6 +2447,7 @@ int run_general_impl(const Plan &P, const GeneralSpec &g) {
         }
         for (uint32_t m = 0; m < M; m++) finite &= std::isfinite(row[m]);
     }
+    if (!finite && branch && !P.all_pieces) return TSKB_ERR_UNSUPPORTED;  // see STAT_TABULATED in run_impl
     double *d_tab = A.get<double>(table.size());
     TSKB_CK(cudaMemcpyAsync(d_tab, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     c.d_result = A.get<double>((size_t) W * M);

@@ -327,9 +327,13 @@ class LLTreeSequence:
             result = np.zeros((len(w) - 1, self.tables.num_nodes, output_dim))
         else:
             result = np.zeros((len(w) - 1, output_dim))
-        _handle(_lib.lib().tskb_treeseq_sample_count_stat_tabulated(
-            self._for_mode(options)._h, 1, _p(sizes), _p(members), output_dim, n + 1, _p(table), len(w) - 1,
-            _p(w), options, _p(result)))
+        args = (1, _p(sizes), _p(members), output_dim, n + 1, _p(table), len(w) - 1, _p(w), options, _p(result))
+        ret = _lib.lib().tskb_treeseq_sample_count_stat_tabulated(self._for_mode(options)._h, *args)
+        if ret == -20003 and (options & STAT_BRANCH) and not np.isfinite(table).all():
+            # NaN / inf summary values reach the running sum through nodes without a branch above them
+            # too (0 x NaN): the engine that keeps every piece reproduces that
+            ret = _lib.lib().tskb_treeseq_sample_count_stat_tabulated(self._for_mode(STAT_NODE)._h, *args)
+        _handle(ret)
         return result
 
     def _general_stat_callback(self, W, summary_func, output_dim, w, options):
@@ -355,8 +359,11 @@ class LLTreeSequence:
                 return -100000
         cb = _lib.GENERAL_STAT_FUNC(trampoline)
         result = np.zeros((len(w) - 1, M))
-        ret = _lib.lib().tskb_treeseq_general_stat(self._h, K, _p(W), M, cb, None, len(w) - 1, _p(w), options,
-                                                   _p(result))
+        args = (K, _p(W), M, cb, None, len(w) - 1, _p(w), options, _p(result))
+        ret = _lib.lib().tskb_treeseq_general_stat(self._h, *args)
+        if ret == -20003 and (options & STAT_BRANCH) and not failure and not self.node_mode:
+            # a summary that is NaN / inf somewhere: the engine that keeps every piece (see above)
+            ret = _lib.lib().tskb_treeseq_general_stat(self._for_mode(STAT_NODE)._h, *args)
         if failure:
             raise failure[0]
         _handle(ret)
