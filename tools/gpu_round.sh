@@ -25,6 +25,7 @@ except Exception as e:
     print(sys.argv[2], "failed", e)
 EOF
 done
+if [ -x tools/mb/red_types ]; then timeout 120 tools/mb/red_types > $OUT/red_types.txt 2>&1; cat $OUT/red_types.txt; fi
 # the other config shapes (C1, C3 shape on the C2 ARG, C5), and the many-column path old vs new
 timeout 600 python tools/probe_configs.py > $OUT/probe_configs.json 2> $OUT/probe_configs.err; echo "probe exit $?"
 TSKB_COLS_VARIANT=old TSKB_SUM_VARIANT=lane timeout 600 python tools/probe_configs.py > $OUT/probe_configs_oldcols.json 2> $OUT/probe_configs_oldcols.err
