@@ -237,7 +237,9 @@ int tskb_treeseq_sample_count_stat_tabulated(const tskb_treeseq_t *self,
  * on the host ONCE PER DISTINCT state vector (branch mode: also at total - state unless
  * TSK_STAT_POLARISED; site mode: the allele states) instead of once per node update, and integrates
  * the tabulated values on the device.  Site and branch mode, state_dim <= 8; node mode and wider
- * states: TSKB_ERR_UNSUPPORTED. */
+ * states: TSKB_ERR_UNSUPPORTED.  Branch mode needs an engine built with TSKB_INIT_NODE_MODE (every
+ * piece kept: a summary that is NaN / inf at the state of a node without a branch above it reaches
+ * the running sum as 0 x NaN, trees.c:1339-1350); TSKB_ERR_UNSUPPORTED otherwise. */
 typedef int tskb_general_stat_func_t(uint64_t state_dim, const double *state, uint64_t result_dim,
     double *result, void *params);
 int tskb_treeseq_general_stat(const tskb_treeseq_t *self, uint64_t state_dim, const double *weights,

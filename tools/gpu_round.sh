@@ -12,7 +12,7 @@ tail -3 $OUT/pytest_gpu.log
 python bench.py --steps 20 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
 head -c 3000 $OUT/bench.json; echo
 # A/B of the branch-summary variants (same box, same plan; device-timed, no CPU legs)
-for v in "lane:" "bins:TSKB_SUM_VARIANT=bins"; do
+for v in "lane:" "hack_no_head_reds:TSKB_SUM_HACK=1"; do
     name=${v%%:*}; envs=${v#*:}
     if [ -n "$envs" ] && [[ "$envs" == TSKB_LIB=* ]] && [ ! -f "${envs#TSKB_LIB=}" ]; then continue; fi
     env $envs python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ab_$name.json 2> $OUT/ab_$name.err
@@ -52,6 +52,9 @@ for i in range(3):
     ll.close()
 EOF
 grep -E "^init|tskb init" $OUT/init_phases.txt | tail -24
+if [ "$MODE" == "matrixq" ]; then
+timeout 900 python tools/bench_matrix.py > $OUT/bench_matrix_c4.json 2> $OUT/bench_matrix_c4.err; echo "matrix exit $?"; cat $OUT/bench_matrix_c4.json
+fi
 if [ "$MODE" == "matrix" ]; then
 # C4: 20 000 samples x 10^6 biallelic sites; TMA kernel vs the cp.async kernel, then the ncu capture
 timeout 900 python tools/bench_matrix.py > $OUT/bench_matrix_c4.json 2> $OUT/bench_matrix_c4.err; echo "matrix exit $?"; cat $OUT/bench_matrix_c4.json

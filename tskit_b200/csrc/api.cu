@@ -893,6 +893,11 @@ int tskb_treeseq_general_stat(const tskb_treeseq_t *self, uint64_t state_dim, co
             return TSKB_ERR_TIME_UNCALIBRATED;
         }
         if (node || state_dim > MAX_STATE_DIM) return TSKB_ERR_UNSUPPORTED;
+        // Branch mode: the reference's running sum also takes 0 x f(state) from nodes without a branch
+        // above them (trees.c:1339-1350), which matters exactly when f is NaN / inf there -- and whether it
+        // is cannot be known without evaluating f at those states.  So the callback form runs on the
+        // plan that keeps every piece (TSKB_INIT_NODE_MODE).
+        if (branch && !P.all_pieces) return TSKB_ERR_UNSUPPORTED;
         GeneralSpec g = {};
         g.K = (uint32_t) state_dim; g.M = (uint32_t) result_dim; g.W = (uint32_t) num_windows;
         g.weights = weights; g.f = (general_stat_func) f; g.params = f_params;

@@ -1056,7 +1056,7 @@ int run_genotype_matrix(const Plan *plan, const int32_t *samples, uint64_t num_s
     G.alloc((size_t) S * n);
     TSKB_CK(cudaMemsetAsync(G.p, 0, (size_t) S * n, s));
     decode_sites(P, ds, n, S0, S0 + S, options, G.p, n, 1);
-    TSKB_CK(cudaMemcpyAsync(genotypes, G.p, (size_t) S * n, cudaMemcpyDeviceToHost, s));
+    staged_download(P.device, genotypes, G.p, (size_t) S * n, s);
     TSKB_CK(cudaStreamSynchronize(s));
     return 0;
 }
@@ -1206,8 +1206,7 @@ int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *size
                 biallelic ? 1 : 0, windows[w + 1] - windows[w], span, d_D.p);
         }
         TSKB_CK_LAUNCH();
-        TSKB_CK(cudaMemcpyAsync(result + (size_t) w * ns * ns, d_D.p, (size_t) ns * ns * sizeof(double),
-            cudaMemcpyDeviceToHost, s));
+        staged_download(P.device, result + (size_t) w * ns * ns, d_D.p, (size_t) ns * ns * sizeof(double), s);
         TSKB_CK(cudaEventRecord(P.ev[3], s));
         TSKB_CK(cudaStreamSynchronize(s));
         float ms = 0;

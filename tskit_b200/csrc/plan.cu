@@ -702,7 +702,8 @@ struct UploadJob {
 struct PinnedPool {
     static constexpr size_t CHUNK = size_t(4) << 20;
     static constexpr int MAX_THREADS = 8;
-    std::mutex mu;
+    std::mutex mu;      // guards buf
+    std::mutex use_mu;  // one transfer at a time uses the buffers
     char *buf[MAX_THREADS][2] = {};
     char *get(int t, int b) {
         std::lock_guard<std::mutex> lock(mu);
@@ -740,8 +741,7 @@ void staged_upload(int device, const std::vector<UploadJob> &jobs, cudaStream_t 
         }
         return;
     }
-    static std::mutex pool_mu;  // the pinned buffers are shared by every plan of the process
-    std::lock_guard<std::mutex> pool_lock(pool_mu);
+    std::lock_guard<std::mutex> pool_lock(pinned_pool().use_mu);  // the buffers are shared by every plan
     TSKB_CK(cudaStreamSynchronize(fallback));  // the destinations were allocated in this stream's order
     std::atomic<size_t> next{ 0 };
     std::atomic<int> failed{ 0 };
@@ -785,6 +785,55 @@ void staged_upload(int device, const std::vector<UploadJob> &jobs, cudaStream_t 
         }
     }
 }
+
+}  // namespace
+
+// Large results back to the caller's pageable buffer: the mirror image of staged_upload.  Each
+// thread copies 4 MB chunks device -> its pinned buffer -> destination, so the host-side copies
+// (and the page faults of a freshly allocated result array) run in parallel.
+void staged_download(int device, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+    TSKB_CK(cudaStreamSynchronize(stream));  // the producers of src ran on this stream
+    const size_t CH = PinnedPool::CHUNK;
+    const size_t nchunks = (bytes + CH - 1) / CH;
+    int nt = (int) std::min<size_t>({ (size_t) PinnedPool::MAX_THREADS, std::max<size_t>(1, std::thread::hardware_concurrency() / 2),
+        std::max<size_t>(1, nchunks / 4) });
+    if (getenv("TSKB_UPLOAD_THREADS") != nullptr) nt = std::max(1, std::min(atoi(getenv("TSKB_UPLOAD_THREADS")), (int) PinnedPool::MAX_THREADS));
+    if (bytes < (size_t(16) << 20) || nt <= 1) {
+        if (bytes) TSKB_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+        TSKB_CK(cudaStreamSynchronize(stream));
+        return;
+    }
+    std::lock_guard<std::mutex> pool_lock(pinned_pool().use_mu);
+    std::atomic<size_t> next{ 0 };
+    std::atomic<int> failed{ 0 };
+    auto worker = [&](int t) {
+        cudaStream_t st = nullptr;
+        char *b = pinned_pool().get(t, 0);
+        bool ok = cudaSetDevice(device) == cudaSuccess && b != nullptr
+                  && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+        while (ok) {
+            const size_t i = next.fetch_add(1);
+            if (i >= nchunks) break;
+            const size_t off = i * CH, n = std::min(CH, bytes - off);
+            ok = cudaMemcpyAsync(b, (const char *) src + off, n, cudaMemcpyDeviceToHost, st) == cudaSuccess
+                 && cudaStreamSynchronize(st) == cudaSuccess;
+            if (ok) memcpy((char *) dst + off, b, n);
+        }
+        if (!ok) failed.store(1);
+        if (st) cudaStreamDestroy(st);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(worker, t);
+    worker(0);
+    for (auto &x : th) x.join();
+    if (failed.load()) {
+        cudaGetLastError();
+        TSKB_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+        TSKB_CK(cudaStreamSynchronize(stream));
+    }
+}
+
+namespace {
 
 template <typename K, typename Vt>
 void sort_pairs(Temp &tmp, const K *kin, K *kout, const Vt *vin, Vt *vout, uint32_t n, int end_bit,

@@ -155,6 +155,10 @@ struct Plan {
 Plan *build_plan(const tskb_tables_t *t, int device, double range_left, double range_right,
     uint32_t options);
 
+// device -> pageable host memory through per-thread pinned staging buffers (large results); returns
+// when the copy is complete
+void staged_download(int device, void *dst, const void *src, size_t bytes, cudaStream_t stream);
+
 // stats.cu
 struct StatSpec {
     int stat_id;          // see StatId

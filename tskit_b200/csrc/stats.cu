@@ -74,6 +74,7 @@ struct SumP {
     const ColP *cols;       // device [M]
     const double *table;    // device [rows * M] (STAT_TABULATED)
     uint32_t table_rows;
+    int timing_hack;        // experiments (TSKB_SUM_HACK): 1 = leave out the run-head reductions (WRONG results)
 };
 
 // x[i] without dynamic register indexing, in the state's own type
@@ -302,7 +303,7 @@ __device__ __forceinline__ void pieces_to_deltas(const SumP &sp, const V &totals
             if (live[q]) G = bl[q] * F_branch<STAT, V>(sp, col, m, st[q], totals);
             const double G_next = __shfl_down_sync(0xffffffffu, G, 1);
             if (!valid[q]) continue;
-            if (!merged_prev[q] && G != 0.0) atomicAdd(Dm + bp0[q], G);
+            if (!merged_prev[q] && G != 0.0 && !sp.timing_hack) atomicAdd(Dm + bp0[q], G);
             const double v = merge_next[q] ? G_next - G : -G;
             if (v != 0.0) atomicAdd(Dm + bp1[q], v);
         }
@@ -2038,6 +2039,7 @@ int run_impl(const Plan &P, const StatSpec &sp) {
     sumP.M = (int) M;
     sumP.polarised = (sp.options & TSKB_STAT_POLARISED) ? 1 : 0;
     sumP.skip_zero_bl = 1;
+    sumP.timing_hack = getenv("TSKB_SUM_HACK") != nullptr ? atoi(getenv("TSKB_SUM_HACK")) : 0;
     V totals;
     for (int k = 0; k < V::N; k++) totals.v[k] = 0;
     for (uint32_t k = 0; k < K; k++) {

@@ -360,10 +360,10 @@ class LLTreeSequence:
         cb = _lib.GENERAL_STAT_FUNC(trampoline)
         result = np.zeros((len(w) - 1, M))
         args = (K, _p(W), M, cb, None, len(w) - 1, _p(w), options, _p(result))
-        ret = _lib.lib().tskb_treeseq_general_stat(self._h, *args)
-        if ret == -20003 and (options & STAT_BRANCH) and not failure and not self.node_mode:
-            # a summary that is NaN / inf somewhere: the engine that keeps every piece (see above)
-            ret = _lib.lib().tskb_treeseq_general_stat(self._for_mode(STAT_NODE)._h, *args)
+        # branch mode runs on the engine that keeps every piece: a summary that is NaN / inf at the state
+        # of a node without a branch above it must reach the running sum as 0 x NaN, as in the reference
+        engine = self._for_mode(STAT_NODE) if (options & STAT_BRANCH) else self
+        ret = _lib.lib().tskb_treeseq_general_stat(engine._h, *args)
         if failure:
             raise failure[0]
         _handle(ret)
