@@ -77,8 +77,9 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, interval_ms=50):
         self.index = index
+        self.interval_ms = interval_ms
         self.proc = None
         self.lines = []
 
@@ -86,7 +87,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "50", "-i", str(self.index)],
+                 "-lms", str(self.interval_ms), "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -319,6 +320,9 @@ def run_ours(args):
     phase_ms = np.zeros(6)
     launches = [0]
     coll_ev = []
+    # TSKB_BENCH_SYNC_COLL=1: the host waits for each step's collective before the next step's sweeps
+    # (no overlap: the NCCL kernel then never shares the SMs with the cooperative sweep)
+    sync_coll = os.environ.get("TSKB_BENCH_SYNC_COLL", "0") == "1"
 
     def step_device(collect=True):
         """One step with inputs and outputs in HBM; returns the engine's device time (CUDA events on
@@ -346,6 +350,8 @@ def run_ours(args):
             e1.record()
             coll_ev.append((e0, e1))
             pending[b] = e1
+            if sync_coll:
+                e1.synchronize()
         return ms
 
     # host buffers for the end-to-end number: the reference-facing C ABI at one GPU, the sharded host
@@ -822,7 +828,7 @@ def run_c3(args):
         step()
     collective_ms()
     phase.clear()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, interval_ms=250)  # steps last 0.03-0.3 s: a few samples per step
     if rank == 0:
         sampler.start()
     barrier()
@@ -846,12 +852,13 @@ def run_c3(args):
         times = torch.tensor([dev_ms, wall, coll_ms, stage_s, gen_s], dtype=torch.float64, device=dev)
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dev_ms, wall, coll_ms, stage_s, gen_s = [float(x) for x in times.cpu()]
-        mem = torch.tensor([st["device_bytes"], st["num_events"]], dtype=torch.float64, device=dev)
+        mem = torch.tensor([st["device_bytes"], st["num_events"], engine_ms / args.steps], dtype=torch.float64,
+                           device=dev)
         g = [torch.empty_like(mem) for _ in range(world)]
         dist.all_gather(g, mem)
-        per_rank = [[int(x[0].item()), int(x[1].item())] for x in g]
+        per_rank = [[int(x[0].item()), int(x[1].item()), round(float(x[2].item()), 3)] for x in g]
     else:
-        per_rank = [[st["device_bytes"], st["num_events"]]]
+        per_rank = [[st["device_bytes"], st["num_events"], round(engine_ms / args.steps, 3)]]
     if rank == 0:
         # parity on a subsample: the reference C library on the rows meeting the first windows
         parity = None
@@ -873,7 +880,7 @@ def run_c3(args):
                 "sharding": ("whole genome on one GPU" if world == 1 else
                              f"{world} genome ranges from sharding.plan_shards; per statistic one all_reduce "
                              f"of the device-resident partials inside the timed region"),
-                "per_rank_plan_bytes_and_edge_diffs": per_rank,
+                "per_rank_plan_bytes_edge_diffs_engine_ms": per_rank,
                 "ms_per_step_by_statistic": {k: v / args.steps for k, v in phase.items()},
                 "collective_ms_per_step": coll_ms / args.steps, "wall_ms_per_step": wall / args.steps * 1e3,
                 "engine_ms_per_step_rank0": engine_ms / args.steps,
