@@ -323,6 +323,12 @@ def run_ours(args):
     # TSKB_BENCH_SYNC_COLL=1: the host waits for each step's collective before the next step's sweeps
     # (no overlap: the NCCL kernel then never shares the SMs with the cooperative sweep)
     sync_coll = os.environ.get("TSKB_BENCH_SYNC_COLL", "0") == "1"
+    # The sum of the ranks' partials: pushed over NVLink peer memory by the engine's own kernels
+    # (sharding.PeerExchange, default) or, with TSKB_BENCH_NCCL=1, one NCCL all_reduce per step.
+    exchange = None
+    coll_wall = [0.0]
+    if world > 1 and os.environ.get("TSKB_BENCH_NCCL", "0") != "1":
+        exchange = sh.use_peer_exchange(2 * W)
 
     def step_device(collect=True):
         """One step with inputs and outputs in HBM; returns the engine's device time (CUDA events on
@@ -343,7 +349,11 @@ def run_ours(args):
                 ms += es["last_call_ms"]
                 phase_ms[:] += np.array(es["last_kernel_ms"][:6])
                 launches[0] += es["last_launches"]
-        if world > 1:
+        if world > 1 and exchange is not None:
+            t_c = time.perf_counter()
+            exchange.sum_into(d_both, d_both, windows, window_axis=1)   # host-synchronous, on the engine's stream
+            coll_wall[0] += (time.perf_counter() - t_c) * 1e3
+        elif world > 1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             sharding.combine(d_both, windows, True, window_axis=1)
@@ -382,8 +392,9 @@ def run_ours(args):
 
     def collective_ms():
         torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b in coll_ev)
+        ms = sum(a.elapsed_time(b) for a, b in coll_ev) + coll_wall[0]
         coll_ev.clear()
+        coll_wall[0] = 0.0
         return ms
 
     warm = max(args.warmup, 3)
@@ -509,10 +520,12 @@ def run_ours(args):
                 "l2": "inputs larger than L2 (plan arrays %.2f GB per rank)" % (st["device_bytes"] / 1e9),
                 "sharding": ("whole genome on one GPU" if world == 1 else
                              f"genome ranges from sharding.plan_shards, one per rank; per statistic one "
-                             f"all_reduce of both statistics' {W} x 1 device-resident partials inside the "
-                             f"timed region ({coll_ms / nsteps:.3f} ms per step on torch's stream incl. waiting "
-                             "for the slowest rank; it overlaps the next step's first sweep); value = edge "
-                             "diffs / device span of the timed region (CUDA events around it)"),
+                             f"sum of both statistics' {W} x 1 device-resident partials inside the timed "
+                             f"region ({coll_ms / nsteps:.3f} ms per step incl. waiting for the slowest rank), "
+                             + ("pushed over NVLink peer memory by the engine's kernels (tskb_exchange_sum), "
+                                "summed in rank order on every rank" if exchange is not None else
+                                "NCCL all_reduce on torch's stream") +
+                             "; value = edge diffs / device span of the timed region (CUDA events around it)"),
                 "timed_blocks": blocks, "timed_steps": nsteps, "timed_seconds_device": dev_ms / 1e3,
                 "stage_s": stage_s, "init_s": init_s, "tile_s": tile_s, "generate_s": gen_s,
                 "phase_ms_per_step": dict(zip(names, [float(x) for x in per_step_ms])),

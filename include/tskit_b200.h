@@ -292,6 +292,21 @@ int tskb_treeseq_stat_device(const tskb_treeseq_t *self, int stat_id,
     const int32_t *d_sample_sets, uint64_t num_index_tuples, const int32_t *index_tuples,
     uint64_t num_windows, const double *windows, uint32_t options, double *d_result);
 
+/* Sum of the ranks' partial results over NVLink peer memory (multi-GPU genome sharding; no reference
+ * counterpart: the reference has no multi-device path).  All pointers except peer_recv / peer_flags
+ * themselves are DEVICE pointers.  This rank pushes d_local[count] into slot [rank] of every peer's
+ * receive buffer (peer_recv[p] = base of peer p's [world x count] buffer for this epoch's parity,
+ * mapped into this process by CUDA IPC; p == rank is the local buffer d_recv), publishes `epoch` in
+ * peer_flags[p][rank], waits (bounded) until its own d_flags[0..world) have all reached `epoch`, and
+ * writes d_out[i] = sum over ranks r, in rank order, of d_recv[r][i], divided by
+ * d_spans[(i / span_stride) % span_count] when d_spans != NULL.  Epochs must increase by one per
+ * call on every rank and alternate between two buffer sets (parity).  TSKB_ERR_CUDA when a peer's
+ * partial does not arrive. */
+int tskb_exchange_sum(const tskb_treeseq_t *self, const double *d_local, uint64_t count, uint32_t world,
+    uint32_t rank, double *const *peer_recv, uint32_t *const *peer_flags, const double *d_recv,
+    const uint32_t *d_flags, uint32_t epoch, const double *d_spans, uint64_t span_stride, uint64_t span_count,
+    double *d_out);
+
 /* Debug/test access to plan arrays (copied to host). name in: "ev_pos",
  * "ev_child", "ev_sign", "voff", "bp_pos", "q_off", "refs", "q_bp0", "q_bp1", "q_bl",
  * "tile_dep", "level", "rank_node", "level_begin", "mut_src", "mut_allele", "mut_alt", "trace".  Returns the element count, or <0 on error; copies at most

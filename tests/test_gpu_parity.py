@@ -703,3 +703,27 @@ def test_restricted_range_engines_on_a_repeated_genome(wf_small):
         sh = sharding.ShardedTreeSequence(t, windows, 0, 1)
         got = sh.stat_host("divergence", sizes, flat, idx, windows, flag | STAT_SPAN_NORMALISE)
         assert close(got, o.stat("divergence", sets, idx, windows=windows, mode=mode))
+
+
+def test_peer_exchange_single_rank(wf_small, engines):
+    """tskb_exchange_sum with a world of one: the push / signal / wait / sum kernels on the local
+    buffers, both parities, with and without span normalisation along either axis (the multi-rank
+    path is exercised by bench.py --gpus N, whose result is checked against the reference)."""
+    import torch
+    from tskit_b200 import sharding
+    ll, _ = engines
+    ex = sharding.PeerExchange(ll, 64, 0, 1)
+    w = np.array([0.0, 1.0, 3.0, 7.0, 8.0, 20.0, 21.0])
+    spans = torch.from_numpy(np.diff(w)).cuda()
+    a = torch.arange(1, 13, dtype=torch.float64, device="cuda").reshape(6, 2)
+    for _ in range(3):
+        out = torch.empty_like(a)
+        ex.sum_into(a, out)
+        assert torch.equal(out, a)
+        ex.sum_into(a, out, w, window_axis=0)
+        assert torch.allclose(out, a / spans[:, None], rtol=1e-15, atol=0)
+    b = a.t().contiguous()  # statistics stacked along axis 0, windows along axis 1
+    ex.sum_into(b, b, w, window_axis=1)
+    assert torch.allclose(b, a.t() / spans[None, :], rtol=1e-15, atol=0)
+    with pytest.raises(ValueError):
+        ex.sum_into(torch.zeros(65, dtype=torch.float64, device="cuda"), torch.zeros(65, dtype=torch.float64, device="cuda"))

@@ -5,8 +5,9 @@ N=${2:-2}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-$TR bench.py --gpus $N --steps 20 --warmup 5 > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err; echo "bench N=$N exit $?"
-TSKB_BENCH_SYNC_COLL=1 $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench_n${N}_sync.json 2> $OUT/bench_n${N}_sync.err; echo "bench sync exit $?"
+timeout 600 $TR bench.py --gpus $N --steps 20 --warmup 5 > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err; echo "bench N=$N exit $?"
+TSKB_BENCH_NCCL=1 TSKB_BENCH_SYNC_COLL=1 $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench_n${N}_sync.json 2> $OUT/bench_n${N}_sync.err; echo "bench nccl sync exit $?"
+tail -3 $OUT/bench_n$N.err
 python - $OUT $N <<'EOF2'
 import json, sys
 for f in (f"bench_n{sys.argv[2]}.json", f"bench_n{sys.argv[2]}_sync.json"):

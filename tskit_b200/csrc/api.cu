@@ -12,10 +12,6 @@
 
 using namespace tskb;
 
-struct tskb_treeseq {
-    Plan *plan;
-};
-
 namespace {
 
 template <typename Fn>

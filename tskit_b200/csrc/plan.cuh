@@ -239,3 +239,8 @@ int run_divergence_matrix(const Plan *plan, uint64_t nsets, const uint64_t *size
     uint64_t num_windows, const double *windows, uint32_t options, double *result);
 
 }  // namespace tskb
+
+// the opaque handle of the C ABI
+struct tskb_treeseq {
+    tskb::Plan *plan;
+};

@@ -206,7 +206,18 @@ class ShardedTreeSequence:
             out = self._buf(("res", name, M), (len(w) - 1, M), torch.float64)
         self.engine.stat_device(name, sizes, d_sets.data_ptr(), idx, w,
                                 options & ~STAT_SPAN_NORMALISE, out.data_ptr())
+        ex = getattr(self, "_exchange", None)
+        if ex is not None and out.numel() <= ex.count:
+            return ex.sum_into(out, out, w if (options & STAT_SPAN_NORMALISE) else None)
         return combine(out, w, bool(options & STAT_SPAN_NORMALISE), group=self.group)
+
+    def use_peer_exchange(self, count):
+        """Sum the partials of ``stat_device`` / ``stat_host`` over NVLink peer memory (``PeerExchange``)
+        instead of an NCCL all_reduce, for results of at most ``count`` doubles.  Collective: every rank
+        of the group must call it."""
+        self._exchange = PeerExchange(self.engine, count, self.rank, self.world, device=self.device,
+                                      group=self.group)
+        return self._exchange
 
     def stat_host(self, name, sizes, sets, indexes, windows, options):
         """The call a user makes: host sample sets in, full host result out on every rank."""
@@ -256,3 +267,65 @@ class ShardedTreeSequence:
         out = [torch.empty_like(pad) for _ in range(self.world)]
         dist.all_gather(out, pad, group=self.group)
         return np.concatenate([o[:c].cpu().numpy() for o, c in zip(out, counts)], axis=0)
+
+
+class PeerExchange:
+    """Sum of the ranks' device-resident partials over NVLink peer memory (``tskb_exchange_sum``): every
+    rank pushes its partial into a receive buffer on every peer, then adds the world's slots in rank
+    order -- no NCCL launch on the path, and the same bits on every rank.  One process per GPU of one
+    node; the receive buffers are exchanged once as CUDA IPC handles (through torch's own tensor
+    sharing, over the process group).  ``count`` doubles per call at most."""
+
+    def __init__(self, engine, count, rank, world, device=0, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.engine, self.count, self.rank, self.world = engine, int(count), rank, world
+        dev = f"cuda:{device}"
+        # [parity][source rank][count] and [parity][source rank]
+        self.recv = torch.zeros((2, world, self.count), dtype=torch.float64, device=dev)
+        self.flags = torch.zeros((2, world), dtype=torch.int32, device=dev)
+        self.epoch = 0
+        torch.cuda.synchronize()
+        if world > 1:
+            mine = (reduce_tensor(self.recv), reduce_tensor(self.flags))
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine, group=group)
+            self._peers = []   # keeps the mappings alive
+            for r, ((f1, a1), (f2, a2)) in enumerate(everyone):
+                self._peers.append((self.recv, self.flags) if r == rank else (f1(*a1), f2(*a2)))
+            dist.barrier(group=group)
+        else:
+            self._peers = [(self.recv, self.flags)]
+        ptr = C.c_void_p * world
+        stride_r = world * self.count * 8
+        stride_f = world * 4
+        self._recv_ptrs = [ptr(*[p[0].data_ptr() + par * stride_r for p in self._peers]) for par in range(2)]
+        self._flag_ptrs = [ptr(*[p[1].data_ptr() + par * stride_f for p in self._peers]) for par in range(2)]
+
+    def sum_into(self, local, out, windows=None, window_axis=0):
+        """``out`` = sum over the ranks of ``local`` (both device tensors of at most ``count`` doubles;
+        they may be the same tensor), span-normalised along ``window_axis`` when ``windows`` is given."""
+        import ctypes as C
+
+        from . import _lib
+        from .lowlevel import _handle
+        n = local.numel()
+        if n > self.count or out.numel() != n or not local.is_contiguous() or not out.is_contiguous():
+            raise ValueError("PeerExchange: tensors must be contiguous and at most `count` doubles")
+        self.epoch += 1
+        par = self.epoch & 1
+        spans, stride, scount = None, 1, 1
+        if windows is not None:
+            sp = _spans(windows, local, window_axis).reshape(-1)
+            spans, scount = sp.data_ptr(), sp.numel()
+            stride = 1
+            for d in local.shape[window_axis + 1:]:
+                stride *= d
+        _handle(_lib.lib().tskb_exchange_sum(
+            self.engine._h, C.c_void_p(local.data_ptr()), n, self.world, self.rank, self._recv_ptrs[par],
+            self._flag_ptrs[par], C.c_void_p(self.recv[par].data_ptr()), C.c_void_p(self.flags[par].data_ptr()),
+            self.epoch, None if spans is None else C.c_void_p(spans), stride, scount, C.c_void_p(out.data_ptr())))
+        return out
