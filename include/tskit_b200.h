@@ -302,6 +302,9 @@ int tskb_treeseq_stat_device(const tskb_treeseq_t *self, int stat_id,
  * d_spans[(i / span_stride) % span_count] when d_spans != NULL.  Epochs must increase by one per
  * call on every rank and alternate between two buffer sets (parity).  TSKB_ERR_CUDA when a peer's
  * partial does not arrive. */
+/* cudaDeviceEnablePeerAccess from `device` to `peer_device` (kernels of this process running on `device`
+ * dereference memory of `peer_device` mapped by CUDA IPC); already enabled is not an error. */
+int tskb_enable_peer_access(int device, int peer_device);
 int tskb_exchange_sum(const tskb_treeseq_t *self, const double *d_local, uint64_t count, uint32_t world,
     uint32_t rank, double *const *peer_recv, uint32_t *const *peer_flags, const double *d_recv,
     const uint32_t *d_flags, uint32_t epoch, const double *d_spans, uint64_t span_stride, uint64_t span_count,

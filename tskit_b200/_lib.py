@@ -72,7 +72,7 @@ SYMBOLS = [
     "tskb_treeseq_divergence_matrix", "tskb_treeseq_genotype_matrix", "tskb_treeseq_decode_sites",
     "tskb_treeseq_general_stat",
     "tskb_treeseq_trees_at", "tskb_treeseq_get_stats", "tskb_treeseq_stat_device",
-    "tskb_treeseq_debug_array", "tskb_exchange_sum",
+    "tskb_treeseq_debug_array", "tskb_exchange_sum", "tskb_enable_peer_access",
 ]
 
 _lib = None
@@ -128,6 +128,7 @@ def lib():
                                                 u64, C.c_void_p, C.c_uint32, C.c_void_p]
         L.tskb_exchange_sum.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, u64, u64, C.c_void_p]
+        L.tskb_enable_peer_access.argtypes = [C.c_int, C.c_int]
         L.tskb_treeseq_debug_array.restype = C.c_int64
         L.tskb_treeseq_debug_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, u64]
         _lib = L

@@ -69,6 +69,24 @@ extern "C" {
 
 using namespace tskb;
 
+int tskb_enable_peer_access(int device, int peer_device) {
+    if (device == peer_device) return 0;
+    int can = 0;
+    if (cudaSetDevice(device) != cudaSuccess || cudaDeviceCanAccessPeer(&can, device, peer_device) != cudaSuccess || !can) {
+        cudaGetLastError();
+        last_error_string() = "no peer access between the two devices";
+        return TSKB_ERR_CUDA;
+    }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        last_error_string() = cudaGetErrorString(e);
+        cudaGetLastError();
+        return TSKB_ERR_CUDA;
+    }
+    cudaGetLastError();
+    return 0;
+}
+
 int tskb_exchange_sum(const tskb_treeseq_t *self, const double *d_local, uint64_t count, uint32_t world,
     uint32_t rank, double *const *peer_recv, uint32_t *const *peer_flags, const double *d_recv,
     const uint32_t *d_flags, uint32_t epoch, const double *d_spans, uint64_t span_stride, uint64_t span_count,

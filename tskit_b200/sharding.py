@@ -294,8 +294,13 @@ class PeerExchange:
             everyone = [None] * world
             dist.all_gather_object(everyone, mine, group=group)
             self._peers = []   # keeps the mappings alive
+            from . import _lib
+            from .lowlevel import _handle
             for r, ((f1, a1), (f2, a2)) in enumerate(everyone):
                 self._peers.append((self.recv, self.flags) if r == rank else (f1(*a1), f2(*a2)))
+                # the mapping lives in the owner's device context of this process: this rank's device
+                # needs peer access to it for its kernels to store there
+                _handle(_lib.lib().tskb_enable_peer_access(int(device), int(self._peers[-1][0].device.index)))
             dist.barrier(group=group)
         else:
             self._peers = [(self.recv, self.flags)]
