@@ -350,9 +350,12 @@ def run_ours(args):
                 phase_ms[:] += np.array(es["last_kernel_ms"][:6])
                 launches[0] += es["last_launches"]
         if world > 1 and exchange is not None:
+            # on the engine's stream, behind the two statistics; the host waits for it only in the
+            # instrumented steps (collect), where its wall time is the exchange incl. the slowest rank
             t_c = time.perf_counter()
-            exchange.sum_into(d_both, d_both, windows, window_axis=1)   # host-synchronous, on the engine's stream
-            coll_wall[0] += (time.perf_counter() - t_c) * 1e3
+            exchange.sum_into(d_both, d_both, windows, window_axis=1, wait=collect)
+            if collect:
+                coll_wall[0] += (time.perf_counter() - t_c) * 1e3
         elif world > 1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -430,7 +433,9 @@ def run_ours(args):
     for _ in range(blocks):
         for _ in range(args.steps):
             dev_ms += step_device(collect=world == 1)
-    span1.record()          # follows the last all_reduce + normalisation; the engine calls are synchronous
+    if exchange is not None:
+        exchange.status()   # the last exchange has completed (and none timed out) before the closing event
+    span1.record()          # follows the last sum + normalisation; the engine calls are synchronous
     torch.cuda.synchronize()
     wall_dev = time.perf_counter() - t0
     coll_ms = collective_ms()
@@ -443,7 +448,9 @@ def run_ours(args):
             step_device(collect=True)
         phase_ms *= nsteps_scale(blocks * args.steps, 5)
         launches[0] = int(launches[0] * nsteps_scale(blocks * args.steps, 5))
-        collective_ms()
+        c5 = collective_ms()
+        if exchange is not None:
+            coll_ms = c5 * nsteps_scale(blocks * args.steps, 5)   # host-waited exchanges of the 5 extra steps
     barrier()
     torch.cuda.synchronize()
     e2e_blocks = max(1, blocks // 2)
@@ -540,7 +547,7 @@ def run_ours(args):
                                 if world == 1 else "sharding.ShardedTreeSequence.stat_host (pinned "
                                 "staging, all_reduce on the device, one read-back)"),
                     "cold_including_staging_value": diffs_per_step / (stage_s + wall_e2e / nsteps_e2e)},
-            "gpu_launches": int(launches[0]),
+            "gpu_launches": int(launches[0]) + (nsteps if exchange is not None else 0),
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(names[dom]),
                          "traffic_note": "bytes per launch of the K=1 instantiation, ncu capture under profiles/",
@@ -810,6 +817,10 @@ def run_c3(args):
             for nm, ix in calls}
     phase = {}
     coll_ev = []
+    coll_wall = [0.0]
+    exchange = None
+    if world > 1 and os.environ.get("TSKB_BENCH_NCCL", "0") != "1":
+        exchange = sh.use_peer_exchange(W * len(pairs))
     p0 = torch.from_numpy(pairs[:, 0].astype(np.int64)).to(dev)
     p1 = torch.from_numpy(pairs[:, 1].astype(np.int64)).to(dev)
 
@@ -822,7 +833,12 @@ def run_c3(args):
             phase[nm] = phase.get(nm, 0.0) + es["last_call_ms"]
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            sharding.combine(outs[nm], windows, True)
+            if exchange is not None:   # host-synchronous, on the engine's stream
+                t_c = time.perf_counter()
+                exchange.sum_into(outs[nm], outs[nm], windows)
+                coll_wall[0] += (time.perf_counter() - t_c) * 1e3
+            else:
+                sharding.combine(outs[nm], windows, True)
             if nm == "divergence":  # Fst = 1 - 2 (pi_u + pi_v) / (pi_u + pi_v + 2 d_uv)
                 pi = outs["diversity"]
                 su = pi[:, p0] + pi[:, p1]
@@ -835,6 +851,9 @@ def run_c3(args):
         torch.cuda.synchronize()
         ms = sum(a.elapsed_time(b) for a, b in coll_ev)
         coll_ev.clear()
+        if exchange is not None:   # the events are on torch's stream and do not see the engine's
+            ms = coll_wall[0]
+        coll_wall[0] = 0.0
         return ms
 
     for _ in range(max(1, args.warmup)):
@@ -891,8 +910,10 @@ def run_c3(args):
                              f"{W} windows; {cfg['arms']} arms x {cfg['generations']} generations"),
                 "edge_diffs_per_sweep": nev_total, "sweeps_per_step": sweeps,
                 "sharding": ("whole genome on one GPU" if world == 1 else
-                             f"{world} genome ranges from sharding.plan_shards; per statistic one all_reduce "
-                             f"of the device-resident partials inside the timed region"),
+                             f"{world} genome ranges from sharding.plan_shards; per statistic one sum of the "
+                             "device-resident partials inside the timed region, "
+                             + ("pushed over NVLink peer memory (tskb_exchange_sum)" if exchange is not None
+                                else "NCCL all_reduce")),
                 "per_rank_plan_bytes_edge_diffs_engine_ms": per_rank,
                 "ms_per_step_by_statistic": {k: v / args.steps for k, v in phase.items()},
                 "collective_ms_per_step": coll_ms / args.steps, "wall_ms_per_step": wall / args.steps * 1e3,

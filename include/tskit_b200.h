@@ -293,22 +293,32 @@ int tskb_treeseq_stat_device(const tskb_treeseq_t *self, int stat_id,
     uint64_t num_windows, const double *windows, uint32_t options, double *d_result);
 
 /* Sum of the ranks' partial results over NVLink peer memory (multi-GPU genome sharding; no reference
- * counterpart: the reference has no multi-device path).  All pointers except peer_recv / peer_flags
- * themselves are DEVICE pointers.  This rank pushes d_local[count] into slot [rank] of every peer's
- * receive buffer (peer_recv[p] = base of peer p's [world x count] buffer for this epoch's parity,
- * mapped into this process by CUDA IPC; p == rank is the local buffer d_recv), publishes `epoch` in
- * peer_flags[p][rank], waits (bounded) until its own d_flags[0..world) have all reached `epoch`, and
- * writes d_out[i] = sum over ranks r, in rank order, of d_recv[r][i], divided by
- * d_spans[(i / span_stride) % span_count] when d_spans != NULL.  Epochs must increase by one per
- * call on every rank and alternate between two buffer sets (parity).  TSKB_ERR_CUDA when a peer's
- * partial does not arrive. */
-/* cudaDeviceEnablePeerAccess from `device` to `peer_device` (kernels of this process running on `device`
- * dereference memory of `peer_device` mapped by CUDA IPC); already enabled is not an error. */
-int tskb_enable_peer_access(int device, int peer_device);
-int tskb_exchange_sum(const tskb_treeseq_t *self, const double *d_local, uint64_t count, uint32_t world,
-    uint32_t rank, double *const *peer_recv, uint32_t *const *peer_flags, const double *d_recv,
-    const uint32_t *d_flags, uint32_t epoch, const double *d_spans, uint64_t span_stride, uint64_t span_count,
-    double *d_out);
+ * counterpart: the reference has no multi-device path; the semantics kept are trees.c:1920-1934,
+ * normalise after accumulation).  One exchange object per rank (one process per GPU of one node, or
+ * several in one process):
+ *   create       allocates this rank's receive slab for results of at most `capacity` doubles;
+ *   get_handle   the slab's CUDA IPC handle (TSKB_EXCHANGE_HANDLE_BYTES bytes) for the other processes;
+ *   connect      maps the peers' slabs: `handles` = world x TSKB_EXCHANGE_HANDLE_BYTES bytes in rank
+ *                order (the own entry is ignored); every rank connects before any rank sums;
+ *   connect_local  same for exchange objects living in this process (members[world], in rank order);
+ *   sum          d_out[i] = sum over ranks r, in rank order, of rank r's d_local[i], divided by
+ *                d_spans[(i / span_stride) % span_count] when d_spans != NULL.  All ranks call it the
+ *                same number of times with the same count.  DEVICE pointers; d_out may equal d_local.
+ *                With `engine` the kernels run on that engine's stream (after the statistic that
+ *                produced d_local), else on the exchange's own.  Host-synchronous unless
+ *                TSKB_EXCHANGE_ASYNC; TSKB_ERR_CUDA when a peer's partial does not arrive in 20 s;
+ *   status       waits for the calls issued so far and reports a timed-out one. */
+#define TSKB_EXCHANGE_HANDLE_BYTES 64
+#define TSKB_EXCHANGE_ASYNC 1u
+typedef struct tskb_exchange tskb_exchange_t;
+int tskb_exchange_create(int device, uint64_t capacity, uint32_t world, uint32_t rank, tskb_exchange_t **out);
+int tskb_exchange_get_handle(const tskb_exchange_t *self, void *handle_out);
+int tskb_exchange_connect(tskb_exchange_t *self, const void *handles);
+int tskb_exchange_connect_local(tskb_exchange_t *self, tskb_exchange_t *const *members);
+int tskb_exchange_sum(tskb_exchange_t *self, const tskb_treeseq_t *engine, const double *d_local, uint64_t count,
+    const double *d_spans, uint64_t span_stride, uint64_t span_count, double *d_out, uint32_t options);
+int tskb_exchange_status(tskb_exchange_t *self, const tskb_treeseq_t *engine);
+int tskb_exchange_free(tskb_exchange_t *self);
 
 /* Debug/test access to plan arrays (copied to host). name in: "ev_pos",
  * "ev_child", "ev_sign", "voff", "bp_pos", "q_off", "refs", "q_bp0", "q_bp1", "q_bl",

@@ -727,3 +727,52 @@ def test_peer_exchange_single_rank(wf_small, engines):
     assert torch.allclose(b, a.t() / spans[None, :], rtol=1e-15, atol=0)
     with pytest.raises(ValueError):
         ex.sum_into(torch.zeros(65, dtype=torch.float64, device="cuda"), torch.zeros(65, dtype=torch.float64, device="cuda"))
+
+
+@pytest.mark.parametrize("world,count", [(2, 96), (4, 5000), (3, 70000)])
+def test_peer_exchange_several_ranks_in_one_process(world, count):
+    """The exchange protocol with several ranks: `world` exchange objects on this device, connected in
+    process (tskb_exchange_connect_local), one host thread per rank, 7 calls each (both parities, the
+    single-CTA kernel and the grid-wide kernels).  Every rank must hold the rank-ordered sum, bit for
+    bit the same, span-normalised."""
+    import threading
+
+    import torch
+    from tskit_b200 import sharding
+    members = [sharding.PeerExchange(None, count, r, world, connect=False) for r in range(world)]
+    sharding.PeerExchange.connect_local(members)
+    rng = np.random.default_rng(5)
+    W = count // 4
+    w = np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 2.0, W))])
+    parts = [[torch.from_numpy(rng.normal(size=(W, 4))).cuda() for _ in range(world)] for _ in range(7)]
+    outs = [[None] * world for _ in range(7)]
+    errors = []
+
+    def run(r):
+        try:
+            for c in range(7):
+                out = torch.empty_like(parts[c][r])
+                members[r].sum_into(parts[c][r], out, w if c % 2 else None, wait=(c % 3 != 0))
+                outs[c][r] = out
+            members[r].status()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    torch.cuda.synchronize()
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    spans = torch.from_numpy(np.diff(w)).cuda()[:, None]
+    for c in range(7):
+        want = parts[c][0].clone()
+        for r in range(1, world):
+            want += parts[c][r]
+        if c % 2:
+            want = want / spans
+        for r in range(world):
+            assert torch.equal(outs[c][r], want), (c, r)
+    for m in members:
+        m.close()

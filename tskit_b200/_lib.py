@@ -72,7 +72,8 @@ SYMBOLS = [
     "tskb_treeseq_divergence_matrix", "tskb_treeseq_genotype_matrix", "tskb_treeseq_decode_sites",
     "tskb_treeseq_general_stat",
     "tskb_treeseq_trees_at", "tskb_treeseq_get_stats", "tskb_treeseq_stat_device",
-    "tskb_treeseq_debug_array", "tskb_exchange_sum", "tskb_enable_peer_access",
+    "tskb_treeseq_debug_array", "tskb_exchange_create", "tskb_exchange_get_handle", "tskb_exchange_connect",
+    "tskb_exchange_connect_local", "tskb_exchange_sum", "tskb_exchange_status", "tskb_exchange_free",
 ]
 
 _lib = None
@@ -126,9 +127,14 @@ def lib():
                                                C.c_void_p]
         L.tskb_treeseq_general_stat.argtypes = [C.c_void_p, u64, C.c_void_p, u64, GENERAL_STAT_FUNC, C.c_void_p,
                                                 u64, C.c_void_p, C.c_uint32, C.c_void_p]
-        L.tskb_exchange_sum.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
-                                        C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, u64, u64, C.c_void_p]
-        L.tskb_enable_peer_access.argtypes = [C.c_int, C.c_int]
+        L.tskb_exchange_create.argtypes = [C.c_int, u64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.tskb_exchange_get_handle.argtypes = [C.c_void_p, C.c_void_p]
+        L.tskb_exchange_connect.argtypes = [C.c_void_p, C.c_void_p]
+        L.tskb_exchange_connect_local.argtypes = [C.c_void_p, C.c_void_p]
+        L.tskb_exchange_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u64, C.c_void_p, u64, u64, C.c_void_p,
+                                        C.c_uint32]
+        L.tskb_exchange_status.argtypes = [C.c_void_p, C.c_void_p]
+        L.tskb_exchange_free.argtypes = [C.c_void_p]
         L.tskb_treeseq_debug_array.restype = C.c_int64
         L.tskb_treeseq_debug_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, u64]
         _lib = L

@@ -123,6 +123,9 @@ def _spans(windows, like, window_axis=0):
         shape = [1] * like.dim()
         shape[window_axis] = len(w) - 1
         t = torch.from_numpy((w[1:] - w[:-1]).reshape(shape)).to(like.device)
+        if t.is_cuda:
+            # the engine's kernels read it on their own (non-blocking) stream: the upload must have landed
+            torch.cuda.current_stream(t.device).synchronize()
         _SPANS[key] = t
     return t
 
@@ -214,10 +217,25 @@ class ShardedTreeSequence:
     def use_peer_exchange(self, count):
         """Sum the partials of ``stat_device`` / ``stat_host`` over NVLink peer memory (``PeerExchange``)
         instead of an NCCL all_reduce, for results of at most ``count`` doubles.  Collective: every rank
-        of the group must call it."""
-        self._exchange = PeerExchange(self.engine, count, self.rank, self.world, device=self.device,
-                                      group=self.group)
-        return self._exchange
+        of the group must call it.  Returns the exchange, or None (on every rank alike, the all_reduce
+        stays) when some rank could not map its peers -- GPUs without peer access, IPC not permitted."""
+        import torch
+        import torch.distributed as dist
+        ex, why = None, ""
+        try:
+            ex = PeerExchange(self.engine, count, self.rank, self.world, device=self.device, group=self.group)
+        except Exception as e:  # noqa: BLE001 -- reported, and agreed on below
+            why = f"{type(e).__name__}: {e}"
+        if self.world > 1:
+            ok = torch.tensor([0 if ex is None else 1], device=f"cuda:{self.device}")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                if ex is not None:
+                    ex.close()
+                ex = None
+        self._exchange = ex
+        self.exchange_note = why
+        return ex
 
     def stat_host(self, name, sizes, sets, indexes, windows, options):
         """The call a user makes: host sample sets in, full host result out on every rank."""
@@ -270,49 +288,68 @@ class ShardedTreeSequence:
 
 
 class PeerExchange:
-    """Sum of the ranks' device-resident partials over NVLink peer memory (``tskb_exchange_sum``): every
-    rank pushes its partial into a receive buffer on every peer, then adds the world's slots in rank
+    """Sum of the ranks' device-resident partials over NVLink peer memory (``tskb_exchange_*``): every
+    rank pushes its partial into a receive slab on every peer, then adds the world's slots in rank
     order -- no NCCL launch on the path, and the same bits on every rank.  One process per GPU of one
-    node; the receive buffers are exchanged once as CUDA IPC handles (through torch's own tensor
-    sharing, over the process group).  ``count`` doubles per call at most."""
+    node: the slabs' CUDA IPC handles (64 bytes each) are exchanged once over the process group and
+    mapped by the library from this rank's device.  ``members`` instead connects exchange objects of
+    THIS process (one per device or stream; no IPC).  ``count`` doubles per call at most."""
 
-    def __init__(self, engine, count, rank, world, device=0, group=None):
+    ASYNC = 1
+
+    def __init__(self, engine, count, rank, world, device=0, group=None, connect=True):
         import ctypes as C
 
-        import torch
-        import torch.distributed as dist
-        from torch.multiprocessing.reductions import reduce_tensor
-        self.engine, self.count, self.rank, self.world = engine, int(count), rank, world
-        dev = f"cuda:{device}"
-        # [parity][source rank][count] and [parity][source rank]
-        self.recv = torch.zeros((2, world, self.count), dtype=torch.float64, device=dev)
-        self.flags = torch.zeros((2, world), dtype=torch.int32, device=dev)
-        self.epoch = 0
-        torch.cuda.synchronize()
-        if world > 1:
-            mine = (reduce_tensor(self.recv), reduce_tensor(self.flags))
+        from . import _lib
+        from .lowlevel import _handle
+        self.engine, self.count, self.rank, self.world, self.device = engine, int(count), rank, world, device
+        L = _lib.lib()
+        self._x = None
+        err = None
+        try:
+            h = C.c_void_p()
+            _handle(L.tskb_exchange_create(int(device), self.count, world, rank, C.byref(h)))
+            self._x = h
+        except Exception as e:  # noqa: BLE001 -- the collectives below still have to be entered
+            err = e
+        if world > 1 and connect:
+            import torch.distributed as dist
+            mine = C.create_string_buffer(64)
+            if err is None:
+                try:
+                    _handle(L.tskb_exchange_get_handle(self._x, mine))
+                except Exception as e:  # noqa: BLE001
+                    err = e
             everyone = [None] * world
-            dist.all_gather_object(everyone, mine, group=group)
-            self._peers = []   # keeps the mappings alive
-            from . import _lib
-            from .lowlevel import _handle
-            for r, ((f1, a1), (f2, a2)) in enumerate(everyone):
-                self._peers.append((self.recv, self.flags) if r == rank else (f1(*a1), f2(*a2)))
-                # the mapping lives in the owner's device context of this process: this rank's device
-                # needs peer access to it for its kernels to store there
-                _handle(_lib.lib().tskb_enable_peer_access(int(device), int(self._peers[-1][0].device.index)))
-            dist.barrier(group=group)
-        else:
-            self._peers = [(self.recv, self.flags)]
-        ptr = C.c_void_p * world
-        stride_r = world * self.count * 8
-        stride_f = world * 4
-        self._recv_ptrs = [ptr(*[p[0].data_ptr() + par * stride_r for p in self._peers]) for par in range(2)]
-        self._flag_ptrs = [ptr(*[p[1].data_ptr() + par * stride_f for p in self._peers]) for par in range(2)]
+            dist.all_gather_object(everyone, None if err is not None else mine.raw, group=group)
+            if err is None and all(h is not None for h in everyone):
+                try:
+                    _handle(L.tskb_exchange_connect(self._x, b"".join(everyone)))
+                except Exception as e:  # noqa: BLE001
+                    err = e
+            elif err is None:
+                err = RuntimeError("PeerExchange: a peer could not export its receive slab")
+            dist.barrier(group=group)   # every slab is mapped everywhere before the first push
+        if err is not None:
+            self.close()
+            raise err
 
-    def sum_into(self, local, out, windows=None, window_axis=0):
+    @staticmethod
+    def connect_local(members):
+        """Connect exchange objects created in this process with ``connect=False`` (rank order)."""
+        import ctypes as C
+
+        from . import _lib
+        from .lowlevel import _handle
+        arr = (C.c_void_p * len(members))(*[m._x for m in members])
+        for m in members:
+            _handle(_lib.lib().tskb_exchange_connect_local(m._x, arr))
+
+    def sum_into(self, local, out, windows=None, window_axis=0, wait=True):
         """``out`` = sum over the ranks of ``local`` (both device tensors of at most ``count`` doubles;
-        they may be the same tensor), span-normalised along ``window_axis`` when ``windows`` is given."""
+        they may be the same tensor), span-normalised along ``window_axis`` when ``windows`` is given.
+        Runs on the engine's stream; ``wait=False`` returns without waiting for the device (``status()``
+        later reports a peer that never delivered)."""
         import ctypes as C
 
         from . import _lib
@@ -320,8 +357,6 @@ class PeerExchange:
         n = local.numel()
         if n > self.count or out.numel() != n or not local.is_contiguous() or not out.is_contiguous():
             raise ValueError("PeerExchange: tensors must be contiguous and at most `count` doubles")
-        self.epoch += 1
-        par = self.epoch & 1
         spans, stride, scount = None, 1, 1
         if windows is not None:
             sp = _spans(windows, local, window_axis).reshape(-1)
@@ -330,7 +365,24 @@ class PeerExchange:
             for d in local.shape[window_axis + 1:]:
                 stride *= d
         _handle(_lib.lib().tskb_exchange_sum(
-            self.engine._h, C.c_void_p(local.data_ptr()), n, self.world, self.rank, self._recv_ptrs[par],
-            self._flag_ptrs[par], C.c_void_p(self.recv[par].data_ptr()), C.c_void_p(self.flags[par].data_ptr()),
-            self.epoch, None if spans is None else C.c_void_p(spans), stride, scount, C.c_void_p(out.data_ptr())))
+            self._x, None if self.engine is None else self.engine._h, C.c_void_p(local.data_ptr()), n,
+            None if spans is None else C.c_void_p(spans), stride, scount, C.c_void_p(out.data_ptr()),
+            0 if wait else self.ASYNC))
         return out
+
+    def status(self):
+        from . import _lib
+        from .lowlevel import _handle
+        _handle(_lib.lib().tskb_exchange_status(self._x, None if self.engine is None else self.engine._h))
+
+    def close(self):
+        if getattr(self, "_x", None):
+            from . import _lib
+            _lib.lib().tskb_exchange_free(self._x)
+            self._x = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
