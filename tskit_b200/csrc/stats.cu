@@ -58,6 +58,15 @@ __host__ __device__ __forceinline__ V ivec_zero() {
     return r;
 }
 
+// statistics whose column reads only the (at most four) sets of its own index tuple: the lane's
+// column then works on a 4-column excerpt of the state, fetched from shared memory
+template <int STAT>
+constexpr bool stat_reads_tuple_only() {
+    return STAT == STAT_DIVERSITY || STAT == STAT_SEGSITES || STAT == STAT_Y1 || STAT == STAT_DIVERGENCE
+           || STAT == STAT_Y2 || STAT == STAT_F2 || STAT == STAT_RELATEDNESS_NC || STAT == STAT_Y3
+           || STAT == STAT_F3 || STAT == STAT_F4;
+}
+
 // one result column: the sample-set indexes of its tuple and their sizes
 struct ColP {
     int32_t i, j, k, l;
@@ -86,13 +95,29 @@ __device__ __forceinline__ typename V::scalar pick_t(const V &s, int i) {
     return r;
 }
 
+// totals - s, evaluated lazily per picked column (see F_branch)
+template <class V>
+struct Compl {
+    const V &s;
+    const V &t;
+    static constexpr int N = V::N;
+    using scalar = typename V::scalar;
+    using inner = V;
+};
+template <class V> struct is_compl { static constexpr bool value = false; };
+template <class V> struct is_compl<Compl<V>> { static constexpr bool value = true; };
+
 // x[i] without dynamic register indexing
 template <class V>
 __device__ __forceinline__ double pick(const V &s, int i) {
-    typename V::scalar r = s.v[0];
+    if constexpr (is_compl<V>::value) {
+        return (double) pick_t<typename V::inner>(s.t, i) - (double) pick_t<typename V::inner>(s.s, i);
+    } else {
+        typename V::scalar r = s.v[0];
 #pragma unroll
-    for (int k = 1; k < V::N; k++) r = (i == k) ? s.v[k] : r;
-    return (double) r;
+        for (int k = 1; k < V::N; k++) r = (i == k) ? s.v[k] : r;
+        return (double) r;
+    }
 }
 
 // Denominator of a column, in the reference's operation order.  The device multiplies by its
@@ -142,7 +167,7 @@ __device__ __forceinline__ double f_eval(const SumP &P, const ColP &c, int m, co
         double sumx = 0;
 #pragma unroll
         for (int k = 0; k < V::N; k++) {
-            if (k < P.K) sumx += (double) s.v[k] / P.n[k];
+            if (k < P.K) sumx += pick<V>(s, k) / P.n[k];
         }
         double meanx = sumx / (double) P.K;
         return (pick<V>(s, c.i) / c.ni - meanx) * (pick<V>(s, c.j) / c.nj - meanx);
@@ -198,7 +223,7 @@ __device__ __forceinline__ double f_eval(const SumP &P, const ColP &c, int m, co
     } else if constexpr (STAT == STAT_REL_WEIGHTED_NC) {
         return pick<V>(s, c.i) * pick<V>(s, c.j);  // trees.c:4822-4838
     } else {  // STAT_TABULATED
-        uint32_t cnt = (uint32_t) (long long) s.v[0];
+        uint32_t cnt = (uint32_t) (long long) pick<V>(s, 0);
         if (cnt >= P.table_rows) cnt = P.table_rows - 1;
         return __ldg(P.table + (size_t) cnt * P.M + m);
     }
@@ -723,6 +748,197 @@ __global__ void k_bins_finalize(const double *__restrict__ gP, const double *__r
     }
 }
 
+// ---- window runs in registers (few windows, finite summaries; the default for up to 5 columns)
+// The window integral of a branch statistic is  sum over pieces of  G x |[x0, x1) meet window|,
+// G = branch_length x F(state).  A thread walks RUN_IPT CONSECUTIVE pieces of the processing order
+// (consecutive pieces are mostly successive pieces of one node: they follow each other along the genome)
+// and keeps the sum for the window it is in IN A REGISTER; it leaves as one fp64 reduction when the
+// thread moves to another window -- 0.3-0.5 reductions per piece instead of one per piece into the
+// per-breakpoint deltas, and no scan over the breakpoints or window integration afterwards.  A piece
+// that crosses window edges adds its parts to the first and the last window it meets and +-G to a
+// difference array over the windows it covers entirely (gC).  The bins are replicated (one copy per
+// group of warps: reductions to one address serialise in L2) and summed by k_runs_finalize.
+constexpr int RUN_TB = 256;
+constexpr int RUN_IPT = 8;
+
+struct RunArgs {
+    const double *windows;  // [W + 1] (device)
+    uint32_t W;
+    double w0, inv_width;   // roughly uniform windows: index guess (x - w0) * inv_width, then corrected
+    int uniform;
+    double step, inv_step, wlast;  // exactly uniform windows: edge i = w0 + i * step (i < W), wlast (i = W)
+    double *bins;           // [copies][(2 W + 1) x ncols]: R[w][col] then C[w][col] (C has W + 1 rows)
+    uint32_t ncols;         // columns per bin row
+    uint32_t copy_mask;     // copies - 1 (a power of two)
+    int clip;               // the windows do not cover the genome: clip the pieces
+    int prefetch;           // L2 prefetch of the thread's next group
+    uint32_t chunk_mul;     // walk by start position: chunk of warp i = i * chunk_mul mod the number of chunks
+};
+
+// window w with win[w] <= x < win[w + 1] (END = false) or win[w] < x <= win[w + 1] (END = true);
+// the caller guarantees win[0] <= x < win[W], resp. win[0] < x <= win[W]
+template <bool END>
+__device__ __forceinline__ uint32_t run_window_of(const double *win, const RunArgs &b, double x) {
+    uint32_t lo = 0, hi = b.W - 1;
+    if (b.uniform) {
+        const double g = (x - b.w0) * b.inv_width;
+        uint32_t w = g <= 0.0 ? 0u : (g >= (double) (b.W - 1) ? b.W - 1 : (uint32_t) g);
+        if (END) {
+            while (w > 0 && x <= win[w]) w--;
+            while (w + 1 < b.W && x > win[w + 1]) w++;
+        } else {
+            while (w > 0 && x < win[w]) w--;
+            while (w + 1 < b.W && x >= win[w + 1]) w++;
+        }
+        return w;
+    }
+    while (lo < hi) {  // largest w with win[w] <= x (resp. < x)
+        const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+        const bool left = END ? win[mid] < x : win[mid] <= x;
+        if (left) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+template <class V>
+struct Run8 {
+    V st[RUN_IPT];
+    double bl[RUN_IPT], x0[RUN_IPT], x1[RUN_IPT];
+    __device__ __forceinline__ void load(uint32_t g, const double *__restrict__ q_x0,
+        const double *__restrict__ q_x1, const double *__restrict__ q_bl, const V *__restrict__ pval) {
+        const size_t base = (size_t) g * RUN_IPT;
+#pragma unroll
+        for (int i = 0; i < RUN_IPT / 2; i++) {
+            const double2 a = __ldg(reinterpret_cast<const double2 *>(q_bl + base) + i);
+            const double2 b = __ldg(reinterpret_cast<const double2 *>(q_x0 + base) + i);
+            const double2 c = __ldg(reinterpret_cast<const double2 *>(q_x1 + base) + i);
+            bl[2 * i] = a.x; bl[2 * i + 1] = a.y;
+            x0[2 * i] = b.x; x0[2 * i + 1] = b.y;
+            x1[2 * i] = c.x; x1[2 * i + 1] = c.y;
+        }
+        constexpr int NQ = (int) (sizeof(V) * RUN_IPT / 16);
+        union { V s[RUN_IPT]; int4 q[NQ]; } u;
+        const int4 *src = reinterpret_cast<const int4 *>(pval + base);
+#pragma unroll
+        for (int i = 0; i < NQ; i++) u.q[i] = src[i];
+#pragma unroll
+        for (int i = 0; i < RUN_IPT; i++) st[i] = u.s[i];
+    }
+};
+
+// Exactly uniform windows (np.linspace: edge i = w0 + i * step, the last one the stop value; the host has
+// checked that every given edge equals this expression bit for bit -- no FMA contraction, -fmad=false):
+// the window of a position is cell(x) = min(trunc((x - w0) / step), W - 1), a monotone function of x.
+// Within a few ulp of an edge cell(x) may name the neighbouring window; the parts of a piece are
+// measured against the nominal edges, so that they still add up to G x (e - a) exactly and the
+// misplaced part is a few ulp of a base pair long.
+template <int STAT, class V>
+__global__ void __launch_bounds__(RUN_TB, 3) k_branch_summary_runs(uint32_t npp,
+    const double *__restrict__ q_x0, const double *__restrict__ q_x1, const double *__restrict__ q_bl,
+    const V *__restrict__ pval, SumP sp, V totals, const ColP *cols, uint32_t m, RunArgs b) {
+    const double first_edge = b.w0, last_edge = b.wlast;
+    const ColP col = cols[m];
+    const uint32_t copy = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) & b.copy_mask;
+    double *gR = b.bins + (size_t) copy * (2 * (size_t) b.W + 1);
+    double *gC = gR + b.W;
+    // npp is a multiple of PROP_TILE = 1024: whole groups, no bounds checks inside a group
+    const uint32_t ngroups = npp / RUN_IPT;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t wc = 0;    // the window the thread's register sum belongs to
+    double acc = 0.0;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+        Run8<V> cur;
+        cur.load(g, q_x0, q_x1, q_bl, pval);
+#pragma unroll
+        for (int q = 0; q < RUN_IPT; q++) {
+            // Straight-line arithmetic for all lanes up to the few predicated reductions: padding
+            // (x1 < 0) and pieces without a branch above them (finite summaries only here) end up with
+            // an empty clipped span or G = 0.
+            const double G = cur.bl[q] * F_branch<STAT, V>(sp, col, m, cur.st[q], totals);
+            // windows need not cover the genome (divergence_matrix): clip to [first_edge, last_edge]
+            const double a = fmax(cur.x0[q], first_edge), e = fmin(cur.x1[q], last_edge);
+            const bool live = a < e && G != 0.0;
+            uint32_t w0, w1;
+            double hi0, lo1;
+            w0 = min((uint32_t) ((a - first_edge) * b.inv_step), b.W - 1);
+            w1 = min((uint32_t) ((e - first_edge) * b.inv_step), b.W - 1);
+            hi0 = w0 + 1 >= b.W ? last_edge : first_edge + (double) (w0 + 1) * b.step;
+            lo1 = first_edge + (double) w1 * b.step;
+            if (live) {
+                if (w0 != wc) {  // the thread's register sum moves to the piece's first window
+                    if (acc != 0.0) atomicAdd(gR + wc, acc);
+                    acc = 0.0;
+                    wc = w0;
+                }
+                if (w1 == w0) {
+                    acc += G * (e - a);
+                } else {  // a piece that ends in a later window closes the first one and opens the last one
+                    atomicAdd(gR + w0, acc + G * (hi0 - a));
+                    if (w1 > w0 + 1) {  // the windows in between are covered entirely
+                        atomicAdd(gC + w0 + 1, G);
+                        atomicAdd(gC + w1, -G);
+                    }
+                    wc = w1;
+                    acc = G * (e - lo1);
+                }
+            }
+        }
+    }
+    if (acc != 0.0) atomicAdd(gR + wc, acc);
+}
+
+// RC[i] = sum over the copies of bins[copy][i], i < block = (2 W + 1) x ncols; CTAs of 1024 threads:
+// lanes are elements, the warps share out the copies
+__global__ void __launch_bounds__(1024) k_runs_reduce(const double *__restrict__ bins, uint32_t block, uint32_t copies,
+    double *RC) {
+    __shared__ double part[32][33];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * 32 + lane;
+    double s = 0.0;
+    if (i < block) {
+        for (uint32_t c = warp; c < copies; c += 32) s += bins[(size_t) c * block + i];
+    }
+    part[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && i < block) {
+        double t = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < 32; k++) t += part[k][lane];
+        RC[i] = t;
+    }
+}
+
+// window w of column c: R[w][c] + span(w) x (C[0][c] + ... + C[w][c]); one warp per column
+__global__ void k_runs_finalize(const double *__restrict__ RC, const double *__restrict__ windows, uint32_t W,
+    uint32_t ncols, uint32_t m0, uint32_t M, int span_normalise, double *result) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncols) return;
+    const double *R = RC + c, *C = RC + (size_t) W * ncols + c;
+    double run = 0.0;
+    for (uint32_t base = 0; base < W; base += 32) {
+        const uint32_t w = base + lane;
+        double v = w < W ? C[(size_t) w * ncols] : 0.0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double u = __shfl_up_sync(0xffffffffu, v, d);
+            if ((int) lane >= d) v += u;
+        }
+        const double S = run + v;
+        run += __shfl_sync(0xffffffffu, v, 31);
+        if (w < W) {
+            const double span = windows[w + 1] - windows[w];
+            double r = R[(size_t) w * ncols] + span * S;
+            if (span_normalise) r /= span;
+            result[(size_t) w * M + m0 + c] = r;
+        }
+    }
+}
+
 // ---- many result columns: lanes are columns
 // With M columns the kernel above issues M reductions per piece, each lane of an instruction to
 // its own cache line.  Here a warp walks its pieces one after the other and lane m evaluates
@@ -815,14 +1031,6 @@ __global__ void k_so_gather(uint32_t n, const uint32_t *__restrict__ slot, const
     bp0[i] = q_bp0[j]; bp1[i] = q_bp1[j]; bl[i] = q_bl[j];
 }
 
-// statistics whose column reads only the (at most four) sets of its own index tuple: the lane's
-// column then works on a 4-column excerpt of the state, fetched from shared memory
-template <int STAT>
-constexpr bool stat_reads_tuple_only() {
-    return STAT == STAT_DIVERSITY || STAT == STAT_SEGSITES || STAT == STAT_Y1 || STAT == STAT_DIVERGENCE
-           || STAT == STAT_Y2 || STAT == STAT_F2 || STAT == STAT_RELATEDNESS_NC || STAT == STAT_Y3
-           || STAT == STAT_F3 || STAT == STAT_F4;
-}
 
 // A warp takes BYPOS_CHUNK consecutive pieces of the summary order, 32 at a time through shared memory
 // (state, branch length, breakpoints).  The lanes are split into 32 / CP groups of CP >= ncols lanes
@@ -905,6 +1113,132 @@ __global__ void __launch_bounds__(TB) k_branch_summary_bypos(uint32_t nsp,
         }
     }
     if (cur != NO_PIECE && mine && acc != 0.0) atomicAdd(Dl + (size_t) cur * ncols, acc);
+}
+
+// ---- many result columns, window runs (finite summaries, windows x columns small enough; default)
+// The same walk by start position, with the window sums kept in registers instead of per-breakpoint
+// deltas (cf. k_branch_summary_runs): the pieces arrive sorted by the position they start at, so the
+// window of a lane group's register sum changes only when the walk passes a window edge, and a piece
+// that ends in a later window (31 % on C2 with 1000 windows) sends its last part there as ONE reduction
+// per column -- a third of the reductions of the delta formulation, into bins that stay in L2, and no
+// scan or integration over the breakpoints afterwards.  The lane that loads a piece also finds its
+// windows (once per piece, not per column).  Concurrent warps take chunks far apart along the genome
+// (chunk = warp x chunk_mul mod chunks) and the bins are replicated: few reductions meet at one address.
+constexpr uint32_t RUN_DEAD = 0xfffffffeu;  // a piece that adds nothing (no branch above it, or outside the windows)
+
+__device__ __forceinline__ void run_piece_windows(const RunArgs &b, int exact, double x0, double x1, uint32_t &w0,
+    uint32_t &w1, double &d0, double &d1) {
+    const double a = fmax(x0, b.w0), e = fmin(x1, b.wlast);
+    if (!(a < e)) {
+        w0 = RUN_DEAD; w1 = RUN_DEAD; d0 = 0.0; d1 = 0.0;
+        return;
+    }
+    double hi0, lo1;
+    if (exact) {
+        w0 = min((uint32_t) ((a - b.w0) * b.inv_step), b.W - 1);
+        w1 = min((uint32_t) ((e - b.w0) * b.inv_step), b.W - 1);
+        hi0 = w0 + 1 >= b.W ? b.wlast : b.w0 + (double) (w0 + 1) * b.step;
+        lo1 = b.w0 + (double) w1 * b.step;
+    } else {
+        w0 = run_window_of<false>(b.windows, b, a);
+        w1 = run_window_of<true>(b.windows, b, e);
+        hi0 = b.windows[w0 + 1];
+        lo1 = b.windows[w1];
+    }
+    d0 = w1 == w0 ? e - a : hi0 - a;
+    d1 = w1 == w0 ? 0.0 : e - lo1;
+}
+
+template <int STAT, class V>
+__global__ void __launch_bounds__(TB) k_branch_summary_bypos_runs(uint32_t nsp,
+    const uint32_t *__restrict__ so_slot, const uint32_t *__restrict__ so_bp0,
+    const uint32_t *__restrict__ so_bp1, const double *__restrict__ so_bl, const double *__restrict__ bp_pos,
+    const V *__restrict__ pval, SumP sp, V totals, const ColP *cols, uint32_t m0, uint32_t ncols, uint32_t CP,
+    RunArgs b, int exact, uint32_t nchunks) {
+    using T = typename V::scalar;
+    using V4 = SVec<T, 4>;
+    __shared__ T s_state[TB / 32][32][V::N];
+    __shared__ double s_bl[TB / 32][32], s_d0[TB / 32][32], s_d1[TB / 32][32];
+    __shared__ uint32_t s_w0[TB / 32][32], s_w1[TB / 32][32];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= nchunks) return;
+    const uint32_t chunk = (uint32_t) (((uint64_t) warp * b.chunk_mul) % nchunks);
+    const uint32_t c0 = chunk * BYPOS_CHUNK;
+    const uint32_t c1 = min(nsp, c0 + BYPOS_CHUNK);
+    const uint32_t groups = 32u / CP, per_group = 32u / groups;  // pieces of a tile each group walks
+    const uint32_t g = lane / CP, cl = lane % CP;
+    const bool mine = cl < ncols;
+    const uint32_t m = m0 + (mine ? cl : 0);
+    ColP col = cols[m];
+    V4 tot4 = ivec_zero<V4>();
+    int idx4[4] = { col.i, col.j, col.k, col.l };
+    if constexpr (stat_reads_tuple_only<STAT>()) {
+        if (STAT == STAT_DIVERSITY || STAT == STAT_SEGSITES || STAT == STAT_Y1) idx4[0] = col.i;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            idx4[a] = idx4[a] < 0 || idx4[a] >= V::N ? 0 : idx4[a];
+            tot4.v[a] = pick_t<V>(totals, idx4[a]);
+        }
+        col.i = 0; col.j = 1; col.k = 2; col.l = 3;
+    }
+    const size_t block = (2 * (size_t) b.W + 1) * ncols;
+    double *gR = b.bins + (size_t) (warp & b.copy_mask) * block + cl;   // R[w * ncols + column]
+    double *gC = gR + (size_t) b.W * ncols;                             // C[w * ncols + column]
+    double acc = 0.0;
+    uint32_t wc = RUN_DEAD;    // window the register sum belongs to (group-uniform)
+    for (uint32_t base = c0; base < c1; base += 32) {
+        const uint32_t j = base + lane;
+        __syncwarp();
+        if (j < c1) {
+            const V st = pval[so_slot[j]];
+#pragma unroll
+            for (int k = 0; k < V::N; k++) s_state[wib][lane][k] = st.v[k];
+            const double bl_j = so_bl[j];
+            uint32_t w0, w1;
+            double d0, d1;
+            run_piece_windows(b, exact, bp_pos[so_bp0[j]], bp_pos[so_bp1[j]], w0, w1, d0, d1);
+            if (bl_j == 0.0) w0 = RUN_DEAD;  // finite summaries only here: 0 x f adds nothing
+            s_bl[wib][lane] = bl_j; s_w0[wib][lane] = w0; s_w1[wib][lane] = w1;
+            s_d0[wib][lane] = d0; s_d1[wib][lane] = d1;
+        } else {
+            s_w0[wib][lane] = NO_PIECE;
+        }
+        __syncwarp();
+        for (uint32_t q = 0; q < per_group; q++) {
+            const uint32_t i = g * per_group + q;
+            const uint32_t w0 = s_w0[wib][i];
+            if (w0 == NO_PIECE) break;  // past the end of the chunk (group-uniform)
+            if (w0 == RUN_DEAD) continue;
+            double G;
+            if constexpr (stat_reads_tuple_only<STAT>()) {
+                V4 t4;
+#pragma unroll
+                for (int a = 0; a < 4; a++) t4.v[a] = s_state[wib][i][idx4[a]];
+                G = s_bl[wib][i] * F_branch<STAT, V4>(sp, col, (int) m, t4, tot4);
+            } else {
+                V s_i;
+#pragma unroll
+                for (int k = 0; k < V::N; k++) s_i.v[k] = s_state[wib][i][k];
+                G = s_bl[wib][i] * F_branch<STAT, V>(sp, col, (int) m, s_i, totals);
+            }
+            if (w0 != wc) {
+                if (wc != RUN_DEAD && mine && acc != 0.0) atomicAdd(gR + (size_t) wc * ncols, acc);
+                acc = 0.0;
+                wc = w0;
+            }
+            acc += G * s_d0[wib][i];
+            const uint32_t w1 = s_w1[wib][i];
+            if (w1 != w0 && mine && G != 0.0) {
+                atomicAdd(gR + (size_t) w1 * ncols, G * s_d1[wib][i]);
+                if (w1 > w0 + 1) {  // the windows in between are covered entirely
+                    atomicAdd(gC + (size_t) (w0 + 1) * ncols, G);
+                    atomicAdd(gC + (size_t) w1 * ncols, -G);
+                }
+            }
+        }
+    }
+    if (wc != RUN_DEAD && mine && acc != 0.0) atomicAdd(gR + (size_t) wc * ncols, acc);
 }
 
 // ---- running sums and window integrals of deltas laid out [breakpoint][column], lanes = columns:
@@ -1683,8 +2017,95 @@ bool run_branch_bins(CallCtx &c, V *pval, V totals) {
     return true;
 }
 
+// window description for the run kernels; exact = the windows are np.linspace-like: every edge is
+// w0 + i * step bit for bit (two roundings, as on the device), the last one the stop value
+RunArgs make_run_args(const double *w, uint32_t W, const double *d_windows, bool &exact) {
+    RunArgs b = {};
+    b.windows = d_windows; b.W = W; b.w0 = w[0]; b.inv_width = (double) W / (w[W] - w[0]); b.uniform = 1;
+    for (uint32_t i = 0; i <= W && b.uniform; i++) {
+        const double ideal = w[0] + (w[W] - w[0]) * ((double) i / (double) W);
+        if (fabs(w[i] - ideal) * b.inv_width > 0.25) b.uniform = 0;
+    }
+    b.step = W > 1 ? w[1] - w[0] : w[W] - w[0];
+    b.inv_step = 1.0 / b.step;
+    b.wlast = w[W];
+    exact = b.step > 0 && getenv("TSKB_RUN_GENERAL") == nullptr;
+    for (uint32_t i = 0; i < W && exact; i++) {
+        volatile double prod = (double) i * b.step;
+        volatile double e = w[0] + prod;
+        if (e != w[i]) exact = false;
+    }
+    if (exact && !(w[W] > w[0] + (double) (W - 1) * b.step)) exact = false;
+    b.clip = 1;
+    b.prefetch = getenv("TSKB_RUN_PREFETCH") == nullptr || atoi(getenv("TSKB_RUN_PREFETCH")) != 0;
+    return b;
+}
+
+constexpr uint32_t RUNS_MAX_W = 4096;   // window edges in shared memory, replicated bins in L2
+
+// Window runs in registers: finite summaries, few columns, windows few enough.  Returns false when the
+// call does not qualify (the delta formulation runs instead).
+template <int STAT, class V>
+bool run_branch_runs(CallCtx &c, V *pval, V totals) {
+    const Plan &P = *c.P;
+    const uint32_t M = c.sp->M, W = c.sp->W;
+    // Default for np.linspace-like windows (the window of a position is arithmetic); other windows run
+    // the delta formulation, which is as fast as this kernel with a window search per piece end
+    // (measured on C2, profiles/r2q: 0.97 vs 0.97 ms per step), unless TSKB_SUM_VARIANT=runs asks for it.
+    const char *variant = getenv("TSKB_SUM_VARIANT");
+    const bool forced = variant != nullptr && variant[0] == 'r';
+    if (variant != nullptr && !forced) return false;
+    if (!c.sumP.skip_zero_bl || P.npp == 0 || P.T == 0 || W == 0 || W > RUNS_MAX_W) return false;
+    // one pass over the pieces per column: with several columns the delta kernel (one pass) wins
+    if (M >= COLS_KERNEL_MIN || (M > 1 && !forced)) return false;
+    bool exact = false;
+    RunArgs b = make_run_args(c.sp->windows, W, c.d_windows, exact);
+    if (!exact) return false;  // the kernel is arithmetic on uniform edges only
+    (void) forced;
+    Arena &A = P.arena;
+    ensure_piece_positions(P, c.s);
+    // copies: reductions to one address serialise in L2; 128 measured as good as 1024 on C2
+    uint32_t copies = 128;
+    if (const char *e = getenv("TSKB_RUN_COPIES")) copies = (uint32_t) std::max(1, atoi(e));  // experiments
+    while (copies > 1 && (size_t) copies * (2 * (size_t) W + 1) * sizeof(double) > (size_t(16) << 20)) copies >>= 1;
+    uint32_t pow2 = 1;
+    while (pow2 * 2 <= copies) pow2 *= 2;
+    copies = pow2;
+    const uint32_t block = 2 * W + 1;
+    double *bins = A.get<double>((size_t) copies * block);
+    double *RC = A.get<double>(block);
+    b.clip = !(c.sp->windows[0] <= P.range_left && c.sp->windows[W] >= P.range_right);
+    b.bins = bins; b.ncols = 1; b.copy_mask = copies - 1;
+    launch_sweep<V>(c, pval);
+    TSKB_CK(cudaEventRecord(P.ev[2], c.s));
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P.device);
+    auto kern = k_branch_summary_runs<STAT, V>;
+    const size_t smem = 0;
+    TSKB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RUN_TB, smem));
+    int mult = std::max(per_sm, 1);
+    if (const char *e = getenv("TSKB_RUN_GRID_MULT")) mult = std::max(1, atoi(e));  // experiments
+    const uint32_t nblocks = (P.npp / RUN_IPT + RUN_TB - 1) / RUN_TB;
+    for (uint32_t m = 0; m < M; m++) {
+        TSKB_CK(cudaMemsetAsync(bins, 0, (size_t) copies * block * sizeof(double), c.s));
+        kern<<<std::min<uint32_t>(nblocks, (uint32_t) (sms * mult)), RUN_TB, smem, c.s>>>(P.npp, P.q_x0.p, P.q_x1.p,
+            P.q_bl.p, pval, c.sumP, totals, c.sumP.cols, m, b);
+        TSKB_CK_LAUNCH();
+        c.launches++;
+        if (m == 0) TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+        k_runs_reduce<<<(block + 31) / 32, 1024, 0, c.s>>>(bins, block, copies, RC);
+        k_runs_finalize<<<1, 32, 0, c.s>>>(RC, c.d_windows, W, 1, m, M,
+            (c.sp->options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0, c.d_result);
+        TSKB_CK_LAUNCH();
+        c.launches += 2;
+    }
+    TSKB_CK(cudaEventRecord(P.ev[4], c.s));
+    return true;
+}
+
 template <int STAT, class V>
 void run_branch(CallCtx &c, V *pval, V totals) {
+    if (run_branch_runs<STAT, V>(c, pval, totals)) return;
     if (run_branch_bins<STAT, V>(c, pval, totals)) return;
     const Plan &P = *c.P;
     const uint32_t M = c.sp->M;
@@ -1708,6 +2129,59 @@ void run_branch(CallCtx &c, V *pval, V totals) {
     }
     uint32_t mc = (uint32_t) std::min<size_t>(M, std::max<size_t>(1, budget / col_bytes));
     if (by_cols) mc = std::min<uint32_t>(mc, 32);
+    // window runs instead of per-breakpoint deltas: finite summaries, bins of a 32-column pass within 64 MB
+    const bool pos_runs = by_pos && c.sumP.skip_zero_bl && P.T > 0 && c.sp->W > 0
+                          && (2 * (size_t) c.sp->W + 1) * std::min<uint32_t>(M, 32) * sizeof(double) <= (size_t(64) << 20)
+                          && !(cols_variant != nullptr && cols_variant[0] == 'd');
+    if (pos_runs) {
+        ensure_summary_order(P, c.s);
+        const uint32_t W = c.sp->W;
+        const uint32_t ncmax = std::min<uint32_t>(M, 32);
+        const size_t block_max = (2 * (size_t) W + 1) * ncmax;
+        uint32_t copies = 64;
+        if (const char *e = getenv("TSKB_RUN_COPIES")) copies = (uint32_t) std::max(1, atoi(e));  // experiments
+        while (copies > 1 && copies * block_max * sizeof(double) > (size_t(64) << 20)) copies >>= 1;
+        uint32_t pow2 = 1;
+        while (pow2 * 2 <= copies) pow2 *= 2;
+        copies = pow2;
+        double *bins = A.get<double>(copies * block_max);
+        double *RC = A.get<double>(block_max);
+        bool exact = false;
+        RunArgs b = make_run_args(c.sp->windows, W, c.d_windows, exact);
+        b.bins = bins; b.copy_mask = copies - 1;
+        const uint32_t nchunks = (P.nsp + BYPOS_CHUNK - 1) / BYPOS_CHUNK;
+        // concurrent warps far apart along the genome: a multiplier coprime to the number of chunks
+        uint32_t mul = std::max<uint32_t>(1, (uint32_t) (nchunks * 0.6180339887) | 1u);
+        auto gcd = [](uint32_t x, uint32_t y) { while (y) { const uint32_t t = x % y; x = y; y = t; } return x; };
+        while (nchunks > 1 && gcd(mul, nchunks) != 1) mul += 2;
+        if (getenv("TSKB_RUN_SEQUENTIAL") != nullptr || nchunks <= 1) mul = 1;  // experiments
+        b.chunk_mul = mul;
+        launch_sweep<V>(c, pval);
+        TSKB_CK(cudaEventRecord(P.ev[2], c.s));
+        for (uint32_t m0 = 0; m0 < M; m0 += 32) {
+            const uint32_t nc = std::min(M, m0 + 32) - m0;
+            const uint32_t block = (2 * W + 1) * nc;
+            b.ncols = nc;
+            TSKB_CK(cudaMemsetAsync(bins, 0, (size_t) copies * block * sizeof(double), c.s));
+            if (P.nsp > 0) {
+                uint32_t CP = 1;
+                while (CP < nc) CP <<= 1;  // lanes per piece: the columns rounded up to a power of two
+                k_branch_summary_bypos_runs<STAT, V><<<grid_for((size_t) nchunks * 32, TB), TB, 0, c.s>>>(P.nsp,
+                    P.so_slot.p, P.so_bp0.p, P.so_bp1.p, P.so_bl.p, P.bp_pos.p, pval, c.sumP, totals, c.sumP.cols, m0,
+                    nc, CP, b, exact ? 1 : 0, nchunks);
+                TSKB_CK_LAUNCH();
+                c.launches++;
+            }
+            if (m0 == 0) TSKB_CK(cudaEventRecord(P.ev[3], c.s));
+            k_runs_reduce<<<(block + 31) / 32, 1024, 0, c.s>>>(bins, block, copies, RC);
+            k_runs_finalize<<<grid_for((size_t) nc * 32, TB), TB, 0, c.s>>>(RC, c.d_windows, W, nc, m0, M,
+                (c.sp->options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0, c.d_result);
+            TSKB_CK_LAUNCH();
+            c.launches += 2;
+        }
+        TSKB_CK(cudaEventRecord(P.ev[4], c.s));
+        return;
+    }
     if (by_pos) {
         ensure_summary_order(P, c.s);
         double *Dp = A.get<double>((size_t) mc * Tp1);  // [breakpoint][column] deltas
