@@ -132,7 +132,7 @@ def measured_traffic(kernel):
         return None
     d = json.load(open(p))
     for key in {"sweep": ("k_sweep<SVec<int, 1>>",),
-                "summary": ("k_branch_summary_c4<0, SVec<int, 1>>", "k_branch_summary<0, SVec<int, 1>>")
+                "summary": ("k_branch_summary_runs<0, SVec<int, 1>>", "k_branch_summary<0, SVec<int, 1>>")
                 }.get(kernel, ()):
         if key in d:
             return d[key]
@@ -816,6 +816,7 @@ def run_c3(args):
     outs = {nm: torch.empty((W, len(sizes) if ix is None else len(ix)), dtype=torch.float64, device=dev)
             for nm, ix in calls}
     phase = {}
+    kphase = {}
     coll_ev = []
     coll_wall = [0.0]
     exchange = None
@@ -831,6 +832,7 @@ def run_c3(args):
             es = ll.engine_stats()
             ms += es["last_call_ms"]
             phase[nm] = phase.get(nm, 0.0) + es["last_call_ms"]
+            kphase[nm] = kphase.get(nm, np.zeros(6)) + np.array(es["last_kernel_ms"][:6])
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             if exchange is not None:   # host-synchronous, on the engine's stream
@@ -860,6 +862,7 @@ def run_c3(args):
         step()
     collective_ms()
     phase.clear()
+    kphase.clear()
     sampler = ClockSampler(local, interval_ms=250)  # steps last 0.03-0.3 s: a few samples per step
     if rank == 0:
         sampler.start()
@@ -916,6 +919,9 @@ def run_c3(args):
                                 else "NCCL all_reduce")),
                 "per_rank_plan_bytes_edge_diffs_engine_ms": per_rank,
                 "ms_per_step_by_statistic": {k: v / args.steps for k, v in phase.items()},
+                "phases_ms_by_statistic_rank0": {
+                    k: dict(zip(["weights", "sweep", "summary", "integrate", "idle", "result"],
+                                [round(float(x) / args.steps, 3) for x in v])) for k, v in kphase.items()},
                 "collective_ms_per_step": coll_ms / args.steps, "wall_ms_per_step": wall / args.steps * 1e3,
                 "engine_ms_per_step_rank0": engine_ms / args.steps,
                 "generate_s": gen_s, "concat_s": concat_s, "stage_s": stage_s, "levels": st["num_levels"],

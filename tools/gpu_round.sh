@@ -12,7 +12,7 @@ tail -3 $OUT/pytest_gpu.log
 python bench.py --steps 20 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
 head -c 3000 $OUT/bench.json; echo
 # A/B of the branch-summary variants (same box, same plan; device-timed, no CPU legs)
-for v in "lane:" "hack_no_head_reds:TSKB_SUM_HACK=1"; do
+for v in "runs_default:" "lane:TSKB_SUM_VARIANT=lane" "c4:TSKB_SUM_VARIANT=c4"; do
     name=${v%%:*}; envs=${v#*:}
     if [ -n "$envs" ] && [[ "$envs" == TSKB_LIB=* ]] && [ ! -f "${envs#TSKB_LIB=}" ]; then continue; fi
     env $envs python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ab_$name.json 2> $OUT/ab_$name.err
@@ -85,14 +85,14 @@ if [ "$MODE" == "full" ]; then
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref exit $?"
 cat $OUT/bench_ref.json
 timeout 300 python tools/piece_stats.py > $OUT/piece_stats.txt 2>&1; tail -12 $OUT/piece_stats.txt
-KREGEX='regex:(k_set_weights|k_sweep|k_branch_summary|k_window|k_site_summary|DeviceScan)'
+KREGEX='regex:(k_set_weights|k_sweep|k_branch_summary|k_runs|k_window|k_site_summary|DeviceScan)'
 TSKB_BENCH_BLOCKS=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 600 \
     --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_launch.log 2>&1
 echo "ncu launches exit $?"
-TSKB_BENCH_BLOCKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_branch_summary -s 6 -c 1 \
+TSKB_BENCH_BLOCKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_branch_summary -s 6 -c 2 \
     -o $OUT/prof_summary -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_sum.log 2>&1
 echo "ncu summary exit $?"
-TSKB_BENCH_BLOCKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 6 -c 1 \
+TSKB_BENCH_BLOCKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 6 -c 2 \
     -o $OUT/prof_sweep -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_prop.log 2>&1
 echo "ncu sweep exit $?"
 fi

@@ -2064,8 +2064,9 @@ bool run_branch_runs(CallCtx &c, V *pval, V totals) {
     (void) forced;
     Arena &A = P.arena;
     ensure_piece_positions(P, c.s);
-    // copies: reductions to one address serialise in L2; 128 measured as good as 1024 on C2
-    uint32_t copies = 128;
+    // copies: reductions that meet at one address serialise in L2.  C2, summary + reduce per step
+    // (profiles/r2x): 32 copies 0.96 ms, 128 0.89, 512 0.87, 1024 0.87
+    uint32_t copies = 1024;
     if (const char *e = getenv("TSKB_RUN_COPIES")) copies = (uint32_t) std::max(1, atoi(e));  // experiments
     while (copies > 1 && (size_t) copies * (2 * (size_t) W + 1) * sizeof(double) > (size_t(16) << 20)) copies >>= 1;
     uint32_t pow2 = 1;
