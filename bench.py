@@ -816,6 +816,7 @@ def run_c3(args):
     outs = {nm: torch.empty((W, len(sizes) if ix is None else len(ix)), dtype=torch.float64, device=dev)
             for nm, ix in calls}
     phase = {}
+    worst = {}
     kphase = {}
     coll_ev = []
     coll_wall = [0.0]
@@ -832,6 +833,7 @@ def run_c3(args):
             es = ll.engine_stats()
             ms += es["last_call_ms"]
             phase[nm] = phase.get(nm, 0.0) + es["last_call_ms"]
+            worst[nm] = max(worst.get(nm, 0.0), es["last_call_ms"])
             kphase[nm] = kphase.get(nm, np.zeros(6)) + np.array(es["last_kernel_ms"][:6])
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -862,6 +864,7 @@ def run_c3(args):
         step()
     collective_ms()
     phase.clear()
+    worst.clear()
     kphase.clear()
     sampler = ClockSampler(local, interval_ms=250)  # steps last 0.03-0.3 s: a few samples per step
     if rank == 0:
@@ -919,6 +922,7 @@ def run_c3(args):
                                 else "NCCL all_reduce")),
                 "per_rank_plan_bytes_edge_diffs_engine_ms": per_rank,
                 "ms_per_step_by_statistic": {k: v / args.steps for k, v in phase.items()},
+                "slowest_call_ms_by_statistic_rank0": {k: round(v, 3) for k, v in worst.items()},
                 "phases_ms_by_statistic_rank0": {
                     k: dict(zip(["weights", "sweep", "summary", "integrate", "idle", "result"],
                                 [round(float(x) / args.steps, 3) for x in v])) for k, v in kphase.items()},

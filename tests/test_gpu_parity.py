@@ -465,6 +465,22 @@ def test_genome_range_shards_sum_to_whole(wf_small, engines):
         assert np.allclose(acc, whole, rtol=1e-11)
         assert close(whole, o.stat("divergence", [s[:100], s[100:]], idx, windows=w, mode=mode,
                                    span_normalise=False))
+    # many columns and more windows (the window-run kernels keep bins only for the windows a range meets)
+    sets8 = [s[25 * i: 25 * i + 22] for i in range(8)]
+    sizes8, flat8 = sets_args(sets8)
+    pairs = np.array([(i, j) for i in range(8) for j in range(i + 1, 8)], dtype=np.int32)
+    for w in (np.linspace(0, L, 41), np.array([0.0, 500.0, 21000.5, 30000.0, 77777.0, 90000.0, L])):
+        whole = ll.divergence(sizes8, flat8, pairs, windows=w, mode="branch", span_normalise=False)
+        one = ll.diversity(sizes8[:1], flat8[:22], windows=w, mode="branch", span_normalise=False)
+        acc, acc1 = np.zeros_like(whole), np.zeros_like(one)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            part = LLTreeSequence(wf_small, genome_range=(a, b))
+            acc += part.divergence(sizes8, flat8, pairs, windows=w, mode="branch", span_normalise=False)
+            acc1 += part.diversity(sizes8[:1], flat8[:22], windows=w, mode="branch", span_normalise=False)
+        assert np.allclose(acc, whole, rtol=1e-11)
+        assert np.allclose(acc1, one, rtol=1e-11)
+        assert close(whole, o.stat("divergence", sets8, pairs, windows=w, mode="branch", span_normalise=False))
+        assert close(one, o.stat("diversity", sets8[:1], windows=w, mode="branch", span_normalise=False))
 
 
 def test_relatedness_vector_genome_range_shards_sum_to_whole(wf_small, engines):

@@ -767,7 +767,8 @@ struct RunArgs {
     double w0, inv_width;   // roughly uniform windows: index guess (x - w0) * inv_width, then corrected
     int uniform;
     double step, inv_step, wlast;  // exactly uniform windows: edge i = w0 + i * step (i < W), wlast (i = W)
-    double *bins;           // [copies][(2 W + 1) x ncols]: R[w][col] then C[w][col] (C has W + 1 rows)
+    uint32_t wlo, Wl;       // the windows this engine's genome range can touch: [wlo, wlo + Wl); bins cover those
+    double *bins;           // [copies][(2 Wl + 1) x ncols]: R[w - wlo][col] then C[w - wlo][col] (C has Wl + 1 rows)
     uint32_t ncols;         // columns per bin row
     uint32_t copy_mask;     // copies - 1 (a power of two)
     int clip;               // the windows do not cover the genome: clip the pieces
@@ -843,8 +844,8 @@ __global__ void __launch_bounds__(RUN_TB, 3) k_branch_summary_runs(uint32_t npp,
     const double first_edge = b.w0, last_edge = b.wlast;
     const ColP col = cols[m];
     const uint32_t copy = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) & b.copy_mask;
-    double *gR = b.bins + (size_t) copy * (2 * (size_t) b.W + 1);
-    double *gC = gR + b.W;
+    double *gR = b.bins + (size_t) copy * (2 * (size_t) b.Wl + 1) - b.wlo;   // indexed by the window itself
+    double *gC = gR + b.Wl;
     // npp is a multiple of PROP_TILE = 1024: whole groups, no bounds checks inside a group
     const uint32_t ngroups = npp / RUN_IPT;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -912,30 +913,39 @@ __global__ void __launch_bounds__(1024) k_runs_reduce(const double *__restrict__
     }
 }
 
-// window w of column c: R[w][c] + span(w) x (C[0][c] + ... + C[w][c]); one warp per column
-__global__ void k_runs_finalize(const double *__restrict__ RC, const double *__restrict__ windows, uint32_t W,
-    uint32_t ncols, uint32_t m0, uint32_t M, int span_normalise, double *result) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= ncols) return;
-    const double *R = RC + c, *C = RC + (size_t) W * ncols + c;
-    double run = 0.0;
-    for (uint32_t base = 0; base < W; base += 32) {
-        const uint32_t w = base + lane;
-        double v = w < W ? C[(size_t) w * ncols] : 0.0;
+// window w of column c: R[w][c] + span(w) x (C[wlo][c] + ... + C[w][c]) for the windows [wlo, wlo + Wl) the bins
+// cover, zero elsewhere; one CTA of 1024 threads per column: a thread sums a run of windows, the CTA scans
+// the run totals, the thread walks its run again
+__global__ void __launch_bounds__(1024) k_runs_finalize(const double *__restrict__ RC, const double *__restrict__ windows,
+    uint32_t W, uint32_t wlo, uint32_t Wl, uint32_t ncols, uint32_t m0, uint32_t M, int span_normalise, double *result) {
+    __shared__ double warp_tot[32];
+    const uint32_t c = blockIdx.x, t = threadIdx.x, lane = t & 31u, wp = t >> 5;
+    const double *R = RC + c, *C = RC + (size_t) Wl * ncols + c;
+    for (uint32_t w = t; w < W; w += blockDim.x) {
+        if (w < wlo || w >= wlo + Wl) result[(size_t) w * M + m0 + c] = 0.0;
+    }
+    const uint32_t per = (Wl + blockDim.x - 1) / blockDim.x;
+    const uint32_t i0 = min(Wl, t * per), i1 = min(Wl, i0 + per);
+    double sum = 0.0;
+    for (uint32_t i = i0; i < i1; i++) sum += C[(size_t) i * ncols];
+    double v = sum;  // inclusive scan over the threads
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const double u = __shfl_up_sync(0xffffffffu, v, d);
-            if ((int) lane >= d) v += u;
-        }
-        const double S = run + v;
-        run += __shfl_sync(0xffffffffu, v, 31);
-        if (w < W) {
-            const double span = windows[w + 1] - windows[w];
-            double r = R[(size_t) w * ncols] + span * S;
-            if (span_normalise) r /= span;
-            result[(size_t) w * M + m0 + c] = r;
-        }
+    for (int d = 1; d < 32; d <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, v, d);
+        if ((int) lane >= d) v += u;
+    }
+    if (lane == 31u) warp_tot[wp] = v;
+    __syncthreads();
+    double before = 0.0;
+    for (uint32_t q = 0; q < wp; q++) before += warp_tot[q];
+    double S = before + v - sum;  // prefix of C before this thread's run
+    for (uint32_t i = i0; i < i1; i++) {
+        S += C[(size_t) i * ncols];
+        const uint32_t w = wlo + i;
+        const double span = windows[w + 1] - windows[w];
+        double r = R[(size_t) i * ncols] + span * S;
+        if (span_normalise) r /= span;
+        result[(size_t) w * M + m0 + c] = r;
     }
 }
 
@@ -1182,9 +1192,9 @@ __global__ void __launch_bounds__(TB) k_branch_summary_bypos_runs(uint32_t nsp,
         }
         col.i = 0; col.j = 1; col.k = 2; col.l = 3;
     }
-    const size_t block = (2 * (size_t) b.W + 1) * ncols;
-    double *gR = b.bins + (size_t) (warp & b.copy_mask) * block + cl;   // R[w * ncols + column]
-    double *gC = gR + (size_t) b.W * ncols;                             // C[w * ncols + column]
+    const size_t block = (2 * (size_t) b.Wl + 1) * ncols;
+    double *gR = b.bins + (size_t) (warp & b.copy_mask) * block + cl - (size_t) b.wlo * ncols;   // R[w * ncols + column]
+    double *gC = gR + (size_t) b.Wl * ncols;                                                      // C[w * ncols + column]
     double acc = 0.0;
     uint32_t wc = RUN_DEAD;    // window the register sum belongs to (group-uniform)
     for (uint32_t base = c0; base < c1; base += 32) {
@@ -2019,8 +2029,19 @@ bool run_branch_bins(CallCtx &c, V *pval, V totals) {
 
 // window description for the run kernels; exact = the windows are np.linspace-like: every edge is
 // w0 + i * step bit for bit (two roundings, as on the device), the last one the stop value
-RunArgs make_run_args(const double *w, uint32_t W, const double *d_windows, bool &exact) {
+RunArgs make_run_args(const double *w, uint32_t W, const double *d_windows, bool &exact, double range_left,
+    double range_right) {
     RunArgs b = {};
+    {
+        // windows meeting [range_left, range_right], with one window of margin on either side (the
+        // arithmetic window lookup may name a neighbour within a few ulp of an edge)
+        const uint32_t i0 = (uint32_t) (std::upper_bound(w, w + W + 1, range_left) - w);   // first edge > left
+        const uint32_t i1 = (uint32_t) (std::lower_bound(w, w + W + 1, range_right) - w);  // first edge >= right
+        const uint32_t lo = i0 >= 2 ? i0 - 2 : 0;
+        const uint32_t hi = std::min<uint32_t>(W, i1 + 1);
+        b.wlo = std::min(lo, W - 1);
+        b.Wl = std::max<uint32_t>(hi, b.wlo + 1) - b.wlo;
+    }
     b.windows = d_windows; b.W = W; b.w0 = w[0]; b.inv_width = (double) W / (w[W] - w[0]); b.uniform = 1;
     for (uint32_t i = 0; i <= W && b.uniform; i++) {
         const double ideal = w[0] + (w[W] - w[0]) * ((double) i / (double) W);
@@ -2059,7 +2080,7 @@ bool run_branch_runs(CallCtx &c, V *pval, V totals) {
     // one pass over the pieces per column: with several columns the delta kernel (one pass) wins
     if (M >= COLS_KERNEL_MIN || (M > 1 && !forced)) return false;
     bool exact = false;
-    RunArgs b = make_run_args(c.sp->windows, W, c.d_windows, exact);
+    RunArgs b = make_run_args(c.sp->windows, W, c.d_windows, exact, P.range_left, P.range_right);
     if (!exact) return false;  // the kernel is arithmetic on uniform edges only
     (void) forced;
     Arena &A = P.arena;
@@ -2068,11 +2089,11 @@ bool run_branch_runs(CallCtx &c, V *pval, V totals) {
     // (profiles/r2x): 32 copies 0.96 ms, 128 0.89, 512 0.87, 1024 0.87
     uint32_t copies = 1024;
     if (const char *e = getenv("TSKB_RUN_COPIES")) copies = (uint32_t) std::max(1, atoi(e));  // experiments
-    while (copies > 1 && (size_t) copies * (2 * (size_t) W + 1) * sizeof(double) > (size_t(16) << 20)) copies >>= 1;
     uint32_t pow2 = 1;
     while (pow2 * 2 <= copies) pow2 *= 2;
     copies = pow2;
-    const uint32_t block = 2 * W + 1;
+    const uint32_t block = 2 * b.Wl + 1;
+    while (copies > 1 && (size_t) copies * block * sizeof(double) > (size_t(16) << 20)) copies >>= 1;
     double *bins = A.get<double>((size_t) copies * block);
     double *RC = A.get<double>(block);
     b.clip = !(c.sp->windows[0] <= P.range_left && c.sp->windows[W] >= P.range_right);
@@ -2095,7 +2116,7 @@ bool run_branch_runs(CallCtx &c, V *pval, V totals) {
         c.launches++;
         if (m == 0) TSKB_CK(cudaEventRecord(P.ev[3], c.s));
         k_runs_reduce<<<(block + 31) / 32, 1024, 0, c.s>>>(bins, block, copies, RC);
-        k_runs_finalize<<<1, 32, 0, c.s>>>(RC, c.d_windows, W, 1, m, M,
+        k_runs_finalize<<<1, 1024, 0, c.s>>>(RC, c.d_windows, W, b.wlo, b.Wl, 1, m, M,
             (c.sp->options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0, c.d_result);
         TSKB_CK_LAUNCH();
         c.launches += 2;
@@ -2119,10 +2140,15 @@ void run_branch(CallCtx &c, V *pval, V totals) {
     const bool by_cols = M >= cols_min && getenv("TSKB_NO_COLS_KERNEL") == nullptr;
     const char *cols_variant = getenv("TSKB_COLS_VARIANT");  // experiments: "old" = processing-order walk
     const bool by_pos = by_cols && !(cols_variant != nullptr && cols_variant[0] == 'o');
+    // window runs instead of per-breakpoint deltas: finite summaries, bins of a 32-column pass within 64 MB
+    const bool pos_runs = by_pos && c.sumP.skip_zero_bl && P.T > 0 && c.sp->W > 0
+                          && (2 * (size_t) c.sp->W + 1) * std::min<uint32_t>(M, 32) * sizeof(double) <= (size_t(64) << 20)
+                          && !(cols_variant != nullptr && cols_variant[0] == 'd');
     size_t budget = DELTA_BUDGET;
-    if (by_pos) {
+    if (by_pos && !pos_runs) {
         // the deltas of a column group may be large (their hot front stays in L2): up to a third of
-        // the free memory, so that all columns go through in as few walks over the pieces as possible
+        // the free memory, so that all columns go through in as few walks over the pieces as possible.
+        // (cudaMemGetInfo costs milliseconds in a process that holds tens of GB and peer mappings: only here.)
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
             budget = std::max(budget, std::min<size_t>((free_b + A.cap) / 3, size_t(24) << 30));
@@ -2130,15 +2156,13 @@ void run_branch(CallCtx &c, V *pval, V totals) {
     }
     uint32_t mc = (uint32_t) std::min<size_t>(M, std::max<size_t>(1, budget / col_bytes));
     if (by_cols) mc = std::min<uint32_t>(mc, 32);
-    // window runs instead of per-breakpoint deltas: finite summaries, bins of a 32-column pass within 64 MB
-    const bool pos_runs = by_pos && c.sumP.skip_zero_bl && P.T > 0 && c.sp->W > 0
-                          && (2 * (size_t) c.sp->W + 1) * std::min<uint32_t>(M, 32) * sizeof(double) <= (size_t(64) << 20)
-                          && !(cols_variant != nullptr && cols_variant[0] == 'd');
     if (pos_runs) {
         ensure_summary_order(P, c.s);
         const uint32_t W = c.sp->W;
+        bool exact = false;
+        RunArgs b = make_run_args(c.sp->windows, W, c.d_windows, exact, P.range_left, P.range_right);
         const uint32_t ncmax = std::min<uint32_t>(M, 32);
-        const size_t block_max = (2 * (size_t) W + 1) * ncmax;
+        const size_t block_max = (2 * (size_t) b.Wl + 1) * ncmax;
         uint32_t copies = 64;
         if (const char *e = getenv("TSKB_RUN_COPIES")) copies = (uint32_t) std::max(1, atoi(e));  // experiments
         while (copies > 1 && copies * block_max * sizeof(double) > (size_t(64) << 20)) copies >>= 1;
@@ -2147,8 +2171,6 @@ void run_branch(CallCtx &c, V *pval, V totals) {
         copies = pow2;
         double *bins = A.get<double>(copies * block_max);
         double *RC = A.get<double>(block_max);
-        bool exact = false;
-        RunArgs b = make_run_args(c.sp->windows, W, c.d_windows, exact);
         b.bins = bins; b.copy_mask = copies - 1;
         const uint32_t nchunks = (P.nsp + BYPOS_CHUNK - 1) / BYPOS_CHUNK;
         // concurrent warps far apart along the genome: a multiplier coprime to the number of chunks
@@ -2161,7 +2183,7 @@ void run_branch(CallCtx &c, V *pval, V totals) {
         TSKB_CK(cudaEventRecord(P.ev[2], c.s));
         for (uint32_t m0 = 0; m0 < M; m0 += 32) {
             const uint32_t nc = std::min(M, m0 + 32) - m0;
-            const uint32_t block = (2 * W + 1) * nc;
+            const uint32_t block = (2 * b.Wl + 1) * nc;
             b.ncols = nc;
             TSKB_CK(cudaMemsetAsync(bins, 0, (size_t) copies * block * sizeof(double), c.s));
             if (P.nsp > 0) {
@@ -2175,7 +2197,7 @@ void run_branch(CallCtx &c, V *pval, V totals) {
             }
             if (m0 == 0) TSKB_CK(cudaEventRecord(P.ev[3], c.s));
             k_runs_reduce<<<(block + 31) / 32, 1024, 0, c.s>>>(bins, block, copies, RC);
-            k_runs_finalize<<<grid_for((size_t) nc * 32, TB), TB, 0, c.s>>>(RC, c.d_windows, W, nc, m0, M,
+            k_runs_finalize<<<nc, 1024, 0, c.s>>>(RC, c.d_windows, W, b.wlo, b.Wl, nc, m0, M,
                 (c.sp->options & TSKB_STAT_SPAN_NORMALISE) ? 1 : 0, c.d_result);
             TSKB_CK_LAUNCH();
             c.launches += 2;
