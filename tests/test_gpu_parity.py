@@ -101,10 +101,13 @@ def test_span_normalise_off_and_many_windows(wf_small, engines, mode):
     ll, o = engines
     s = wf_small.samples
     sizes, flat = sets_args([s])
-    windows = np.linspace(0, wf_small.sequence_length, 20001)  # windows far smaller than trees
-    got = ll.diversity(sizes, flat, windows=windows, mode=mode, span_normalise=False)
-    want = o.stat("diversity", [s], windows=windows, mode=mode, span_normalise=False)
-    assert close(got, want)
+    # windows far smaller than trees: 20 000 (window runs: most pieces cover many windows entirely) and
+    # 40 000 (past the limit of the window-run bins: per-breakpoint deltas)
+    for count in (20001, 40001):
+        windows = np.linspace(0, wf_small.sequence_length, count)
+        got = ll.diversity(sizes, flat, windows=windows, mode=mode, span_normalise=False)
+        want = o.stat("diversity", [s], windows=windows, mode=mode, span_normalise=False)
+        assert close(got, want), count
 
 
 def test_overlapping_sample_sets_and_eight_sets(wf_small, engines):

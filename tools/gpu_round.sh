@@ -25,11 +25,11 @@ except Exception as e:
     print(sys.argv[2], "failed", e)
 EOF
 done
-if [ -x tools/mb/red_types ]; then timeout 120 tools/mb/red_types > $OUT/red_types.txt 2>&1; cat $OUT/red_types.txt; fi
+if [ -n "$FULLER" ] && [ -x tools/mb/red_types ]; then timeout 120 tools/mb/red_types > $OUT/red_types.txt 2>&1; cat $OUT/red_types.txt; fi
 # the other config shapes (C1, C3 shape on the C2 ARG, C5), and the many-column path old vs new
 timeout 600 python tools/probe_configs.py > $OUT/probe_configs.json 2> $OUT/probe_configs.err; echo "probe exit $?"
-TSKB_COLS_VARIANT=old TSKB_SUM_VARIANT=lane timeout 600 python tools/probe_configs.py > $OUT/probe_configs_oldcols.json 2> $OUT/probe_configs_oldcols.err
-TSKB_COLS_MIN=2 timeout 600 python tools/probe_configs.py > $OUT/probe_configs_colsmin2.json 2> $OUT/probe_configs_colsmin2.err
+[ -n "$FULLER" ] && TSKB_COLS_VARIANT=old TSKB_SUM_VARIANT=lane timeout 600 python tools/probe_configs.py > $OUT/probe_configs_oldcols.json 2> $OUT/probe_configs_oldcols.err
+[ -n "$FULLER" ] && TSKB_COLS_MIN=2 timeout 600 python tools/probe_configs.py > $OUT/probe_configs_colsmin2.json 2> $OUT/probe_configs_colsmin2.err
 python - $OUT <<'EOF2'
 import json, sys
 for f in ("probe_configs.json", "probe_configs_oldcols.json", "probe_configs_colsmin2.json"):
@@ -84,7 +84,7 @@ fi
 if [ "$MODE" == "full" ]; then
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref exit $?"
 cat $OUT/bench_ref.json
-timeout 300 python tools/piece_stats.py > $OUT/piece_stats.txt 2>&1; tail -12 $OUT/piece_stats.txt
+[ -n "$FULLER" ] && (timeout 300 python tools/piece_stats.py > $OUT/piece_stats.txt 2>&1; tail -12 $OUT/piece_stats.txt)
 KREGEX='regex:(k_set_weights|k_sweep|k_branch_summary|k_runs|k_window|k_site_summary|DeviceScan)'
 TSKB_BENCH_BLOCKS=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 600 \
     --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_launch.log 2>&1
@@ -95,5 +95,8 @@ echo "ncu summary exit $?"
 TSKB_BENCH_BLOCKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 6 -c 2 \
     -o $OUT/prof_sweep -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_prop.log 2>&1
 echo "ncu sweep exit $?"
+timeout 900 python bench.py --config c3 --steps 6 --warmup 2 > $OUT/c3_n1.json 2> $OUT/c3_n1.err; echo "c3 N=1 exit $?"
+head -c 2600 $OUT/c3_n1.json; echo; tail -3 $OUT/c3_n1.err
+timeout 300 python tools/probe_c3shape.py default TSKB_COLS_VARIANT=d > $OUT/c3shape.json 2> $OUT/c3shape.err; cat $OUT/c3shape.json
 fi
 ls -la $OUT

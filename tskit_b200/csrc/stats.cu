@@ -2062,7 +2062,7 @@ RunArgs make_run_args(const double *w, uint32_t W, const double *d_windows, bool
     return b;
 }
 
-constexpr uint32_t RUNS_MAX_W = 4096;   // window edges in shared memory, replicated bins in L2
+constexpr uint32_t RUNS_MAX_WL = 32768;  // windows met by the engine's range: at least 32 copies of the bins in 16 MB
 
 // Window runs in registers: finite summaries, few columns, windows few enough.  Returns false when the
 // call does not qualify (the delta formulation runs instead).
@@ -2076,12 +2076,13 @@ bool run_branch_runs(CallCtx &c, V *pval, V totals) {
     const char *variant = getenv("TSKB_SUM_VARIANT");
     const bool forced = variant != nullptr && variant[0] == 'r';
     if (variant != nullptr && !forced) return false;
-    if (!c.sumP.skip_zero_bl || P.npp == 0 || P.T == 0 || W == 0 || W > RUNS_MAX_W) return false;
+    if (!c.sumP.skip_zero_bl || P.npp == 0 || P.T == 0 || W == 0) return false;
     // one pass over the pieces per column: with several columns the delta kernel (one pass) wins
     if (M >= COLS_KERNEL_MIN || (M > 1 && !forced)) return false;
     bool exact = false;
     RunArgs b = make_run_args(c.sp->windows, W, c.d_windows, exact, P.range_left, P.range_right);
     if (!exact) return false;  // the kernel is arithmetic on uniform edges only
+    if (b.Wl > RUNS_MAX_WL) return false;  // too few copies of the bins would fit L2: the deltas scale better
     (void) forced;
     Arena &A = P.arena;
     ensure_piece_positions(P, c.s);
