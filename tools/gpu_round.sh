@@ -12,7 +12,7 @@ tail -3 $OUT/pytest_gpu.log
 python bench.py --steps 20 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
 head -c 3000 $OUT/bench.json; echo
 # A/B of the branch-summary variants (same box, same plan; device-timed, no CPU legs)
-for v in "runs_default:" "lane:TSKB_SUM_VARIANT=lane" "c4:TSKB_SUM_VARIANT=c4"; do
+[ "$MODE" == "final" ] || for v in "runs_default:" "lane:TSKB_SUM_VARIANT=lane" "c4:TSKB_SUM_VARIANT=c4"; do
     name=${v%%:*}; envs=${v#*:}
     if [ -n "$envs" ] && [[ "$envs" == TSKB_LIB=* ]] && [ ! -f "${envs#TSKB_LIB=}" ]; then continue; fi
     env $envs python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ab_$name.json 2> $OUT/ab_$name.err
@@ -27,7 +27,7 @@ EOF
 done
 if [ -n "$FULLER" ] && [ -x tools/mb/red_types ]; then timeout 120 tools/mb/red_types > $OUT/red_types.txt 2>&1; cat $OUT/red_types.txt; fi
 # the other config shapes (C1, C3 shape on the C2 ARG, C5), and the many-column path old vs new
-timeout 600 python tools/probe_configs.py > $OUT/probe_configs.json 2> $OUT/probe_configs.err; echo "probe exit $?"
+[ "$MODE" == "final" ] || (timeout 600 python tools/probe_configs.py > $OUT/probe_configs.json 2> $OUT/probe_configs.err; echo "probe exit $?")
 [ -n "$FULLER" ] && TSKB_COLS_VARIANT=old TSKB_SUM_VARIANT=lane timeout 600 python tools/probe_configs.py > $OUT/probe_configs_oldcols.json 2> $OUT/probe_configs_oldcols.err
 [ -n "$FULLER" ] && TSKB_COLS_MIN=2 timeout 600 python tools/probe_configs.py > $OUT/probe_configs_colsmin2.json 2> $OUT/probe_configs_colsmin2.err
 python - $OUT <<'EOF2'
@@ -42,7 +42,7 @@ for f in ("probe_configs.json", "probe_configs_oldcols.json", "probe_configs_col
         print(f, "failed", e)
 EOF2
 # phases of tskb_treeseq_init on C2 (second init in the process: context and modules already loaded)
-TSKB_TIMING=1 python - > $OUT/init_phases.txt 2>&1 <<'EOF'
+[ "$MODE" == "final" ] || TSKB_TIMING=1 python - > $OUT/init_phases.txt 2>&1 <<'EOF'
 import time, bench
 from tskit_b200.lowlevel import LLTreeSequence
 t, W, _ = bench.load_workload("c2")
@@ -81,7 +81,7 @@ if [ "$MODE" == "c3" ]; then
 timeout 1500 python bench.py --config c3 --steps 3 --warmup 1 > $OUT/c3_n1.json 2> $OUT/c3_n1.err; echo "c3 N=1 exit $?"
 head -c 3000 $OUT/c3_n1.json; echo; tail -5 $OUT/c3_n1.err
 fi
-if [ "$MODE" == "full" ]; then
+if [ "$MODE" == "full" ] || [ "$MODE" == "final" ]; then
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref exit $?"
 cat $OUT/bench_ref.json
 [ -n "$FULLER" ] && (timeout 300 python tools/piece_stats.py > $OUT/piece_stats.txt 2>&1; tail -12 $OUT/piece_stats.txt)
@@ -99,4 +99,11 @@ timeout 900 python bench.py --config c3 --steps 6 --warmup 2 > $OUT/c3_n1.json 2
 head -c 2600 $OUT/c3_n1.json; echo; tail -3 $OUT/c3_n1.err
 timeout 300 python tools/probe_c3shape.py default TSKB_COLS_VARIANT=d > $OUT/c3shape.json 2> $OUT/c3shape.err; cat $OUT/c3shape.json
 fi
-ls -la $OUT
+# the .ncu-rep files (60 MB each) do not travel back: their summaries do
+if ls $OUT/*.ncu-rep > /dev/null 2>&1; then
+  python tools/ncu_summary.py $TAG > /dev/null 2>&1
+  mkdir -p $OUT/profiles; cp profiles/${TAG}_* profiles/traffic.json $OUT/profiles/ 2>/dev/null
+  for r in $OUT/*.ncu-rep; do python tools/ncu_sass_hot.py $r > $OUT/profiles/${TAG}_$(basename $r .ncu-rep)_sass_hot.txt 2>/dev/null; done
+  rm -f $OUT/*.ncu-rep
+fi
+ls -la $OUT $OUT/profiles 2>/dev/null

@@ -2079,10 +2079,18 @@ bool run_branch_runs(CallCtx &c, V *pval, V totals) {
     if (!c.sumP.skip_zero_bl || P.npp == 0 || P.T == 0 || W == 0) return false;
     // one pass over the pieces per column: with several columns the delta kernel (one pass) wins
     if (M >= COLS_KERNEL_MIN || (M > 1 && !forced)) return false;
+    {
+        // too many windows in the engine's range for enough copies of the bins in L2: the deltas scale
+        // better (decided before the per-edge exactness check below, which is a host loop over W)
+        const double *w = c.sp->windows;
+        const size_t i0 = std::upper_bound(w, w + W + 1, P.range_left) - w;
+        const size_t i1 = std::lower_bound(w, w + W + 1, P.range_right) - w;
+        if (i1 > i0 + RUNS_MAX_WL) return false;
+    }
     bool exact = false;
     RunArgs b = make_run_args(c.sp->windows, W, c.d_windows, exact, P.range_left, P.range_right);
     if (!exact) return false;  // the kernel is arithmetic on uniform edges only
-    if (b.Wl > RUNS_MAX_WL) return false;  // too few copies of the bins would fit L2: the deltas scale better
+    if (b.Wl > RUNS_MAX_WL + 3) return false;
     (void) forced;
     Arena &A = P.arena;
     ensure_piece_positions(P, c.s);
