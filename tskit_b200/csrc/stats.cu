@@ -758,8 +758,17 @@ __global__ void k_bins_finalize(const double *__restrict__ gP, const double *__r
 // that crosses window edges adds its parts to the first and the last window it meets and +-G to a
 // difference array over the windows it covers entirely (gC).  The bins are replicated (one copy per
 // group of warps: reductions to one address serialise in L2) and summed by k_runs_finalize.
-constexpr int RUN_TB = 256;
-constexpr int RUN_IPT = 8;
+#ifndef TSKB_RUN_TB
+#define TSKB_RUN_TB 256
+#endif
+#ifndef TSKB_RUN_IPT
+#define TSKB_RUN_IPT 8
+#endif
+#ifndef TSKB_RUN_MINB
+#define TSKB_RUN_MINB 3
+#endif
+constexpr int RUN_TB = TSKB_RUN_TB;
+constexpr int RUN_IPT = TSKB_RUN_IPT;   // consecutive pieces per thread (a multiple of 4: 16-byte loads)
 
 struct RunArgs {
     const double *windows;  // [W + 1] (device)
@@ -838,7 +847,7 @@ struct Run8 {
 // measured against the nominal edges, so that they still add up to G x (e - a) exactly and the
 // misplaced part is a few ulp of a base pair long.
 template <int STAT, class V>
-__global__ void __launch_bounds__(RUN_TB, 3) k_branch_summary_runs(uint32_t npp,
+__global__ void __launch_bounds__(RUN_TB, TSKB_RUN_MINB) k_branch_summary_runs(uint32_t npp,
     const double *__restrict__ q_x0, const double *__restrict__ q_x1, const double *__restrict__ q_bl,
     const V *__restrict__ pval, SumP sp, V totals, const ColP *cols, uint32_t m, RunArgs b) {
     const double first_edge = b.w0, last_edge = b.wlast;
