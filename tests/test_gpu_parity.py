@@ -76,8 +76,10 @@ def test_all_statistics_wright_fisher(wf_small, engines, mode, polarised):
 
 @pytest.mark.parametrize("variant", ["lane", "c4", "runs", "bins"])
 def test_branch_summary_kernel_variants(wf_small, engines, monkeypatch, variant):
-    """The default branch summary is the shared-memory window-bin kernel; the per-breakpoint delta
-    kernels (one piece per lane; four pieces per thread) stay selectable and must agree with the oracle."""
+    """The default branch summary of a one-column call with uniform windows is the window-run kernel; the
+    per-breakpoint delta kernels (one piece per lane; four pieces per thread), the window runs for 2-5
+    columns and non-uniform windows (which fall back to the deltas), and the shared-memory window bins
+    stay selectable and must agree with the oracle."""
     ll, o = engines
     s = wf_small.samples
     sets = [s[:50], s[50:120], s[120:]]

@@ -780,8 +780,6 @@ struct RunArgs {
     double *bins;           // [copies][(2 Wl + 1) x ncols]: R[w - wlo][col] then C[w - wlo][col] (C has Wl + 1 rows)
     uint32_t ncols;         // columns per bin row
     uint32_t copy_mask;     // copies - 1 (a power of two)
-    int clip;               // the windows do not cover the genome: clip the pieces
-    int prefetch;           // L2 prefetch of the thread's next group
     uint32_t chunk_mul;     // walk by start position: chunk of warp i = i * chunk_mul mod the number of chunks
 };
 
@@ -808,10 +806,6 @@ __device__ __forceinline__ uint32_t run_window_of(const double *win, const RunAr
         if (left) lo = mid; else hi = mid - 1;
     }
     return lo;
-}
-
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 template <class V>
@@ -2066,8 +2060,6 @@ RunArgs make_run_args(const double *w, uint32_t W, const double *d_windows, bool
         if (e != w[i]) exact = false;
     }
     if (exact && !(w[W] > w[0] + (double) (W - 1) * b.step)) exact = false;
-    b.clip = 1;
-    b.prefetch = getenv("TSKB_RUN_PREFETCH") == nullptr || atoi(getenv("TSKB_RUN_PREFETCH")) != 0;
     return b;
 }
 
@@ -2080,8 +2072,9 @@ bool run_branch_runs(CallCtx &c, V *pval, V totals) {
     const Plan &P = *c.P;
     const uint32_t M = c.sp->M, W = c.sp->W;
     // Default for np.linspace-like windows (the window of a position is arithmetic); other windows run
-    // the delta formulation, which is as fast as this kernel with a window search per piece end
-    // (measured on C2, profiles/r2q: 0.97 vs 0.97 ms per step), unless TSKB_SUM_VARIANT=runs asks for it.
+    // the delta formulation, which was as fast as a version of this kernel with a window search per
+    // piece end (measured on C2: 0.97 vs 0.97 ms per step).  TSKB_SUM_VARIANT=runs also takes calls
+    // with 2-5 columns (one pass per column); any other value of the variable selects another kernel.
     const char *variant = getenv("TSKB_SUM_VARIANT");
     const bool forced = variant != nullptr && variant[0] == 'r';
     if (variant != nullptr && !forced) return false;
@@ -2100,7 +2093,6 @@ bool run_branch_runs(CallCtx &c, V *pval, V totals) {
     RunArgs b = make_run_args(c.sp->windows, W, c.d_windows, exact, P.range_left, P.range_right);
     if (!exact) return false;  // the kernel is arithmetic on uniform edges only
     if (b.Wl > RUNS_MAX_WL + 3) return false;
-    (void) forced;
     Arena &A = P.arena;
     ensure_piece_positions(P, c.s);
     // copies: reductions that meet at one address serialise in L2.  C2, summary + reduce per step
@@ -2114,7 +2106,6 @@ bool run_branch_runs(CallCtx &c, V *pval, V totals) {
     while (copies > 1 && (size_t) copies * block * sizeof(double) > (size_t(16) << 20)) copies >>= 1;
     double *bins = A.get<double>((size_t) copies * block);
     double *RC = A.get<double>(block);
-    b.clip = !(c.sp->windows[0] <= P.range_left && c.sp->windows[W] >= P.range_right);
     b.bins = bins; b.ncols = 1; b.copy_mask = copies - 1;
     launch_sweep<V>(c, pval);
     TSKB_CK(cudaEventRecord(P.ev[2], c.s));
