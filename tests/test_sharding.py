@@ -229,3 +229,46 @@ def test_restricted_tables_of_a_repeated_genome_sum_to_whole(wf_small):
                                      windows=np.linspace(0, base.sequence_length, W + 1), mode=mode,
                                      span_normalise=False)
         assert np.allclose(want.reshape(copies, W), one.reshape(1, W), rtol=1e-11, atol=0)
+
+
+def _fallback_worker(rank, world, port_no, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t = Tables.load(DATA).ensure_derived()
+    L = t.sequence_length
+    windows = np.linspace(0, L, 6)
+    sh = sharding.ShardedTreeSequence(t, windows, rank, world, engine_factory=OracleRangeEngine)
+    ex = sh.use_peer_exchange(64)   # no CUDA device here: every rank must agree on "no exchange"
+    s = t.samples
+    got = sh.stat("diversity", [s[:30], s[30:]], windows=windows, mode="branch")
+    q.put((rank, ex is None, sh.exchange_note, got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_falls_back_collectively_without_a_device():
+    """use_peer_exchange where the receive slab cannot be created (this container has no GPU): every
+    rank gets None after the same collectives (no rank left waiting in one) and the statistics go on
+    through the all_reduce."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a host without a CUDA device")
+    from oracle import port
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = 29500 + (os.getpid() + 1483) % 2000
+    procs = [ctx.Process(target=_fallback_worker, args=(r, 2, port_no, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    t = Tables.load(DATA).ensure_derived()
+    s = t.samples
+    want = port.Oracle(t).stat("diversity", [s[:30], s[30:]], windows=np.linspace(0, t.sequence_length, 6),
+                               mode="branch")
+    for rank, is_none, note, got in res:
+        assert is_none and note
+        assert np.allclose(got, want, rtol=1e-9)

@@ -227,7 +227,8 @@ class ShardedTreeSequence:
         except Exception as e:  # noqa: BLE001 -- reported, and agreed on below
             why = f"{type(e).__name__}: {e}"
         if self.world > 1:
-            ok = torch.tensor([0 if ex is None else 1], device=f"cuda:{self.device}")
+            dev = f"cuda:{self.device}" if torch.cuda.is_available() else "cpu"
+            ok = torch.tensor([0 if ex is None else 1], device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
             if int(ok.item()) == 0:
                 if ex is not None:
